@@ -1,0 +1,293 @@
+"""ctypes binding of include/carskit_b200.h (the C ABI a JNI shim would bind).
+
+Nothing here computes: it marshals numpy arrays into the plain-pointer ABI and raises when the CUDA
+library is missing or a call fails.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+ABI_VERSION = 1
+PMF, BIASEDMF, CAMF_C, CAMF_CI, CAMF_CU, FM = range(6)
+EXACT, FAST = 0, 1
+MODEL_NAMES = {"pmf": PMF, "biasedmf": BIASEDMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM}
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcarskit_b200.so")
+
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+
+class CarsDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("model", C.c_int32), ("mode", C.c_int32), ("device", C.c_int32),
+        ("num_users", C.c_int32), ("num_items", C.c_int32), ("num_conditions", C.c_int32),
+        ("num_contexts", C.c_int32), ("num_factors", C.c_int32), ("reserved0", C.c_int32),
+        ("nnz", C.c_int64),
+        ("u", _i32p), ("j", _i32p), ("ctx", _i32p), ("r", _f64p), ("ctx_ptr", _i32p), ("ctx_cond", _i32p),
+        ("global_mean", C.c_double),
+        ("reg_u", C.c_double), ("reg_i", C.c_double), ("reg_b", C.c_double), ("reg_c", C.c_double),
+        ("reg_lw", C.c_double), ("reg_lf", C.c_double),
+        ("rank", C.c_int32), ("world_size", C.c_int32),
+        ("stream", C.c_void_p),
+    ]
+
+
+class CarsModelArrays(C.Structure):
+    _fields_ = [(n, _f64p) for n in ("P", "Q", "user_bias", "item_bias", "cond_bias", "ic_bias", "uc_bias")]
+
+
+class CarsStats(C.Structure):
+    _fields_ = [
+        ("nnz", C.c_int64), ("num_levels", C.c_int64), ("max_level_size", C.c_int64),
+        ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("schedule_ms", C.c_double), ("last_epoch_ms", C.c_double),
+        ("grid_ctas", C.c_int32), ("block_threads", C.c_int32), ("sm_count", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+# every symbol include/carskit_b200.h declares
+EXPORTS = [
+    "cars_create", "cars_upload", "cars_epoch", "cars_epoch_begin", "cars_epoch_wait", "cars_download",
+    "cars_predict", "cars_eval_ratings", "cars_destroy", "cars_last_error", "cars_get_stats",
+    "cars_get_stream", "cars_version",
+]
+
+
+class CarsError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"carskit_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). carskit_b200 has no CPU fallback.")
+    lib = C.CDLL(p)
+    H = C.c_void_p
+    lib.cars_create.argtypes = [C.POINTER(CarsDesc), C.POINTER(H)]
+    lib.cars_create.restype = C.c_int
+    lib.cars_upload.argtypes = [H, C.POINTER(CarsModelArrays)]
+    lib.cars_upload.restype = C.c_int
+    lib.cars_download.argtypes = [H, C.POINTER(CarsModelArrays)]
+    lib.cars_download.restype = C.c_int
+    lib.cars_epoch.argtypes = [H, C.c_double, _f64p]
+    lib.cars_epoch.restype = C.c_int
+    lib.cars_epoch_begin.argtypes = [H, C.c_double]
+    lib.cars_epoch_begin.restype = C.c_int
+    lib.cars_epoch_wait.argtypes = [H, _f64p]
+    lib.cars_epoch_wait.restype = C.c_int
+    lib.cars_predict.argtypes = [H, C.c_int64, _i32p, _i32p, _i32p, C.c_int32, C.c_double, C.c_double, _f64p]
+    lib.cars_predict.restype = C.c_int
+    lib.cars_eval_ratings.argtypes = [H, C.c_int64, _i32p, _i32p, _i32p, _f64p, C.c_double, C.c_double, _f64p, _f64p]
+    lib.cars_eval_ratings.restype = C.c_int
+    lib.cars_destroy.argtypes = [H]
+    lib.cars_destroy.restype = None
+    lib.cars_last_error.argtypes = [H]
+    lib.cars_last_error.restype = C.c_char_p
+    lib.cars_get_stats.argtypes = [H, C.POINTER(CarsStats)]
+    lib.cars_get_stats.restype = C.c_int
+    lib.cars_get_stream.argtypes = [H]
+    lib.cars_get_stream.restype = C.c_void_p
+    lib.cars_version.argtypes = []
+    lib.cars_version.restype = C.c_char_p
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr_i32(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return a.ctypes.data_as(_i32p)
+
+
+def _ptr_f64(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(_f64p)
+
+
+def f32(x: float) -> float:
+    """Java `float` field widened to double: 1e-4f -> 9.999999747378752e-05 (IterativeRecommender.java:40)."""
+    return float(np.float32(x))
+
+
+@dataclass
+class TrainingSet:
+    """Flattened view of what buildModel() iterates: ratings in the reference's iteration order
+    (CRS order of trainMatrix, CAMF_CI.java:80) plus the context -> conditions table
+    (rateDao.getContextConditionsList(), DataDAO.java:1035) in CSR form."""
+    num_users: int
+    num_items: int
+    u: np.ndarray
+    j: np.ndarray
+    r: np.ndarray
+    ctx: Optional[np.ndarray] = None
+    num_conditions: int = 0
+    num_contexts: int = 0
+    ctx_ptr: Optional[np.ndarray] = None
+    ctx_cond: Optional[np.ndarray] = None
+    global_mean: float = 0.0
+
+    def __post_init__(self):
+        self.u = np.ascontiguousarray(self.u, dtype=np.int32)
+        self.j = np.ascontiguousarray(self.j, dtype=np.int32)
+        self.r = np.ascontiguousarray(self.r, dtype=np.float64)
+        if self.ctx is not None:
+            self.ctx = np.ascontiguousarray(self.ctx, dtype=np.int32)
+            self.ctx_ptr = np.ascontiguousarray(self.ctx_ptr, dtype=np.int32)
+            self.ctx_cond = np.ascontiguousarray(self.ctx_cond, dtype=np.int32)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.u.shape[0])
+
+
+def make_desc(ts: TrainingSet, model: int, num_factors: int, *, mode: int = EXACT, device: int = 0,
+              reg_u: float = 0.0, reg_i: float = 0.0, reg_b: float = 0.0, reg_c: float = 0.0,
+              reg_lw: float = 0.0, reg_lf: float = 0.0, rank: int = 0, world_size: int = 1,
+              stream: int = 0) -> CarsDesc:
+    """Fill a cars_desc.  The reg_* values must already be float-widened (use f32())."""
+    d = CarsDesc()
+    d.abi_version = ABI_VERSION
+    d.model, d.mode, d.device = model, mode, device
+    d.num_users, d.num_items = ts.num_users, ts.num_items
+    d.num_conditions, d.num_contexts = ts.num_conditions, ts.num_contexts
+    d.num_factors = num_factors
+    d.nnz = ts.nnz
+    d.u, d.j, d.r = _ptr_i32(ts.u), _ptr_i32(ts.j), _ptr_f64(ts.r)
+    use_ctx = model in (CAMF_C, CAMF_CI, CAMF_CU, FM) and ts.ctx is not None
+    d.ctx = _ptr_i32(ts.ctx) if use_ctx else None
+    d.ctx_ptr = _ptr_i32(ts.ctx_ptr) if use_ctx else None
+    d.ctx_cond = _ptr_i32(ts.ctx_cond) if use_ctx else None
+    d.global_mean = ts.global_mean
+    d.reg_u, d.reg_i, d.reg_b, d.reg_c, d.reg_lw, d.reg_lf = reg_u, reg_i, reg_b, reg_c, reg_lw, reg_lf
+    d.rank, d.world_size = rank, world_size
+    d.stream = stream or None
+    return d
+
+
+MODEL_MEMBERS = {
+    PMF: ("P", "Q"),
+    BIASEDMF: ("P", "Q", "user_bias", "item_bias"),
+    CAMF_C: ("P", "Q", "user_bias", "item_bias", "cond_bias"),
+    CAMF_CI: ("P", "Q", "user_bias", "ic_bias"),
+    CAMF_CU: ("P", "Q", "item_bias", "uc_bias"),
+}
+
+
+def member_shapes(model: int, num_users: int, num_items: int, num_conditions: int, F: int):
+    all_shapes = {
+        "P": (num_users, F), "Q": (num_items, F), "user_bias": (num_users,), "item_bias": (num_items,),
+        "cond_bias": (num_conditions,), "ic_bias": (num_items, num_conditions),
+        "uc_bias": (num_users, num_conditions),
+    }
+    return {k: all_shapes[k] for k in MODEL_MEMBERS[model]}
+
+
+def make_arrays(arrs: dict) -> CarsModelArrays:
+    a = CarsModelArrays()
+    for name, _ in CarsModelArrays._fields_:
+        v = arrs.get(name)
+        setattr(a, name, _ptr_f64(v) if v is not None else None)
+    return a
+
+
+class Engine:
+    """Thin RAII wrapper: cars_create .. cars_destroy."""
+
+    def __init__(self, desc: CarsDesc, keepalive=None):
+        self.lib = load_library()
+        self._keep = keepalive
+        self.h = C.c_void_p()
+        rc = self.lib.cars_create(C.byref(desc), C.byref(self.h))
+        if rc != 0:
+            raise CarsError(rc, self.lib.cars_last_error(None).decode())
+        self.model = desc.model
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise CarsError(rc, self.lib.cars_last_error(self.h).decode())
+
+    def upload(self, arrs: dict):
+        a = make_arrays(arrs)
+        self._check(self.lib.cars_upload(self.h, C.byref(a)))
+
+    def download(self, arrs: dict):
+        a = make_arrays(arrs)
+        self._check(self.lib.cars_download(self.h, C.byref(a)))
+
+    def epoch(self, lrate: float) -> float:
+        loss = C.c_double()
+        self._check(self.lib.cars_epoch(self.h, lrate, C.byref(loss)))
+        return loss.value
+
+    def epoch_begin(self, lrate: float):
+        self._check(self.lib.cars_epoch_begin(self.h, lrate))
+
+    def epoch_wait(self) -> float:
+        loss = C.c_double()
+        self._check(self.lib.cars_epoch_wait(self.h, C.byref(loss)))
+        return loss.value
+
+    def predict(self, u, j, ctx=None, bound=False, min_rate=0.0, max_rate=0.0) -> np.ndarray:
+        u = np.ascontiguousarray(u, dtype=np.int32)
+        j = np.ascontiguousarray(j, dtype=np.int32)
+        ctx = None if ctx is None else np.ascontiguousarray(ctx, dtype=np.int32)
+        out = np.empty(u.shape[0], dtype=np.float64)
+        self._check(self.lib.cars_predict(self.h, u.shape[0], _ptr_i32(u), _ptr_i32(j), _ptr_i32(ctx),
+                                          1 if bound else 0, min_rate, max_rate, _ptr_f64(out)))
+        return out
+
+    def eval_ratings(self, u, j, ctx, r, min_rate, max_rate):
+        u = np.ascontiguousarray(u, dtype=np.int32)
+        j = np.ascontiguousarray(j, dtype=np.int32)
+        ctx = None if ctx is None else np.ascontiguousarray(ctx, dtype=np.int32)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        sa, ss = C.c_double(), C.c_double()
+        self._check(self.lib.cars_eval_ratings(self.h, u.shape[0], _ptr_i32(u), _ptr_i32(j), _ptr_i32(ctx),
+                                               _ptr_f64(r), min_rate, max_rate, C.byref(sa), C.byref(ss)))
+        return sa.value, ss.value
+
+    def stats(self) -> CarsStats:
+        s = CarsStats()
+        self._check(self.lib.cars_get_stats(self.h, C.byref(s)))
+        return s
+
+    def stream(self) -> int:
+        return int(self.lib.cars_get_stream(self.h) or 0)
+
+    def close(self):
+        if self.h:
+            self.lib.cars_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,598 @@
+// engine.cu -- the C ABI of include/carskit_b200.h on top of the sm_100a kernels.
+//
+// What lives here: handle lifetime, host<->device marshalling of the flattened Java containers,
+// the dependency schedule (wavefront levels) and kernel dispatch.  No CPU implementation of the
+// update exists in this library: without a CUDA sm_100 device cars_create() fails.
+#include "../../include/carskit_b200.h"
+#include "schedule.cuh"
+#include "sgd_kernels.cuh"
+
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace cars;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_create_error = "";
+
+struct cars_handle {
+  cars_desc d;  // scalars only; pointer members are nulled after create
+  std::string err;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev_beg = nullptr, ev_end = nullptr;
+
+  // model
+  DeviceModel m{};
+  int Dmax = 0;
+  int32_t* d_ctx_tab = nullptr;
+  bool uploaded = false;
+
+  // ratings in schedule order
+  int64_t nnz = 0;
+  int32_t *d_u = nullptr, *d_j = nullptr, *d_ctx = nullptr;
+  double* d_r = nullptr;
+  int64_t* d_level_start = nullptr;
+  int64_t num_levels = 0, max_level_size = 0;
+  bool serial = false;  // CAMF_C exact: reference order, one warp
+
+  // kernel plumbing
+  unsigned* d_barrier = nullptr;
+  double* d_partial = nullptr;
+  double* d_loss = nullptr;
+  double* h_loss = nullptr;  // pinned
+  int grid = 0, block = 0, sm_count = 0;
+  size_t smem = 0;
+  bool epoch_pending = false;
+
+  cars_stats st{};
+};
+
+static int fail(cars_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h)
+    h->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(h, _e == cudaErrorMemoryAllocation ? CARS_E_OOM : CARS_E_CUDA, "%s failed: %s",  \
+                  #expr, cudaGetErrorString(_e));                                                  \
+  } while (0)
+
+template <typename T>
+static cudaError_t dev_alloc(T** p, size_t n) {
+  return cudaMalloc(reinterpret_cast<void**>(p), (n ? n : 1) * sizeof(T));
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch: model x (lanes per rating, chunks per lane) chosen from num_factors
+// ------------------------------------------------------------------------------------------------
+static constexpr int kThreads = 512;
+
+struct LaunchPlan {
+  const void* fn = nullptr;
+  int lpr = 0, v = 0;
+};
+
+template <int MODEL, bool ATOMIC>
+static LaunchPlan pick_wavefront(int Fp) {
+  LaunchPlan p;
+  if (Fp <= 16) {
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 1, ATOMIC, kThreads>; p.lpr = 8; p.v = 1;
+  } else if (Fp <= 32) {
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 2, ATOMIC, kThreads>; p.lpr = 8; p.v = 2;
+  } else if (Fp <= 64) {
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 4, ATOMIC, kThreads>; p.lpr = 8; p.v = 4;
+  } else if (Fp <= 128) {
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 16, 4, ATOMIC, kThreads>; p.lpr = 16; p.v = 4;
+  } else if (Fp <= 256) {
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 32, 4, ATOMIC, kThreads>; p.lpr = 32; p.v = 4;
+  } else if (Fp <= 512) {
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 32, 8, ATOMIC, kThreads>; p.lpr = 32; p.v = 8;
+  }
+  return p;
+}
+
+static LaunchPlan pick_plan(int model, int mode, int Fp) {
+  switch (model) {
+    case CARS_PMF: return pick_wavefront<M_PMF, false>(Fp);
+    case CARS_BIASEDMF: return pick_wavefront<M_BIASEDMF, false>(Fp);
+    case CARS_CAMF_C: return mode == CARS_FAST ? pick_wavefront<M_CAMF_C, true>(Fp) : LaunchPlan{};
+    case CARS_CAMF_CI: return pick_wavefront<M_CAMF_CI, false>(Fp);
+    case CARS_CAMF_CU: return pick_wavefront<M_CAMF_CU, false>(Fp);
+  }
+  return LaunchPlan{};
+}
+
+template <int MODEL>
+static const void* pick_serial_m(int Fp) {
+  if (Fp <= 64) return (const void*)sgd_serial_kernel<MODEL, 1>;
+  if (Fp <= 128) return (const void*)sgd_serial_kernel<MODEL, 2>;
+  if (Fp <= 256) return (const void*)sgd_serial_kernel<MODEL, 4>;
+  if (Fp <= 512) return (const void*)sgd_serial_kernel<MODEL, 8>;
+  return nullptr;
+}
+static const void* pick_serial(int model, int Fp) {
+  switch (model) {
+    case CARS_PMF: return pick_serial_m<M_PMF>(Fp);
+    case CARS_BIASEDMF: return pick_serial_m<M_BIASEDMF>(Fp);
+    case CARS_CAMF_C: return pick_serial_m<M_CAMF_C>(Fp);
+    case CARS_CAMF_CI: return pick_serial_m<M_CAMF_CI>(Fp);
+    case CARS_CAMF_CU: return pick_serial_m<M_CAMF_CU>(Fp);
+  }
+  return nullptr;
+}
+
+static bool model_has_ctx(int model) {
+  return model == CARS_CAMF_C || model == CARS_CAMF_CI || model == CARS_CAMF_CU;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cars_create
+// ------------------------------------------------------------------------------------------------
+static int validate(const cars_desc* d) {
+  if (!d) return fail(nullptr, CARS_E_INVALID, "desc is NULL");
+  if (d->abi_version != CARS_ABI_VERSION)
+    return fail(nullptr, CARS_E_INVALID, "abi_version %d != %d", d->abi_version, CARS_ABI_VERSION);
+  if (d->model < CARS_PMF || d->model > CARS_FM) return fail(nullptr, CARS_E_INVALID, "unknown model %d", d->model);
+  if (d->model == CARS_FM)
+    return fail(nullptr, CARS_E_UNSUPPORTED, "FM (ALS, FM.java:115-220) is not built yet");
+  if (d->mode != CARS_EXACT && d->mode != CARS_FAST) return fail(nullptr, CARS_E_INVALID, "unknown mode %d", d->mode);
+  if (d->num_users <= 0 || d->num_items <= 0) return fail(nullptr, CARS_E_INVALID, "num_users/num_items must be > 0");
+  if (d->num_factors <= 0 || d->num_factors > 512)
+    return fail(nullptr, CARS_E_UNSUPPORTED, "num_factors %d outside 1..512", d->num_factors);
+  if (d->nnz < 0) return fail(nullptr, CARS_E_INVALID, "nnz < 0");
+  if (d->nnz > 0 && (!d->u || !d->j || !d->r)) return fail(nullptr, CARS_E_INVALID, "u/j/r must not be NULL");
+  if (model_has_ctx(d->model)) {
+    if (d->num_conditions <= 0 || d->num_contexts <= 0)
+      return fail(nullptr, CARS_E_INVALID, "context model needs num_conditions/num_contexts > 0");
+    if (!d->ctx_ptr || !d->ctx_cond || (d->nnz > 0 && !d->ctx))
+      return fail(nullptr, CARS_E_INVALID, "context model needs ctx, ctx_ptr, ctx_cond");
+  }
+  return CARS_OK;
+}
+
+extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
+  if (!out) return fail(nullptr, CARS_E_INVALID, "out is NULL");
+  *out = nullptr;
+  int rc = validate(desc);
+  if (rc) return rc;
+
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, CARS_E_NO_DEVICE, "no CUDA device (%s); this engine has no CPU path",
+                ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  if (desc->device < 0 || desc->device >= ndev)
+    return fail(nullptr, CARS_E_INVALID, "device %d out of range (have %d)", desc->device, ndev);
+  cudaDeviceProp prop;
+  CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, desc->device));
+  if (prop.major != 10)
+    return fail(nullptr, CARS_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                desc->device, prop.major, prop.minor);
+
+  cars_handle* h = new (std::nothrow) cars_handle();
+  if (!h) return fail(nullptr, CARS_E_OOM, "host allocation failed");
+  // from here on failures must free h
+  auto bail = [&](int code) {
+    g_create_error = h->err;
+    cars_destroy(h);
+    return code;
+  };
+#define CUDA_TRY_H(expr)                                                                                \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      fail(h, CARS_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));                             \
+      return bail(_e == cudaErrorMemoryAllocation ? CARS_E_OOM : CARS_E_CUDA);                          \
+    }                                                                                                   \
+  } while (0)
+
+  h->d = *desc;
+  h->device = desc->device;
+  h->sm_count = prop.multiProcessorCount;
+  CUDA_TRY_H(cudaSetDevice(h->device));
+  if (desc->stream) {
+    h->stream = (cudaStream_t)desc->stream;
+  } else {
+    CUDA_TRY_H(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  CUDA_TRY_H(cudaEventCreate(&h->ev_beg));
+  CUDA_TRY_H(cudaEventCreate(&h->ev_end));
+
+  const int F = desc->num_factors;
+  const int Fp = (F + 1) & ~1;
+  const bool has_ctx = model_has_ctx(desc->model);
+
+  // ---- context -> condition table (dense, -1 padded) ------------------------------------------------
+  int Dmax = 0;
+  std::vector<int32_t> ctx_tab;
+  if (has_ctx) {
+    for (int c = 0; c < desc->num_contexts; c++) {
+      int len = desc->ctx_ptr[c + 1] - desc->ctx_ptr[c];
+      if (len < 0) { fail(h, CARS_E_INVALID, "ctx_ptr not monotone at %d", c); return bail(CARS_E_INVALID); }
+      if (len > Dmax) Dmax = len;
+    }
+    if (Dmax == 0) Dmax = 1;
+    ctx_tab.assign((size_t)desc->num_contexts * Dmax, -1);
+    for (int c = 0; c < desc->num_contexts; c++) {
+      int k0 = desc->ctx_ptr[c], k1 = desc->ctx_ptr[c + 1];
+      for (int k = k0; k < k1; k++) {
+        int cond = desc->ctx_cond[k];
+        if (cond < 0 || cond >= desc->num_conditions) {
+          fail(h, CARS_E_INVALID, "condition id %d of context %d out of range", cond, c);
+          return bail(CARS_E_INVALID);
+        }
+        for (int k2 = k0; k2 < k; k2++)
+          if (desc->ctx_cond[k2] == cond) {
+            fail(h, CARS_E_UNSUPPORTED, "context %d lists condition %d twice", c, cond);
+            return bail(CARS_E_UNSUPPORTED);
+          }
+        ctx_tab[(size_t)c * Dmax + (k - k0)] = cond;
+      }
+    }
+    CUDA_TRY_H(dev_alloc(&h->d_ctx_tab, ctx_tab.size()));
+    CUDA_TRY_H(cudaMemcpyAsync(h->d_ctx_tab, ctx_tab.data(), ctx_tab.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    h->st.h2d_bytes += (int64_t)ctx_tab.size() * 4;
+  }
+  h->Dmax = Dmax;
+
+  // ---- range checks on the rating arrays -------------------------------------------------------------
+  const int64_t nnz = desc->nnz;
+  for (int64_t n = 0; n < nnz; n++) {
+    if ((unsigned)desc->u[n] >= (unsigned)desc->num_users || (unsigned)desc->j[n] >= (unsigned)desc->num_items ||
+        (has_ctx && (unsigned)desc->ctx[n] >= (unsigned)desc->num_contexts)) {
+      fail(h, CARS_E_INVALID, "rating %lld has an id out of range (u=%d j=%d ctx=%d)", (long long)n, desc->u[n],
+           desc->j[n], has_ctx ? desc->ctx[n] : -1);
+      return bail(CARS_E_INVALID);
+    }
+  }
+
+  // ---- schedule ----------------------------------------------------------------------------------------
+  auto t0 = std::chrono::steady_clock::now();
+  h->serial = (desc->model == CARS_CAMF_C && desc->mode == CARS_EXACT);
+  h->nnz = nnz;
+  std::vector<int64_t> level_start;
+  HostSchedule sched;
+  const int32_t* su = desc->u;
+  const int32_t* sj = desc->j;
+  const int32_t* sc = desc->ctx;
+  const double* sr = desc->r;
+  if (!h->serial) {
+    if (!build_wavefront_schedule(desc->num_users, desc->num_items, nnz, desc->u, desc->j, has_ctx ? desc->ctx : nullptr,
+                                  desc->r, &sched)) {
+      fail(h, CARS_E_OOM, "host allocation failed while building the schedule");
+      return bail(CARS_E_OOM);
+    }
+    su = sched.u.data(); sj = sched.j.data(); sc = has_ctx ? sched.ctx.data() : nullptr; sr = sched.r.data();
+    h->num_levels = (int64_t)sched.level_start.size() - 1;
+    h->max_level_size = sched.max_level_size;
+  } else {
+    h->num_levels = nnz;  // every rating is its own level
+    h->max_level_size = nnz ? 1 : 0;
+  }
+  h->st.schedule_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+
+  CUDA_TRY_H(dev_alloc(&h->d_u, nnz));
+  CUDA_TRY_H(dev_alloc(&h->d_j, nnz));
+  CUDA_TRY_H(dev_alloc(&h->d_r, nnz));
+  if (has_ctx) CUDA_TRY_H(dev_alloc(&h->d_ctx, nnz));
+  if (nnz) {
+    CUDA_TRY_H(cudaMemcpyAsync(h->d_u, su, nnz * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY_H(cudaMemcpyAsync(h->d_j, sj, nnz * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY_H(cudaMemcpyAsync(h->d_r, sr, nnz * 8, cudaMemcpyHostToDevice, h->stream));
+    if (has_ctx) CUDA_TRY_H(cudaMemcpyAsync(h->d_ctx, sc, nnz * 4, cudaMemcpyHostToDevice, h->stream));
+    h->st.h2d_bytes += nnz * (has_ctx ? 20 : 16);
+  }
+  if (!h->serial) {
+    CUDA_TRY_H(dev_alloc(&h->d_level_start, sched.level_start.size()));
+    CUDA_TRY_H(cudaMemcpyAsync(h->d_level_start, sched.level_start.data(), sched.level_start.size() * 8,
+                               cudaMemcpyHostToDevice, h->stream));
+    h->st.h2d_bytes += (int64_t)sched.level_start.size() * 8;
+  }
+
+  // ---- model storage ----------------------------------------------------------------------------------
+  DeviceModel& m = h->m;
+  m.F = F; m.Fp = Fp; m.C = desc->num_conditions; m.Dmax = Dmax;
+  m.global_mean = desc->global_mean;
+  m.reg_u = desc->reg_u; m.reg_i = desc->reg_i; m.reg_b = desc->reg_b; m.reg_c = desc->reg_c;
+  m.ctx_tab = h->d_ctx_tab;
+  const int model = desc->model;
+  const size_t U = desc->num_users, I = desc->num_items, C = desc->num_conditions;
+  CUDA_TRY_H(dev_alloc(&m.P, U * Fp));
+  CUDA_TRY_H(dev_alloc(&m.Q, I * Fp));
+  if (model == CARS_BIASEDMF || model == CARS_CAMF_C || model == CARS_CAMF_CI) CUDA_TRY_H(dev_alloc(&m.user_bias, U));
+  if (model == CARS_BIASEDMF || model == CARS_CAMF_C || model == CARS_CAMF_CU) CUDA_TRY_H(dev_alloc(&m.item_bias, I));
+  if (model == CARS_CAMF_C) CUDA_TRY_H(dev_alloc(&m.cond_bias, C));
+  if (model == CARS_CAMF_CI) CUDA_TRY_H(dev_alloc(&m.ic_bias, I * C));
+  if (model == CARS_CAMF_CU) CUDA_TRY_H(dev_alloc(&m.uc_bias, U * C));
+
+  // ---- launch geometry -----------------------------------------------------------------------------------
+  if (h->serial) {
+    h->grid = 1; h->block = 32;
+    h->smem = (size_t)(Fp + 2) * 8;
+  } else {
+    LaunchPlan plan = pick_plan(model, desc->mode, Fp);
+    if (!plan.fn) { fail(h, CARS_E_UNSUPPORTED, "no kernel for model %d mode %d F %d", model, desc->mode, F); return bail(CARS_E_UNSUPPORTED); }
+    const int G = 32 / plan.lpr;
+    h->block = kThreads;
+    h->smem = (size_t)(kThreads / 32) * G * (Fp + 2) * 8;
+    CUDA_TRY_H(cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    int per_sm = 0;
+    CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, kThreads, h->smem));
+    if (per_sm < 1) { fail(h, CARS_E_CUDA, "SGD kernel does not fit on an SM (smem %zu)", h->smem); return bail(CARS_E_CUDA); }
+    h->grid = h->sm_count * per_sm;
+  }
+  CUDA_TRY_H(dev_alloc(&h->d_barrier, 1));
+  CUDA_TRY_H(dev_alloc(&h->d_partial, (size_t)h->grid));
+  CUDA_TRY_H(dev_alloc(&h->d_loss, 1));
+  CUDA_TRY_H(cudaMallocHost((void**)&h->h_loss, sizeof(double)));
+  CUDA_TRY_H(cudaStreamSynchronize(h->stream));  // host staging vectors die at return
+
+  h->st.nnz = nnz;
+  h->st.num_levels = h->num_levels;
+  h->st.max_level_size = h->max_level_size;
+  h->st.grid_ctas = h->grid;
+  h->st.block_threads = h->block;
+  h->st.sm_count = h->sm_count;
+  // the handle must not keep caller pointers
+  h->d.u = h->d.j = h->d.ctx = nullptr; h->d.r = nullptr; h->d.ctx_ptr = h->d.ctx_cond = nullptr; h->d.stream = nullptr;
+  *out = h;
+  return CARS_OK;
+#undef CUDA_TRY_H
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload / download
+// ------------------------------------------------------------------------------------------------
+static int copy_rows(cars_handle* h, bool to_device, double* dev, double* host, size_t rows, int F, int Fp) {
+  if (rows == 0) return CARS_OK;
+  if (to_device) {
+    if (F != Fp) CUDA_TRY(h, cudaMemsetAsync(dev, 0, rows * Fp * 8, h->stream));
+    CUDA_TRY(h, cudaMemcpy2DAsync(dev, (size_t)Fp * 8, host, (size_t)F * 8, (size_t)F * 8, rows, cudaMemcpyHostToDevice, h->stream));
+    h->st.h2d_bytes += (int64_t)rows * F * 8;
+  } else {
+    CUDA_TRY(h, cudaMemcpy2DAsync(host, (size_t)F * 8, dev, (size_t)Fp * 8, (size_t)F * 8, rows, cudaMemcpyDeviceToHost, h->stream));
+    h->st.d2h_bytes += (int64_t)rows * F * 8;
+  }
+  return CARS_OK;
+}
+
+static int copy_vec(cars_handle* h, bool to_device, double* dev, double* host, size_t n) {
+  if (n == 0) return CARS_OK;
+  if (to_device) {
+    CUDA_TRY(h, cudaMemcpyAsync(dev, host, n * 8, cudaMemcpyHostToDevice, h->stream));
+    h->st.h2d_bytes += (int64_t)n * 8;
+  } else {
+    CUDA_TRY(h, cudaMemcpyAsync(host, dev, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    h->st.d2h_bytes += (int64_t)n * 8;
+  }
+  return CARS_OK;
+}
+
+static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device) {
+  if (!h) return CARS_E_INVALID;
+  if (!a) return fail(h, CARS_E_INVALID, "arrays is NULL");
+  if (h->epoch_pending) return fail(h, CARS_E_STATE, "an epoch is pending; call cars_epoch_wait first");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const DeviceModel& m = h->m;
+  const size_t U = h->d.num_users, I = h->d.num_items, C = h->d.num_conditions;
+  struct Item { double* dev; double* host; const char* name; };
+  const Item need[] = {{m.P, a->P, "P"}, {m.Q, a->Q, "Q"}, {m.user_bias, a->user_bias, "user_bias"},
+                       {m.item_bias, a->item_bias, "item_bias"}, {m.cond_bias, a->cond_bias, "cond_bias"},
+                       {m.ic_bias, a->ic_bias, "ic_bias"}, {m.uc_bias, a->uc_bias, "uc_bias"}};
+  for (const Item& it : need)
+    if (it.dev && !it.host) return fail(h, CARS_E_INVALID, "model array %s is required for this model but NULL", it.name);
+  int rc;
+  if ((rc = copy_rows(h, to_device, m.P, a->P, U, m.F, m.Fp))) return rc;
+  if ((rc = copy_rows(h, to_device, m.Q, a->Q, I, m.F, m.Fp))) return rc;
+  if (m.user_bias && (rc = copy_vec(h, to_device, m.user_bias, a->user_bias, U))) return rc;
+  if (m.item_bias && (rc = copy_vec(h, to_device, m.item_bias, a->item_bias, I))) return rc;
+  if (m.cond_bias && (rc = copy_vec(h, to_device, m.cond_bias, a->cond_bias, C))) return rc;
+  if (m.ic_bias && (rc = copy_vec(h, to_device, m.ic_bias, a->ic_bias, I * C))) return rc;
+  if (m.uc_bias && (rc = copy_vec(h, to_device, m.uc_bias, a->uc_bias, U * C))) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return CARS_OK;
+}
+
+extern "C" int cars_upload(cars_handle* h, const cars_model_arrays* host) {
+  int rc = transfer(h, host, true);
+  if (rc == CARS_OK) h->uploaded = true;
+  return rc;
+}
+
+extern "C" int cars_download(cars_handle* h, const cars_model_arrays* host) {
+  if (h && !h->uploaded) return fail(h, CARS_E_STATE, "cars_download before cars_upload");
+  return transfer(h, host, false);
+}
+
+// ------------------------------------------------------------------------------------------------
+// epoch
+// ------------------------------------------------------------------------------------------------
+extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
+  if (!h) return CARS_E_INVALID;
+  if (!h->uploaded) return fail(h, CARS_E_STATE, "cars_epoch before cars_upload");
+  if (h->epoch_pending) return fail(h, CARS_E_STATE, "previous epoch not collected; call cars_epoch_wait");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  RatingStream s;
+  s.u = h->d_u; s.j = h->d_j; s.ctx = h->d_ctx; s.r = h->d_r;
+  s.level_start = h->d_level_start;
+  s.num_levels = (int32_t)h->num_levels;
+  DeviceModel m = h->m;
+  CUDA_TRY(h, cudaEventRecord(h->ev_beg, h->stream));
+  if (h->serial) {
+    const void* fn = pick_serial(h->d.model, m.Fp);
+    int64_t nnz = h->nnz;
+    void* args[] = {&m, &s, &nnz, &lrate, &h->d_partial};
+    CUDA_TRY(h, cudaLaunchKernel(fn, dim3(1), dim3(32), args, h->smem, h->stream));
+    h->st.kernel_launches += 1;
+  } else {
+    LaunchPlan plan = pick_plan(h->d.model, h->d.mode, m.Fp);
+    CUDA_TRY(h, cudaMemsetAsync(h->d_barrier, 0, sizeof(unsigned), h->stream));
+    void* args[] = {&m, &s, &lrate, &h->d_barrier, &h->d_partial};
+    CUDA_TRY(h, cudaLaunchCooperativeKernel(plan.fn, dim3(h->grid), dim3(h->block), args, h->smem, h->stream));
+    h->st.kernel_launches += 1;
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev_end, h->stream));
+  loss_finalize_kernel<<<1, 32, 0, h->stream>>>(h->d_partial, h->grid, h->d_loss);
+  CUDA_TRY(h, cudaGetLastError());
+  h->st.kernel_launches += 1;
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  h->st.d2h_bytes += 8;
+  h->epoch_pending = true;
+  return CARS_OK;
+}
+
+extern "C" int cars_epoch_wait(cars_handle* h, double* loss_out) {
+  if (!h) return CARS_E_INVALID;
+  if (!h->epoch_pending) return fail(h, CARS_E_STATE, "no epoch pending");
+  h->epoch_pending = false;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev_beg, h->ev_end));
+  h->st.last_epoch_ms = ms;
+  if (loss_out) *loss_out = *h->h_loss;
+  return CARS_OK;
+}
+
+extern "C" int cars_epoch(cars_handle* h, double lrate, double* loss_out) {
+  int rc = cars_epoch_begin(h, lrate);
+  if (rc) return rc;
+  return cars_epoch_wait(h, loss_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// predict / evalRatings
+// ------------------------------------------------------------------------------------------------
+static int predict_device(cars_handle* h, int64_t n, const int32_t* u, const int32_t* j, const int32_t* ctx,
+                          int bound, double lo, double hi, double* d_out, int32_t** du_, int32_t** dj_, int32_t** dc_) {
+  const bool has_ctx = model_has_ctx(h->d.model);
+  if (has_ctx && !ctx) return fail(h, CARS_E_INVALID, "ctx is required for this model");
+  for (int64_t i = 0; i < n; i++)
+    if ((unsigned)u[i] >= (unsigned)h->d.num_users || (unsigned)j[i] >= (unsigned)h->d.num_items ||
+        (has_ctx && (unsigned)ctx[i] >= (unsigned)h->d.num_contexts))
+      return fail(h, CARS_E_INVALID, "query %lld has an id out of range", (long long)i);
+  CUDA_TRY(h, dev_alloc(du_, (size_t)n));
+  CUDA_TRY(h, dev_alloc(dj_, (size_t)n));
+  if (has_ctx) CUDA_TRY(h, dev_alloc(dc_, (size_t)n));
+  CUDA_TRY(h, cudaMemcpyAsync(*du_, u, n * 4, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(*dj_, j, n * 4, cudaMemcpyHostToDevice, h->stream));
+  if (has_ctx) CUDA_TRY(h, cudaMemcpyAsync(*dc_, ctx, n * 4, cudaMemcpyHostToDevice, h->stream));
+  h->st.h2d_bytes += n * (has_ctx ? 12 : 8);
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  DeviceModel m = h->m;
+  switch (h->d.model) {
+    case CARS_PMF: predict_kernel<M_PMF><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
+    case CARS_BIASEDMF: predict_kernel<M_BIASEDMF><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
+    case CARS_CAMF_C: predict_kernel<M_CAMF_C><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
+    case CARS_CAMF_CI: predict_kernel<M_CAMF_CI><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
+    case CARS_CAMF_CU: predict_kernel<M_CAMF_CU><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
+    default: return fail(h, CARS_E_UNSUPPORTED, "predict: model %d", h->d.model);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  h->st.kernel_launches += 1;
+  return CARS_OK;
+}
+
+extern "C" int cars_predict(cars_handle* h, int64_t n, const int32_t* u, const int32_t* j, const int32_t* ctx,
+                            int32_t bound, double min_rate, double max_rate, double* out) {
+  if (!h) return CARS_E_INVALID;
+  if (!h->uploaded) return fail(h, CARS_E_STATE, "cars_predict before cars_upload");
+  if (h->epoch_pending) return fail(h, CARS_E_STATE, "an epoch is pending; call cars_epoch_wait first");
+  if (n < 0 || (n > 0 && (!u || !j || !out))) return fail(h, CARS_E_INVALID, "bad predict arguments");
+  if (n == 0) return CARS_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int32_t *du = nullptr, *dj = nullptr, *dc = nullptr;
+  double* d_out = nullptr;
+  int rc = CARS_OK;
+  cudaError_t e = dev_alloc(&d_out, (size_t)n);
+  if (e != cudaSuccess) rc = fail(h, CARS_E_OOM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  if (!rc) rc = predict_device(h, n, u, j, ctx, bound, min_rate, max_rate, d_out, &du, &dj, &dc);
+  if (!rc) {
+    e = cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = fail(h, CARS_E_CUDA, "predict copy-back failed: %s", cudaGetErrorString(e));
+    h->st.d2h_bytes += n * 8;
+  } else {
+    cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(du); cudaFree(dj); cudaFree(dc); cudaFree(d_out);
+  return rc;
+}
+
+extern "C" int cars_eval_ratings(cars_handle* h, int64_t n, const int32_t* u, const int32_t* j, const int32_t* ctx,
+                                 const double* r, double min_rate, double max_rate, double* sum_abs_err,
+                                 double* sum_sq_err) {
+  if (!h) return CARS_E_INVALID;
+  if (n < 0 || (n > 0 && !r) || !sum_abs_err || !sum_sq_err) return fail(h, CARS_E_INVALID, "bad eval arguments");
+  std::vector<double> pred;
+  try { pred.resize((size_t)n); } catch (...) { return fail(h, CARS_E_OOM, "host allocation failed"); }
+  int rc = cars_predict(h, n, u, j, ctx, 1, min_rate, max_rate, pred.data());
+  if (rc) return rc;
+  // Java accumulates sequentially in test-matrix order (Recommender.java:518-545); keep that order so
+  // MAE/RMSE are bit-identical given identical predictions.
+  double sa = 0.0, ss = 0.0;
+  for (int64_t i = 0; i < n; i++) {
+    if (std::isnan(pred[i])) continue;
+    double err = std::fabs(r[i] - pred[i]);
+    sa += err;
+    ss += err * err;
+  }
+  *sum_abs_err = sa;
+  *sum_sq_err = ss;
+  return CARS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// misc
+// ------------------------------------------------------------------------------------------------
+extern "C" void cars_destroy(cars_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_ctx_tab);
+  cudaFree(h->d_u); cudaFree(h->d_j); cudaFree(h->d_ctx); cudaFree(h->d_r); cudaFree(h->d_level_start);
+  cudaFree(h->m.P); cudaFree(h->m.Q); cudaFree(h->m.user_bias); cudaFree(h->m.item_bias);
+  cudaFree(h->m.cond_bias); cudaFree(h->m.ic_bias); cudaFree(h->m.uc_bias);
+  cudaFree(h->d_barrier); cudaFree(h->d_partial); cudaFree(h->d_loss);
+  if (h->h_loss) cudaFreeHost(h->h_loss);
+  if (h->ev_beg) cudaEventDestroy(h->ev_beg);
+  if (h->ev_end) cudaEventDestroy(h->ev_end);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" const char* cars_last_error(const cars_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int cars_get_stats(const cars_handle* h, cars_stats* out) {
+  if (!h || !out) return CARS_E_INVALID;
+  *out = h->st;
+  return CARS_OK;
+}
+
+extern "C" void* cars_get_stream(const cars_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+extern "C" const char* cars_version(void) { return "carskit_b200 abi 1, sm_100a, fp64 serial-equivalent SGD"; }

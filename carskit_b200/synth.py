@@ -1,0 +1,86 @@
+"""Synthetic (users, items, contexts, nnz) training sets shaped like BASELINE.json's configs.
+
+Harness code (tests + bench): builds the flattened arrays a Java buildModel() would hand to the C ABI,
+in the reference's iteration order: user-item pair id ascending, then context id ascending
+(CAMF_CI.java:80; pair ids as DataDAO assigns them to a file sorted by user then item).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from .capi import TrainingSet
+
+
+def context_table(dims: Sequence[int]) -> Tuple[np.ndarray, np.ndarray, int, int]:
+    """All combinations of one condition per dimension.  Context id = mixed-radix number of its
+    conditions; condition ids are numbered dimension by dimension like the one-hot header columns
+    (DataDAO.java:202-215).  Returns (ctx_ptr, ctx_cond, num_contexts, num_conditions)."""
+    dims = [int(d) for d in dims]
+    D = len(dims)
+    num_ctx = int(np.prod(dims))
+    offs = np.concatenate([[0], np.cumsum(dims)[:-1]]).astype(np.int64)
+    ids = np.arange(num_ctx, dtype=np.int64)
+    cond = np.empty((num_ctx, D), dtype=np.int32)
+    rem = ids.copy()
+    for k, d in enumerate(dims):
+        cond[:, k] = (rem % d + offs[k]).astype(np.int32)
+        rem //= d
+    ctx_ptr = (np.arange(num_ctx + 1, dtype=np.int64) * D).astype(np.int32)
+    return ctx_ptr, cond.reshape(-1).copy(), num_ctx, int(sum(dims))
+
+
+def make_training_set(num_users: int, num_items: int, dims: Optional[Sequence[int]], nnz: int, seed: int,
+                      order: str = "user_sorted", item_zipf: float = 0.0, rating_levels: int = 5,
+                      holdout: float = 0.0):
+    """Unique (u, j, ctx) triples with u uniform, j uniform (or Zipf(item_zipf)), ctx uniform, ratings
+    uniform in {1..rating_levels}.
+
+    order = "user_sorted": pair ids follow (u, j) order, i.e. a ratings file sorted by user then item.
+    order = "shuffled":    pair ids in random first-appearance order (an unsorted ratings file).
+    Returns (train TrainingSet, test dict or None)."""
+    rng = np.random.default_rng(seed)
+    u = rng.integers(0, num_users, size=nnz, dtype=np.int64)
+    if item_zipf > 0:
+        w = 1.0 / np.power(np.arange(1, num_items + 1, dtype=np.float64), item_zipf)
+        j = rng.choice(num_items, size=nnz, p=w / w.sum()).astype(np.int64)
+    else:
+        j = rng.integers(0, num_items, size=nnz, dtype=np.int64)
+    if dims is not None:
+        ctx_ptr, ctx_cond, num_ctx, num_cond = context_table(dims)
+        c = rng.integers(0, num_ctx, size=nnz, dtype=np.int64)
+    else:
+        ctx_ptr = ctx_cond = None
+        num_ctx, num_cond = 1, 0
+        c = np.zeros(nnz, dtype=np.int64)
+    pair = u * num_items + j
+    if order == "shuffled":
+        # pair id = rank of first appearance in the (random) generation order
+        uniq, first = np.unique(pair, return_index=True)
+        rank_of = np.empty(uniq.shape[0], dtype=np.int64)
+        rank_of[np.argsort(first, kind="stable")] = np.arange(uniq.shape[0])
+        ui = rank_of[np.searchsorted(uniq, pair)]
+    elif order == "user_sorted":
+        ui = pair
+    else:
+        raise ValueError(order)
+    key = ui * num_ctx + c
+    key, idx = np.unique(key, return_index=True)  # CRS order; duplicates: keep one
+    u, j, c = u[idx].astype(np.int32), j[idx].astype(np.int32), c[idx].astype(np.int32)
+    r = rng.integers(1, rating_levels + 1, size=u.shape[0]).astype(np.float64)
+
+    test = None
+    if holdout > 0:
+        mask = rng.random(u.shape[0]) < holdout
+        test = {"u": u[mask].copy(), "j": j[mask].copy(), "ctx": c[mask].copy() if dims is not None else None,
+                "r": r[mask].copy()}
+        keep = ~mask
+        u, j, c, r = u[keep], j[keep], c[keep], r[keep]
+    # SparseMatrix.getGlobalAvg: sequential sum / count of non-zeros (structure/SparseMatrix.java:49-56)
+    gm = float(np.cumsum(r)[-1] / np.count_nonzero(r)) if r.shape[0] else 0.0
+    ts = TrainingSet(num_users=num_users, num_items=num_items, u=u, j=j, r=r,
+                     ctx=c if dims is not None else None, num_conditions=num_cond,
+                     num_contexts=num_ctx if dims is not None else 0, ctx_ptr=ctx_ptr, ctx_cond=ctx_cond,
+                     global_mean=gm)
+    return ts, test

@@ -1,0 +1,188 @@
+/*
+ * carskit_b200.h -- C ABI of the B200-native engine for the CARSKit SGD hot path.
+ *
+ * The reference (irecsys/CARSKit, 100 % Java) has no FFI; the plug-in point is the
+ * template-method hook `protected void buildModel()` (src/carskit/generic/Recommender.java:1088)
+ * that Recommender.execute() calls between initModel() and evalRatings()/evalRankings()
+ * (Recommender.java:319-346).  A subclass such as CAMF_CI_B200 overrides only buildModel(), flattens
+ * the Java containers once and calls the entry points below through a 1:1 JNI wrapper
+ * (see INTEGRATION.md).  Every entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are caller-owned HOST memory, valid for the duration
+ *     of the call; the handle owns every device allocation.
+ *   - return 0 on success, a negative CARS_E_* code otherwise; message via cars_last_error().
+ *     The library never calls exit(); a NaN/Inf loss is *returned* so the Java-side check
+ *     (IterativeRecommender.java:181-184) still fires.
+ *   - re-entrant per handle (CARSKit runs K cross-validation folds on K threads,
+ *     src/carskit/main/CARSKit.java:395-412); no global mutable state.
+ *   - there is NO CPU fallback: without a usable CUDA device cars_create() fails with
+ *     CARS_E_NO_DEVICE.
+ */
+#ifndef CARSKIT_B200_H
+#define CARSKIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CARS_ABI_VERSION 1
+
+/* Recommender classes on the hot path. */
+enum cars_model {
+  CARS_PMF      = 0, /* src/carskit/alg/baseline/cf/PMF.java:47-82            (2-D `train`, ctx = NULL) */
+  CARS_BIASEDMF = 1, /* src/carskit/alg/baseline/cf/BiasedMF.java:58-108      (2-D `train`, ctx = NULL) */
+  CARS_CAMF_C   = 2, /* .../cars/adaptation/dependent/dev/CAMF_C.java:74-138  */
+  CARS_CAMF_CI  = 3, /* .../cars/adaptation/dependent/dev/CAMF_CI.java:74-131 */
+  CARS_CAMF_CU  = 4, /* .../cars/adaptation/dependent/dev/CAMF_CU.java:71-128 */
+  CARS_FM       = 5  /* .../cars/adaptation/dependent/FM.java:115-220 (ALS; not built in round 1) */
+};
+
+/* Update schedule.
+ * EXACT: serial-equivalent.  Ratings that share a user or an item run in the reference's iteration
+ *        order (CRS order of trainMatrix, CAMF_CI.java:80); independent ratings run concurrently.
+ *        P, Q and every bias end bit-identical to the Java loop; only `loss` (a 67*nnz-term
+ *        sequential fp64 sum in Java) differs, by summation order (~1e-13 relative).
+ *        CAMF_C in EXACT mode runs on one warp (every rating touches the shared condBias vector,
+ *        CAMF_C.java:107-113), so it is meant for small data.
+ * FAST:  same schedule, but vectors shared by all ratings (condBias of CAMF_C) are updated with
+ *        relaxed atomics, and the dot product uses a shuffle tree; not serial-equivalent. */
+enum cars_mode { CARS_EXACT = 0, CARS_FAST = 1 };
+
+enum cars_error {
+  CARS_OK            =  0,
+  CARS_E_INVALID     = -1, /* bad argument / inconsistent descriptor            */
+  CARS_E_NO_DEVICE   = -2, /* no CUDA device, or device is not sm_100           */
+  CARS_E_CUDA        = -3, /* a CUDA runtime call failed                        */
+  CARS_E_OOM         = -4, /* host or device allocation failed                  */
+  CARS_E_UNSUPPORTED = -5, /* model/mode combination not built                  */
+  CARS_E_STATE       = -6  /* call order violated (e.g. epoch before upload)    */
+};
+
+/* Training-set descriptor: what buildModel() can reach without reflection.
+ *   u/j/ctx/r   one entry per training rating, in the reference's iteration order
+ *               (`for (MatrixEntry me : trainMatrix)`: row = user-item pair id ascending, column =
+ *               context id ascending; u = rateDao.getUserIdFromUI(ui), j = getItemIdFromUI(ui),
+ *               DataDAO.java:1038-1046).  For PMF/BiasedMF iterate the 2-D `train` matrix and pass
+ *               ctx = NULL.
+ *   ctx_ptr/ctx_cond   CSR form of rateDao.getContextConditionsList() (DataDAO.java:1035): the
+ *               condition ids of context c are ctx_cond[ctx_ptr[c] .. ctx_ptr[c+1]), in the order
+ *               ContextRecommender.getConditions() yields them (ContextRecommender.java:53-61).
+ *   reg_*       the static floats regU/regI/regB/regC (IterativeRecommender.java:92-99) and FM's
+ *               regLw/regLf (FM.java:53-54) ALREADY widened float->double by the caller
+ *               (1e-4f -> 9.999999747378752e-05); never re-parse the decimal string as a double.
+ */
+typedef struct cars_desc {
+  int32_t abi_version;     /* = CARS_ABI_VERSION */
+  int32_t model;           /* enum cars_model */
+  int32_t mode;            /* enum cars_mode  */
+  int32_t device;          /* CUDA device ordinal */
+  int32_t num_users;
+  int32_t num_items;
+  int32_t num_conditions;  /* rateDao.numConditions(), ContextRecommender.java:43 */
+  int32_t num_contexts;
+  int32_t num_factors;     /* IterativeRecommender.numFactors (:101) */
+  int32_t reserved0;
+  int64_t nnz;
+  const int32_t* u;
+  const int32_t* j;
+  const int32_t* ctx;      /* NULL for PMF / BiasedMF */
+  const double*  r;
+  const int32_t* ctx_ptr;  /* [num_contexts + 1], NULL when ctx == NULL */
+  const int32_t* ctx_cond; /* [ctx_ptr[num_contexts]] */
+  double global_mean;      /* Recommender.globalMean (Recommender.java:265) */
+  double reg_u, reg_i, reg_b, reg_c, reg_lw, reg_lf;
+  /* Multi-GPU (one process per GPU).  Rank g of world_size trains the ratings whose user lies in
+   * its contiguous user range; see cars_shard_* below.  world_size <= 1 means a single GPU. */
+  int32_t rank;
+  int32_t world_size;
+  void*   stream;          /* cudaStream_t to launch on; NULL = the handle creates its own */
+} cars_desc;
+
+typedef struct cars_handle cars_handle;
+
+/* Model arrays, row-major contiguous, NULL where the model has no such member:
+ *   P [num_users x F], Q [num_items x F]              IterativeRecommender.java:55-58
+ *   user_bias [num_users], item_bias [num_items]      IterativeRecommender.java:61-63
+ *   cond_bias [num_conditions]                        CAMF.java (condBias), CAMF_C.java:60
+ *   ic_bias [num_items x num_conditions]              CAMF_CI.java:58
+ *   uc_bias [num_users x num_conditions]              CAMF_CU.java:55 */
+typedef struct cars_model_arrays {
+  double* P;
+  double* Q;
+  double* user_bias;
+  double* item_bias;
+  double* cond_bias;
+  double* ic_bias;
+  double* uc_bias;
+} cars_model_arrays;
+
+/* Replaces the set-up a Java buildModel() does implicitly by holding trainMatrix/rateDao: copies the
+ * rating arrays to the device and builds the dependency schedule (wavefront levels). */
+int cars_create(const cars_desc* desc, cars_handle** out);
+
+/* Hands over the arrays Java's initModel() produced (IterativeRecommender.java:231-247 and
+ * CAMF_*.initModel).  May be called again to reset the model. */
+int cars_upload(cars_handle* h, const cars_model_arrays* host);
+
+/* One pass over all training ratings == one iteration of the `for (int iter = 1; ...)` loop body of
+ * buildModel() up to and including `loss *= 0.5` (CAMF_CI.java:79-124 and siblings).  `lrate` is the
+ * instance field lRate.  The caller keeps isConverged(iter)/updateLRate (IterativeRecommender.java:
+ * 145-229) in Java and passes the new lRate next time. */
+int cars_epoch(cars_handle* h, double lrate, double* loss_out);
+
+/* Asynchronous variant: enqueue the epoch on the handle's stream and return; cars_epoch_wait() blocks
+ * and fetches the loss.  cars_epoch == cars_epoch_begin + cars_epoch_wait. */
+int cars_epoch_begin(cars_handle* h, double lrate);
+int cars_epoch_wait(cars_handle* h, double* loss_out);
+
+/* Copies the trained arrays back so the inherited Java predict()/evalRatings()/evalRankings()
+ * (Recommender.java:306-317, 504-594, 672-960) see them. */
+int cars_download(cars_handle* h, const cars_model_arrays* host);
+
+/* Batched Recommender.predict(u, j, c, bound) (Recommender.java:306-317) with the model's
+ * predict(u,j,c) (CAMF_CI.java:65-72 etc.); sequential-order dot product, so bit-identical to Java.
+ * ctx may be NULL for PMF/BiasedMF. */
+int cars_predict(cars_handle* h, int64_t n, const int32_t* u, const int32_t* j, const int32_t* ctx,
+                 int32_t bound, double min_rate, double max_rate, double* out);
+
+/* evalRatings() core (Recommender.java:518-545): sum |err| and sum err^2 over a test set, computed on
+ * the device from the resident model; the caller derives MAE/RMSE (:567-570). */
+int cars_eval_ratings(cars_handle* h, int64_t n, const int32_t* u, const int32_t* j, const int32_t* ctx,
+                      const double* r, double min_rate, double max_rate, double* sum_abs_err,
+                      double* sum_sq_err);
+
+void cars_destroy(cars_handle* h);
+
+/* Message of the last failure on this handle (or of the last failed cars_create when h == NULL;
+ * thread-local).  Never NULL. */
+const char* cars_last_error(const cars_handle* h);
+
+/* Introspection used by the benchmark and the tests (no reference counterpart). */
+typedef struct cars_stats {
+  int64_t nnz;              /* ratings trained by this handle (after sharding)         */
+  int64_t num_levels;       /* wavefront levels of the dependency DAG                  */
+  int64_t max_level_size;
+  int64_t kernel_launches;  /* engine kernels launched so far on this handle           */
+  int64_t h2d_bytes;        /* bytes copied host->device so far                        */
+  int64_t d2h_bytes;        /* bytes copied device->host so far                        */
+  double  schedule_ms;      /* wall time spent building the schedule in cars_create    */
+  double  last_epoch_ms;    /* device time of the last epoch's SGD kernel (CUDA events on the
+                               launching stream)                                       */
+  int32_t grid_ctas;        /* persistent grid of the SGD kernel                       */
+  int32_t block_threads;
+  int32_t sm_count;
+  int32_t reserved;
+} cars_stats;
+int cars_get_stats(const cars_handle* h, cars_stats* out);
+void* cars_get_stream(const cars_handle* h); /* cudaStream_t the kernels are launched on */
+
+/* Library self-description: "carskit_b200 <abi> sm_100a ..." */
+const char* cars_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARSKIT_B200_H */

@@ -1,0 +1,235 @@
+"""CPU tests of the oracle (oracle/cars_oracle.cpp): known answers and an independent restatement.
+
+The reference pins nothing (no tests, no golden files, no JVM here -- SURVEY.md section 4/8c), so the
+pins are (1) java.util.Random known answers, (2) a second, independent pure-Python reading of the Java
+loops on small inputs, (3) self-minted golden vectors under tests/golden (regression pins).
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from carskit_b200 import capi, synth
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ---------------------------------------------------------------------------------------------------
+# java.util.Random known answers (widely published outputs of the JDK LCG)
+# ---------------------------------------------------------------------------------------------------
+def test_java_random_known_answers(oracle):
+    assert oracle.JavaRandom(42).next_int() == -1170105035
+    assert oracle.JavaRandom(0).next_int() == -1155484576
+    g = oracle.JavaRandom(42)
+    assert [g.next_int_bound(10) for _ in range(5)] == [0, 3, 8, 4, 0]
+    assert oracle.JavaRandom(42).next_double() == 0.7275636800328681
+    assert oracle.JavaRandom(0).next_double() == 0.730967787376657
+    assert oracle.JavaRandom(0).next_gaussian() == 0.8025330637390305
+    g = oracle.JavaRandom(0)
+    g.next_gaussian()
+    assert g.next_gaussian() == -0.9015460884175122  # the cached second value of the polar pair
+    assert g.next_gaussian() == 2.080920790428163
+    assert oracle.JavaRandom(42).next_gaussian() == float("1.1419053154730547")
+
+
+def test_oracle_compiled_without_fma(oracle):
+    assert oracle.lib().oracle_selftest_no_fma() == 1
+
+
+def test_float_widening():
+    # IterativeRecommender.java:40: regs and initLRate are Java floats widened at use
+    assert capi.f32(0.02) == 0.019999999552965164
+    assert capi.f32(1e-4) == 9.999999747378752e-05
+    assert capi.f32(1e-3) == 0.0010000000474974513
+
+
+# ---------------------------------------------------------------------------------------------------
+# independent pure-Python restatement (Python floats are IEEE doubles, never fused)
+# ---------------------------------------------------------------------------------------------------
+def py_epoch(model, ts, F, arrs, lr, regU, regI, regB, regC):
+    P, Q = arrs["P"], arrs["Q"]
+    ub, ib = arrs.get("user_bias"), arrs.get("item_bias")
+    cb, ic, uc = arrs.get("cond_bias"), arrs.get("ic_bias"), arrs.get("uc_bias")
+    gm = ts.global_mean
+    loss = 0.0
+    for n in range(ts.nnz):
+        u, j, r = int(ts.u[n]), int(ts.j[n]), float(ts.r[n])
+        conds = []
+        if ts.ctx is not None and model in (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU):
+            c = int(ts.ctx[n])
+            conds = [int(x) for x in ts.ctx_cond[ts.ctx_ptr[c]:ts.ctx_ptr[c + 1]]]
+        dot = 0.0
+        for f in range(F):
+            dot += float(P[u, f]) * float(Q[j, f])
+        if model == capi.PMF:
+            pred = dot
+        elif model == capi.BIASEDMF:
+            pred = gm + float(ub[u]) + float(ib[j]) + dot
+        elif model == capi.CAMF_C:
+            pred = gm + float(ub[u]) + float(ib[j]) + dot
+            for cd in conds:
+                pred += float(cb[cd])
+        elif model == capi.CAMF_CI:
+            pred = gm + float(ub[u]) + dot
+            for cd in conds:
+                pred += float(ic[j, cd])
+        elif model == capi.CAMF_CU:
+            pred = gm + float(ib[j]) + dot
+            for cd in conds:
+                pred += float(uc[u, cd])
+        e = r - pred
+        loss += e * e
+        if model in (capi.BIASEDMF, capi.CAMF_C, capi.CAMF_CI):
+            bu = float(ub[u])
+            ub[u] = bu + lr * (e - regB * bu)
+            loss += regB * bu * bu
+        if model in (capi.BIASEDMF, capi.CAMF_C, capi.CAMF_CU):
+            bj = float(ib[j])
+            ib[j] = bj + lr * (e - regB * bj)
+            loss += regB * bj * bj
+        if model == capi.CAMF_C:
+            s = 0.0
+            for cd in conds:
+                b = float(cb[cd])
+                s += b
+                cb[cd] = b + lr * (e - regC * b)
+            loss += regB * s
+        if model == capi.CAMF_CI:
+            s = 0.0
+            for cd in conds:
+                b = float(ic[j, cd])
+                s += b * b
+                ic[j, cd] = b + lr * (e - regC * b)
+            loss += regC * s
+        if model == capi.CAMF_CU:
+            s = 0.0
+            for cd in conds:
+                b = float(uc[u, cd])
+                s += b * b
+                uc[u, cd] = b + lr * (e - regC * b)
+            loss += regC * s
+        for f in range(F):
+            p, q = float(P[u, f]), float(Q[j, f])
+            du = e * q - regU * p
+            dj = e * p - regI * q
+            P[u, f] = p + lr * du
+            Q[j, f] = q + lr * dj
+            loss += regU * p * p + regI * q * q
+    return loss * 0.5
+
+
+def init_arrays(oracle, model, ts, F, seed):
+    """initModel(): gaussian N(0, 0.1) for P, Q and the bias vectors, uniform(0,1) for the
+    item-context / user-context bias matrices (CAMF_CI.java:55-60, CAMF_CU.java:52-57)."""
+    g = oracle.JavaRandom(seed)
+    shapes = capi.member_shapes(model, ts.num_users, ts.num_items, ts.num_conditions, F)
+    out = {}
+    for k, shp in shapes.items():
+        out[k] = g.uniform(shp) if k in ("ic_bias", "uc_bias") else g.gaussian(shp)
+    return out
+
+
+REGS = dict(reg_u=capi.f32(1e-4), reg_i=capi.f32(1e-4), reg_b=capi.f32(1e-4), reg_c=capi.f32(1e-3))
+
+
+@pytest.mark.parametrize("model", [capi.PMF, capi.BIASEDMF, capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU])
+@pytest.mark.parametrize("order", ["user_sorted", "shuffled"])
+def test_oracle_matches_independent_restatement(oracle, model, order):
+    ctxm = model in (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU)
+    ts, _ = synth.make_training_set(23, 11, [2, 3, 2] if ctxm else None, 400, seed=3, order=order)
+    F = 7
+    desc = capi.make_desc(ts, model, F, **REGS)
+    a = init_arrays(oracle, model, ts, F, seed=5)
+    b = {k: v.copy() for k, v in a.items()}
+    lr = capi.f32(0.02)
+    for _ in range(3):
+        la = oracle.epoch(desc, a, lr)
+        lb = py_epoch(model, ts, F, b, lr, REGS["reg_u"], REGS["reg_i"], REGS["reg_b"], REGS["reg_c"])
+        assert la == lb  # bit-exact, including the sequentially accumulated loss
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_oracle_predict_and_eval(oracle):
+    ts, test = synth.make_training_set(40, 15, [3, 2], 900, seed=11, holdout=0.2)
+    F = 6
+    desc = capi.make_desc(ts, capi.CAMF_CI, F, **REGS)
+    a = init_arrays(oracle, capi.CAMF_CI, ts, F, seed=2)
+    oracle.epoch(desc, a, capi.f32(0.02))
+    p = oracle.predict(desc, a, test["u"], test["j"], test["ctx"], bound=True, min_rate=1.0, max_rate=5.0)
+    assert p.min() >= 1.0 and p.max() <= 5.0
+    raw = oracle.predict(desc, a, test["u"], test["j"], test["ctx"])
+    # independent value for query 0
+    u, j, c = int(test["u"][0]), int(test["j"][0]), int(test["ctx"][0])
+    dot = 0.0
+    for f in range(F):
+        dot += float(a["P"][u, f]) * float(a["Q"][j, f])
+    pred = ts.global_mean + float(a["user_bias"][u]) + dot
+    for cd in ts.ctx_cond[ts.ctx_ptr[c]:ts.ctx_ptr[c + 1]]:
+        pred += float(a["ic_bias"][j, cd])
+    assert raw[0] == pred
+    sa, ss, cnt = oracle.eval_ratings(desc, a, test["u"], test["j"], test["ctx"], test["r"], 1.0, 5.0)
+    err = np.abs(test["r"] - p)
+    assert cnt == len(p)
+    assert math.isclose(sa, float(err.sum()), rel_tol=1e-12)
+    assert math.isclose(ss, float((err * err).sum()), rel_tol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------
+# epoch control: IterativeRecommender.isConverged / updateLRate (:145-229)
+# ---------------------------------------------------------------------------------------------------
+def test_bold_driver_and_convergence(oracle):
+    L = oracle.lib()
+    import ctypes as C
+    s = oracle.new_state(capi.f32(0.02), bold_driver=True)
+    s.loss = 100.0
+    assert L.oracle_is_converged(C.byref(s), 1) == 0
+    assert s.lRate == capi.f32(0.02)  # no change at iter 1 (bold driver needs iter > 1)
+    s.loss = 90.0
+    assert L.oracle_is_converged(C.byref(s), 2) == 0
+    assert s.lRate == capi.f32(0.02) * 1.05
+    s.loss = 95.0
+    assert L.oracle_is_converged(C.byref(s), 3) == 0
+    assert s.lRate == capi.f32(0.02) * 1.05 * 0.5
+    s.loss = 1e-6
+    assert L.oracle_is_converged(C.byref(s), 4) == 1
+    s.loss = float("nan")
+    assert L.oracle_is_converged(C.byref(s), 5) == -1
+    # decay + max clamp
+    s = oracle.new_state(0.5, bold_driver=False, decay=0.9, max_lrate=0.4)
+    s.loss = 10.0
+    assert L.oracle_is_converged(C.byref(s), 1) == 0
+    assert s.lRate == pytest.approx(0.4)  # 0.5 * 0.9f = 0.45 -> clamped to 0.4f
+    # early stop on Loss: delta in (0, 1e-5) converges
+    s = oracle.new_state(0.01, bold_driver=False, early_stop=1)
+    s.loss = 5.0
+    assert L.oracle_is_converged(C.byref(s), 1) == 0
+    s.loss = 5.0 - 1e-6
+    assert L.oracle_is_converged(C.byref(s), 2) == 1
+
+
+def test_global_mean_counts_nonzeros(oracle):
+    r = np.array([4.0, 0.0, 2.0, 0.0, 3.0])
+    assert oracle.global_mean(r) == 3.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden vectors (minted by tests/golden/make_golden.py from this oracle; regression pins)
+# ---------------------------------------------------------------------------------------------------
+def _golden_cases():
+    path = os.path.join(GOLDEN, "sgd_golden.json")
+    if not os.path.exists(path):
+        return []
+    with open(path) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", _golden_cases(), ids=lambda c: c["name"])
+def test_oracle_reproduces_golden(oracle, case):
+    from tests.golden.make_golden import run_case
+    got = run_case(oracle, case["spec"])
+    assert got["losses_hex"] == case["losses_hex"]
+    assert got["digest"] == case["digest"]
+    assert got["rmse_hex"] == case["rmse_hex"]
