@@ -95,32 +95,32 @@ struct LaunchPlan {
   int lpr = 0, v = 0;
 };
 
-template <int MODEL, bool ATOMIC>
+template <int MODEL>
 static LaunchPlan pick_wavefront(int Fp) {
   LaunchPlan p;
   if (Fp <= 16) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 1, ATOMIC, kThreads>; p.lpr = 8; p.v = 1;
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 1, kThreads>; p.lpr = 8; p.v = 1;
   } else if (Fp <= 32) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 2, ATOMIC, kThreads>; p.lpr = 8; p.v = 2;
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 2, kThreads>; p.lpr = 8; p.v = 2;
   } else if (Fp <= 64) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 4, ATOMIC, kThreads>; p.lpr = 8; p.v = 4;
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 4, kThreads>; p.lpr = 8; p.v = 4;
   } else if (Fp <= 128) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 16, 4, ATOMIC, kThreads>; p.lpr = 16; p.v = 4;
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 16, 4, kThreads>; p.lpr = 16; p.v = 4;
   } else if (Fp <= 256) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 32, 4, ATOMIC, kThreads>; p.lpr = 32; p.v = 4;
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 32, 4, kThreads>; p.lpr = 32; p.v = 4;
   } else if (Fp <= 512) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 32, 8, ATOMIC, kThreads>; p.lpr = 32; p.v = 8;
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 32, 8, kThreads>; p.lpr = 32; p.v = 8;
   }
   return p;
 }
 
-static LaunchPlan pick_plan(int model, int mode, int Fp) {
+static LaunchPlan pick_plan(int model, int /*mode*/, int Fp) {
   switch (model) {
-    case CARS_PMF: return pick_wavefront<M_PMF, false>(Fp);
-    case CARS_BIASEDMF: return pick_wavefront<M_BIASEDMF, false>(Fp);
-    case CARS_CAMF_C: return mode == CARS_FAST ? pick_wavefront<M_CAMF_C, true>(Fp) : LaunchPlan{};
-    case CARS_CAMF_CI: return pick_wavefront<M_CAMF_CI, false>(Fp);
-    case CARS_CAMF_CU: return pick_wavefront<M_CAMF_CU, false>(Fp);
+    case CARS_PMF: return pick_wavefront<M_PMF>(Fp);
+    case CARS_BIASEDMF: return pick_wavefront<M_BIASEDMF>(Fp);
+    case CARS_CAMF_C: return LaunchPlan{};  // every rating touches condBias: serial kernel only
+    case CARS_CAMF_CI: return pick_wavefront<M_CAMF_CI>(Fp);
+    case CARS_CAMF_CU: return pick_wavefront<M_CAMF_CU>(Fp);
   }
   return LaunchPlan{};
 }
@@ -159,6 +159,8 @@ static int validate(const cars_desc* d) {
   if (d->model == CARS_FM)
     return fail(nullptr, CARS_E_UNSUPPORTED, "FM (ALS, FM.java:115-220) is not built yet");
   if (d->mode != CARS_EXACT && d->mode != CARS_FAST) return fail(nullptr, CARS_E_INVALID, "unknown mode %d", d->mode);
+  if (d->mode == CARS_FAST)
+    return fail(nullptr, CARS_E_UNSUPPORTED, "FAST (non serial-equivalent) mode is not built; use CARS_EXACT");
   if (d->num_users <= 0 || d->num_items <= 0) return fail(nullptr, CARS_E_INVALID, "num_users/num_items must be > 0");
   if (d->num_factors <= 0 || d->num_factors > 512)
     return fail(nullptr, CARS_E_UNSUPPORTED, "num_factors %d outside 1..512", d->num_factors);
@@ -272,7 +274,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
 
   // ---- schedule ----------------------------------------------------------------------------------------
   auto t0 = std::chrono::steady_clock::now();
-  h->serial = (desc->model == CARS_CAMF_C && desc->mode == CARS_EXACT);
+  h->serial = (desc->model == CARS_CAMF_C);
   h->nnz = nnz;
   std::vector<int64_t> level_start;
   HostSchedule sched;

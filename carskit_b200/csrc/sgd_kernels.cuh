@@ -105,9 +105,8 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
 // One rating update by one group of LPR lanes.  V = 16-byte chunks per lane (LPR * V * 2 >= Fp).
 // `prod` = this group's shared-memory scratch of Fp doubles (for the in-order dot product).
 // Returns this lane's contribution to the epoch loss (un-halved).
-//   kAtomicCond: CAMF_C only -- update the shared condBias vector with relaxed atomics (FAST mode).
 // ------------------------------------------------------------------------------------------------
-template <int MODEL, int LPR, int V, bool kAtomicCond>
+template <int MODEL, int LPR, int V>
 __device__ __forceinline__ double rating_update(const DeviceModel& m, int u, int j, int ctx, double r,
                                                 double lr, double* prod, int gl /*lane in group*/,
                                                 unsigned gmask /*lanes of this group*/) {
@@ -216,10 +215,7 @@ __device__ __forceinline__ double rating_update(const DeviceModel& m, int u, int
     if (cb_ptr != nullptr) {
       const double sgd = __dsub_rn(e, __dmul_rn(m.reg_c, cb));
       const double step = __dmul_rn(lr, sgd);
-      if (MODEL == M_CAMF_C && kAtomicCond)
-        atomicAdd(cb_ptr, step);
-      else
-        st_cg_f64(cb_ptr, __dadd_rn(cb, step));
+      st_cg_f64(cb_ptr, __dadd_rn(cb, step));
       // CAMF_C.java:115 adds regB * sum(bc) (not squared); CI/CU add regC * sum(b^2) (:108 / :105)
       if (MODEL == M_CAMF_C)
         lane_loss = __dadd_rn(lane_loss, __dmul_rn(m.reg_b, cb));
@@ -235,10 +231,7 @@ __device__ __forceinline__ double rating_update(const DeviceModel& m, int u, int
                                           : m.uc_bias + (int64_t)u * m.C + cond;
         const double b = ld_cg_f64(bp);
         const double step = __dmul_rn(lr, __dsub_rn(e, __dmul_rn(m.reg_c, b)));
-        if (MODEL == M_CAMF_C && kAtomicCond)
-          atomicAdd(bp, step);
-        else
-          st_cg_f64(bp, __dadd_rn(b, step));
+        st_cg_f64(bp, __dadd_rn(b, step));
         lane_loss = __dadd_rn(lane_loss, MODEL == M_CAMF_C ? __dmul_rn(m.reg_b, b)
                                                              : __dmul_rn(m.reg_c, __dmul_rn(b, b)));
       }
@@ -273,7 +266,7 @@ __device__ __forceinline__ double rating_update(const DeviceModel& m, int u, int
 // barrier separates levels.  Launched cooperatively with one CTA per SM slot.
 // block_partial[blockIdx.x] receives the CTA's loss partial (reduced in fixed order by K3).
 // ------------------------------------------------------------------------------------------------
-template <int MODEL, int LPR, int V, bool kAtomicCond, int THREADS>
+template <int MODEL, int LPR, int V, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
     sgd_wavefront_kernel(DeviceModel m, RatingStream s, double lr, unsigned* barrier_counter,
                          double* block_partial) {
@@ -301,7 +294,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       const int j = __ldg(s.j + n);
       const int ctx = s.ctx ? __ldg(s.ctx + n) : 0;
       const double r = __ldg(s.r + n);
-      acc = __dadd_rn(acc, rating_update<MODEL, LPR, V, kAtomicCond>(m, u, j, ctx, r, lr, prod, gl, gmask));
+      acc = __dadd_rn(acc, rating_update<MODEL, LPR, V>(m, u, j, ctx, r, lr, prod, gl, gmask));
     }
     if (L + 1 < s.num_levels) grid_barrier(barrier_counter, (unsigned)(L + 1) * gridDim.x);
   }
@@ -332,7 +325,7 @@ __global__ void __launch_bounds__(32, 1)
     const int j = __ldg(s.j + n);
     const int ctx = s.ctx ? __ldg(s.ctx + n) : 0;
     const double r = __ldg(s.r + n);
-    acc = __dadd_rn(acc, rating_update<MODEL, 32, V, false>(m, u, j, ctx, r, lr, prod, lane, 0xffffffffu));
+    acc = __dadd_rn(acc, rating_update<MODEL, 32, V>(m, u, j, ctx, r, lr, prod, lane, 0xffffffffu));
     __syncwarp();
     __threadfence_block();
   }

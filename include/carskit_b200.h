@@ -47,8 +47,9 @@ enum cars_model {
  *        sequential fp64 sum in Java) differs, by summation order (~1e-13 relative).
  *        CAMF_C in EXACT mode runs on one warp (every rating touches the shared condBias vector,
  *        CAMF_C.java:107-113), so it is meant for small data.
- * FAST:  same schedule, but vectors shared by all ratings (condBias of CAMF_C) are updated with
- *        relaxed atomics, and the dot product uses a shuffle tree; not serial-equivalent. */
+ * FAST:  reserved for a non serial-equivalent schedule; cars_create() returns CARS_E_UNSUPPORTED
+ *        (hogwild updates of the shared condBias vector of CAMF_C were measured to diverge, see
+ *        DESIGN.md). */
 enum cars_mode { CARS_EXACT = 0, CARS_FAST = 1 };
 
 enum cars_error {

@@ -74,15 +74,11 @@ def test_camf_c_exact_serial_kernel(oracle, cars_lib):
     np.testing.assert_allclose(gl, rl, rtol=LOSS_RTOL, atol=0)
 
 
-def test_camf_c_fast_mode_close(oracle, cars_lib):
-    # FAST relaxes only the shared condBias vector (atomics): not serial-equivalent; stated tolerance
-    ts, test = synth.make_training_set(957, 4082, [7, 7, 2, 3, 2, 9, 80, 233], 96203, seed=1, holdout=0.1)
-    ref, got, rl, gl, _ = run_both(oracle, capi.CAMF_C, ts, 10, epochs=5, seed=5, mode=capi.FAST)
-    np.testing.assert_allclose(gl, rl, rtol=2e-2)
-    desc = capi.make_desc(ts, capi.CAMF_C, 10, **REGS)
-    sa, ss, cnt = oracle.eval_ratings(desc, ref, test["u"], test["j"], test["ctx"], test["r"], 1.0, 5.0)
-    sa2, ss2, _ = oracle.eval_ratings(desc, got, test["u"], test["j"], test["ctx"], test["r"], 1.0, 5.0)
-    assert abs(math.sqrt(ss / cnt) - math.sqrt(ss2 / cnt)) < 2e-2
+def test_fast_mode_is_refused_not_faked(oracle, cars_lib):
+    ts, _ = synth.make_training_set(90, 120, [7, 7], 3000, seed=21)
+    with pytest.raises(capi.CarsError) as e:
+        capi.Engine(capi.make_desc(ts, capi.CAMF_C, 10, mode=capi.FAST, **REGS), keepalive=ts)
+    assert e.value.code == -5
 
 
 def test_many_context_dimensions(oracle, cars_lib):
