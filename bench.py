@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- SGD rating-updates/sec of the CARSKit hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one epoch of buildModel() -- one pass of the per-rating SGD loop over the whole synthetic
+training set (CAMF_CI.java:79-124).  Workload at N = 1: BASELINE.json configs[2], the configuration the
+metric is quoted on -- CAMF_CI, 64 factors, 1 M users x 100 K items x 32 conditions (4 dims x 8),
+100 M unique (u, j, ctx) ratings.  At N > 1 every rank trains its own 1 M-user shard of the same shape
+(weak scaling) and the item-side arrays are combined once per epoch (DESIGN.md "Multi-GPU").
+
+One JSON line on stdout (rank 0).  `value` = whole-job updates/s with the training set and the model
+resident in HBM; `e2e` = the same through recommender.buildModel() from host numpy buffers (schedule
+build, H2D of ratings and model, K epochs each returning its loss, D2H of the model);
+`roofline.achieved` = algorithmic bytes/update (16 + 4*F*8 + (2 + 2*D)*8 = 2144 B at F = 64,
+D = 4) * updates per launch / SGD-kernel duration (CUDA events on the launching stream, inside the
+library).  `cpu_baseline` = the CPU oracle's loop on a bounded prefix sample, 1 core (the reference's
+buildModel() is single-threaded).
+
+`--impl reference` times that CPU loop alone (the reference is Java and no JVM exists in the image, so
+the oracle port stands in; see DESIGN.md "Oracle").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sgd_rating_updates_per_sec"
+UNIT = "updates/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[2] (SURVEY.md 8d "Config 3")
+    "camf_ci_f64_1Mx100Kx32c_100M": dict(model="camf_ci", F=64, users=1_000_000, items=100_000, dims=[8, 8, 8, 8],
+                                         nnz=100_000_000, seed=20261017),
+    # small variants for quick checks (not the bench line)
+    "camf_ci_f64_100Kx10Kx32c_10M": dict(model="camf_ci", F=64, users=100_000, items=10_000, dims=[8, 8, 8, 8],
+                                         nnz=10_000_000, seed=20261017),
+    "camf_ci_f64_tiny": dict(model="camf_ci", F=64, users=5_000, items=1_000, dims=[8, 8, 8, 8], nnz=200_000,
+                             seed=20261017),
+    "camf_cu_f128_2Mx200Kx64c_200M": dict(model="camf_cu", F=128, users=2_000_000, items=200_000,
+                                          dims=[16, 16, 16, 16], nnz=200_000_000, seed=20261017),
+}
+DEFAULT_WORKLOAD = "camf_ci_f64_1Mx100Kx32c_100M"
+
+
+def algorithmic_bytes(model: str, F: int, D: int) -> int:
+    """B(F, D, s=8) = 16 + 4*F*8 + bias(8, D)."""
+    bias = {"pmf": 0, "biasedmf": 4 * 8, "camf_c": 4 * 8 + 2 * D * 8, "camf_ci": 2 * 8 + 2 * D * 8,
+            "camf_cu": 2 * 8 + 2 * D * 8}[model]
+    return 16 + 4 * F * 8 + bias
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md "clocks line")
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v == "Active":
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# inputs
+# ------------------------------------------------------------------------------------------------------
+def make_inputs(wl: dict, rank: int):
+    from carskit_b200 import capi, synth
+    t0 = time.time()
+    ts, _ = synth.make_training_set(wl["users"], wl["items"], wl["dims"], wl["nnz"], seed=wl["seed"] + rank,
+                                    order="user_sorted")
+    model = capi.MODEL_NAMES[wl["model"]]
+    F = wl["F"]
+    rng = np.random.default_rng(wl["seed"] + 7919)  # same model init on every rank (item side is replicated)
+    arrs = {}
+    for k, s in capi.member_shapes(model, ts.num_users, ts.num_items, ts.num_conditions, F).items():
+        if k in ("ic_bias", "uc_bias"):
+            arrs[k] = rng.random(s)
+        else:
+            arrs[k] = 0.1 * rng.standard_normal(s)
+    log(f"[bench] rank {rank}: synthetic training set nnz={ts.nnz} built in {time.time() - t0:.1f}s")
+    return ts, model, arrs
+
+
+def cpu_loop(wl: dict, ts, model, arrs, target_s: float, steps: int = 1, warmup: int = 0):
+    """The reference's buildModel() loop on the host: CPU oracle (a single-threaded port), on a PREFIX of the
+    training set in reference order (the first users' ratings, every item still present), sized from a
+    short calibration so one step takes about target_s."""
+    from carskit_b200 import capi
+    from oracle import oracle_py as orc
+    orc.build()
+    F = wl["F"]
+    regs = dict(reg_u=capi.f32(1e-4), reg_i=capi.f32(1e-4), reg_b=capi.f32(1e-4), reg_c=capi.f32(1e-3))
+
+    def sub(n):
+        from carskit_b200.capi import TrainingSet
+        return TrainingSet(num_users=ts.num_users, num_items=ts.num_items, u=ts.u[:n], j=ts.j[:n], r=ts.r[:n],
+                           ctx=None if ts.ctx is None else ts.ctx[:n], num_conditions=ts.num_conditions,
+                           num_contexts=ts.num_contexts, ctx_ptr=ts.ctx_ptr, ctx_cond=ts.ctx_cond,
+                           global_mean=ts.global_mean)
+
+    work = {k: v.copy() for k, v in arrs.items()}
+    lr = capi.f32(0.02)
+    n_cal = min(ts.nnz, 1_000_000)
+    s_cal = sub(n_cal)
+    t0 = time.perf_counter()
+    orc.epoch(capi.make_desc(s_cal, model, F, **regs), work, lr)
+    rate = n_cal / (time.perf_counter() - t0)
+    n = int(min(ts.nnz, max(n_cal, rate * target_s)))
+    s = sub(n)
+    desc = capi.make_desc(s, model, F, **regs)
+    for _ in range(warmup):
+        orc.epoch(desc, work, lr)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = orc.epoch(desc, work, lr)
+    dt = time.perf_counter() - t0
+    if not math.isfinite(loss):
+        raise RuntimeError("oracle loss is not finite")
+    return n * steps / dt, dt / steps, f"first {n} of {ts.nnz} ratings in reference order (user prefix, all items), " \
+                                       f"{steps} pass(es)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# arms
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args, wl, wl_name, rank, world):
+    if rank != 0:
+        return
+    ts, model, arrs = make_inputs(wl, 0)
+    per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    val, s_per_step, sample = cpu_loop(wl, ts, model, arrs, per_step, steps=args.steps, warmup=args.warmup)
+    D = len(wl["dims"]) if wl["dims"] else 0
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl_name, "model": wl["model"], "factors": wl["F"], "users": wl["users"],
+                   "items": wl["items"], "conditions": int(sum(wl["dims"])) if wl["dims"] else 0,
+                   "context_dims": D, "nnz": ts.nnz,
+                   "note": "reference arm = CPU oracle port of the Java buildModel() loop (no JVM in the image); "
+                           "single thread because the reference loop is single-threaded per fold"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def run_b200(args, wl, wl_name, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from carskit_b200 import capi, recommender
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; carskit_b200 has no CPU path (use --impl reference for the CPU loop)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ts, model, arrs = make_inputs(wl, rank)
+    F = wl["F"]
+    D = len(wl["dims"]) if wl["dims"] else 0
+    B = algorithmic_bytes(wl["model"], F, D)
+    conf = {"num.factors": str(F), "num.max.iter": str(args.steps), "learn.rate": "2e-2 -max -1 -bold-driver",
+            "reg.lambda": "0.0001 -c 0.001"}
+    Rec = recommender.getRecommender(wl["model"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm: `value` -----------------------------------------------------
+    stream = torch.cuda.current_stream().cuda_stream
+    rec = Rec(ts, None, conf=conf, device=local_rank, stream=stream)
+    rec.initModel(init={k: v.copy() for k, v in arrs.items()})
+    t0 = time.time()
+    eng = rec.open_engine()
+    st0 = eng.stats()
+    log(f"[bench] rank {rank}: cars_create+upload {time.time() - t0:.1f}s (schedule {st0.schedule_ms:.0f} ms, "
+        f"levels {st0.num_levels}, max level {st0.max_level_size}, grid {st0.grid_ctas}x{st0.block_threads})")
+    losses = []
+    for it in range(args.warmup):
+        rec.train_epoch(it + 1)
+        losses.append(rec.loss)
+    launches0 = eng.stats().kernel_launches
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    ev0.record()
+    for it in range(args.steps):
+        rec.train_epoch(args.warmup + it + 1)
+        losses.append(rec.loss)
+        kernel_ms.append(eng.stats().last_epoch_ms)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.stats().kernel_launches - launches0
+    if not all(math.isfinite(x) for x in losses):
+        raise RuntimeError(f"non-finite loss: {losses}")
+    nnz_local = ts.nnz
+    t = torch.tensor([ms, float(nnz_local), float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, nnz_total, kms = float(tmax[0]), float(tsum[1]), float(tmax[2])
+    else:
+        nnz_total, kms = float(nnz_local), float(np.mean(kernel_ms))
+    value = nnz_total * args.steps / (ms * 1e-3)
+    rec.close_engine()
+    log(f"[bench] rank {rank}: {args.steps} epochs in {ms:.1f} ms; SGD kernel {np.mean(kernel_ms):.2f} ms/epoch; "
+        f"losses {losses[:3]}..")
+
+    # ---------------- end-to-end arm: recommender.buildModel() from host buffers --------------------------
+    rec2 = Rec(ts, None, conf=conf, device=local_rank, stream=stream)
+    rec2.initModel(init=arrs)
+    barrier()
+    t0 = time.perf_counter()
+    rec2.buildModel()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    iters = len(rec2.iter_losses)
+    st2 = rec2.stats
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t[0])
+    e2e_value = nnz_total * iters / e2e_s
+    log(f"[bench] rank {rank}: buildModel() e2e {e2e_s:.2f}s for {iters} epochs (schedule {st2.schedule_ms:.0f} ms, "
+        f"h2d {st2.h2d_bytes / 1e9:.2f} GB, d2h {st2.d2h_bytes / 1e9:.2f} GB)")
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---------------- CPU baseline on rank 0 at N = 1 ---------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, _, sample = cpu_loop(wl, ts, model, arrs, target_s=12.0)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+               "host_cores_available": os.cpu_count()}
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = B * nnz_local / (float(np.mean(kernel_ms)) * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(wl_name, {}).get("dram_bytes_per_launch")
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl_name, "model": wl["model"], "factors": F, "users_per_gpu": wl["users"],
+                   "items": wl["items"], "conditions": int(sum(wl["dims"])) if wl["dims"] else 0, "context_dims": D,
+                   "nnz_per_gpu": nnz_local, "nnz_total": int(nnz_total), "mode": "exact (serial-equivalent wavefront)",
+                   "levels": int(st0.num_levels), "parallelism": f"user-range shards x{world}" if world > 1 else "1 gpu",
+                   "l2": "inputs larger than L2 (ratings 2 GB + P 0.5 GB per epoch vs 126 MB L2); no flush",
+                   "e2e_definition": f"recommender.buildModel() with num.max.iter={args.steps}: cars_create (schedule "
+                                     "+ H2D ratings) + cars_upload + epochs (loss D2H each) + cars_download"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st2.h2d_bytes / max(1, iters)),
+                "d2h_bytes_per_step": int(st2.d2h_bytes / max(1, iters)), "seconds": e2e_s, "epochs": iters,
+                "schedule_ms": st2.schedule_ms},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "sgd_wavefront_kernel", "kernel_ms_per_launch": kms,
+                     "algorithmic_bytes_per_update": B, "updates_per_launch": nnz_local, "peak_source": peak_src},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("CARS_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, args.workload, rank, world)
+    else:
+        if world != args.gpus and world == 1 and args.gpus > 1:
+            raise SystemExit(f"bench.py --gpus {args.gpus} must be launched with torchrun (one process per GPU)")
+        run_b200(args, wl, args.workload, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

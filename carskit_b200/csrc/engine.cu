@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -88,39 +89,55 @@ static cudaError_t dev_alloc(T** p, size_t n) {
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch: model x (lanes per rating, chunks per lane) chosen from num_factors
 // ------------------------------------------------------------------------------------------------
-static constexpr int kThreads = 512;
-
+// Launch shape of the wavefront kernel: threads per CTA x co-resident CTAs per SM (register cap).
+// Variant 0 is the default; CARS_WF_VARIANT selects another one (tuning knob).
 struct LaunchPlan {
   const void* fn = nullptr;
-  int lpr = 0, v = 0;
+  int lpr = 0, v = 0, threads = 0;
 };
 
-template <int MODEL>
-static LaunchPlan pick_wavefront(int Fp) {
+template <int MODEL, int THREADS, int MINB>
+static LaunchPlan pick_wavefront_shape(int Fp) {
   LaunchPlan p;
+  p.threads = THREADS;
   if (Fp <= 16) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 1, kThreads>; p.lpr = 8; p.v = 1;
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 1, THREADS, MINB>; p.lpr = 8; p.v = 1;
   } else if (Fp <= 32) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 2, kThreads>; p.lpr = 8; p.v = 2;
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 2, THREADS, MINB>; p.lpr = 8; p.v = 2;
   } else if (Fp <= 64) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 4, kThreads>; p.lpr = 8; p.v = 4;
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 4, THREADS, MINB>; p.lpr = 8; p.v = 4;
   } else if (Fp <= 128) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 16, 4, kThreads>; p.lpr = 16; p.v = 4;
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 16, 4, THREADS, MINB>; p.lpr = 16; p.v = 4;
   } else if (Fp <= 256) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 32, 4, kThreads>; p.lpr = 32; p.v = 4;
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 32, 4, THREADS, MINB>; p.lpr = 32; p.v = 4;
   } else if (Fp <= 512) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 32, 8, kThreads>; p.lpr = 32; p.v = 8;
+    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 32, 8, THREADS, MINB>; p.lpr = 32; p.v = 8;
   }
   return p;
 }
 
+template <int MODEL>
+static LaunchPlan pick_wavefront(int Fp, int variant) {
+  switch (variant) {
+    case 1: return pick_wavefront_shape<MODEL, 512, 2>(Fp);
+    case 2: return pick_wavefront_shape<MODEL, 256, 3>(Fp);
+    default: return pick_wavefront_shape<MODEL, 512, 1>(Fp);
+  }
+}
+
+static int wavefront_variant() {
+  const char* e = getenv("CARS_WF_VARIANT");
+  return e ? atoi(e) : 0;
+}
+
 static LaunchPlan pick_plan(int model, int /*mode*/, int Fp) {
+  const int v = wavefront_variant();
   switch (model) {
-    case CARS_PMF: return pick_wavefront<M_PMF>(Fp);
-    case CARS_BIASEDMF: return pick_wavefront<M_BIASEDMF>(Fp);
+    case CARS_PMF: return pick_wavefront<M_PMF>(Fp, v);
+    case CARS_BIASEDMF: return pick_wavefront<M_BIASEDMF>(Fp, v);
     case CARS_CAMF_C: return LaunchPlan{};  // every rating touches condBias: serial kernel only
-    case CARS_CAMF_CI: return pick_wavefront<M_CAMF_CI>(Fp);
-    case CARS_CAMF_CU: return pick_wavefront<M_CAMF_CU>(Fp);
+    case CARS_CAMF_CI: return pick_wavefront<M_CAMF_CI>(Fp, v);
+    case CARS_CAMF_CU: return pick_wavefront<M_CAMF_CU>(Fp, v);
   }
   return LaunchPlan{};
 }
@@ -339,11 +356,11 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     LaunchPlan plan = pick_plan(model, desc->mode, Fp);
     if (!plan.fn) { fail(h, CARS_E_UNSUPPORTED, "no kernel for model %d mode %d F %d", model, desc->mode, F); return bail(CARS_E_UNSUPPORTED); }
     const int G = 32 / plan.lpr;
-    h->block = kThreads;
-    h->smem = (size_t)(kThreads / 32) * G * (Fp + 2) * 8;
+    h->block = plan.threads;
+    h->smem = (size_t)(plan.threads / 32) * G * (Fp + 2) * 8;
     CUDA_TRY_H(cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     int per_sm = 0;
-    CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, kThreads, h->smem));
+    CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, plan.threads, h->smem));
     if (per_sm < 1) { fail(h, CARS_E_CUDA, "SGD kernel does not fit on an SM (smem %zu)", h->smem); return bail(CARS_E_CUDA); }
     h->grid = h->sm_count * per_sm;
   }

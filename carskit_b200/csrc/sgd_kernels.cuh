@@ -266,8 +266,8 @@ __device__ __forceinline__ double rating_update(const DeviceModel& m, int u, int
 // barrier separates levels.  Launched cooperatively with one CTA per SM slot.
 // block_partial[blockIdx.x] receives the CTA's loss partial (reduced in fixed order by K3).
 // ------------------------------------------------------------------------------------------------
-template <int MODEL, int LPR, int V, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int MODEL, int LPR, int V, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
     sgd_wavefront_kernel(DeviceModel m, RatingStream s, double lr, unsigned* barrier_counter,
                          double* block_partial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -1,0 +1,320 @@
+"""Host-side mirror of the reference's recommender classes for the SGD hot path.
+
+The reference is Java and no JVM exists in this image, so the host side above the C ABI is written
+here with the reference's own names, argument meaning and call order:
+
+    Recommender.execute()              src/carskit/generic/Recommender.java:319-357
+      initModel() -> buildModel() -> evalRatings()
+    IterativeRecommender               src/carskit/generic/IterativeRecommender.java:36-108 (hyper-parameters),
+      isConverged(iter)                :145-199
+      updateLRate(iter)                :216-229
+    PMF / BiasedMF                     src/carskit/alg/baseline/cf/{PMF,BiasedMF}.java
+    CAMF_C / CAMF_CI / CAMF_CU         src/carskit/alg/cars/adaptation/dependent/dev/*.java
+
+Only buildModel() differs from the reference: instead of the per-rating Java loop it flattens the
+containers once and drives `cars_epoch` (include/carskit_b200.h) once per iteration, keeping
+isConverged()/updateLRate() on the host exactly as a Java subclass would.  Nothing in
+this module computes a rating update; without libcarskit_b200.so and an sm_100 device it raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import capi
+from .capi import TrainingSet
+
+
+def _f32(x) -> float:
+    return float(np.float32(x))
+
+
+class LineConfiger:
+    """`happy.coding.io.LineConfiger`: "main -opt v1 -flag ..." split on [,\\t ]; the first token that is
+    not an option is the main parameter."""
+
+    def __init__(self, line: str):
+        toks = [t for t in line.replace(",", " ").replace("\t", " ").split(" ") if t]
+        self.main: Optional[str] = None
+        self.opts: Dict[str, list] = {}
+        cur = None
+        for t in toks:
+            if t.startswith("-") and not _is_number(t):
+                cur = t
+                self.opts.setdefault(cur, [])
+            elif cur is None:
+                if self.main is None:
+                    self.main = t
+            else:
+                self.opts[cur].append(t)
+
+    def getMainParam(self) -> Optional[str]:
+        return self.main
+
+    def contains(self, key: str) -> bool:
+        return key in self.opts
+
+    def getFloat(self, key: str, default: float) -> float:
+        v = self.opts.get(key)
+        return _f32(v[0]) if v else _f32(default)
+
+    def getString(self, key: str, default: Optional[str] = None) -> Optional[str]:
+        v = self.opts.get(key)
+        return v[0] if v else default
+
+
+def _is_number(t: str) -> bool:
+    try:
+        float(t)
+        return True
+    except ValueError:
+        return False
+
+
+DEFAULT_CONF = {  # setting.conf:52-59
+    "num.factors": "10",
+    "num.max.iter": "100",
+    "learn.rate": "2e-2 -max -1 -bold-driver",
+    "reg.lambda": "0.0001 -c 0.001",
+    "evaluation.setup": "test-set --test-view all",
+}
+
+
+class IterativeRecommender:
+    """Hyper-parameters are Java *floats* widened to double at every use
+    (IterativeRecommender.java:36-49): 0.02f -> 0.019999999552965164."""
+
+    MODEL = capi.PMF
+    algoName = "IterativeRecommender"
+
+    def __init__(self, trainMatrix: TrainingSet, testMatrix: Optional[dict] = None, fold: int = -1,
+                 conf: Optional[Dict[str, str]] = None, device: int = 0, stream: int = 0):
+        cf = dict(DEFAULT_CONF)
+        cf.update(conf or {})
+        self.cf = cf
+        self.trainMatrix, self.testMatrix, self.fold = trainMatrix, testMatrix, fold
+        self.device, self.stream = device, stream
+        self.numUsers, self.numItems = trainMatrix.num_users, trainMatrix.num_items
+        self.numConditions = trainMatrix.num_conditions
+        self.globalMean = trainMatrix.global_mean  # Recommender.java:265
+
+        lc = LineConfiger(cf["learn.rate"])  # :83-90
+        self.initLRate = _f32(lc.getMainParam())
+        self.maxLRate = lc.getFloat("-max", -1)
+        self.isBoldDriver = lc.contains("-bold-driver")
+        self.decay = lc.getFloat("-decay", -1)
+        ro = LineConfiger(cf["reg.lambda"])  # :92-99
+        self.reg = _f32(ro.getMainParam())
+        self.regU = ro.getFloat("-u", self.reg)
+        self.regI = ro.getFloat("-i", self.reg)
+        self.regB = ro.getFloat("-b", self.reg)
+        self.regC = ro.getFloat("-c", self.reg)
+        self.numFactors = int(cf["num.factors"])  # :101
+        self.numIters = int(cf["num.max.iter"])  # :102
+        ev = LineConfiger(cf["evaluation.setup"])
+        self.earlyStopMeasure = ev.getString("--early-stop")  # Recommender.java:221-229
+        self.minRate = float(cf.get("rating.min", 1.0))  # rateDao.getRatingScale(), Recommender.java:196-198
+        self.maxRate = float(cf.get("rating.max", 5.0))
+        self.initMean, self.initStd = 0.0, 0.1  # Recommender.java:203-204
+
+        self.lRate = float(self.initLRate)  # :106
+        self.loss = 0.0
+        self.last_loss = 0.0
+        self.measure = 0.0
+        self.last_measure = 0.0
+        self.verbose = False
+        self.model: Dict[str, np.ndarray] = {}
+        self.engine: Optional[capi.Engine] = None
+        self.iter_losses = []
+        self.measures: Dict[str, float] = {}
+
+    # ---- model members ---------------------------------------------------------------------------
+    def initModel(self, init: Optional[Dict[str, np.ndarray]] = None, seed: int = 0):
+        """IterativeRecommender.initModel (:231-247) + the subclass' initModel.  `init` hands over arrays
+        produced elsewhere (what a JNI subclass receives from Java).  Otherwise P, Q and the bias
+        vectors are drawn N(initMean, initStd) and icBias/ucBias U(0,1) (CAMF_CI.java:55-60); the
+        reference's own generator is wall-clock seeded, so any generator is faithful."""
+        shapes = capi.member_shapes(self.MODEL, self.numUsers, self.numItems, self.numConditions, self.numFactors)
+        if init is not None:
+            for k, s in shapes.items():
+                a = np.ascontiguousarray(init[k], dtype=np.float64)
+                if a.shape != tuple(s):
+                    raise ValueError(f"{k}: shape {a.shape} != {s}")
+                self.model[k] = a
+            return
+        rng = np.random.default_rng(seed)
+        for k, s in shapes.items():
+            if k in ("ic_bias", "uc_bias"):
+                self.model[k] = rng.random(s)
+            else:
+                self.model[k] = self.initMean + self.initStd * rng.standard_normal(s)
+
+    # ---- epoch control (host, unchanged semantics) --------------------------------------------------
+    def updateLRate(self, iter: int):
+        """IterativeRecommender.java:216-229."""
+        if self.lRate <= 0:
+            return
+        if self.isBoldDriver and iter > 1:
+            self.lRate = self.lRate * 1.05 if abs(self.last_loss) > abs(self.loss) else self.lRate * 0.5
+        elif 0 < self.decay < 1:
+            self.lRate *= self.decay
+        if self.maxLRate > 0 and self.lRate > self.maxLRate:
+            self.lRate = self.maxLRate
+
+    def isConverged(self, iter: int) -> bool:
+        """IterativeRecommender.java:145-199 (the debug print is kept behind `verbose`)."""
+        delta_loss = _f32(self.last_loss - self.loss)
+        if self.earlyStopMeasure is not None:
+            if self.earlyStopMeasure.lower() == "loss":
+                self.measure, self.last_measure = self.loss, self.last_loss
+            else:
+                self.measure = self.evalRatings()[self.earlyStopMeasure.upper()]
+        delta_measure = _f32(self.last_measure - self.measure)
+        if self.verbose:
+            print(f"{self.algoName} iter {iter}: loss = {_f32(self.loss)}, delta_loss = {delta_loss}, "
+                  f"learn_rate = {_f32(self.lRate)}")
+        if math.isnan(self.loss) or math.isinf(self.loss):
+            # the reference calls System.exit(-1) here (:181-184); a library raises instead
+            raise FloatingPointError("Loss = NaN or Infinity: current settings does not fit the recommender!")
+        cond1 = abs(self.loss) < 1e-5
+        cond2 = (delta_measure > 0) and (delta_measure < 1e-5)
+        converged = cond1 or cond2
+        if not converged:
+            self.updateLRate(iter)
+        self.last_loss = self.loss
+        self.last_measure = self.measure
+        return converged
+
+    # ---- the hot path ---------------------------------------------------------------------------------
+    def _desc(self):
+        return capi.make_desc(self.trainMatrix, self.MODEL, self.numFactors, device=self.device,
+                              reg_u=self.regU, reg_i=self.regI, reg_b=self.regB, reg_c=self.regC,
+                              stream=self.stream)
+
+    def open_engine(self) -> capi.Engine:
+        """cars_create + cars_upload: what buildModel() does before its first iteration."""
+        if not self.model:
+            raise RuntimeError("buildModel before initModel")
+        eng = capi.Engine(self._desc(), keepalive=self.trainMatrix)
+        try:
+            eng.upload(self.model)
+        except Exception:
+            eng.close()
+            raise
+        self.engine = eng
+        return eng
+
+    def train_epoch(self, iter: int) -> bool:
+        """One iteration of the `for (int iter = 1; ...)` loop (CAMF_CI.java:77-128): the per-rating pass on
+        the device, then isConverged(iter) on the host.  Returns isConverged's verdict."""
+        self.loss = self.engine.epoch(self.lRate)
+        self.iter_losses.append(self.loss)
+        return self.isConverged(iter)
+
+    def close_engine(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
+
+    def buildModel(self):
+        """Replaces the per-rating loop of buildModel() (CAMF_CI.java:74-131 and siblings): flatten once,
+        one cars_epoch per iteration, isConverged() on the host, copy the model back."""
+        self.iter_losses = []
+        eng = self.open_engine()
+        try:
+            for it in range(1, self.numIters + 1):
+                if self.train_epoch(it):
+                    break
+            eng.download(self.model)
+            self.stats = eng.stats()
+        finally:
+            if not getattr(self, "keep_engine", False):
+                self.close_engine()
+
+    # ---- consumers of the trained model ------------------------------------------------------------------
+    def _eval_engine(self) -> capi.Engine:
+        if self.engine is not None:
+            return self.engine
+        eng = capi.Engine(self._desc_for_predict(), keepalive=self.trainMatrix)
+        eng.upload(self.model)
+        return eng
+
+    def _desc_for_predict(self):
+        # an engine without training ratings: predict()/evalRatings() only need the model
+        ts = self.trainMatrix
+        empty = TrainingSet(num_users=ts.num_users, num_items=ts.num_items, u=np.empty(0, np.int32),
+                            j=np.empty(0, np.int32), r=np.empty(0, np.float64),
+                            ctx=None if ts.ctx is None else np.empty(0, np.int32),
+                            num_conditions=ts.num_conditions, num_contexts=ts.num_contexts, ctx_ptr=ts.ctx_ptr,
+                            ctx_cond=ts.ctx_cond, global_mean=ts.global_mean)
+        self._empty_keep = empty
+        return capi.make_desc(empty, self.MODEL, self.numFactors, device=self.device, reg_u=self.regU,
+                              reg_i=self.regI, reg_b=self.regB, reg_c=self.regC)
+
+    def predict(self, u, j, c=None, bound: bool = False) -> np.ndarray:
+        """Recommender.predict(u, j, c, bound) (Recommender.java:306-317), batched."""
+        eng = self._eval_engine()
+        try:
+            return eng.predict(u, j, c, bound=bound, min_rate=self.minRate, max_rate=self.maxRate)
+        finally:
+            if eng is not self.engine:
+                eng.close()
+
+    def evalRatings(self) -> Dict[str, float]:
+        """Recommender.evalRatings (:504-594): MAE / RMSE over testMatrix with bounded predictions."""
+        t = self.testMatrix
+        if t is None or len(t["u"]) == 0:
+            return {"MAE": float("nan"), "RMSE": float("nan")}
+        eng = self._eval_engine()
+        try:
+            sa, ss = eng.eval_ratings(t["u"], t["j"], t.get("ctx"), t["r"], self.minRate, self.maxRate)
+        finally:
+            if eng is not self.engine:
+                eng.close()
+        n = len(t["u"])
+        return {"MAE": sa / n, "RMSE": math.sqrt(ss / n)}
+
+    def execute(self, init: Optional[Dict[str, np.ndarray]] = None, seed: int = 0) -> Dict[str, float]:
+        """Recommender.execute (:319-357): initModel -> buildModel -> evalRatings."""
+        self.initModel(init, seed)
+        self.keep_engine = True
+        try:
+            self.buildModel()
+            self.measures = self.evalRatings()
+        finally:
+            self.keep_engine = False
+            if self.engine is not None:
+                self.engine.close()
+                self.engine = None
+        return self.measures
+
+
+class PMF(IterativeRecommender):
+    MODEL, algoName = capi.PMF, "PMF"
+
+
+class BiasedMF(IterativeRecommender):
+    MODEL, algoName = capi.BIASEDMF, "BiasedMF"
+
+
+class CAMF_C(IterativeRecommender):
+    MODEL, algoName = capi.CAMF_C, "CAMF_C"
+
+
+class CAMF_CI(IterativeRecommender):
+    MODEL, algoName = capi.CAMF_CI, "CAMF_CI"
+
+
+class CAMF_CU(IterativeRecommender):
+    MODEL, algoName = capi.CAMF_CU, "CAMF_CU"
+
+
+def getRecommender(name: str):
+    """The `switch` of CARSKit.getRecommender (src/carskit/main/CARSKit.java:429-705) for this path."""
+    table = {"pmf": PMF, "biasedmf": BiasedMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU}
+    try:
+        return table[name.lower()]
+    except KeyError:
+        raise ValueError(f"recommender '{name}' is not on the B200 hot path") from None
