@@ -15,6 +15,7 @@ import numpy as np
 ABI_VERSION = 1
 PMF, BIASEDMF, CAMF_C, CAMF_CI, CAMF_CU, FM = range(6)
 EXACT, FAST = 0, 1
+SCHED_DATAFLOW, SCHED_WAVEFRONT, SCHED_FLAGGED = 0, 1, 2
 MODEL_NAMES = {"pmf": PMF, "biasedmf": BIASEDMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -28,7 +29,7 @@ class CarsDesc(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("model", C.c_int32), ("mode", C.c_int32), ("device", C.c_int32),
         ("num_users", C.c_int32), ("num_items", C.c_int32), ("num_conditions", C.c_int32),
-        ("num_contexts", C.c_int32), ("num_factors", C.c_int32), ("reserved0", C.c_int32),
+        ("num_contexts", C.c_int32), ("num_factors", C.c_int32), ("schedule", C.c_int32),
         ("nnz", C.c_int64),
         ("u", _i32p), ("j", _i32p), ("ctx", _i32p), ("r", _f64p), ("ctx_ptr", _i32p), ("ctx_cond", _i32p),
         ("global_mean", C.c_double),
@@ -164,11 +165,12 @@ class TrainingSet:
 def make_desc(ts: TrainingSet, model: int, num_factors: int, *, mode: int = EXACT, device: int = 0,
               reg_u: float = 0.0, reg_i: float = 0.0, reg_b: float = 0.0, reg_c: float = 0.0,
               reg_lw: float = 0.0, reg_lf: float = 0.0, rank: int = 0, world_size: int = 1,
-              stream: int = 0) -> CarsDesc:
+              stream: int = 0, schedule: int = SCHED_DATAFLOW) -> CarsDesc:
     """Fill a cars_desc.  The reg_* values must already be float-widened (use f32())."""
     d = CarsDesc()
     d.abi_version = ABI_VERSION
     d.model, d.mode, d.device = model, mode, device
+    d.schedule = schedule
     d.num_users, d.num_items = ts.num_users, ts.num_items
     d.num_conditions, d.num_contexts = ts.num_conditions, ts.num_contexts
     d.num_factors = num_factors

@@ -46,7 +46,16 @@ struct cars_handle {
   double* d_r = nullptr;
   int64_t* d_level_start = nullptr;
   int64_t num_levels = 0, max_level_size = 0;
-  bool serial = false;  // CAMF_C exact: reference order, one warp
+  bool serial = false;    // CAMF_C exact: reference order, one warp
+  bool dataflow = false;  // default schedule: reference order + per-user / per-item completion counters
+  bool flagged = false;   // level order + completion counters (no barriers)
+  RatingRec* d_rec = nullptr;
+  int64_t* d_chunk_start = nullptr;
+  double* d_chunk_loss = nullptr;
+  unsigned* d_flags = nullptr;  // [counter (pad to 64 u32) | done_j | done_u]
+  size_t flags_words = 0;
+  int64_t num_chunks = 0;
+  int loss_blocks = 0;
 
   // kernel plumbing
   unsigned* d_barrier = nullptr;
@@ -138,6 +147,86 @@ static LaunchPlan pick_plan(int model, int /*mode*/, int Fp) {
     case CARS_CAMF_C: return LaunchPlan{};  // every rating touches condBias: serial kernel only
     case CARS_CAMF_CI: return pick_wavefront<M_CAMF_CI>(Fp, v);
     case CARS_CAMF_CU: return pick_wavefront<M_CAMF_CU>(Fp, v);
+  }
+  return LaunchPlan{};
+}
+
+template <int MODEL, int THREADS, int MINB>
+static LaunchPlan pick_dataflow_shape(int Fp) {
+  LaunchPlan p;
+  p.threads = THREADS;
+  if (Fp <= 16) {
+    p.fn = (const void*)sgd_dataflow_kernel<MODEL, 8, 1, THREADS, MINB>; p.lpr = 8; p.v = 1;
+  } else if (Fp <= 32) {
+    p.fn = (const void*)sgd_dataflow_kernel<MODEL, 8, 2, THREADS, MINB>; p.lpr = 8; p.v = 2;
+  } else if (Fp <= 64) {
+    p.fn = (const void*)sgd_dataflow_kernel<MODEL, 8, 4, THREADS, MINB>; p.lpr = 8; p.v = 4;
+  } else if (Fp <= 128) {
+    p.fn = (const void*)sgd_dataflow_kernel<MODEL, 16, 4, THREADS, MINB>; p.lpr = 16; p.v = 4;
+  } else if (Fp <= 256) {
+    p.fn = (const void*)sgd_dataflow_kernel<MODEL, 32, 4, THREADS, MINB>; p.lpr = 32; p.v = 4;
+  } else if (Fp <= 512) {
+    p.fn = (const void*)sgd_dataflow_kernel<MODEL, 32, 8, THREADS, MINB>; p.lpr = 32; p.v = 8;
+  }
+  return p;
+}
+
+template <int MODEL>
+static LaunchPlan pick_dataflow(int Fp, int variant) {
+  switch (variant) {
+    case 1: return pick_dataflow_shape<MODEL, 512, 2>(Fp);
+    case 2: return pick_dataflow_shape<MODEL, 256, 3>(Fp);
+    default: return pick_dataflow_shape<MODEL, 512, 1>(Fp);
+  }
+}
+
+template <int MODEL, int THREADS, int MINB>
+static LaunchPlan pick_flagged_shape(int Fp) {
+  LaunchPlan p;
+  p.threads = THREADS;
+  if (Fp <= 16) {
+    p.fn = (const void*)sgd_flagged_kernel<MODEL, 8, 1, THREADS, MINB>; p.lpr = 8; p.v = 1;
+  } else if (Fp <= 32) {
+    p.fn = (const void*)sgd_flagged_kernel<MODEL, 8, 2, THREADS, MINB>; p.lpr = 8; p.v = 2;
+  } else if (Fp <= 64) {
+    p.fn = (const void*)sgd_flagged_kernel<MODEL, 8, 4, THREADS, MINB>; p.lpr = 8; p.v = 4;
+  } else if (Fp <= 128) {
+    p.fn = (const void*)sgd_flagged_kernel<MODEL, 16, 4, THREADS, MINB>; p.lpr = 16; p.v = 4;
+  } else if (Fp <= 256) {
+    p.fn = (const void*)sgd_flagged_kernel<MODEL, 32, 4, THREADS, MINB>; p.lpr = 32; p.v = 4;
+  } else if (Fp <= 512) {
+    p.fn = (const void*)sgd_flagged_kernel<MODEL, 32, 8, THREADS, MINB>; p.lpr = 32; p.v = 8;
+  }
+  return p;
+}
+
+template <int MODEL>
+static LaunchPlan pick_flagged(int Fp, int variant) {
+  switch (variant) {
+    case 1: return pick_flagged_shape<MODEL, 512, 2>(Fp);
+    case 2: return pick_flagged_shape<MODEL, 256, 3>(Fp);
+    default: return pick_flagged_shape<MODEL, 512, 1>(Fp);
+  }
+}
+
+static LaunchPlan pick_flagged_plan(int model, int Fp) {
+  const int v = wavefront_variant();
+  switch (model) {
+    case CARS_PMF: return pick_flagged<M_PMF>(Fp, v);
+    case CARS_BIASEDMF: return pick_flagged<M_BIASEDMF>(Fp, v);
+    case CARS_CAMF_CI: return pick_flagged<M_CAMF_CI>(Fp, v);
+    case CARS_CAMF_CU: return pick_flagged<M_CAMF_CU>(Fp, v);
+  }
+  return LaunchPlan{};
+}
+
+static LaunchPlan pick_dataflow_plan(int model, int Fp) {
+  const int v = wavefront_variant();
+  switch (model) {
+    case CARS_PMF: return pick_dataflow<M_PMF>(Fp, v);
+    case CARS_BIASEDMF: return pick_dataflow<M_BIASEDMF>(Fp, v);
+    case CARS_CAMF_CI: return pick_dataflow<M_CAMF_CI>(Fp, v);
+    case CARS_CAMF_CU: return pick_dataflow<M_CAMF_CU>(Fp, v);
   }
   return LaunchPlan{};
 }
@@ -289,47 +378,148 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     }
   }
 
+  // ---- launch geometry (the dataflow schedule sizes its chunks from the number of resident groups) ------
+  const int model = desc->model;
+  h->serial = (model == CARS_CAMF_C);
+  int sched = desc->schedule;
+  if (const char* e = getenv("CARS_SCHEDULE"))
+    sched = strcmp(e, "wavefront") == 0 ? CARS_SCHED_WAVEFRONT : strcmp(e, "flagged") == 0 ? CARS_SCHED_FLAGGED : CARS_SCHED_DATAFLOW;
+  if (sched != CARS_SCHED_DATAFLOW && sched != CARS_SCHED_WAVEFRONT && sched != CARS_SCHED_FLAGGED) {
+    fail(h, CARS_E_INVALID, "unknown schedule %d", sched);
+    return bail(CARS_E_INVALID);
+  }
+  h->dataflow = !h->serial && sched == CARS_SCHED_DATAFLOW;
+  h->flagged = !h->serial && sched == CARS_SCHED_FLAGGED;
+  int groups_per_cta = 1;
+  if (h->serial) {
+    h->grid = 1; h->block = 32;
+    h->smem = (size_t)(Fp + 2) * 8;
+  } else {
+    LaunchPlan plan = h->dataflow ? pick_dataflow_plan(model, Fp)
+                      : h->flagged ? pick_flagged_plan(model, Fp) : pick_plan(model, desc->mode, Fp);
+    if (!plan.fn) { fail(h, CARS_E_UNSUPPORTED, "no kernel for model %d mode %d F %d", model, desc->mode, F); return bail(CARS_E_UNSUPPORTED); }
+    const int G = 32 / plan.lpr;
+    groups_per_cta = (plan.threads / 32) * G;
+    h->block = plan.threads;
+    h->smem = (size_t)groups_per_cta * (Fp + 2) * 8;
+    CUDA_TRY_H(cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    int per_sm = 0;
+    CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, plan.threads, h->smem));
+    if (per_sm < 1) { fail(h, CARS_E_CUDA, "SGD kernel does not fit on an SM (smem %zu)", h->smem); return bail(CARS_E_CUDA); }
+    h->grid = h->sm_count * per_sm;
+  }
+
   // ---- schedule ----------------------------------------------------------------------------------------
   auto t0 = std::chrono::steady_clock::now();
-  h->serial = (desc->model == CARS_CAMF_C);
   h->nnz = nnz;
-  std::vector<int64_t> level_start;
-  HostSchedule sched;
-  const int32_t* su = desc->u;
-  const int32_t* sj = desc->j;
-  const int32_t* sc = desc->ctx;
-  const double* sr = desc->r;
-  if (!h->serial) {
-    if (!build_wavefront_schedule(desc->num_users, desc->num_items, nnz, desc->u, desc->j, has_ctx ? desc->ctx : nullptr,
-                                  desc->r, &sched)) {
+  const size_t U = desc->num_users, I = desc->num_items, C = desc->num_conditions;
+  if (h->dataflow) {
+    // K7d: reference order is kept; every rating learns its position in its user's and its item's chain,
+    // and the stream is cut into chunks (at user changes) that the kernel hands out in order.
+    std::vector<RatingRec> recs;
+    std::vector<int64_t> chunk_start;
+    int64_t max_chunk = 0;
+    try {
+      recs.resize((size_t)nnz);
+      std::vector<uint32_t> cu(U, 0u), cj(I, 0u);
+      const int64_t total_groups = (int64_t)h->grid * groups_per_cta;
+      int64_t lmin = nnz / (4 * total_groups);
+      lmin = lmin < 1 ? 1 : (lmin > 64 ? 64 : lmin);
+      chunk_start.reserve((size_t)(nnz / lmin + 2));
+      int64_t cur = 0;
+      for (int64_t n = 0; n < nnz; n++) {
+        const int32_t uu = desc->u[n], jj = desc->j[n];
+        if (n == 0) {
+          chunk_start.push_back(0);
+        } else if (uu != desc->u[n - 1] && n - cur >= lmin) {
+          if (n - cur > max_chunk) max_chunk = n - cur;
+          chunk_start.push_back(n);
+          cur = n;
+        }
+        RatingRec& x = recs[(size_t)n];
+        x.u = uu; x.j = jj; x.ctx = has_ctx ? desc->ctx[n] : 0;
+        x.ku = (int32_t)cu[uu]++; x.kj = (int32_t)cj[jj]++; x.pad = 0; x.r = desc->r[n];
+      }
+      if (nnz - cur > max_chunk) max_chunk = nnz - cur;
+      chunk_start.push_back(nnz);
+    } catch (...) {
       fail(h, CARS_E_OOM, "host allocation failed while building the schedule");
       return bail(CARS_E_OOM);
     }
-    su = sched.u.data(); sj = sched.j.data(); sc = has_ctx ? sched.ctx.data() : nullptr; sr = sched.r.data();
-    h->num_levels = (int64_t)sched.level_start.size() - 1;
-    h->max_level_size = sched.max_level_size;
+    h->num_chunks = nnz ? (int64_t)chunk_start.size() - 1 : 0;
+    h->num_levels = h->num_chunks;
+    h->max_level_size = max_chunk;
+    h->st.schedule_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    CUDA_TRY_H(dev_alloc(&h->d_rec, (size_t)nnz));
+    CUDA_TRY_H(dev_alloc(&h->d_chunk_start, chunk_start.size()));
+    CUDA_TRY_H(dev_alloc(&h->d_chunk_loss, (size_t)h->num_chunks));
+    h->flags_words = 64 + I + U;
+    CUDA_TRY_H(dev_alloc(&h->d_flags, h->flags_words));
+    if (nnz) {
+      CUDA_TRY_H(cudaMemcpyAsync(h->d_rec, recs.data(), (size_t)nnz * sizeof(RatingRec), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY_H(cudaMemcpyAsync(h->d_chunk_start, chunk_start.data(), chunk_start.size() * 8, cudaMemcpyHostToDevice, h->stream));
+      h->st.h2d_bytes += nnz * (int64_t)sizeof(RatingRec) + (int64_t)chunk_start.size() * 8;
+    }
+    h->loss_blocks = (int)((h->num_chunks + 1023) / 1024);
+    if (h->loss_blocks < 1) h->loss_blocks = 1;
+    if (h->loss_blocks > 1024) h->loss_blocks = 1024;
+    CUDA_TRY_H(cudaStreamSynchronize(h->stream));  // recs / chunk_start die at the end of this block
+  } else if (h->flagged) {
+    std::vector<RatingRec> recs;
+    if (!build_flagged_schedule(desc->num_users, desc->num_items, nnz, desc->u, desc->j, has_ctx ? desc->ctx : nullptr,
+                                desc->r, &recs, &h->num_levels, &h->max_level_size)) {
+      fail(h, CARS_E_OOM, "host allocation failed while building the schedule");
+      return bail(CARS_E_OOM);
+    }
+    h->st.schedule_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    CUDA_TRY_H(dev_alloc(&h->d_rec, (size_t)nnz));
+    h->flags_words = 64 + I + U;
+    CUDA_TRY_H(dev_alloc(&h->d_flags, h->flags_words));
+    if (nnz) {
+      CUDA_TRY_H(cudaMemcpyAsync(h->d_rec, recs.data(), (size_t)nnz * sizeof(RatingRec), cudaMemcpyHostToDevice, h->stream));
+      h->st.h2d_bytes += nnz * (int64_t)sizeof(RatingRec);
+    }
+    CUDA_TRY_H(cudaStreamSynchronize(h->stream));
   } else {
-    h->num_levels = nnz;  // every rating is its own level
-    h->max_level_size = nnz ? 1 : 0;
-  }
-  h->st.schedule_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::vector<int64_t> level_start;
+    HostSchedule sched_host;
+    const int32_t* su = desc->u;
+    const int32_t* sj = desc->j;
+    const int32_t* sc = desc->ctx;
+    const double* sr = desc->r;
+    if (!h->serial) {
+      if (!build_wavefront_schedule(desc->num_users, desc->num_items, nnz, desc->u, desc->j, has_ctx ? desc->ctx : nullptr,
+                                    desc->r, &sched_host)) {
+        fail(h, CARS_E_OOM, "host allocation failed while building the schedule");
+        return bail(CARS_E_OOM);
+      }
+      su = sched_host.u.data(); sj = sched_host.j.data(); sc = has_ctx ? sched_host.ctx.data() : nullptr; sr = sched_host.r.data();
+      h->num_levels = (int64_t)sched_host.level_start.size() - 1;
+      h->max_level_size = sched_host.max_level_size;
+    } else {
+      h->num_levels = nnz;  // every rating is its own level
+      h->max_level_size = nnz ? 1 : 0;
+    }
+    h->st.schedule_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
-  CUDA_TRY_H(dev_alloc(&h->d_u, nnz));
-  CUDA_TRY_H(dev_alloc(&h->d_j, nnz));
-  CUDA_TRY_H(dev_alloc(&h->d_r, nnz));
-  if (has_ctx) CUDA_TRY_H(dev_alloc(&h->d_ctx, nnz));
-  if (nnz) {
-    CUDA_TRY_H(cudaMemcpyAsync(h->d_u, su, nnz * 4, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY_H(cudaMemcpyAsync(h->d_j, sj, nnz * 4, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY_H(cudaMemcpyAsync(h->d_r, sr, nnz * 8, cudaMemcpyHostToDevice, h->stream));
-    if (has_ctx) CUDA_TRY_H(cudaMemcpyAsync(h->d_ctx, sc, nnz * 4, cudaMemcpyHostToDevice, h->stream));
-    h->st.h2d_bytes += nnz * (has_ctx ? 20 : 16);
-  }
-  if (!h->serial) {
-    CUDA_TRY_H(dev_alloc(&h->d_level_start, sched.level_start.size()));
-    CUDA_TRY_H(cudaMemcpyAsync(h->d_level_start, sched.level_start.data(), sched.level_start.size() * 8,
-                               cudaMemcpyHostToDevice, h->stream));
-    h->st.h2d_bytes += (int64_t)sched.level_start.size() * 8;
+    CUDA_TRY_H(dev_alloc(&h->d_u, nnz));
+    CUDA_TRY_H(dev_alloc(&h->d_j, nnz));
+    CUDA_TRY_H(dev_alloc(&h->d_r, nnz));
+    if (has_ctx) CUDA_TRY_H(dev_alloc(&h->d_ctx, nnz));
+    if (nnz) {
+      CUDA_TRY_H(cudaMemcpyAsync(h->d_u, su, nnz * 4, cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY_H(cudaMemcpyAsync(h->d_j, sj, nnz * 4, cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY_H(cudaMemcpyAsync(h->d_r, sr, nnz * 8, cudaMemcpyHostToDevice, h->stream));
+      if (has_ctx) CUDA_TRY_H(cudaMemcpyAsync(h->d_ctx, sc, nnz * 4, cudaMemcpyHostToDevice, h->stream));
+      h->st.h2d_bytes += nnz * (has_ctx ? 20 : 16);
+    }
+    if (!h->serial) {
+      CUDA_TRY_H(dev_alloc(&h->d_level_start, sched_host.level_start.size()));
+      CUDA_TRY_H(cudaMemcpyAsync(h->d_level_start, sched_host.level_start.data(), sched_host.level_start.size() * 8,
+                                 cudaMemcpyHostToDevice, h->stream));
+      h->st.h2d_bytes += (int64_t)sched_host.level_start.size() * 8;
+    }
+    CUDA_TRY_H(cudaStreamSynchronize(h->stream));  // host staging vectors die at the end of this block
   }
 
   // ---- model storage ----------------------------------------------------------------------------------
@@ -338,8 +528,6 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   m.global_mean = desc->global_mean;
   m.reg_u = desc->reg_u; m.reg_i = desc->reg_i; m.reg_b = desc->reg_b; m.reg_c = desc->reg_c;
   m.ctx_tab = h->d_ctx_tab;
-  const int model = desc->model;
-  const size_t U = desc->num_users, I = desc->num_items, C = desc->num_conditions;
   CUDA_TRY_H(dev_alloc(&m.P, U * Fp));
   CUDA_TRY_H(dev_alloc(&m.Q, I * Fp));
   if (model == CARS_BIASEDMF || model == CARS_CAMF_C || model == CARS_CAMF_CI) CUDA_TRY_H(dev_alloc(&m.user_bias, U));
@@ -348,24 +536,8 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   if (model == CARS_CAMF_CI) CUDA_TRY_H(dev_alloc(&m.ic_bias, I * C));
   if (model == CARS_CAMF_CU) CUDA_TRY_H(dev_alloc(&m.uc_bias, U * C));
 
-  // ---- launch geometry -----------------------------------------------------------------------------------
-  if (h->serial) {
-    h->grid = 1; h->block = 32;
-    h->smem = (size_t)(Fp + 2) * 8;
-  } else {
-    LaunchPlan plan = pick_plan(model, desc->mode, Fp);
-    if (!plan.fn) { fail(h, CARS_E_UNSUPPORTED, "no kernel for model %d mode %d F %d", model, desc->mode, F); return bail(CARS_E_UNSUPPORTED); }
-    const int G = 32 / plan.lpr;
-    h->block = plan.threads;
-    h->smem = (size_t)(plan.threads / 32) * G * (Fp + 2) * 8;
-    CUDA_TRY_H(cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    int per_sm = 0;
-    CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, plan.threads, h->smem));
-    if (per_sm < 1) { fail(h, CARS_E_CUDA, "SGD kernel does not fit on an SM (smem %zu)", h->smem); return bail(CARS_E_CUDA); }
-    h->grid = h->sm_count * per_sm;
-  }
   CUDA_TRY_H(dev_alloc(&h->d_barrier, 1));
-  CUDA_TRY_H(dev_alloc(&h->d_partial, (size_t)h->grid));
+  CUDA_TRY_H(dev_alloc(&h->d_partial, (size_t)(h->grid > 1024 ? h->grid : 1024)));
   CUDA_TRY_H(dev_alloc(&h->d_loss, 1));
   CUDA_TRY_H(cudaMallocHost((void**)&h->h_loss, sizeof(double)));
   CUDA_TRY_H(cudaStreamSynchronize(h->stream));  // host staging vectors die at return
@@ -461,11 +633,39 @@ extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
   s.num_levels = (int32_t)h->num_levels;
   DeviceModel m = h->m;
   CUDA_TRY(h, cudaEventRecord(h->ev_beg, h->stream));
+  int partials = h->grid;
   if (h->serial) {
     const void* fn = pick_serial(h->d.model, m.Fp);
     int64_t nnz = h->nnz;
     void* args[] = {&m, &s, &nnz, &lrate, &h->d_partial};
     CUDA_TRY(h, cudaLaunchKernel(fn, dim3(1), dim3(32), args, h->smem, h->stream));
+    h->st.kernel_launches += 1;
+  } else if (h->dataflow) {
+    LaunchPlan plan = pick_dataflow_plan(h->d.model, m.Fp);
+    DataflowStream ds;
+    ds.rec = h->d_rec; ds.chunk_start = h->d_chunk_start; ds.chunk_loss = h->d_chunk_loss;
+    ds.counter = h->d_flags; ds.done_j = h->d_flags + 64; ds.done_u = h->d_flags + 64 + h->d.num_items;
+    ds.num_chunks = (uint32_t)h->num_chunks;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_flags, 0, h->flags_words * sizeof(unsigned), h->stream));
+    if (h->num_chunks > 0) {
+      void* args[] = {&m, &ds, &lrate};
+      CUDA_TRY(h, cudaLaunchKernel(plan.fn, dim3(h->grid), dim3(h->block), args, h->smem, h->stream));
+      h->st.kernel_launches += 1;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_end, h->stream));
+    chunk_loss_reduce_kernel<<<h->loss_blocks, 256, 0, h->stream>>>(h->d_chunk_loss, h->num_chunks, h->d_partial);
+    CUDA_TRY(h, cudaGetLastError());
+    h->st.kernel_launches += 1;
+    partials = h->loss_blocks;
+  } else if (h->flagged) {
+    LaunchPlan plan = pick_flagged_plan(h->d.model, m.Fp);
+    CUDA_TRY(h, cudaMemsetAsync(h->d_flags, 0, h->flags_words * sizeof(unsigned), h->stream));
+    const RatingRec* recs = h->d_rec;
+    int64_t nnz = h->nnz;
+    unsigned* done_j = h->d_flags + 64;
+    unsigned* done_u = h->d_flags + 64 + h->d.num_items;
+    void* args[] = {&m, &recs, &nnz, &done_u, &done_j, &lrate, &h->d_partial};
+    CUDA_TRY(h, cudaLaunchCooperativeKernel(plan.fn, dim3(h->grid), dim3(h->block), args, h->smem, h->stream));
     h->st.kernel_launches += 1;
   } else {
     LaunchPlan plan = pick_plan(h->d.model, h->d.mode, m.Fp);
@@ -474,8 +674,8 @@ extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
     CUDA_TRY(h, cudaLaunchCooperativeKernel(plan.fn, dim3(h->grid), dim3(h->block), args, h->smem, h->stream));
     h->st.kernel_launches += 1;
   }
-  CUDA_TRY(h, cudaEventRecord(h->ev_end, h->stream));
-  loss_finalize_kernel<<<1, 32, 0, h->stream>>>(h->d_partial, h->grid, h->d_loss);
+  if (!h->dataflow) CUDA_TRY(h, cudaEventRecord(h->ev_end, h->stream));
+  loss_finalize_kernel<<<1, 32, 0, h->stream>>>(h->d_partial, partials, h->d_loss);
   CUDA_TRY(h, cudaGetLastError());
   h->st.kernel_launches += 1;
   CUDA_TRY(h, cudaMemcpyAsync(h->h_loss, h->d_loss, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -596,6 +796,7 @@ extern "C" void cars_destroy(cars_handle* h) {
   cudaFree(h->d_u); cudaFree(h->d_j); cudaFree(h->d_ctx); cudaFree(h->d_r); cudaFree(h->d_level_start);
   cudaFree(h->m.P); cudaFree(h->m.Q); cudaFree(h->m.user_bias); cudaFree(h->m.item_bias);
   cudaFree(h->m.cond_bias); cudaFree(h->m.ic_bias); cudaFree(h->m.uc_bias);
+  cudaFree(h->d_rec); cudaFree(h->d_chunk_start); cudaFree(h->d_chunk_loss); cudaFree(h->d_flags);
   cudaFree(h->d_barrier); cudaFree(h->d_partial); cudaFree(h->d_loss);
   if (h->h_loss) cudaFreeHost(h->h_loss);
   if (h->ev_beg) cudaEventDestroy(h->ev_beg);

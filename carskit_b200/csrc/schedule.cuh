@@ -12,6 +12,8 @@
 #include <cstdint>
 #include <vector>
 
+#include "sgd_kernels.cuh"
+
 namespace cars {
 
 struct HostSchedule {
@@ -61,6 +63,46 @@ inline bool build_wavefront_schedule(int32_t num_users, int32_t num_items, int64
       out->r[pos] = r[n];
       if (ctx) out->ctx[pos] = ctx[n];
     }
+    return true;
+  } catch (...) {
+    return false;
+  }
+}
+
+// K7f: level-sorted records for the flagged wavefront (K1f): same order as build_wavefront_schedule,
+// each record carrying its position in its user's and its item's chain (counted in reference order).
+inline bool build_flagged_schedule(int32_t num_users, int32_t num_items, int64_t nnz, const int32_t* u,
+                                   const int32_t* j, const int32_t* ctx, const double* r,
+                                   std::vector<RatingRec>* out, int64_t* num_levels_out, int64_t* max_level_out) {
+  try {
+    std::vector<int32_t> last_u((size_t)num_users, 0), last_j((size_t)num_items, 0);
+    std::vector<uint32_t> cu((size_t)num_users, 0u), cj((size_t)num_items, 0u);
+    std::vector<int32_t> level((size_t)nnz), ku((size_t)nnz), kj((size_t)nnz);
+    int32_t num_levels = 0;
+    for (int64_t n = 0; n < nnz; n++) {
+      const int32_t a = last_u[u[n]], b = last_j[j[n]];
+      const int32_t l = 1 + (a > b ? a : b);
+      last_u[u[n]] = l;
+      last_j[j[n]] = l;
+      level[n] = l;
+      ku[n] = (int32_t)cu[u[n]]++;
+      kj[n] = (int32_t)cj[j[n]]++;
+      if (l > num_levels) num_levels = l;
+    }
+    std::vector<int64_t> start((size_t)num_levels + 2, 0);
+    for (int64_t n = 0; n < nnz; n++) start[level[n] + 1]++;
+    int64_t max_sz = 0;
+    for (int32_t l = 1; l <= num_levels + 1; l++) {
+      if (start[l] > max_sz) max_sz = start[l];
+      start[l] += start[l - 1];
+    }
+    out->resize((size_t)nnz);
+    for (int64_t n = 0; n < nnz; n++) {
+      RatingRec& x = (*out)[(size_t)start[level[n]]++];
+      x.u = u[n]; x.j = j[n]; x.ctx = ctx ? ctx[n] : 0; x.ku = ku[n]; x.kj = kj[n]; x.pad = 0; x.r = r[n];
+    }
+    *num_levels_out = num_levels;
+    *max_level_out = max_sz;
     return true;
   } catch (...) {
     return false;

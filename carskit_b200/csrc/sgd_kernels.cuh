@@ -44,6 +44,33 @@ struct RatingStream {
   int32_t num_levels;
 };
 
+// One training rating in the reference's iteration order, plus its position in the two dependency
+// chains it belongs to: ku / kj = number of EARLIER ratings (reference order) of the same user / item.
+struct __align__(16) RatingRec {
+  int32_t u, j, ctx, ku;
+  int32_t kj, pad;
+  double r;
+};
+static_assert(sizeof(RatingRec) == 32, "RatingRec must be 32 bytes");
+
+// Dataflow schedule (K1d): ratings stay in reference order, cut into chunks of consecutive ratings.
+struct DataflowStream {
+  const RatingRec* rec;        // [nnz]
+  const int64_t* chunk_start;  // [num_chunks + 1]
+  double* chunk_loss;          // [num_chunks]  loss partial of each chunk (deterministic final reduce)
+  unsigned* done_u;            // [num_users]   ratings of user u completed this epoch
+  unsigned* done_j;            // [num_items]   ratings of item j completed this epoch
+  unsigned* counter;           // next chunk to hand out
+  uint32_t num_chunks;
+};
+
+// User-side state a group keeps in registers while consecutive ratings share the user.
+template <int V>
+struct UserRegs {
+  double2 p[V];
+  double bu;
+};
+
 // ------------------------------------------------------------------------------------------------
 // small PTX helpers
 // ------------------------------------------------------------------------------------------------
@@ -68,6 +95,13 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -104,32 +138,38 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
 // ------------------------------------------------------------------------------------------------
 // One rating update by one group of LPR lanes.  V = 16-byte chunks per lane (LPR * V * 2 >= Fp).
 // `prod` = this group's shared-memory scratch of Fp doubles (for the in-order dot product).
+// `us` holds the user's factor row (and userBias) in registers: it is read from memory when `load_user`
+// and written back when `store_user`, so a run of consecutive ratings of one user touches P[u] once.
 // Returns this lane's contribution to the epoch loss (un-halved).
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int LPR, int V>
 __device__ __forceinline__ double rating_update(const DeviceModel& m, int u, int j, int ctx, double r,
                                                 double lr, double* prod, int gl /*lane in group*/,
-                                                unsigned gmask /*lanes of this group*/) {
+                                                unsigned gmask /*lanes of this group*/, UserRegs<V>& us,
+                                                bool load_user, bool store_user) {
   const int Fp = m.Fp;
   double* prow = m.P + (int64_t)u * Fp;
   double* qrow = m.Q + (int64_t)j * Fp;
+  constexpr bool kUserBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CI);
+  constexpr bool kItemBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CU);
 
   // ---- gather -------------------------------------------------------------------------------
-  double2 p[V], q[V];
+  double2 q[V];
 #pragma unroll
   for (int v = 0; v < V; v++) {
     const int c = gl + v * LPR;  // chunk index
     if (2 * c < Fp) {
-      p[v] = ld_cg_f64x2(prow + 2 * c);
       q[v] = ld_cg_f64x2(qrow + 2 * c);
+      if (load_user) us.p[v] = ld_cg_f64x2(prow + 2 * c);
     } else {
-      p[v] = make_double2(0.0, 0.0);
       q[v] = make_double2(0.0, 0.0);
+      us.p[v] = make_double2(0.0, 0.0);
     }
   }
-  double bu = 0.0, bj = 0.0;
-  if (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CI) bu = ld_cg_f64(m.user_bias + u);
-  if (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CU) bj = ld_cg_f64(m.item_bias + j);
+  if (kUserBias && load_user) us.bu = ld_cg_f64(m.user_bias + u);
+  double bj = 0.0;
+  if (kItemBias) bj = ld_cg_f64(m.item_bias + j);
+  const double bu = kUserBias ? us.bu : 0.0;
 
   // context-condition biases: lane d of the group owns condition d (d < D <= Dmax)
   constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU);
@@ -151,7 +191,7 @@ __device__ __forceinline__ double rating_update(const DeviceModel& m, int u, int
   for (int v = 0; v < V; v++) {
     const int c = gl + v * LPR;
     if (2 * c < Fp) {
-      double2 t = make_double2(__dmul_rn(p[v].x, q[v].x), __dmul_rn(p[v].y, q[v].y));
+      double2 t = make_double2(__dmul_rn(us.p[v].x, q[v].x), __dmul_rn(us.p[v].y, q[v].y));
       *reinterpret_cast<double2*>(prod + 2 * c) = t;
     }
   }
@@ -198,14 +238,15 @@ __device__ __forceinline__ double rating_update(const DeviceModel& m, int u, int
   const double e = __dsub_rn(r, pred);
 
   // ---- bias steps -----------------------------------------------------------------------------
+  if (kUserBias) {  // every lane keeps the same copy of bu; lane 0 owns the loss term and the write-back
+    const double sgd = __dsub_rn(e, __dmul_rn(m.reg_b, bu));
+    us.bu = __dadd_rn(bu, __dmul_rn(lr, sgd));
+    if (store_user && gl == 0) st_cg_f64(m.user_bias + u, us.bu);
+  }
   if (gl == 0) {
     lane_loss = __dmul_rn(e, e);
-    if (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CI) {
-      const double sgd = __dsub_rn(e, __dmul_rn(m.reg_b, bu));
-      st_cg_f64(m.user_bias + u, __dadd_rn(bu, __dmul_rn(lr, sgd)));
-      lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_b, bu), bu));
-    }
-    if (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CU) {
+    if (kUserBias) lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_b, bu), bu));
+    if (kItemBias) {
       const double sgd = __dsub_rn(e, __dmul_rn(m.reg_b, bj));
       st_cg_f64(m.item_bias + j, __dadd_rn(bj, __dmul_rn(lr, sgd)));
       lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_b, bj), bj));
@@ -239,24 +280,29 @@ __device__ __forceinline__ double rating_update(const DeviceModel& m, int u, int
   }
 
   // ---- factor steps (both from the OLD p, q) and scatter -------------------------------------------
+  // The regularisation terms of the loss, sum_f regU*p^2 + regI*q^2, are accumulated as regU*sum(p^2) +
+  // regI*sum(q^2) with FMAs: `loss` is a report value (1e-11 relative), the model is not.
+  double sp = 0.0, sq = 0.0;
 #pragma unroll
   for (int v = 0; v < V; v++) {
     const int c = gl + v * LPR;
     if (2 * c < Fp) {
-      const double2 po = p[v], qo = q[v];
+      const double2 po = us.p[v], qo = q[v];
       double2 pn, qn;
       pn.x = __dadd_rn(po.x, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, qo.x), __dmul_rn(m.reg_u, po.x))));
       qn.x = __dadd_rn(qo.x, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, po.x), __dmul_rn(m.reg_i, qo.x))));
       pn.y = __dadd_rn(po.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, qo.y), __dmul_rn(m.reg_u, po.y))));
       qn.y = __dadd_rn(qo.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, po.y), __dmul_rn(m.reg_i, qo.y))));
-      st_cg_f64x2(prow + 2 * c, pn);
+      us.p[v] = pn;
       st_cg_f64x2(qrow + 2 * c, qn);
-      lane_loss = __dadd_rn(lane_loss, __dadd_rn(__dmul_rn(__dmul_rn(m.reg_u, po.x), po.x),
-                                                 __dmul_rn(__dmul_rn(m.reg_i, qo.x), qo.x)));
-      lane_loss = __dadd_rn(lane_loss, __dadd_rn(__dmul_rn(__dmul_rn(m.reg_u, po.y), po.y),
-                                                 __dmul_rn(__dmul_rn(m.reg_i, qo.y), qo.y)));
+      if (store_user) st_cg_f64x2(prow + 2 * c, pn);
+      sp = fma(po.x, po.x, sp);
+      sq = fma(qo.x, qo.x, sq);
+      sp = fma(po.y, po.y, sp);
+      sq = fma(qo.y, qo.y, sq);
     }
   }
+  lane_loss = __dadd_rn(lane_loss, fma(m.reg_u, sp, __dmul_rn(m.reg_i, sq)));
   return lane_loss;
 }
 
@@ -294,7 +340,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
       const int j = __ldg(s.j + n);
       const int ctx = s.ctx ? __ldg(s.ctx + n) : 0;
       const double r = __ldg(s.r + n);
-      acc = __dadd_rn(acc, rating_update<MODEL, LPR, V>(m, u, j, ctx, r, lr, prod, gl, gmask));
+      UserRegs<V> us;
+      acc = __dadd_rn(acc, rating_update<MODEL, LPR, V>(m, u, j, ctx, r, lr, prod, gl, gmask, us, true, true));
     }
     if (L + 1 < s.num_levels) grid_barrier(barrier_counter, (unsigned)(L + 1) * gridDim.x);
   }
@@ -325,12 +372,193 @@ __global__ void __launch_bounds__(32, 1)
     const int j = __ldg(s.j + n);
     const int ctx = s.ctx ? __ldg(s.ctx + n) : 0;
     const double r = __ldg(s.r + n);
-    acc = __dadd_rn(acc, rating_update<MODEL, 32, V>(m, u, j, ctx, r, lr, prod, lane, 0xffffffffu));
+    UserRegs<V> us;
+    acc = __dadd_rn(acc, rating_update<MODEL, 32, V>(m, u, j, ctx, r, lr, prod, lane, 0xffffffffu, us, true, true));
     __syncwarp();
     __threadfence_block();
   }
   acc = warp_sum_f64(acc);
   if (lane == 0) block_partial[0] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1d: dataflow SGD (the default schedule).  Ratings stay in the reference's iteration order and are
+// cut into chunks of consecutive ratings; groups take chunks IN ORDER from a global counter and walk
+// each chunk sequentially.  A rating may run once the previous rating of its user and of its item (in
+// reference order) has completed: done_u[u] == ku and done_j[j] == kj.  Completion is published with a
+// release store after the group's stores; waiting is a non-blocking acquire poll (a group that is not
+// ready skips the turn, so the other groups of its warp keep going -- no intra-warp deadlock).
+// Because chunks are handed out in order and every dependency of a rating lies earlier in reference
+// order, the earliest unfinished chunk can always progress: no grid-wide barrier, no co-residency needed.
+// While consecutive ratings share the user (a ratings file sorted by user) P[u] and userBias[u] stay in
+// registers; Q, itemBias and icBias (tens of MB) stay L2-resident.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ RatingRec ld_rec(const RatingRec* p) {
+  const int4 a = __ldg(reinterpret_cast<const int4*>(p));
+  const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+  RatingRec x;
+  x.u = a.x; x.j = a.y; x.ctx = a.z; x.ku = a.w;
+  x.kj = b.x; x.pad = 0;
+  x.r = __hiloint2double(b.w, b.z);
+  return x;
+}
+
+template <int MODEL, int LPR, int V, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    sgd_dataflow_kernel(DeviceModel m, DataflowStream s, double lr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int G = 32 / LPR;  // groups per warp
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int gl = lane % LPR;
+  const int gw = lane / LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (gw * LPR));
+  const int prod_stride = m.Fp + 2;
+  double* prod = reinterpret_cast<double*>(smem_raw) + (size_t)(warp * G + gw) * prod_stride;
+
+  int64_t n = 0, end = 0;
+  int64_t chunk = -1;
+  bool done = false;
+  int prev_u = -1;
+  double acc = 0.0;
+  UserRegs<V> us;
+#pragma unroll
+  for (int v = 0; v < V; v++) us.p[v] = make_double2(0.0, 0.0);
+  us.bu = 0.0;
+
+  for (;;) {
+    if (!done && n == end) {
+      if (chunk >= 0) {  // publish the finished chunk's loss partial (fixed-order tree over the group)
+        double t = acc;
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) t = __dadd_rn(t, shfl_f64(gmask, t, gl + o, LPR));
+        if (gl == 0) s.chunk_loss[chunk] = t;
+        acc = 0.0;
+      }
+      unsigned c = 0;
+      if (gl == 0) c = atomicAdd(s.counter, 1u);
+      c = __shfl_sync(gmask, c, 0, LPR);
+      if (c >= s.num_chunks) {
+        done = true;
+      } else {
+        chunk = c;
+        n = __ldg(s.chunk_start + c);
+        end = __ldg(s.chunk_start + c + 1);
+        prev_u = -1;
+      }
+    }
+    __syncwarp();
+    if (__all_sync(0xffffffffu, done)) break;
+    if (!done) {
+      const RatingRec rec = ld_rec(s.rec + n);
+      const bool first = (rec.u != prev_u);
+      bool ok = true;
+      if (gl == 0) ok = (ld_acquire_u32(s.done_j + rec.j) == (unsigned)rec.kj);
+      if (gl == 1 && first) ok = (ld_acquire_u32(s.done_u + rec.u) == (unsigned)rec.ku);
+      const unsigned b = __ballot_sync(gmask, ok);
+      if ((b & gmask) == gmask) {
+        __syncwarp(gmask);  // the leaders' acquire loads happen-before every lane's loads below
+        bool last = (n + 1 == end);
+        if (!last) last = (__ldg(&s.rec[n + 1].u) != rec.u);
+        acc = __dadd_rn(acc, rating_update<MODEL, LPR, V>(m, rec.u, rec.j, rec.ctx, rec.r, lr, prod, gl, gmask,
+                                                          us, first, last));
+        __syncwarp(gmask);  // the group's stores happen-before lane 0's release
+        if (gl == 0) {
+          fence_acq_rel_gpu();
+          st_relaxed_u32(s.done_j + rec.j, (unsigned)rec.kj + 1u);
+          if (last) st_relaxed_u32(s.done_u + rec.u, (unsigned)rec.ku + 1u);
+        }
+        prev_u = rec.u;
+        n++;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1f: flagged wavefront.  Ratings sorted by dependency level as for K1, statically dealt round-robin
+// to the co-resident groups (rating n -> group n mod T), but instead of a grid-wide barrier per level
+// every rating waits only for ITS two predecessors (done_u[u] == ku, done_j[j] == kj).  The sorted
+// order is a topological order of the conflict DAG and every group walks its ratings in that order, so
+// the earliest unfinished rating is always runnable: deadlock-free given co-residency (cooperative
+// launch).  Levels overlap: the tail of level L runs beside the head of level L+1.
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int LPR, int V, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    sgd_flagged_kernel(DeviceModel m, const RatingRec* __restrict__ recs, int64_t nnz, unsigned* done_u,
+                       unsigned* done_j, double lr, double* block_partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int G = 32 / LPR;
+  constexpr int WARPS = THREADS / 32;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int gl = lane % LPR;
+  const int gw = lane / LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (gw * LPR));
+  const int prod_stride = m.Fp + 2;
+  double* prod = reinterpret_cast<double*>(smem_raw) + (size_t)(warp * G + gw) * prod_stride;
+
+  // interleave CTAs so that consecutive ratings land on different SMs
+  const int64_t total_groups = (int64_t)gridDim.x * WARPS * G;
+  int64_t n = ((int64_t)warp * gridDim.x + blockIdx.x) * G + gw;
+
+  double acc = 0.0;
+  RatingRec rec;
+  if (n < nnz) rec = ld_rec(recs + n);
+  for (;;) {
+    const bool active = n < nnz;
+    if (!__any_sync(0xffffffffu, active)) break;
+    if (active) {
+      bool ok = true;
+      if (gl == 0) ok = (ld_acquire_u32(done_j + rec.j) == (unsigned)rec.kj);
+      if (gl == 1) ok = (ld_acquire_u32(done_u + rec.u) == (unsigned)rec.ku);
+      const unsigned b = __ballot_sync(gmask, ok);
+      if ((b & gmask) == gmask) {
+        __syncwarp(gmask);
+        UserRegs<V> us;
+        acc = __dadd_rn(acc, rating_update<MODEL, LPR, V>(m, rec.u, rec.j, rec.ctx, rec.r, lr, prod, gl, gmask, us,
+                                                          true, true));
+        const int64_t nn = n + total_groups;
+        RatingRec next = rec;
+        if (nn < nnz) next = ld_rec(recs + nn);  // overlaps the fence below
+        __syncwarp(gmask);
+        if (gl == 0) {
+          fence_acq_rel_gpu();
+          st_relaxed_u32(done_j + rec.j, (unsigned)rec.kj + 1u);
+          st_relaxed_u32(done_u + rec.u, (unsigned)rec.ku + 1u);
+        }
+        rec = next;
+        n = nn;
+      }
+    }
+  }
+
+  acc = warp_sum_f64(acc);
+  __shared__ double warp_sum[WARPS];
+  if (lane == 0) warp_sum[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < WARPS; w++) t += warp_sum[w];
+    block_partial[blockIdx.x] = t;
+  }
+}
+
+// K3a: deterministic reduction of the per-chunk loss partials: block b sums a fixed contiguous slice.
+__global__ void __launch_bounds__(256) chunk_loss_reduce_kernel(const double* chunk_loss, int64_t n, double* block_partial) {
+  __shared__ double sh[256];
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t beg = (int64_t)blockIdx.x * per;
+  const int64_t end = beg + per < n ? beg + per : n;
+  double t = 0.0;
+  for (int64_t i = beg + threadIdx.x; i < end; i += 256) t += chunk_loss[i];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) block_partial[blockIdx.x] = sh[0];
 }
 
 // K3: final loss reduction in fixed order, then `loss *= 0.5` (CAMF_CI.java:124).

@@ -40,7 +40,7 @@ enum cars_model {
   CARS_FM       = 5  /* .../cars/adaptation/dependent/FM.java:115-220 (ALS; not built in round 1) */
 };
 
-/* Update schedule.
+/* Update mode.
  * EXACT: serial-equivalent.  Ratings that share a user or an item run in the reference's iteration
  *        order (CRS order of trainMatrix, CAMF_CI.java:80); independent ratings run concurrently.
  *        P, Q and every bias end bit-identical to the Java loop; only `loss` (a 67*nnz-term
@@ -51,6 +51,15 @@ enum cars_model {
  *        (hogwild updates of the shared condBias vector of CAMF_C were measured to diverge, see
  *        DESIGN.md). */
 enum cars_mode { CARS_EXACT = 0, CARS_FAST = 1 };
+
+/* How EXACT mode orders independent ratings (both are serial-equivalent and bit-identical):
+ * DATAFLOW  (default) ratings stay in reference order; each waits for the previous rating of its user
+ *           and of its item through per-row completion counters; a user's factor row stays in
+ *           registers across consecutive ratings of that user.
+ * WAVEFRONT ratings are sorted into dependency levels; a grid-wide barrier separates levels.
+ * FLAGGED   the WAVEFRONT order without barriers: every rating waits only for its own two predecessors.
+ */
+enum cars_schedule { CARS_SCHED_DATAFLOW = 0, CARS_SCHED_WAVEFRONT = 1, CARS_SCHED_FLAGGED = 2 };
 
 enum cars_error {
   CARS_OK            =  0,
@@ -85,7 +94,7 @@ typedef struct cars_desc {
   int32_t num_conditions;  /* rateDao.numConditions(), ContextRecommender.java:43 */
   int32_t num_contexts;
   int32_t num_factors;     /* IterativeRecommender.numFactors (:101) */
-  int32_t reserved0;
+  int32_t schedule;        /* enum cars_schedule (EXACT mode only) */
   int64_t nnz;
   const int32_t* u;
   const int32_t* j;
@@ -164,8 +173,8 @@ const char* cars_last_error(const cars_handle* h);
 /* Introspection used by the benchmark and the tests (no reference counterpart). */
 typedef struct cars_stats {
   int64_t nnz;              /* ratings trained by this handle (after sharding)         */
-  int64_t num_levels;       /* wavefront levels of the dependency DAG                  */
-  int64_t max_level_size;
+  int64_t num_levels;       /* WAVEFRONT: levels of the dependency DAG; DATAFLOW: chunks */
+  int64_t max_level_size;   /* WAVEFRONT: largest level; DATAFLOW: longest chunk       */
   int64_t kernel_launches;  /* engine kernels launched so far on this handle           */
   int64_t h2d_bytes;        /* bytes copied host->device so far                        */
   int64_t d2h_bytes;        /* bytes copied device->host so far                        */

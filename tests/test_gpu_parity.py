@@ -22,8 +22,8 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "sgd_golden.json")
 CTX_MODELS = (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU)
 
 
-def run_both(oracle, model, ts, F, epochs, seed, mode=capi.EXACT, lr0=capi.f32(0.02)):
-    desc = capi.make_desc(ts, model, F, mode=mode, **REGS)
+def run_both(oracle, model, ts, F, epochs, seed, mode=capi.EXACT, lr0=capi.f32(0.02), schedule=capi.SCHED_DATAFLOW):
+    desc = capi.make_desc(ts, model, F, mode=mode, schedule=schedule, **REGS)
     ref = init_arrays(oracle, model, ts, F, seed)
     got = {k: v.copy() for k, v in ref.items()}
     ref_losses, got_losses = [], []
@@ -58,13 +58,51 @@ def test_exact_mode_bit_identical(oracle, cars_lib, model, F):
     assert st.num_levels > 1 and st.kernel_launches >= 6
 
 
-@pytest.mark.parametrize("order", ["user_sorted", "shuffled"])
-@pytest.mark.parametrize("zipf", [0.0, 1.0])
-def test_exact_mode_orders_and_skew(oracle, cars_lib, order, zipf):
-    ts, _ = synth.make_training_set(2000, 300, [8, 8, 8, 8], 60000, seed=9, order=order, item_zipf=zipf)
-    ref, got, rl, gl, _ = run_both(oracle, capi.CAMF_CI, ts, 64, epochs=2, seed=3)
+@pytest.mark.parametrize("model", [capi.PMF, capi.BIASEDMF, capi.CAMF_CI, capi.CAMF_CU])
+@pytest.mark.parametrize("F", [7, 64, 128])
+@pytest.mark.parametrize("schedule", [capi.SCHED_WAVEFRONT, capi.SCHED_FLAGGED])
+def test_level_schedules_bit_identical(oracle, cars_lib, model, F, schedule):
+    dims = [4, 3, 2] if model in CTX_MODELS else None
+    ts, _ = synth.make_training_set(500, 120, dims, 20000, seed=F, order="user_sorted")
+    ref, got, rl, gl, st = run_both(oracle, model, ts, F, epochs=3, seed=F + 1, schedule=schedule)
     assert_bit_identical(ref, got)
     np.testing.assert_allclose(gl, rl, rtol=LOSS_RTOL, atol=0)
+
+
+@pytest.mark.parametrize("schedule", [capi.SCHED_DATAFLOW, capi.SCHED_WAVEFRONT, capi.SCHED_FLAGGED])
+@pytest.mark.parametrize("order", ["user_sorted", "shuffled"])
+@pytest.mark.parametrize("zipf", [0.0, 1.0])
+def test_exact_mode_orders_and_skew(oracle, cars_lib, order, zipf, schedule):
+    ts, _ = synth.make_training_set(2000, 300, [8, 8, 8, 8], 60000, seed=9, order=order, item_zipf=zipf)
+    ref, got, rl, gl, _ = run_both(oracle, capi.CAMF_CI, ts, 64, epochs=2, seed=3, schedule=schedule)
+    assert_bit_identical(ref, got)
+    np.testing.assert_allclose(gl, rl, rtol=LOSS_RTOL, atol=0)
+
+
+@pytest.mark.parametrize("model", [capi.BIASEDMF, capi.CAMF_CI, capi.CAMF_CU])
+@pytest.mark.parametrize("schedule", [capi.SCHED_DATAFLOW, capi.SCHED_FLAGGED])
+def test_flag_schedules_large_random(oracle, cars_lib, model, schedule):
+    # enough ratings to keep every resident group busy and to make cross-group dependencies frequent:
+    # few items => long item chains that hop between groups on every rating
+    dims = [8, 8, 8, 8] if model in CTX_MODELS else None
+    for order, users, items in (("user_sorted", 20000, 64), ("shuffled", 3000, 2000)):
+        ts, _ = synth.make_training_set(users, items, dims, 600000, seed=77, order=order)
+        ref, got, rl, gl, _ = run_both(oracle, model, ts, 64, epochs=2, seed=5, schedule=schedule)
+        assert_bit_identical(ref, got)
+        np.testing.assert_allclose(gl, rl, rtol=LOSS_RTOL, atol=0)
+
+
+def test_dataflow_loss_is_deterministic(oracle, cars_lib):
+    # chunks are handed out dynamically, but the loss is reduced per chunk in a fixed order
+    ts, _ = synth.make_training_set(5000, 500, [8, 8], 200000, seed=13, order="shuffled")
+    desc = capi.make_desc(ts, capi.CAMF_CI, 32, **REGS)
+    arrs = init_arrays(oracle, capi.CAMF_CI, ts, 32, 2)
+    runs = []
+    for _ in range(3):
+        with capi.Engine(desc, keepalive=ts) as eng:
+            eng.upload(arrs)
+            runs.append([eng.epoch(0.02).hex() for _ in range(2)])
+    assert runs[0] == runs[1] == runs[2]
 
 
 def test_camf_c_exact_serial_kernel(oracle, cars_lib):
