@@ -134,9 +134,9 @@ static LaunchPlan pick_wavefront(int Fp, int variant) {
   }
 }
 
-static int wavefront_variant() {
+static int wavefront_variant(int dflt = 2) {  // 256 threads x 3 CTAs per SM measured best on B200 (profiles/)
   const char* e = getenv("CARS_WF_VARIANT");
-  return e ? atoi(e) : 0;
+  return e ? atoi(e) : dflt;
 }
 
 static LaunchPlan pick_plan(int model, int /*mode*/, int Fp) {
@@ -203,9 +203,10 @@ static LaunchPlan pick_flagged_shape(int Fp) {
 template <int MODEL>
 static LaunchPlan pick_flagged(int Fp, int variant) {
   switch (variant) {
-    case 1: return pick_flagged_shape<MODEL, 512, 2>(Fp);
+    case 1: return pick_flagged_shape<MODEL, 512, 1>(Fp);
     case 2: return pick_flagged_shape<MODEL, 256, 3>(Fp);
-    default: return pick_flagged_shape<MODEL, 512, 1>(Fp);
+    case 3: return pick_flagged_shape<MODEL, 384, 1>(Fp);
+    default: return pick_flagged_shape<MODEL, 256, 2>(Fp);
   }
 }
 
@@ -402,6 +403,12 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     groups_per_cta = (plan.threads / 32) * G;
     h->block = plan.threads;
     h->smem = (size_t)groups_per_cta * (Fp + 2) * 8;
+    if (h->flagged) {
+      // the last warp of the CTA is the release warp; per worker group: mbarrier, mailbox, dot-product scratch
+      // and the TMA landing slot (one P row, one Q row)
+      groups_per_cta = (plan.threads / 32 - 1) * G;
+      h->smem = flagged_smem_bytes(groups_per_cta, Fp);
+    }
     CUDA_TRY_H(cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     int per_sm = 0;
     CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, plan.threads, h->smem));
@@ -662,9 +669,9 @@ extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
     CUDA_TRY(h, cudaMemsetAsync(h->d_flags, 0, h->flags_words * sizeof(unsigned), h->stream));
     const RatingRec* recs = h->d_rec;
     int64_t nnz = h->nnz;
-    unsigned* done_j = h->d_flags + 64;
-    unsigned* done_u = h->d_flags + 64 + h->d.num_items;
-    void* args[] = {&m, &recs, &nnz, &done_u, &done_j, &lrate, &h->d_partial};
+    unsigned off_j = 64u;
+    unsigned off_u = 64u + (unsigned)h->d.num_items;
+    void* args[] = {&m, &recs, &nnz, &h->d_flags, &off_u, &off_j, &lrate, &h->d_partial};
     CUDA_TRY(h, cudaLaunchCooperativeKernel(plan.fn, dim3(h->grid), dim3(h->block), args, h->smem, h->stream));
     h->st.kernel_launches += 1;
   } else {
