@@ -238,7 +238,7 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
 
     # ---------------- device-resident arm: `value` -----------------------------------------------------
     stream = torch.cuda.current_stream().cuda_stream
-    rec = Rec(ts, None, conf=conf, device=local_rank, stream=stream)
+    rec = Rec(ts, None, conf=conf, device=local_rank, stream=stream, world=world)
     rec.initModel(init={k: v.copy() for k, v in arrs.items()})
     t0 = time.time()
     eng = rec.open_engine()
@@ -284,7 +284,7 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
         f"losses {losses[:3]}..")
 
     # ---------------- end-to-end arm: recommender.buildModel() from host buffers --------------------------
-    rec2 = Rec(ts, None, conf=conf, device=local_rank, stream=stream)
+    rec2 = Rec(ts, None, conf=conf, device=local_rank, stream=stream, world=world)
     rec2.initModel(init=arrs)
     barrier()
     t0 = time.perf_counter()

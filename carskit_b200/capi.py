@@ -15,7 +15,7 @@ import numpy as np
 ABI_VERSION = 1
 PMF, BIASEDMF, CAMF_C, CAMF_CI, CAMF_CU, FM = range(6)
 EXACT, FAST = 0, 1
-SCHED_DATAFLOW, SCHED_WAVEFRONT, SCHED_FLAGGED = 0, 1, 2
+SCHED_FLAGGED, SCHED_WAVEFRONT, SCHED_DATAFLOW = 0, 1, 2
 MODEL_NAMES = {"pmf": PMF, "biasedmf": BIASEDMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -57,7 +57,8 @@ class CarsStats(C.Structure):
 EXPORTS = [
     "cars_create", "cars_upload", "cars_epoch", "cars_epoch_begin", "cars_epoch_wait", "cars_download",
     "cars_predict", "cars_eval_ratings", "cars_destroy", "cars_last_error", "cars_get_stats",
-    "cars_get_stream", "cars_version",
+    "cars_get_stream", "cars_version", "cars_item_block_doubles", "cars_epoch_sharded_begin",
+    "cars_epoch_sharded_finish",
 ]
 
 
@@ -105,6 +106,12 @@ def load_library(path: Optional[str] = None):
     lib.cars_get_stats.restype = C.c_int
     lib.cars_get_stream.argtypes = [H]
     lib.cars_get_stream.restype = C.c_void_p
+    lib.cars_item_block_doubles.argtypes = [H, C.POINTER(C.c_int64)]
+    lib.cars_item_block_doubles.restype = C.c_int
+    lib.cars_epoch_sharded_begin.argtypes = [H, C.c_double, C.c_void_p]
+    lib.cars_epoch_sharded_begin.restype = C.c_int
+    lib.cars_epoch_sharded_finish.argtypes = [H, C.c_void_p, _f64p]
+    lib.cars_epoch_sharded_finish.restype = C.c_int
     lib.cars_version.argtypes = []
     lib.cars_version.restype = C.c_char_p
     if path is None:
@@ -165,7 +172,7 @@ class TrainingSet:
 def make_desc(ts: TrainingSet, model: int, num_factors: int, *, mode: int = EXACT, device: int = 0,
               reg_u: float = 0.0, reg_i: float = 0.0, reg_b: float = 0.0, reg_c: float = 0.0,
               reg_lw: float = 0.0, reg_lf: float = 0.0, rank: int = 0, world_size: int = 1,
-              stream: int = 0, schedule: int = SCHED_DATAFLOW) -> CarsDesc:
+              stream: int = 0, schedule: int = SCHED_FLAGGED) -> CarsDesc:
     """Fill a cars_desc.  The reg_* values must already be float-widened (use f32())."""
     d = CarsDesc()
     d.abi_version = ABI_VERSION
@@ -248,6 +255,20 @@ class Engine:
     def epoch_wait(self) -> float:
         loss = C.c_double()
         self._check(self.lib.cars_epoch_wait(self.h, C.byref(loss)))
+        return loss.value
+
+    def item_block_doubles(self) -> int:
+        n = C.c_int64()
+        self._check(self.lib.cars_item_block_doubles(self.h, C.byref(n)))
+        return n.value
+
+    def epoch_sharded_begin(self, lrate: float, dev_delta_ptr: int):
+        """dev_delta_ptr: device address of item_block_doubles() doubles owned by the caller."""
+        self._check(self.lib.cars_epoch_sharded_begin(self.h, lrate, C.c_void_p(dev_delta_ptr)))
+
+    def epoch_sharded_finish(self, dev_delta_ptr: int) -> float:
+        loss = C.c_double()
+        self._check(self.lib.cars_epoch_sharded_finish(self.h, C.c_void_p(dev_delta_ptr), C.byref(loss)))
         return loss.value
 
     def predict(self, u, j, ctx=None, bound=False, min_rate=0.0, max_rate=0.0) -> np.ndarray:

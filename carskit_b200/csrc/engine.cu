@@ -56,6 +56,8 @@ struct cars_handle {
   size_t flags_words = 0;
   int64_t num_chunks = 0;
   int loss_blocks = 0;
+  double* d_item_old = nullptr;  // snapshot of the item block (multi-GPU exchange), allocated on first use
+  bool sharded_pending = false;
 
   // kernel plumbing
   unsigned* d_barrier = nullptr;
@@ -203,10 +205,25 @@ static LaunchPlan pick_flagged_shape(int Fp) {
 template <int MODEL>
 static LaunchPlan pick_flagged(int Fp, int variant) {
   switch (variant) {
-    case 1: return pick_flagged_shape<MODEL, 512, 1>(Fp);
+    case 1: return pick_flagged_shape<MODEL, 512, 2>(Fp);
     case 2: return pick_flagged_shape<MODEL, 256, 3>(Fp);
-    case 3: return pick_flagged_shape<MODEL, 384, 1>(Fp);
-    default: return pick_flagged_shape<MODEL, 256, 2>(Fp);
+    case 3: {  // 4 lanes per rating (16 factors per lane): more ratings in flight per SM at F <= 64
+      LaunchPlan p;
+      if (Fp > 32 && Fp <= 64) {
+        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 4, 8, 256, 2>; p.lpr = 4; p.v = 8;
+        return p;
+      }
+      return pick_flagged_shape<MODEL, 256, 3>(Fp);
+    }
+    case 4: {
+      LaunchPlan p;
+      if (Fp > 32 && Fp <= 64) {
+        p.threads = 128; p.fn = (const void*)sgd_flagged_kernel<MODEL, 4, 8, 128, 5>; p.lpr = 4; p.v = 8;
+        return p;
+      }
+      return pick_flagged_shape<MODEL, 256, 3>(Fp);
+    }
+    default: return pick_flagged_shape<MODEL, 512, 1>(Fp);
   }
 }
 
@@ -384,7 +401,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   h->serial = (model == CARS_CAMF_C);
   int sched = desc->schedule;
   if (const char* e = getenv("CARS_SCHEDULE"))
-    sched = strcmp(e, "wavefront") == 0 ? CARS_SCHED_WAVEFRONT : strcmp(e, "flagged") == 0 ? CARS_SCHED_FLAGGED : CARS_SCHED_DATAFLOW;
+    sched = strcmp(e, "wavefront") == 0 ? CARS_SCHED_WAVEFRONT : strcmp(e, "dataflow") == 0 ? CARS_SCHED_DATAFLOW : CARS_SCHED_FLAGGED;
   if (sched != CARS_SCHED_DATAFLOW && sched != CARS_SCHED_WAVEFRONT && sched != CARS_SCHED_FLAGGED) {
     fail(h, CARS_E_INVALID, "unknown schedule %d", sched);
     return bail(CARS_E_INVALID);
@@ -403,12 +420,6 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     groups_per_cta = (plan.threads / 32) * G;
     h->block = plan.threads;
     h->smem = (size_t)groups_per_cta * (Fp + 2) * 8;
-    if (h->flagged) {
-      // the last warp of the CTA is the release warp; per worker group: mbarrier, mailbox, dot-product scratch
-      // and the TMA landing slot (one P row, one Q row)
-      groups_per_cta = (plan.threads / 32 - 1) * G;
-      h->smem = flagged_smem_bytes(groups_per_cta, Fp);
-    }
     CUDA_TRY_H(cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     int per_sm = 0;
     CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, plan.threads, h->smem));
@@ -703,6 +714,84 @@ extern "C" int cars_epoch_wait(cars_handle* h, double* loss_out) {
   return CARS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// multi-GPU exchange of the item block (C1)
+// ------------------------------------------------------------------------------------------------
+struct ItemPart {
+  double* ptr;
+  int64_t n;
+};
+static int item_parts(const cars_handle* h, ItemPart out[3]) {
+  const DeviceModel& m = h->m;
+  const int64_t I = h->d.num_items;
+  int k = 0;
+  out[k++] = {m.Q, I * m.Fp};
+  if (m.item_bias) out[k++] = {m.item_bias, I};
+  if (m.ic_bias) out[k++] = {m.ic_bias, I * (int64_t)m.C};
+  return k;
+}
+
+extern "C" int cars_item_block_doubles(const cars_handle* h, int64_t* out) {
+  if (!h || !out) return CARS_E_INVALID;
+  ItemPart parts[3];
+  const int k = item_parts(h, parts);
+  int64_t n = 0;
+  for (int i = 0; i < k; i++) n += parts[i].n;
+  *out = n;
+  return CARS_OK;
+}
+
+extern "C" int cars_epoch_sharded_begin(cars_handle* h, double lrate, double* dev_delta) {
+  if (!h) return CARS_E_INVALID;
+  if (!dev_delta) return fail(h, CARS_E_INVALID, "dev_delta is NULL");
+  if (h->d.model == CARS_CAMF_C)
+    return fail(h, CARS_E_UNSUPPORTED, "CAMF_C shares condBias between all ratings; it is not sharded");
+  if (h->sharded_pending) return fail(h, CARS_E_STATE, "previous sharded epoch not finished");
+  if (!h->uploaded) return fail(h, CARS_E_STATE, "cars_epoch before cars_upload");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  ItemPart parts[3];
+  const int k = item_parts(h, parts);
+  int64_t total = 0;
+  for (int i = 0; i < k; i++) total += parts[i].n;
+  if (!h->d_item_old) CUDA_TRY(h, dev_alloc(&h->d_item_old, (size_t)total));
+  int64_t off = 0;
+  for (int i = 0; i < k; i++) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_item_old + off, parts[i].ptr, (size_t)parts[i].n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    off += parts[i].n;
+  }
+  int rc = cars_epoch_begin(h, lrate);
+  if (rc) return rc;
+  off = 0;
+  const int blocks = h->sm_count * 8;
+  for (int i = 0; i < k; i++) {
+    item_delta_kernel<<<blocks, 256, 0, h->stream>>>(parts[i].ptr, h->d_item_old + off, dev_delta + off, parts[i].n);
+    CUDA_TRY(h, cudaGetLastError());
+    h->st.kernel_launches += 1;
+    off += parts[i].n;
+  }
+  h->sharded_pending = true;
+  return CARS_OK;
+}
+
+extern "C" int cars_epoch_sharded_finish(cars_handle* h, const double* dev_delta, double* loss_out) {
+  if (!h) return CARS_E_INVALID;
+  if (!h->sharded_pending) return fail(h, CARS_E_STATE, "no sharded epoch pending");
+  if (!dev_delta) return fail(h, CARS_E_INVALID, "dev_delta is NULL");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  ItemPart parts[3];
+  const int k = item_parts(h, parts);
+  int64_t off = 0;
+  const int blocks = h->sm_count * 8;
+  for (int i = 0; i < k; i++) {
+    item_apply_kernel<<<blocks, 256, 0, h->stream>>>(parts[i].ptr, h->d_item_old + off, dev_delta + off, parts[i].n);
+    CUDA_TRY(h, cudaGetLastError());
+    h->st.kernel_launches += 1;
+    off += parts[i].n;
+  }
+  h->sharded_pending = false;
+  return cars_epoch_wait(h, loss_out);
+}
+
 extern "C" int cars_epoch(cars_handle* h, double lrate, double* loss_out) {
   int rc = cars_epoch_begin(h, lrate);
   if (rc) return rc;
@@ -804,6 +893,7 @@ extern "C" void cars_destroy(cars_handle* h) {
   cudaFree(h->m.P); cudaFree(h->m.Q); cudaFree(h->m.user_bias); cudaFree(h->m.item_bias);
   cudaFree(h->m.cond_bias); cudaFree(h->m.ic_bias); cudaFree(h->m.uc_bias);
   cudaFree(h->d_rec); cudaFree(h->d_chunk_start); cudaFree(h->d_chunk_loss); cudaFree(h->d_flags);
+  cudaFree(h->d_item_old);
   cudaFree(h->d_barrier); cudaFree(h->d_partial); cudaFree(h->d_loss);
   if (h->h_loss) cudaFreeHost(h->h_loss);
   if (h->ev_beg) cudaEventDestroy(h->ev_beg);

@@ -95,6 +95,11 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -495,8 +500,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
       const RatingRec rec = ld_rec(s.rec + n);
       const bool first = (rec.u != prev_u);
       bool ok = true;
-      if (gl == 0) ok = (ld_acquire_u32(s.done_j + rec.j) == (unsigned)rec.kj);
-      if (gl == 1 && first) ok = (ld_acquire_u32(s.done_u + rec.u) == (unsigned)rec.ku);
+      if (gl == 0) ok = (ld_relaxed_u32(s.done_j + rec.j) == (unsigned)rec.kj);
+      if (gl == 1 && first) ok = (ld_relaxed_u32(s.done_u + rec.u) == (unsigned)rec.ku);
       const unsigned b = __ballot_sync(gmask, ok);
       if ((b & gmask) == gmask) {
         __syncwarp(gmask);  // the leaders' acquire loads happen-before every lane's loads below
@@ -506,8 +511,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
                                                           us, first, last));
         __syncwarp(gmask);  // the group's stores happen-before lane 0's release
         if (gl == 0) {
-          fence_acq_rel_gpu();
-          st_relaxed_u32(s.done_j + rec.j, (unsigned)rec.kj + 1u);
+          st_release_u32(s.done_j + rec.j, (unsigned)rec.kj + 1u);
           if (last) st_relaxed_u32(s.done_u + rec.u, (unsigned)rec.ku + 1u);
         }
         prev_u = rec.u;
@@ -518,81 +522,20 @@ __global__ void __launch_bounds__(THREADS, MINB)
 }
 
 // ------------------------------------------------------------------------------------------------
-// TMA (1-D bulk async copy) + mbarrier helpers: one factor row = one cp.async.bulk into shared memory.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_row(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// shared-memory layout of K1f (host and device use the same arithmetic)
-__host__ __device__ constexpr int flagged_mail_offset(int groups) { return (groups * 8 + 15) & ~15; }
-__host__ __device__ constexpr int flagged_rows_offset(int groups) {
-  return (flagged_mail_offset(groups) + groups * 24 + 4 + 15) & ~15;
-}
-__host__ __device__ constexpr size_t flagged_smem_bytes(int groups, int Fp) {
-  return (size_t)flagged_rows_offset(groups) + (size_t)groups * (3 * Fp + 2) * 8;
-}
-
-__device__ __forceinline__ unsigned lds_volatile_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned lds_acquire_cta_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_release_cta_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ void sts_volatile_u32(unsigned* p, unsigned v) {
-  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1f: flagged wavefront, software-pipelined and warp-specialised (the default schedule).
+// K1f: flagged wavefront (the default schedule).
 // Ratings are sorted by dependency level as for K1 and statically dealt round-robin to the co-resident
-// worker groups (rating n -> group n mod T), but instead of a grid-wide barrier per level every rating
-// waits only for ITS two predecessors: done_u[u] == ku and done_j[j] == kj (completion counters).
+// groups (rating n -> group n mod T), but instead of a grid-wide barrier per level every rating waits
+// only for ITS two predecessors: done_u[u] == ku and done_j[j] == kj (completion counters).
 // The sorted order is a topological order of the conflict DAG and every group walks its ratings in
 // that order, so the earliest unfinished rating is always runnable: deadlock-free given co-residency
 // (cooperative launch).  A group that is not ready skips its turn (no blocking wait on another group
-// inside a warp).
+// inside a warp).  Levels overlap: the tail of level L runs beside the head of level L+1.
 //
-// Worker group, one rating per turn:
-//   [rows of rating i landed in the group's shared-memory slot through TMA (cp.async.bulk)]
-//   issue the polls of rating i+1's counters; copy slot -> registers; if i+1's predecessors are done,
-//   TMA its two rows into the slot and fetch its scalars (they fly during the arithmetic of i);
-//   arithmetic + scatter of i; hand (counter, value) x 2 to the CTA's release warp.
-// Release warp (last warp of the CTA): collects the hand-offs of all groups, executes ONE
-// fence (st.release.gpu = MEMBAR.ALL.GPU) for the batch and publishes the counters -- the workers never
-// stall on a GPU-scope fence.  worker -> release warp is a CTA-scope release/acquire through shared
-// memory, release warp -> consumer a GPU-scope release (cumulative), consumer side: ld.relaxed.gpu poll,
-// then only L2-level accesses (ld/st .cg, TMA), so no L1 invalidation is needed and none is issued.
+// Memory ordering: the producer stores its rows (st.global.cg), __syncwarp, then lane 0 publishes the
+// two counters with st.release.gpu (MEMBAR.ALL.GPU, cumulative over the group's stores).  The consumer
+// polls with ld.relaxed.gpu and, after a control dependency and __syncwarp, reads the rows with
+// ld.global.cg: every data access is served by L2, the point of coherence, so no L1 invalidation
+// (CCTL.IVALL, which ld.acquire.gpu would add on every poll) is needed.
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int LPR, int V, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -601,202 +544,58 @@ __global__ void __launch_bounds__(THREADS, MINB)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int G = 32 / LPR;
   constexpr int WARPS = THREADS / 32;
-  constexpr int WORKERS = WARPS - 1;  // worker warps; the last warp publishes completions
-  constexpr int GROUPS = WORKERS * G;
-  constexpr int PER_LANE = (GROUPS + 31) / 32;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int Fp = m.Fp;
-  // shared memory: [mbarriers GROUPS x 8][mail GROUPS x 16][seq GROUPS x 4][ack GROUPS x 4][finished 16]
-  //                [per group: prod (Fp + 2) | slot P (Fp) | slot Q (Fp)]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  uint4* mail = reinterpret_cast<uint4*>(smem_raw + flagged_mail_offset(GROUPS));
-  unsigned* seq = reinterpret_cast<unsigned*>(smem_raw + flagged_mail_offset(GROUPS) + GROUPS * 16);
-  unsigned* ack = seq + GROUPS;
-  unsigned* finished = ack + GROUPS;
-  double* rows = reinterpret_cast<double*>(smem_raw + flagged_rows_offset(GROUPS));
-  for (int i = threadIdx.x; i < GROUPS; i += THREADS) {
-    mbar_init(smem_u32(bars + i), 1);
-    seq[i] = 0u;
-    ack[i] = 0u;
-  }
-  if (threadIdx.x == 0) *finished = 0u;
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
+  const int gl = lane % LPR;
+  const int gw = lane / LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (gw * LPR));
+  const int prod_stride = m.Fp + 2;
+  double* prod = reinterpret_cast<double*>(smem_raw) + (size_t)(warp * G + gw) * prod_stride;
+  unsigned* done_u = flags + off_u;
+  unsigned* done_j = flags + off_j;
+
+  // interleave CTAs so that consecutive ratings land on different SMs
+  const int64_t T = (int64_t)gridDim.x * WARPS * G;
+  int64_t n = ((int64_t)warp * gridDim.x + blockIdx.x) * G + gw;
 
   double acc = 0.0;
-  if (warp == WORKERS) {
-    // ---------------- release warp ---------------------------------------------------------------------
-    unsigned seen[PER_LANE];
-#pragma unroll
-    for (int k = 0; k < PER_LANE; k++) seen[k] = 0u;
-    for (;;) {
-      const unsigned fin = lds_acquire_cta_u32(finished);  // read BEFORE the scan (exit condition)
-      uint4 pl[PER_LANE];
-      unsigned cur[PER_LANE];
-      bool pend[PER_LANE];
-      bool any = false;
-#pragma unroll
-      for (int k = 0; k < PER_LANE; k++) {
-        const int g = lane + 32 * k;
-        pend[k] = false;
-        if (g < GROUPS) {
-          cur[k] = lds_acquire_cta_u32(seq + g);
-          if (cur[k] != seen[k]) {
-            pl[k] = mail[g];
-            pend[k] = true;
-            any = true;
-          }
-        }
-      }
-      if (__any_sync(0xffffffffu, any)) {
-        if (any) {
-          bool first = true;
-#pragma unroll
-          for (int k = 0; k < PER_LANE; k++) {
-            if (pend[k]) {
-              if (first) st_release_u32(flags + pl[k].x, pl[k].y);  // the fence of the whole batch
-              else st_relaxed_u32(flags + pl[k].x, pl[k].y);
-              first = false;
-              st_relaxed_u32(flags + pl[k].z, pl[k].w);
-              seen[k] = cur[k];
-              sts_volatile_u32(ack + lane + 32 * k, cur[k]);
-            }
-          }
-        }
-      } else if (fin == (unsigned)WORKERS) {
-        break;
-      }
-    }
-  } else {
-    // ---------------- worker warps -----------------------------------------------------------------------
-    const int gl = lane % LPR;
-    const int gw = lane / LPR;
-    const int gid = warp * G + gw;  // group within the CTA
-    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (gw * LPR));
-    double* gbase = rows + (size_t)gid * (3 * Fp + 2);
-    double* prod = gbase;
-    double* slot_p = gbase + Fp + 2;
-    double* slot_q = slot_p + Fp;
-    const uint32_t bar = smem_u32(bars + gid);
-    const uint32_t row_bytes = (uint32_t)Fp * 8u;
-    const unsigned* done_u = flags + off_u;
-    const unsigned* done_j = flags + off_j;
-
-    // interleave CTAs so that consecutive ratings land on different SMs
-    const int64_t T = (int64_t)gridDim.x * GROUPS;
-    int64_t n = ((int64_t)warp * gridDim.x + blockIdx.x) * G + gw;
-
-    constexpr bool kUserBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_CI);
-    uint32_t parity = 0;
-    unsigned posted = 0;  // hand-offs so far (lane 0)
-    bool have = false;    // the slot holds (or is receiving) the rows of rating n
-    RatingRec rec, rec1;
-    rec.u = rec.j = rec.ctx = rec.ku = rec.kj = 0; rec.r = 0.0;
-    rec1 = rec;
-    Operands<V> o, o1;
-    o.bj = o.cb = o1.bj = o1.cb = 0.0;
-    o.cb_ptr = o1.cb_ptr = nullptr;
-    double bu = 0.0, bu1 = 0.0;
-    if (n < nnz) rec = ld_rec(recs + n);
-    if (n + T < nnz) rec1 = ld_rec(recs + n + T);
-
-    // lanes 0 / 1 read the item / user counter of rating x (a relaxed L2 load; the value is used later)
-    auto poll = [&](const RatingRec& x) -> unsigned {
-      unsigned f = 0u;
-      if (gl == 0) f = ld_relaxed_u32(done_j + x.j);
-      if (gl == 1) f = ld_relaxed_u32(done_u + x.u);
-      return f;
-    };
-    auto ready = [&](const RatingRec& x, unsigned f) -> bool {
+  RatingRec rec, next;
+  rec.u = rec.j = rec.ctx = rec.ku = rec.kj = 0; rec.r = 0.0;
+  if (n < nnz) rec = ld_rec(recs + n);
+  next = rec;
+  for (;;) {
+    const bool active = n < nnz;
+    if (!__any_sync(0xffffffffu, active)) break;
+    if (active) {
       bool ok = true;
-      if (gl == 0) ok = (f == (unsigned)x.kj);
-      if (gl == 1) ok = (f == (unsigned)x.ku);
-      return (__ballot_sync(gmask, ok) & gmask) == gmask;
-    };
-    // both predecessors are done: TMA the two rows into the slot, fetch the scalars
-    auto issue = [&](const RatingRec& x, Operands<V>& ox, double& bux) {
-      __syncwarp(gmask);
-      if (gl == 0) {
-        mbar_expect_tx(bar, 2u * row_bytes);
-        tma_load_row(smem_u32(slot_p), m.P + (int64_t)x.u * Fp, row_bytes, bar);
-        tma_load_row(smem_u32(slot_q), m.Q + (int64_t)x.j * Fp, row_bytes, bar);
-      }
-      gather_scalars<MODEL, LPR, V>(m, x.u, x.j, x.ctx, gl, ox);
-      if (kUserBias) bux = ld_cg_f64(m.user_bias + x.u);
-    };
-
-    for (;;) {
-      const bool active = n < nnz;
-      if (!__any_sync(0xffffffffu, active)) break;
-      if (active) {
-        if (!have) {
-          const unsigned f = poll(rec);
-          if (ready(rec, f)) {
-            issue(rec, o, bu);
-            have = true;
-          }
+      if (gl == 0) ok = (ld_relaxed_u32(done_j + rec.j) == (unsigned)rec.kj);
+      if (gl == 1) ok = (ld_relaxed_u32(done_u + rec.u) == (unsigned)rec.ku);
+      const unsigned b = __ballot_sync(gmask, ok);
+      if ((b & gmask) == gmask) {
+        __syncwarp(gmask);
+        const int64_t nn = n + T;
+        if (nn < nnz) next = ld_rec(recs + nn);  // flies during this rating's gather and arithmetic
+        UserRegs<V> us;
+        acc = __dadd_rn(acc, rating_update<MODEL, LPR, V>(m, rec.u, rec.j, rec.ctx, rec.r, lr, prod, gl, gmask, us,
+                                                          true, true));
+        __syncwarp(gmask);  // the group's stores happen-before lane 0's release
+        if (gl == 0) {
+          st_release_u32(done_j + rec.j, (unsigned)rec.kj + 1u);
+          st_relaxed_u32(done_u + rec.u, (unsigned)rec.ku + 1u);
         }
-        if (have) {
-          const int64_t n1 = n + T;
-          unsigned f1 = 0u;
-          if (n1 < nnz) f1 = poll(rec1);  // flies while we wait for our own rows
-          while (!mbar_try_wait(bar, parity)) {
-          }
-          parity ^= 1u;
-          UserRegs<V> us;
-#pragma unroll
-          for (int v = 0; v < V; v++) {
-            const int c = gl + v * LPR;
-            if (2 * c < Fp) {
-              us.p[v] = *reinterpret_cast<const double2*>(slot_p + 2 * c);
-              o.q[v] = *reinterpret_cast<const double2*>(slot_q + 2 * c);
-            } else {
-              us.p[v] = make_double2(0.0, 0.0);
-              o.q[v] = make_double2(0.0, 0.0);
-            }
-          }
-          us.bu = bu;
-          bool have1 = false;
-          if (n1 < nnz && ready(rec1, f1)) {  // ready() converges the group: every lane has read the slot
-            issue(rec1, o1, bu1);
-            have1 = true;
-          }
-          acc = __dadd_rn(acc, compute_scatter<MODEL, LPR, V>(m, rec.u, rec.j, rec.ctx, rec.r, lr, prod, gl, gmask,
-                                                              us, o, true));
-          __syncwarp(gmask);  // the group's stores happen-before lane 0's hand-off
-          if (gl == 0) {
-            while (lds_volatile_u32(ack + gid) != posted) {  // previous hand-off published?
-            }
-            mail[gid] = make_uint4(off_j + (unsigned)rec.j, (unsigned)rec.kj + 1u, off_u + (unsigned)rec.u,
-                                   (unsigned)rec.ku + 1u);
-            posted++;
-            sts_release_cta_u32(seq + gid, posted);
-          }
-          // advance
-          rec = rec1;
-          bu = bu1;
-          o.bj = o1.bj; o.cb = o1.cb; o.cb_ptr = o1.cb_ptr;
-          have = have1;
-          n = n1;
-          if (n + T < nnz) rec1 = ld_rec(recs + n + T);
-        }
+        rec = next;
+        n = nn;
       }
     }
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      atomicAdd(finished, 1u);
-    }
-    acc = warp_sum_f64(acc);
   }
 
+  acc = warp_sum_f64(acc);
   __shared__ double warp_sum[WARPS];
   if (lane == 0) warp_sum[warp] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int w = 0; w < WORKERS; w++) t += warp_sum[w];
+    for (int w = 0; w < WARPS; w++) t += warp_sum[w];
     block_partial[blockIdx.x] = t;
   }
 }
@@ -816,6 +615,22 @@ __global__ void __launch_bounds__(256) chunk_loss_reduce_kernel(const double* ch
     __syncthreads();
   }
   if (threadIdx.x == 0) block_partial[blockIdx.x] = sh[0];
+}
+
+// C1 helpers: the per-epoch exchange of the item block between user-range shards (one GPU each).
+//   delta = cur - old   (fused with nothing else: one streaming pass, HBM-bound)
+//   cur   = old + sum   (after the caller's all-reduce of delta)
+__global__ void __launch_bounds__(256) item_delta_kernel(const double* __restrict__ cur, const double* __restrict__ old,
+                                                         double* __restrict__ delta, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    delta[i] = __dsub_rn(cur[i], old[i]);
+}
+__global__ void __launch_bounds__(256) item_apply_kernel(double* __restrict__ cur, const double* __restrict__ old,
+                                                         const double* __restrict__ sum, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    cur[i] = __dadd_rn(old[i], sum[i]);
 }
 
 // K3: final loss reduction in fixed order, then `loss *= 0.5` (CAMF_CI.java:124).

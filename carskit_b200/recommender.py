@@ -90,12 +90,17 @@ class IterativeRecommender:
     algoName = "IterativeRecommender"
 
     def __init__(self, trainMatrix: TrainingSet, testMatrix: Optional[dict] = None, fold: int = -1,
-                 conf: Optional[Dict[str, str]] = None, device: int = 0, stream: int = 0):
+                 conf: Optional[Dict[str, str]] = None, device: int = 0, stream: int = 0, world: int = 1,
+                 group=None):
+        """`world` > 1: this process is one rank of a user-range-sharded job (sharding.py); trainMatrix /
+        testMatrix are THIS rank's shard and torch.distributed is initialised.  The engine then runs on
+        torch's current CUDA stream so the all-reduce is ordered with the kernels."""
         cf = dict(DEFAULT_CONF)
         cf.update(conf or {})
         self.cf = cf
         self.trainMatrix, self.testMatrix, self.fold = trainMatrix, testMatrix, fold
         self.device, self.stream = device, stream
+        self.world, self.group, self.exchange = world, group, None
         self.numUsers, self.numItems = trainMatrix.num_users, trainMatrix.num_items
         self.numConditions = trainMatrix.num_conditions
         self.globalMean = trainMatrix.global_mean  # Recommender.java:265
@@ -197,19 +202,35 @@ class IterativeRecommender:
         """cars_create + cars_upload: what buildModel() does before its first iteration."""
         if not self.model:
             raise RuntimeError("buildModel before initModel")
-        eng = capi.Engine(self._desc(), keepalive=self.trainMatrix)
+        eng = self._new_engine()
         try:
             eng.upload(self.model)
+            if self.world > 1:
+                from .sharding import ItemBlockExchange
+                self.exchange = ItemBlockExchange(eng, self._exchange_device(), self.group)
         except Exception:
             eng.close()
             raise
         self.engine = eng
         return eng
 
+    def _new_engine(self):
+        if self.world > 1 and not self.stream:  # the all-reduce must be stream-ordered with the kernels
+            import torch
+            self.stream = torch.cuda.current_stream(self.device).cuda_stream
+        return capi.Engine(self._desc(), keepalive=self.trainMatrix)
+
+    def _exchange_device(self):
+        import torch
+        return torch.device("cuda", self.device)
+
     def train_epoch(self, iter: int) -> bool:
         """One iteration of the `for (int iter = 1; ...)` loop (CAMF_CI.java:77-128): the per-rating pass on
         the device, then isConverged(iter) on the host.  Returns isConverged's verdict."""
-        self.loss = self.engine.epoch(self.lRate)
+        if self.world > 1:
+            self.loss = self.exchange.epoch(self.engine, self.lRate)
+        else:
+            self.loss = self.engine.epoch(self.lRate)
         self.iter_losses.append(self.loss)
         return self.isConverged(iter)
 
@@ -217,6 +238,7 @@ class IterativeRecommender:
         if self.engine is not None:
             self.engine.close()
             self.engine = None
+        self.exchange = None
 
     def buildModel(self):
         """Replaces the per-rating loop of buildModel() (CAMF_CI.java:74-131 and siblings): flatten once,
@@ -262,18 +284,33 @@ class IterativeRecommender:
             if eng is not self.engine:
                 eng.close()
 
+    def _allreduce_sum(self, vals):
+        if self.world <= 1:
+            return list(vals)
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor(list(vals), dtype=torch.float64, device=self._exchange_device())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return [float(x) for x in t.tolist()]
+
     def evalRatings(self) -> Dict[str, float]:
-        """Recommender.evalRatings (:504-594): MAE / RMSE over testMatrix with bounded predictions."""
+        """Recommender.evalRatings (:504-594): MAE / RMSE over testMatrix with bounded predictions.
+        Sharded runs sum |err|, err^2 and the count over the ranks (each rank holds its users' test ratings)."""
         t = self.testMatrix
-        if t is None or len(t["u"]) == 0:
+        if t is None:
             return {"MAE": float("nan"), "RMSE": float("nan")}
-        eng = self._eval_engine()
-        try:
-            sa, ss = eng.eval_ratings(t["u"], t["j"], t.get("ctx"), t["r"], self.minRate, self.maxRate)
-        finally:
-            if eng is not self.engine:
-                eng.close()
         n = len(t["u"])
+        sa = ss = 0.0
+        if n:
+            eng = self._eval_engine()
+            try:
+                sa, ss = eng.eval_ratings(t["u"], t["j"], t.get("ctx"), t["r"], self.minRate, self.maxRate)
+            finally:
+                if eng is not self.engine:
+                    eng.close()
+        sa, ss, n = self._allreduce_sum([sa, ss, float(n)])
+        if n == 0:
+            return {"MAE": float("nan"), "RMSE": float("nan")}
         return {"MAE": sa / n, "RMSE": math.sqrt(ss / n)}
 
     def execute(self, init: Optional[Dict[str, np.ndarray]] = None, seed: int = 0) -> Dict[str, float]:

@@ -1,0 +1,85 @@
+"""User-range sharding of the SGD hot path across the GPUs of one box.
+
+The reference is single-process, so this layer has no Java counterpart; it defines the N > 1 semantics:
+
+  * rank g of `world` owns the contiguous user range [lo, hi) (users are the rows of P): its ratings, its
+    rows of P, userBias (and ucBias for CAMF_CU) -- trained locally, never communicated;
+  * the item block (Q, itemBias, icBias) is replicated; every epoch each rank trains against its copy and
+    the ranks combine   block <- old + sum_g (new_g - old)   with ONE all-reduce (NCCL over NVLink);
+  * within a rank the epoch is the EXACT serial-equivalent engine epoch; across ranks it is a block-Jacobi
+    step (not serial-equivalent -- DESIGN.md "Multi-GPU" states the tolerance the tests use).
+
+Nothing here computes an update: the delta / apply passes are CUDA kernels inside libcarskit_b200.so
+(cars_epoch_sharded_begin / _finish); this module only moves a device buffer through torch.distributed.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+from .capi import TrainingSet
+
+
+def user_range(num_users: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced ranges: the first (num_users % world) ranks get one extra user."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world {world}")
+    base, extra = divmod(num_users, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_training_set(ts: TrainingSet, rank: int, world: int) -> Tuple[TrainingSet, int]:
+    """The ratings whose user lies in this rank's range, in the reference's iteration order, with user ids
+    rebased to the range (local row of P = u - lo).  Returns (shard, lo)."""
+    lo, hi = user_range(ts.num_users, rank, world)
+    keep = (ts.u >= lo) & (ts.u < hi)
+    shard = TrainingSet(num_users=hi - lo, num_items=ts.num_items, u=ts.u[keep] - lo, j=ts.j[keep], r=ts.r[keep],
+                        ctx=None if ts.ctx is None else ts.ctx[keep], num_conditions=ts.num_conditions,
+                        num_contexts=ts.num_contexts, ctx_ptr=ts.ctx_ptr, ctx_cond=ts.ctx_cond,
+                        global_mean=ts.global_mean)  # globalMean is a property of the WHOLE training matrix
+    return shard, lo
+
+
+def shard_test_set(test: Optional[dict], lo: int, hi: int) -> Optional[dict]:
+    if test is None:
+        return None
+    keep = (test["u"] >= lo) & (test["u"] < hi)
+    return {"u": test["u"][keep] - lo, "j": test["j"][keep],
+            "ctx": None if test.get("ctx") is None else test["ctx"][keep], "r": test["r"][keep]}
+
+
+def shard_user_rows(arr: np.ndarray, lo: int, hi: int) -> np.ndarray:
+    return np.ascontiguousarray(arr[lo:hi])
+
+
+class ItemBlockExchange:
+    """Per-epoch exchange of the item block.  `device` is a torch device; the delta buffer lives there
+    (CUDA for the engine; CPU tensors + gloo exercise the same orchestration in the CPU tests)."""
+
+    def __init__(self, engine, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.n = engine.item_block_doubles()
+        self.delta = torch.zeros(self.n, dtype=torch.float64, device=device)
+        self.scalar = torch.zeros(1, dtype=torch.float64, device=device)
+        self.bytes_per_epoch = self.n * 8
+
+    def epoch(self, engine, lrate: float) -> float:
+        """One sharded epoch; returns the GLOBAL loss (sum of the ranks' losses: the reference's loss is a sum
+        over ratings, CAMF_CI.java:91-124)."""
+        ptr = self.delta.data_ptr()
+        engine.epoch_sharded_begin(lrate, ptr)
+        self.dist.all_reduce(self.delta, op=self.dist.ReduceOp.SUM, group=self.group)
+        local = engine.epoch_sharded_finish(ptr)
+        self.scalar[0] = local
+        self.dist.all_reduce(self.scalar, op=self.dist.ReduceOp.SUM, group=self.group)
+        return float(self.scalar.item())
+
+    def sum_scalars(self, *vals: float):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.delta.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return [float(x) for x in t.tolist()]

@@ -52,14 +52,14 @@ enum cars_model {
  *        DESIGN.md). */
 enum cars_mode { CARS_EXACT = 0, CARS_FAST = 1 };
 
-/* How EXACT mode orders independent ratings (both are serial-equivalent and bit-identical):
- * DATAFLOW  (default) ratings stay in reference order; each waits for the previous rating of its user
- *           and of its item through per-row completion counters; a user's factor row stays in
- *           registers across consecutive ratings of that user.
- * WAVEFRONT ratings are sorted into dependency levels; a grid-wide barrier separates levels.
- * FLAGGED   the WAVEFRONT order without barriers: every rating waits only for its own two predecessors.
- */
-enum cars_schedule { CARS_SCHED_DATAFLOW = 0, CARS_SCHED_WAVEFRONT = 1, CARS_SCHED_FLAGGED = 2 };
+/* How EXACT mode orders independent ratings (all three are serial-equivalent and bit-identical):
+ * FLAGGED   (default) ratings are sorted into dependency levels and dealt round-robin to the resident
+ *           groups; every rating waits only for the previous rating of its user and of its item through
+ *           per-row completion counters (no grid-wide barrier; levels overlap).
+ * WAVEFRONT same order, a grid-wide barrier separates levels.
+ * DATAFLOW  ratings stay in reference order; same counters; a user's factor row stays in registers across
+ *           consecutive ratings of that user (cheapest set-up, fastest on small inputs sorted by user). */
+enum cars_schedule { CARS_SCHED_FLAGGED = 0, CARS_SCHED_WAVEFRONT = 1, CARS_SCHED_DATAFLOW = 2 };
 
 enum cars_error {
   CARS_OK            =  0,
@@ -163,6 +163,22 @@ int cars_predict(cars_handle* h, int64_t n, const int32_t* u, const int32_t* j, 
 int cars_eval_ratings(cars_handle* h, int64_t n, const int32_t* u, const int32_t* j, const int32_t* ctx,
                       const double* r, double min_rate, double max_rate, double* sum_abs_err,
                       double* sum_sq_err);
+
+/* ---- multi-GPU: one process (and one handle) per GPU, users sharded by contiguous range ------------------
+ * The reference is single-process; SURVEY.md 8e defines the sharded semantics: every rank trains the
+ * ratings of ITS users against its own copy of the item-side arrays (Q, itemBias, icBias -- "the item
+ * block"), then the ranks combine  item_block <- old + sum_over_ranks(new_rank - old)  once per epoch.
+ * Within a rank the epoch is EXACT (serial-equivalent on the rank's ratings); across ranks it is a
+ * block-Jacobi step, not serial-equivalent (DESIGN.md "Multi-GPU").  The library does not link NCCL:
+ * the caller owns the DEVICE buffer `dev_delta` (cars_item_block_doubles() doubles, e.g. a torch tensor),
+ * all-reduces it (sum) on the handle's stream between the two calls below.
+ *   cars_epoch_sharded_begin : snapshot the item block, run the epoch, write (new - old) to dev_delta
+ *   cars_epoch_sharded_finish: item block <- old + dev_delta (now the sum over ranks); returns the local loss
+ * Layout of the item block: [Q (num_items x Fp, row stride Fp = F rounded up to even) | item_bias | ic_bias],
+ * members the model lacks are absent. */
+int cars_item_block_doubles(const cars_handle* h, int64_t* out);
+int cars_epoch_sharded_begin(cars_handle* h, double lrate, double* dev_delta);
+int cars_epoch_sharded_finish(cars_handle* h, const double* dev_delta, double* loss_out);
 
 void cars_destroy(cars_handle* h);
 

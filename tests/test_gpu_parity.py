@@ -22,7 +22,7 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "sgd_golden.json")
 CTX_MODELS = (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU)
 
 
-def run_both(oracle, model, ts, F, epochs, seed, mode=capi.EXACT, lr0=capi.f32(0.02), schedule=capi.SCHED_DATAFLOW):
+def run_both(oracle, model, ts, F, epochs, seed, mode=capi.EXACT, lr0=capi.f32(0.02), schedule=capi.SCHED_FLAGGED):
     desc = capi.make_desc(ts, model, F, mode=mode, schedule=schedule, **REGS)
     ref = init_arrays(oracle, model, ts, F, seed)
     got = {k: v.copy() for k, v in ref.items()}
