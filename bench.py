@@ -237,7 +237,9 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm: `value` -----------------------------------------------------
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream(device=dev)  # the engine's kernels, the collectives and the events share it
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
     rec = Rec(ts, None, conf=conf, device=local_rank, stream=stream, world=world)
     rec.initModel(init={k: v.copy() for k, v in arrs.items()})
     t0 = time.time()

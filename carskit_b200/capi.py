@@ -110,7 +110,7 @@ def load_library(path: Optional[str] = None):
     lib.cars_item_block_doubles.restype = C.c_int
     lib.cars_epoch_sharded_begin.argtypes = [H, C.c_double, C.c_void_p]
     lib.cars_epoch_sharded_begin.restype = C.c_int
-    lib.cars_epoch_sharded_finish.argtypes = [H, C.c_void_p, _f64p]
+    lib.cars_epoch_sharded_finish.argtypes = [H, C.c_void_p, C.c_double, _f64p]
     lib.cars_epoch_sharded_finish.restype = C.c_int
     lib.cars_version.argtypes = []
     lib.cars_version.restype = C.c_char_p
@@ -266,9 +266,9 @@ class Engine:
         """dev_delta_ptr: device address of item_block_doubles() doubles owned by the caller."""
         self._check(self.lib.cars_epoch_sharded_begin(self.h, lrate, C.c_void_p(dev_delta_ptr)))
 
-    def epoch_sharded_finish(self, dev_delta_ptr: int) -> float:
+    def epoch_sharded_finish(self, dev_delta_ptr: int, scale: float = 1.0) -> float:
         loss = C.c_double()
-        self._check(self.lib.cars_epoch_sharded_finish(self.h, C.c_void_p(dev_delta_ptr), C.byref(loss)))
+        self._check(self.lib.cars_epoch_sharded_finish(self.h, C.c_void_p(dev_delta_ptr), scale, C.byref(loss)))
         return loss.value
 
     def predict(self, u, j, ctx=None, bound=False, min_rate=0.0, max_rate=0.0) -> np.ndarray:

@@ -228,7 +228,7 @@ static LaunchPlan pick_flagged(int Fp, int variant) {
 }
 
 static LaunchPlan pick_flagged_plan(int model, int Fp) {
-  const int v = wavefront_variant();
+  const int v = wavefront_variant(3);
   switch (model) {
     case CARS_PMF: return pick_flagged<M_PMF>(Fp, v);
     case CARS_BIASEDMF: return pick_flagged<M_BIASEDMF>(Fp, v);
@@ -773,7 +773,7 @@ extern "C" int cars_epoch_sharded_begin(cars_handle* h, double lrate, double* de
   return CARS_OK;
 }
 
-extern "C" int cars_epoch_sharded_finish(cars_handle* h, const double* dev_delta, double* loss_out) {
+extern "C" int cars_epoch_sharded_finish(cars_handle* h, const double* dev_delta, double scale, double* loss_out) {
   if (!h) return CARS_E_INVALID;
   if (!h->sharded_pending) return fail(h, CARS_E_STATE, "no sharded epoch pending");
   if (!dev_delta) return fail(h, CARS_E_INVALID, "dev_delta is NULL");
@@ -783,7 +783,7 @@ extern "C" int cars_epoch_sharded_finish(cars_handle* h, const double* dev_delta
   int64_t off = 0;
   const int blocks = h->sm_count * 8;
   for (int i = 0; i < k; i++) {
-    item_apply_kernel<<<blocks, 256, 0, h->stream>>>(parts[i].ptr, h->d_item_old + off, dev_delta + off, parts[i].n);
+    item_apply_kernel<<<blocks, 256, 0, h->stream>>>(parts[i].ptr, h->d_item_old + off, dev_delta + off, scale, parts[i].n);
     CUDA_TRY(h, cudaGetLastError());
     h->st.kernel_launches += 1;
     off += parts[i].n;

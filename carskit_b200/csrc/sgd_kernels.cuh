@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(256) chunk_loss_reduce_kernel(const double* ch
 
 // C1 helpers: the per-epoch exchange of the item block between user-range shards (one GPU each).
 //   delta = cur - old   (fused with nothing else: one streaming pass, HBM-bound)
-//   cur   = old + sum   (after the caller's all-reduce of delta)
+//   cur   = old + scale * sum   (after the caller's all-reduce of delta)
 __global__ void __launch_bounds__(256) item_delta_kernel(const double* __restrict__ cur, const double* __restrict__ old,
                                                          double* __restrict__ delta, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -627,10 +627,10 @@ __global__ void __launch_bounds__(256) item_delta_kernel(const double* __restric
     delta[i] = __dsub_rn(cur[i], old[i]);
 }
 __global__ void __launch_bounds__(256) item_apply_kernel(double* __restrict__ cur, const double* __restrict__ old,
-                                                         const double* __restrict__ sum, int64_t n) {
+                                                         const double* __restrict__ sum, double scale, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    cur[i] = __dadd_rn(old[i], sum[i]);
+    cur[i] = __dadd_rn(old[i], __dmul_rn(scale, sum[i]));
 }
 
 // K3: final loss reduction in fixed order, then `loss *= 0.5` (CAMF_CI.java:124).

@@ -91,7 +91,7 @@ class IterativeRecommender:
 
     def __init__(self, trainMatrix: TrainingSet, testMatrix: Optional[dict] = None, fold: int = -1,
                  conf: Optional[Dict[str, str]] = None, device: int = 0, stream: int = 0, world: int = 1,
-                 group=None):
+                 group=None, combine: str = "mean"):
         """`world` > 1: this process is one rank of a user-range-sharded job (sharding.py); trainMatrix /
         testMatrix are THIS rank's shard and torch.distributed is initialised.  The engine then runs on
         torch's current CUDA stream so the all-reduce is ordered with the kernels."""
@@ -100,7 +100,8 @@ class IterativeRecommender:
         self.cf = cf
         self.trainMatrix, self.testMatrix, self.fold = trainMatrix, testMatrix, fold
         self.device, self.stream = device, stream
-        self.world, self.group, self.exchange = world, group, None
+        self.world, self.group, self.exchange, self.combine = world, group, None, combine
+        self._torch_stream = None
         self.numUsers, self.numItems = trainMatrix.num_users, trainMatrix.num_items
         self.numConditions = trainMatrix.num_conditions
         self.globalMean = trainMatrix.global_mean  # Recommender.java:265
@@ -207,7 +208,8 @@ class IterativeRecommender:
             eng.upload(self.model)
             if self.world > 1:
                 from .sharding import ItemBlockExchange
-                self.exchange = ItemBlockExchange(eng, self._exchange_device(), self.group)
+                self.exchange = ItemBlockExchange(eng, self._exchange_device(), self.group, self.combine,
+                                                  self._torch_stream)
         except Exception:
             eng.close()
             raise
@@ -215,9 +217,13 @@ class IterativeRecommender:
         return eng
 
     def _new_engine(self):
-        if self.world > 1 and not self.stream:  # the all-reduce must be stream-ordered with the kernels
+        if self.world > 1:  # the all-reduce must be stream-ordered with the kernels
             import torch
-            self.stream = torch.cuda.current_stream(self.device).cuda_stream
+            if self.stream:
+                self._torch_stream = torch.cuda.ExternalStream(self.stream, device=self.device)
+            else:
+                self._torch_stream = torch.cuda.Stream(device=self.device)
+                self.stream = self._torch_stream.cuda_stream
         return capi.Engine(self._desc(), keepalive=self.trainMatrix)
 
     def _exchange_device(self):
@@ -289,9 +295,12 @@ class IterativeRecommender:
             return list(vals)
         import torch
         import torch.distributed as dist
-        t = torch.tensor(list(vals), dtype=torch.float64, device=self._exchange_device())
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-        return [float(x) for x in t.tolist()]
+        import contextlib
+        ctx = torch.cuda.stream(self._torch_stream) if self._torch_stream is not None else contextlib.nullcontext()
+        with ctx:
+            t = torch.tensor(list(vals), dtype=torch.float64, device=self._exchange_device())
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            return [float(x) for x in t.tolist()]
 
     def evalRatings(self) -> Dict[str, float]:
         """Recommender.evalRatings (:504-594): MAE / RMSE over testMatrix with bounded predictions.

@@ -5,7 +5,11 @@ The reference is single-process, so this layer has no Java counterpart; it defin
   * rank g of `world` owns the contiguous user range [lo, hi) (users are the rows of P): its ratings, its
     rows of P, userBias (and ucBias for CAMF_CU) -- trained locally, never communicated;
   * the item block (Q, itemBias, icBias) is replicated; every epoch each rank trains against its copy and
-    the ranks combine   block <- old + sum_g (new_g - old)   with ONE all-reduce (NCCL over NVLink);
+    the ranks combine   block <- old + scale * sum_g (new_g - old)   with ONE all-reduce (NCCL over NVLink).
+    scale = 1/world ("mean", the default) averages the ranks' item blocks -- stable for any shard size;
+    scale = 1 ("sum") adds the ranks' steps, which is only safe while one epoch moves an item row a little
+    (with ~1000 ratings per item and shard every rank nearly converges the row on its own, and the summed
+    step overshoots world-fold: measured to diverge on the bench workload at world = 2);
   * within a rank the epoch is the EXACT serial-equivalent engine epoch; across ranks it is a block-Jacobi
     step (not serial-equivalent -- DESIGN.md "Multi-GPU" states the tolerance the tests use).
 
@@ -58,11 +62,16 @@ class ItemBlockExchange:
     """Per-epoch exchange of the item block.  `device` is a torch device; the delta buffer lives there
     (CUDA for the engine; CPU tensors + gloo exercise the same orchestration in the CPU tests)."""
 
-    def __init__(self, engine, device, group=None):
+    def __init__(self, engine, device, group=None, combine: str = "mean", torch_stream=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.group = group
+        if combine not in ("mean", "sum"):
+            raise ValueError(combine)
+        self.scale = 1.0 / dist.get_world_size(group) if combine == "mean" else 1.0
+        # the engine's CUDA stream as a torch stream: collectives issued under it are ordered with the kernels
+        self.torch_stream = torch_stream
         self.n = engine.item_block_doubles()
         self.delta = torch.zeros(self.n, dtype=torch.float64, device=device)
         self.scalar = torch.zeros(1, dtype=torch.float64, device=device)
@@ -73,13 +82,22 @@ class ItemBlockExchange:
         over ratings, CAMF_CI.java:91-124)."""
         ptr = self.delta.data_ptr()
         engine.epoch_sharded_begin(lrate, ptr)
-        self.dist.all_reduce(self.delta, op=self.dist.ReduceOp.SUM, group=self.group)
-        local = engine.epoch_sharded_finish(ptr)
-        self.scalar[0] = local
-        self.dist.all_reduce(self.scalar, op=self.dist.ReduceOp.SUM, group=self.group)
-        return float(self.scalar.item())
+        with self._on_stream():
+            self.dist.all_reduce(self.delta, op=self.dist.ReduceOp.SUM, group=self.group)
+        local = engine.epoch_sharded_finish(ptr, self.scale)
+        with self._on_stream():
+            self.scalar[0] = local
+            self.dist.all_reduce(self.scalar, op=self.dist.ReduceOp.SUM, group=self.group)
+            return float(self.scalar.item())
+
+    def _on_stream(self):
+        import contextlib
+        if self.torch_stream is None:
+            return contextlib.nullcontext()
+        return self.torch.cuda.stream(self.torch_stream)
 
     def sum_scalars(self, *vals: float):
-        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.delta.device)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
-        return [float(x) for x in t.tolist()]
+        with self._on_stream():
+            t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.delta.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            return [float(x) for x in t.tolist()]

@@ -173,12 +173,14 @@ int cars_eval_ratings(cars_handle* h, int64_t n, const int32_t* u, const int32_t
  * the caller owns the DEVICE buffer `dev_delta` (cars_item_block_doubles() doubles, e.g. a torch tensor),
  * all-reduces it (sum) on the handle's stream between the two calls below.
  *   cars_epoch_sharded_begin : snapshot the item block, run the epoch, write (new - old) to dev_delta
- *   cars_epoch_sharded_finish: item block <- old + dev_delta (now the sum over ranks); returns the local loss
+ *   cars_epoch_sharded_finish: item block <- old + scale * dev_delta (dev_delta now holds the sum over ranks;
+ *                              scale = 1/world averages the ranks' item blocks, scale = 1 sums their
+ *                              steps); returns the local loss
  * Layout of the item block: [Q (num_items x Fp, row stride Fp = F rounded up to even) | item_bias | ic_bias],
  * members the model lacks are absent. */
 int cars_item_block_doubles(const cars_handle* h, int64_t* out);
 int cars_epoch_sharded_begin(cars_handle* h, double lrate, double* dev_delta);
-int cars_epoch_sharded_finish(cars_handle* h, const double* dev_delta, double* loss_out);
+int cars_epoch_sharded_finish(cars_handle* h, const double* dev_delta, double scale, double* loss_out);
 
 void cars_destroy(cars_handle* h);
 

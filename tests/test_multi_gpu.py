@@ -11,7 +11,7 @@ from tests.test_sharding import _free_port, _problem, block_jacobi_reference
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, model_name, F, epochs, out_dir):
+def _worker(rank, world, port, model_name, F, epochs, out_dir, combine):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -23,7 +23,7 @@ def _worker(rank, world, port, model_name, F, epochs, out_dir):
         hi = lo + shard.num_users
         conf = {"num.factors": str(F), "num.max.iter": str(epochs)}
         rec = recommender.getRecommender(model_name)(shard, sharding.shard_test_set(test, lo, hi), conf=conf,
-                                                     device=rank, world=world)
+                                                     device=rank, world=world, combine=combine)
         local = {k: (sharding.shard_user_rows(v, lo, hi) if k in ("P", "user_bias", "uc_bias") else v.copy())
                  for k, v in init.items()}
         rec.initModel(init=local)
@@ -36,15 +36,15 @@ def _worker(rank, world, port, model_name, F, epochs, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("model_name", ["camf_ci", "camf_cu", "biasedmf"])
-def test_two_gpus_match_block_jacobi_reference(oracle, cars_lib, tmp_path, model_name):
+@pytest.mark.parametrize("model_name,combine", [("camf_ci", "mean"), ("camf_cu", "mean"), ("biasedmf", "sum")])
+def test_two_gpus_match_block_jacobi_reference(oracle, cars_lib, tmp_path, model_name, combine):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
     F, epochs, world = 8, 3, 2
-    mp.spawn(_worker, args=(world, _free_port(), model_name, F, epochs, str(tmp_path)), nprocs=world, join=True)
-    shards, locals_, item, losses = block_jacobi_reference(oracle, model_name, F, epochs, world)
+    mp.spawn(_worker, args=(world, _free_port(), model_name, F, epochs, str(tmp_path), combine), nprocs=world, join=True)
+    shards, locals_, item, losses = block_jacobi_reference(oracle, model_name, F, epochs, world, combine)
     for g in range(world):
         got = np.load(tmp_path / f"rank{g}.npz")
         for k, v in locals_[g].items():

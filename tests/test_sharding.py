@@ -70,8 +70,8 @@ class OracleEngine:
         self.loss = self.oracle.epoch(self.desc, self.arrs, lrate)
         self._view(ptr)[:] = self._pack() - self.old
 
-    def epoch_sharded_finish(self, ptr):
-        new = self.old + self._view(ptr)
+    def epoch_sharded_finish(self, ptr, scale=1.0):
+        new = self.old + scale * self._view(ptr)
         off = 0
         for k in self.members:
             a = self.arrs[k]
@@ -102,7 +102,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, model_name, F, epochs, out_dir):
+def _worker(rank, world, port, model_name, F, epochs, out_dir, combine):
     import torch
     import torch.distributed as dist
     from oracle import oracle_py as orc
@@ -125,7 +125,7 @@ def _worker(rank, world, port, model_name, F, epochs, out_dir):
                 return self.engine if self.engine is not None else OracleEngine(self._desc(), self.MODEL, self.model, orc)
 
         conf = {"num.factors": str(F), "num.max.iter": str(epochs)}
-        rec = CpuRec(shard, sharding.shard_test_set(test, lo, hi), conf=conf, world=world)
+        rec = CpuRec(shard, sharding.shard_test_set(test, lo, hi), conf=conf, world=world, combine=combine)
         local = {k: (sharding.shard_user_rows(v, lo, hi) if k in ("P", "user_bias", "uc_bias") else v.copy())
                  for k, v in init.items()}
         rec.initModel(init=local)
@@ -149,7 +149,7 @@ def _problem(model_name, F):
     return ts, test, init
 
 
-def block_jacobi_reference(oracle, model_name, F, epochs, world):
+def block_jacobi_reference(oracle, model_name, F, epochs, world, combine="mean"):
     """Single-process statement of the sharded semantics, driven like buildModel()."""
     model = capi.MODEL_NAMES[model_name]
     ts, test, init = _problem(model_name, F)
@@ -159,6 +159,7 @@ def block_jacobi_reference(oracle, model_name, F, epochs, world):
     locals_ = [{k: sharding.shard_user_rows(v, lo, lo + sh.num_users) for k, v in init.items() if k in user_side}
                for sh, lo in shards]
     lr, last, losses = capi.f32(0.02), 0.0, []
+    scale = 1.0 / world if combine == "mean" else 1.0
     for it in range(1, epochs + 1):
         deltas, loss = [], 0.0
         for (sh, lo), loc in zip(shards, locals_):
@@ -169,7 +170,7 @@ def block_jacobi_reference(oracle, model_name, F, epochs, world):
             s = deltas[0][k]
             for d in deltas[1:]:
                 s = s + d[k]
-            item[k] = item[k] + s
+            item[k] = item[k] + scale * s
         losses.append(loss)
         if it > 1:  # bold driver, IterativeRecommender.java:216-229
             lr = lr * 1.05 if abs(last) > abs(loss) else lr * 0.5
@@ -177,12 +178,12 @@ def block_jacobi_reference(oracle, model_name, F, epochs, world):
     return shards, locals_, item, losses
 
 
-@pytest.mark.parametrize("model_name", ["camf_ci", "camf_cu", "biasedmf"])
-def test_two_rank_gloo_matches_block_jacobi_reference(oracle, tmp_path, model_name):
+@pytest.mark.parametrize("model_name,combine", [("camf_ci", "mean"), ("camf_cu", "mean"), ("biasedmf", "sum")])
+def test_two_rank_gloo_matches_block_jacobi_reference(oracle, tmp_path, model_name, combine):
     import torch.multiprocessing as mp
     F, epochs, world = 8, 3, 2
-    mp.spawn(_worker, args=(world, _free_port(), model_name, F, epochs, str(tmp_path)), nprocs=world, join=True)
-    shards, locals_, item, losses = block_jacobi_reference(oracle, model_name, F, epochs, world)
+    mp.spawn(_worker, args=(world, _free_port(), model_name, F, epochs, str(tmp_path), combine), nprocs=world, join=True)
+    shards, locals_, item, losses = block_jacobi_reference(oracle, model_name, F, epochs, world, combine)
     for g in range(world):
         got = np.load(tmp_path / f"rank{g}.npz")
         # the sum of two deltas is order-independent, so world = 2 is bit-exact; the loss is a sum of two terms
