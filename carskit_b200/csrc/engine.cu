@@ -5,6 +5,7 @@
 // update exists in this library: without a CUDA sm_100 device cars_create() fails.
 #include "../../include/carskit_b200.h"
 #include "schedule.cuh"
+#include "schedule_gpu.cuh"
 #include "sgd_kernels.cuh"
 
 #include <cuda_runtime.h>
@@ -387,7 +388,12 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
 
   // ---- range checks on the rating arrays -------------------------------------------------------------
   const int64_t nnz = desc->nnz;
-  for (int64_t n = 0; n < nnz; n++) {
+  int sched_req = desc->schedule;
+  if (const char* e = getenv("CARS_SCHEDULE"))
+    sched_req = strcmp(e, "wavefront") == 0 ? CARS_SCHED_WAVEFRONT : strcmp(e, "dataflow") == 0 ? CARS_SCHED_DATAFLOW : CARS_SCHED_FLAGGED;
+  // the flagged schedule validates the ids inside its own pass over the ratings
+  const bool fused_check = (sched_req == CARS_SCHED_FLAGGED && desc->model != CARS_CAMF_C);
+  for (int64_t n = 0; n < nnz && !fused_check; n++) {
     if ((unsigned)desc->u[n] >= (unsigned)desc->num_users || (unsigned)desc->j[n] >= (unsigned)desc->num_items ||
         (has_ctx && (unsigned)desc->ctx[n] >= (unsigned)desc->num_contexts)) {
       fail(h, CARS_E_INVALID, "rating %lld has an id out of range (u=%d j=%d ctx=%d)", (long long)n, desc->u[n],
@@ -399,9 +405,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   // ---- launch geometry (the dataflow schedule sizes its chunks from the number of resident groups) ------
   const int model = desc->model;
   h->serial = (model == CARS_CAMF_C);
-  int sched = desc->schedule;
-  if (const char* e = getenv("CARS_SCHEDULE"))
-    sched = strcmp(e, "wavefront") == 0 ? CARS_SCHED_WAVEFRONT : strcmp(e, "dataflow") == 0 ? CARS_SCHED_DATAFLOW : CARS_SCHED_FLAGGED;
+  const int sched = sched_req;
   if (sched != CARS_SCHED_DATAFLOW && sched != CARS_SCHED_WAVEFRONT && sched != CARS_SCHED_FLAGGED) {
     fail(h, CARS_E_INVALID, "unknown schedule %d", sched);
     return bail(CARS_E_INVALID);
@@ -483,21 +487,27 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     if (h->loss_blocks > 1024) h->loss_blocks = 1024;
     CUDA_TRY_H(cudaStreamSynchronize(h->stream));  // recs / chunk_start die at the end of this block
   } else if (h->flagged) {
-    std::vector<RatingRec> recs;
-    if (!build_flagged_schedule(desc->num_users, desc->num_items, nnz, desc->u, desc->j, has_ctx ? desc->ctx : nullptr,
-                                desc->r, &recs, &h->num_levels, &h->max_level_size)) {
-      fail(h, CARS_E_OOM, "host allocation failed while building the schedule");
-      return bail(CARS_E_OOM);
-    }
-    h->st.schedule_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    // level assignment on the host (one sequential pass, overlapped with the H2D copies), sort on the device
     CUDA_TRY_H(dev_alloc(&h->d_rec, (size_t)nnz));
     h->flags_words = 64 + I + U;
     CUDA_TRY_H(dev_alloc(&h->d_flags, h->flags_words));
-    if (nnz) {
-      CUDA_TRY_H(cudaMemcpyAsync(h->d_rec, recs.data(), (size_t)nnz * sizeof(RatingRec), cudaMemcpyHostToDevice, h->stream));
-      h->st.h2d_bytes += nnz * (int64_t)sizeof(RatingRec);
+    FlaggedBuild fb;
+    cudaError_t be = build_flagged_on_device(desc->num_users, desc->num_items, desc->num_contexts, nnz, desc->u, desc->j,
+                                             has_ctx ? desc->ctx : nullptr, desc->r, h->stream, h->sm_count, h->d_rec, &fb);
+    if (fb.bad_index >= 0) {
+      const int64_t n = fb.bad_index;
+      fail(h, CARS_E_INVALID, "rating %lld has an id out of range (u=%d j=%d ctx=%d)", (long long)n, desc->u[n], desc->j[n],
+           has_ctx ? desc->ctx[n] : -1);
+      return bail(CARS_E_INVALID);
     }
-    CUDA_TRY_H(cudaStreamSynchronize(h->stream));
+    if (be != cudaSuccess) {
+      fail(h, be == cudaErrorMemoryAllocation ? CARS_E_OOM : CARS_E_CUDA, "building the schedule failed: %s", cudaGetErrorString(be));
+      return bail(be == cudaErrorMemoryAllocation ? CARS_E_OOM : CARS_E_CUDA);
+    }
+    h->num_levels = fb.num_levels;
+    h->max_level_size = fb.max_level_size;
+    h->st.h2d_bytes += fb.h2d_bytes;
+    h->st.schedule_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   } else {
     std::vector<int64_t> level_start;
     HostSchedule sched_host;
