@@ -332,7 +332,7 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl_name, "model": wl["model"], "factors": F, "users_per_gpu": wl["users"],
                    "items": wl["items"], "conditions": int(sum(wl["dims"])) if wl["dims"] else 0, "context_dims": D,
-                   "nnz_per_gpu": nnz_local, "nnz_total": int(nnz_total), "mode": "exact (serial-equivalent wavefront)",
+                   "nnz_per_gpu": nnz_local, "nnz_total": int(nnz_total), "mode": "exact (serial-equivalent; flagged wavefront schedule)",
                    "levels": int(st0.num_levels), "parallelism": f"user-range shards x{world}" if world > 1 else "1 gpu",
                    "l2": "inputs larger than L2 (ratings 2 GB + P 0.5 GB per epoch vs 126 MB L2); no flush",
                    "e2e_definition": f"recommender.buildModel() with num.max.iter={args.steps}: cars_create (schedule "
@@ -343,7 +343,7 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
                 "schedule_ms": st2.schedule_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "sgd_wavefront_kernel", "kernel_ms_per_launch": kms,
+                     "traffic": traffic, "kernel": "sgd_flagged_kernel", "kernel_ms_per_launch": kms,
                      "algorithmic_bytes_per_update": B, "updates_per_launch": nnz_local, "peak_source": peak_src},
         "cpu_baseline": cpu,
     }

@@ -35,7 +35,7 @@ class CarsDesc(C.Structure):
         ("global_mean", C.c_double),
         ("reg_u", C.c_double), ("reg_i", C.c_double), ("reg_b", C.c_double), ("reg_c", C.c_double),
         ("reg_lw", C.c_double), ("reg_lf", C.c_double),
-        ("rank", C.c_int32), ("world_size", C.c_int32),
+        ("num_context_dims", C.c_int32), ("reserved1", C.c_int32),
         ("stream", C.c_void_p),
     ]
 
@@ -58,8 +58,18 @@ EXPORTS = [
     "cars_create", "cars_upload", "cars_epoch", "cars_epoch_begin", "cars_epoch_wait", "cars_download",
     "cars_predict", "cars_eval_ratings", "cars_destroy", "cars_last_error", "cars_get_stats",
     "cars_get_stream", "cars_version", "cars_item_block_doubles", "cars_epoch_sharded_begin",
-    "cars_epoch_sharded_finish",
+    "cars_epoch_sharded_finish", "cars_fm_create", "cars_fm_upload", "cars_fm_prepare", "cars_fm_iteration",
+    "cars_fm_download", "cars_fm_predict", "cars_fm_get_stats", "cars_fm_last_error", "cars_fm_destroy",
 ]
+
+
+class CarsFmArrays(C.Structure):
+    _fields_ = [("w0", _f64p), ("w", _f64p), ("V", _f64p)]
+
+
+class CarsFmStats(C.Structure):
+    _fields_ = [("nnz", C.c_int64), ("p", C.c_int64), ("pieces", C.c_int64), ("kernel_launches", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("last_iteration_ms", C.c_double)]
 
 
 class CarsError(RuntimeError):
@@ -112,6 +122,24 @@ def load_library(path: Optional[str] = None):
     lib.cars_epoch_sharded_begin.restype = C.c_int
     lib.cars_epoch_sharded_finish.argtypes = [H, C.c_void_p, C.c_double, _f64p]
     lib.cars_epoch_sharded_finish.restype = C.c_int
+    lib.cars_fm_create.argtypes = [C.POINTER(CarsDesc), C.POINTER(H)]
+    lib.cars_fm_create.restype = C.c_int
+    lib.cars_fm_upload.argtypes = [H, C.POINTER(CarsFmArrays)]
+    lib.cars_fm_upload.restype = C.c_int
+    lib.cars_fm_download.argtypes = [H, C.POINTER(CarsFmArrays)]
+    lib.cars_fm_download.restype = C.c_int
+    lib.cars_fm_prepare.argtypes = [H]
+    lib.cars_fm_prepare.restype = C.c_int
+    lib.cars_fm_iteration.argtypes = [H, _f64p]
+    lib.cars_fm_iteration.restype = C.c_int
+    lib.cars_fm_predict.argtypes = [H, C.c_int64, _i32p, _i32p, _i32p, C.c_int32, C.c_double, C.c_double, _f64p]
+    lib.cars_fm_predict.restype = C.c_int
+    lib.cars_fm_get_stats.argtypes = [H, C.POINTER(CarsFmStats)]
+    lib.cars_fm_get_stats.restype = C.c_int
+    lib.cars_fm_last_error.argtypes = [H]
+    lib.cars_fm_last_error.restype = C.c_char_p
+    lib.cars_fm_destroy.argtypes = [H]
+    lib.cars_fm_destroy.restype = None
     lib.cars_version.argtypes = []
     lib.cars_version.restype = C.c_char_p
     if path is None:
@@ -171,7 +199,7 @@ class TrainingSet:
 
 def make_desc(ts: TrainingSet, model: int, num_factors: int, *, mode: int = EXACT, device: int = 0,
               reg_u: float = 0.0, reg_i: float = 0.0, reg_b: float = 0.0, reg_c: float = 0.0,
-              reg_lw: float = 0.0, reg_lf: float = 0.0, rank: int = 0, world_size: int = 1,
+              reg_lw: float = 0.0, reg_lf: float = 0.0, num_context_dims: int = 0,
               stream: int = 0, schedule: int = SCHED_FLAGGED) -> CarsDesc:
     """Fill a cars_desc.  The reg_* values must already be float-widened (use f32())."""
     d = CarsDesc()
@@ -189,7 +217,7 @@ def make_desc(ts: TrainingSet, model: int, num_factors: int, *, mode: int = EXAC
     d.ctx_cond = _ptr_i32(ts.ctx_cond) if use_ctx else None
     d.global_mean = ts.global_mean
     d.reg_u, d.reg_i, d.reg_b, d.reg_c, d.reg_lw, d.reg_lf = reg_u, reg_i, reg_b, reg_c, reg_lw, reg_lf
-    d.rank, d.world_size = rank, world_size
+    d.num_context_dims = num_context_dims
     d.stream = stream or None
     return d
 
@@ -301,6 +329,75 @@ class Engine:
     def close(self):
         if self.h:
             self.lib.cars_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_fm_arrays(arrs: dict) -> CarsFmArrays:
+    a = CarsFmArrays()
+    a.w0, a.w, a.V = _ptr_f64(arrs["w0"]), _ptr_f64(arrs["w"]), _ptr_f64(arrs["V"])
+    return a
+
+
+class FmEngine:
+    """cars_fm_create .. cars_fm_destroy (FM.java, ALS)."""
+
+    def __init__(self, desc: CarsDesc, keepalive=None):
+        self.lib = load_library()
+        self._keep = keepalive
+        self.h = C.c_void_p()
+        rc = self.lib.cars_fm_create(C.byref(desc), C.byref(self.h))
+        if rc != 0:
+            raise CarsError(rc, self.lib.cars_fm_last_error(None).decode())
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise CarsError(rc, self.lib.cars_fm_last_error(self.h).decode())
+
+    def upload(self, arrs: dict):
+        a = make_fm_arrays(arrs)
+        self._check(self.lib.cars_fm_upload(self.h, C.byref(a)))
+
+    def download(self, arrs: dict):
+        a = make_fm_arrays(arrs)
+        self._check(self.lib.cars_fm_download(self.h, C.byref(a)))
+
+    def prepare(self):
+        self._check(self.lib.cars_fm_prepare(self.h))
+
+    def iteration(self) -> float:
+        loss = C.c_double()
+        self._check(self.lib.cars_fm_iteration(self.h, C.byref(loss)))
+        return loss.value
+
+    def predict(self, u, j, ctx, bound=False, min_rate=0.0, max_rate=0.0) -> np.ndarray:
+        u = np.ascontiguousarray(u, dtype=np.int32)
+        j = np.ascontiguousarray(j, dtype=np.int32)
+        ctx = np.ascontiguousarray(ctx, dtype=np.int32)
+        out = np.empty(u.shape[0], dtype=np.float64)
+        self._check(self.lib.cars_fm_predict(self.h, u.shape[0], _ptr_i32(u), _ptr_i32(j), _ptr_i32(ctx),
+                                             1 if bound else 0, min_rate, max_rate, _ptr_f64(out)))
+        return out
+
+    def stats(self) -> CarsFmStats:
+        s = CarsFmStats()
+        self._check(self.lib.cars_fm_get_stats(self.h, C.byref(s)))
+        return s
+
+    def close(self):
+        if self.h:
+            self.lib.cars_fm_destroy(self.h)
             self.h = C.c_void_p()
 
     def __enter__(self):

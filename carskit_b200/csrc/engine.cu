@@ -282,7 +282,7 @@ static int validate(const cars_desc* d) {
     return fail(nullptr, CARS_E_INVALID, "abi_version %d != %d", d->abi_version, CARS_ABI_VERSION);
   if (d->model < CARS_PMF || d->model > CARS_FM) return fail(nullptr, CARS_E_INVALID, "unknown model %d", d->model);
   if (d->model == CARS_FM)
-    return fail(nullptr, CARS_E_UNSUPPORTED, "FM (ALS, FM.java:115-220) is not built yet");
+    return fail(nullptr, CARS_E_INVALID, "FM is an ALS model with its own entry points: use cars_fm_create");
   if (d->mode != CARS_EXACT && d->mode != CARS_FAST) return fail(nullptr, CARS_E_INVALID, "unknown mode %d", d->mode);
   if (d->mode == CARS_FAST)
     return fail(nullptr, CARS_E_UNSUPPORTED, "FAST (non serial-equivalent) mode is not built; use CARS_EXACT");

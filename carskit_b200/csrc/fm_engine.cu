@@ -1,0 +1,361 @@
+// fm_engine.cu -- C ABI of the FM recommender (cars_fm_* in include/carskit_b200.h) on the K4 kernels.
+// No CPU implementation exists here: without a CUDA sm_100 device cars_fm_create() fails.
+#include "../../include/carskit_b200.h"
+#include "fm_kernels.cuh"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace carsfm;
+
+static thread_local std::string g_fm_create_error = "";
+
+struct FieldStore {
+  int32_t *d_coord_of_row = nullptr, *d_perm = nullptr, *d_piece_coord = nullptr;
+  int64_t *d_piece_beg = nullptr, *d_coord_piece = nullptr, *d_coord_rows = nullptr;
+  double* d_delta = nullptr;
+  FmField f{};
+};
+
+struct cars_fm_handle {
+  std::string err;
+  int device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int32_t U = 0, I = 0, C = 0, p = 0, k = 0, D = 1;
+  int64_t N = 0;
+  double reg_lw = 0, reg_lf = 0, w0_denom = 1, xc = 1;
+  int32_t *d_u = nullptr, *d_j = nullptr, *d_c = nullptr;
+  double *d_r = nullptr, *d_e = nullptr, *d_Qc = nullptr;
+  double *d_w0 = nullptr, *d_w = nullptr, *d_V = nullptr;
+  double *d_part = nullptr, *d_scal = nullptr;
+  double* h_scal = nullptr;
+  int64_t max_pieces = 0;
+  int red_blocks = 0;
+  FieldStore fld[3];
+  bool uploaded = false, prepared = false;
+  int64_t launches = 0, h2d = 0, d2h = 0;
+  cudaEvent_t ev_beg = nullptr, ev_end = nullptr;
+  double last_iter_ms = 0;
+};
+
+static int fm_fail(cars_fm_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_fm_create_error = buf;
+  return code;
+}
+
+#define FM_TRY(h, expr)                                                                             \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fm_fail(h, _e == cudaErrorMemoryAllocation ? CARS_E_OOM : CARS_E_CUDA, "%s failed: %s", \
+                     #expr, cudaGetErrorString(_e));                                                \
+  } while (0)
+
+template <typename T>
+static cudaError_t fm_alloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), (n ? n : 1) * sizeof(T)); }
+
+template <typename T>
+static cudaError_t fm_put(cars_fm_handle* h, T** dst, const std::vector<T>& v) {
+  cudaError_t e = fm_alloc(dst, v.size());
+  if (e != cudaSuccess) return e;
+  if (!v.empty()) e = cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+  h->h2d += (int64_t)(v.size() * sizeof(T));
+  return e;
+}
+
+// rows sorted by coordinate (stable counting sort), cut into pieces of <= kPiece rows
+static const int64_t kPiece = 1024;
+static int build_field(cars_fm_handle* h, int which, const std::vector<int32_t>& coord_of_row, int32_t ncoord,
+                       int32_t offset, double x) {
+  FieldStore& fs = h->fld[which];
+  const int64_t N = h->N;
+  std::vector<int64_t> start((size_t)ncoord + 1, 0);
+  for (int64_t n = 0; n < N; n++)
+    if (coord_of_row[n] >= 0) start[(size_t)coord_of_row[n] + 1]++;
+  std::vector<int64_t> rows((size_t)ncoord);
+  for (int32_t l = 0; l < ncoord; l++) { rows[l] = start[(size_t)l + 1]; start[(size_t)l + 1] += start[l]; }
+  const int64_t total = start[ncoord];
+  std::vector<int32_t> perm((size_t)total);
+  {
+    std::vector<int64_t> cur(start.begin(), start.end() - 1);
+    for (int64_t n = 0; n < N; n++)
+      if (coord_of_row[n] >= 0) perm[(size_t)cur[coord_of_row[n]]++] = (int32_t)n;
+  }
+  std::vector<int64_t> piece_beg, coord_piece((size_t)ncoord + 1);
+  std::vector<int32_t> piece_coord;
+  for (int32_t l = 0; l < ncoord; l++) {
+    coord_piece[l] = (int64_t)piece_coord.size();
+    for (int64_t b = start[l]; b < start[(size_t)l + 1]; b += kPiece) {
+      piece_beg.push_back(b);
+      piece_coord.push_back(l);
+    }
+  }
+  coord_piece[ncoord] = (int64_t)piece_coord.size();
+  piece_beg.push_back(total);
+  // a piece must end where its coordinate ends: piece_beg[q + 1] of the last piece of l is start[l + 1]
+  // (pieces are contiguous within a coordinate and coordinates are contiguous in perm, so it is).
+  FM_TRY(h, fm_put(h, &fs.d_coord_of_row, coord_of_row));
+  FM_TRY(h, fm_put(h, &fs.d_perm, perm));
+  FM_TRY(h, fm_put(h, &fs.d_piece_beg, piece_beg));
+  FM_TRY(h, fm_put(h, &fs.d_piece_coord, piece_coord));
+  FM_TRY(h, fm_put(h, &fs.d_coord_piece, coord_piece));
+  FM_TRY(h, fm_put(h, &fs.d_coord_rows, rows));
+  FM_TRY(h, fm_alloc(&fs.d_delta, (size_t)ncoord));
+  FM_TRY(h, cudaStreamSynchronize(h->stream));
+  fs.f.coord_of_row = fs.d_coord_of_row; fs.f.perm = fs.d_perm; fs.f.piece_beg = fs.d_piece_beg;
+  fs.f.piece_coord = fs.d_piece_coord; fs.f.coord_piece = fs.d_coord_piece; fs.f.coord_rows = fs.d_coord_rows;
+  fs.f.num_pieces = (int64_t)piece_coord.size(); fs.f.ncoord = ncoord; fs.f.offset = offset; fs.f.x = x;
+  if (fs.f.num_pieces > h->max_pieces) h->max_pieces = fs.f.num_pieces;
+  return CARS_OK;
+}
+
+extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
+  if (!out) return fm_fail(nullptr, CARS_E_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!d) return fm_fail(nullptr, CARS_E_INVALID, "desc is NULL");
+  if (d->abi_version != CARS_ABI_VERSION) return fm_fail(nullptr, CARS_E_INVALID, "abi_version mismatch");
+  if (d->model != CARS_FM) return fm_fail(nullptr, CARS_E_INVALID, "cars_fm_create needs model = CARS_FM");
+  if (d->num_users <= 0 || d->num_items <= 0 || d->num_conditions < 0 || d->num_factors <= 0 || d->nnz < 0)
+    return fm_fail(nullptr, CARS_E_INVALID, "bad sizes");
+  if (d->num_context_dims <= 0) return fm_fail(nullptr, CARS_E_INVALID, "num_context_dims must be > 0 (rateDao.numContextDims())");
+  if (d->nnz > 0 && (!d->u || !d->j || !d->ctx || !d->r)) return fm_fail(nullptr, CARS_E_INVALID, "u/j/ctx/r must not be NULL");
+  if (d->nnz >= (1ll << 31)) return fm_fail(nullptr, CARS_E_UNSUPPORTED, "nnz >= 2^31 rows per handle");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) return fm_fail(nullptr, CARS_E_NO_DEVICE, "no CUDA device; this engine has no CPU path");
+  if (d->device < 0 || d->device >= ndev) return fm_fail(nullptr, CARS_E_INVALID, "device %d out of range", d->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess || prop.major != 10)
+    return fm_fail(nullptr, CARS_E_NO_DEVICE, "device %d is not sm_100", d->device);
+  for (int64_t n = 0; n < d->nnz; n++)
+    if ((uint32_t)d->u[n] >= (uint32_t)d->num_users || (uint32_t)d->j[n] >= (uint32_t)d->num_items || d->ctx[n] < 0)
+      return fm_fail(nullptr, CARS_E_INVALID, "rating %lld has an id out of range", (long long)n);
+
+  cars_fm_handle* h = new (std::nothrow) cars_fm_handle();
+  if (!h) return fm_fail(nullptr, CARS_E_OOM, "host allocation failed");
+  auto bail = [&](int code) { g_fm_create_error = h->err; cars_fm_destroy(h); return code; };
+  h->device = d->device; h->sm_count = prop.multiProcessorCount;
+  h->U = d->num_users; h->I = d->num_items; h->C = d->num_conditions; h->p = h->U + h->I + h->C;
+  h->k = d->num_factors; h->D = d->num_context_dims; h->N = d->nnz;
+  h->reg_lw = d->reg_lw; h->reg_lf = d->reg_lf;
+  h->xc = 1.0 / (double)h->D;                                   // FM.java:86
+  h->w0_denom = (double)((float)h->N + (float)d->reg_lw);      // FM.java:159: int + float is a FLOAT addition
+  int rc = CARS_OK;
+#define FM_TRY_H(expr)                                      \
+  do {                                                      \
+    cudaError_t _e = (expr);                                \
+    if (_e != cudaSuccess) {                                \
+      fm_fail(h, CARS_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+      return bail(_e == cudaErrorMemoryAllocation ? CARS_E_OOM : CARS_E_CUDA);  \
+    }                                                       \
+  } while (0)
+  FM_TRY_H(cudaSetDevice(h->device));
+  if (d->stream) h->stream = (cudaStream_t)d->stream;
+  else { FM_TRY_H(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  FM_TRY_H(cudaEventCreate(&h->ev_beg));
+  FM_TRY_H(cudaEventCreate(&h->ev_end));
+  const int64_t N = h->N;
+  FM_TRY_H(fm_alloc(&h->d_u, (size_t)N)); FM_TRY_H(fm_alloc(&h->d_j, (size_t)N)); FM_TRY_H(fm_alloc(&h->d_c, (size_t)N));
+  FM_TRY_H(fm_alloc(&h->d_r, (size_t)N)); FM_TRY_H(fm_alloc(&h->d_e, (size_t)N));
+  FM_TRY_H(fm_alloc(&h->d_Qc, (size_t)N * h->k));
+  FM_TRY_H(fm_alloc(&h->d_w0, 1)); FM_TRY_H(fm_alloc(&h->d_w, (size_t)h->p)); FM_TRY_H(fm_alloc(&h->d_V, (size_t)h->p * h->k));
+  if (N) {
+    FM_TRY_H(cudaMemcpyAsync(h->d_u, d->u, N * 4, cudaMemcpyHostToDevice, h->stream));
+    FM_TRY_H(cudaMemcpyAsync(h->d_j, d->j, N * 4, cudaMemcpyHostToDevice, h->stream));
+    FM_TRY_H(cudaMemcpyAsync(h->d_c, d->ctx, N * 4, cudaMemcpyHostToDevice, h->stream));
+    FM_TRY_H(cudaMemcpyAsync(h->d_r, d->r, N * 8, cudaMemcpyHostToDevice, h->stream));
+    h->h2d += N * 20;
+  }
+  try {
+    std::vector<int32_t> cu((size_t)N), cj((size_t)N), cc((size_t)N);
+    for (int64_t n = 0; n < N; n++) {
+      cu[n] = d->u[n];
+      cj[n] = d->j[n];
+      cc[n] = d->ctx[n] < h->C ? d->ctx[n] : -1;  // FM.java:81: the context feature exists only if its index is < p
+    }
+    if ((rc = build_field(h, 0, cu, h->U, 0, 1.0))) return bail(rc);
+    if ((rc = build_field(h, 1, cj, h->I, h->U, 1.0))) return bail(rc);
+    if ((rc = build_field(h, 2, cc, h->C, h->U + h->I, h->xc))) return bail(rc);
+  } catch (...) {
+    fm_fail(h, CARS_E_OOM, "host allocation failed");
+    return bail(CARS_E_OOM);
+  }
+  h->red_blocks = h->sm_count * 4;
+  const size_t part = (size_t)(2 * (h->max_pieces > h->red_blocks ? h->max_pieces : h->red_blocks));
+  FM_TRY_H(fm_alloc(&h->d_part, part));
+  FM_TRY_H(fm_alloc(&h->d_scal, 8));
+  FM_TRY_H(cudaMallocHost((void**)&h->h_scal, 8 * sizeof(double)));
+  FM_TRY_H(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return CARS_OK;
+#undef FM_TRY_H
+}
+
+static int fm_transfer(cars_fm_handle* h, const cars_fm_arrays* a, bool up) {
+  if (!h) return CARS_E_INVALID;
+  if (!a || !a->w0 || !a->w || !a->V) return fm_fail(h, CARS_E_INVALID, "w0, w and V are required");
+  FM_TRY(h, cudaSetDevice(h->device));
+  const cudaMemcpyKind kd = up ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  auto cp = [&](double* dev, double* host, size_t n) {
+    return up ? cudaMemcpyAsync(dev, host, n * 8, kd, h->stream) : cudaMemcpyAsync(host, dev, n * 8, kd, h->stream);
+  };
+  FM_TRY(h, cp(h->d_w0, a->w0, 1));
+  FM_TRY(h, cp(h->d_w, a->w, (size_t)h->p));
+  FM_TRY(h, cp(h->d_V, a->V, (size_t)h->p * h->k));
+  FM_TRY(h, cudaStreamSynchronize(h->stream));
+  (up ? h->h2d : h->d2h) += (int64_t)(1 + h->p + (int64_t)h->p * h->k) * 8;
+  return CARS_OK;
+}
+
+extern "C" int cars_fm_upload(cars_fm_handle* h, const cars_fm_arrays* a) {
+  int rc = fm_transfer(h, a, true);
+  if (rc == CARS_OK) { h->uploaded = true; h->prepared = false; }
+  return rc;
+}
+extern "C" int cars_fm_download(cars_fm_handle* h, const cars_fm_arrays* a) {
+  if (h && !h->uploaded) return fm_fail(h, CARS_E_STATE, "cars_fm_download before cars_fm_upload");
+  return fm_transfer(h, a, false);
+}
+
+extern "C" int cars_fm_prepare(cars_fm_handle* h) {
+  if (!h) return CARS_E_INVALID;
+  if (!h->uploaded) return fm_fail(h, CARS_E_STATE, "cars_fm_prepare before cars_fm_upload");
+  FM_TRY(h, cudaSetDevice(h->device));
+  if (h->N) {
+    const unsigned blocks = (unsigned)((h->N + 255) / 256);
+    fm_prepare_kernel<<<blocks, 256, 0, h->stream>>>(h->d_u, h->d_j, h->d_c, h->d_r, h->d_w, h->d_V, h->d_w0, h->U, h->I,
+                                                    h->p, h->k, h->xc, h->N, h->d_e, h->d_Qc);
+    FM_TRY(h, cudaGetLastError());
+    h->launches++;
+  }
+  FM_TRY(h, cudaStreamSynchronize(h->stream));
+  h->prepared = true;
+  return CARS_OK;
+}
+
+template <int MODE>
+static int field_step(cars_fm_handle* h, int which, double* coef, int stride, int col, double* Qf, double size_reg) {
+  FieldStore& fs = h->fld[which];
+  const FmField& f = fs.f;
+  if (f.ncoord == 0) return CARS_OK;
+  if (f.num_pieces > 0) {
+    const unsigned blocks = (unsigned)((f.num_pieces * 32 + 255) / 256);
+    fm_piece_reduce_kernel<MODE><<<blocks, 256, 0, h->stream>>>(f, h->d_e, Qf, coef, stride, col, h->d_part);
+    FM_TRY(h, cudaGetLastError());
+    h->launches++;
+  }
+  fm_coord_kernel<MODE><<<(unsigned)((f.ncoord + 255) / 256), 256, 0, h->stream>>>(f, h->d_part, size_reg, coef, stride, col,
+                                                                                  fs.d_delta);
+  FM_TRY(h, cudaGetLastError());
+  h->launches++;
+  if (h->N) {
+    fm_row_update_kernel<MODE><<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(f, fs.d_delta, h->N, h->d_e, Qf);
+    FM_TRY(h, cudaGetLastError());
+    h->launches++;
+  }
+  return CARS_OK;
+}
+
+extern "C" int cars_fm_iteration(cars_fm_handle* h, double* loss_out) {
+  if (!h) return CARS_E_INVALID;
+  if (!h->prepared) return fm_fail(h, CARS_E_STATE, "cars_fm_iteration before cars_fm_prepare");
+  FM_TRY(h, cudaSetDevice(h->device));
+  FM_TRY(h, cudaEventRecord(h->ev_beg, h->stream));
+  int rc;
+  // w0 (FM.java:152-169)
+  fm_w0_reduce_kernel<<<h->red_blocks, 256, 0, h->stream>>>(h->d_e, h->d_w0, h->N, h->d_part);
+  fm_w0_finish_kernel<<<1, 32, 0, h->stream>>>(h->d_part, h->red_blocks, h->w0_denom, h->reg_lw, h->d_w0, h->d_scal);
+  if (h->N) fm_w0_apply_kernel<<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(h->d_e, h->d_scal, h->N);
+  fm_wreg_kernel<<<1, 256, 0, h->stream>>>(h->d_w, h->p, h->reg_lw, h->d_scal + 3);  // uses the OLD w (:187)
+  FM_TRY(h, cudaGetLastError());
+  h->launches += 4;
+  // w_l, l = 0..p-1 (:172-191): users, items, contexts
+  const double w_reg = (double)h->N * h->reg_lw;
+  for (int fld = 0; fld < 3; fld++)
+    if ((rc = field_step<0>(h, fld, h->d_w, 1, 0, nullptr, w_reg))) return rc;
+  // V_lf, f = 0..k-1 { l = 0..p-1 } (:194-217)
+  const double v_reg = (double)h->N * h->reg_lf;
+  for (int f = 0; f < h->k; f++)
+    for (int fld = 0; fld < 3; fld++)
+      if ((rc = field_step<1>(h, fld, h->d_V, h->k, f, h->d_Qc + (int64_t)f * h->N, v_reg))) return rc;
+  FM_TRY(h, cudaEventRecord(h->ev_end, h->stream));
+  FM_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  FM_TRY(h, cudaStreamSynchronize(h->stream));
+  h->d2h += 32;
+  float ms = 0.f;
+  FM_TRY(h, cudaEventElapsedTime(&ms, h->ev_beg, h->ev_end));
+  h->last_iter_ms = ms;
+  if (loss_out) *loss_out = (h->h_scal[2] + h->h_scal[3]) * 0.05;  // loss *= 0.05 (:218)
+  return CARS_OK;
+}
+
+extern "C" int cars_fm_predict(cars_fm_handle* h, int64_t n, const int32_t* u, const int32_t* j, const int32_t* ctx,
+                               int32_t bound, double min_rate, double max_rate, double* out) {
+  if (!h) return CARS_E_INVALID;
+  if (!h->uploaded) return fm_fail(h, CARS_E_STATE, "cars_fm_predict before cars_fm_upload");
+  if (n < 0 || (n > 0 && (!u || !j || !ctx || !out))) return fm_fail(h, CARS_E_INVALID, "bad predict arguments");
+  if (n == 0) return CARS_OK;
+  for (int64_t i = 0; i < n; i++)
+    if ((uint32_t)u[i] >= (uint32_t)h->U || (uint32_t)j[i] >= (uint32_t)h->I || ctx[i] < 0)
+      return fm_fail(h, CARS_E_INVALID, "query %lld has an id out of range", (long long)i);
+  FM_TRY(h, cudaSetDevice(h->device));
+  int32_t *du = nullptr, *dj = nullptr, *dc = nullptr;
+  double* dout = nullptr;
+  cudaError_t e = fm_alloc(&du, (size_t)n);
+  if (e == cudaSuccess) e = fm_alloc(&dj, (size_t)n);
+  if (e == cudaSuccess) e = fm_alloc(&dc, (size_t)n);
+  if (e == cudaSuccess) e = fm_alloc(&dout, (size_t)n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(du, u, n * 4, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dj, j, n * 4, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dc, ctx, n * 4, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    fm_predict_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(du, dj, dc, h->d_w, h->d_V, h->d_w0, h->U, h->I, h->p,
+                                                                         h->k, h->xc, n, bound, min_rate, max_rate, dout);
+    e = cudaGetLastError();
+    h->launches++;
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(du); cudaFree(dj); cudaFree(dc); cudaFree(dout);
+  h->h2d += n * 12; h->d2h += n * 8;
+  if (e != cudaSuccess) return fm_fail(h, CARS_E_CUDA, "predict failed: %s", cudaGetErrorString(e));
+  return CARS_OK;
+}
+
+extern "C" int cars_fm_get_stats(const cars_fm_handle* h, cars_fm_stats* out) {
+  if (!h || !out) return CARS_E_INVALID;
+  out->nnz = h->N; out->p = h->p; out->kernel_launches = h->launches; out->h2d_bytes = h->h2d; out->d2h_bytes = h->d2h;
+  out->last_iteration_ms = h->last_iter_ms;
+  out->pieces = h->fld[0].f.num_pieces + h->fld[1].f.num_pieces + h->fld[2].f.num_pieces;
+  return CARS_OK;
+}
+
+extern "C" const char* cars_fm_last_error(const cars_fm_handle* h) { return h ? h->err.c_str() : g_fm_create_error.c_str(); }
+
+extern "C" void cars_fm_destroy(cars_fm_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_u); cudaFree(h->d_j); cudaFree(h->d_c); cudaFree(h->d_r); cudaFree(h->d_e); cudaFree(h->d_Qc);
+  cudaFree(h->d_w0); cudaFree(h->d_w); cudaFree(h->d_V); cudaFree(h->d_part); cudaFree(h->d_scal);
+  for (auto& f : h->fld) {
+    cudaFree(f.d_coord_of_row); cudaFree(f.d_perm); cudaFree(f.d_piece_coord); cudaFree(f.d_piece_beg);
+    cudaFree(f.d_coord_piece); cudaFree(f.d_coord_rows); cudaFree(f.d_delta);
+  }
+  if (h->h_scal) cudaFreeHost(h->h_scal);
+  if (h->ev_beg) cudaEventDestroy(h->ev_beg);
+  if (h->ev_end) cudaEventDestroy(h->ev_end);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}

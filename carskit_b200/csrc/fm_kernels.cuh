@@ -1,0 +1,232 @@
+// fm_kernels.cuh -- K4: sm_100a kernels of the FM recommender's ALS sweep
+// (reference: src/carskit/alg/cars/adaptation/dependent/FM.java:93-113 predict, :115-220 buildModel).
+//
+// The reference loops `for l < p` over ALL coordinates and `for i < size` over ALL rows through a dense
+// feature table (O(k*p*size)).  Every row has exactly three non-zero features -- x_u = 1, x_{U+j} = 1 and
+// x_{U+I+ctx} = 1/numContextDims (only when that index is < p, FM.java:81) -- so the coordinates of one
+// FIELD (all users / all items / all contexts) touch disjoint rows: solving them concurrently is
+// identical to the reference's sequential order.  Fields and factors stay sequential.
+//
+// One coordinate step = (a) reduce numerator/denominator over rows(l), (b) new value + delta per
+// coordinate, (c) e_n += delta*x (and Qc[n][f] += delta*x) for the rows of that coordinate.
+// (a) is a deterministic two-level reduction: rows sorted by coordinate are cut into pieces of <= 1024
+// rows, one warp sums a piece in a fixed order, one thread sums a coordinate's pieces in order.
+// Arithmetic: fp64, no FMA contraction in the update formulas (Java semantics); sums are tree-ordered, so
+// results equal the sparse oracle's up to summation order (tolerance stated in tests/test_fm_gpu.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace carsfm {
+
+struct FmField {
+  const int32_t* coord_of_row;  // [N] coordinate (within the field) of every row, -1 = feature absent
+  const int32_t* perm;          // [rows_in_field] row ids sorted by coordinate (stable)
+  const int64_t* piece_beg;     // [num_pieces + 1] offsets into perm
+  const int32_t* piece_coord;   // [num_pieces]
+  const int64_t* coord_piece;   // [ncoord + 1] first piece of every coordinate
+  const int64_t* coord_rows;    // [ncoord] number of rows
+  int64_t num_pieces;
+  int32_t ncoord;
+  int32_t offset;  // index of the field's first coordinate in w / V
+  double x;        // feature value of the field
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    int lo = __shfl_down_sync(0xffffffffu, __double2loint(v), o);
+    int hi = __shfl_down_sync(0xffffffffu, __double2hiint(v), o);
+    v = __dadd_rn(v, __hiloint2double(hi, lo));
+  }
+  return v;
+}
+
+// FM.predict in sparse form, ascending feature index (FM.java:93-113)
+__device__ __forceinline__ double fm_predict_one(const double* __restrict__ w, const double* __restrict__ V, double w0,
+                                                 int U, int I, int p, int k, double xc, int u, int j, int c) {
+  const int iu = u, ij = U + j, ic = U + I + c;
+  const bool has_c = ic < p;
+  double pred = w0;
+  pred = __dadd_rn(pred, __dmul_rn(w[iu], 1.0));
+  pred = __dadd_rn(pred, __dmul_rn(w[ij], 1.0));
+  if (has_c) pred = __dadd_rn(pred, __dmul_rn(w[ic], xc));
+  double sum = 0.0;
+  for (int f = 0; f < k; ++f) {
+    double sum1 = 0.0, sum2 = 0.0;
+    double d = V[(int64_t)iu * k + f];
+    sum1 = __dadd_rn(sum1, d); sum2 = __dadd_rn(sum2, __dmul_rn(d, d));
+    d = V[(int64_t)ij * k + f];
+    sum1 = __dadd_rn(sum1, d); sum2 = __dadd_rn(sum2, __dmul_rn(d, d));
+    if (has_c) {
+      d = __dmul_rn(V[(int64_t)ic * k + f], xc);
+      sum1 = __dadd_rn(sum1, d); sum2 = __dadd_rn(sum2, __dmul_rn(d, d));
+    }
+    sum = __dadd_rn(sum, __dsub_rn(__dmul_rn(sum1, sum1), sum2));
+  }
+  return __dadd_rn(pred, __dmul_rn(0.5, sum));
+}
+
+// Pre-pass (FM.java:118-146): e_n = r_n - predict, Qc[f][n] = sum_i V[i][f] x_n[i].  Qc is factor-major.
+__global__ void __launch_bounds__(256) fm_prepare_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ j,
+                                                         const int32_t* __restrict__ c, const double* __restrict__ r,
+                                                         const double* __restrict__ w, const double* __restrict__ V,
+                                                         const double* __restrict__ w0p, int U, int I, int p, int k,
+                                                         double xc, int64_t N, double* __restrict__ e,
+                                                         double* __restrict__ Qc) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int uu = u[n], jj = j[n], cc = c[n];
+  e[n] = __dsub_rn(r[n], fm_predict_one(w, V, *w0p, U, I, p, k, xc, uu, jj, cc));
+  const int ic = U + I + cc;
+  for (int f = 0; f < k; ++f) {
+    double v = 0.0;
+    v = __dadd_rn(v, V[(int64_t)uu * k + f]);
+    v = __dadd_rn(v, V[(int64_t)(U + jj) * k + f]);
+    if (ic < p) v = __dadd_rn(v, __dmul_rn(V[(int64_t)ic * k + f], xc));
+    Qc[(int64_t)f * N + n] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) fm_predict_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ j,
+                                                         const int32_t* __restrict__ c, const double* __restrict__ w,
+                                                         const double* __restrict__ V, const double* __restrict__ w0p,
+                                                         int U, int I, int p, int k, double xc, int64_t n, int bound,
+                                                         double lo, double hi, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double pr = fm_predict_one(w, V, *w0p, U, I, p, k, xc, u[i], j[i], c[i]);
+  if (bound) {
+    if (pr > hi) pr = hi;
+    if (pr < lo) pr = lo;
+  }
+  out[i] = pr;
+}
+
+// w0 step, pass 1 (FM.java:152-158): block partials of sum(e - w0) and sum(e^2), fixed slices.
+__global__ void __launch_bounds__(256) fm_w0_reduce_kernel(const double* __restrict__ e, const double* __restrict__ w0p,
+                                                           int64_t N, double* __restrict__ part /*[2 x grid]*/) {
+  __shared__ double sa[8], sb[8];
+  const double w0 = *w0p;
+  const int64_t per = (N + gridDim.x - 1) / gridDim.x;
+  const int64_t beg = (int64_t)blockIdx.x * per, end = beg + per < N ? beg + per : N;
+  double a = 0.0, b = 0.0;
+  for (int64_t i = beg + threadIdx.x; i < end; i += 256) {
+    const double x = e[i];
+    a = __dadd_rn(a, __dsub_rn(x, w0));
+    b = __dadd_rn(b, __dmul_rn(x, x));
+  }
+  a = warp_sum(a); b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int w = 0; w < 8; w++) { ta += sa[w]; tb += sb[w]; }
+    part[blockIdx.x] = ta;
+    part[gridDim.x + blockIdx.x] = tb;
+  }
+}
+
+// w0 step, pass 2 (:159-169): new w0, loss terms; scal = {w0, delta (new - old as two separate values), loss}
+__global__ void fm_w0_finish_kernel(const double* __restrict__ part, int nblocks, double denom, double reg_lw,
+                                    double* __restrict__ w0p, double* __restrict__ scal /*[0]=new [1]=old [2]=loss*/) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double ta = 0.0, tb = 0.0;
+  for (int i = 0; i < nblocks; i++) { ta += part[i]; tb += part[nblocks + i]; }
+  const double w0 = *w0p;
+  double up = ta / denom;
+  up = 0.0 - up;
+  scal[0] = up;
+  scal[1] = w0;
+  scal[2] = tb + (reg_lw * w0) * w0;
+  *w0p = up;
+}
+__global__ void __launch_bounds__(256) fm_w0_apply_kernel(double* __restrict__ e, const double* __restrict__ scal, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) e[i] = __dsub_rn(__dadd_rn(e[i], scal[0]), scal[1]);  // errors + update_w0 - w0 (:165)
+}
+
+// (a) one warp per piece.  MODE 0: w step (:175-179)  num += (e - w_l x) x.
+//                         MODE 1: V step (:199-204)  h = x Qc - x^2 V_lf; num += (e - V_lf h) h; den += h^2.
+template <int MODE>
+__global__ void __launch_bounds__(256) fm_piece_reduce_kernel(FmField fld, const double* __restrict__ e,
+                                                              const double* __restrict__ Qf /*Qc[f]*/,
+                                                              const double* __restrict__ coef /*w or V*/, int coef_stride,
+                                                              int coef_col, double* __restrict__ part /*[2 x pieces]*/) {
+  const int64_t piece = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (piece >= fld.num_pieces) return;
+  const int lane = threadIdx.x & 31;
+  const int l = fld.piece_coord[piece];
+  const double x = fld.x;
+  const double cl = coef[(int64_t)(fld.offset + l) * coef_stride + coef_col];
+  const int64_t beg = fld.piece_beg[piece], end = fld.piece_beg[piece + 1];
+  double num = 0.0, den = 0.0;
+  for (int64_t i = beg + lane; i < end; i += 32) {
+    const int64_t n = fld.perm[i];
+    const double en = e[n];
+    if (MODE == 0) {
+      num = __dadd_rn(num, __dmul_rn(__dsub_rn(en, __dmul_rn(cl, x)), x));
+    } else {
+      const double h = __dsub_rn(__dmul_rn(x, Qf[n]), __dmul_rn(__dmul_rn(x, x), cl));
+      num = __dadd_rn(num, __dmul_rn(__dsub_rn(en, __dmul_rn(cl, h)), h));
+      den = __dadd_rn(den, __dmul_rn(h, h));
+    }
+  }
+  num = warp_sum(num);
+  if (MODE == 1) den = warp_sum(den);
+  if (lane == 0) {
+    part[piece] = num;
+    part[fld.num_pieces + piece] = den;
+  }
+}
+
+// (b) one thread per coordinate: sum its pieces in order, new = 0 - num/den, delta = new - old.
+template <int MODE>
+__global__ void __launch_bounds__(256) fm_coord_kernel(FmField fld, const double* __restrict__ part, double size_reg,
+                                                       double* __restrict__ coef, int coef_stride, int coef_col,
+                                                       double* __restrict__ delta /*[ncoord]*/) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= fld.ncoord) return;
+  double num = 0.0, den = 0.0;
+  for (int64_t q = fld.coord_piece[l]; q < fld.coord_piece[l + 1]; q++) {
+    num = __dadd_rn(num, part[q]);
+    if (MODE == 1) den = __dadd_rn(den, part[fld.num_pieces + q]);
+  }
+  if (MODE == 0) den = __dmul_rn((double)fld.coord_rows[l], __dmul_rn(fld.x, fld.x));
+  den = __dadd_rn(den, size_reg);
+  double* cp = coef + (int64_t)(fld.offset + l) * coef_stride + coef_col;
+  const double old = *cp;
+  const double nv = __dsub_rn(0.0, num / den);
+  *cp = nv;
+  delta[l] = __dsub_rn(nv, old);
+}
+
+// (c) row-parallel: e_n += (new - old) x ; V step also Qc[n][f] += (new - old) x  (:184-185, :208-211)
+template <int MODE>
+__global__ void __launch_bounds__(256) fm_row_update_kernel(FmField fld, const double* __restrict__ delta, int64_t N,
+                                                            double* __restrict__ e, double* __restrict__ Qf) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int l = fld.coord_of_row[n];
+  if (l < 0) return;
+  const double d = __dmul_rn(delta[l], fld.x);
+  e[n] = __dadd_rn(e[n], d);
+  if (MODE == 1) Qf[n] = __dadd_rn(Qf[n], d);
+}
+
+// sum_l (regLw * w_l) * w_l over all p coordinates, deterministic (one block)
+__global__ void __launch_bounds__(256) fm_wreg_kernel(const double* __restrict__ w, int p, double reg_lw,
+                                                      double* __restrict__ out) {
+  __shared__ double sh[256];
+  double t = 0.0;
+  for (int i = threadIdx.x; i < p; i += 256) t = __dadd_rn(t, __dmul_rn(__dmul_rn(reg_lw, w[i]), w[i]));
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+}  // namespace carsfm

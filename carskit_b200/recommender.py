@@ -357,9 +357,94 @@ class CAMF_CU(IterativeRecommender):
     MODEL, algoName = capi.CAMF_CU, "CAMF_CU"
 
 
+class FM(IterativeRecommender):
+    """carskit.alg.cars.adaptation.dependent.FM (FM.java): ALS factorization machine over the one-hot features
+    (user, item, context).  `FM=-lw <f> -lf <f>` in the configuration (FM.java:53-54); learn.rate and
+    isConverged() are not used by the reference's buildModel() (:148-219 runs exactly numIters iterations)."""
+    MODEL, algoName = capi.FM, "FM"
+
+    def __init__(self, trainMatrix, testMatrix=None, fold=-1, conf=None, device=0, stream=0, **kw):
+        super().__init__(trainMatrix, testMatrix, fold, conf, device, stream, **kw)
+        opts = LineConfiger(self.cf.get("FM", "-lw 0.01 -lf 0.02"))
+        self.regLw, self.regLf = opts.getFloat("-lw", 0.0), opts.getFloat("-lf", 0.0)
+        # rateDao.numContextDims(): one condition per dimension in every context (DataDAO.java:281-290)
+        ts = trainMatrix
+        self.numContextDims = int(self.cf.get("num.context.dims", 0)) or (
+            int(ts.ctx_ptr[1] - ts.ctx_ptr[0]) if ts.ctx_ptr is not None and len(ts.ctx_ptr) > 1 else 1)
+        self.p = self.numUsers + self.numItems + self.numConditions
+        self.k = self.numFactors
+
+    def initModel(self, init=None, seed: int = 0):
+        """FM.initModel (FM.java:57-74): w0 = 0, w ~ U(0,1) (DenseVector.init()), V ~ N(0, 0.1)."""
+        if init is not None:
+            self.model = {"w0": np.ascontiguousarray(init["w0"], dtype=np.float64).reshape(1),
+                          "w": np.ascontiguousarray(init["w"], dtype=np.float64),
+                          "V": np.ascontiguousarray(init["V"], dtype=np.float64)}
+            if self.model["w"].shape != (self.p,) or self.model["V"].shape != (self.p, self.k):
+                raise ValueError("FM arrays: w must be [p], V [p x k]")
+            return
+        rng = np.random.default_rng(seed)
+        self.model = {"w0": np.zeros(1), "w": rng.random(self.p),
+                      "V": self.initMean + self.initStd * rng.standard_normal((self.p, self.k))}
+
+    def _desc(self):
+        return capi.make_desc(self.trainMatrix, capi.FM, self.k, device=self.device, reg_lw=self.regLw,
+                              reg_lf=self.regLf, num_context_dims=self.numContextDims, stream=self.stream)
+
+    def _new_engine(self):
+        return capi.FmEngine(self._desc(), keepalive=self.trainMatrix)
+
+    def open_engine(self):
+        if not self.model:
+            raise RuntimeError("buildModel before initModel")
+        eng = self._new_engine()
+        try:
+            eng.upload(self.model)
+            eng.prepare()  # FM.java:118-146
+        except Exception:
+            eng.close()
+            raise
+        self.engine = eng
+        return eng
+
+    def train_epoch(self, iter: int) -> bool:
+        self.loss = self.engine.iteration()
+        self.iter_losses.append(self.loss)
+        return False  # FM.java never calls isConverged()
+
+    def _eval_engine(self):
+        if self.engine is not None:
+            return self.engine
+        eng = capi.FmEngine(self._desc_for_predict(), keepalive=self.trainMatrix)
+        eng.upload(self.model)
+        return eng
+
+    def _desc_for_predict(self):
+        d = super()._desc_for_predict()
+        return capi.make_desc(self._empty_keep, capi.FM, self.k, device=self.device, reg_lw=self.regLw,
+                              reg_lf=self.regLf, num_context_dims=self.numContextDims)
+
+    def evalRatings(self):
+        t = self.testMatrix
+        if t is None or len(t["u"]) == 0:
+            return {"MAE": float("nan"), "RMSE": float("nan")}
+        eng = self._eval_engine()
+        try:
+            pred = eng.predict(t["u"], t["j"], t["ctx"], bound=True, min_rate=self.minRate, max_rate=self.maxRate)
+        finally:
+            if eng is not self.engine:
+                eng.close()
+        err = np.abs(np.asarray(t["r"], dtype=np.float64) - pred)  # Recommender.java:518-545
+        sa, ss = 0.0, 0.0
+        for e in err.tolist():
+            sa += e
+            ss += e * e
+        return {"MAE": sa / len(err), "RMSE": math.sqrt(ss / len(err))}
+
+
 def getRecommender(name: str):
     """The `switch` of CARSKit.getRecommender (src/carskit/main/CARSKit.java:429-705) for this path."""
-    table = {"pmf": PMF, "biasedmf": BiasedMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU}
+    table = {"pmf": PMF, "biasedmf": BiasedMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM}
     try:
         return table[name.lower()]
     except KeyError:

@@ -37,7 +37,7 @@ enum cars_model {
   CARS_CAMF_C   = 2, /* .../cars/adaptation/dependent/dev/CAMF_C.java:74-138  */
   CARS_CAMF_CI  = 3, /* .../cars/adaptation/dependent/dev/CAMF_CI.java:74-131 */
   CARS_CAMF_CU  = 4, /* .../cars/adaptation/dependent/dev/CAMF_CU.java:71-128 */
-  CARS_FM       = 5  /* .../cars/adaptation/dependent/FM.java:115-220 (ALS; not built in round 1) */
+  CARS_FM       = 5  /* .../cars/adaptation/dependent/FM.java:115-220 (ALS; cars_fm_* entry points below) */
 };
 
 /* Update mode.
@@ -104,10 +104,8 @@ typedef struct cars_desc {
   const int32_t* ctx_cond; /* [ctx_ptr[num_contexts]] */
   double global_mean;      /* Recommender.globalMean (Recommender.java:265) */
   double reg_u, reg_i, reg_b, reg_c, reg_lw, reg_lf;
-  /* Multi-GPU (one process per GPU).  Rank g of world_size trains the ratings whose user lies in
-   * its contiguous user range; see cars_shard_* below.  world_size <= 1 means a single GPU. */
-  int32_t rank;
-  int32_t world_size;
+  int32_t num_context_dims; /* rateDao.numContextDims() (FM.java:86); FM only */
+  int32_t reserved1;
   void*   stream;          /* cudaStream_t to launch on; NULL = the handle creates its own */
 } cars_desc;
 
@@ -206,6 +204,42 @@ typedef struct cars_stats {
 } cars_stats;
 int cars_get_stats(const cars_handle* h, cars_stats* out);
 void* cars_get_stream(const cars_handle* h); /* cudaStream_t the kernels are launched on */
+
+/* ---- FM (src/carskit/alg/cars/adaptation/dependent/FM.java): ALS factorization machine ------------------
+ * Not SGD: coordinate descent with cached residuals over the one-hot features x_u = 1, x_{U+j} = 1,
+ * x_{U+I+ctx} = 1/numContextDims (FM.java:76-91; the context feature only exists while its index is < p =
+ * numUsers + numItems + numConditions).  Uses cars_desc with model = CARS_FM, u/j/ctx/r in trainMatrix
+ * iteration order, num_factors = k, reg_lw / reg_lf = the floats of `FM=-lw .. -lf ..` (FM.java:53-54)
+ * widened to double, num_context_dims.  learn.rate and isConverged() are not used by FM.java.
+ *   cars_fm_upload     w0, w [p], V [p x k] as FM.initModel() made them (FM.java:57-74)
+ *   cars_fm_prepare    the pre-pass of buildModel(): errors[n] = r - predict, Q[n][f] = sum_i V[i][f] x_n[i] (:118-146)
+ *   cars_fm_iteration  one iteration of `for (iter ...)`: w0 step, w_l steps, V_lf steps (:148-219).  The
+ *                      coordinates of one field touch disjoint rows and are solved concurrently (identical
+ *                      to the sequential order); sums are tree-ordered, so results match the reference up to
+ *                      summation order.  loss_out = 0.05 * (sum e^2 + regLw w0^2 + sum_l regLw w_l^2): the
+ *                      O(size) part of FM.java's `loss`; its O(k p size) reporting term (:206) is never read
+ *                      by the reference and is omitted.
+ *   cars_fm_predict    FM.predict(u, j, c) (:93-113) + Recommender.predict(.., bound) (Recommender.java:306-317) */
+typedef struct cars_fm_handle cars_fm_handle;
+typedef struct cars_fm_arrays {
+  double* w0; /* [1] */
+  double* w;  /* [p] */
+  double* V;  /* [p x k] row-major */
+} cars_fm_arrays;
+typedef struct cars_fm_stats {
+  int64_t nnz, p, pieces, kernel_launches, h2d_bytes, d2h_bytes;
+  double last_iteration_ms; /* device time of the last cars_fm_iteration (CUDA events) */
+} cars_fm_stats;
+int cars_fm_create(const cars_desc* desc, cars_fm_handle** out);
+int cars_fm_upload(cars_fm_handle* h, const cars_fm_arrays* host);
+int cars_fm_prepare(cars_fm_handle* h);
+int cars_fm_iteration(cars_fm_handle* h, double* loss_out);
+int cars_fm_download(cars_fm_handle* h, const cars_fm_arrays* host);
+int cars_fm_predict(cars_fm_handle* h, int64_t n, const int32_t* u, const int32_t* j, const int32_t* ctx,
+                    int32_t bound, double min_rate, double max_rate, double* out);
+int cars_fm_get_stats(const cars_fm_handle* h, cars_fm_stats* out);
+const char* cars_fm_last_error(const cars_fm_handle* h);
+void cars_fm_destroy(cars_fm_handle* h);
 
 /* Library self-description: "carskit_b200 <abi> sm_100a ..." */
 const char* cars_version(void);

@@ -164,3 +164,98 @@ def build_model(desc: CarsDesc, arrs: dict, state: EpochState, num_iters: int):
 def global_mean(r: np.ndarray) -> float:
     r = np.ascontiguousarray(r, dtype=np.float64)
     return lib().oracle_global_mean(_ptr_f64(r), r.shape[0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# FM (fm_oracle.cpp)
+# ---------------------------------------------------------------------------------------------------
+class FmProblem(C.Structure):
+    _fields_ = [("num_users", C.c_int32), ("num_items", C.c_int32), ("num_conditions", C.c_int32),
+                ("num_context_dims", C.c_int32), ("k", C.c_int32), ("pad", C.c_int32), ("size", C.c_int64),
+                ("u", C.POINTER(C.c_int32)), ("j", C.POINTER(C.c_int32)), ("ctx", C.POINTER(C.c_int32)),
+                ("r", C.POINTER(C.c_double)), ("reg_lw", C.c_float), ("reg_lf", C.c_float)]
+
+
+class FmModel(C.Structure):
+    _fields_ = [("w0", C.POINTER(C.c_double)), ("w", C.POINTER(C.c_double)), ("V", C.POINTER(C.c_double))]
+
+
+_fm_ready = False
+
+
+def _fm_lib():
+    global _fm_ready
+    L = lib()
+    if not _fm_ready:
+        f64p, i32p = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        P, M = C.POINTER(FmProblem), C.POINTER(FmModel)
+        L.oracle_fm_dense_predict.argtypes = [P, M, C.c_int, C.c_int, C.c_int]
+        L.oracle_fm_dense_predict.restype = C.c_double
+        L.oracle_fm_dense_build.argtypes = [P, M, C.c_int, f64p, f64p, f64p]
+        L.oracle_fm_dense_build.restype = C.c_double
+        L.oracle_fm_predict.argtypes = [P, M, C.c_int, C.c_int, C.c_int]
+        L.oracle_fm_predict.restype = C.c_double
+        L.oracle_fm_predict_batch.argtypes = [P, M, C.c_int64, i32p, i32p, i32p, C.c_int32, C.c_double, C.c_double, f64p]
+        L.oracle_fm_predict_batch.restype = C.c_int
+        L.oracle_fm_prepare.argtypes = [P, M, f64p, f64p]
+        L.oracle_fm_prepare.restype = None
+        L.oracle_fm_iteration.argtypes = [P, M, f64p, f64p, C.c_int]
+        L.oracle_fm_iteration.restype = C.c_double
+        _fm_ready = True
+    return L
+
+
+def fm_problem(ts, k: int, num_context_dims: int, reg_lw: float, reg_lf: float) -> FmProblem:
+    """ts: carskit_b200.capi.TrainingSet (kept alive by the caller)."""
+    p = FmProblem()
+    p.num_users, p.num_items, p.num_conditions = ts.num_users, ts.num_items, ts.num_conditions
+    p.num_context_dims, p.k, p.size = num_context_dims, k, ts.nnz
+    p.u, p.j, p.ctx, p.r = _ptr_i32(ts.u), _ptr_i32(ts.j), _ptr_i32(ts.ctx), _ptr_f64(ts.r)
+    p.reg_lw, p.reg_lf = reg_lw, reg_lf
+    return p
+
+
+def _fm_model(arrs: dict) -> FmModel:
+    m = FmModel()
+    m.w0, m.w, m.V = _ptr_f64(arrs["w0"]), _ptr_f64(arrs["w"]), _ptr_f64(arrs["V"])
+    return m
+
+
+def fm_dense_build(prob: FmProblem, arrs: dict, num_iters: int):
+    """Literal FM.buildModel(); returns (loss, errors, Q)."""
+    p = prob.num_users + prob.num_items + prob.num_conditions
+    errors = np.zeros(prob.size)
+    Q = np.zeros((prob.size, prob.k))
+    fv = np.zeros((prob.size, p))
+    m = _fm_model(arrs)
+    loss = _fm_lib().oracle_fm_dense_build(C.byref(prob), C.byref(m), num_iters, _ptr_f64(errors), _ptr_f64(Q), _ptr_f64(fv))
+    return loss, errors, Q
+
+
+def fm_dense_predict(prob: FmProblem, arrs: dict, u: int, j: int, c: int) -> float:
+    m = _fm_model(arrs)
+    return _fm_lib().oracle_fm_dense_predict(C.byref(prob), C.byref(m), u, j, c)
+
+
+def fm_predict(prob: FmProblem, arrs: dict, u, j, ctx, bound=False, lo=0.0, hi=0.0) -> np.ndarray:
+    u = np.ascontiguousarray(u, dtype=np.int32)
+    j = np.ascontiguousarray(j, dtype=np.int32)
+    ctx = np.ascontiguousarray(ctx, dtype=np.int32)
+    out = np.empty(u.shape[0])
+    m = _fm_model(arrs)
+    _fm_lib().oracle_fm_predict_batch(C.byref(prob), C.byref(m), u.shape[0], _ptr_i32(u), _ptr_i32(j), _ptr_i32(ctx),
+                                      1 if bound else 0, lo, hi, _ptr_f64(out))
+    return out
+
+
+def fm_prepare(prob: FmProblem, arrs: dict):
+    errors = np.zeros(prob.size)
+    Q = np.zeros((prob.size, prob.k))
+    m = _fm_model(arrs)
+    _fm_lib().oracle_fm_prepare(C.byref(prob), C.byref(m), _ptr_f64(errors), _ptr_f64(Q))
+    return errors, Q
+
+
+def fm_iteration(prob: FmProblem, arrs: dict, errors: np.ndarray, Q: np.ndarray, closed_den: bool) -> float:
+    m = _fm_model(arrs)
+    return _fm_lib().oracle_fm_iteration(C.byref(prob), C.byref(m), _ptr_f64(errors), _ptr_f64(Q), 1 if closed_den else 0)

@@ -66,8 +66,14 @@ def test_create_rejects_bad_descriptors(cars_lib):
     assert b"abi_version" in cars_lib.cars_last_error(None)
     d = capi.make_desc(ts, capi.CAMF_CI, 0)
     assert cars_lib.cars_create(C.byref(d), C.byref(h)) == -5
-    d = capi.make_desc(ts, capi.FM, 8)
-    assert cars_lib.cars_create(C.byref(d), C.byref(h)) == -5  # not built yet: says so, never falls back
+    d = capi.make_desc(ts, capi.FM, 8, num_context_dims=2)
+    assert cars_lib.cars_create(C.byref(d), C.byref(h)) == -1  # FM has its own entry points
+    assert b"cars_fm_create" in cars_lib.cars_last_error(None)
+    d = capi.make_desc(ts, capi.CAMF_CI, 8)
+    assert cars_lib.cars_fm_create(C.byref(d), C.byref(h)) == -1
+    d = capi.make_desc(ts, capi.FM, 8, num_context_dims=0)
+    assert cars_lib.cars_fm_create(C.byref(d), C.byref(h)) == -1
+    assert b"num_context_dims" in cars_lib.cars_fm_last_error(None)
     d = capi.make_desc(ts, capi.CAMF_CI, 8)
     d.ctx_ptr = None
     assert cars_lib.cars_create(C.byref(d), C.byref(h)) == -1
@@ -85,6 +91,10 @@ def test_no_cpu_fallback_without_a_device(cars_lib):
     assert b"no CPU path" in cars_lib.cars_last_error(None)
     with pytest.raises(capi.CarsError):
         capi.Engine(d)
+    d = capi.make_desc(ts, capi.FM, 8, num_context_dims=2)
+    assert cars_lib.cars_fm_create(C.byref(d), C.byref(h)) == -2
+    with pytest.raises(capi.CarsError):
+        capi.FmEngine(d)
 
 
 def test_product_never_imports_the_oracle():

@@ -1,0 +1,95 @@
+"""FM on the GPU (cars_fm_* through the C ABI) against the sparse CPU oracle with the same closed-form
+denominators.  The engine's sums are tree-ordered, the oracle's sequential: equality is up to summation
+order -- tolerances below; the model-level bar of the north star (predictions / RMSE within 1e-5) is
+asserted against the LITERAL dense oracle on an input it can afford."""
+import math
+
+import numpy as np
+import pytest
+
+from carskit_b200 import capi, recommender
+from tests.test_fm_oracle import clone, fm_inputs
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-9, 1e-12
+
+
+def run_gpu(ts, arrs, k, D, iters):
+    desc = capi.make_desc(ts, capi.FM, k, reg_lw=float(np.float32(0.01)), reg_lf=float(np.float32(0.02)), num_context_dims=D)
+    got = clone(arrs)
+    losses = []
+    with capi.FmEngine(desc, keepalive=ts) as eng:
+        eng.upload(got)
+        eng.prepare()
+        for _ in range(iters):
+            losses.append(eng.iteration())
+        eng.download(got)
+        st = eng.stats()
+    return got, losses, st
+
+
+@pytest.mark.parametrize("users,items,dims,nnz,k", [(12, 9, [2, 3], 150, 3), (300, 120, [4, 8], 20000, 16),
+                                                    (2000, 50, [32], 60000, 8), (50, 2000, [3, 3, 3], 30000, 64)])
+def test_fm_matches_sparse_oracle(oracle, cars_lib, users, items, dims, nnz, k):
+    ts, _, prob, arrs = fm_inputs(oracle, users, items, dims, nnz, k, seed=7)
+    iters = 3
+    got, losses, st = run_gpu(ts, arrs, k, len(dims), iters)
+    ref = clone(arrs)
+    e, Q = oracle.fm_prepare(prob, ref)
+    ref_losses = [oracle.fm_iteration(prob, ref, e, Q, closed_den=True) for _ in range(iters)]
+    for name in ("w0", "w", "V"):
+        np.testing.assert_allclose(got[name], ref[name], rtol=RTOL, atol=ATOL, err_msg=name)
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-10)
+    assert st.kernel_launches > 0 and st.nnz == ts.nnz
+
+
+def test_fm_within_1e5_of_the_literal_algorithm(oracle, cars_lib):
+    ts, test, prob, arrs = fm_inputs(oracle, 40, 30, [2, 3], 900, 4, seed=9, holdout=0.15)
+    dense = clone(arrs)
+    iters = 5
+    oracle.fm_dense_build(prob, dense, iters)
+    got, _, _ = run_gpu(ts, arrs, 4, 2, iters)
+    desc = capi.make_desc(ts, capi.FM, 4, reg_lw=float(np.float32(0.01)), reg_lf=float(np.float32(0.02)), num_context_dims=2)
+    with capi.FmEngine(desc, keepalive=ts) as eng:
+        eng.upload(got)
+        p_gpu = eng.predict(test["u"], test["j"], test["ctx"], bound=True, min_rate=1.0, max_rate=5.0)
+    p_ref = oracle.fm_predict(prob, dense, test["u"], test["j"], test["ctx"], bound=True, lo=1.0, hi=5.0)
+    assert np.max(np.abs(p_gpu - p_ref)) < 1e-5
+    rmse = lambda p: math.sqrt(float(np.mean((test["r"] - p) ** 2)))
+    assert abs(rmse(p_gpu) - rmse(p_ref)) < 1e-5
+
+
+def test_fm_predict_bit_identical_to_oracle(oracle, cars_lib):
+    ts, test, prob, arrs = fm_inputs(oracle, 100, 60, [3, 5], 4000, 10, seed=11, holdout=0.2)
+    arrs["w0"][0] = 0.25
+    desc = capi.make_desc(ts, capi.FM, 10, reg_lw=0.01, reg_lf=0.02, num_context_dims=2)
+    with capi.FmEngine(desc, keepalive=ts) as eng:
+        eng.upload(arrs)
+        for bound in (False, True):
+            a = eng.predict(test["u"], test["j"], test["ctx"], bound=bound, min_rate=1.0, max_rate=5.0)
+            b = oracle.fm_predict(prob, arrs, test["u"], test["j"], test["ctx"], bound=bound, lo=1.0, hi=5.0)
+            assert np.array_equal(a, b)
+
+
+def test_fm_recommender_mirror_and_errors(oracle, cars_lib):
+    ts, test, prob, arrs = fm_inputs(oracle, 150, 80, [4, 4], 8000, 8, seed=13, holdout=0.1)
+    rec = recommender.getRecommender("fm")(ts, test, conf={"num.factors": "8", "num.max.iter": "4", "FM": "-lw 0.01 -lf 0.02"})
+    m = rec.execute(init=arrs)
+    assert len(rec.iter_losses) == 4 and rec.iter_losses[-1] < rec.iter_losses[0]
+    ref = clone(arrs)
+    e, Q = oracle.fm_prepare(prob, ref)
+    for _ in range(4):
+        oracle.fm_iteration(prob, ref, e, Q, closed_den=True)
+    p_ref = oracle.fm_predict(prob, ref, test["u"], test["j"], test["ctx"], bound=True, lo=1.0, hi=5.0)
+    assert abs(m["RMSE"] - math.sqrt(float(np.mean((test["r"] - p_ref) ** 2)))) < 1e-9
+    # call-order and argument errors
+    desc = capi.make_desc(ts, capi.FM, 8, reg_lw=0.01, reg_lf=0.02, num_context_dims=2)
+    with capi.FmEngine(desc, keepalive=ts) as eng:
+        with pytest.raises(capi.CarsError) as ex:
+            eng.iteration()
+        assert ex.value.code == -6
+    with pytest.raises(capi.CarsError):
+        capi.FmEngine(capi.make_desc(ts, capi.FM, 8, num_context_dims=0), keepalive=ts)
+    with pytest.raises(capi.CarsError):
+        capi.Engine(capi.make_desc(ts, capi.FM, 8, num_context_dims=2), keepalive=ts)
