@@ -51,6 +51,10 @@ WORKLOADS = {
                              seed=20261017),
     "camf_cu_f128_2Mx200Kx64c_200M": dict(model="camf_cu", F=128, users=2_000_000, items=200_000,
                                           dims=[16, 16, 16, 16], nnz=200_000_000, seed=20261017),
+    # FM (reference ALS semantics, FM.java); BASELINE.json configs[3] shape scaled to one GPU's share
+    "fm_k64_250Kx25Kx32c_25M": dict(model="fm", F=64, users=250_000, items=25_000, dims=[32], nnz=25_000_000,
+                                    seed=20261017),
+    "fm_k16_tiny": dict(model="fm", F=16, users=5_000, items=1_000, dims=[32], nnz=200_000, seed=20261017),
 }
 DEFAULT_WORKLOAD = "camf_ci_f64_1Mx100Kx32c_100M"
 
@@ -353,6 +357,91 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_fm(args, wl, wl_name, rank, world, local_rank):
+    """FM (ALS) line: rating-iterations/s of cars_fm_iteration, single GPU.  Same JSON contract; the unit of
+    work is one rating x one ALS iteration (88 + 144 k algorithmic bytes)."""
+    import torch
+    from carskit_b200 import capi, recommender, synth
+    if world > 1:
+        raise SystemExit("bench.py: the FM path is single-GPU in this round (DESIGN.md section 7)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; carskit_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    ts, _ = synth.make_training_set(wl["users"], wl["items"], wl["dims"], wl["nnz"], seed=wl["seed"], order="user_sorted")
+    k, D = wl["F"], len(wl["dims"])
+    p = ts.num_users + ts.num_items + ts.num_conditions
+    rng = np.random.default_rng(wl["seed"] + 7919)
+    init = {"w0": np.zeros(1), "w": rng.random(p), "V": 0.1 * rng.standard_normal((p, k))}
+    conf = {"num.factors": str(k), "num.max.iter": str(args.steps), "FM": "-lw 0.01 -lf 0.02"}
+    rec = recommender.FM(ts, None, conf=conf, device=local_rank)
+    rec.initModel(init={n: v.copy() for n, v in init.items()})
+    eng = rec.open_engine()
+    for it in range(args.warmup):
+        rec.train_epoch(it + 1)
+    l0 = eng.stats().kernel_launches
+    sampler = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    sampler.start()
+    t0 = time.perf_counter()
+    kms = []
+    for it in range(args.steps):
+        rec.train_epoch(args.warmup + it + 1)
+        kms.append(eng.stats().last_iteration_ms)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = eng.stats().kernel_launches - l0
+    rec.close_engine()
+    ms = float(np.sum(kms))  # device time (CUDA events inside the library, on its stream)
+    value = ts.nnz * args.steps / (ms * 1e-3)
+    rec2 = recommender.FM(ts, None, conf=conf, device=local_rank)
+    rec2.initModel(init=init)
+    t0 = time.perf_counter()
+    rec2.buildModel()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    st2 = rec2.stats
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle_py as orc
+        orc.build()
+        n = min(ts.nnz, 400_000)
+        sub = capi.TrainingSet(num_users=ts.num_users, num_items=ts.num_items, u=ts.u[:n], j=ts.j[:n], r=ts.r[:n],
+                               ctx=ts.ctx[:n], num_conditions=ts.num_conditions, num_contexts=ts.num_contexts,
+                               ctx_ptr=ts.ctx_ptr, ctx_cond=ts.ctx_cond, global_mean=ts.global_mean)
+        prob = orc.fm_problem(sub, k, D, np.float32(0.01), np.float32(0.02))
+        work = {n_: v.copy() for n_, v in init.items()}
+        e, Q = orc.fm_prepare(prob, work)
+        t0 = time.perf_counter()
+        orc.fm_iteration(prob, work, e, Q, closed_den=True)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n / dt, "unit": "rating-iterations/s", "cores": 1, "kind": "port",
+               "sample": f"first {n} of {ts.nnz} ratings, one ALS iteration of the sparse oracle (the reference's own "
+                         "dense loops are O(k*p*size))", "host_cores_available": os.cpu_count()}
+    B = 88 + 144 * k
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    achieved = B * ts.nnz / (float(np.mean(kms)) * 1e-3) / 1e9
+    out = {
+        "metric": "fm_als_rating_iterations_per_sec", "value": value, "unit": "rating-iterations/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl_name, "model": "fm", "factors": k, "users": wl["users"], "items": wl["items"],
+                   "conditions": int(sum(wl["dims"])), "context_dims": D, "nnz": ts.nnz,
+                   "l2": "inputs larger than L2 (Qc alone is nnz*k*8 bytes); no flush", "wall_ms_per_step": wall * 1e3 / args.steps},
+        "clocks": clocks,
+        "e2e": {"value": ts.nnz * args.steps / e2e_s, "unit": "rating-iterations/s",
+                "h2d_bytes_per_step": int(st2.h2d_bytes / args.steps), "d2h_bytes_per_step": int(st2.d2h_bytes / args.steps),
+                "seconds": e2e_s},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "fm_piece_reduce_kernel + fm_row_update_kernel (one ALS iteration)",
+                     "algorithmic_bytes_per_update": B, "updates_per_launch": ts.nnz},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -366,7 +455,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if wl["model"] == "fm":
+        if args.impl == "reference":
+            raise SystemExit("bench.py: --impl reference times the SGD loop; the FM line carries its own cpu_baseline")
+        run_fm(args, wl, args.workload, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, wl, args.workload, rank, world)
     else:
         if world != args.gpus and world == 1 and args.gpus > 1:
