@@ -19,7 +19,8 @@ SCHED_FLAGGED, SCHED_WAVEFRONT, SCHED_DATAFLOW = 0, 1, 2
 MODEL_NAMES = {"pmf": PMF, "biasedmf": BIASEDMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcarskit_b200.so")
+# CARSKIT_B200_LIB selects another build of the same ABI (e.g. the developer build with stage tracing)
+LIB_PATH = os.environ.get("CARSKIT_B200_LIB") or os.path.join(_HERE, "libcarskit_b200.so")
 
 _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)

@@ -216,10 +216,18 @@ static LaunchPlan pick_flagged(int Fp, int variant) {
       }
       return pick_flagged_shape<MODEL, 256, 3>(Fp);
     }
-    case 4: {
+    case 5: {  // 16 lanes per rating: two ratings per warp, short turns
       LaunchPlan p;
       if (Fp > 32 && Fp <= 64) {
-        p.threads = 128; p.fn = (const void*)sgd_flagged_kernel<MODEL, 4, 8, 128, 5>; p.lpr = 4; p.v = 8;
+        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 16, 2, 256, 4>; p.lpr = 16; p.v = 2;
+        return p;
+      }
+      return pick_flagged_shape<MODEL, 256, 3>(Fp);
+    }
+    case 6: {  // one rating per warp
+      LaunchPlan p;
+      if (Fp > 32 && Fp <= 64) {
+        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 32, 1, 256, 6>; p.lpr = 32; p.v = 1;
         return p;
       }
       return pick_flagged_shape<MODEL, 256, 3>(Fp);
@@ -692,8 +700,30 @@ extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
     int64_t nnz = h->nnz;
     unsigned off_j = 64u;
     unsigned off_u = 64u + (unsigned)h->d.num_items;
+#ifdef CARS_TRACE
+    // developer build only (scripts/trace_flagged.py): per-rating stage timestamps of a window of ratings
+    static unsigned long long* d_trace = nullptr;
+    int64_t trace_lo = 0, trace_n = 0;
+    if (const char* e = getenv("CARS_TRACE_WINDOW")) sscanf(e, "%lld:%lld", (long long*)&trace_lo, (long long*)&trace_n);
+    if (trace_n > 0 && !d_trace) cudaMalloc((void**)&d_trace, (size_t)trace_n * 64);
+    void* args[] = {&m, &recs, &nnz, &h->d_flags, &off_u, &off_j, &lrate, &h->d_partial, &d_trace, &trace_lo, &trace_n};
+#else
     void* args[] = {&m, &recs, &nnz, &h->d_flags, &off_u, &off_j, &lrate, &h->d_partial};
+#endif
     CUDA_TRY(h, cudaLaunchCooperativeKernel(plan.fn, dim3(h->grid), dim3(h->block), args, h->smem, h->stream));
+#ifdef CARS_TRACE
+    if (trace_n > 0) {
+      if (const char* out = getenv("CARS_TRACE_OUT")) {
+        std::vector<unsigned long long> hb((size_t)trace_n * 8);
+        cudaStreamSynchronize(h->stream);
+        cudaMemcpy(hb.data(), d_trace, hb.size() * 8, cudaMemcpyDeviceToHost);
+        std::vector<RatingRec> hr((size_t)trace_n);
+        cudaMemcpy(hr.data(), h->d_rec + trace_lo, hr.size() * sizeof(RatingRec), cudaMemcpyDeviceToHost);
+        FILE* f = fopen(out, "wb");
+        if (f) { fwrite(hb.data(), 8, hb.size(), f); fwrite(hr.data(), sizeof(RatingRec), hr.size(), f); fclose(f); }
+      }
+    }
+#endif
     h->st.kernel_launches += 1;
   } else {
     LaunchPlan plan = pick_plan(h->d.model, h->d.mode, m.Fp);

@@ -157,8 +157,11 @@ struct Operands {
 };
 
 // Scalars of one update: itemBias[j] and the lane's condition-bias cell.
+constexpr int kCondUnknown = -2;  // "look the condition id up" (a pre-fetched id is >= -1)
+
 template <int MODEL, int LPR, int V>
-__device__ __forceinline__ void gather_scalars(const DeviceModel& m, int u, int j, int ctx, int gl, Operands<V>& o) {
+__device__ __forceinline__ void gather_scalars(const DeviceModel& m, int u, int j, int ctx, int gl, Operands<V>& o,
+                                               int cond_prefetched = kCondUnknown) {
   constexpr bool kItemBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CU);
   constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU);
   o.bj = 0.0;
@@ -166,7 +169,7 @@ __device__ __forceinline__ void gather_scalars(const DeviceModel& m, int u, int 
   o.cb_ptr = nullptr;
   o.cb = 0.0;
   if (kHasCond && gl < m.Dmax) {
-    const int cond = __ldg(m.ctx_tab + (int64_t)ctx * m.Dmax + gl);
+    const int cond = cond_prefetched != kCondUnknown ? cond_prefetched : __ldg(m.ctx_tab + (int64_t)ctx * m.Dmax + gl);
     if (cond >= 0) {
       if (MODEL == M_CAMF_C) o.cb_ptr = m.cond_bias + cond;
       if (MODEL == M_CAMF_CI) o.cb_ptr = m.ic_bias + (int64_t)j * m.C + cond;
@@ -540,7 +543,11 @@ __global__ void __launch_bounds__(THREADS, MINB)
 template <int MODEL, int LPR, int V, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
     sgd_flagged_kernel(DeviceModel m, const RatingRec* __restrict__ recs, int64_t nnz, unsigned* flags,
-                       unsigned off_u, unsigned off_j, double lr, double* block_partial) {
+                       unsigned off_u, unsigned off_j, double lr, double* block_partial
+#ifdef CARS_TRACE
+                       , unsigned long long* trace, int64_t trace_lo, int64_t trace_n
+#endif
+    ) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int G = 32 / LPR;
   constexpr int WARPS = THREADS / 32;
@@ -553,6 +560,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
   double* prod = reinterpret_cast<double*>(smem_raw) + (size_t)(warp * G + gw) * prod_stride;
   unsigned* done_u = flags + off_u;
   unsigned* done_j = flags + off_j;
+  constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU);
 
   // interleave CTAs so that consecutive ratings land on different SMs
   const int64_t T = (int64_t)gridDim.x * WARPS * G;
@@ -563,10 +571,20 @@ __global__ void __launch_bounds__(THREADS, MINB)
   rec.u = rec.j = rec.ctx = rec.ku = rec.kj = 0; rec.r = 0.0;
   if (n < nnz) rec = ld_rec(recs + n);
   next = rec;
+#ifdef CARS_TRACE
+  unsigned long long tries = 0;
+#endif
   for (;;) {
     const bool active = n < nnz;
     if (!__any_sync(0xffffffffu, active)) break;
     if (active) {
+#ifdef CARS_TRACE
+      const long long tc0 = clock64();
+      tries++;
+#endif
+      // the lane's condition id (static table) is fetched beside the poll, off the gather's critical path
+      int cond = -1;
+      if (kHasCond && gl < m.Dmax) cond = __ldg(m.ctx_tab + (int64_t)rec.ctx * m.Dmax + gl);
       bool ok = true;
       if (gl == 0) ok = (ld_relaxed_u32(done_j + rec.j) == (unsigned)rec.kj);
       if (gl == 1) ok = (ld_relaxed_u32(done_u + rec.u) == (unsigned)rec.ku);
@@ -575,14 +593,40 @@ __global__ void __launch_bounds__(THREADS, MINB)
         __syncwarp(gmask);
         const int64_t nn = n + T;
         if (nn < nnz) next = ld_rec(recs + nn);  // flies during this rating's gather and arithmetic
+#ifdef CARS_TRACE
+        const long long tc1 = clock64();
+        unsigned long long tg1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg1));
+#endif
         UserRegs<V> us;
-        acc = __dadd_rn(acc, rating_update<MODEL, LPR, V>(m, rec.u, rec.j, rec.ctx, rec.r, lr, prod, gl, gmask, us,
-                                                          true, true));
+        Operands<V> o;
+        gather_rows<MODEL, LPR, V>(m, rec.u, rec.j, gl, us, o, true);
+        gather_scalars<MODEL, LPR, V>(m, rec.u, rec.j, rec.ctx, gl, o, cond);
+#ifdef CARS_TRACE
+        long long tc2;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(tc2) : "d"(us.p[V - 1].y), "d"(o.q[V - 1].y), "d"(o.cb), "d"(us.p[0].x), "d"(o.q[0].x));
+#endif
+        acc = __dadd_rn(acc, compute_scatter<MODEL, LPR, V>(m, rec.u, rec.j, rec.ctx, rec.r, lr, prod, gl, gmask, us,
+                                                            o, true));
         __syncwarp(gmask);  // the group's stores happen-before lane 0's release
+#ifdef CARS_TRACE
+        const long long tc3 = clock64();
+#endif
         if (gl == 0) {
           st_release_u32(done_j + rec.j, (unsigned)rec.kj + 1u);
           st_relaxed_u32(done_u + rec.u, (unsigned)rec.ku + 1u);
         }
+#ifdef CARS_TRACE
+        if (gl == 0 && trace && n >= trace_lo && n < trace_lo + trace_n) {
+          const long long tc4 = clock64();
+          unsigned long long tg4;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg4));
+          unsigned long long* t = trace + (n - trace_lo) * 8;
+          t[0] = (unsigned long long)(tc1 - tc0); t[1] = (unsigned long long)(tc2 - tc1); t[2] = (unsigned long long)(tc3 - tc2);
+          t[3] = (unsigned long long)(tc4 - tc3); t[4] = tg1; t[5] = tg4; t[6] = tries; t[7] = (unsigned long long)tc0;
+        }
+        tries = 0;
+#endif
         rec = next;
         n = nn;
       }
