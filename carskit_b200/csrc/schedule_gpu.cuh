@@ -1,10 +1,11 @@
 // schedule_gpu.cuh -- K7f on the device: building the level-sorted record stream of the flagged wavefront
 // without a host-side sort.
 //
-// Host part (inherently sequential, one pass in reference order, ~5 ns per rating): for every rating its
+// Host part (inherently sequential, one pass in reference order, a few ns per rating): for every rating its
 // dependency level  level(n) = 1 + max(level(prev rating of u), level(prev rating of j))  and its positions
 // ku / kj in the user's / item's chain.  The pass is chunked; each chunk is written straight into pinned
-// staging buffers and copied to the device while the next chunk is being computed.
+// staging buffers and copied to the device while the next chunk is being computed.  The caller's own
+// u / j / ctx / r arrays are copied by a second host thread on a second stream at the same time.
 // Device part: stable LSD radix sort of (level, n) pairs (CUB), then one gather kernel that packs the
 // 32-byte RatingRec stream in level order.
 #pragma once
@@ -12,6 +13,7 @@
 
 #include <cstdint>
 #include <cub/device/device_radix_sort.cuh>
+#include <thread>
 #include <vector>
 
 #include "sgd_kernels.cuh"
@@ -53,24 +55,30 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
   if (nnz == 0) return cudaSuccess;
   const int64_t CH = 1 << 22;  // ratings per staging chunk
   struct Stage {
-    int32_t* i32 = nullptr;  // [6 x CH] u j ctx level ku kj
-    double* r = nullptr;
+    int32_t* i32 = nullptr;  // [3 x CH] level ku kj
     cudaEvent_t ev = nullptr;
     bool used = false;
   } st[2];
   RatingSoA d;
   uint32_t *d_idx_in = nullptr, *d_idx_out = nullptr, *d_key_out = nullptr;
   void* d_temp = nullptr;
+  cudaStream_t copy_stream = nullptr;
   cudaError_t e = cudaSuccess;
-  std::vector<int32_t> last_u, last_j;
-  std::vector<uint32_t> cu, cj;
+  struct Chain {
+    int32_t level;
+    uint32_t count;
+  };
+  std::vector<Chain> tu, tj;  // per user / per item: level of its last rating, ratings seen so far
   std::vector<int64_t> level_count;
+  std::thread copier;
+  cudaError_t copy_err = cudaSuccess;
   auto cleanup = [&]() {
+    if (copier.joinable()) copier.join();
     for (auto& s : st) {
       if (s.i32) cudaFreeHost(s.i32);
-      if (s.r) cudaFreeHost(s.r);
       if (s.ev) cudaEventDestroy(s.ev);
     }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     cudaFree(d.u); cudaFree(d.j); cudaFree(d.ctx); cudaFree(d.level); cudaFree(d.ku); cudaFree(d.kj); cudaFree(d.r);
     cudaFree(d_idx_in); cudaFree(d_idx_out); cudaFree(d_key_out); cudaFree(d_temp);
   };
@@ -85,8 +93,7 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
 
   const int64_t ch = nnz < CH ? nnz : CH;
   for (auto& s : st) {
-    SG_TRY(cudaMallocHost((void**)&s.i32, (size_t)ch * 6 * sizeof(int32_t)));
-    SG_TRY(cudaMallocHost((void**)&s.r, (size_t)ch * sizeof(double)));
+    SG_TRY(cudaMallocHost((void**)&s.i32, (size_t)ch * 3 * sizeof(int32_t)));
     SG_TRY(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
   }
   SG_TRY(cudaMalloc((void**)&d.u, (size_t)nnz * 4));
@@ -96,59 +103,71 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
   SG_TRY(cudaMalloc((void**)&d.ku, (size_t)nnz * 4));
   SG_TRY(cudaMalloc((void**)&d.kj, (size_t)nnz * 4));
   SG_TRY(cudaMalloc((void**)&d.r, (size_t)nnz * 8));
+  SG_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
   try {
-    last_u.assign((size_t)num_users, 0);
-    last_j.assign((size_t)num_items, 0);
-    cu.assign((size_t)num_users, 0u);
-    cj.assign((size_t)num_items, 0u);
+    tu.assign((size_t)num_users, Chain{0, 0u});
+    tj.assign((size_t)num_items, Chain{0, 0u});
     level_count.assign(1024, 0);
   } catch (...) {
     cleanup();
     return cudaErrorMemoryAllocation;
   }
+  // second host thread: the caller's arrays go to the device as they are (pageable copies are staged by the
+  // driver and block the issuing thread, hence a thread of their own)
+  int dev = 0;
+  SG_TRY(cudaGetDevice(&dev));
+  copier = std::thread([&, dev]() {
+    cudaError_t ce = cudaSetDevice(dev);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d.u, u, (size_t)nnz * 4, cudaMemcpyHostToDevice, copy_stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d.j, j, (size_t)nnz * 4, cudaMemcpyHostToDevice, copy_stream);
+    if (ce == cudaSuccess && ctx) ce = cudaMemcpyAsync(d.ctx, ctx, (size_t)nnz * 4, cudaMemcpyHostToDevice, copy_stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d.r, r, (size_t)nnz * 8, cudaMemcpyHostToDevice, copy_stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(copy_stream);
+    copy_err = ce;
+  });
+  info->h2d_bytes += nnz * (ctx ? 20 : 16);
 
   int32_t num_levels = 0;
   for (int64_t base = 0, c = 0; base < nnz; base += ch, c++) {
     Stage& s = st[c & 1];
     if (s.used) SG_TRY(cudaEventSynchronize(s.ev));
     const int64_t len = (nnz - base < ch) ? nnz - base : ch;
-    int32_t *su = s.i32, *sj = s.i32 + ch, *sc = s.i32 + 2 * ch, *sl = s.i32 + 3 * ch, *sku = s.i32 + 4 * ch,
-            *skj = s.i32 + 5 * ch;
+    int32_t *sl = s.i32, *sku = s.i32 + ch, *skj = s.i32 + 2 * ch;
     for (int64_t i = 0; i < len; i++) {
       const int64_t n = base + i;
       const int32_t uu = u[n], jj = j[n];
-      const int32_t cc = ctx ? ctx[n] : 0;
       if ((uint32_t)uu >= (uint32_t)num_users || (uint32_t)jj >= (uint32_t)num_items ||
-          (ctx && (uint32_t)cc >= (uint32_t)num_contexts)) {
+          (ctx && (uint32_t)ctx[n] >= (uint32_t)num_contexts)) {
         info->bad_index = n;
         cudaStreamSynchronize(stream);
         cleanup();
         return cudaSuccess;
       }
-      const int32_t a = last_u[uu], b = last_j[jj];
-      const int32_t l = 1 + (a > b ? a : b);
-      last_u[uu] = l;
-      last_j[jj] = l;
+      Chain& a = tu[(size_t)uu];
+      Chain& b = tj[(size_t)jj];
+      const int32_t l = 1 + (a.level > b.level ? a.level : b.level);
+      a.level = l;
+      b.level = l;
       if (l > num_levels) {
         num_levels = l;
         if ((size_t)l >= level_count.size()) level_count.resize((size_t)l * 2, 0);
       }
       level_count[l]++;
-      su[i] = uu; sj[i] = jj; sc[i] = cc; sl[i] = l;
-      sku[i] = (int32_t)cu[uu]++;
-      skj[i] = (int32_t)cj[jj]++;
-      s.r[i] = r[n];
+      sl[i] = l;
+      sku[i] = (int32_t)a.count++;
+      skj[i] = (int32_t)b.count++;
     }
-    SG_TRY(cudaMemcpyAsync(d.u + base, su, (size_t)len * 4, cudaMemcpyHostToDevice, stream));
-    SG_TRY(cudaMemcpyAsync(d.j + base, sj, (size_t)len * 4, cudaMemcpyHostToDevice, stream));
-    if (ctx) SG_TRY(cudaMemcpyAsync(d.ctx + base, sc, (size_t)len * 4, cudaMemcpyHostToDevice, stream));
     SG_TRY(cudaMemcpyAsync(d.level + base, sl, (size_t)len * 4, cudaMemcpyHostToDevice, stream));
     SG_TRY(cudaMemcpyAsync(d.ku + base, sku, (size_t)len * 4, cudaMemcpyHostToDevice, stream));
     SG_TRY(cudaMemcpyAsync(d.kj + base, skj, (size_t)len * 4, cudaMemcpyHostToDevice, stream));
-    SG_TRY(cudaMemcpyAsync(d.r + base, s.r, (size_t)len * 8, cudaMemcpyHostToDevice, stream));
     SG_TRY(cudaEventRecord(s.ev, stream));
     s.used = true;
-    info->h2d_bytes += len * (ctx ? 32 : 28);
+    info->h2d_bytes += len * 12;
+  }
+  copier.join();
+  if (copy_err != cudaSuccess) {
+    cleanup();
+    return copy_err;
   }
   info->num_levels = num_levels;
   for (int32_t l = 1; l <= num_levels; l++)
