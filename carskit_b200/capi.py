@@ -36,7 +36,7 @@ class CarsDesc(C.Structure):
         ("global_mean", C.c_double),
         ("reg_u", C.c_double), ("reg_i", C.c_double), ("reg_b", C.c_double), ("reg_c", C.c_double),
         ("reg_lw", C.c_double), ("reg_lf", C.c_double),
-        ("num_context_dims", C.c_int32), ("reserved1", C.c_int32),
+        ("num_context_dims", C.c_int32), ("reserved1", C.c_int32), ("global_nnz", C.c_int64),
         ("stream", C.c_void_p),
     ]
 
@@ -61,7 +61,10 @@ EXPORTS = [
     "cars_get_stream", "cars_version", "cars_item_block_doubles", "cars_epoch_sharded_begin",
     "cars_epoch_sharded_finish", "cars_fm_create", "cars_fm_upload", "cars_fm_prepare", "cars_fm_iteration",
     "cars_fm_download", "cars_fm_predict", "cars_fm_get_stats", "cars_fm_last_error", "cars_fm_destroy",
+    "cars_fm_exchange_doubles", "cars_fm_iteration_sharded", "cars_fm_get_stream",
 ]
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
 
 
 class CarsFmArrays(C.Structure):
@@ -139,6 +142,12 @@ def load_library(path: Optional[str] = None):
     lib.cars_fm_get_stats.restype = C.c_int
     lib.cars_fm_last_error.argtypes = [H]
     lib.cars_fm_last_error.restype = C.c_char_p
+    lib.cars_fm_exchange_doubles.argtypes = [H, C.POINTER(C.c_int64)]
+    lib.cars_fm_exchange_doubles.restype = C.c_int
+    lib.cars_fm_iteration_sharded.argtypes = [H, C.c_void_p, ALLREDUCE_FN, C.c_void_p, _f64p]
+    lib.cars_fm_iteration_sharded.restype = C.c_int
+    lib.cars_fm_get_stream.argtypes = [H]
+    lib.cars_fm_get_stream.restype = C.c_void_p
     lib.cars_fm_destroy.argtypes = [H]
     lib.cars_fm_destroy.restype = None
     lib.cars_version.argtypes = []
@@ -201,7 +210,7 @@ class TrainingSet:
 def make_desc(ts: TrainingSet, model: int, num_factors: int, *, mode: int = EXACT, device: int = 0,
               reg_u: float = 0.0, reg_i: float = 0.0, reg_b: float = 0.0, reg_c: float = 0.0,
               reg_lw: float = 0.0, reg_lf: float = 0.0, num_context_dims: int = 0,
-              stream: int = 0, schedule: int = SCHED_FLAGGED) -> CarsDesc:
+              stream: int = 0, schedule: int = SCHED_FLAGGED, global_nnz: int = 0) -> CarsDesc:
     """Fill a cars_desc.  The reg_* values must already be float-widened (use f32())."""
     d = CarsDesc()
     d.abi_version = ABI_VERSION
@@ -219,6 +228,7 @@ def make_desc(ts: TrainingSet, model: int, num_factors: int, *, mode: int = EXAC
     d.global_mean = ts.global_mean
     d.reg_u, d.reg_i, d.reg_b, d.reg_c, d.reg_lw, d.reg_lf = reg_u, reg_i, reg_b, reg_c, reg_lw, reg_lf
     d.num_context_dims = num_context_dims
+    d.global_nnz = global_nnz
     d.stream = stream or None
     return d
 
@@ -381,6 +391,35 @@ class FmEngine:
         loss = C.c_double()
         self._check(self.lib.cars_fm_iteration(self.h, C.byref(loss)))
         return loss.value
+
+    def exchange_doubles(self) -> int:
+        n = C.c_int64()
+        self._check(self.lib.cars_fm_exchange_doubles(self.h, C.byref(n)))
+        return n.value
+
+    def iteration_sharded(self, dev_buf_ptr: int, allreduce) -> float:
+        """allreduce(dev_ptr: int, count: int) must sum `count` doubles at device address dev_ptr over the
+        ranks, in place, ordered on the handle's stream; exceptions it raises fail the iteration."""
+        err = []
+
+        def _cb(user, ptr, count):
+            try:
+                allreduce(int(ptr), int(count))
+                return 0
+            except Exception as ex:  # noqa: BLE001 -- reported through the return code
+                err.append(ex)
+                return 1
+
+        cb = ALLREDUCE_FN(_cb)
+        loss = C.c_double()
+        rc = self.lib.cars_fm_iteration_sharded(self.h, C.c_void_p(dev_buf_ptr), cb, None, C.byref(loss))
+        if err:
+            raise err[0]
+        self._check(rc)
+        return loss.value
+
+    def stream(self) -> int:
+        return int(self.lib.cars_fm_get_stream(self.h) or 0)
 
     def predict(self, u, j, ctx, bound=False, min_rate=0.0, max_rate=0.0) -> np.ndarray:
         u = np.ascontiguousarray(u, dtype=np.int32)

@@ -28,7 +28,7 @@ struct cars_fm_handle {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int32_t U = 0, I = 0, C = 0, p = 0, k = 0, D = 1;
-  int64_t N = 0;
+  int64_t N = 0, Nglobal = 0;
   double reg_lw = 0, reg_lf = 0, w0_denom = 1, xc = 1;
   int32_t *d_u = nullptr, *d_j = nullptr, *d_c = nullptr;
   double *d_r = nullptr, *d_e = nullptr, *d_Qc = nullptr;
@@ -148,9 +148,10 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
   h->device = d->device; h->sm_count = prop.multiProcessorCount;
   h->U = d->num_users; h->I = d->num_items; h->C = d->num_conditions; h->p = h->U + h->I + h->C;
   h->k = d->num_factors; h->D = d->num_context_dims; h->N = d->nnz;
+  h->Nglobal = d->global_nnz > 0 ? d->global_nnz : d->nnz;
   h->reg_lw = d->reg_lw; h->reg_lf = d->reg_lf;
   h->xc = 1.0 / (double)h->D;                                   // FM.java:86
-  h->w0_denom = (double)((float)h->N + (float)d->reg_lw);      // FM.java:159: int + float is a FLOAT addition
+  h->w0_denom = (double)((float)h->Nglobal + (float)d->reg_lw);  // FM.java:159: int + float is a FLOAT addition
   int rc = CARS_OK;
 #define FM_TRY_H(expr)                                      \
   do {                                                      \
@@ -281,11 +282,11 @@ extern "C" int cars_fm_iteration(cars_fm_handle* h, double* loss_out) {
   FM_TRY(h, cudaGetLastError());
   h->launches += 4;
   // w_l, l = 0..p-1 (:172-191): users, items, contexts
-  const double w_reg = (double)h->N * h->reg_lw;
+  const double w_reg = (double)h->Nglobal * h->reg_lw;
   for (int fld = 0; fld < 3; fld++)
     if ((rc = field_step<0>(h, fld, h->d_w, 1, 0, nullptr, w_reg))) return rc;
   // V_lf, f = 0..k-1 { l = 0..p-1 } (:194-217)
-  const double v_reg = (double)h->N * h->reg_lf;
+  const double v_reg = (double)h->Nglobal * h->reg_lf;
   for (int f = 0; f < h->k; f++)
     for (int fld = 0; fld < 3; fld++)
       if ((rc = field_step<1>(h, fld, h->d_V, h->k, f, h->d_Qc + (int64_t)f * h->N, v_reg))) return rc;
@@ -297,6 +298,79 @@ extern "C" int cars_fm_iteration(cars_fm_handle* h, double* loss_out) {
   FM_TRY(h, cudaEventElapsedTime(&ms, h->ev_beg, h->ev_end));
   h->last_iter_ms = ms;
   if (loss_out) *loss_out = (h->h_scal[2] + h->h_scal[3]) * 0.05;  // loss *= 0.05 (:218)
+  return CARS_OK;
+}
+
+// ---- row-sharded iteration: the same sweep with an all-reduce of the per-coordinate sums ------------------
+template <int MODE>
+static int field_step_sharded(cars_fm_handle* h, int which, double* coef, int stride, int col, double* Qf, double size_reg,
+                              double* dev_buf, cars_allreduce_fn ar, void* user) {
+  FieldStore& fs = h->fld[which];
+  const FmField& f = fs.f;
+  if (f.ncoord == 0) return CARS_OK;
+  if (f.num_pieces > 0) {
+    const unsigned blocks = (unsigned)((f.num_pieces * 32 + 255) / 256);
+    fm_piece_reduce_kernel<MODE><<<blocks, 256, 0, h->stream>>>(f, h->d_e, Qf, coef, stride, col, h->d_part);
+    FM_TRY(h, cudaGetLastError());
+    h->launches++;
+  }
+  const unsigned cb = (unsigned)((f.ncoord + 255) / 256);
+  fm_coord_partial_kernel<MODE><<<cb, 256, 0, h->stream>>>(f, h->d_part, dev_buf);
+  FM_TRY(h, cudaGetLastError());
+  if (ar(user, dev_buf, 2 * (int64_t)f.ncoord) != 0) return fm_fail(h, CARS_E_STATE, "the all-reduce callback failed");
+  fm_coord_finish_kernel<<<cb, 256, 0, h->stream>>>(f, dev_buf, size_reg, coef, stride, col, fs.d_delta);
+  FM_TRY(h, cudaGetLastError());
+  h->launches += 2;
+  if (h->N) {
+    fm_row_update_kernel<MODE><<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(f, fs.d_delta, h->N, h->d_e, Qf);
+    FM_TRY(h, cudaGetLastError());
+    h->launches++;
+  }
+  return CARS_OK;
+}
+
+extern "C" int cars_fm_exchange_doubles(const cars_fm_handle* h, int64_t* out) {
+  if (!h || !out) return CARS_E_INVALID;
+  int64_t m = h->U > h->I ? h->U : h->I;
+  if (h->C > m) m = h->C;
+  *out = 2 * m + 2;
+  return CARS_OK;
+}
+
+extern "C" int cars_fm_iteration_sharded(cars_fm_handle* h, double* dev_buf, cars_allreduce_fn ar, void* user,
+                                         double* loss_out) {
+  if (!h) return CARS_E_INVALID;
+  if (!dev_buf || !ar) return fm_fail(h, CARS_E_INVALID, "dev_buf and allreduce are required");
+  if (!h->prepared) return fm_fail(h, CARS_E_STATE, "cars_fm_iteration before cars_fm_prepare");
+  FM_TRY(h, cudaSetDevice(h->device));
+  FM_TRY(h, cudaEventRecord(h->ev_beg, h->stream));
+  int rc;
+  fm_w0_reduce_kernel<<<h->red_blocks, 256, 0, h->stream>>>(h->d_e, h->d_w0, h->N, h->d_part);
+  fm_w0_partial_kernel<<<1, 32, 0, h->stream>>>(h->d_part, h->red_blocks, dev_buf);
+  FM_TRY(h, cudaGetLastError());
+  // sum(e - w0) is a sum over the LOCAL rows of (e_n - w0): the global sum is the sum of the parts
+  if (ar(user, dev_buf, 2) != 0) return fm_fail(h, CARS_E_STATE, "the all-reduce callback failed");
+  fm_w0_finish_global_kernel<<<1, 32, 0, h->stream>>>(dev_buf, h->w0_denom, h->reg_lw, h->d_w0, h->d_scal);
+  if (h->N) fm_w0_apply_kernel<<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(h->d_e, h->d_scal, h->N);
+  fm_wreg_kernel<<<1, 256, 0, h->stream>>>(h->d_w, h->p, h->reg_lw, h->d_scal + 3);
+  FM_TRY(h, cudaGetLastError());
+  h->launches += 5;
+  const double w_reg = (double)h->Nglobal * h->reg_lw;
+  for (int fld = 0; fld < 3; fld++)
+    if ((rc = field_step_sharded<0>(h, fld, h->d_w, 1, 0, nullptr, w_reg, dev_buf, ar, user))) return rc;
+  const double v_reg = (double)h->Nglobal * h->reg_lf;
+  for (int f = 0; f < h->k; f++)
+    for (int fld = 0; fld < 3; fld++)
+      if ((rc = field_step_sharded<1>(h, fld, h->d_V, h->k, f, h->d_Qc + (int64_t)f * h->N, v_reg, dev_buf, ar, user)))
+        return rc;
+  FM_TRY(h, cudaEventRecord(h->ev_end, h->stream));
+  FM_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  FM_TRY(h, cudaStreamSynchronize(h->stream));
+  h->d2h += 32;
+  float ms = 0.f;
+  FM_TRY(h, cudaEventElapsedTime(&ms, h->ev_beg, h->ev_end));
+  h->last_iter_ms = ms;
+  if (loss_out) *loss_out = (h->h_scal[2] + h->h_scal[3]) * 0.05;  // scal[2] already holds the GLOBAL sum e^2
   return CARS_OK;
 }
 
@@ -340,6 +414,8 @@ extern "C" int cars_fm_get_stats(const cars_fm_handle* h, cars_fm_stats* out) {
   out->pieces = h->fld[0].f.num_pieces + h->fld[1].f.num_pieces + h->fld[2].f.num_pieces;
   return CARS_OK;
 }
+
+extern "C" void* cars_fm_get_stream(const cars_fm_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 extern "C" const char* cars_fm_last_error(const cars_fm_handle* h) { return h ? h->err.c_str() : g_fm_create_error.c_str(); }
 

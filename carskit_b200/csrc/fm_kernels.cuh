@@ -201,6 +201,55 @@ __global__ void __launch_bounds__(256) fm_coord_kernel(FmField fld, const double
   delta[l] = __dsub_rn(nv, old);
 }
 
+// Sharded variant of (b), split around the caller's all-reduce (rows of a coordinate live on several GPUs):
+// (b1) per-coordinate LOCAL sums -> buf[l] = num, buf[ncoord + l] = den part (MODE 0: local row count * x^2)
+template <int MODE>
+__global__ void __launch_bounds__(256) fm_coord_partial_kernel(FmField fld, const double* __restrict__ part,
+                                                               double* __restrict__ buf /*[2 x ncoord]*/) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= fld.ncoord) return;
+  double num = 0.0, den = 0.0;
+  for (int64_t q = fld.coord_piece[l]; q < fld.coord_piece[l + 1]; q++) {
+    num = __dadd_rn(num, part[q]);
+    if (MODE == 1) den = __dadd_rn(den, part[fld.num_pieces + q]);
+  }
+  if (MODE == 0) den = __dmul_rn((double)fld.coord_rows[l], __dmul_rn(fld.x, fld.x));
+  buf[l] = num;
+  buf[fld.ncoord + l] = den;
+}
+// (b2) after the all-reduce: every rank computes the same new value from the same global sums
+__global__ void __launch_bounds__(256) fm_coord_finish_kernel(FmField fld, const double* __restrict__ buf, double size_reg,
+                                                              double* __restrict__ coef, int coef_stride, int coef_col,
+                                                              double* __restrict__ delta) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= fld.ncoord) return;
+  const double den = __dadd_rn(buf[fld.ncoord + l], size_reg);
+  double* cp = coef + (int64_t)(fld.offset + l) * coef_stride + coef_col;
+  const double old = *cp;
+  const double nv = __dsub_rn(0.0, buf[l] / den);
+  *cp = nv;
+  delta[l] = __dsub_rn(nv, old);
+}
+// w0 step, sharded: the two local sums -> buf[0..1]; finish from the global sums
+__global__ void fm_w0_partial_kernel(const double* __restrict__ part, int nblocks, double* __restrict__ buf) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double ta = 0.0, tb = 0.0;
+  for (int i = 0; i < nblocks; i++) { ta += part[i]; tb += part[nblocks + i]; }
+  buf[0] = ta;
+  buf[1] = tb;
+}
+__global__ void fm_w0_finish_global_kernel(const double* __restrict__ buf, double denom, double reg_lw,
+                                           double* __restrict__ w0p, double* __restrict__ scal) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double w0 = *w0p;
+  double up = buf[0] / denom;
+  up = 0.0 - up;
+  scal[0] = up;
+  scal[1] = w0;
+  scal[2] = buf[1] + (reg_lw * w0) * w0;
+  *w0p = up;
+}
+
 // (c) row-parallel: e_n += (new - old) x ; V step also Qc[n][f] += (new - old) x  (:184-185, :208-211)
 template <int MODE>
 __global__ void __launch_bounds__(256) fm_row_update_kernel(FmField fld, const double* __restrict__ delta, int64_t N,

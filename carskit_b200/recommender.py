@@ -373,6 +373,7 @@ class FM(IterativeRecommender):
             int(ts.ctx_ptr[1] - ts.ctx_ptr[0]) if ts.ctx_ptr is not None and len(ts.ctx_ptr) > 1 else 1)
         self.p = self.numUsers + self.numItems + self.numConditions
         self.k = self.numFactors
+        self.globalSize = 0
 
     def initModel(self, init=None, seed: int = 0):
         """FM.initModel (FM.java:57-74): w0 = 0, w ~ U(0,1) (DenseVector.init()), V ~ N(0, 0.1)."""
@@ -389,18 +390,34 @@ class FM(IterativeRecommender):
 
     def _desc(self):
         return capi.make_desc(self.trainMatrix, capi.FM, self.k, device=self.device, reg_lw=self.regLw,
-                              reg_lf=self.regLf, num_context_dims=self.numContextDims, stream=self.stream)
+                              reg_lf=self.regLf, num_context_dims=self.numContextDims, stream=self.stream,
+                              global_nnz=self.globalSize)
 
     def _new_engine(self):
+        if self.world > 1:  # the coordinate-sum all-reduces must be stream-ordered with the kernels
+            import torch
+            if self.stream:
+                self._torch_stream = torch.cuda.ExternalStream(self.stream, device=self.device)
+            else:
+                self._torch_stream = torch.cuda.Stream(device=self.device)
+                self.stream = self._torch_stream.cuda_stream
         return capi.FmEngine(self._desc(), keepalive=self.trainMatrix)
 
     def open_engine(self):
+        """world > 1: trainMatrix holds THIS rank's contiguous range of rows (sharding.shard_rows); w0, w and V
+        are replicated; `size` in FM.java's denominators is the global row count."""
         if not self.model:
             raise RuntimeError("buildModel before initModel")
+        self.globalSize = 0
+        if self.world > 1:
+            self.globalSize = int(self._allreduce_sum([float(self.trainMatrix.nnz)])[0])
         eng = self._new_engine()
         try:
             eng.upload(self.model)
             eng.prepare()  # FM.java:118-146
+            if self.world > 1:
+                from .sharding import CoordinateSumExchange
+                self.exchange = CoordinateSumExchange(eng, self._exchange_device(), self.group, self._torch_stream)
         except Exception:
             eng.close()
             raise
@@ -408,7 +425,7 @@ class FM(IterativeRecommender):
         return eng
 
     def train_epoch(self, iter: int) -> bool:
-        self.loss = self.engine.iteration()
+        self.loss = self.exchange.iteration(self.engine) if self.world > 1 else self.engine.iteration()
         self.iter_losses.append(self.loss)
         return False  # FM.java never calls isConverged()
 

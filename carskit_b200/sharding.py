@@ -58,6 +58,47 @@ def shard_user_rows(arr: np.ndarray, lo: int, hi: int) -> np.ndarray:
     return np.ascontiguousarray(arr[lo:hi])
 
 
+def row_range(nnz: int, rank: int, world: int) -> Tuple[int, int]:
+    """FM shards ROWS (ratings) by contiguous range of the reference order."""
+    return user_range(nnz, rank, world)
+
+
+def shard_rows(ts: TrainingSet, rank: int, world: int) -> TrainingSet:
+    lo, hi = row_range(ts.nnz, rank, world)
+    return TrainingSet(num_users=ts.num_users, num_items=ts.num_items, u=ts.u[lo:hi], j=ts.j[lo:hi], r=ts.r[lo:hi],
+                       ctx=None if ts.ctx is None else ts.ctx[lo:hi], num_conditions=ts.num_conditions,
+                       num_contexts=ts.num_contexts, ctx_ptr=ts.ctx_ptr, ctx_cond=ts.ctx_cond,
+                       global_mean=ts.global_mean)
+
+
+class CoordinateSumExchange:
+    """FM: the all-reduce of the per-coordinate (numerator, denominator) sums between the row shards.  The engine
+    calls back 3 * (1 + k) + 1 times per ALS iteration with a slice of the device buffer owned here."""
+
+    def __init__(self, engine, device, group=None, torch_stream=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group, self.torch_stream = torch, dist, group, torch_stream
+        self.buf = torch.zeros(engine.exchange_doubles(), dtype=torch.float64, device=device)
+        self.base = self.buf.data_ptr()
+        self.calls = 0
+        self.bytes = 0
+
+    def allreduce(self, dev_ptr: int, count: int):
+        off = (dev_ptr - self.base) // 8
+        view = self.buf[off:off + count]
+        if self.torch_stream is not None:
+            with self.torch.cuda.stream(self.torch_stream):
+                self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.calls += 1
+        self.bytes += count * 8
+
+    def iteration(self, engine) -> float:
+        return engine.iteration_sharded(self.base, self.allreduce)
+
+
 class ItemBlockExchange:
     """Per-epoch exchange of the item block.  `device` is a torch device; the delta buffer lives there
     (CUDA for the engine; CPU tensors + gloo exercise the same orchestration in the CPU tests)."""

@@ -106,6 +106,7 @@ typedef struct cars_desc {
   double reg_u, reg_i, reg_b, reg_c, reg_lw, reg_lf;
   int32_t num_context_dims; /* rateDao.numContextDims() (FM.java:86); FM only */
   int32_t reserved1;
+  int64_t global_nnz;       /* FM row sharding: rows over all ranks; 0 = nnz (single GPU) */
   void*   stream;          /* cudaStream_t to launch on; NULL = the handle creates its own */
 } cars_desc;
 
@@ -237,7 +238,19 @@ int cars_fm_iteration(cars_fm_handle* h, double* loss_out);
 int cars_fm_download(cars_fm_handle* h, const cars_fm_arrays* host);
 int cars_fm_predict(cars_fm_handle* h, int64_t n, const int32_t* u, const int32_t* j, const int32_t* ctx,
                     int32_t bound, double min_rate, double max_rate, double* out);
+/* Multi-GPU FM: rows sharded by contiguous range (one handle per GPU over its rows; w0, w, V replicated).
+ * desc->global_nnz = number of rows over ALL ranks (the `size` of FM.java's denominators); 0 = nnz.
+ * Every coordinate step needs the sums over all rows: the engine writes its local per-coordinate sums into
+ * `dev_buf` (caller-owned DEVICE memory, >= cars_fm_exchange_doubles() doubles) and calls `allreduce`, which
+ * must sum dev_buf[0 .. count) over the ranks in place, ordered on the handle's stream (e.g.
+ * torch.distributed.all_reduce under that stream).  3 * (1 + k) + 1 calls per iteration.  All ranks then
+ * compute identical new coordinates.  loss_out is the GLOBAL loss. */
+typedef int (*cars_allreduce_fn)(void* user, double* dev_ptr, int64_t count);
+int cars_fm_exchange_doubles(const cars_fm_handle* h, int64_t* out);
+int cars_fm_iteration_sharded(cars_fm_handle* h, double* dev_buf, cars_allreduce_fn allreduce, void* user,
+                              double* loss_out);
 int cars_fm_get_stats(const cars_fm_handle* h, cars_fm_stats* out);
+void* cars_fm_get_stream(const cars_fm_handle* h);
 const char* cars_fm_last_error(const cars_fm_handle* h);
 void cars_fm_destroy(cars_fm_handle* h);
 
