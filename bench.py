@@ -361,19 +361,22 @@ def run_fm(args, wl, wl_name, rank, world, local_rank):
     """FM (ALS) line: rating-iterations/s of cars_fm_iteration, single GPU.  Same JSON contract; the unit of
     work is one rating x one ALS iteration (88 + 144 k algorithmic bytes)."""
     import torch
+    import torch.distributed as dist
     from carskit_b200 import capi, recommender, synth
-    if world > 1:
-        raise SystemExit("bench.py: the FM path is single-GPU in this round (DESIGN.md section 7)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; carskit_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
-    ts, _ = synth.make_training_set(wl["users"], wl["items"], wl["dims"], wl["nnz"], seed=wl["seed"], order="user_sorted")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # weak scaling: every rank holds its own range of rows over the SAME users / items / contexts
+    ts, _ = synth.make_training_set(wl["users"], wl["items"], wl["dims"], wl["nnz"], seed=wl["seed"] + rank,
+                                    order="user_sorted")
     k, D = wl["F"], len(wl["dims"])
     p = ts.num_users + ts.num_items + ts.num_conditions
     rng = np.random.default_rng(wl["seed"] + 7919)
     init = {"w0": np.zeros(1), "w": rng.random(p), "V": 0.1 * rng.standard_normal((p, k))}
     conf = {"num.factors": str(k), "num.max.iter": str(args.steps), "FM": "-lw 0.01 -lf 0.02"}
-    rec = recommender.FM(ts, None, conf=conf, device=local_rank)
+    rec = recommender.FM(ts, None, conf=conf, device=local_rank, world=world)
     rec.initModel(init={n: v.copy() for n, v in init.items()})
     eng = rec.open_engine()
     for it in range(args.warmup):
@@ -393,16 +396,31 @@ def run_fm(args, wl, wl_name, rank, world, local_rank):
     launches = eng.stats().kernel_launches - l0
     rec.close_engine()
     ms = float(np.sum(kms))  # device time (CUDA events inside the library, on its stream)
-    value = ts.nnz * args.steps / (ms * 1e-3)
-    rec2 = recommender.FM(ts, None, conf=conf, device=local_rank)
+    nnz_total = ts.nnz
+    if world > 1:
+        t = torch.tensor([ms, float(ts.nnz)], dtype=torch.float64, device="cuda")
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, nnz_total = float(tm[0]), int(t[1])
+    value = nnz_total * args.steps / (ms * 1e-3)
+    rec2 = recommender.FM(ts, None, conf=conf, device=local_rank, world=world)
     rec2.initModel(init=init)
     t0 = time.perf_counter()
     rec2.buildModel()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     st2 = rec2.stats
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         from oracle import oracle_py as orc
         orc.build()
         n = min(ts.nnz, 400_000)
@@ -423,14 +441,15 @@ def run_fm(args, wl, wl_name, rank, world, local_rank):
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
     achieved = B * ts.nnz / (float(np.mean(kms)) * 1e-3) / 1e9
     out = {
-        "metric": "fm_als_rating_iterations_per_sec", "value": value, "unit": "rating-iterations/s", "n_gpus": 1,
+        "metric": "fm_als_rating_iterations_per_sec", "value": value, "unit": "rating-iterations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl_name, "model": "fm", "factors": k, "users": wl["users"], "items": wl["items"],
-                   "conditions": int(sum(wl["dims"])), "context_dims": D, "nnz": ts.nnz,
+                   "conditions": int(sum(wl["dims"])), "context_dims": D, "nnz_per_gpu": ts.nnz, "nnz_total": nnz_total,
+                   "parallelism": f"row shards x{world}, {3 * (1 + k) + 1} all-reduces of per-coordinate sums per iteration" if world > 1 else "1 gpu",
                    "l2": "inputs larger than L2 (Qc alone is nnz*k*8 bytes); no flush", "wall_ms_per_step": wall * 1e3 / args.steps},
         "clocks": clocks,
-        "e2e": {"value": ts.nnz * args.steps / e2e_s, "unit": "rating-iterations/s",
+        "e2e": {"value": nnz_total * args.steps / e2e_s, "unit": "rating-iterations/s",
                 "h2d_bytes_per_step": int(st2.h2d_bytes / args.steps), "d2h_bytes_per_step": int(st2.d2h_bytes / args.steps),
                 "seconds": e2e_s},
         "gpu_launches": int(launches),
