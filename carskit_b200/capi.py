@@ -61,7 +61,7 @@ EXPORTS = [
     "cars_get_stream", "cars_version", "cars_item_block_doubles", "cars_epoch_sharded_begin",
     "cars_epoch_sharded_finish", "cars_fm_create", "cars_fm_upload", "cars_fm_prepare", "cars_fm_iteration",
     "cars_fm_download", "cars_fm_predict", "cars_fm_get_stats", "cars_fm_last_error", "cars_fm_destroy",
-    "cars_fm_exchange_doubles", "cars_fm_iteration_sharded", "cars_fm_get_stream",
+    "cars_fm_exchange_doubles", "cars_fm_iteration_sharded", "cars_fm_get_stream", "cars_rank_topn",
 ]
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
@@ -120,6 +120,9 @@ def load_library(path: Optional[str] = None):
     lib.cars_get_stats.restype = C.c_int
     lib.cars_get_stream.argtypes = [H]
     lib.cars_get_stream.restype = C.c_void_p
+    lib.cars_rank_topn.argtypes = [H, C.c_int64, _i32p, _i32p, C.c_int32, _i32p, C.POINTER(C.c_int64), _i32p, C.c_double,
+                                   C.c_int32, _i32p, _f64p, _i32p, _i32p]
+    lib.cars_rank_topn.restype = C.c_int
     lib.cars_item_block_doubles.argtypes = [H, C.POINTER(C.c_int64)]
     lib.cars_item_block_doubles.restype = C.c_int
     lib.cars_epoch_sharded_begin.argtypes = [H, C.c_double, C.c_void_p]
@@ -318,6 +321,25 @@ class Engine:
         self._check(self.lib.cars_predict(self.h, u.shape[0], _ptr_i32(u), _ptr_i32(j), _ptr_i32(ctx),
                                           1 if bound else 0, min_rate, max_rate, _ptr_f64(out)))
         return out
+
+    def rank_topn(self, qu, qc, cand, rated_ptr=None, rated_items=None, bin_thold: float = -1.0, num_recs: int = 10):
+        """evalRankings' scoring + top-N cut for a batch of (user, context) queries; see cars_rank_topn.
+        Returns (items [nq x num_recs], scores, count, kept)."""
+        qu = np.ascontiguousarray(qu, dtype=np.int32)
+        qc = None if qc is None else np.ascontiguousarray(qc, dtype=np.int32)
+        cand = np.ascontiguousarray(cand, dtype=np.int32)
+        nq = qu.shape[0]
+        items = np.full((nq, num_recs), -1, dtype=np.int32)
+        scores = np.zeros((nq, num_recs), dtype=np.float64)
+        count = np.zeros(nq, dtype=np.int32)
+        kept = np.zeros(nq, dtype=np.int32)
+        rp = None if rated_ptr is None else np.ascontiguousarray(rated_ptr, dtype=np.int64)
+        ri = None if rated_items is None else np.ascontiguousarray(rated_items, dtype=np.int32)
+        self._check(self.lib.cars_rank_topn(
+            self.h, nq, _ptr_i32(qu), _ptr_i32(qc), cand.shape[0], _ptr_i32(cand),
+            None if rp is None else rp.ctypes.data_as(C.POINTER(C.c_int64)), _ptr_i32(ri), bin_thold, num_recs,
+            _ptr_i32(items), _ptr_f64(scores), _ptr_i32(count), _ptr_i32(kept)))
+        return items, scores, count, kept
 
     def eval_ratings(self, u, j, ctx, r, min_rate, max_rate):
         u = np.ascontiguousarray(u, dtype=np.int32)

@@ -7,6 +7,7 @@
 #include "schedule.cuh"
 #include "schedule_gpu.cuh"
 #include "sgd_kernels.cuh"
+#include "rank_kernels.cuh"
 
 #include <cuda_runtime.h>
 
@@ -918,6 +919,134 @@ extern "C" int cars_eval_ratings(cars_handle* h, int64_t n, const int32_t* u, co
   }
   *sum_abs_err = sa;
   *sum_sq_err = ss;
+  return CARS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// evalRankings scoring + top-N (K6)
+// ------------------------------------------------------------------------------------------------
+template <int MODEL>
+static cudaError_t launch_rank_score(cars_handle* h, int64_t q0, int64_t nq, const int32_t* qu, const int32_t* qc,
+                                     int32_t num_cand, const int32_t* cand, double thold, unsigned long long* keys) {
+  const int FC = h->m.F < kRankFC ? h->m.F : kRankFC;
+  const size_t smem = (size_t)(kRankTQ + kRankTJ) * (FC + 1) * 8;
+  cudaError_t e = cudaFuncSetAttribute(rank_score_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)((num_cand + kRankTJ - 1) / kRankTJ), (unsigned)((nq + kRankTQ - 1) / kRankTQ));
+  rank_score_kernel<MODEL><<<grid, 256, smem, h->stream>>>(h->m, q0, nq, qu, qc, num_cand, cand, thold, keys);
+  return cudaGetLastError();
+}
+
+extern "C" int cars_rank_topn(cars_handle* h, int64_t num_queries, const int32_t* qu, const int32_t* qc, int32_t num_cand,
+                              const int32_t* cand, const int64_t* rated_ptr, const int32_t* rated_items, double bin_thold,
+                              int32_t num_recs, int32_t* out_items, double* out_scores, int32_t* out_count,
+                              int32_t* out_kept) {
+  if (!h) return CARS_E_INVALID;
+  if (!h->uploaded) return fail(h, CARS_E_STATE, "cars_rank_topn before cars_upload");
+  if (h->epoch_pending) return fail(h, CARS_E_STATE, "an epoch is pending; call cars_epoch_wait first");
+  const bool has_ctx = model_has_ctx(h->d.model);
+  if (num_queries < 0 || num_cand < 0 || num_recs <= 0 || num_recs > 4096)
+    return fail(h, CARS_E_INVALID, "bad sizes (num_recs must be in 1..4096)");
+  if (num_queries > 0 && (!qu || (has_ctx && !qc) || !out_items || !out_scores || !out_count || !out_kept))
+    return fail(h, CARS_E_INVALID, "NULL argument");
+  if (num_cand > 0 && !cand) return fail(h, CARS_E_INVALID, "cand is NULL");
+  if (num_queries == 0) return CARS_OK;
+  const int32_t I = h->d.num_items;
+  for (int64_t q = 0; q < num_queries; q++)
+    if ((unsigned)qu[q] >= (unsigned)h->d.num_users || (has_ctx && (unsigned)qc[q] >= (unsigned)h->d.num_contexts))
+      return fail(h, CARS_E_INVALID, "query %lld has an id out of range", (long long)q);
+  std::vector<int32_t> cidx;
+  try { cidx.assign((size_t)I, -1); } catch (...) { return fail(h, CARS_E_OOM, "host allocation failed"); }
+  for (int32_t c = 0; c < num_cand; c++) {
+    if ((unsigned)cand[c] >= (unsigned)I) return fail(h, CARS_E_INVALID, "candidate %d is not an item id", c);
+    if (cidx[cand[c]] >= 0) return fail(h, CARS_E_INVALID, "candidate item %d listed twice", cand[c]);
+    cidx[cand[c]] = c;
+  }
+  const int64_t nrated = rated_ptr ? rated_ptr[num_queries] : 0;
+  if (rated_ptr) {
+    if (nrated > 0 && !rated_items) return fail(h, CARS_E_INVALID, "rated_items is NULL");
+    for (int64_t i = 0; i < nrated; i++)
+      if ((unsigned)rated_items[i] >= (unsigned)I) return fail(h, CARS_E_INVALID, "rated item %lld out of range", (long long)i);
+  }
+  for (int64_t q = 0; q < num_queries; q++) { out_count[q] = 0; out_kept[q] = 0; }
+  if (num_cand == 0) return CARS_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+
+  int32_t *d_qu = nullptr, *d_qc = nullptr, *d_cand = nullptr, *d_cidx = nullptr, *d_rated = nullptr, *d_items = nullptr,
+          *d_count = nullptr, *d_kept = nullptr;
+  int64_t* d_rptr = nullptr;
+  double* d_scores = nullptr;
+  unsigned long long* d_keys = nullptr;
+  // queries per pass: the key matrix [chunk x num_cand] is kept under ~1 GiB
+  int64_t chunk = (int64_t)((1ull << 30) / ((uint64_t)num_cand * 8));
+  if (chunk < kRankTQ) chunk = kRankTQ;
+  if (chunk > num_queries) chunk = num_queries;
+  if (chunk > 65535ll * kRankTQ) chunk = 65535ll * kRankTQ;
+  int rc = CARS_OK;
+  cudaError_t e = cudaSuccess;
+#define RK(x) do { if (e == cudaSuccess) e = (x); } while (0)
+  RK(dev_alloc(&d_qu, (size_t)num_queries));
+  if (has_ctx) RK(dev_alloc(&d_qc, (size_t)num_queries));
+  RK(dev_alloc(&d_cand, (size_t)num_cand));
+  RK(dev_alloc(&d_cidx, (size_t)I));
+  RK(dev_alloc(&d_items, (size_t)num_queries * num_recs));
+  RK(dev_alloc(&d_scores, (size_t)num_queries * num_recs));
+  RK(dev_alloc(&d_count, (size_t)num_queries));
+  RK(dev_alloc(&d_kept, (size_t)num_queries));
+  RK(dev_alloc(&d_keys, (size_t)chunk * num_cand));
+  if (rated_ptr) {
+    RK(dev_alloc(&d_rptr, (size_t)num_queries + 1));
+    RK(dev_alloc(&d_rated, (size_t)nrated));
+  }
+  RK(cudaMemcpyAsync(d_qu, qu, num_queries * 4, cudaMemcpyHostToDevice, h->stream));
+  if (has_ctx) RK(cudaMemcpyAsync(d_qc, qc, num_queries * 4, cudaMemcpyHostToDevice, h->stream));
+  RK(cudaMemcpyAsync(d_cand, cand, (size_t)num_cand * 4, cudaMemcpyHostToDevice, h->stream));
+  RK(cudaMemcpyAsync(d_cidx, cidx.data(), (size_t)I * 4, cudaMemcpyHostToDevice, h->stream));
+  RK(cudaMemsetAsync(d_count, 0, (size_t)num_queries * 4, h->stream));
+  RK(cudaMemsetAsync(d_kept, 0, (size_t)num_queries * 4, h->stream));
+  RK(cudaMemsetAsync(d_items, 0xff, (size_t)num_queries * num_recs * 4, h->stream));
+  RK(cudaMemsetAsync(d_scores, 0, (size_t)num_queries * num_recs * 8, h->stream));
+  if (rated_ptr) {
+    RK(cudaMemcpyAsync(d_rptr, rated_ptr, ((size_t)num_queries + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    if (nrated) RK(cudaMemcpyAsync(d_rated, rated_items, (size_t)nrated * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  h->st.h2d_bytes += num_queries * (has_ctx ? 8 : 4) + (int64_t)num_cand * 4 + (int64_t)I * 4 + nrated * 4;
+  for (int64_t q0 = 0; q0 < num_queries && e == cudaSuccess; q0 += chunk) {
+    const int64_t nq = num_queries - q0 < chunk ? num_queries - q0 : chunk;
+    switch (h->d.model) {
+      case CARS_PMF: RK(launch_rank_score<M_PMF>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
+      case CARS_BIASEDMF: RK(launch_rank_score<M_BIASEDMF>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
+      case CARS_CAMF_C: RK(launch_rank_score<M_CAMF_C>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
+      case CARS_CAMF_CI: RK(launch_rank_score<M_CAMF_CI>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
+      case CARS_CAMF_CU: RK(launch_rank_score<M_CAMF_CU>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
+      default: rc = fail(h, CARS_E_UNSUPPORTED, "rank: model %d", h->d.model); break;
+    }
+    if (rc) break;
+    if (rated_ptr && e == cudaSuccess) {
+      rank_drop_rated_kernel<<<(unsigned)nq, 256, 0, h->stream>>>(q0, nq, d_rptr, d_rated, d_cidx, num_cand, d_keys);
+      RK(cudaGetLastError());
+      h->st.kernel_launches += 1;
+    }
+    if (e == cudaSuccess) {
+      rank_select_kernel<<<(unsigned)nq, 256, 0, h->stream>>>(q0, nq, num_cand, d_cand, num_recs, d_keys, d_items, d_scores,
+                                                             d_count, d_kept);
+      RK(cudaGetLastError());
+      h->st.kernel_launches += 2;
+    }
+  }
+  RK(cudaMemcpyAsync(out_items, d_items, (size_t)num_queries * num_recs * 4, cudaMemcpyDeviceToHost, h->stream));
+  RK(cudaMemcpyAsync(out_scores, d_scores, (size_t)num_queries * num_recs * 8, cudaMemcpyDeviceToHost, h->stream));
+  RK(cudaMemcpyAsync(out_count, d_count, (size_t)num_queries * 4, cudaMemcpyDeviceToHost, h->stream));
+  RK(cudaMemcpyAsync(out_kept, d_kept, (size_t)num_queries * 4, cudaMemcpyDeviceToHost, h->stream));
+  cudaError_t es = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = es;
+#undef RK
+  h->st.d2h_bytes += num_queries * ((int64_t)num_recs * 12 + 8);
+  cudaFree(d_qu); cudaFree(d_qc); cudaFree(d_cand); cudaFree(d_cidx); cudaFree(d_rated); cudaFree(d_items);
+  cudaFree(d_count); cudaFree(d_kept); cudaFree(d_rptr); cudaFree(d_scores); cudaFree(d_keys);
+  if (rc) return rc;
+  if (e != cudaSuccess)
+    return fail(h, e == cudaErrorMemoryAllocation ? CARS_E_OOM : CARS_E_CUDA, "cars_rank_topn failed: %s", cudaGetErrorString(e));
   return CARS_OK;
 }
 

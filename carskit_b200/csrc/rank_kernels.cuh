@@ -1,0 +1,157 @@
+// rank_kernels.cuh -- K6: the scoring loop and top-N selection of Recommender.evalRankings()
+// (src/carskit/generic/Recommender.java:797-824): for one (user, context) query, every candidate item that the
+// user has not rated in that context is scored with ranking(u, j, c) = predict(u, j, c), kept if
+// score > binThold, sorted by descending score (Lists.sortList: a STABLE sort, ties keep the candidates'
+// iteration order) and cut to numRecs.
+//
+// Scores are bit-identical to Java's: the dot product is accumulated in f = 0..F-1 order with separately
+// rounded multiply and add, exactly like predict_kernel -- which is why this is an fp64 SIMT contraction and
+// not a tensor-core GEMM: DMMA accumulates with fused multiply-adds in a different order (and tcgen05 has no
+// fp64 kind), and the north star asks for bit-exact top-N indices.  The P x Q^T structure is still exploited:
+// a CTA stages a tile of 16 query rows and 64 candidate rows in shared memory and every thread keeps four
+// independent accumulation chains in flight.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sgd_kernels.cuh"
+
+namespace cars {
+
+constexpr int kRankTQ = 16;  // queries per tile
+constexpr int kRankTJ = 64;  // candidates per tile
+constexpr int kRankFC = 128; // factors staged in shared memory per pass
+
+// Double.compareTo order as an unsigned key (larger key = larger double; -0.0 < +0.0; NaN never gets here)
+__device__ __forceinline__ unsigned long long sortable_key(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+// "not a candidate for this query": below every real key
+constexpr unsigned long long kRankDropped = 0ull;
+
+// scores[q][c] = sortable key of predict(u_q, cand_c, ctx_q) if it is a number > bin_thold, else kRankDropped
+template <int MODEL>
+__global__ void __launch_bounds__(256) rank_score_kernel(DeviceModel m, int64_t q0, int64_t nq, const int32_t* __restrict__ qu,
+                                                         const int32_t* __restrict__ qc, int32_t num_cand,
+                                                         const int32_t* __restrict__ cand, double bin_thold,
+                                                         unsigned long long* __restrict__ keys /*[nq x num_cand]*/) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int F = m.F;
+  const int FC = F < kRankFC ? F : kRankFC;  // factors staged per pass; the chains simply continue across passes
+  const int ld = FC + 1;                     // padded row stride: 16 rows read at the same f hit 16 different banks
+  double* Ps = reinterpret_cast<double*>(smem_raw);
+  double* Qs = Ps + kRankTQ * ld;
+  const int64_t qt = (int64_t)blockIdx.y * kRankTQ;
+  const int ct = blockIdx.x * kRankTJ;
+  const int tq = threadIdx.x / 16, tj = threadIdx.x % 16;
+  const double* p = Ps + tq * ld;
+  const double* qa = Qs + (tj)*ld;
+  const double* qb = Qs + (tj + 16) * ld;
+  const double* qcc = Qs + (tj + 32) * ld;
+  const double* qd = Qs + (tj + 48) * ld;
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+  for (int f0 = 0; f0 < F; f0 += FC) {
+    const int fl = F - f0 < FC ? F - f0 : FC;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kRankTQ * fl; i += 256) {
+      const int r = i / fl, f = i % fl;
+      const int64_t q = qt + r;
+      Ps[r * ld + f] = q < nq ? m.P[(int64_t)qu[q0 + q] * m.Fp + f0 + f] : 0.0;
+    }
+    for (int i = threadIdx.x; i < kRankTJ * fl; i += 256) {
+      const int r = i / fl, f = i % fl;
+      const int c = ct + r;
+      Qs[r * ld + f] = c < num_cand ? m.Q[(int64_t)cand[c] * m.Fp + f0 + f] : 0.0;
+    }
+    __syncthreads();
+    for (int f = 0; f < fl; f++) {  // DenseMatrix.rowMult order, four independent chains
+      const double pf = p[f];
+      d0 = __dadd_rn(d0, __dmul_rn(pf, qa[f]));
+      d1 = __dadd_rn(d1, __dmul_rn(pf, qb[f]));
+      d2 = __dadd_rn(d2, __dmul_rn(pf, qcc[f]));
+      d3 = __dadd_rn(d3, __dmul_rn(pf, qd[f]));
+    }
+  }
+  const int64_t q = qt + tq;
+  if (q >= nq) return;
+  const int u = qu[q0 + q], ctx = qc ? qc[q0 + q] : 0;
+  const double dots[4] = {d0, d1, d2, d3};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int c = ct + tj + 16 * i;
+    if (c >= num_cand) continue;
+    const double s = predict_from_dot<MODEL>(m, u, cand[c], ctx, dots[i]);
+    keys[q * num_cand + c] = (s == s && s > bin_thold) ? sortable_key(s) : kRankDropped;  // !isNaN && rank > binThold
+  }
+}
+
+// items the user rated in this context in the TRAINING set leave the candidate list (Recommender.java:792,800)
+__global__ void __launch_bounds__(256) rank_drop_rated_kernel(int64_t q0, int64_t nq, const int64_t* __restrict__ rated_ptr,
+                                                              const int32_t* __restrict__ rated_items,
+                                                              const int32_t* __restrict__ cand_index_of_item,
+                                                              int32_t num_cand, unsigned long long* __restrict__ keys) {
+  const int64_t q = blockIdx.x;
+  if (q >= nq) return;
+  for (int64_t i = rated_ptr[q0 + q] + threadIdx.x; i < rated_ptr[q0 + q + 1]; i += 256) {
+    const int c = cand_index_of_item[rated_items[i]];
+    if (c >= 0) keys[q * num_cand + c] = kRankDropped;
+  }
+}
+
+// one CTA per query: num_recs rounds of "largest key, lowest candidate index on ties" == the first num_recs
+// entries of the reference's stable descending sort
+__global__ void __launch_bounds__(256) rank_select_kernel(int64_t q0, int64_t nq, int32_t num_cand, const int32_t* __restrict__ cand,
+                                                          int32_t num_recs, unsigned long long* __restrict__ keys,
+                                                          int32_t* __restrict__ out_items, double* __restrict__ out_scores,
+                                                          int32_t* __restrict__ out_count, int32_t* __restrict__ out_kept) {
+  __shared__ unsigned long long sk[8];
+  __shared__ int si[8];
+  __shared__ int skept[8];
+  const int64_t q = blockIdx.x;
+  if (q >= nq) return;
+  unsigned long long* row = keys + q * num_cand;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int count = 0;
+  for (int round = 0; round < num_recs; round++) {
+    unsigned long long best = kRankDropped;
+    int bi = 0x7fffffff, kept = 0;
+    for (int c = threadIdx.x; c < num_cand; c += 256) {
+      const unsigned long long k = row[c];
+      if (k != kRankDropped) kept++;
+      if (k > best) { best = k; bi = c; }  // strided scan visits a thread's candidates in ascending order
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ok = __shfl_down_sync(0xffffffffu, best, o);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+      if (ok > best || (ok == best && oi < bi)) { best = ok; bi = oi; }
+      kept += __shfl_down_sync(0xffffffffu, kept, o);
+    }
+    if (lane == 0) { sk[warp] = best; si[warp] = bi; skept[warp] = kept; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int kt = 0;
+      for (int w = 0; w < 8; w++) {
+        kt += skept[w];
+        if (sk[w] > best || (sk[w] == best && si[w] < bi)) { best = sk[w]; bi = si[w]; }
+      }
+      sk[0] = best; si[0] = bi; skept[0] = kt;
+    }
+    __syncthreads();
+    best = sk[0]; bi = si[0];
+    if (round == 0 && threadIdx.x == 0) out_kept[q0 + q] = skept[0];  // itemScores.size()
+    if (best == kRankDropped) break;                                 // fewer than num_recs survivors
+    if (threadIdx.x == 0) {
+      out_items[(q0 + q) * num_recs + round] = cand[bi];
+      const unsigned long long b = (best & 0x8000000000000000ull) ? (best & 0x7fffffffffffffffull) : ~best;
+      out_scores[(q0 + q) * num_recs + round] = __longlong_as_double((long long)b);
+      row[bi] = kRankDropped;
+    }
+    count++;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out_count[q0 + q] = count;
+}
+
+}  // namespace cars

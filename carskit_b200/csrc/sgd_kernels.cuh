@@ -691,11 +691,20 @@ __global__ void loss_finalize_kernel(const double* block_partial, int n, double*
 // value is bit-identical to Java's (Recommender.java:306-317 + the model's predict()).
 // ------------------------------------------------------------------------------------------------
 template <int MODEL>
+__device__ __forceinline__ double predict_from_dot(const DeviceModel& m, int u, int j, int ctx, double dot);
+
+template <int MODEL>
 __device__ __forceinline__ double predict_one(const DeviceModel& m, int u, int j, int ctx) {
   const double* p = m.P + (int64_t)u * m.Fp;
   const double* q = m.Q + (int64_t)j * m.Fp;
   double dot = 0.0;
   for (int f = 0; f < m.F; f++) dot = __dadd_rn(dot, __dmul_rn(p[f], q[f]));
+  return predict_from_dot<MODEL>(m, u, j, ctx, dot);
+}
+
+// everything of the model's predict(u, j, c) after DenseMatrix.rowMult, in the reference's order of additions
+template <int MODEL>
+__device__ __forceinline__ double predict_from_dot(const DeviceModel& m, int u, int j, int ctx, double dot) {
   double pred;
   if (MODEL == M_PMF) pred = dot;
   if (MODEL == M_BIASEDMF || MODEL == M_CAMF_C)

@@ -65,6 +65,31 @@ class LineConfiger:
         return v[0] if v else default
 
 
+def java_hashset_order(ids_in_insertion_order) -> np.ndarray:
+    """Iteration order of a java.util.HashSet<Integer> filled by add() in the given order (JDK 8 HashMap: table
+    of 16 doubling while size > 0.75 * capacity, bucket = (h ^ (h >>> 16)) & (capacity - 1) with h = the int
+    itself, buckets walked in index order, entries of one bucket in insertion order -- resizes preserve that).
+    evalRankings() iterates candItems = rateDao.getItemList(trainMatrix) in this order (Recommender.java:704,
+    DataDAO.java:1210-1218), and ties of the stable sort keep it, so it is part of the ranking contract."""
+    seen, uniq = set(), []
+    for v in ids_in_insertion_order:
+        v = int(v)
+        if v not in seen:
+            seen.add(v)
+            uniq.append(v)
+    cap = 16
+    while len(uniq) > 0.75 * cap:
+        cap *= 2
+    buckets: Dict[int, list] = {}
+    for v in uniq:
+        h = v & 0xFFFFFFFF
+        buckets.setdefault((h ^ (h >> 16)) & (cap - 1), []).append(v)
+    out = []
+    for b in sorted(buckets):
+        out.extend(buckets[b])
+    return np.asarray(out, dtype=np.int32)
+
+
 def _is_number(t: str) -> bool:
     try:
         float(t)
@@ -321,6 +346,59 @@ class IterativeRecommender:
         if n == 0:
             return {"MAE": float("nan"), "RMSE": float("nan")}
         return {"MAE": sa / n, "RMSE": math.sqrt(ss / n)}
+
+    def evalRankings(self, numRecs: int = 10, binThold: float = -1.0):
+        """The scoring half of Recommender.evalRankings (:738-824) on the device: for every test user u and every
+        context c in which u has a positive test rating (rating > binThold, DataDAO.java:1114-1139), all
+        candidate items (items of trainMatrix, in the reference's HashSet order) that u has not rated in c in
+        the training set are scored, filtered by score > binThold, stably sorted and cut to numRecs.
+        Returns a list of dicts {u, c, ranked (item ids), scores, kept, correct (positive test items that are
+        candidates)} in (u, c) order; the measures (Measures.PrecAt ..., :852-858) are left to the caller."""
+        t, tr = self.testMatrix, self.trainMatrix
+        if t is None:
+            return []
+        cand = java_hashset_order(tr.j)  # getItemList iterates the rows of trainMatrix (DataDAO.java:1213)
+        cand_set = set(int(x) for x in cand)
+        tc = t.get("ctx")
+        tctx = np.zeros(len(t["u"]), dtype=np.int32) if tc is None else np.asarray(tc)
+        pos: Dict[tuple, list] = {}
+        for u, j, c, r in zip(t["u"].tolist(), t["j"].tolist(), tctx.tolist(), np.asarray(t["r"]).tolist()):
+            if r > binThold:
+                pos.setdefault((u, c), []).append(j)
+        trctx = np.zeros(tr.nnz, dtype=np.int32) if tr.ctx is None else tr.ctx
+        rated: Dict[tuple, list] = {}
+        for u, j, c in zip(tr.u.tolist(), tr.j.tolist(), trctx.tolist()):
+            if (u, c) in pos:
+                rated.setdefault((u, c), []).append(j)
+        queries = []
+        for (u, c) in sorted(pos):
+            correct = [j for j in pos[(u, c)] if j in cand_set]
+            if correct:  # :781-782 `continue` when no positive item is a candidate
+                queries.append((u, c, correct))
+        if not queries:
+            return []
+        qu = np.array([q[0] for q in queries], dtype=np.int32)
+        qc = np.array([q[1] for q in queries], dtype=np.int32)
+        rptr = np.zeros(len(queries) + 1, dtype=np.int64)
+        ritems = []
+        for i, (u, c, _) in enumerate(queries):
+            ritems.extend(rated.get((u, c), []))
+            rptr[i + 1] = len(ritems)
+        eng = self._eval_engine()
+        try:
+            items, scores, count, kept = eng.rank_topn(qu, None if tr.ctx is None else qc, cand, rptr,
+                                                       np.asarray(ritems, dtype=np.int32), binThold, numRecs)
+        finally:
+            if eng is not self.engine:
+                eng.close()
+        out = []
+        for i, (u, c, correct) in enumerate(queries):
+            n = int(count[i])
+            if n == 0:
+                continue  # :817-818 no recommendations available
+            out.append({"u": u, "c": c, "ranked": items[i, :n].tolist(), "scores": scores[i, :n].tolist(),
+                        "kept": int(kept[i]), "correct": correct})
+        return out
 
     def execute(self, init: Optional[Dict[str, np.ndarray]] = None, seed: int = 0) -> Dict[str, float]:
         """Recommender.execute (:319-357): initModel -> buildModel -> evalRatings."""

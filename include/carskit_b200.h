@@ -163,6 +163,21 @@ int cars_eval_ratings(cars_handle* h, int64_t n, const int32_t* u, const int32_t
                       const double* r, double min_rate, double max_rate, double* sum_abs_err,
                       double* sum_sq_err);
 
+/* The scoring loop and top-N cut of evalRankings() (Recommender.java:797-824) for a batch of (user, context)
+ * queries: every candidate item not in the query's `rated` list (items the user rated in that context in the
+ * TRAINING set, :792/:800) is scored with ranking(u, j, c) = predict(u, j, c) (:807, :1016), dropped if NaN or
+ * not > bin_thold (:808-811), and the survivors are ordered like Lists.sortList(itemScores, true) (:822): by
+ * descending score, ties in candidate order -- `cand` must therefore list candItems in the iteration order of
+ * the reference's HashSet (:704).  Scores are bit-identical to Java's, so are the ranked ids.
+ *   out_items / out_scores  [num_queries x num_recs] the first min(num_recs, kept) entries are valid
+ *   out_count               ranked entries per query (rankedItems.size())
+ *   out_kept                itemScores.size() before the cut (numDropped = numCands - rankedItems.size(), :841)
+ * rated_ptr may be NULL (nothing excluded); qc may be NULL for PMF / BiasedMF.  The measures themselves
+ * (Measures.PrecAt .. RRAt, :852-858) stay with the caller. */
+int cars_rank_topn(cars_handle* h, int64_t num_queries, const int32_t* qu, const int32_t* qc, int32_t num_cand,
+                   const int32_t* cand, const int64_t* rated_ptr, const int32_t* rated_items, double bin_thold,
+                   int32_t num_recs, int32_t* out_items, double* out_scores, int32_t* out_count, int32_t* out_kept);
+
 /* ---- multi-GPU: one process (and one handle) per GPU, users sharded by contiguous range ------------------
  * The reference is single-process; SURVEY.md 8e defines the sharded semantics: every rank trains the
  * ratings of ITS users against its own copy of the item-side arrays (Q, itemBias, icBias -- "the item

@@ -15,6 +15,7 @@
 // (IterativeRecommender.java:40) arrive already widened to double in cars_desc.
 #include "../include/carskit_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -392,6 +393,57 @@ int oracle_build_model(const cars_desc* d, const cars_model_arrays* m, oracle_ep
     if (c) return iter;
   }
   return numIters;
+}
+
+// ---------------------------------------------------------------------------------------------
+// evalRankings scoring loop + top-N cut (Recommender.java:797-824), one query at a time exactly as written:
+//   for (Integer j : candItems) if (!ratedItems.contains(j)) { rank = ranking(u, j, c);
+//       if (!Double.isNaN(rank)) if (rank > binThold) itemScores.add((j, rank)); }
+//   Lists.sortList(itemScores, true);   // stable Collections.sort, comparator -(a.value.compareTo(b.value))
+//   recomd = itemScores.subList(0, numRecs)
+// `cand` is candItems in the reference's HashSet iteration order.
+// ---------------------------------------------------------------------------------------------
+static inline int java_double_compare(double a, double b) {  // Double.compare for non-NaN values
+  if (a < b) return -1;
+  if (a > b) return 1;
+  int64_t x, y;
+  std::memcpy(&x, &a, 8);
+  std::memcpy(&y, &b, 8);
+  return x == y ? 0 : (x < y ? -1 : 1);  // -0.0 < +0.0
+}
+
+int oracle_rank_topn(const cars_desc* d, const cars_model_arrays* m, int64_t num_queries, const int32_t* qu,
+                     const int32_t* qc, int32_t num_cand, const int32_t* cand, const int64_t* rated_ptr,
+                     const int32_t* rated_items, double bin_thold, int32_t num_recs, int32_t* out_items,
+                     double* out_scores, int32_t* out_count, int32_t* out_kept) {
+  std::vector<char> rated((size_t)d->num_items, 0);
+  std::vector<std::pair<int32_t, double>> scores;
+  for (int64_t q = 0; q < num_queries; q++) {
+    const int u = qu[q], c = qc ? qc[q] : 0;
+    if (rated_ptr)
+      for (int64_t i = rated_ptr[q]; i < rated_ptr[q + 1]; i++) rated[(size_t)rated_items[i]] = 1;
+    scores.clear();
+    for (int32_t k = 0; k < num_cand; k++) {
+      const int j = cand[k];
+      if (rated[(size_t)j]) continue;
+      const double rank = predict_one(d, m, u, j, c);
+      if (!std::isnan(rank))
+        if (rank > bin_thold) scores.emplace_back(j, rank);
+    }
+    if (rated_ptr)
+      for (int64_t i = rated_ptr[q]; i < rated_ptr[q + 1]; i++) rated[(size_t)rated_items[i]] = 0;
+    std::stable_sort(scores.begin(), scores.end(), [](const std::pair<int32_t, double>& a, const std::pair<int32_t, double>& b) {
+      return java_double_compare(a.second, b.second) > 0;
+    });
+    out_kept[q] = (int32_t)scores.size();
+    const int32_t n = (int32_t)scores.size() < num_recs ? (int32_t)scores.size() : num_recs;
+    out_count[q] = n;
+    for (int32_t i = 0; i < num_recs; i++) {
+      out_items[q * num_recs + i] = i < n ? scores[(size_t)i].first : -1;
+      out_scores[q * num_recs + i] = i < n ? scores[(size_t)i].second : 0.0;
+    }
+  }
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

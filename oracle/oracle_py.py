@@ -144,6 +144,31 @@ def eval_ratings(desc: CarsDesc, arrs: dict, u, j, ctx, r, min_rate, max_rate):
     return sa.value, ss.value, cnt.value
 
 
+def rank_topn(desc: CarsDesc, arrs: dict, qu, qc, cand, rated_ptr, rated_items, bin_thold: float, num_recs: int):
+    L = lib()
+    i64p = C.POINTER(C.c_int64)
+    L.oracle_rank_topn.argtypes = [C.POINTER(CarsDesc), C.POINTER(CarsModelArrays), C.c_int64, C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), i64p, C.POINTER(C.c_int32),
+                                   C.c_double, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.oracle_rank_topn.restype = C.c_int
+    qu = np.ascontiguousarray(qu, dtype=np.int32)
+    qc = None if qc is None else np.ascontiguousarray(qc, dtype=np.int32)
+    cand = np.ascontiguousarray(cand, dtype=np.int32)
+    nq = qu.shape[0]
+    items = np.full((nq, num_recs), -1, dtype=np.int32)
+    scores = np.zeros((nq, num_recs))
+    count = np.zeros(nq, dtype=np.int32)
+    kept = np.zeros(nq, dtype=np.int32)
+    rp = None if rated_ptr is None else np.ascontiguousarray(rated_ptr, dtype=np.int64)
+    ri = None if rated_items is None else np.ascontiguousarray(rated_items, dtype=np.int32)
+    a = make_arrays(arrs)
+    L.oracle_rank_topn(C.byref(desc), C.byref(a), nq, _ptr_i32(qu), _ptr_i32(qc), cand.shape[0], _ptr_i32(cand),
+                       None if rp is None else rp.ctypes.data_as(i64p), _ptr_i32(ri), bin_thold, num_recs,
+                       _ptr_i32(items), _ptr_f64(scores), _ptr_i32(count), _ptr_i32(kept))
+    return items, scores, count, kept
+
+
 def new_state(lrate: float, bold_driver=True, decay=-1.0, max_lrate=-1.0, early_stop=0) -> EpochState:
     s = EpochState()
     s.lRate = lrate
