@@ -233,3 +233,36 @@ def test_oracle_reproduces_golden(oracle, case):
     assert got["losses_hex"] == case["losses_hex"]
     assert got["digest"] == case["digest"]
     assert got["rmse_hex"] == case["rmse_hex"]
+
+
+def test_rank_topn_matches_independent_restatement(oracle):
+    # Recommender.java:797-824 restated with Python's stable sort on the oracle's own predictions
+    from tests.golden.make_golden import REGS, init_arrays
+    ts, test = synth.make_training_set(40, 60, [3, 2], 1500, seed=5, holdout=0.2)
+    model, F = capi.CAMF_CI, 6
+    arrs = init_arrays(oracle, model, ts, F, seed=3)
+    arrs["Q"][[7, 30]] = arrs["Q"][7]
+    arrs["ic_bias"][[7, 30]] = arrs["ic_bias"][7]  # an exact tie
+    desc = capi.make_desc(ts, model, F, **REGS)
+    cand = np.array(sorted(set(ts.j.tolist())), dtype=np.int32)[::-1].copy()  # any order: ties must follow it
+    keys = sorted({(int(u), int(c)) for u, c in zip(test["u"], test["ctx"])})[:25]
+    qu = np.array([k[0] for k in keys], dtype=np.int32)
+    qc = np.array([k[1] for k in keys], dtype=np.int32)
+    rated = {}
+    for u, j, c in zip(ts.u.tolist(), ts.j.tolist(), ts.ctx.tolist()):
+        rated.setdefault((u, c), set()).add(j)
+    rptr, ritems = [0], []
+    for k in keys:
+        ritems.extend(sorted(rated.get(k, ())))
+        rptr.append(len(ritems))
+    thold, nrec = 3.0, 7
+    items, scores, count, kept = oracle.rank_topn(desc, arrs, qu, qc, cand, np.array(rptr), np.array(ritems, dtype=np.int32),
+                                                  thold, nrec)
+    for q, (u, c) in enumerate(keys):
+        js = [int(j) for j in cand if int(j) not in rated.get((u, c), ())]
+        pr = oracle.predict(desc, arrs, [u] * len(js), js, [c] * len(js))
+        pairs = [(j, p) for j, p in zip(js, pr.tolist()) if p == p and p > thold]
+        pairs.sort(key=lambda x: -x[1])  # stable
+        assert kept[q] == len(pairs) and count[q] == min(nrec, len(pairs))
+        assert items[q, :count[q]].tolist() == [p[0] for p in pairs[:nrec]]
+        assert scores[q, :count[q]].tolist() == [p[1] for p in pairs[:nrec]]
