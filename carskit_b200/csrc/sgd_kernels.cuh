@@ -90,6 +90,29 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) {
 __device__ __forceinline__ void st_cg_f64(double* p, double v) {
   asm volatile("st.global.cg.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+// Model accesses by cache policy.  L1 = false: ld/st .cg (L2 only) -- required whenever another SM may have
+// written the row (every multi-CTA schedule).  L1 = true: default caching, for the single-warp serial kernel
+// where nobody else touches the model and an L1 hit saves an L2 round trip on every dependent load.
+template <bool L1>
+__device__ __forceinline__ double2 ldm_f64x2(const double* p) {
+  if (L1) return *reinterpret_cast<const double2*>(p);
+  return ld_cg_f64x2(p);
+}
+template <bool L1>
+__device__ __forceinline__ double ldm_f64(const double* p) {
+  if (L1) return *p;
+  return ld_cg_f64(p);
+}
+template <bool L1>
+__device__ __forceinline__ void stm_f64x2(double* p, double2 v) {
+  if (L1) *reinterpret_cast<double2*>(p) = v;
+  else st_cg_f64x2(p, v);
+}
+template <bool L1>
+__device__ __forceinline__ void stm_f64(double* p, double v) {
+  if (L1) *p = v;
+  else st_cg_f64(p, v);
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -159,13 +182,13 @@ struct Operands {
 // Scalars of one update: itemBias[j] and the lane's condition-bias cell.
 constexpr int kCondUnknown = -2;  // "look the condition id up" (a pre-fetched id is >= -1)
 
-template <int MODEL, int LPR, int V>
+template <int MODEL, int LPR, int V, bool L1 = false>
 __device__ __forceinline__ void gather_scalars(const DeviceModel& m, int u, int j, int ctx, int gl, Operands<V>& o,
                                                int cond_prefetched = kCondUnknown) {
   constexpr bool kItemBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CU);
   constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU);
   o.bj = 0.0;
-  if (kItemBias) o.bj = ld_cg_f64(m.item_bias + j);
+  if (kItemBias) o.bj = ldm_f64<L1>(m.item_bias + j);
   o.cb_ptr = nullptr;
   o.cb = 0.0;
   if (kHasCond && gl < m.Dmax) {
@@ -174,13 +197,13 @@ __device__ __forceinline__ void gather_scalars(const DeviceModel& m, int u, int 
       if (MODEL == M_CAMF_C) o.cb_ptr = m.cond_bias + cond;
       if (MODEL == M_CAMF_CI) o.cb_ptr = m.ic_bias + (int64_t)j * m.C + cond;
       if (MODEL == M_CAMF_CU) o.cb_ptr = m.uc_bias + (int64_t)u * m.C + cond;
-      o.cb = ld_cg_f64(o.cb_ptr);
+      o.cb = ldm_f64<L1>(o.cb_ptr);
     }
   }
 }
 
 // Factor rows straight from global memory (L2) into registers.
-template <int MODEL, int LPR, int V>
+template <int MODEL, int LPR, int V, bool L1 = false>
 __device__ __forceinline__ void gather_rows(const DeviceModel& m, int u, int j, int gl, UserRegs<V>& us,
                                             Operands<V>& o, bool load_user) {
   constexpr bool kUserBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CI);
@@ -191,14 +214,14 @@ __device__ __forceinline__ void gather_rows(const DeviceModel& m, int u, int j, 
   for (int v = 0; v < V; v++) {
     const int c = gl + v * LPR;  // chunk index
     if (2 * c < Fp) {
-      o.q[v] = ld_cg_f64x2(qrow + 2 * c);
-      if (load_user) us.p[v] = ld_cg_f64x2(prow + 2 * c);
+      o.q[v] = ldm_f64x2<L1>(qrow + 2 * c);
+      if (load_user) us.p[v] = ldm_f64x2<L1>(prow + 2 * c);
     } else {
       o.q[v] = make_double2(0.0, 0.0);
       us.p[v] = make_double2(0.0, 0.0);
     }
   }
-  if (kUserBias && load_user) us.bu = ld_cg_f64(m.user_bias + u);
+  if (kUserBias && load_user) us.bu = ldm_f64<L1>(m.user_bias + u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -207,7 +230,7 @@ __device__ __forceinline__ void gather_rows(const DeviceModel& m, int u, int j, 
 // scratch of Fp doubles (for the in-order dot product).  The user's row (and userBias) live in `us`
 // and are written back only when `store_user`.  Returns this lane's contribution to the epoch loss.
 // ------------------------------------------------------------------------------------------------
-template <int MODEL, int LPR, int V>
+template <int MODEL, int LPR, int V, bool L1 = false>
 __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, int j, int ctx, double r, double lr,
                                                   double* prod, int gl, unsigned gmask, UserRegs<V>& us,
                                                   const Operands<V>& o, bool store_user) {
@@ -269,7 +292,7 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
         const double* bp = MODEL == M_CAMF_C    ? m.cond_bias + cond
                            : MODEL == M_CAMF_CI ? m.ic_bias + (int64_t)j * m.C + cond
                                                 : m.uc_bias + (int64_t)u * m.C + cond;
-        pred = __dadd_rn(pred, ld_cg_f64(bp));
+        pred = __dadd_rn(pred, ldm_f64<L1>(bp));
       }
     }
   }
@@ -279,14 +302,14 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
   if (kUserBias) {  // every lane keeps the same copy of bu; lane 0 owns the loss term and the write-back
     const double sgd = __dsub_rn(e, __dmul_rn(m.reg_b, bu));
     us.bu = __dadd_rn(bu, __dmul_rn(lr, sgd));
-    if (store_user && gl == 0) st_cg_f64(m.user_bias + u, us.bu);
+    if (store_user && gl == 0) stm_f64<L1>(m.user_bias + u, us.bu);
   }
   if (gl == 0) {
     lane_loss = __dmul_rn(e, e);
     if (kUserBias) lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_b, bu), bu));
     if (kItemBias) {
       const double sgd = __dsub_rn(e, __dmul_rn(m.reg_b, bj));
-      st_cg_f64(m.item_bias + j, __dadd_rn(bj, __dmul_rn(lr, sgd)));
+      stm_f64<L1>(m.item_bias + j, __dadd_rn(bj, __dmul_rn(lr, sgd)));
       lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_b, bj), bj));
     }
   }
@@ -294,7 +317,7 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
     if (cb_ptr != nullptr) {
       const double sgd = __dsub_rn(e, __dmul_rn(m.reg_c, cb));
       const double step = __dmul_rn(lr, sgd);
-      st_cg_f64(cb_ptr, __dadd_rn(cb, step));
+      stm_f64<L1>(cb_ptr, __dadd_rn(cb, step));
       // CAMF_C.java:115 adds regB * sum(bc) (not squared); CI/CU add regC * sum(b^2) (:108 / :105)
       if (MODEL == M_CAMF_C)
         lane_loss = __dadd_rn(lane_loss, __dmul_rn(m.reg_b, cb));
@@ -308,9 +331,9 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
         double* bp = MODEL == M_CAMF_C    ? m.cond_bias + cond
                      : MODEL == M_CAMF_CI ? m.ic_bias + (int64_t)j * m.C + cond
                                           : m.uc_bias + (int64_t)u * m.C + cond;
-        const double b = ld_cg_f64(bp);
+        const double b = ldm_f64<L1>(bp);
         const double step = __dmul_rn(lr, __dsub_rn(e, __dmul_rn(m.reg_c, b)));
-        st_cg_f64(bp, __dadd_rn(b, step));
+        stm_f64<L1>(bp, __dadd_rn(b, step));
         lane_loss = __dadd_rn(lane_loss, MODEL == M_CAMF_C ? __dmul_rn(m.reg_b, b)
                                                              : __dmul_rn(m.reg_c, __dmul_rn(b, b)));
       }
@@ -332,8 +355,8 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
       pn.y = __dadd_rn(po.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, qo.y), __dmul_rn(m.reg_u, po.y))));
       qn.y = __dadd_rn(qo.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, po.y), __dmul_rn(m.reg_i, qo.y))));
       us.p[v] = pn;
-      st_cg_f64x2(qrow + 2 * c, qn);
-      if (store_user) st_cg_f64x2(prow + 2 * c, pn);
+      stm_f64x2<L1>(qrow + 2 * c, qn);
+      if (store_user) stm_f64x2<L1>(prow + 2 * c, pn);
       sp = fma(po.x, po.x, sp);
       sq = fma(qo.x, qo.x, sq);
       sp = fma(po.y, po.y, sp);
@@ -345,15 +368,15 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
 }
 
 // gather + compute + scatter with plain loads (wavefront, serial and dataflow kernels).
-template <int MODEL, int LPR, int V>
+template <int MODEL, int LPR, int V, bool L1 = false>
 __device__ __forceinline__ double rating_update(const DeviceModel& m, int u, int j, int ctx, double r,
                                                 double lr, double* prod, int gl /*lane in group*/,
                                                 unsigned gmask /*lanes of this group*/, UserRegs<V>& us,
                                                 bool load_user, bool store_user) {
   Operands<V> o;
-  gather_rows<MODEL, LPR, V>(m, u, j, gl, us, o, load_user);
-  gather_scalars<MODEL, LPR, V>(m, u, j, ctx, gl, o);
-  return compute_scatter<MODEL, LPR, V>(m, u, j, ctx, r, lr, prod, gl, gmask, us, o, store_user);
+  gather_rows<MODEL, LPR, V, L1>(m, u, j, gl, us, o, load_user);
+  gather_scalars<MODEL, LPR, V, L1>(m, u, j, ctx, gl, o);
+  return compute_scatter<MODEL, LPR, V, L1>(m, u, j, ctx, r, lr, prod, gl, gmask, us, o, store_user);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -422,8 +445,9 @@ __global__ void __launch_bounds__(32, 1)
     const int j = __ldg(s.j + n);
     const int ctx = s.ctx ? __ldg(s.ctx + n) : 0;
     const double r = __ldg(s.r + n);
+    // one warp owns the whole model, so its accesses go through L1 (rating_update<.., L1 = true>)
     UserRegs<V> us;
-    acc = __dadd_rn(acc, rating_update<MODEL, 32, V>(m, u, j, ctx, r, lr, prod, lane, 0xffffffffu, us, true, true));
+    acc = __dadd_rn(acc, rating_update<MODEL, 32, V, true>(m, u, j, ctx, r, lr, prod, lane, 0xffffffffu, us, true, true));
     __syncwarp();
     __threadfence_block();
   }

@@ -47,7 +47,19 @@ def make_training_set(num_users: int, num_items: int, dims: Optional[Sequence[in
         j = rng.choice(num_items, size=nnz, p=w / w.sum()).astype(np.int64)
     else:
         j = rng.integers(0, num_items, size=nnz, dtype=np.int64)
-    if dims is not None:
+    if dims is not None and float(np.prod([float(d) for d in dims])) > max(4.0 * nnz, 1e6):
+        # far more combinations than ratings (Frappe: 7*7*2*3*2*9*80*233 = 98.6 M for 96 K rows): like DataDAO,
+        # only the contexts that OCCUR get an id (ids in lexicographic order of their condition tuples)
+        # a pool of about nnz/5 distinct contexts, reused by the ratings (Frappe: 18.6 K contexts for 96 K rows)
+        offs = np.concatenate([[0], np.cumsum(dims)[:-1]]).astype(np.int64)
+        pool = max(1000, nnz // 5)
+        rows = np.stack([rng.integers(0, d, size=pool, dtype=np.int64) for d in dims], axis=1)
+        uniq = np.unique(rows, axis=0)
+        num_ctx, num_cond = int(uniq.shape[0]), int(sum(dims))
+        c = rng.integers(0, num_ctx, size=nnz, dtype=np.int64)
+        ctx_cond = (uniq + offs[None, :]).astype(np.int32).reshape(-1).copy()
+        ctx_ptr = (np.arange(num_ctx + 1, dtype=np.int64) * len(dims)).astype(np.int32)
+    elif dims is not None:
         ctx_ptr, ctx_cond, num_ctx, num_cond = context_table(dims)
         c = rng.integers(0, num_ctx, size=nnz, dtype=np.int64)
     else:
