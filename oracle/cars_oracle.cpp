@@ -6,8 +6,9 @@
 //
 // PARITY UNPINNED: the reference ships no tests, no golden vectors and cannot run here (no JVM in the
 // image).  The only external pins are the java.util.Random known answers in
-// tests/test_oracle.py and the hand-traced layout of sampleData/train_binary.csv.  Everything else is
-// a line-by-line reading of the Java sources cited at each function.
+// tests/test_oracle.py and the layout of the reference's own sampleData/train_binary.csv (tests/test_data.py,
+// against carskit_b200/data.py).  Everything else is a line-by-line reading of the Java sources cited at each
+// function, cross-checked by an independent Python restatement (tests/test_oracle.py).
 //
 // Arithmetic rules: every value is fp64; Java never contracts a*b+c, so this
 // file must be compiled with -ffp-contract=off (the Makefile does; a static_assert-style runtime

@@ -29,7 +29,7 @@ class EpochState(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("cars_oracle.cpp", "fm_oracle.cpp", "loader_oracle.cpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("cars_oracle.cpp", "fm_oracle.cpp")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return LIB_PATH
