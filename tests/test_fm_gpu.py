@@ -93,3 +93,22 @@ def test_fm_recommender_mirror_and_errors(oracle, cars_lib):
         capi.FmEngine(capi.make_desc(ts, capi.FM, 8, num_context_dims=0), keepalive=ts)
     with pytest.raises(capi.CarsError):
         capi.Engine(capi.make_desc(ts, capi.FM, 8, num_context_dims=2), keepalive=ts)
+
+
+def test_fm_against_committed_golden_vectors(oracle, cars_lib):
+    import json
+    import os
+    from tests.golden.make_fm_golden import SPEC
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fm_golden.json")))
+    ts, test, prob, arrs = fm_inputs(oracle, SPEC["users"], SPEC["items"], SPEC["dims"], SPEC["nnz"], SPEC["k"],
+                                     seed=SPEC["seed"], holdout=SPEC["holdout"])
+    got, _, _ = run_gpu(ts, arrs, SPEC["k"], len(SPEC["dims"]), SPEC["iters"])
+    np.testing.assert_allclose(got["w0"][0], float.fromhex(g["w0"]), rtol=1e-8)
+    np.testing.assert_allclose(got["w"], [float.fromhex(x) for x in g["w"]], rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(got["V"].reshape(-1), [float.fromhex(x) for x in g["V"]], rtol=1e-8, atol=1e-11)
+    desc = capi.make_desc(ts, capi.FM, SPEC["k"], reg_lw=float(np.float32(0.01)), reg_lf=float(np.float32(0.02)),
+                          num_context_dims=len(SPEC["dims"]))
+    with capi.FmEngine(desc, keepalive=ts) as eng:
+        eng.upload(got)
+        p = eng.predict(test["u"], test["j"], test["ctx"], bound=True, min_rate=1.0, max_rate=5.0)
+    assert np.max(np.abs(p - np.array([float.fromhex(x) for x in g["pred"]]))) < 1e-5  # the north star's tolerance

@@ -83,3 +83,13 @@ def test_reference_quirks_are_reproduced_not_repaired(oracle):
     true_sse0, true_sse = float(np.sum((ts.r - pred0) ** 2)), float(np.sum((ts.r - pred) ** 2))
     assert true_sse > true_sse0  # ... while the model's real training error goes UP (sign convention)
     assert np.max(np.abs(e - (ts.r - pred))) > 1.0
+
+
+def test_dense_oracle_reproduces_fm_golden(oracle):
+    import json
+    import os
+    from tests.golden.make_fm_golden import run
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fm_golden.json")))
+    got = run(oracle)
+    for k in ("w0", "w", "V", "pred"):
+        assert got[k] == g[k], k
