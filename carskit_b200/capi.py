@@ -13,10 +13,11 @@ from typing import Optional
 import numpy as np
 
 ABI_VERSION = 1
-PMF, BIASEDMF, CAMF_C, CAMF_CI, CAMF_CU, FM = range(6)
+PMF, BIASEDMF, CAMF_C, CAMF_CI, CAMF_CU, FM, CAMF_CUCI = range(7)
 EXACT, FAST = 0, 1
 SCHED_FLAGGED, SCHED_WAVEFRONT, SCHED_DATAFLOW = 0, 1, 2
-MODEL_NAMES = {"pmf": PMF, "biasedmf": BIASEDMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM}
+MODEL_NAMES = {"pmf": PMF, "biasedmf": BIASEDMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM,
+               "camf_cuci": CAMF_CUCI}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # CARSKIT_B200_LIB selects another build of the same ABI (e.g. the developer build with stage tracing)
@@ -224,7 +225,7 @@ def make_desc(ts: TrainingSet, model: int, num_factors: int, *, mode: int = EXAC
     d.num_factors = num_factors
     d.nnz = ts.nnz
     d.u, d.j, d.r = _ptr_i32(ts.u), _ptr_i32(ts.j), _ptr_f64(ts.r)
-    use_ctx = model in (CAMF_C, CAMF_CI, CAMF_CU, FM) and ts.ctx is not None
+    use_ctx = model in (CAMF_C, CAMF_CI, CAMF_CU, CAMF_CUCI, FM) and ts.ctx is not None
     d.ctx = _ptr_i32(ts.ctx) if use_ctx else None
     d.ctx_ptr = _ptr_i32(ts.ctx_ptr) if use_ctx else None
     d.ctx_cond = _ptr_i32(ts.ctx_cond) if use_ctx else None
@@ -242,6 +243,7 @@ MODEL_MEMBERS = {
     CAMF_C: ("P", "Q", "user_bias", "item_bias", "cond_bias"),
     CAMF_CI: ("P", "Q", "user_bias", "ic_bias"),
     CAMF_CU: ("P", "Q", "item_bias", "uc_bias"),
+    CAMF_CUCI: ("P", "Q", "ic_bias", "uc_bias"),
 }
 
 

@@ -151,6 +151,7 @@ static LaunchPlan pick_plan(int model, int /*mode*/, int Fp) {
     case CARS_CAMF_C: return LaunchPlan{};  // every rating touches condBias: serial kernel only
     case CARS_CAMF_CI: return pick_wavefront<M_CAMF_CI>(Fp, v);
     case CARS_CAMF_CU: return pick_wavefront<M_CAMF_CU>(Fp, v);
+    case CARS_CAMF_CUCI: return pick_wavefront<M_CAMF_CUCI>(Fp, v);
   }
   return LaunchPlan{};
 }
@@ -244,6 +245,7 @@ static LaunchPlan pick_flagged_plan(int model, int Fp) {
     case CARS_BIASEDMF: return pick_flagged<M_BIASEDMF>(Fp, v);
     case CARS_CAMF_CI: return pick_flagged<M_CAMF_CI>(Fp, v);
     case CARS_CAMF_CU: return pick_flagged<M_CAMF_CU>(Fp, v);
+    case CARS_CAMF_CUCI: return pick_flagged<M_CAMF_CUCI>(Fp, v);
   }
   return LaunchPlan{};
 }
@@ -255,6 +257,7 @@ static LaunchPlan pick_dataflow_plan(int model, int Fp) {
     case CARS_BIASEDMF: return pick_dataflow<M_BIASEDMF>(Fp, v);
     case CARS_CAMF_CI: return pick_dataflow<M_CAMF_CI>(Fp, v);
     case CARS_CAMF_CU: return pick_dataflow<M_CAMF_CU>(Fp, v);
+    case CARS_CAMF_CUCI: return pick_dataflow<M_CAMF_CUCI>(Fp, v);
   }
   return LaunchPlan{};
 }
@@ -274,12 +277,13 @@ static const void* pick_serial(int model, int Fp) {
     case CARS_CAMF_C: return pick_serial_m<M_CAMF_C>(Fp);
     case CARS_CAMF_CI: return pick_serial_m<M_CAMF_CI>(Fp);
     case CARS_CAMF_CU: return pick_serial_m<M_CAMF_CU>(Fp);
+    case CARS_CAMF_CUCI: return pick_serial_m<M_CAMF_CUCI>(Fp);
   }
   return nullptr;
 }
 
 static bool model_has_ctx(int model) {
-  return model == CARS_CAMF_C || model == CARS_CAMF_CI || model == CARS_CAMF_CU;
+  return model == CARS_CAMF_C || model == CARS_CAMF_CI || model == CARS_CAMF_CU || model == CARS_CAMF_CUCI;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -289,7 +293,7 @@ static int validate(const cars_desc* d) {
   if (!d) return fail(nullptr, CARS_E_INVALID, "desc is NULL");
   if (d->abi_version != CARS_ABI_VERSION)
     return fail(nullptr, CARS_E_INVALID, "abi_version %d != %d", d->abi_version, CARS_ABI_VERSION);
-  if (d->model < CARS_PMF || d->model > CARS_FM) return fail(nullptr, CARS_E_INVALID, "unknown model %d", d->model);
+  if (d->model < CARS_PMF || d->model > CARS_CAMF_CUCI) return fail(nullptr, CARS_E_INVALID, "unknown model %d", d->model);
   if (d->model == CARS_FM)
     return fail(nullptr, CARS_E_INVALID, "FM is an ALS model with its own entry points: use cars_fm_create");
   if (d->mode != CARS_EXACT && d->mode != CARS_FAST) return fail(nullptr, CARS_E_INVALID, "unknown mode %d", d->mode);
@@ -570,8 +574,8 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   if (model == CARS_BIASEDMF || model == CARS_CAMF_C || model == CARS_CAMF_CI) CUDA_TRY_H(dev_alloc(&m.user_bias, U));
   if (model == CARS_BIASEDMF || model == CARS_CAMF_C || model == CARS_CAMF_CU) CUDA_TRY_H(dev_alloc(&m.item_bias, I));
   if (model == CARS_CAMF_C) CUDA_TRY_H(dev_alloc(&m.cond_bias, C));
-  if (model == CARS_CAMF_CI) CUDA_TRY_H(dev_alloc(&m.ic_bias, I * C));
-  if (model == CARS_CAMF_CU) CUDA_TRY_H(dev_alloc(&m.uc_bias, U * C));
+  if (model == CARS_CAMF_CI || model == CARS_CAMF_CUCI) CUDA_TRY_H(dev_alloc(&m.ic_bias, I * C));
+  if (model == CARS_CAMF_CU || model == CARS_CAMF_CUCI) CUDA_TRY_H(dev_alloc(&m.uc_bias, U * C));
 
   CUDA_TRY_H(dev_alloc(&h->d_barrier, 1));
   CUDA_TRY_H(dev_alloc(&h->d_partial, (size_t)(h->grid > 1024 ? h->grid : 1024)));
@@ -866,6 +870,7 @@ static int predict_device(cars_handle* h, int64_t n, const int32_t* u, const int
     case CARS_CAMF_C: predict_kernel<M_CAMF_C><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
     case CARS_CAMF_CI: predict_kernel<M_CAMF_CI><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
     case CARS_CAMF_CU: predict_kernel<M_CAMF_CU><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
+    case CARS_CAMF_CUCI: predict_kernel<M_CAMF_CUCI><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
     default: return fail(h, CARS_E_UNSUPPORTED, "predict: model %d", h->d.model);
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -1019,6 +1024,7 @@ extern "C" int cars_rank_topn(cars_handle* h, int64_t num_queries, const int32_t
       case CARS_CAMF_C: RK(launch_rank_score<M_CAMF_C>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
       case CARS_CAMF_CI: RK(launch_rank_score<M_CAMF_CI>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
       case CARS_CAMF_CU: RK(launch_rank_score<M_CAMF_CU>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
+      case CARS_CAMF_CUCI: RK(launch_rank_score<M_CAMF_CUCI>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
       default: rc = fail(h, CARS_E_UNSUPPORTED, "rank: model %d", h->d.model); break;
     }
     if (rc) break;

@@ -2,7 +2,8 @@
 //
 // One "rating update" is the body of the per-rating loop of buildModel()
 // (reference: src/carskit/alg/cars/adaptation/dependent/dev/CAMF_CI.java:80-121 and the sibling
-// classes CAMF_C.java:80-128, CAMF_CU.java:77-118, baseline/cf/BiasedMF.java:63-99, PMF.java:52-71).
+// classes CAMF_C.java:80-128, CAMF_CU.java:77-118, CAMF_CUCI.java:81-127, baseline/cf/BiasedMF.java:63-99,
+// PMF.java:52-71).
 //
 // Arithmetic contract: fp64, every * + - separately rounded (Java has no FMA
 // contraction) -> all arithmetic below goes through __dmul_rn/__dadd_rn/__dsub_rn, which nvcc never
@@ -17,7 +18,7 @@
 
 namespace cars {
 
-enum : int { M_PMF = 0, M_BIASEDMF = 1, M_CAMF_C = 2, M_CAMF_CI = 3, M_CAMF_CU = 4 };
+enum : int { M_PMF = 0, M_BIASEDMF = 1, M_CAMF_C = 2, M_CAMF_CI = 3, M_CAMF_CU = 4, M_CAMF_CUCI = 5 };
 
 // Device-resident state shared by all kernels.  Plain pointers into the handle's allocations.
 struct DeviceModel {
@@ -177,6 +178,8 @@ struct Operands {
   double bj;       // itemBias[j]
   double cb;       // this lane's condition-bias cell (lane d owns context dimension d)
   double* cb_ptr;  // its address; nullptr when the lane owns none
+  double cb2;      // CAMF_CUCI only: cb = icBias[j][cond], cb2 = ucBias[u][cond]
+  double* cb2_ptr;
 };
 
 // Scalars of one update: itemBias[j] and the lane's condition-bias cell.
@@ -186,18 +189,24 @@ template <int MODEL, int LPR, int V, bool L1 = false>
 __device__ __forceinline__ void gather_scalars(const DeviceModel& m, int u, int j, int ctx, int gl, Operands<V>& o,
                                                int cond_prefetched = kCondUnknown) {
   constexpr bool kItemBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CU);
-  constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU);
+  constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU || MODEL == M_CAMF_CUCI);
   o.bj = 0.0;
   if (kItemBias) o.bj = ldm_f64<L1>(m.item_bias + j);
   o.cb_ptr = nullptr;
   o.cb = 0.0;
+  o.cb2_ptr = nullptr;
+  o.cb2 = 0.0;
   if (kHasCond && gl < m.Dmax) {
     const int cond = cond_prefetched != kCondUnknown ? cond_prefetched : __ldg(m.ctx_tab + (int64_t)ctx * m.Dmax + gl);
     if (cond >= 0) {
       if (MODEL == M_CAMF_C) o.cb_ptr = m.cond_bias + cond;
-      if (MODEL == M_CAMF_CI) o.cb_ptr = m.ic_bias + (int64_t)j * m.C + cond;
+      if (MODEL == M_CAMF_CI || MODEL == M_CAMF_CUCI) o.cb_ptr = m.ic_bias + (int64_t)j * m.C + cond;
       if (MODEL == M_CAMF_CU) o.cb_ptr = m.uc_bias + (int64_t)u * m.C + cond;
       o.cb = ldm_f64<L1>(o.cb_ptr);
+      if (MODEL == M_CAMF_CUCI) {
+        o.cb2_ptr = m.uc_bias + (int64_t)u * m.C + cond;
+        o.cb2 = ldm_f64<L1>(o.cb2_ptr);
+      }
     }
   }
 }
@@ -236,7 +245,7 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
                                                   const Operands<V>& o, bool store_user) {
   constexpr bool kUserBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CI);
   constexpr bool kItemBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CU);
-  constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU);
+  constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU || MODEL == M_CAMF_CUCI);
   const int Fp = m.Fp;
   const int Dmax = m.Dmax;
   double* prow = m.P + (int64_t)u * Fp;
@@ -277,22 +286,27 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
     pred = __dadd_rn(__dadd_rn(__dadd_rn(m.global_mean, bu), bj), dot);
   if (MODEL == M_CAMF_CI) pred = __dadd_rn(__dadd_rn(m.global_mean, bu), dot);
   if (MODEL == M_CAMF_CU) pred = __dadd_rn(__dadd_rn(m.global_mean, bj), dot);
+  if (MODEL == M_CAMF_CUCI) pred = __dadd_rn(m.global_mean, dot);
 
   double lane_loss = 0.0;
   if (kHasCond) {
     // conditions beyond the first LPR (Dmax > LPR) are handled by the slow path below
     const int D1 = Dmax < LPR ? Dmax : LPR;
+    // CAMF_CUCI.java:71: pred += icBias(j,cond) + ucBias(u,cond) -- the two cells are added first
+    const double cbs = MODEL == M_CAMF_CUCI ? __dadd_rn(cb, o.cb2) : cb;
     for (int d = 0; d < D1; d++) {
-      const double b = shfl_f64(gmask, cb, d, LPR);
+      const double b = shfl_f64(gmask, cbs, d, LPR);
       pred = __dadd_rn(pred, b);  // adding a padded slot adds +0.0: exact
     }
     for (int d = LPR; d < Dmax; d++) {  // rare: more context dimensions than lanes in a group
       const int cond = __ldg(m.ctx_tab + (int64_t)ctx * Dmax + d);
       if (cond >= 0) {
         const double* bp = MODEL == M_CAMF_C    ? m.cond_bias + cond
-                           : MODEL == M_CAMF_CI ? m.ic_bias + (int64_t)j * m.C + cond
+                           : (MODEL == M_CAMF_CI || MODEL == M_CAMF_CUCI) ? m.ic_bias + (int64_t)j * m.C + cond
                                                 : m.uc_bias + (int64_t)u * m.C + cond;
-        pred = __dadd_rn(pred, ldm_f64<L1>(bp));
+        double b = ldm_f64<L1>(bp);
+        if (MODEL == M_CAMF_CUCI) b = __dadd_rn(b, ldm_f64<L1>(m.uc_bias + (int64_t)u * m.C + cond));
+        pred = __dadd_rn(pred, b);
       }
     }
   }
@@ -323,19 +337,32 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
         lane_loss = __dadd_rn(lane_loss, __dmul_rn(m.reg_b, cb));
       else
         lane_loss = __dadd_rn(lane_loss, __dmul_rn(m.reg_c, __dmul_rn(cb, cb)));
+      if (MODEL == M_CAMF_CUCI) {  // CAMF_CUCI.java:104-112: the user-context cell, same step with Buc
+        const double cb2 = o.cb2;
+        const double step2 = __dmul_rn(lr, __dsub_rn(e, __dmul_rn(m.reg_c, cb2)));
+        stm_f64<L1>(o.cb2_ptr, __dadd_rn(cb2, step2));
+        lane_loss = __dadd_rn(lane_loss, __dmul_rn(m.reg_c, __dmul_rn(cb2, cb2)));
+      }
     }
     if (gl == 0) {
       for (int d = LPR; d < Dmax; d++) {
         const int cond = __ldg(m.ctx_tab + (int64_t)ctx * Dmax + d);
         if (cond < 0) continue;
         double* bp = MODEL == M_CAMF_C    ? m.cond_bias + cond
-                     : MODEL == M_CAMF_CI ? m.ic_bias + (int64_t)j * m.C + cond
+                     : (MODEL == M_CAMF_CI || MODEL == M_CAMF_CUCI) ? m.ic_bias + (int64_t)j * m.C + cond
                                           : m.uc_bias + (int64_t)u * m.C + cond;
         const double b = ldm_f64<L1>(bp);
         const double step = __dmul_rn(lr, __dsub_rn(e, __dmul_rn(m.reg_c, b)));
         stm_f64<L1>(bp, __dadd_rn(b, step));
         lane_loss = __dadd_rn(lane_loss, MODEL == M_CAMF_C ? __dmul_rn(m.reg_b, b)
                                                              : __dmul_rn(m.reg_c, __dmul_rn(b, b)));
+        if (MODEL == M_CAMF_CUCI) {
+          double* bp2 = m.uc_bias + (int64_t)u * m.C + cond;
+          const double b2 = ldm_f64<L1>(bp2);
+          const double step2 = __dmul_rn(lr, __dsub_rn(e, __dmul_rn(m.reg_c, b2)));
+          stm_f64<L1>(bp2, __dadd_rn(b2, step2));
+          lane_loss = __dadd_rn(lane_loss, __dmul_rn(m.reg_c, __dmul_rn(b2, b2)));
+        }
       }
     }
   }
@@ -584,7 +611,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
   double* prod = reinterpret_cast<double*>(smem_raw) + (size_t)(warp * G + gw) * prod_stride;
   unsigned* done_u = flags + off_u;
   unsigned* done_j = flags + off_j;
-  constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU);
+  constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU || MODEL == M_CAMF_CUCI);
 
   // interleave CTAs so that consecutive ratings land on different SMs
   const int64_t T = (int64_t)gridDim.x * WARPS * G;
@@ -735,13 +762,15 @@ __device__ __forceinline__ double predict_from_dot(const DeviceModel& m, int u, 
     pred = __dadd_rn(__dadd_rn(__dadd_rn(m.global_mean, m.user_bias[u]), m.item_bias[j]), dot);
   if (MODEL == M_CAMF_CI) pred = __dadd_rn(__dadd_rn(m.global_mean, m.user_bias[u]), dot);
   if (MODEL == M_CAMF_CU) pred = __dadd_rn(__dadd_rn(m.global_mean, m.item_bias[j]), dot);
-  if (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU) {
+  if (MODEL == M_CAMF_CUCI) pred = __dadd_rn(m.global_mean, dot);  // CAMF_CUCI.java:69
+  if (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU || MODEL == M_CAMF_CUCI) {
     for (int d = 0; d < m.Dmax; d++) {
       const int cond = m.ctx_tab[(int64_t)ctx * m.Dmax + d];
       if (cond < 0) continue;
-      const double b = MODEL == M_CAMF_C    ? m.cond_bias[cond]
-                       : MODEL == M_CAMF_CI ? m.ic_bias[(int64_t)j * m.C + cond]
-                                            : m.uc_bias[(int64_t)u * m.C + cond];
+      double b = MODEL == M_CAMF_C    ? m.cond_bias[cond]
+                 : (MODEL == M_CAMF_CI || MODEL == M_CAMF_CUCI) ? m.ic_bias[(int64_t)j * m.C + cond]
+                                      : m.uc_bias[(int64_t)u * m.C + cond];
+      if (MODEL == M_CAMF_CUCI) b = __dadd_rn(b, m.uc_bias[(int64_t)u * m.C + cond]);  // :71 (ic + uc) first
       pred = __dadd_rn(pred, b);
     }
   }

@@ -9,7 +9,7 @@ here with the reference's own names, argument meaning and call order:
       isConverged(iter)                :145-199
       updateLRate(iter)                :216-229
     PMF / BiasedMF                     src/carskit/alg/baseline/cf/{PMF,BiasedMF}.java
-    CAMF_C / CAMF_CI / CAMF_CU         src/carskit/alg/cars/adaptation/dependent/dev/*.java
+    CAMF_C / CAMF_CI / CAMF_CU / CAMF_CUCI  src/carskit/alg/cars/adaptation/dependent/dev/*.java
 
 Only buildModel() differs from the reference: instead of the per-rating Java loop it flattens the
 containers once and drives `cars_epoch` (include/carskit_b200.h) once per iteration, keeping
@@ -113,6 +113,7 @@ class IterativeRecommender:
 
     MODEL = capi.PMF
     algoName = "IterativeRecommender"
+    GAUSSIAN_CONTEXT_BIAS = False  # icBias / ucBias ~ U(0,1) (CAMF_CI.java:58-59); CAMF_CUCI draws Gaussians
 
     def __init__(self, trainMatrix: TrainingSet, testMatrix: Optional[dict] = None, fold: int = -1,
                  conf: Optional[Dict[str, str]] = None, device: int = 0, stream: int = 0, world: int = 1,
@@ -177,7 +178,7 @@ class IterativeRecommender:
             return
         rng = np.random.default_rng(seed)
         for k, s in shapes.items():
-            if k in ("ic_bias", "uc_bias"):
+            if k in ("ic_bias", "uc_bias") and not self.GAUSSIAN_CONTEXT_BIAS:
                 self.model[k] = rng.random(s)
             else:
                 self.model[k] = self.initMean + self.initStd * rng.standard_normal(s)
@@ -435,6 +436,13 @@ class CAMF_CU(IterativeRecommender):
     MODEL, algoName = capi.CAMF_CU, "CAMF_CU"
 
 
+class CAMF_CUCI(IterativeRecommender):
+    """CAMF_CUCI.java: item-context AND user-context deviations; its Guava tables hold one Gaussian cell per
+    (user | item, condition) (:58-64), passed to the engine as dense arrays."""
+    MODEL, algoName = capi.CAMF_CUCI, "CAMF_CUCI"
+    GAUSSIAN_CONTEXT_BIAS = True
+
+
 class FM(IterativeRecommender):
     """carskit.alg.cars.adaptation.dependent.FM (FM.java): ALS factorization machine over the one-hot features
     (user, item, context).  `FM=-lw <f> -lf <f>` in the configuration (FM.java:53-54); learn.rate and
@@ -539,7 +547,8 @@ class FM(IterativeRecommender):
 
 def getRecommender(name: str):
     """The `switch` of CARSKit.getRecommender (src/carskit/main/CARSKit.java:429-705) for this path."""
-    table = {"pmf": PMF, "biasedmf": BiasedMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM}
+    table = {"pmf": PMF, "biasedmf": BiasedMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM,
+             "camf_cuci": CAMF_CUCI}
     try:
         return table[name.lower()]
     except KeyError:

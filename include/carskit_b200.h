@@ -37,7 +37,10 @@ enum cars_model {
   CARS_CAMF_C   = 2, /* .../cars/adaptation/dependent/dev/CAMF_C.java:74-138  */
   CARS_CAMF_CI  = 3, /* .../cars/adaptation/dependent/dev/CAMF_CI.java:74-131 */
   CARS_CAMF_CU  = 4, /* .../cars/adaptation/dependent/dev/CAMF_CU.java:71-128 */
-  CARS_FM       = 5  /* .../cars/adaptation/dependent/FM.java:115-220 (ALS; cars_fm_* entry points below) */
+  CARS_FM       = 5, /* .../cars/adaptation/dependent/FM.java:115-220 (ALS; cars_fm_* entry points below) */
+  CARS_CAMF_CUCI = 6 /* .../cars/adaptation/dependent/dev/CAMF_CUCI.java:78-134: ic_bias AND uc_bias, no user /
+                        item bias; the reference's Guava tables icBias / ucBias are passed as dense
+                        [num_items x C] / [num_users x C] arrays (every cell is initialised, :58-64) */
 };
 
 /* Update mode.
@@ -117,7 +120,8 @@ typedef struct cars_handle cars_handle;
  *   user_bias [num_users], item_bias [num_items]      IterativeRecommender.java:61-63
  *   cond_bias [num_conditions]                        CAMF.java (condBias), CAMF_C.java:60
  *   ic_bias [num_items x num_conditions]              CAMF_CI.java:58
- *   uc_bias [num_users x num_conditions]              CAMF_CU.java:55 */
+ *   uc_bias [num_users x num_conditions]              CAMF_CU.java:55
+ *   (CAMF_CUCI: both ic_bias and uc_bias, CAMF_CUCI.java:42-43, 58-64) */
 typedef struct cars_model_arrays {
   double* P;
   double* Q;

@@ -186,6 +186,13 @@ static inline double predict_one(const cars_desc* d, const cars_model_arrays* m,
       for (int k = d->ctx_ptr[c]; k < d->ctx_ptr[c + 1]; k++)
         pred += m->uc_bias[(int64_t)u * C + d->ctx_cond[k]];
       return pred;
+    case CARS_CAMF_CUCI:  // CAMF_CUCI.java:68-74 (`pred += ic + uc`: the two cells are added first)
+      pred = d->global_mean + row_mult(m->P, u, m->Q, j, F);
+      for (int k = d->ctx_ptr[c]; k < d->ctx_ptr[c + 1]; k++) {
+        int cond = d->ctx_cond[k];
+        pred += m->ic_bias[(int64_t)j * C + cond] + m->uc_bias[(int64_t)u * C + cond];
+      }
+      return pred;
     default:
       return NAN;
   }
@@ -329,6 +336,23 @@ double oracle_epoch(const cars_desc* d, const cars_model_arrays* m, double lRate
           m->uc_bias[(int64_t)u * C + cond] = Buc + lRate * sgd;
         }
         loss += regC * Buc_sum;
+        break;
+      }
+      case CARS_CAMF_CUCI: {  // CAMF_CUCI.java:98-114
+        double Buc_sum = 0;
+        double Bic_sum = 0;
+        for (int k = d->ctx_ptr[ctx]; k < d->ctx_ptr[ctx + 1]; k++) {
+          int cond = d->ctx_cond[k];
+          double Buc = m->uc_bias[(int64_t)u * C + cond];
+          double Bic = m->ic_bias[(int64_t)j * C + cond];
+          Buc_sum += Buc * Buc;
+          Bic_sum += Bic * Bic;
+          double sgdu = euj - regC * Buc;
+          double sgdj = euj - regC * Bic;
+          m->uc_bias[(int64_t)u * C + cond] = Buc + lRate * sgdu;
+          m->ic_bias[(int64_t)j * C + cond] = Bic + lRate * sgdj;
+        }
+        loss += regC * Bic_sum + regC * Buc_sum;
         break;
       }
       default:

@@ -29,13 +29,16 @@ SPECS = [
     dict(name="camf_ci_f64", model="camf_ci", users=300, items=80, dims=[8, 8, 8, 8], nnz=6000, F=64, epochs=4, seed=4, order="user_sorted"),
     dict(name="camf_ci_f7_shuffled", model="camf_ci", users=50, items=40, dims=[3, 2], nnz=1800, F=7, epochs=6, seed=5, order="shuffled"),
     dict(name="camf_cu_f128", model="camf_cu", users=200, items=60, dims=[16, 16, 16, 16], nnz=5000, F=128, epochs=3, seed=6, order="user_sorted"),
+    dict(name="camf_cuci_f32", model="camf_cuci", users=150, items=90, dims=[5, 4, 3], nnz=5000, F=32, epochs=4, seed=7, order="shuffled"),
 ]
 
 
 def init_arrays(oracle, model, ts, F, seed):
     g = oracle.JavaRandom(seed)
     shapes = capi.member_shapes(model, ts.num_users, ts.num_items, ts.num_conditions, F)
-    return {k: (g.uniform(s) if k in ("ic_bias", "uc_bias") else g.gaussian(s)) for k, s in shapes.items()}
+    # icBias / ucBias ~ U(0,1) (CAMF_CI.java:58-59, CAMF_CU.java:55-56); CAMF_CUCI's tables are Gaussian (:58-64)
+    return {k: (g.uniform(s) if k in ("ic_bias", "uc_bias") and model != capi.CAMF_CUCI else g.gaussian(s))
+            for k, s in shapes.items()}
 
 
 def make_inputs(oracle, spec):

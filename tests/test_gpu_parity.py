@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 LOSS_RTOL = 1e-11
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "sgd_golden.json")
-CTX_MODELS = (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU)
+CTX_MODELS = (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI)
 
 
 def run_both(oracle, model, ts, F, epochs, seed, mode=capi.EXACT, lr0=capi.f32(0.02), schedule=capi.SCHED_FLAGGED):
@@ -47,7 +47,7 @@ def assert_bit_identical(ref, got):
         assert np.array_equal(ref[k], got[k]), f"{k}: max abs diff {np.abs(ref[k] - got[k]).max()}"
 
 
-@pytest.mark.parametrize("model", [capi.PMF, capi.BIASEDMF, capi.CAMF_CI, capi.CAMF_CU])
+@pytest.mark.parametrize("model", [capi.PMF, capi.BIASEDMF, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI])
 @pytest.mark.parametrize("F", [1, 7, 10, 16, 32, 64, 100, 128, 200])
 def test_exact_mode_bit_identical(oracle, cars_lib, model, F):
     dims = [4, 3, 2] if model in CTX_MODELS else None
@@ -58,7 +58,7 @@ def test_exact_mode_bit_identical(oracle, cars_lib, model, F):
     assert st.num_levels > 1 and st.kernel_launches >= 6
 
 
-@pytest.mark.parametrize("model", [capi.PMF, capi.BIASEDMF, capi.CAMF_CI, capi.CAMF_CU])
+@pytest.mark.parametrize("model", [capi.PMF, capi.BIASEDMF, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI])
 @pytest.mark.parametrize("F", [7, 64, 128])
 @pytest.mark.parametrize("schedule", [capi.SCHED_WAVEFRONT, capi.SCHED_FLAGGED])
 def test_level_schedules_bit_identical(oracle, cars_lib, model, F, schedule):
@@ -79,7 +79,7 @@ def test_exact_mode_orders_and_skew(oracle, cars_lib, order, zipf, schedule):
     np.testing.assert_allclose(gl, rl, rtol=LOSS_RTOL, atol=0)
 
 
-@pytest.mark.parametrize("model", [capi.BIASEDMF, capi.CAMF_CI, capi.CAMF_CU])
+@pytest.mark.parametrize("model", [capi.BIASEDMF, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI])
 @pytest.mark.parametrize("schedule", [capi.SCHED_DATAFLOW, capi.SCHED_FLAGGED])
 def test_flag_schedules_large_random(oracle, cars_lib, model, schedule):
     # enough ratings to keep every resident group busy and to make cross-group dependencies frequent:
@@ -181,7 +181,7 @@ def test_call_order_errors(oracle, cars_lib):
     assert e.value.code == -1
 
 
-@pytest.mark.parametrize("model", [capi.PMF, capi.BIASEDMF, capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU])
+@pytest.mark.parametrize("model", [capi.PMF, capi.BIASEDMF, capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI])
 def test_predict_and_eval_bit_identical(oracle, cars_lib, model):
     dims = [3, 4] if model in CTX_MODELS else None
     ts, test = synth.make_training_set(300, 90, dims, 9000, seed=12, holdout=0.2)

@@ -57,7 +57,7 @@ def py_epoch(model, ts, F, arrs, lr, regU, regI, regB, regC):
     for n in range(ts.nnz):
         u, j, r = int(ts.u[n]), int(ts.j[n]), float(ts.r[n])
         conds = []
-        if ts.ctx is not None and model in (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU):
+        if ts.ctx is not None and model in (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI):
             c = int(ts.ctx[n])
             conds = [int(x) for x in ts.ctx_cond[ts.ctx_ptr[c]:ts.ctx_ptr[c + 1]]]
         dot = 0.0
@@ -79,6 +79,10 @@ def py_epoch(model, ts, F, arrs, lr, regU, regI, regB, regC):
             pred = gm + float(ib[j]) + dot
             for cd in conds:
                 pred += float(uc[u, cd])
+        elif model == capi.CAMF_CUCI:  # CAMF_CUCI.java:69-72
+            pred = gm + dot
+            for cd in conds:
+                pred += float(ic[j, cd]) + float(uc[u, cd])
         e = r - pred
         loss += e * e
         if model in (capi.BIASEDMF, capi.CAMF_C, capi.CAMF_CI):
@@ -110,6 +114,15 @@ def py_epoch(model, ts, F, arrs, lr, regU, regI, regB, regC):
                 s += b * b
                 uc[u, cd] = b + lr * (e - regC * b)
             loss += regC * s
+        if model == capi.CAMF_CUCI:  # CAMF_CUCI.java:98-114
+            su, si = 0.0, 0.0
+            for cd in conds:
+                bu_, bi_ = float(uc[u, cd]), float(ic[j, cd])
+                su += bu_ * bu_
+                si += bi_ * bi_
+                uc[u, cd] = bu_ + lr * (e - regC * bu_)
+                ic[j, cd] = bi_ + lr * (e - regC * bi_)
+            loss += regC * si + regC * su
         for f in range(F):
             p, q = float(P[u, f]), float(Q[j, f])
             du = e * q - regU * p
@@ -127,17 +140,18 @@ def init_arrays(oracle, model, ts, F, seed):
     shapes = capi.member_shapes(model, ts.num_users, ts.num_items, ts.num_conditions, F)
     out = {}
     for k, shp in shapes.items():
-        out[k] = g.uniform(shp) if k in ("ic_bias", "uc_bias") else g.gaussian(shp)
+        # CAMF_CUCI draws its two tables from the Gaussian (CAMF_CUCI.java:58-64)
+        out[k] = g.uniform(shp) if k in ("ic_bias", "uc_bias") and model != capi.CAMF_CUCI else g.gaussian(shp)
     return out
 
 
 REGS = dict(reg_u=capi.f32(1e-4), reg_i=capi.f32(1e-4), reg_b=capi.f32(1e-4), reg_c=capi.f32(1e-3))
 
 
-@pytest.mark.parametrize("model", [capi.PMF, capi.BIASEDMF, capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU])
+@pytest.mark.parametrize("model", [capi.PMF, capi.BIASEDMF, capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI])
 @pytest.mark.parametrize("order", ["user_sorted", "shuffled"])
 def test_oracle_matches_independent_restatement(oracle, model, order):
-    ctxm = model in (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU)
+    ctxm = model in (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI)
     ts, _ = synth.make_training_set(23, 11, [2, 3, 2] if ctxm else None, 400, seed=3, order=order)
     F = 7
     desc = capi.make_desc(ts, model, F, **REGS)

@@ -8,7 +8,7 @@ from carskit_b200 import capi, recommender, synth
 from tests.golden.make_golden import REGS, init_arrays
 
 pytestmark = pytest.mark.gpu
-CTX_MODELS = (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU)
+CTX_MODELS = (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI)
 
 
 def make_queries(ts, test, rng, n):
@@ -29,7 +29,7 @@ def make_queries(ts, test, rng, n):
 
 
 @pytest.mark.parametrize("model,F", [(capi.PMF, 10), (capi.BIASEDMF, 7), (capi.CAMF_C, 16), (capi.CAMF_CI, 64),
-                                     (capi.CAMF_CU, 200)])
+                                     (capi.CAMF_CU, 200), (capi.CAMF_CUCI, 24)])
 def test_topn_identical_to_oracle(oracle, cars_lib, model, F):
     dims = [4, 3] if model in CTX_MODELS else None
     ts, test = synth.make_training_set(300, 700, dims, 20000, seed=31, holdout=0.1)

@@ -15,7 +15,8 @@ CONF = {"num.max.iter": "6", "learn.rate": "2e-2 -max -1 -bold-driver", "reg.lam
 
 
 @pytest.mark.parametrize("name,F,dims", [("pmf", 10, None), ("biasedmf", 10, None), ("camf_c", 10, [7, 7, 2, 3]),
-                                          ("camf_ci", 64, [8, 8, 8, 8]), ("camf_cu", 128, [16, 16])])
+                                          ("camf_ci", 64, [8, 8, 8, 8]), ("camf_cu", 128, [16, 16]),
+                                          ("camf_cuci", 32, [5, 4, 3])])
 def test_execute_matches_oracle_build_model(oracle, cars_lib, name, F, dims):
     model = capi.MODEL_NAMES[name]
     nnz = 3000 if name == "camf_c" else 30000
