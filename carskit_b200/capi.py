@@ -52,6 +52,7 @@ class CarsStats(C.Structure):
         ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("schedule_ms", C.c_double), ("last_epoch_ms", C.c_double),
         ("grid_ctas", C.c_int32), ("block_threads", C.c_int32), ("sm_count", C.c_int32), ("reserved", C.c_int32),
+        ("schedule_copy_ms", C.c_double), ("schedule_levels_ms", C.c_double), ("schedule_pack_ms", C.c_double),
     ]
 
 

@@ -7,6 +7,7 @@
 #include "schedule.cuh"
 #include "schedule_gpu.cuh"
 #include "sgd_kernels.cuh"
+#include "staged_copy.cuh"
 #include "rank_kernels.cuh"
 
 #include <cuda_runtime.h>
@@ -35,6 +36,7 @@ struct cars_handle {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev_beg = nullptr, ev_end = nullptr;
+  StagedCopier copier;  // host <-> device transfers of the caller's (pageable or pinned) arrays
 
   // model
   DeviceModel m{};
@@ -361,6 +363,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   }
   CUDA_TRY_H(cudaEventCreate(&h->ev_beg));
   CUDA_TRY_H(cudaEventCreate(&h->ev_end));
+  CUDA_TRY_H(h->copier.init(h->device));
 
   const int F = desc->num_factors;
   const int Fp = (F + 1) & ~1;
@@ -500,13 +503,14 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     if (h->loss_blocks > 1024) h->loss_blocks = 1024;
     CUDA_TRY_H(cudaStreamSynchronize(h->stream));  // recs / chunk_start die at the end of this block
   } else if (h->flagged) {
-    // level assignment on the host (one sequential pass, overlapped with the H2D copies), sort on the device
+    // chains, dependency levels (Kahn by frontiers) and the level sort all run on the device (schedule_gpu.cuh)
     CUDA_TRY_H(dev_alloc(&h->d_rec, (size_t)nnz));
     h->flags_words = 64 + I + U;
     CUDA_TRY_H(dev_alloc(&h->d_flags, h->flags_words));
     FlaggedBuild fb;
     cudaError_t be = build_flagged_on_device(desc->num_users, desc->num_items, desc->num_contexts, nnz, desc->u, desc->j,
-                                             has_ctx ? desc->ctx : nullptr, desc->r, h->stream, h->sm_count, h->d_rec, &fb);
+                                             has_ctx ? desc->ctx : nullptr, desc->r, h->stream, h->sm_count, h->copier,
+                                             h->d_rec, &fb);
     if (fb.bad_index >= 0) {
       const int64_t n = fb.bad_index;
       fail(h, CARS_E_INVALID, "rating %lld has an id out of range (u=%d j=%d ctx=%d)", (long long)n, desc->u[n], desc->j[n],
@@ -520,6 +524,10 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     h->num_levels = fb.num_levels;
     h->max_level_size = fb.max_level_size;
     h->st.h2d_bytes += fb.h2d_bytes;
+    h->st.kernel_launches += fb.kernel_launches;
+    h->st.schedule_copy_ms = fb.copy_ms;
+    h->st.schedule_levels_ms = fb.levels_ms;
+    h->st.schedule_pack_ms = fb.pack_ms;
     h->st.schedule_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   } else {
     std::vector<int64_t> level_start;
@@ -599,8 +607,15 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
 // ------------------------------------------------------------------------------------------------
 // upload / download
 // ------------------------------------------------------------------------------------------------
-static int copy_rows(cars_handle* h, bool to_device, double* dev, double* host, size_t rows, int F, int Fp) {
+static int copy_rows(cars_handle* h, bool to_device, double* dev, double* host, size_t rows, int F, int Fp,
+                     std::vector<CopySeg>* segs) {
   if (rows == 0) return CARS_OK;
+  if (F == Fp) {  // contiguous on both sides: goes with the other arrays through the staged copier
+    segs->push_back(CopySeg{dev, host, rows * (size_t)F * 8});
+    if (to_device) h->st.h2d_bytes += (int64_t)rows * F * 8;
+    else h->st.d2h_bytes += (int64_t)rows * F * 8;
+    return CARS_OK;
+  }
   if (to_device) {
     if (F != Fp) CUDA_TRY(h, cudaMemsetAsync(dev, 0, rows * Fp * 8, h->stream));
     CUDA_TRY(h, cudaMemcpy2DAsync(dev, (size_t)Fp * 8, host, (size_t)F * 8, (size_t)F * 8, rows, cudaMemcpyHostToDevice, h->stream));
@@ -612,15 +627,11 @@ static int copy_rows(cars_handle* h, bool to_device, double* dev, double* host, 
   return CARS_OK;
 }
 
-static int copy_vec(cars_handle* h, bool to_device, double* dev, double* host, size_t n) {
+static int copy_vec(cars_handle* h, bool to_device, double* dev, double* host, size_t n, std::vector<CopySeg>* segs) {
   if (n == 0) return CARS_OK;
-  if (to_device) {
-    CUDA_TRY(h, cudaMemcpyAsync(dev, host, n * 8, cudaMemcpyHostToDevice, h->stream));
-    h->st.h2d_bytes += (int64_t)n * 8;
-  } else {
-    CUDA_TRY(h, cudaMemcpyAsync(host, dev, n * 8, cudaMemcpyDeviceToHost, h->stream));
-    h->st.d2h_bytes += (int64_t)n * 8;
-  }
+  segs->push_back(CopySeg{dev, host, n * 8});
+  if (to_device) h->st.h2d_bytes += (int64_t)n * 8;
+  else h->st.d2h_bytes += (int64_t)n * 8;
   return CARS_OK;
 }
 
@@ -638,14 +649,17 @@ static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device) 
   for (const Item& it : need)
     if (it.dev && !it.host) return fail(h, CARS_E_INVALID, "model array %s is required for this model but NULL", it.name);
   int rc;
-  if ((rc = copy_rows(h, to_device, m.P, a->P, U, m.F, m.Fp))) return rc;
-  if ((rc = copy_rows(h, to_device, m.Q, a->Q, I, m.F, m.Fp))) return rc;
-  if (m.user_bias && (rc = copy_vec(h, to_device, m.user_bias, a->user_bias, U))) return rc;
-  if (m.item_bias && (rc = copy_vec(h, to_device, m.item_bias, a->item_bias, I))) return rc;
-  if (m.cond_bias && (rc = copy_vec(h, to_device, m.cond_bias, a->cond_bias, C))) return rc;
-  if (m.ic_bias && (rc = copy_vec(h, to_device, m.ic_bias, a->ic_bias, I * C))) return rc;
-  if (m.uc_bias && (rc = copy_vec(h, to_device, m.uc_bias, a->uc_bias, U * C))) return rc;
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  std::vector<CopySeg> segs;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // the staged copies run on the copier's own streams
+  if ((rc = copy_rows(h, to_device, m.P, a->P, U, m.F, m.Fp, &segs))) return rc;
+  if ((rc = copy_rows(h, to_device, m.Q, a->Q, I, m.F, m.Fp, &segs))) return rc;
+  if (m.user_bias && (rc = copy_vec(h, to_device, m.user_bias, a->user_bias, U, &segs))) return rc;
+  if (m.item_bias && (rc = copy_vec(h, to_device, m.item_bias, a->item_bias, I, &segs))) return rc;
+  if (m.cond_bias && (rc = copy_vec(h, to_device, m.cond_bias, a->cond_bias, C, &segs))) return rc;
+  if (m.ic_bias && (rc = copy_vec(h, to_device, m.ic_bias, a->ic_bias, I * C, &segs))) return rc;
+  if (m.uc_bias && (rc = copy_vec(h, to_device, m.uc_bias, a->uc_bias, U * C, &segs))) return rc;
+  CUDA_TRY(h, h->copier.run(segs.data(), (int)segs.size(), to_device));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // the strided (odd F) row copies
   return CARS_OK;
 }
 
@@ -1071,6 +1085,7 @@ extern "C" void cars_destroy(cars_handle* h) {
   cudaFree(h->d_item_old);
   cudaFree(h->d_barrier); cudaFree(h->d_partial); cudaFree(h->d_loss);
   if (h->h_loss) cudaFreeHost(h->h_loss);
+  h->copier.destroy();
   if (h->ev_beg) cudaEventDestroy(h->ev_beg);
   if (h->ev_end) cudaEventDestroy(h->ev_end);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

@@ -1,22 +1,29 @@
-// schedule_gpu.cuh -- K7f on the device: building the level-sorted record stream of the flagged wavefront
-// without a host-side sort.
+// schedule_gpu.cuh -- K7f: the level-sorted record stream of the flagged wavefront, built on the device.
 //
-// Host part (inherently sequential, one pass in reference order, a few ns per rating): for every rating its
-// dependency level  level(n) = 1 + max(level(prev rating of u), level(prev rating of j))  and its positions
-// ku / kj in the user's / item's chain.  The pass is chunked; each chunk is written straight into pinned
-// staging buffers and copied to the device while the next chunk is being computed.  The caller's own
-// u / j / ctx / r arrays are copied by a second host thread on a second stream at the same time.
-// Device part: stable LSD radix sort of (level, n) pairs (CUB), then one gather kernel that packs the
-// 32-byte RatingRec stream in level order.
+// Needed per rating n (reference order): ku / kj = its position in its user's / item's chain, and
+//   level(n) = 1 + max(level(prev rating of u), level(prev rating of j))
+// -- the longest path to n in the conflict DAG (schedule.cuh).  Everything runs on the GPU; the host only
+// moves the caller's four arrays across PCIe (StagedCopier):
+//   1. validate_ids_kernel      range check of u / j / ctx (first bad index via atomicMin)
+//   2. CUB stable radix sort of (u, n) and of (j, n): neighbours in sorted order are chain neighbours
+//      -> chain_heads_kernel / chain_link_kernel give ku, kj and each rating's successor in both chains
+//   3. kahn_roots_kernel + kahn_levels_kernel: Kahn's algorithm by frontiers on a persistent cooperative
+//      grid -- frontier L holds exactly the ratings of level L (in-degree <= 2, counted down with atomics);
+//      one grid barrier per level, ~4 us each (3 268 levels at config 3)
+//   4. CUB stable radix sort of (level, n), gather_recs_kernel packs the 32-byte RatingRec stream.
+// The stable sort makes the stream independent of the order in which Kahn's frontiers were filled.
+// The previous host pass (one thread, 8 ns per rating: 0.82 s at 100 M ratings) is kept behind
+// CARS_LEVELS=host for A/B measurements (build_flagged_host_levels).
 #pragma once
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
-#include <thread>
 #include <vector>
 
 #include "sgd_kernels.cuh"
+#include "staged_copy.cuh"
 
 namespace cars {
 
@@ -42,45 +49,210 @@ __global__ void __launch_bounds__(256) gather_recs_kernel(RatingSoA s, const uin
   }
 }
 
-// Returns cudaSuccess, or the failing CUDA error; *bad_index >= 0 when an id is out of range.
+// first rating with an id out of range (unsigned compare also rejects negatives); *bad starts at ~0
+__global__ void __launch_bounds__(256) validate_ids_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ j,
+                                                           const int32_t* __restrict__ ctx, int64_t n, uint32_t num_users,
+                                                           uint32_t num_items, uint32_t num_contexts,
+                                                           unsigned long long* bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if ((uint32_t)u[i] >= num_users || (uint32_t)j[i] >= num_items || (ctx && (uint32_t)ctx[i] >= num_contexts))
+      atomicMin(bad, (unsigned long long)i);
+}
+
+// skey / ord: the ratings stably sorted by one id (user or item).  start[key] = first sorted position.
+__global__ void __launch_bounds__(256) chain_heads_kernel(const uint32_t* __restrict__ skey, int64_t n, uint32_t* __restrict__ start) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride)
+    if (p == 0 || skey[p - 1] != skey[p]) start[skey[p]] = (uint32_t)p;
+}
+// kpos[n] = earlier ratings of the same id; succ[2 n + which] = the next rating of the same id, or -1
+__global__ void __launch_bounds__(256) chain_link_kernel(const uint32_t* __restrict__ skey, const uint32_t* __restrict__ ord,
+                                                         int64_t n, const uint32_t* __restrict__ start,
+                                                         int32_t* __restrict__ kpos, int32_t* __restrict__ succ, int which) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    const uint32_t key = skey[p];
+    const uint32_t me = ord[p];
+    kpos[me] = (int32_t)((uint32_t)p - start[key]);
+    succ[2 * (int64_t)me + which] = (p + 1 < n && skey[p + 1] == key) ? (int32_t)ord[p + 1] : -1;
+  }
+}
+
+struct KahnCtl {  // zero-initialised
+  unsigned cnt[3];  // frontier sizes, rotating: level L reads cnt[L % 3], fills cnt[(L + 1) % 3]
+  unsigned barrier;
+  unsigned num_levels;
+  unsigned max_level;
+  unsigned long long processed;
+};
+
+// in-degree of every rating in the conflict DAG (0, 1 or 2); the roots form frontier 1
+__global__ void __launch_bounds__(256) kahn_roots_kernel(const int32_t* __restrict__ ku, const int32_t* __restrict__ kj, int64_t n,
+                                                         int* __restrict__ indeg, uint32_t* __restrict__ frontier, KahnCtl* ctl) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
+    const int64_t i = i0 + threadIdx.x;
+    int d = -1;
+    if (i < n) {
+      d = (ku[i] > 0) + (kj[i] > 0);
+      indeg[i] = d;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, d == 0);
+    if (m) {
+      const int lane = threadIdx.x & 31;
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(&ctl->cnt[1], (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (d == 0) frontier[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+    }
+  }
+}
+
+__device__ __forceinline__ void kahn_grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    red_release_add_u32(counter, 1u);
+    while ((int)(ld_acquire_u32(counter) - target) < 0) {  // wrap-safe
+    }
+  }
+  __syncthreads();
+}
+
+// Persistent cooperative grid.  Level L: every rating of frontier L gets level L and counts its (at most two)
+// successors' in-degree down; a successor that reaches 0 joins frontier L + 1.  fr0 / fr1 alternate.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) kahn_levels_kernel(const int2* __restrict__ succ, int* __restrict__ indeg,
+                                                                 int32_t* __restrict__ level, uint32_t* fr0, uint32_t* fr1,
+                                                                 KahnCtl* ctl) {
+  __shared__ unsigned s_cnt, s_base;
+  __shared__ unsigned s_warp[THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned maxc = 0;
+  unsigned long long total = 0;
+  unsigned lvl = 1;
+  for (;; lvl++) {
+    const unsigned count = ld_relaxed_u32(&ctl->cnt[lvl % 3]);
+    if (count == 0) break;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      st_relaxed_u32(&ctl->cnt[(lvl + 2) % 3], 0u);  // read one level ago, filled one level from now
+      if (count > maxc) maxc = count;
+      total += count;
+    }
+    const uint32_t* cur = (lvl & 1) ? fr0 : fr1;
+    uint32_t* nxt = (lvl & 1) ? fr1 : fr0;
+    unsigned* ncnt = &ctl->cnt[(lvl + 1) % 3];
+    for (unsigned i0 = blockIdx.x * THREADS; i0 < count; i0 += gridDim.x * THREADS) {
+      const unsigned i = i0 + threadIdx.x;
+      int a = -1, b = -1;
+      if (i < count) {
+        const uint32_t n = __ldcg(cur + i);  // written by other SMs one level ago: L2, not L1
+        level[n] = (int32_t)lvl;
+        const int2 s = __ldg(succ + n);
+        if (s.x >= 0 && atomicSub(indeg + s.x, 1) == 1) a = s.x;
+        if (s.y >= 0 && atomicSub(indeg + s.y, 1) == 1) b = s.y;
+      }
+      // CTA-aggregated append: warp scan -> shared -> one global atomic per CTA
+      const unsigned k = (unsigned)(a >= 0) + (unsigned)(b >= 0);
+      unsigned incl = k;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) s_warp[warp] = incl;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int w = 0; w < THREADS / 32; w++) {
+          const unsigned t = s_warp[w];
+          s_warp[w] = run;
+          run += t;
+        }
+        s_cnt = run;
+        if (run) s_base = atomicAdd(ncnt, run);
+      }
+      __syncthreads();
+      if (k) {
+        unsigned off = s_base + s_warp[warp] + incl - k;
+        if (a >= 0) nxt[off++] = (uint32_t)a;
+        if (b >= 0) nxt[off] = (uint32_t)b;
+      }
+      __syncthreads();  // s_warp / s_base are rewritten by the next pass
+    }
+    kahn_grid_barrier(&ctl->barrier, lvl * gridDim.x);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctl->num_levels = lvl - 1;
+    ctl->max_level = maxc;
+    ctl->processed = total;
+  }
+}
+
 struct FlaggedBuild {
   int64_t num_levels = 0, max_level_size = 0, bad_index = -1;
   int64_t h2d_bytes = 0;
-  double host_ms = 0.0;
+  int64_t kernel_launches = 0;
+  double copy_ms = 0.0, levels_ms = 0.0, pack_ms = 0.0;
 };
 
-inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items, int32_t num_contexts, int64_t nnz,
-                                           const int32_t* u, const int32_t* j, const int32_t* ctx, const double* r,
-                                           cudaStream_t stream, int sm_count, RatingRec* d_rec, FlaggedBuild* info) {
-  if (nnz == 0) return cudaSuccess;
-  const int64_t CH = 1 << 22;  // ratings per staging chunk
-  struct Stage {
-    int32_t* i32 = nullptr;  // [3 x CH] level ku kj
-    cudaEvent_t ev = nullptr;
-    bool used = false;
-  } st[2];
-  RatingSoA d;
-  uint32_t *d_idx_in = nullptr, *d_idx_out = nullptr, *d_key_out = nullptr;
-  void* d_temp = nullptr;
-  cudaStream_t copy_stream = nullptr;
-  cudaError_t e = cudaSuccess;
+// Level pass on the host (the pre-Kahn builder): fills level / ku / kj for ratings in reference order.
+inline bool build_flagged_host_levels(int32_t num_users, int32_t num_items, int64_t nnz, const int32_t* u, const int32_t* j,
+                                      int32_t* level, int32_t* ku, int32_t* kj, int64_t* num_levels, int64_t* max_level) {
   struct Chain {
     int32_t level;
     uint32_t count;
   };
-  std::vector<Chain> tu, tj;  // per user / per item: level of its last rating, ratings seen so far
-  std::vector<int64_t> level_count;
-  std::thread copier;
-  cudaError_t copy_err = cudaSuccess;
-  auto cleanup = [&]() {
-    if (copier.joinable()) copier.join();
-    for (auto& s : st) {
-      if (s.i32) cudaFreeHost(s.i32);
-      if (s.ev) cudaEventDestroy(s.ev);
+  try {
+    std::vector<Chain> tu((size_t)num_users, Chain{0, 0u}), tj((size_t)num_items, Chain{0, 0u});
+    std::vector<int64_t> level_count(1024, 0);
+    int32_t nl = 0;
+    for (int64_t n = 0; n < nnz; n++) {
+      Chain& a = tu[(size_t)u[n]];
+      Chain& b = tj[(size_t)j[n]];
+      const int32_t l = 1 + (a.level > b.level ? a.level : b.level);
+      a.level = l;
+      b.level = l;
+      if (l > nl) {
+        nl = l;
+        if ((size_t)l >= level_count.size()) level_count.resize((size_t)l * 2, 0);
+      }
+      level_count[l]++;
+      level[n] = l;
+      ku[n] = (int32_t)a.count++;
+      kj[n] = (int32_t)b.count++;
     }
-    if (copy_stream) cudaStreamDestroy(copy_stream);
+    *num_levels = nl;
+    *max_level = 0;
+    for (int32_t l = 1; l <= nl; l++)
+      if (level_count[l] > *max_level) *max_level = level_count[l];
+    return true;
+  } catch (...) {
+    return false;
+  }
+}
+
+// Returns cudaSuccess, or the failing CUDA error; info->bad_index >= 0 when an id is out of range.
+inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items, int32_t num_contexts, int64_t nnz,
+                                           const int32_t* u, const int32_t* j, const int32_t* ctx, const double* r,
+                                           cudaStream_t stream, int sm_count, StagedCopier& copier, RatingRec* d_rec,
+                                           FlaggedBuild* info) {
+  if (nnz == 0) return cudaSuccess;
+  RatingSoA d;
+  uint32_t *d_idx = nullptr, *d_ord = nullptr, *d_skey = nullptr, *d_start = nullptr, *d_fr0 = nullptr, *d_fr1 = nullptr;
+  int32_t* d_succ = nullptr;
+  int* d_indeg = nullptr;
+  KahnCtl* d_ctl = nullptr;
+  unsigned long long* d_bad = nullptr;
+  void* d_temp = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaError_t e = cudaSuccess;
+  auto cleanup = [&]() {
     cudaFree(d.u); cudaFree(d.j); cudaFree(d.ctx); cudaFree(d.level); cudaFree(d.ku); cudaFree(d.kj); cudaFree(d.r);
-    cudaFree(d_idx_in); cudaFree(d_idx_out); cudaFree(d_key_out); cudaFree(d_temp);
+    cudaFree(d_idx); cudaFree(d_ord); cudaFree(d_skey); cudaFree(d_start); cudaFree(d_fr0); cudaFree(d_fr1);
+    cudaFree(d_succ); cudaFree(d_indeg); cudaFree(d_ctl); cudaFree(d_bad); cudaFree(d_temp);
+    for (auto& x : ev)
+      if (x) cudaEventDestroy(x);
   };
 #define SG_TRY(x)              \
   do {                         \
@@ -91,104 +263,139 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
     }                          \
   } while (0)
 
-  const int64_t ch = nnz < CH ? nnz : CH;
-  for (auto& s : st) {
-    SG_TRY(cudaMallocHost((void**)&s.i32, (size_t)ch * 3 * sizeof(int32_t)));
-    SG_TRY(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+  const size_t N = (size_t)nnz;
+  const size_t ids = (size_t)(num_users > num_items ? num_users : num_items);
+  const size_t fcap = (size_t)(num_users < num_items ? num_users : num_items);  // a level has distinct users and items
+  for (auto& x : ev) SG_TRY(cudaEventCreate(&x));
+  SG_TRY(cudaMalloc((void**)&d.u, N * 4));
+  SG_TRY(cudaMalloc((void**)&d.j, N * 4));
+  if (ctx) SG_TRY(cudaMalloc((void**)&d.ctx, N * 4));
+  SG_TRY(cudaMalloc((void**)&d.level, N * 4));
+  SG_TRY(cudaMalloc((void**)&d.ku, N * 4));
+  SG_TRY(cudaMalloc((void**)&d.kj, N * 4));
+  SG_TRY(cudaMalloc((void**)&d.r, N * 8));
+  SG_TRY(cudaMalloc((void**)&d_idx, N * 4));
+  SG_TRY(cudaMalloc((void**)&d_ord, N * 4));
+  SG_TRY(cudaMalloc((void**)&d_skey, N * 4));
+  SG_TRY(cudaMalloc((void**)&d_bad, 8));
+
+  // ---- the caller's arrays cross PCIe ------------------------------------------------------------------
+  SG_TRY(cudaEventRecord(ev[0], stream));
+  {
+    CopySeg segs[4] = {{d.u, (void*)u, N * 4}, {d.j, (void*)j, N * 4}, {d.ctx, (void*)ctx, ctx ? N * 4 : 0}, {d.r, (void*)r, N * 8}};
+    SG_TRY(copier.run(segs, 4, true));
   }
-  SG_TRY(cudaMalloc((void**)&d.u, (size_t)nnz * 4));
-  SG_TRY(cudaMalloc((void**)&d.j, (size_t)nnz * 4));
-  if (ctx) SG_TRY(cudaMalloc((void**)&d.ctx, (size_t)nnz * 4));
-  SG_TRY(cudaMalloc((void**)&d.level, (size_t)nnz * 4));
-  SG_TRY(cudaMalloc((void**)&d.ku, (size_t)nnz * 4));
-  SG_TRY(cudaMalloc((void**)&d.kj, (size_t)nnz * 4));
-  SG_TRY(cudaMalloc((void**)&d.r, (size_t)nnz * 8));
-  SG_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-  try {
-    tu.assign((size_t)num_users, Chain{0, 0u});
-    tj.assign((size_t)num_items, Chain{0, 0u});
-    level_count.assign(1024, 0);
-  } catch (...) {
-    cleanup();
-    return cudaErrorMemoryAllocation;
-  }
-  // second host thread: the caller's arrays go to the device as they are (pageable copies are staged by the
-  // driver and block the issuing thread, hence a thread of their own)
-  int dev = 0;
-  SG_TRY(cudaGetDevice(&dev));
-  copier = std::thread([&, dev]() {
-    cudaError_t ce = cudaSetDevice(dev);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d.u, u, (size_t)nnz * 4, cudaMemcpyHostToDevice, copy_stream);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d.j, j, (size_t)nnz * 4, cudaMemcpyHostToDevice, copy_stream);
-    if (ce == cudaSuccess && ctx) ce = cudaMemcpyAsync(d.ctx, ctx, (size_t)nnz * 4, cudaMemcpyHostToDevice, copy_stream);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d.r, r, (size_t)nnz * 8, cudaMemcpyHostToDevice, copy_stream);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(copy_stream);
-    copy_err = ce;
-  });
   info->h2d_bytes += nnz * (ctx ? 20 : 16);
-
-  int32_t num_levels = 0;
-  for (int64_t base = 0, c = 0; base < nnz; base += ch, c++) {
-    Stage& s = st[c & 1];
-    if (s.used) SG_TRY(cudaEventSynchronize(s.ev));
-    const int64_t len = (nnz - base < ch) ? nnz - base : ch;
-    int32_t *sl = s.i32, *sku = s.i32 + ch, *skj = s.i32 + 2 * ch;
-    for (int64_t i = 0; i < len; i++) {
-      const int64_t n = base + i;
-      const int32_t uu = u[n], jj = j[n];
-      if ((uint32_t)uu >= (uint32_t)num_users || (uint32_t)jj >= (uint32_t)num_items ||
-          (ctx && (uint32_t)ctx[n] >= (uint32_t)num_contexts)) {
-        info->bad_index = n;
-        cudaStreamSynchronize(stream);
-        cleanup();
-        return cudaSuccess;
-      }
-      Chain& a = tu[(size_t)uu];
-      Chain& b = tj[(size_t)jj];
-      const int32_t l = 1 + (a.level > b.level ? a.level : b.level);
-      a.level = l;
-      b.level = l;
-      if (l > num_levels) {
-        num_levels = l;
-        if ((size_t)l >= level_count.size()) level_count.resize((size_t)l * 2, 0);
-      }
-      level_count[l]++;
-      sl[i] = l;
-      sku[i] = (int32_t)a.count++;
-      skj[i] = (int32_t)b.count++;
-    }
-    SG_TRY(cudaMemcpyAsync(d.level + base, sl, (size_t)len * 4, cudaMemcpyHostToDevice, stream));
-    SG_TRY(cudaMemcpyAsync(d.ku + base, sku, (size_t)len * 4, cudaMemcpyHostToDevice, stream));
-    SG_TRY(cudaMemcpyAsync(d.kj + base, skj, (size_t)len * 4, cudaMemcpyHostToDevice, stream));
-    SG_TRY(cudaEventRecord(s.ev, stream));
-    s.used = true;
-    info->h2d_bytes += len * 12;
-  }
-  copier.join();
-  if (copy_err != cudaSuccess) {
-    cleanup();
-    return copy_err;
-  }
-  info->num_levels = num_levels;
-  for (int32_t l = 1; l <= num_levels; l++)
-    if (level_count[l] > info->max_level_size) info->max_level_size = level_count[l];
-
-  // stable sort of (level, n) on the device, then pack the records in that order
-  int bits = 1;
-  while ((1ll << bits) <= num_levels) bits++;
-  SG_TRY(cudaMalloc((void**)&d_idx_in, (size_t)nnz * 4));
-  SG_TRY(cudaMalloc((void**)&d_idx_out, (size_t)nnz * 4));
-  SG_TRY(cudaMalloc((void**)&d_key_out, (size_t)nnz * 4));
-  iota_kernel<<<sm_count * 8, 256, 0, stream>>>(d_idx_in, nnz);
+  SG_TRY(cudaEventRecord(ev[1], stream));
+  const int blocks = sm_count * 8;
+  SG_TRY(cudaMemsetAsync(d_bad, 0xff, 8, stream));
+  validate_ids_kernel<<<blocks, 256, 0, stream>>>(d.u, d.j, d.ctx, nnz, (uint32_t)num_users, (uint32_t)num_items,
+                                                  (uint32_t)num_contexts, d_bad);
   SG_TRY(cudaGetLastError());
-  size_t temp_bytes = 0;
-  const uint32_t* keys_in = reinterpret_cast<const uint32_t*>(d.level);
-  SG_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, d_key_out, d_idx_in, d_idx_out, nnz, 0, bits, stream));
-  SG_TRY(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 1));
-  SG_TRY(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, keys_in, d_key_out, d_idx_in, d_idx_out, nnz, 0, bits, stream));
-  gather_recs_kernel<<<sm_count * 8, 256, 0, stream>>>(d, d_idx_out, nnz, d_rec);
-  SG_TRY(cudaGetLastError());
+  unsigned long long bad = 0;
+  SG_TRY(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, stream));
   SG_TRY(cudaStreamSynchronize(stream));
+  info->kernel_launches += 1;
+  if (bad != ~0ull) {
+    info->bad_index = (int64_t)bad;
+    cleanup();
+    return cudaSuccess;
+  }
+
+  iota_kernel<<<blocks, 256, 0, stream>>>(d_idx, nnz);
+  SG_TRY(cudaGetLastError());
+  info->kernel_launches += 1;
+  size_t temp_bytes = 0, need = 0;
+  auto bits_for = [](int64_t n_values) {
+    int b = 1;
+    while ((1ll << b) < n_values) b++;
+    return b;
+  };
+  const bool host_levels = [] {
+    const char* s = getenv("CARS_LEVELS");
+    return s && strcmp(s, "host") == 0;
+  }();
+  if (!host_levels) {
+    SG_TRY(cudaMalloc((void**)&d_start, ids * 4));
+    SG_TRY(cudaMalloc((void**)&d_succ, N * 8));
+    SG_TRY(cudaMalloc((void**)&d_indeg, N * 4));
+    SG_TRY(cudaMalloc((void**)&d_fr0, (fcap + 1) * 4));
+    SG_TRY(cudaMalloc((void**)&d_fr1, (fcap + 1) * 4));
+    SG_TRY(cudaMalloc((void**)&d_ctl, sizeof(KahnCtl)));
+    SG_TRY(cudaMemsetAsync(d_ctl, 0, sizeof(KahnCtl), stream));
+    // chains: stable sort by user, then by item
+    const int bu = bits_for(num_users), bj = bits_for(num_items);
+    SG_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t*)d.u, d_skey, d_idx, d_ord, nnz, 0, bu, stream));
+    SG_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, (const uint32_t*)d.j, d_skey, d_idx, d_ord, nnz, 0, bj, stream));
+    if (need > temp_bytes) temp_bytes = need;
+    SG_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, (const uint32_t*)d.level, d_skey, d_idx, d_ord, nnz, 0, 32, stream));
+    if (need > temp_bytes) temp_bytes = need;
+    SG_TRY(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 1));
+    for (int which = 0; which < 2; which++) {
+      const uint32_t* keys = (const uint32_t*)(which == 0 ? d.u : d.j);
+      size_t tb = temp_bytes;
+      SG_TRY(cub::DeviceRadixSort::SortPairs(d_temp, tb, keys, d_skey, d_idx, d_ord, nnz, 0, which == 0 ? bu : bj, stream));
+      chain_heads_kernel<<<blocks, 256, 0, stream>>>(d_skey, nnz, d_start);
+      SG_TRY(cudaGetLastError());
+      chain_link_kernel<<<blocks, 256, 0, stream>>>(d_skey, d_ord, nnz, d_start, which == 0 ? d.ku : d.kj, d_succ, which);
+      SG_TRY(cudaGetLastError());
+      info->kernel_launches += 3;
+    }
+    kahn_roots_kernel<<<blocks, 256, 0, stream>>>(d.ku, d.kj, nnz, d_indeg, d_fr0, d_ctl);
+    SG_TRY(cudaGetLastError());
+    {
+      constexpr int KT = 512;
+      const int2* succ2 = reinterpret_cast<const int2*>(d_succ);
+      void* args[] = {(void*)&succ2, (void*)&d_indeg, (void*)&d.level, (void*)&d_fr0, (void*)&d_fr1, (void*)&d_ctl};
+      SG_TRY(cudaLaunchCooperativeKernel((const void*)kahn_levels_kernel<KT>, dim3(sm_count), dim3(KT), args, 0, stream));
+    }
+    info->kernel_launches += 2;
+    KahnCtl ctl;
+    SG_TRY(cudaMemcpyAsync(&ctl, d_ctl, sizeof ctl, cudaMemcpyDeviceToHost, stream));
+    SG_TRY(cudaEventRecord(ev[2], stream));
+    SG_TRY(cudaStreamSynchronize(stream));
+    if ((int64_t)ctl.processed != nnz) {  // cannot happen for chains built above; refuse rather than train garbage
+      cleanup();
+      return cudaErrorUnknown;
+    }
+    info->num_levels = ctl.num_levels;
+    info->max_level_size = ctl.max_level;
+  } else {
+    std::vector<int32_t> hl, hku, hkj;
+    try {
+      hl.resize(N); hku.resize(N); hkj.resize(N);
+    } catch (...) {
+      cleanup();
+      return cudaErrorMemoryAllocation;
+    }
+    if (!build_flagged_host_levels(num_users, num_items, nnz, u, j, hl.data(), hku.data(), hkj.data(), &info->num_levels,
+                                   &info->max_level_size)) {
+      cleanup();
+      return cudaErrorMemoryAllocation;
+    }
+    CopySeg segs[3] = {{d.level, hl.data(), N * 4}, {d.ku, hku.data(), N * 4}, {d.kj, hkj.data(), N * 4}};
+    SG_TRY(copier.run(segs, 3, true));
+    info->h2d_bytes += nnz * 12;
+    SG_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t*)d.level, d_skey, d_idx, d_ord, nnz, 0, 32, stream));
+    SG_TRY(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 1));
+    SG_TRY(cudaEventRecord(ev[2], stream));
+  }
+
+  // ---- stable sort of (level, n), then pack the records in that order --------------------------------------
+  {
+    size_t tb = temp_bytes;
+    SG_TRY(cub::DeviceRadixSort::SortPairs(d_temp, tb, (const uint32_t*)d.level, d_skey, d_idx, d_ord, nnz, 0,
+                                           bits_for(info->num_levels + 1), stream));
+  }
+  gather_recs_kernel<<<blocks, 256, 0, stream>>>(d, d_ord, nnz, d_rec);
+  SG_TRY(cudaGetLastError());
+  info->kernel_launches += 2;
+  SG_TRY(cudaEventRecord(ev[3], stream));
+  SG_TRY(cudaStreamSynchronize(stream));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) info->copy_ms = ms;
+  if (cudaEventElapsedTime(&ms, ev[1], ev[2]) == cudaSuccess) info->levels_ms = ms;
+  if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) info->pack_ms = ms;
   cleanup();
 #undef SG_TRY
   return cudaSuccess;

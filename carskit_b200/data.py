@@ -104,3 +104,82 @@ def read_binary_csv(path: str) -> Tuple[TrainingSet, RatingDao]:
                      ctx_cond=np.asarray(flat, dtype=np.int32), global_mean=total / len(r) if len(r) else 0.0)
     ts.pair_ids = ui  # the CRS row (user-item pair id) of every entry, for callers that need it
     return ts, dao
+
+
+# ------------------------------------------------------------------------------------------------------
+# k-fold assignment: carskit.data.processor.DataSplitter (src/carskit/data/processor/DataSplitter.java)
+# ------------------------------------------------------------------------------------------------------
+_JR_MULT = np.uint64(0x5DEECE66D)
+_JR_ADD = np.uint64(0xB)
+_JR_MASK = np.uint64((1 << 48) - 1)
+
+
+def java_random_doubles(seed: int, n: int) -> np.ndarray:
+    """The first n values of `new java.util.Random(seed).nextDouble()` -- what happy.coding.math.Randoms.uniform()
+    returns after Randoms.seed(seed) (CARSKit.java:174).  The 48-bit LCG
+    s' = s * 0x5DEECE66D + 0xB is jumped ahead in closed form (s_k = A_k s_0 + C_k, all arithmetic wrapping
+    mod 2^64 and masked to 48 bits), so the whole sequence is vectorised:
+    nextDouble = ((next(26) << 27) + next(27)) * 2^-53, two LCG steps per double."""
+    if n == 0:
+        return np.empty(0, dtype=np.float64)
+    s0 = np.uint64((int(seed) ^ 0x5DEECE66D) & ((1 << 48) - 1))
+    steps = 2 * n
+    with np.errstate(over="ignore"):
+        a_pow = np.empty(steps + 1, dtype=np.uint64)  # A_k = a^k
+        a_pow[0] = 1
+        a_pow[1:] = _JR_MULT
+        np.multiply.accumulate(a_pow, out=a_pow)
+        c_sum = np.add.accumulate(a_pow[:-1]) * _JR_ADD  # C_k = c * (a^0 + .. + a^(k-1)), k = 1..steps
+        states = (a_pow[1:] * s0 + c_sum) & _JR_MASK
+    hi = (states[0::2] >> np.uint64(48 - 26)).astype(np.int64)
+    lo = (states[1::2] >> np.uint64(48 - 27)).astype(np.int64)
+    return ((hi << 27) + lo).astype(np.float64) * (1.0 / (1 << 53))
+
+
+class DataSplitter:
+    """`new DataSplitter(rateMatrix, kfold)` + getKthFold(k) (DataSplitter.java:46-50, 68-133) over the flattened
+    CRS entries of a TrainingSet (entry f = the f-th (user-item pair, context) cell in iteration order).
+
+    splitFolds: rdm[i] = Randoms.uniform(); fold[i] = (int)(i / (numRates / numFold)) + 1 (:108-118);
+    Sortor.quickSort(rdm, fold, ..) sorts rdm ascending carrying fold (:120) -- an argsort, as long as no two
+    draws are equal (checked); the f-th CRS entry then gets fold[f] (:125-132).  getKthFold(k): the entries
+    labelled k are the TEST set, the others the training set, order kept (reshape drops the zeroed cells).
+    `seed` = evaluation.setup's --rand-seed; the reference seeds the generator right before the splitter draws
+    (CARSKit.java:174 precedes :393), so the draws are the first numRates doubles of Random(seed)."""
+
+    def __init__(self, ts: TrainingSet, kfold: int, seed: int):
+        self.ts = ts
+        n = ts.nnz
+        self.numFold = min(int(kfold), n) if n else int(kfold)
+        if self.numFold < 1:
+            raise ValueError("kfold must be > 0")
+        rdm = java_random_doubles(seed, n)
+        indv = (n + 0.0) / self.numFold
+        fold = (np.arange(n, dtype=np.float64) / indv).astype(np.int32) + 1
+        order = np.argsort(rdm, kind="stable")
+        srt = rdm[order]
+        ties = np.nonzero(srt[1:] == srt[:-1])[0]
+        if ties.size and np.any(fold[order[ties]] != fold[order[ties + 1]]):
+            # equal keys: the reference's Lomuto partition order decides; not reproduced (p ~ n^2 / 2^54)
+            raise NotImplementedError("two equal random draws carry different fold labels")
+        self.assign = fold[order]  # assignMatrix in CRS order
+
+    def getKthFold(self, k: int):
+        """Returns (train TrainingSet, test dict) for fold k (1-based), or None when k is out of range (:69-70)."""
+        if k > self.numFold or k < 1:
+            return None
+        ts = self.ts
+        test_mask = self.assign == k
+        keep = ~test_mask
+        has_ctx = ts.ctx is not None
+        r = ts.r[keep]
+        total = 0.0
+        for v in r.tolist():  # SparseMatrix.getGlobalAvg of the TRAINING matrix (Recommender.java:265)
+            total += v
+        train = TrainingSet(num_users=ts.num_users, num_items=ts.num_items, u=ts.u[keep], j=ts.j[keep], r=r,
+                            ctx=ts.ctx[keep] if has_ctx else None, num_conditions=ts.num_conditions,
+                            num_contexts=ts.num_contexts, ctx_ptr=ts.ctx_ptr, ctx_cond=ts.ctx_cond,
+                            global_mean=total / len(r) if len(r) else 0.0)
+        test = {"u": ts.u[test_mask].copy(), "j": ts.j[test_mask].copy(),
+                "ctx": ts.ctx[test_mask].copy() if has_ctx else None, "r": ts.r[test_mask].copy()}
+        return train, test

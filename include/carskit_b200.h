@@ -214,13 +214,18 @@ typedef struct cars_stats {
   int64_t kernel_launches;  /* engine kernels launched so far on this handle           */
   int64_t h2d_bytes;        /* bytes copied host->device so far                        */
   int64_t d2h_bytes;        /* bytes copied device->host so far                        */
-  double  schedule_ms;      /* wall time spent building the schedule in cars_create    */
+  double  schedule_ms;      /* wall time spent building the schedule in cars_create (H2D of the ratings included) */
   double  last_epoch_ms;    /* device time of the last epoch's SGD kernel (CUDA events on the
                                launching stream)                                       */
   int32_t grid_ctas;        /* persistent grid of the SGD kernel                       */
   int32_t block_threads;
   int32_t sm_count;
   int32_t reserved;
+  /* FLAGGED schedule build, split: the caller's arrays crossing PCIe / chains + dependency levels on the
+     device / level sort + record packing (device times, CUDA events) */
+  double  schedule_copy_ms;
+  double  schedule_levels_ms;
+  double  schedule_pack_ms;
 } cars_stats;
 int cars_get_stats(const cars_handle* h, cars_stats* out);
 void* cars_get_stream(const cars_handle* h); /* cudaStream_t the kernels are launched on */

@@ -248,3 +248,83 @@ def test_two_handles_concurrently(oracle, cars_lib):
         e2.download(g2)
     assert_bit_identical(r1, g1)
     assert_bit_identical(r2, g2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the schedule is built on the device (schedule_gpu.cuh): same levels as the sequential host pass
+# ---------------------------------------------------------------------------------------------------
+def host_levels(ts):
+    lu, lj = np.zeros(ts.num_users, np.int64), np.zeros(ts.num_items, np.int64)
+    sizes = {}
+    for u, j in zip(ts.u.tolist(), ts.j.tolist()):
+        l = 1 + max(lu[u], lj[j])
+        lu[u] = lj[j] = l
+        sizes[l] = sizes.get(l, 0) + 1
+    return (max(sizes), max(sizes.values())) if sizes else (0, 0)
+
+
+@pytest.mark.parametrize("order,users,items,nnz,zipf", [("user_sorted", 500, 120, 20000, 0.0), ("shuffled", 3000, 2000, 100000, 1.0),
+                                                         ("shuffled", 1, 300, 300, 0.0), ("user_sorted", 4000, 3, 9000, 0.0)])
+def test_device_built_levels_match_the_sequential_pass(oracle, cars_lib, monkeypatch, order, users, items, nnz, zipf):
+    ts, _ = synth.make_training_set(users, items, [4, 3], nnz, seed=11, order=order, item_zipf=zipf)
+    want = host_levels(ts)
+    desc = capi.make_desc(ts, capi.CAMF_CI, 8, **REGS)
+    arrs = init_arrays(oracle, capi.CAMF_CI, ts, 8, 1)
+    out = {}
+    for how in ("device", "host"):
+        monkeypatch.setenv("CARS_LEVELS", how)
+        got = {k: v.copy() for k, v in arrs.items()}
+        with capi.Engine(desc, keepalive=ts) as eng:
+            st = eng.stats()
+            assert (st.num_levels, st.max_level_size) == want, how
+            eng.upload(got)
+            loss = eng.epoch(0.02)
+            eng.download(got)
+        out[how] = (loss.hex(), digest(got))
+    assert out["device"] == out["host"]  # same record stream => same loss bits, same model
+
+
+def test_large_pageable_and_pinned_transfers(oracle, cars_lib):
+    # arrays well above the staging chunk (4 MiB): several host threads copy through pinned double buffers;
+    # pinned inputs (torch pin_memory) are DMA'd directly.  Both must be byte-exact in both directions.
+    import torch
+    ts, _ = synth.make_training_set(300_000, 2_000, [4, 4], 3_000_000, seed=5, order="user_sorted")
+    F = 16
+    desc = capi.make_desc(ts, capi.CAMF_CU, F, **REGS)
+    arrs = init_arrays(oracle, capi.CAMF_CU, ts, F, 2)
+    assert arrs["P"].nbytes > 8 * (4 << 20)
+    ref = {k: v.copy() for k, v in arrs.items()}
+    want_loss = oracle.epoch(desc, ref, capi.f32(0.02))
+
+    def pinned(a):
+        t = torch.from_numpy(a).pin_memory()
+        return t, t.numpy()
+
+    for pin in (False, True):
+        keep = []
+        if pin:
+            fields = {}
+            for name in ("u", "j", "ctx", "r"):
+                t, v = pinned(getattr(ts, name))
+                keep.append(t)
+                fields[name] = v
+            ts2 = capi.TrainingSet(num_users=ts.num_users, num_items=ts.num_items, num_conditions=ts.num_conditions,
+                                   num_contexts=ts.num_contexts, ctx_ptr=ts.ctx_ptr, ctx_cond=ts.ctx_cond,
+                                   global_mean=ts.global_mean, **fields)
+            got = {}
+            for k, v in arrs.items():
+                t, a = pinned(v)
+                keep.append(t)
+                got[k] = a
+        else:
+            ts2, got = ts, {k: v.copy() for k, v in arrs.items()}
+        d2 = capi.make_desc(ts2, capi.CAMF_CU, F, **REGS)
+        with capi.Engine(d2, keepalive=ts2) as eng:
+            eng.upload(got)
+            back = {k: np.zeros_like(v) for k, v in got.items()}
+            eng.download(back)
+            assert_bit_identical(arrs, back)  # round trip without an epoch
+            loss = eng.epoch(capi.f32(0.02))
+            eng.download(got)
+        assert_bit_identical(ref, got)
+        np.testing.assert_allclose(loss, want_loss, rtol=LOSS_RTOL, atol=0)
