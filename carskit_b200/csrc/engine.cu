@@ -507,6 +507,9 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     CUDA_TRY_H(dev_alloc(&h->d_rec, (size_t)nnz));
     h->flags_words = 64 + I + U;
     CUDA_TRY_H(dev_alloc(&h->d_flags, h->flags_words));
+    if (getenv("CARS_SCHED_TRACE"))
+      fprintf(stderr, "[cars schedule] %-28s %8.2f ms\n", "cudaMalloc(records, flags)",
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     FlaggedBuild fb;
     cudaError_t be = build_flagged_on_device(desc->num_users, desc->num_items, desc->num_contexts, nnz, desc->u, desc->j,
                                              has_ctx ? desc->ctx : nullptr, desc->r, h->stream, h->sm_count, h->copier,

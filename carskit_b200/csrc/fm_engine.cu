@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -19,6 +20,7 @@ struct FieldStore {
   int32_t *d_coord_of_row = nullptr, *d_perm = nullptr, *d_piece_coord = nullptr;
   int64_t *d_piece_beg = nullptr, *d_coord_piece = nullptr, *d_coord_rows = nullptr;
   double* d_delta = nullptr;
+  bool wide = false;  // few coordinates with many pieces each: one warp sums a coordinate's pieces
   FmField f{};
 };
 
@@ -39,6 +41,7 @@ struct cars_fm_handle {
   int red_blocks = 0;
   FieldStore fld[3];
   bool uploaded = false, prepared = false;
+  bool fuse_update = true;  // CARS_FM_FUSE=0: the row update before a streaming reduce stays a kernel of its own
   int64_t launches = 0, h2d = 0, d2h = 0;
   cudaEvent_t ev_beg = nullptr, ev_end = nullptr;
   double last_iter_ms = 0;
@@ -75,9 +78,9 @@ static cudaError_t fm_put(cars_fm_handle* h, T** dst, const std::vector<T>& v) {
 }
 
 // rows sorted by coordinate (stable counting sort), cut into pieces of <= kPiece rows
-static const int64_t kPiece = 1024;
+static const int64_t kPiece = 256;
 static int build_field(cars_fm_handle* h, int which, const std::vector<int32_t>& coord_of_row, int32_t ncoord,
-                       int32_t offset, double x) {
+                       int32_t offset, double x, bool dense) {
   FieldStore& fs = h->fld[which];
   const int64_t N = h->N;
   std::vector<int64_t> start((size_t)ncoord + 1, 0);
@@ -116,6 +119,8 @@ static int build_field(cars_fm_handle* h, int which, const std::vector<int32_t>&
   fs.f.coord_of_row = fs.d_coord_of_row; fs.f.perm = fs.d_perm; fs.f.piece_beg = fs.d_piece_beg;
   fs.f.piece_coord = fs.d_piece_coord; fs.f.coord_piece = fs.d_coord_piece; fs.f.coord_rows = fs.d_coord_rows;
   fs.f.num_pieces = (int64_t)piece_coord.size(); fs.f.ncoord = ncoord; fs.f.offset = offset; fs.f.x = x;
+  fs.f.dense_blocks = dense ? h->sm_count * 3 : 0;
+  fs.wide = dense || (ncoord > 0 && fs.f.num_pieces / ncoord >= 8);
   if (fs.f.num_pieces > h->max_pieces) h->max_pieces = fs.f.num_pieces;
   return CARS_OK;
 }
@@ -171,29 +176,76 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
   FM_TRY_H(fm_alloc(&h->d_r, (size_t)N)); FM_TRY_H(fm_alloc(&h->d_e, (size_t)N));
   FM_TRY_H(fm_alloc(&h->d_Qc, (size_t)N * h->k));
   FM_TRY_H(fm_alloc(&h->d_w0, 1)); FM_TRY_H(fm_alloc(&h->d_w, (size_t)h->p)); FM_TRY_H(fm_alloc(&h->d_V, (size_t)h->p * h->k));
-  if (N) {
-    FM_TRY_H(cudaMemcpyAsync(h->d_u, d->u, N * 4, cudaMemcpyHostToDevice, h->stream));
-    FM_TRY_H(cudaMemcpyAsync(h->d_j, d->j, N * 4, cudaMemcpyHostToDevice, h->stream));
-    FM_TRY_H(cudaMemcpyAsync(h->d_c, d->ctx, N * 4, cudaMemcpyHostToDevice, h->stream));
-    FM_TRY_H(cudaMemcpyAsync(h->d_r, d->r, N * 8, cudaMemcpyHostToDevice, h->stream));
-    h->h2d += N * 20;
-  }
   try {
+    // Internal row order.  The rows (errors[n], Q[n][f]) are private to the engine, and every sum of the sweep
+    // runs over the rows of ONE coordinate, so the rows may be stored in any order.  They are sorted by
+    // (item block, context, caller's order): the item field then gathers e / Qc[f] inside one block of
+    // ~kBlockRows rows (L2-resident), the context field reads long contiguous runs, and the user field reads
+    // (item blocks x contexts) streams in which neighbouring users are neighbours -- instead of 8-byte reads
+    // scattered over all N rows, one DRAM sector each (profiles/r1: 0.31 of the HBM roofline before).
+    int64_t block_rows = 1536 * 1024;
+    if (const char* e = getenv("CARS_FM_BLOCK_ROWS")) block_rows = atoll(e);
+    // few contexts: that field is reduced by streaming the rows (fm_dense_reduce_kernel), so the context does not
+    // enter the row order and a user's rows stay contiguous inside every item block
+    int64_t dense_min_rows = 65536;
+    if (const char* e = getenv("CARS_FM_DENSE_MIN_ROWS")) dense_min_rows = atoll(e);
+    const bool ctx_dense = h->C > 0 && h->C <= kDenseMaxCoord && N >= dense_min_rows;
     std::vector<int32_t> cu((size_t)N), cj((size_t)N), cc((size_t)N);
-    for (int64_t n = 0; n < N; n++) {
-      cu[n] = d->u[n];
-      cj[n] = d->j[n];
-      cc[n] = d->ctx[n] < h->C ? d->ctx[n] : -1;  // FM.java:81: the context feature exists only if its index is < p
+    std::vector<double> cr((size_t)N);
+    std::vector<int32_t> order;  // new position -> caller's row
+    if (block_rows > 0 && N > block_rows) {
+      const int64_t nblk = (N + block_rows - 1) / block_rows;
+      const int32_t items_per_blk = (int32_t)((h->I + nblk - 1) / nblk);
+      const int64_t nctx = ctx_dense ? 1 : (int64_t)h->C + 1;  // contexts without a feature (index >= p) share the last slot
+      const int64_t nkeys = ((int64_t)(h->I - 1) / items_per_blk + 1) * nctx;
+      std::vector<int64_t> start((size_t)nkeys + 1, 0);
+      auto key_of = [&](int64_t n) {
+        const int32_t c = ctx_dense ? 0 : (d->ctx[n] < h->C ? d->ctx[n] : h->C);
+        return (int64_t)(d->j[n] / items_per_blk) * nctx + c;
+      };
+      for (int64_t n = 0; n < N; n++) start[(size_t)key_of(n) + 1]++;
+      for (int64_t q = 0; q < nkeys; q++) start[(size_t)q + 1] += start[(size_t)q];
+      order.resize((size_t)N);
+      for (int64_t n = 0; n < N; n++) order[(size_t)start[(size_t)key_of(n)]++] = (int32_t)n;
     }
-    if ((rc = build_field(h, 0, cu, h->U, 0, 1.0))) return bail(rc);
-    if ((rc = build_field(h, 1, cj, h->I, h->U, 1.0))) return bail(rc);
-    if ((rc = build_field(h, 2, cc, h->C, h->U + h->I, h->xc))) return bail(rc);
+    for (int64_t i = 0; i < N; i++) {
+      const int64_t n = order.empty() ? i : order[(size_t)i];
+      cu[i] = d->u[n];
+      cj[i] = d->j[n];
+      cr[i] = d->r[n];
+      cc[i] = d->ctx[n];
+    }
+    if (N) {
+      FM_TRY_H(cudaMemcpyAsync(h->d_u, cu.data(), N * 4, cudaMemcpyHostToDevice, h->stream));
+      FM_TRY_H(cudaMemcpyAsync(h->d_j, cj.data(), N * 4, cudaMemcpyHostToDevice, h->stream));
+      FM_TRY_H(cudaMemcpyAsync(h->d_c, cc.data(), N * 4, cudaMemcpyHostToDevice, h->stream));
+      FM_TRY_H(cudaMemcpyAsync(h->d_r, cr.data(), N * 8, cudaMemcpyHostToDevice, h->stream));
+      FM_TRY_H(cudaStreamSynchronize(h->stream));
+      h->h2d += N * 20;
+    }
+    for (int64_t i = 0; i < N; i++)
+      if (cc[i] >= h->C) cc[i] = -1;  // FM.java:81: the context feature exists only if its index is < p
+    if ((rc = build_field(h, 0, cu, h->U, 0, 1.0, false))) return bail(rc);
+    if ((rc = build_field(h, 1, cj, h->I, h->U, 1.0, false))) return bail(rc);
+    if ((rc = build_field(h, 2, cc, h->C, h->U + h->I, h->xc, ctx_dense))) return bail(rc);
+    if (ctx_dense) {
+      const int smem = (int)((size_t)h->C * kDenseThreads * sizeof(double2));
+      FM_TRY_H(cudaFuncSetAttribute(fm_dense_reduce_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      FM_TRY_H(cudaFuncSetAttribute(fm_dense_reduce_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      FM_TRY_H(cudaFuncSetAttribute(fm_dense_reduce_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      FM_TRY_H(cudaFuncSetAttribute(fm_dense_reduce_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      if (const char* e = getenv("CARS_FM_FUSE")) h->fuse_update = atoi(e) != 0;
+    }
   } catch (...) {
     fm_fail(h, CARS_E_OOM, "host allocation failed");
     return bail(CARS_E_OOM);
   }
   h->red_blocks = h->sm_count * 4;
-  const size_t part = (size_t)(2 * (h->max_pieces > h->red_blocks ? h->max_pieces : h->red_blocks));
+  size_t part = (size_t)(2 * (h->max_pieces > h->red_blocks ? h->max_pieces : h->red_blocks));
+  for (const FieldStore& fs : h->fld) {
+    const size_t need = (size_t)2 * fs.f.dense_blocks * (fs.f.ncoord > 0 ? fs.f.ncoord : 0);
+    if (need > part) part = need;
+  }
   FM_TRY_H(fm_alloc(&h->d_part, part));
   FM_TRY_H(fm_alloc(&h->d_scal, 8));
   FM_TRY_H(cudaMallocHost((void**)&h->h_scal, 8 * sizeof(double)));
@@ -245,25 +297,73 @@ extern "C" int cars_fm_prepare(cars_fm_handle* h) {
   return CARS_OK;
 }
 
+// One sweep over the three fields (users, items, contexts) for one coefficient column: per field
+// (a) reduce -> (b) new coordinates + deltas [all-reduce of the per-coordinate sums in between when sharded] ->
+// (c) row update.  When the NEXT field is reduced by the streaming kernel, (c) is not launched: the pending update
+// rides along in that field's reduce (fm_dense_reduce_kernel<.., FUSED = true>).
+struct FmExchange {  // row-sharded run: caller's device buffer and all-reduce (cars_fm_iteration_sharded)
+  double* dev_buf = nullptr;
+  cars_allreduce_fn ar = nullptr;
+  void* user = nullptr;
+};
+
 template <int MODE>
-static int field_step(cars_fm_handle* h, int which, double* coef, int stride, int col, double* Qf, double size_reg) {
-  FieldStore& fs = h->fld[which];
-  const FmField& f = fs.f;
-  if (f.ncoord == 0) return CARS_OK;
-  if (f.num_pieces > 0) {
-    const unsigned blocks = (unsigned)((f.num_pieces * 32 + 255) / 256);
-    fm_piece_reduce_kernel<MODE><<<blocks, 256, 0, h->stream>>>(f, h->d_e, Qf, coef, stride, col, h->d_part);
-    FM_TRY(h, cudaGetLastError());
-    h->launches++;
-  }
-  fm_coord_kernel<MODE><<<(unsigned)((f.ncoord + 255) / 256), 256, 0, h->stream>>>(f, h->d_part, size_reg, coef, stride, col,
-                                                                                  fs.d_delta);
-  FM_TRY(h, cudaGetLastError());
-  h->launches++;
-  if (h->N) {
-    fm_row_update_kernel<MODE><<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(f, fs.d_delta, h->N, h->d_e, Qf);
-    FM_TRY(h, cudaGetLastError());
-    h->launches++;
+static int field_sweep(cars_fm_handle* h, double* coef, int stride, int col, double* Qf, double size_reg, const FmExchange* ex) {
+  int pending = -1;  // field whose row update has not been applied yet
+  for (int which = 0; which < 3; which++) {
+    FieldStore& fs = h->fld[which];
+    const FmField& f = fs.f;
+    if (f.ncoord == 0) continue;
+    // (a)
+    if (f.dense_blocks > 0) {
+      const size_t smem = (size_t)f.ncoord * kDenseThreads * sizeof(double2);
+      if (pending >= 0)
+        fm_dense_reduce_kernel<MODE, true><<<f.dense_blocks, kDenseThreads, smem, h->stream>>>(
+            f, h->d_e, Qf, coef, stride, col, h->N, h->d_part, h->fld[pending].f, h->fld[pending].d_delta);
+      else
+        fm_dense_reduce_kernel<MODE, false><<<f.dense_blocks, kDenseThreads, smem, h->stream>>>(f, h->d_e, Qf, coef, stride, col,
+                                                                                               h->N, h->d_part, f, nullptr);
+      pending = -1;
+      FM_TRY(h, cudaGetLastError());
+      h->launches++;
+    } else if (f.num_pieces > 0) {
+      const unsigned blocks = (unsigned)((f.num_pieces * 32 + 255) / 256);
+      fm_piece_reduce_kernel<MODE><<<blocks, 256, 0, h->stream>>>(f, h->d_e, Qf, coef, stride, col, h->d_part);
+      FM_TRY(h, cudaGetLastError());
+      h->launches++;
+    }
+    // (b)
+    const unsigned cb = fs.wide ? (unsigned)(((int64_t)f.ncoord * 32 + 255) / 256) : (unsigned)((f.ncoord + 255) / 256);
+    if (!ex) {
+      if (fs.wide)
+        fm_coord_kernel<MODE, true><<<cb, 256, 0, h->stream>>>(f, h->d_part, size_reg, coef, stride, col, fs.d_delta);
+      else
+        fm_coord_kernel<MODE, false><<<cb, 256, 0, h->stream>>>(f, h->d_part, size_reg, coef, stride, col, fs.d_delta);
+      FM_TRY(h, cudaGetLastError());
+      h->launches++;
+    } else {
+      if (fs.wide)
+        fm_coord_partial_kernel<MODE, true><<<cb, 256, 0, h->stream>>>(f, h->d_part, ex->dev_buf);
+      else
+        fm_coord_partial_kernel<MODE, false><<<cb, 256, 0, h->stream>>>(f, h->d_part, ex->dev_buf);
+      FM_TRY(h, cudaGetLastError());
+      if (ex->ar(ex->user, ex->dev_buf, 2 * (int64_t)f.ncoord) != 0) return fm_fail(h, CARS_E_STATE, "the all-reduce callback failed");
+      fm_coord_finish_kernel<<<(unsigned)((f.ncoord + 255) / 256), 256, 0, h->stream>>>(f, ex->dev_buf, size_reg, coef, stride, col,
+                                                                                       fs.d_delta);
+      FM_TRY(h, cudaGetLastError());
+      h->launches += 2;
+    }
+    // (c)
+    if (h->N == 0) continue;
+    int next = which + 1;
+    while (next < 3 && h->fld[next].f.ncoord == 0) next++;
+    if (h->fuse_update && next < 3 && h->fld[next].f.dense_blocks > 0) {
+      pending = which;
+    } else {
+      fm_row_update_kernel<MODE><<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(f, fs.d_delta, h->N, h->d_e, Qf);
+      FM_TRY(h, cudaGetLastError());
+      h->launches++;
+    }
   }
   return CARS_OK;
 }
@@ -283,13 +383,11 @@ extern "C" int cars_fm_iteration(cars_fm_handle* h, double* loss_out) {
   h->launches += 4;
   // w_l, l = 0..p-1 (:172-191): users, items, contexts
   const double w_reg = (double)h->Nglobal * h->reg_lw;
-  for (int fld = 0; fld < 3; fld++)
-    if ((rc = field_step<0>(h, fld, h->d_w, 1, 0, nullptr, w_reg))) return rc;
+  if ((rc = field_sweep<0>(h, h->d_w, 1, 0, nullptr, w_reg, nullptr))) return rc;
   // V_lf, f = 0..k-1 { l = 0..p-1 } (:194-217)
   const double v_reg = (double)h->Nglobal * h->reg_lf;
   for (int f = 0; f < h->k; f++)
-    for (int fld = 0; fld < 3; fld++)
-      if ((rc = field_step<1>(h, fld, h->d_V, h->k, f, h->d_Qc + (int64_t)f * h->N, v_reg))) return rc;
+    if ((rc = field_sweep<1>(h, h->d_V, h->k, f, h->d_Qc + (int64_t)f * h->N, v_reg, nullptr))) return rc;
   FM_TRY(h, cudaEventRecord(h->ev_end, h->stream));
   FM_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   FM_TRY(h, cudaStreamSynchronize(h->stream));
@@ -302,33 +400,6 @@ extern "C" int cars_fm_iteration(cars_fm_handle* h, double* loss_out) {
 }
 
 // ---- row-sharded iteration: the same sweep with an all-reduce of the per-coordinate sums ------------------
-template <int MODE>
-static int field_step_sharded(cars_fm_handle* h, int which, double* coef, int stride, int col, double* Qf, double size_reg,
-                              double* dev_buf, cars_allreduce_fn ar, void* user) {
-  FieldStore& fs = h->fld[which];
-  const FmField& f = fs.f;
-  if (f.ncoord == 0) return CARS_OK;
-  if (f.num_pieces > 0) {
-    const unsigned blocks = (unsigned)((f.num_pieces * 32 + 255) / 256);
-    fm_piece_reduce_kernel<MODE><<<blocks, 256, 0, h->stream>>>(f, h->d_e, Qf, coef, stride, col, h->d_part);
-    FM_TRY(h, cudaGetLastError());
-    h->launches++;
-  }
-  const unsigned cb = (unsigned)((f.ncoord + 255) / 256);
-  fm_coord_partial_kernel<MODE><<<cb, 256, 0, h->stream>>>(f, h->d_part, dev_buf);
-  FM_TRY(h, cudaGetLastError());
-  if (ar(user, dev_buf, 2 * (int64_t)f.ncoord) != 0) return fm_fail(h, CARS_E_STATE, "the all-reduce callback failed");
-  fm_coord_finish_kernel<<<cb, 256, 0, h->stream>>>(f, dev_buf, size_reg, coef, stride, col, fs.d_delta);
-  FM_TRY(h, cudaGetLastError());
-  h->launches += 2;
-  if (h->N) {
-    fm_row_update_kernel<MODE><<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(f, fs.d_delta, h->N, h->d_e, Qf);
-    FM_TRY(h, cudaGetLastError());
-    h->launches++;
-  }
-  return CARS_OK;
-}
-
 extern "C" int cars_fm_exchange_doubles(const cars_fm_handle* h, int64_t* out) {
   if (!h || !out) return CARS_E_INVALID;
   int64_t m = h->U > h->I ? h->U : h->I;
@@ -356,13 +427,12 @@ extern "C" int cars_fm_iteration_sharded(cars_fm_handle* h, double* dev_buf, car
   FM_TRY(h, cudaGetLastError());
   h->launches += 5;
   const double w_reg = (double)h->Nglobal * h->reg_lw;
-  for (int fld = 0; fld < 3; fld++)
-    if ((rc = field_step_sharded<0>(h, fld, h->d_w, 1, 0, nullptr, w_reg, dev_buf, ar, user))) return rc;
+  FmExchange ex;
+  ex.dev_buf = dev_buf; ex.ar = ar; ex.user = user;
+  if ((rc = field_sweep<0>(h, h->d_w, 1, 0, nullptr, w_reg, &ex))) return rc;
   const double v_reg = (double)h->Nglobal * h->reg_lf;
   for (int f = 0; f < h->k; f++)
-    for (int fld = 0; fld < 3; fld++)
-      if ((rc = field_step_sharded<1>(h, fld, h->d_V, h->k, f, h->d_Qc + (int64_t)f * h->N, v_reg, dev_buf, ar, user)))
-        return rc;
+    if ((rc = field_sweep<1>(h, h->d_V, h->k, f, h->d_Qc + (int64_t)f * h->N, v_reg, &ex))) return rc;
   FM_TRY(h, cudaEventRecord(h->ev_end, h->stream));
   FM_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   FM_TRY(h, cudaStreamSynchronize(h->stream));

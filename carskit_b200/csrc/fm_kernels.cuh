@@ -9,8 +9,10 @@
 //
 // One coordinate step = (a) reduce numerator/denominator over rows(l), (b) new value + delta per
 // coordinate, (c) e_n += delta*x (and Qc[n][f] += delta*x) for the rows of that coordinate.
-// (a) is a deterministic two-level reduction: rows sorted by coordinate are cut into pieces of <= 1024
-// rows, one warp sums a piece in a fixed order, one thread sums a coordinate's pieces in order.
+// (a) is a deterministic two-level reduction: rows sorted by coordinate are cut into pieces of <= 256
+// rows, one warp sums a piece in a fixed order, one thread (or warp) sums a coordinate's pieces in order.
+// Fields with few coordinates (contexts) are reduced by streaming the rows instead (fm_dense_reduce_kernel),
+// with the previous field's row update fused in.
 // Arithmetic: fp64, no FMA contraction in the update formulas (Java semantics); sums are tree-ordered, so
 // results equal the sparse oracle's up to summation order (tolerance stated in tests/test_fm_gpu.py).
 #pragma once
@@ -30,7 +32,11 @@ struct FmField {
   int32_t ncoord;
   int32_t offset;  // index of the field's first coordinate in w / V
   double x;        // feature value of the field
+  int32_t dense_blocks;  // > 0: the field is reduced by fm_dense_reduce_kernel on this many CTAs (no pieces)
 };
+
+constexpr int kDenseThreads = 128;
+constexpr int kDenseMaxCoord = 64;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -161,16 +167,27 @@ __global__ void __launch_bounds__(256) fm_piece_reduce_kernel(FmField fld, const
   const double cl = coef[(int64_t)(fld.offset + l) * coef_stride + coef_col];
   const int64_t beg = fld.piece_beg[piece], end = fld.piece_beg[piece + 1];
   double num = 0.0, den = 0.0;
-  for (int64_t i = beg + lane; i < end; i += 32) {
-    const int64_t n = fld.perm[i];
-    const double en = e[n];
+  auto add_row = [&](double en, double qn) {  // one row's terms, in the row order of the piece
     if (MODE == 0) {
       num = __dadd_rn(num, __dmul_rn(__dsub_rn(en, __dmul_rn(cl, x)), x));
     } else {
-      const double h = __dsub_rn(__dmul_rn(x, Qf[n]), __dmul_rn(__dmul_rn(x, x), cl));
+      const double h = __dsub_rn(__dmul_rn(x, qn), __dmul_rn(__dmul_rn(x, x), cl));
       num = __dadd_rn(num, __dmul_rn(__dsub_rn(en, __dmul_rn(cl, h)), h));
       den = __dadd_rn(den, __dmul_rn(h, h));
     }
+  };
+  int64_t i = beg + lane;
+  // four independent gathers in flight per lane (same order of additions as the plain loop)
+  for (; i + 96 < end; i += 128) {
+    const int64_t n0 = fld.perm[i], n1 = fld.perm[i + 32], n2 = fld.perm[i + 64], n3 = fld.perm[i + 96];
+    const double e0 = e[n0], e1 = e[n1], e2 = e[n2], e3 = e[n3];
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+    if (MODE == 1) { q0 = Qf[n0]; q1 = Qf[n1]; q2 = Qf[n2]; q3 = Qf[n3]; }
+    add_row(e0, q0); add_row(e1, q1); add_row(e2, q2); add_row(e3, q3);
+  }
+  for (; i < end; i += 32) {
+    const int64_t n = fld.perm[i];
+    add_row(e[n], MODE == 1 ? Qf[n] : 0.0);
   }
   num = warp_sum(num);
   if (MODE == 1) den = warp_sum(den);
@@ -180,19 +197,149 @@ __global__ void __launch_bounds__(256) fm_piece_reduce_kernel(FmField fld, const
   }
 }
 
-// (b) one thread per coordinate: sum its pieces in order, new = 0 - num/den, delta = new - old.
-template <int MODE>
+// (a') fields with FEW coordinates (contexts: <= kDenseMaxCoord): the rows are streamed in storage order, fully
+// coalesced, and every thread adds a row's terms into ITS OWN accumulator of the row's coordinate in shared
+// memory (bins[coordinate][thread]: no conflicts, fixed order).  A CTA owns a fixed slice of rows; its per-
+// coordinate sums (fixed-order tree over the threads) go to part[(block * ncoord + c) * 2 + {0, 1}].  Deterministic.
+// FUSED: the pending row update of the PREVIOUS field's step (e_n += delta x, Qc[n][f] += delta x -- what
+// fm_row_update_kernel does) is applied on the way: both are streaming passes over the same rows, so the fused
+// pass saves one full read of e and Qc[f].  Same arithmetic in the same order as the two separate kernels.
+template <int MODE, bool FUSED>
+__global__ void __launch_bounds__(kDenseThreads) fm_dense_reduce_kernel(FmField fld, double* __restrict__ e,
+                                                                        double* __restrict__ Qf,
+                                                                        const double* __restrict__ coef, int coef_stride,
+                                                                        int coef_col, int64_t N, double* __restrict__ part,
+                                                                        FmField prev, const double* __restrict__ prev_delta) {
+  extern __shared__ __align__(16) unsigned char dense_smem[];
+  double2* bins = reinterpret_cast<double2*>(dense_smem);  // [ncoord][kDenseThreads]
+  __shared__ double cls[kDenseMaxCoord];
+  constexpr int T = kDenseThreads;
+  constexpr int UNR = 8;  // rows in flight per thread
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nc = fld.ncoord;
+  const double x = fld.x;
+  for (int c = tid; c < nc; c += T) cls[c] = coef[(int64_t)(fld.offset + c) * coef_stride + coef_col];
+  for (int i = tid; i < nc * T; i += T) bins[i] = make_double2(0.0, 0.0);
+  __syncthreads();
+  const int64_t per = (N + gridDim.x - 1) / gridDim.x;
+  const int64_t beg = (int64_t)blockIdx.x * per, end = beg + per < N ? beg + per : N;
+  auto add_row = [&](int c, double en, double qn) {
+    if (c < 0) return;
+    const double cl = cls[c];
+    double2 b = bins[c * T + tid];
+    if (MODE == 0) {
+      b.x = __dadd_rn(b.x, __dmul_rn(__dsub_rn(en, __dmul_rn(cl, x)), x));
+    } else {
+      const double h = __dsub_rn(__dmul_rn(x, qn), __dmul_rn(__dmul_rn(x, x), cl));
+      b.x = __dadd_rn(b.x, __dmul_rn(__dsub_rn(en, __dmul_rn(cl, h)), h));
+      b.y = __dadd_rn(b.y, __dmul_rn(h, h));
+    }
+    bins[c * T + tid] = b;
+  };
+  int64_t n = beg + tid;
+  for (; n + (UNR - 1) * T < end; n += UNR * T) {
+    int c[UNR], lp[UNR];
+    double en[UNR], qn[UNR];
+#pragma unroll
+    for (int k = 0; k < UNR; k++) {
+      c[k] = fld.coord_of_row[n + k * T];
+      en[k] = e[n + k * T];
+      qn[k] = MODE == 1 ? Qf[n + k * T] : 0.0;
+      lp[k] = FUSED ? prev.coord_of_row[n + k * T] : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; k++) {
+      if (FUSED && lp[k] >= 0) {
+        const double d = __dmul_rn(prev_delta[lp[k]], prev.x);
+        en[k] = __dadd_rn(en[k], d);
+        e[n + k * T] = en[k];
+        if (MODE == 1) {
+          qn[k] = __dadd_rn(qn[k], d);
+          Qf[n + k * T] = qn[k];
+        }
+      }
+      add_row(c[k], en[k], qn[k]);
+    }
+  }
+  for (; n < end; n += T) {
+    double en = e[n], qn = MODE == 1 ? Qf[n] : 0.0;
+    const int lp = FUSED ? prev.coord_of_row[n] : -1;
+    if (FUSED && lp >= 0) {
+      const double d = __dmul_rn(prev_delta[lp], prev.x);
+      en = __dadd_rn(en, d);
+      e[n] = en;
+      if (MODE == 1) {
+        qn = __dadd_rn(qn, d);
+        Qf[n] = qn;
+      }
+    }
+    add_row(fld.coord_of_row[n], en, qn);
+  }
+  __syncthreads();
+  for (int c = warp; c < nc; c += T / 32) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int k = 0; k < T / 32; k++) {
+      const double2 v = bins[c * T + lane + 32 * k];
+      a = __dadd_rn(a, v.x);
+      b = __dadd_rn(b, v.y);
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) {
+      part[((int64_t)blockIdx.x * nc + c) * 2] = a;
+      part[((int64_t)blockIdx.x * nc + c) * 2 + 1] = b;
+    }
+  }
+}
+
+// Sum of a coordinate's piece partials.  WIDE = false: one thread walks the pieces in order (fields with many
+// coordinates of a few pieces each: users, items).  WIDE = true: one warp per coordinate, lanes stride the pieces
+// and a fixed-order tree joins them (fields with few coordinates of many pieces: contexts) -- both deterministic.
+template <int MODE, bool WIDE>
+__device__ __forceinline__ void coord_piece_sums(const FmField& fld, const double* __restrict__ part, int l, int lane,
+                                                 double& num, double& den) {
+  num = 0.0;
+  den = 0.0;
+  if (WIDE && fld.dense_blocks > 0) {  // partials of fm_dense_reduce_kernel: one pair per CTA and coordinate
+    for (int b = lane; b < fld.dense_blocks; b += 32) {
+      num = __dadd_rn(num, part[((int64_t)b * fld.ncoord + l) * 2]);
+      if (MODE == 1) den = __dadd_rn(den, part[((int64_t)b * fld.ncoord + l) * 2 + 1]);
+    }
+    num = warp_sum(num);
+    if (MODE == 1) den = warp_sum(den);
+    if (MODE == 0) den = __dmul_rn((double)fld.coord_rows[l], __dmul_rn(fld.x, fld.x));
+    return;
+  }
+  const int64_t q0 = fld.coord_piece[l], q1 = fld.coord_piece[l + 1];
+  if (WIDE) {
+    for (int64_t q = q0 + lane; q < q1; q += 32) {
+      num = __dadd_rn(num, part[q]);
+      if (MODE == 1) den = __dadd_rn(den, part[fld.num_pieces + q]);
+    }
+    num = warp_sum(num);
+    if (MODE == 1) den = warp_sum(den);
+  } else {
+    for (int64_t q = q0; q < q1; q++) {
+      num = __dadd_rn(num, part[q]);
+      if (MODE == 1) den = __dadd_rn(den, part[fld.num_pieces + q]);
+    }
+  }
+  if (MODE == 0) den = __dmul_rn((double)fld.coord_rows[l], __dmul_rn(fld.x, fld.x));
+}
+
+// (b) per coordinate: sum its pieces, new = 0 - num/den, delta = new - old.
+template <int MODE, bool WIDE>
 __global__ void __launch_bounds__(256) fm_coord_kernel(FmField fld, const double* __restrict__ part, double size_reg,
                                                        double* __restrict__ coef, int coef_stride, int coef_col,
                                                        double* __restrict__ delta /*[ncoord]*/) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = WIDE ? (t >> 5) : t;
+  const int lane = threadIdx.x & 31;
   if (l >= fld.ncoord) return;
-  double num = 0.0, den = 0.0;
-  for (int64_t q = fld.coord_piece[l]; q < fld.coord_piece[l + 1]; q++) {
-    num = __dadd_rn(num, part[q]);
-    if (MODE == 1) den = __dadd_rn(den, part[fld.num_pieces + q]);
-  }
-  if (MODE == 0) den = __dmul_rn((double)fld.coord_rows[l], __dmul_rn(fld.x, fld.x));
+  double num, den;
+  coord_piece_sums<MODE, WIDE>(fld, part, l, lane, num, den);
+  if (WIDE && lane != 0) return;
   den = __dadd_rn(den, size_reg);
   double* cp = coef + (int64_t)(fld.offset + l) * coef_stride + coef_col;
   const double old = *cp;
@@ -203,17 +350,16 @@ __global__ void __launch_bounds__(256) fm_coord_kernel(FmField fld, const double
 
 // Sharded variant of (b), split around the caller's all-reduce (rows of a coordinate live on several GPUs):
 // (b1) per-coordinate LOCAL sums -> buf[l] = num, buf[ncoord + l] = den part (MODE 0: local row count * x^2)
-template <int MODE>
+template <int MODE, bool WIDE>
 __global__ void __launch_bounds__(256) fm_coord_partial_kernel(FmField fld, const double* __restrict__ part,
                                                                double* __restrict__ buf /*[2 x ncoord]*/) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = WIDE ? (t >> 5) : t;
+  const int lane = threadIdx.x & 31;
   if (l >= fld.ncoord) return;
-  double num = 0.0, den = 0.0;
-  for (int64_t q = fld.coord_piece[l]; q < fld.coord_piece[l + 1]; q++) {
-    num = __dadd_rn(num, part[q]);
-    if (MODE == 1) den = __dadd_rn(den, part[fld.num_pieces + q]);
-  }
-  if (MODE == 0) den = __dmul_rn((double)fld.coord_rows[l], __dmul_rn(fld.x, fld.x));
+  double num, den;
+  coord_piece_sums<MODE, WIDE>(fld, part, l, lane, num, den);
+  if (WIDE && lane != 0) return;
   buf[l] = num;
   buf[fld.ncoord + l] = den;
 }

@@ -17,7 +17,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 #include <vector>
@@ -37,15 +39,27 @@ __global__ void __launch_bounds__(256) iota_kernel(uint32_t* v, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = (uint32_t)i;
 }
 
-__global__ void __launch_bounds__(256) gather_recs_kernel(RatingSoA s, const uint32_t* __restrict__ order, int64_t n,
-                                                          RatingRec* __restrict__ out) {
+// Records are packed in reference order first (coalesced reads of the six arrays), then moved to level order as
+// whole 32-byte records: one DRAM sector per rating instead of six scattered 4 / 8-byte reads (measured
+// 710 B of DRAM reads per rating before, profiles/r1/launches_r1b_default.txt).
+__global__ void __launch_bounds__(256) pack_recs_kernel(RatingSoA s, int64_t n, RatingRec* __restrict__ out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint32_t k = order[i];
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
     RatingRec x;
     x.u = s.u[k]; x.j = s.j[k]; x.ctx = s.ctx ? s.ctx[k] : 0; x.ku = s.ku[k];
     x.kj = s.kj[k]; x.pad = 0; x.r = s.r[k];
-    out[i] = x;
+    out[k] = x;
+  }
+}
+__global__ void __launch_bounds__(256) gather_recs_kernel(const RatingRec* __restrict__ in, const uint32_t* __restrict__ order,
+                                                          int64_t n, RatingRec* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int4* src = reinterpret_cast<const int4*>(in + order[i]);
+    const int4 a = __ldg(src), b = __ldg(src + 1);
+    int4* dst = reinterpret_cast<int4*>(out + i);
+    dst[0] = a;
+    dst[1] = b;
   }
 }
 
@@ -238,19 +252,27 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
                                            cudaStream_t stream, int sm_count, StagedCopier& copier, RatingRec* d_rec,
                                            FlaggedBuild* info) {
   if (nnz == 0) return cudaSuccess;
+  const bool trace = getenv("CARS_SCHED_TRACE") != nullptr;  // host wall time of every phase, to stderr
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[cars schedule] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   RatingSoA d;
   uint32_t *d_idx = nullptr, *d_ord = nullptr, *d_skey = nullptr, *d_start = nullptr, *d_fr0 = nullptr, *d_fr1 = nullptr;
   int32_t* d_succ = nullptr;
+  RatingRec* d_tmp_rec = nullptr;
   int* d_indeg = nullptr;
   KahnCtl* d_ctl = nullptr;
   unsigned long long* d_bad = nullptr;
   void* d_temp = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaError_t e = cudaSuccess;
+  char* arena = nullptr;  // every temporary below is carved from ONE allocation (cudaMalloc / cudaFree are not free)
   auto cleanup = [&]() {
-    cudaFree(d.u); cudaFree(d.j); cudaFree(d.ctx); cudaFree(d.level); cudaFree(d.ku); cudaFree(d.kj); cudaFree(d.r);
-    cudaFree(d_idx); cudaFree(d_ord); cudaFree(d_skey); cudaFree(d_start); cudaFree(d_fr0); cudaFree(d_fr1);
-    cudaFree(d_succ); cudaFree(d_indeg); cudaFree(d_ctl); cudaFree(d_bad); cudaFree(d_temp);
+    cudaFree(arena);
     for (auto& x : ev)
       if (x) cudaEventDestroy(x);
   };
@@ -267,17 +289,47 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
   const size_t ids = (size_t)(num_users > num_items ? num_users : num_items);
   const size_t fcap = (size_t)(num_users < num_items ? num_users : num_items);  // a level has distinct users and items
   for (auto& x : ev) SG_TRY(cudaEventCreate(&x));
-  SG_TRY(cudaMalloc((void**)&d.u, N * 4));
-  SG_TRY(cudaMalloc((void**)&d.j, N * 4));
-  if (ctx) SG_TRY(cudaMalloc((void**)&d.ctx, N * 4));
-  SG_TRY(cudaMalloc((void**)&d.level, N * 4));
-  SG_TRY(cudaMalloc((void**)&d.ku, N * 4));
-  SG_TRY(cudaMalloc((void**)&d.kj, N * 4));
-  SG_TRY(cudaMalloc((void**)&d.r, N * 8));
-  SG_TRY(cudaMalloc((void**)&d_idx, N * 4));
-  SG_TRY(cudaMalloc((void**)&d_ord, N * 4));
-  SG_TRY(cudaMalloc((void**)&d_skey, N * 4));
-  SG_TRY(cudaMalloc((void**)&d_bad, 8));
+  auto bits_for = [](int64_t n_values) {
+    int b = 1;
+    while ((1ll << b) < n_values) b++;
+    return b;
+  };
+  const bool host_levels = [] {
+    const char* s = getenv("CARS_LEVELS");
+    return s && strcmp(s, "host") == 0;
+  }();
+  size_t temp_bytes = 0;  // CUB scratch: the 32-bit-key sort bounds the three sorts below
+  SG_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                         (uint32_t*)nullptr, nnz, 0, 32, stream));
+  {
+    size_t total = 0;
+    auto reserve = [&](size_t bytes) {
+      const size_t off = total;
+      total += (bytes + 255) & ~(size_t)255;
+      return off;
+    };
+    const size_t o_u = reserve(N * 4), o_j = reserve(N * 4), o_ctx = reserve(ctx ? N * 4 : 0), o_level = reserve(N * 4),
+                 o_ku = reserve(N * 4), o_kj = reserve(N * 4), o_r = reserve(N * 8), o_idx = reserve(N * 4),
+                 o_ord = reserve(N * 4), o_skey = reserve(N * 4), o_bad = reserve(8), o_temp = reserve(temp_bytes),
+                 o_tmp = reserve(N * sizeof(RatingRec));
+    size_t o_start = 0, o_succ = 0, o_indeg = 0, o_fr0 = 0, o_fr1 = 0, o_ctl = 0;
+    if (!host_levels) {
+      o_start = reserve(ids * 4); o_succ = reserve(N * 8); o_indeg = reserve(N * 4);
+      o_fr0 = reserve((fcap + 1) * 4); o_fr1 = reserve((fcap + 1) * 4); o_ctl = reserve(sizeof(KahnCtl));
+    }
+    lap("size queries");
+    SG_TRY(cudaMalloc((void**)&arena, total));
+    lap("cudaMalloc(arena)");
+    d.u = (int32_t*)(arena + o_u); d.j = (int32_t*)(arena + o_j); d.ctx = ctx ? (int32_t*)(arena + o_ctx) : nullptr;
+    d.level = (int32_t*)(arena + o_level); d.ku = (int32_t*)(arena + o_ku); d.kj = (int32_t*)(arena + o_kj);
+    d.r = (double*)(arena + o_r); d_idx = (uint32_t*)(arena + o_idx); d_ord = (uint32_t*)(arena + o_ord);
+    d_skey = (uint32_t*)(arena + o_skey); d_bad = (unsigned long long*)(arena + o_bad); d_temp = arena + o_temp;
+    d_tmp_rec = (RatingRec*)(arena + o_tmp);
+    if (!host_levels) {
+      d_start = (uint32_t*)(arena + o_start); d_succ = (int32_t*)(arena + o_succ); d_indeg = (int*)(arena + o_indeg);
+      d_fr0 = (uint32_t*)(arena + o_fr0); d_fr1 = (uint32_t*)(arena + o_fr1); d_ctl = (KahnCtl*)(arena + o_ctl);
+    }
+  }
 
   // ---- the caller's arrays cross PCIe ------------------------------------------------------------------
   SG_TRY(cudaEventRecord(ev[0], stream));
@@ -286,6 +338,7 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
     SG_TRY(copier.run(segs, 4, true));
   }
   info->h2d_bytes += nnz * (ctx ? 20 : 16);
+  lap("H2D of u, j, ctx, r");
   SG_TRY(cudaEventRecord(ev[1], stream));
   const int blocks = sm_count * 8;
   SG_TRY(cudaMemsetAsync(d_bad, 0xff, 8, stream));
@@ -296,6 +349,7 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
   SG_TRY(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, stream));
   SG_TRY(cudaStreamSynchronize(stream));
   info->kernel_launches += 1;
+  lap("validate + sync");
   if (bad != ~0ull) {
     info->bad_index = (int64_t)bad;
     cleanup();
@@ -305,32 +359,10 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
   iota_kernel<<<blocks, 256, 0, stream>>>(d_idx, nnz);
   SG_TRY(cudaGetLastError());
   info->kernel_launches += 1;
-  size_t temp_bytes = 0, need = 0;
-  auto bits_for = [](int64_t n_values) {
-    int b = 1;
-    while ((1ll << b) < n_values) b++;
-    return b;
-  };
-  const bool host_levels = [] {
-    const char* s = getenv("CARS_LEVELS");
-    return s && strcmp(s, "host") == 0;
-  }();
   if (!host_levels) {
-    SG_TRY(cudaMalloc((void**)&d_start, ids * 4));
-    SG_TRY(cudaMalloc((void**)&d_succ, N * 8));
-    SG_TRY(cudaMalloc((void**)&d_indeg, N * 4));
-    SG_TRY(cudaMalloc((void**)&d_fr0, (fcap + 1) * 4));
-    SG_TRY(cudaMalloc((void**)&d_fr1, (fcap + 1) * 4));
-    SG_TRY(cudaMalloc((void**)&d_ctl, sizeof(KahnCtl)));
     SG_TRY(cudaMemsetAsync(d_ctl, 0, sizeof(KahnCtl), stream));
     // chains: stable sort by user, then by item
     const int bu = bits_for(num_users), bj = bits_for(num_items);
-    SG_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t*)d.u, d_skey, d_idx, d_ord, nnz, 0, bu, stream));
-    SG_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, (const uint32_t*)d.j, d_skey, d_idx, d_ord, nnz, 0, bj, stream));
-    if (need > temp_bytes) temp_bytes = need;
-    SG_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, (const uint32_t*)d.level, d_skey, d_idx, d_ord, nnz, 0, 32, stream));
-    if (need > temp_bytes) temp_bytes = need;
-    SG_TRY(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 1));
     for (int which = 0; which < 2; which++) {
       const uint32_t* keys = (const uint32_t*)(which == 0 ? d.u : d.j);
       size_t tb = temp_bytes;
@@ -354,6 +386,7 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
     SG_TRY(cudaMemcpyAsync(&ctl, d_ctl, sizeof ctl, cudaMemcpyDeviceToHost, stream));
     SG_TRY(cudaEventRecord(ev[2], stream));
     SG_TRY(cudaStreamSynchronize(stream));
+    lap("chains + Kahn levels + sync");
     if ((int64_t)ctl.processed != nnz) {  // cannot happen for chains built above; refuse rather than train garbage
       cleanup();
       return cudaErrorUnknown;
@@ -376,8 +409,6 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
     CopySeg segs[3] = {{d.level, hl.data(), N * 4}, {d.ku, hku.data(), N * 4}, {d.kj, hkj.data(), N * 4}};
     SG_TRY(copier.run(segs, 3, true));
     info->h2d_bytes += nnz * 12;
-    SG_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t*)d.level, d_skey, d_idx, d_ord, nnz, 0, 32, stream));
-    SG_TRY(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 1));
     SG_TRY(cudaEventRecord(ev[2], stream));
   }
 
@@ -387,16 +418,20 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
     SG_TRY(cub::DeviceRadixSort::SortPairs(d_temp, tb, (const uint32_t*)d.level, d_skey, d_idx, d_ord, nnz, 0,
                                            bits_for(info->num_levels + 1), stream));
   }
-  gather_recs_kernel<<<blocks, 256, 0, stream>>>(d, d_ord, nnz, d_rec);
+  pack_recs_kernel<<<blocks, 256, 0, stream>>>(d, nnz, d_tmp_rec);
   SG_TRY(cudaGetLastError());
-  info->kernel_launches += 2;
+  gather_recs_kernel<<<blocks, 256, 0, stream>>>(d_tmp_rec, d_ord, nnz, d_rec);
+  SG_TRY(cudaGetLastError());
+  info->kernel_launches += 3;
   SG_TRY(cudaEventRecord(ev[3], stream));
   SG_TRY(cudaStreamSynchronize(stream));
   float ms = 0.f;
+  lap("level sort + pack + sync");
   if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) info->copy_ms = ms;
   if (cudaEventElapsedTime(&ms, ev[1], ev[2]) == cudaSuccess) info->levels_ms = ms;
   if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) info->pack_ms = ms;
   cleanup();
+  lap("cudaFree(arena)");
 #undef SG_TRY
   return cudaSuccess;
 }

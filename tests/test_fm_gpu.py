@@ -31,7 +31,13 @@ def run_gpu(ts, arrs, k, D, iters):
 
 @pytest.mark.parametrize("users,items,dims,nnz,k", [(12, 9, [2, 3], 150, 3), (300, 120, [4, 8], 20000, 16),
                                                     (2000, 50, [32], 60000, 8), (50, 2000, [3, 3, 3], 30000, 64)])
-def test_fm_matches_sparse_oracle(oracle, cars_lib, users, items, dims, nnz, k):
+@pytest.mark.parametrize("block_rows", [None, "700"])
+def test_fm_matches_sparse_oracle(oracle, cars_lib, monkeypatch, users, items, dims, nnz, k, block_rows):
+    # block_rows: the engine's internal row order (item block, context, caller's order) with tiny blocks, so the
+    # permuted layout the big inputs use is exercised at oracle sizes; results do not depend on it beyond rounding
+    if block_rows is not None:
+        monkeypatch.setenv("CARS_FM_BLOCK_ROWS", block_rows)
+        monkeypatch.setenv("CARS_FM_DENSE_MIN_ROWS", "0")  # and the streaming reduce of the context field
     ts, _, prob, arrs = fm_inputs(oracle, users, items, dims, nnz, k, seed=7)
     iters = 3
     got, losses, st = run_gpu(ts, arrs, k, len(dims), iters)

@@ -105,9 +105,26 @@ def test_dataflow_loss_is_deterministic(oracle, cars_lib):
     assert runs[0] == runs[1] == runs[2]
 
 
-def test_camf_c_exact_serial_kernel(oracle, cars_lib):
-    ts, _ = synth.make_training_set(90, 120, [7, 7, 2, 3, 2, 9, 5, 4], 3000, seed=21, order="shuffled")
-    ref, got, rl, gl, st = run_both(oracle, capi.CAMF_C, ts, 10, epochs=3, seed=5)
+@pytest.mark.parametrize("F,order", [(10, "shuffled"), (10, "user_sorted"), (1, "user_sorted"), (64, "shuffled"), (100, "user_sorted")])
+def test_camf_c_exact_serial_kernel(oracle, cars_lib, F, order):
+    # user_sorted order makes consecutive ratings share user, item (same pair, other context) and conditions
+    ts, _ = synth.make_training_set(90, 120, [7, 7, 2, 3, 2, 9, 5, 4], 3000, seed=21, order=order)
+    ref, got, rl, gl, st = run_both(oracle, capi.CAMF_C, ts, F, epochs=3, seed=5)
+    assert_bit_identical(ref, got)
+    np.testing.assert_allclose(gl, rl, rtol=LOSS_RTOL, atol=0)
+
+
+def test_camf_c_ragged_contexts(oracle, cars_lib):
+    # contexts of different lengths (and an empty one) put one condition id at different positions of the table
+    rng = np.random.default_rng(3)
+    ts, _ = synth.make_training_set(40, 30, [3, 4, 2], 1500, seed=8, order="user_sorted")
+    ctxs = [[], [0], [3, 0], [1, 4, 7], [7], [8, 2], [5, 8, 1]]
+    ptr = np.cumsum([0] + [len(c) for c in ctxs]).astype(np.int32)
+    cond = np.array([x for c in ctxs for x in c], dtype=np.int32)
+    ts2 = capi.TrainingSet(num_users=ts.num_users, num_items=ts.num_items, u=ts.u, j=ts.j, r=ts.r,
+                           ctx=rng.integers(0, len(ctxs), ts.nnz).astype(np.int32), num_conditions=9,
+                           num_contexts=len(ctxs), ctx_ptr=ptr, ctx_cond=cond, global_mean=ts.global_mean)
+    ref, got, rl, gl, st = run_both(oracle, capi.CAMF_C, ts2, 10, epochs=3, seed=5)
     assert_bit_identical(ref, got)
     np.testing.assert_allclose(gl, rl, rtol=LOSS_RTOL, atol=0)
 
