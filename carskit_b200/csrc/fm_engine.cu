@@ -30,7 +30,7 @@ struct cars_fm_handle {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int32_t U = 0, I = 0, C = 0, p = 0, k = 0, D = 1;
-  int64_t N = 0, Nglobal = 0;
+  int64_t N = 0, Nglobal = 0, Nq = 0;  // Nq: row stride of Qc (N rounded up to even: 16-byte aligned factor rows)
   double reg_lw = 0, reg_lf = 0, w0_denom = 1, xc = 1;
   int32_t *d_u = nullptr, *d_j = nullptr, *d_c = nullptr;
   double *d_r = nullptr, *d_e = nullptr, *d_Qc = nullptr;
@@ -41,7 +41,6 @@ struct cars_fm_handle {
   int red_blocks = 0;
   FieldStore fld[3];
   bool uploaded = false, prepared = false;
-  bool fuse_update = true;  // CARS_FM_FUSE=0: the row update before a streaming reduce stays a kernel of its own
   int64_t launches = 0, h2d = 0, d2h = 0;
   cudaEvent_t ev_beg = nullptr, ev_end = nullptr;
   double last_iter_ms = 0;
@@ -174,7 +173,8 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
   const int64_t N = h->N;
   FM_TRY_H(fm_alloc(&h->d_u, (size_t)N)); FM_TRY_H(fm_alloc(&h->d_j, (size_t)N)); FM_TRY_H(fm_alloc(&h->d_c, (size_t)N));
   FM_TRY_H(fm_alloc(&h->d_r, (size_t)N)); FM_TRY_H(fm_alloc(&h->d_e, (size_t)N));
-  FM_TRY_H(fm_alloc(&h->d_Qc, (size_t)N * h->k));
+  h->Nq = (N + 1) & ~(int64_t)1;
+  FM_TRY_H(fm_alloc(&h->d_Qc, (size_t)h->Nq * h->k));
   FM_TRY_H(fm_alloc(&h->d_w0, 1)); FM_TRY_H(fm_alloc(&h->d_w, (size_t)h->p)); FM_TRY_H(fm_alloc(&h->d_V, (size_t)h->p * h->k));
   try {
     // Internal row order.  The rows (errors[n], Q[n][f]) are private to the engine, and every sum of the sweep
@@ -230,11 +230,8 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
     if ((rc = build_field(h, 2, cc, h->C, h->U + h->I, h->xc, ctx_dense))) return bail(rc);
     if (ctx_dense) {
       const int smem = (int)((size_t)h->C * kDenseThreads * sizeof(double2));
-      FM_TRY_H(cudaFuncSetAttribute(fm_dense_reduce_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      FM_TRY_H(cudaFuncSetAttribute(fm_dense_reduce_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      FM_TRY_H(cudaFuncSetAttribute(fm_dense_reduce_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      FM_TRY_H(cudaFuncSetAttribute(fm_dense_reduce_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      if (const char* e = getenv("CARS_FM_FUSE")) h->fuse_update = atoi(e) != 0;
+      FM_TRY_H(cudaFuncSetAttribute(fm_dense_reduce_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      FM_TRY_H(cudaFuncSetAttribute(fm_dense_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
   } catch (...) {
     fm_fail(h, CARS_E_OOM, "host allocation failed");
@@ -288,7 +285,7 @@ extern "C" int cars_fm_prepare(cars_fm_handle* h) {
   if (h->N) {
     const unsigned blocks = (unsigned)((h->N + 255) / 256);
     fm_prepare_kernel<<<blocks, 256, 0, h->stream>>>(h->d_u, h->d_j, h->d_c, h->d_r, h->d_w, h->d_V, h->d_w0, h->U, h->I,
-                                                    h->p, h->k, h->xc, h->N, h->d_e, h->d_Qc);
+                                                    h->p, h->k, h->xc, h->N, h->Nq, h->d_e, h->d_Qc);
     FM_TRY(h, cudaGetLastError());
     h->launches++;
   }
@@ -299,8 +296,8 @@ extern "C" int cars_fm_prepare(cars_fm_handle* h) {
 
 // One sweep over the three fields (users, items, contexts) for one coefficient column: per field
 // (a) reduce -> (b) new coordinates + deltas [all-reduce of the per-coordinate sums in between when sharded] ->
-// (c) row update.  When the NEXT field is reduced by the streaming kernel, (c) is not launched: the pending update
-// rides along in that field's reduce (fm_dense_reduce_kernel<.., FUSED = true>).
+// (c) row update.  (Fusing (c) into the next field's streaming reduce was measured slower -- 416 us against
+// 189 + 158 us, profiles/r1/launches_r1b_fm_fused.txt -- and is not kept.)
 struct FmExchange {  // row-sharded run: caller's device buffer and all-reduce (cars_fm_iteration_sharded)
   double* dev_buf = nullptr;
   cars_allreduce_fn ar = nullptr;
@@ -309,7 +306,6 @@ struct FmExchange {  // row-sharded run: caller's device buffer and all-reduce (
 
 template <int MODE>
 static int field_sweep(cars_fm_handle* h, double* coef, int stride, int col, double* Qf, double size_reg, const FmExchange* ex) {
-  int pending = -1;  // field whose row update has not been applied yet
   for (int which = 0; which < 3; which++) {
     FieldStore& fs = h->fld[which];
     const FmField& f = fs.f;
@@ -317,13 +313,8 @@ static int field_sweep(cars_fm_handle* h, double* coef, int stride, int col, dou
     // (a)
     if (f.dense_blocks > 0) {
       const size_t smem = (size_t)f.ncoord * kDenseThreads * sizeof(double2);
-      if (pending >= 0)
-        fm_dense_reduce_kernel<MODE, true><<<f.dense_blocks, kDenseThreads, smem, h->stream>>>(
-            f, h->d_e, Qf, coef, stride, col, h->N, h->d_part, h->fld[pending].f, h->fld[pending].d_delta);
-      else
-        fm_dense_reduce_kernel<MODE, false><<<f.dense_blocks, kDenseThreads, smem, h->stream>>>(f, h->d_e, Qf, coef, stride, col,
-                                                                                               h->N, h->d_part, f, nullptr);
-      pending = -1;
+      fm_dense_reduce_kernel<MODE><<<f.dense_blocks, kDenseThreads, smem, h->stream>>>(f, h->d_e, Qf, coef, stride, col, h->N,
+                                                                                      h->d_part);
       FM_TRY(h, cudaGetLastError());
       h->launches++;
     } else if (f.num_pieces > 0) {
@@ -355,15 +346,9 @@ static int field_sweep(cars_fm_handle* h, double* coef, int stride, int col, dou
     }
     // (c)
     if (h->N == 0) continue;
-    int next = which + 1;
-    while (next < 3 && h->fld[next].f.ncoord == 0) next++;
-    if (h->fuse_update && next < 3 && h->fld[next].f.dense_blocks > 0) {
-      pending = which;
-    } else {
-      fm_row_update_kernel<MODE><<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(f, fs.d_delta, h->N, h->d_e, Qf);
-      FM_TRY(h, cudaGetLastError());
-      h->launches++;
-    }
+    fm_row_update_kernel<MODE><<<(unsigned)(((h->N + 1) / 2 + 255) / 256), 256, 0, h->stream>>>(f, fs.d_delta, h->N, h->d_e, Qf);
+    FM_TRY(h, cudaGetLastError());
+    h->launches++;
   }
   return CARS_OK;
 }
@@ -387,7 +372,7 @@ extern "C" int cars_fm_iteration(cars_fm_handle* h, double* loss_out) {
   // V_lf, f = 0..k-1 { l = 0..p-1 } (:194-217)
   const double v_reg = (double)h->Nglobal * h->reg_lf;
   for (int f = 0; f < h->k; f++)
-    if ((rc = field_sweep<1>(h, h->d_V, h->k, f, h->d_Qc + (int64_t)f * h->N, v_reg, nullptr))) return rc;
+    if ((rc = field_sweep<1>(h, h->d_V, h->k, f, h->d_Qc + (int64_t)f * h->Nq, v_reg, nullptr))) return rc;
   FM_TRY(h, cudaEventRecord(h->ev_end, h->stream));
   FM_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   FM_TRY(h, cudaStreamSynchronize(h->stream));
@@ -432,7 +417,7 @@ extern "C" int cars_fm_iteration_sharded(cars_fm_handle* h, double* dev_buf, car
   if ((rc = field_sweep<0>(h, h->d_w, 1, 0, nullptr, w_reg, &ex))) return rc;
   const double v_reg = (double)h->Nglobal * h->reg_lf;
   for (int f = 0; f < h->k; f++)
-    if ((rc = field_sweep<1>(h, h->d_V, h->k, f, h->d_Qc + (int64_t)f * h->N, v_reg, &ex))) return rc;
+    if ((rc = field_sweep<1>(h, h->d_V, h->k, f, h->d_Qc + (int64_t)f * h->Nq, v_reg, &ex))) return rc;
   FM_TRY(h, cudaEventRecord(h->ev_end, h->stream));
   FM_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   FM_TRY(h, cudaStreamSynchronize(h->stream));

@@ -11,8 +11,7 @@
 // coordinate, (c) e_n += delta*x (and Qc[n][f] += delta*x) for the rows of that coordinate.
 // (a) is a deterministic two-level reduction: rows sorted by coordinate are cut into pieces of <= 256
 // rows, one warp sums a piece in a fixed order, one thread (or warp) sums a coordinate's pieces in order.
-// Fields with few coordinates (contexts) are reduced by streaming the rows instead (fm_dense_reduce_kernel),
-// with the previous field's row update fused in.
+// Fields with few coordinates (contexts) are reduced by streaming the rows instead (fm_dense_reduce_kernel).
 // Arithmetic: fp64, no FMA contraction in the update formulas (Java semantics); sums are tree-ordered, so
 // results equal the sparse oracle's up to summation order (tolerance stated in tests/test_fm_gpu.py).
 #pragma once
@@ -78,8 +77,8 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(const int32_t* __restri
                                                          const int32_t* __restrict__ c, const double* __restrict__ r,
                                                          const double* __restrict__ w, const double* __restrict__ V,
                                                          const double* __restrict__ w0p, int U, int I, int p, int k,
-                                                         double xc, int64_t N, double* __restrict__ e,
-                                                         double* __restrict__ Qc) {
+                                                         double xc, int64_t N, int64_t Nq /*Qc row stride*/,
+                                                         double* __restrict__ e, double* __restrict__ Qc) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int uu = u[n], jj = j[n], cc = c[n];
@@ -90,7 +89,7 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(const int32_t* __restri
     v = __dadd_rn(v, V[(int64_t)uu * k + f]);
     v = __dadd_rn(v, V[(int64_t)(U + jj) * k + f]);
     if (ic < p) v = __dadd_rn(v, __dmul_rn(V[(int64_t)ic * k + f], xc));
-    Qc[(int64_t)f * N + n] = v;
+    Qc[(int64_t)f * Nq + n] = v;
   }
 }
 
@@ -201,15 +200,11 @@ __global__ void __launch_bounds__(256) fm_piece_reduce_kernel(FmField fld, const
 // coalesced, and every thread adds a row's terms into ITS OWN accumulator of the row's coordinate in shared
 // memory (bins[coordinate][thread]: no conflicts, fixed order).  A CTA owns a fixed slice of rows; its per-
 // coordinate sums (fixed-order tree over the threads) go to part[(block * ncoord + c) * 2 + {0, 1}].  Deterministic.
-// FUSED: the pending row update of the PREVIOUS field's step (e_n += delta x, Qc[n][f] += delta x -- what
-// fm_row_update_kernel does) is applied on the way: both are streaming passes over the same rows, so the fused
-// pass saves one full read of e and Qc[f].  Same arithmetic in the same order as the two separate kernels.
-template <int MODE, bool FUSED>
-__global__ void __launch_bounds__(kDenseThreads) fm_dense_reduce_kernel(FmField fld, double* __restrict__ e,
-                                                                        double* __restrict__ Qf,
+template <int MODE>
+__global__ void __launch_bounds__(kDenseThreads) fm_dense_reduce_kernel(FmField fld, const double* __restrict__ e,
+                                                                        const double* __restrict__ Qf,
                                                                         const double* __restrict__ coef, int coef_stride,
-                                                                        int coef_col, int64_t N, double* __restrict__ part,
-                                                                        FmField prev, const double* __restrict__ prev_delta) {
+                                                                        int coef_col, int64_t N, double* __restrict__ part) {
   extern __shared__ __align__(16) unsigned char dense_smem[];
   double2* bins = reinterpret_cast<double2*>(dense_smem);  // [ncoord][kDenseThreads]
   __shared__ double cls[kDenseMaxCoord];
@@ -238,43 +233,18 @@ __global__ void __launch_bounds__(kDenseThreads) fm_dense_reduce_kernel(FmField 
   };
   int64_t n = beg + tid;
   for (; n + (UNR - 1) * T < end; n += UNR * T) {
-    int c[UNR], lp[UNR];
+    int c[UNR];
     double en[UNR], qn[UNR];
 #pragma unroll
     for (int k = 0; k < UNR; k++) {
       c[k] = fld.coord_of_row[n + k * T];
       en[k] = e[n + k * T];
       qn[k] = MODE == 1 ? Qf[n + k * T] : 0.0;
-      lp[k] = FUSED ? prev.coord_of_row[n + k * T] : -1;
     }
 #pragma unroll
-    for (int k = 0; k < UNR; k++) {
-      if (FUSED && lp[k] >= 0) {
-        const double d = __dmul_rn(prev_delta[lp[k]], prev.x);
-        en[k] = __dadd_rn(en[k], d);
-        e[n + k * T] = en[k];
-        if (MODE == 1) {
-          qn[k] = __dadd_rn(qn[k], d);
-          Qf[n + k * T] = qn[k];
-        }
-      }
-      add_row(c[k], en[k], qn[k]);
-    }
+    for (int k = 0; k < UNR; k++) add_row(c[k], en[k], qn[k]);
   }
-  for (; n < end; n += T) {
-    double en = e[n], qn = MODE == 1 ? Qf[n] : 0.0;
-    const int lp = FUSED ? prev.coord_of_row[n] : -1;
-    if (FUSED && lp >= 0) {
-      const double d = __dmul_rn(prev_delta[lp], prev.x);
-      en = __dadd_rn(en, d);
-      e[n] = en;
-      if (MODE == 1) {
-        qn = __dadd_rn(qn, d);
-        Qf[n] = qn;
-      }
-    }
-    add_row(fld.coord_of_row[n], en, qn);
-  }
+  for (; n < end; n += T) add_row(fld.coord_of_row[n], e[n], MODE == 1 ? Qf[n] : 0.0);
   __syncthreads();
   for (int c = warp; c < nc; c += T / 32) {
     double a = 0.0, b = 0.0;
@@ -396,17 +366,36 @@ __global__ void fm_w0_finish_global_kernel(const double* __restrict__ buf, doubl
   *w0p = up;
 }
 
-// (c) row-parallel: e_n += (new - old) x ; V step also Qc[n][f] += (new - old) x  (:184-185, :208-211)
+// (c) row-parallel: e_n += (new - old) x ; V step also Qc[n][f] += (new - old) x  (:184-185, :208-211).
+// Two consecutive rows per thread with 16-byte accesses (e and every Qc[f] start 16-byte aligned: the Qc row
+// stride is padded to even).
 template <int MODE>
 __global__ void __launch_bounds__(256) fm_row_update_kernel(FmField fld, const double* __restrict__ delta, int64_t N,
                                                             double* __restrict__ e, double* __restrict__ Qf) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
   if (n >= N) return;
-  const int l = fld.coord_of_row[n];
-  if (l < 0) return;
-  const double d = __dmul_rn(delta[l], fld.x);
-  e[n] = __dadd_rn(e[n], d);
-  if (MODE == 1) Qf[n] = __dadd_rn(Qf[n], d);
+  if (n + 1 < N) {
+    const int2 l = *reinterpret_cast<const int2*>(fld.coord_of_row + n);
+    if (l.x < 0 && l.y < 0) return;
+    const double d0 = l.x >= 0 ? __dmul_rn(delta[l.x], fld.x) : 0.0;
+    const double d1 = l.y >= 0 ? __dmul_rn(delta[l.y], fld.x) : 0.0;
+    double2 ev = *reinterpret_cast<double2*>(e + n);
+    if (l.x >= 0) ev.x = __dadd_rn(ev.x, d0);
+    if (l.y >= 0) ev.y = __dadd_rn(ev.y, d1);
+    *reinterpret_cast<double2*>(e + n) = ev;
+    if (MODE == 1) {
+      double2 qv = *reinterpret_cast<double2*>(Qf + n);
+      if (l.x >= 0) qv.x = __dadd_rn(qv.x, d0);
+      if (l.y >= 0) qv.y = __dadd_rn(qv.y, d1);
+      *reinterpret_cast<double2*>(Qf + n) = qv;
+    }
+  } else {
+    const int l = fld.coord_of_row[n];
+    if (l < 0) return;
+    const double d = __dmul_rn(delta[l], fld.x);
+    e[n] = __dadd_rn(e[n], d);
+    if (MODE == 1) Qf[n] = __dadd_rn(Qf[n], d);
+  }
 }
 
 // sum_l (regLw * w_l) * w_l over all p coordinates, deterministic (one block)
