@@ -54,6 +54,12 @@ WORKLOADS = {
     # FM (reference ALS semantics, FM.java); BASELINE.json configs[3] shape scaled to one GPU's share
     "fm_k64_250Kx25Kx32c_25M": dict(model="fm", F=64, users=250_000, items=25_000, dims=[32], nnz=25_000_000,
                                     seed=20261017),
+    # BASELINE.json configs[3] at full size: 5 M users x 500 K items x 32 contexts, 500 M rows over 4 GPUs (125 M per rank)
+    "fm_k64_5Mx500Kx32c_125M_per_gpu": dict(model="fm", F=64, users=5_000_000, items=500_000, dims=[32], nnz=125_000_000,
+                                            seed=20261017),
+    # BASELINE.json configs[4] at full size: 10 M users (1.25 M per rank) x 1 M items x 64 conditions, 1 B ratings over 8 GPUs
+    "camf_cu_f128_1250Kx1Mx64c_125M_per_gpu": dict(model="camf_cu", F=128, users=1_250_000, items=1_000_000,
+                                                   dims=[16, 16, 16, 16], nnz=125_000_000, seed=20261017),
     "fm_k16_tiny": dict(model="fm", F=16, users=5_000, items=1_000, dims=[32], nnz=200_000, seed=20261017),
 }
 DEFAULT_WORKLOAD = "camf_ci_f64_1Mx100Kx32c_100M"

@@ -2,6 +2,8 @@
 // No CPU implementation exists here: without a CUDA sm_100 device cars_fm_create() fails.
 #include "../../include/carskit_b200.h"
 #include "fm_kernels.cuh"
+#include "fm_setup.cuh"
+#include "staged_copy.cuh"
 
 #include <cuda_runtime.h>
 
@@ -17,6 +19,7 @@ using namespace carsfm;
 static thread_local std::string g_fm_create_error = "";
 
 struct FieldStore {
+  bool owns_coord = true;  // users / items: coord_of_row IS the engine's u / j array
   int32_t *d_coord_of_row = nullptr, *d_perm = nullptr, *d_piece_coord = nullptr;
   int64_t *d_piece_beg = nullptr, *d_coord_piece = nullptr, *d_coord_rows = nullptr;
   double* d_delta = nullptr;
@@ -44,6 +47,7 @@ struct cars_fm_handle {
   int64_t launches = 0, h2d = 0, d2h = 0;
   cudaEvent_t ev_beg = nullptr, ev_end = nullptr;
   double last_iter_ms = 0;
+  cars::StagedCopier copier;
 };
 
 static int fm_fail(cars_fm_handle* h, int code, const char* fmt, ...) {
@@ -67,57 +71,81 @@ static int fm_fail(cars_fm_handle* h, int code, const char* fmt, ...) {
 template <typename T>
 static cudaError_t fm_alloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), (n ? n : 1) * sizeof(T)); }
 
-template <typename T>
-static cudaError_t fm_put(cars_fm_handle* h, T** dst, const std::vector<T>& v) {
-  cudaError_t e = fm_alloc(dst, v.size());
-  if (e != cudaSuccess) return e;
-  if (!v.empty()) e = cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream);
-  h->h2d += (int64_t)(v.size() * sizeof(T));
-  return e;
-}
-
-// rows sorted by coordinate (stable counting sort), cut into pieces of <= kPiece rows
+// One field on the device: rows sorted by coordinate (stable radix sort; rows without the feature last), cut into
+// pieces of <= kPiece rows.  `coord` is the device array of the rows' coordinates (-1 = absent); `scratch_*` are
+// caller-provided buffers of N uint32 each, `d_temp` CUB scratch.
 static const int64_t kPiece = 256;
-static int build_field(cars_fm_handle* h, int which, const std::vector<int32_t>& coord_of_row, int32_t ncoord,
-                       int32_t offset, double x, bool dense) {
+struct FmScratch {
+  uint32_t *key = nullptr, *key_out = nullptr, *idx = nullptr;  // [N] each; idx = 0..N-1
+  void* temp = nullptr;
+  size_t temp_bytes = 0;
+};
+static int build_field(cars_fm_handle* h, int which, int32_t* coord, bool owns_coord, int32_t ncoord, int32_t offset, double x,
+                       bool dense, const FmScratch& sc) {
   FieldStore& fs = h->fld[which];
   const int64_t N = h->N;
-  std::vector<int64_t> start((size_t)ncoord + 1, 0);
-  for (int64_t n = 0; n < N; n++)
-    if (coord_of_row[n] >= 0) start[(size_t)coord_of_row[n] + 1]++;
-  std::vector<int64_t> rows((size_t)ncoord);
-  for (int32_t l = 0; l < ncoord; l++) { rows[l] = start[(size_t)l + 1]; start[(size_t)l + 1] += start[l]; }
-  const int64_t total = start[ncoord];
-  std::vector<int32_t> perm((size_t)total);
+  const int blocks = h->sm_count * 8;
+  fs.d_coord_of_row = coord;
+  fs.owns_coord = owns_coord;
+  unsigned long long* d_rows = nullptr;
+  long long *d_np = nullptr, *d_start = nullptr;
+  auto drop = [&]() { cudaFree(d_rows); cudaFree(d_np); cudaFree(d_start); };
+#define BF_TRY(expr)                                                                                    \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      drop();                                                                                           \
+      return fm_fail(h, _e == cudaErrorMemoryAllocation ? CARS_E_OOM : CARS_E_CUDA, "%s failed: %s", #expr, \
+                     cudaGetErrorString(_e));                                                           \
+    }                                                                                                   \
+  } while (0)
+  const size_t nc1 = (size_t)ncoord + 1;
+  BF_TRY(fm_alloc(&d_rows, nc1));
+  BF_TRY(fm_alloc(&d_np, nc1));
+  BF_TRY(fm_alloc(&d_start, nc1));
+  BF_TRY(fm_alloc(&fs.d_coord_rows, nc1));
+  BF_TRY(fm_alloc(&fs.d_coord_piece, nc1));
+  BF_TRY(fm_alloc(&fs.d_perm, (size_t)N));
+  BF_TRY(fm_alloc(&fs.d_delta, (size_t)ncoord));
+  BF_TRY(cudaMemsetAsync(d_rows, 0, nc1 * 8, h->stream));
+  long long tot[2] = {0, 0};  // rows that carry the feature, pieces
+  if (N > 0) {
+    fms_field_key_kernel<<<blocks, 256, 0, h->stream>>>(coord, N, ncoord, sc.key, d_rows);
+    BF_TRY(cudaGetLastError());
+    int bits = 1;
+    while ((1ll << bits) < (long long)ncoord + 1) bits++;
+    size_t tb = sc.temp_bytes;
+    BF_TRY(cub::DeviceRadixSort::SortPairs(sc.temp, tb, sc.key, sc.key_out, sc.idx, reinterpret_cast<uint32_t*>(fs.d_perm), N, 0,
+                                           bits, h->stream));
+    h->launches += 2;
+  }
+  fms_piece_count_kernel<<<(unsigned)((nc1 + 255) / 256), 256, 0, h->stream>>>(d_rows, ncoord, kPiece,
+                                                                              reinterpret_cast<long long*>(fs.d_coord_rows), d_np);
+  BF_TRY(cudaGetLastError());
   {
-    std::vector<int64_t> cur(start.begin(), start.end() - 1);
-    for (int64_t n = 0; n < N; n++)
-      if (coord_of_row[n] >= 0) perm[(size_t)cur[coord_of_row[n]]++] = (int32_t)n;
+    size_t tb = sc.temp_bytes;
+    BF_TRY(cub::DeviceScan::ExclusiveSum(sc.temp, tb, reinterpret_cast<long long*>(fs.d_coord_rows), d_start, (int)nc1, h->stream));
+    tb = sc.temp_bytes;
+    BF_TRY(cub::DeviceScan::ExclusiveSum(sc.temp, tb, d_np, reinterpret_cast<long long*>(fs.d_coord_piece), (int)nc1, h->stream));
   }
-  std::vector<int64_t> piece_beg, coord_piece((size_t)ncoord + 1);
-  std::vector<int32_t> piece_coord;
-  for (int32_t l = 0; l < ncoord; l++) {
-    coord_piece[l] = (int64_t)piece_coord.size();
-    for (int64_t b = start[l]; b < start[(size_t)l + 1]; b += kPiece) {
-      piece_beg.push_back(b);
-      piece_coord.push_back(l);
-    }
-  }
-  coord_piece[ncoord] = (int64_t)piece_coord.size();
-  piece_beg.push_back(total);
-  // a piece must end where its coordinate ends: piece_beg[q + 1] of the last piece of l is start[l + 1]
-  // (pieces are contiguous within a coordinate and coordinates are contiguous in perm, so it is).
-  FM_TRY(h, fm_put(h, &fs.d_coord_of_row, coord_of_row));
-  FM_TRY(h, fm_put(h, &fs.d_perm, perm));
-  FM_TRY(h, fm_put(h, &fs.d_piece_beg, piece_beg));
-  FM_TRY(h, fm_put(h, &fs.d_piece_coord, piece_coord));
-  FM_TRY(h, fm_put(h, &fs.d_coord_piece, coord_piece));
-  FM_TRY(h, fm_put(h, &fs.d_coord_rows, rows));
-  FM_TRY(h, fm_alloc(&fs.d_delta, (size_t)ncoord));
-  FM_TRY(h, cudaStreamSynchronize(h->stream));
+  BF_TRY(cudaMemcpyAsync(&tot[0], d_start + ncoord, 8, cudaMemcpyDeviceToHost, h->stream));
+  BF_TRY(cudaMemcpyAsync(&tot[1], fs.d_coord_piece + ncoord, 8, cudaMemcpyDeviceToHost, h->stream));
+  BF_TRY(cudaStreamSynchronize(h->stream));
+  h->launches += 3;
+  const int64_t total = tot[0], num_pieces = dense ? 0 : tot[1];
+  BF_TRY(fm_alloc(&fs.d_piece_beg, (size_t)num_pieces + 1));
+  BF_TRY(fm_alloc(&fs.d_piece_coord, (size_t)num_pieces));
+  fms_piece_fill_kernel<<<(unsigned)((num_pieces + 1 + 255) / 256), 256, 0, h->stream>>>(
+      reinterpret_cast<long long*>(fs.d_coord_piece), d_start, ncoord, num_pieces, kPiece, total,
+      reinterpret_cast<long long*>(fs.d_piece_beg), fs.d_piece_coord);
+  BF_TRY(cudaGetLastError());
+  BF_TRY(cudaStreamSynchronize(h->stream));
+  h->launches++;
+  drop();
+#undef BF_TRY
   fs.f.coord_of_row = fs.d_coord_of_row; fs.f.perm = fs.d_perm; fs.f.piece_beg = fs.d_piece_beg;
   fs.f.piece_coord = fs.d_piece_coord; fs.f.coord_piece = fs.d_coord_piece; fs.f.coord_rows = fs.d_coord_rows;
-  fs.f.num_pieces = (int64_t)piece_coord.size(); fs.f.ncoord = ncoord; fs.f.offset = offset; fs.f.x = x;
+  fs.f.num_pieces = num_pieces; fs.f.ncoord = ncoord; fs.f.offset = offset; fs.f.x = x;
   fs.f.dense_blocks = dense ? h->sm_count * 3 : 0;
   fs.wide = dense || (ncoord > 0 && fs.f.num_pieces / ncoord >= 8);
   if (fs.f.num_pieces > h->max_pieces) h->max_pieces = fs.f.num_pieces;
@@ -142,9 +170,6 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess || prop.major != 10)
     return fm_fail(nullptr, CARS_E_NO_DEVICE, "device %d is not sm_100", d->device);
-  for (int64_t n = 0; n < d->nnz; n++)
-    if ((uint32_t)d->u[n] >= (uint32_t)d->num_users || (uint32_t)d->j[n] >= (uint32_t)d->num_items || d->ctx[n] < 0)
-      return fm_fail(nullptr, CARS_E_INVALID, "rating %lld has an id out of range", (long long)n);
 
   cars_fm_handle* h = new (std::nothrow) cars_fm_handle();
   if (!h) return fm_fail(nullptr, CARS_E_OOM, "host allocation failed");
@@ -176,13 +201,14 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
   h->Nq = (N + 1) & ~(int64_t)1;
   FM_TRY_H(fm_alloc(&h->d_Qc, (size_t)h->Nq * h->k));
   FM_TRY_H(fm_alloc(&h->d_w0, 1)); FM_TRY_H(fm_alloc(&h->d_w, (size_t)h->p)); FM_TRY_H(fm_alloc(&h->d_V, (size_t)h->p * h->k));
-  try {
+  FM_TRY_H(h->copier.init(h->device));
+  {
     // Internal row order.  The rows (errors[n], Q[n][f]) are private to the engine, and every sum of the sweep
-    // runs over the rows of ONE coordinate, so the rows may be stored in any order.  They are sorted by
-    // (item block, context, caller's order): the item field then gathers e / Qc[f] inside one block of
-    // ~kBlockRows rows (L2-resident), the context field reads long contiguous runs, and the user field reads
-    // (item blocks x contexts) streams in which neighbouring users are neighbours -- instead of 8-byte reads
-    // scattered over all N rows, one DRAM sector each (profiles/r1: 0.31 of the HBM roofline before).
+    // runs over the rows of ONE coordinate, so the rows may be stored in any order.  They are sorted by item
+    // block (and by context when the context field is reduced by pieces), the caller's order inside: the item
+    // field then gathers e / Qc[f] inside one block of ~block_rows rows (L2-resident) and the user field reads
+    // short contiguous runs in which neighbouring users are neighbours -- instead of 8-byte reads scattered over
+    // all N rows, one DRAM sector each (profiles/r1: 0.31 of the HBM roofline before).
     int64_t block_rows = 1536 * 1024;
     if (const char* e = getenv("CARS_FM_BLOCK_ROWS")) block_rows = atoll(e);
     // few contexts: that field is reduced by streaming the rows (fm_dense_reduce_kernel), so the context does not
@@ -190,52 +216,111 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
     int64_t dense_min_rows = 65536;
     if (const char* e = getenv("CARS_FM_DENSE_MIN_ROWS")) dense_min_rows = atoll(e);
     const bool ctx_dense = h->C > 0 && h->C <= kDenseMaxCoord && N >= dense_min_rows;
-    std::vector<int32_t> cu((size_t)N), cj((size_t)N), cc((size_t)N);
-    std::vector<double> cr((size_t)N);
-    std::vector<int32_t> order;  // new position -> caller's row
-    if (block_rows > 0 && N > block_rows) {
-      const int64_t nblk = (N + block_rows - 1) / block_rows;
-      const int32_t items_per_blk = (int32_t)((h->I + nblk - 1) / nblk);
-      const int64_t nctx = ctx_dense ? 1 : (int64_t)h->C + 1;  // contexts without a feature (index >= p) share the last slot
-      const int64_t nkeys = ((int64_t)(h->I - 1) / items_per_blk + 1) * nctx;
-      std::vector<int64_t> start((size_t)nkeys + 1, 0);
-      auto key_of = [&](int64_t n) {
-        const int32_t c = ctx_dense ? 0 : (d->ctx[n] < h->C ? d->ctx[n] : h->C);
-        return (int64_t)(d->j[n] / items_per_blk) * nctx + c;
-      };
-      for (int64_t n = 0; n < N; n++) start[(size_t)key_of(n) + 1]++;
-      for (int64_t q = 0; q < nkeys; q++) start[(size_t)q + 1] += start[(size_t)q];
-      order.resize((size_t)N);
-      for (int64_t n = 0; n < N; n++) order[(size_t)start[(size_t)key_of(n)]++] = (int32_t)n;
-    }
-    for (int64_t i = 0; i < N; i++) {
-      const int64_t n = order.empty() ? i : order[(size_t)i];
-      cu[i] = d->u[n];
-      cj[i] = d->j[n];
-      cr[i] = d->r[n];
-      cc[i] = d->ctx[n];
+    const int blocks = h->sm_count * 8;
+    const size_t Na = (size_t)(N ? N : 1);
+    int32_t *r_u = nullptr, *r_j = nullptr, *r_c = nullptr, *d_cc = nullptr;
+    double* r_r = nullptr;
+    unsigned long long* d_bad = nullptr;
+    FmScratch sc;
+    auto drop = [&]() {
+      cudaFree(r_u); cudaFree(r_j); cudaFree(r_c); cudaFree(r_r); cudaFree(d_bad);
+      cudaFree(sc.key); cudaFree(sc.key_out); cudaFree(sc.idx); cudaFree(sc.temp);
+    };
+#define FS_TRY(expr)                                                           \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) {                                                   \
+      drop();                                                                  \
+      fm_fail(h, CARS_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+      return bail(_e == cudaErrorMemoryAllocation ? CARS_E_OOM : CARS_E_CUDA); \
+    }                                                                          \
+  } while (0)
+    FS_TRY(fm_alloc(&sc.key, Na)); FS_TRY(fm_alloc(&sc.key_out, Na)); FS_TRY(fm_alloc(&sc.idx, Na));
+    FS_TRY(fm_alloc(&d_bad, 1));
+    {
+      size_t a = 0, b = 0;
+      FS_TRY(cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                             (uint32_t*)nullptr, N, 0, 32, h->stream));
+      int64_t m = h->U > h->I ? h->U : h->I;
+      if (h->C > m) m = h->C;
+      FS_TRY(cub::DeviceScan::ExclusiveSum(nullptr, b, (long long*)nullptr, (long long*)nullptr, (int)(m + 1), h->stream));
+      sc.temp_bytes = a > b ? a : b;
+      FS_TRY(cudaMalloc(&sc.temp, sc.temp_bytes ? sc.temp_bytes : 1));
     }
     if (N) {
-      FM_TRY_H(cudaMemcpyAsync(h->d_u, cu.data(), N * 4, cudaMemcpyHostToDevice, h->stream));
-      FM_TRY_H(cudaMemcpyAsync(h->d_j, cj.data(), N * 4, cudaMemcpyHostToDevice, h->stream));
-      FM_TRY_H(cudaMemcpyAsync(h->d_c, cc.data(), N * 4, cudaMemcpyHostToDevice, h->stream));
-      FM_TRY_H(cudaMemcpyAsync(h->d_r, cr.data(), N * 8, cudaMemcpyHostToDevice, h->stream));
-      FM_TRY_H(cudaStreamSynchronize(h->stream));
+      // the caller's arrays go straight into the engine's arrays (no row permutation) or into staging copies
+      const bool permute = block_rows > 0 && N > block_rows;
+      int32_t *t_u = h->d_u, *t_j = h->d_j, *t_c = h->d_c;
+      double* t_r = h->d_r;
+      if (permute) {
+        FS_TRY(fm_alloc(&r_u, Na)); FS_TRY(fm_alloc(&r_j, Na)); FS_TRY(fm_alloc(&r_c, Na)); FS_TRY(fm_alloc(&r_r, Na));
+        t_u = r_u; t_j = r_j; t_c = r_c; t_r = r_r;
+      }
+      cars::CopySeg segs[4] = {{t_u, (void*)d->u, (size_t)N * 4}, {t_j, (void*)d->j, (size_t)N * 4},
+                               {t_c, (void*)d->ctx, (size_t)N * 4}, {t_r, (void*)d->r, (size_t)N * 8}};
+      FS_TRY(h->copier.run(segs, 4, true));
       h->h2d += N * 20;
+      FS_TRY(cudaMemsetAsync(d_bad, 0xff, 8, h->stream));
+      fms_validate_kernel<<<blocks, 256, 0, h->stream>>>(t_u, t_j, t_c, N, (uint32_t)h->U, (uint32_t)h->I, d_bad);
+      FS_TRY(cudaGetLastError());
+      unsigned long long bad = 0;
+      FS_TRY(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, h->stream));
+      FS_TRY(cudaStreamSynchronize(h->stream));
+      if (bad != ~0ull) {
+        drop();
+        fm_fail(h, CARS_E_INVALID, "rating %lld has an id out of range", (long long)bad);
+        return bail(CARS_E_INVALID);
+      }
+      fms_iota_kernel<<<blocks, 256, 0, h->stream>>>(sc.idx, N);
+      FS_TRY(cudaGetLastError());
+      h->launches += 2;
+      if (permute) {
+        const int64_t nblk = (N + block_rows - 1) / block_rows;
+        const int32_t items_per_blk = (int32_t)((h->I + nblk - 1) / nblk);
+        const int32_t ctx_slots = ctx_dense ? 1 : h->C + 1;  // contexts without a feature (index >= p) share the last slot
+        const int64_t nkeys = ((int64_t)(h->I - 1) / items_per_blk + 1) * ctx_slots;
+        int bits = 1;
+        while ((1ll << bits) < nkeys) bits++;
+        if (bits > 32) {
+          drop();
+          fm_fail(h, CARS_E_UNSUPPORTED, "row-order key does not fit 32 bits");
+          return bail(CARS_E_UNSUPPORTED);
+        }
+        fms_row_key_kernel<<<blocks, 256, 0, h->stream>>>(r_j, r_c, N, items_per_blk, ctx_slots, h->C, sc.key);
+        FS_TRY(cudaGetLastError());
+        uint32_t* order = nullptr;
+        FS_TRY(fm_alloc(&order, Na));
+        size_t tb = sc.temp_bytes;
+        cudaError_t se = cub::DeviceRadixSort::SortPairs(sc.temp, tb, sc.key, sc.key_out, sc.idx, order, N, 0, bits, h->stream);
+        if (se == cudaSuccess) {
+          fms_permute_rows_kernel<<<blocks, 256, 0, h->stream>>>(order, N, r_u, r_j, r_c, r_r, h->d_u, h->d_j, h->d_c, h->d_r);
+          se = cudaGetLastError();
+        }
+        if (se == cudaSuccess) se = cudaStreamSynchronize(h->stream);
+        cudaFree(order);
+        FS_TRY(se);
+        h->launches += 3;
+      }
     }
-    for (int64_t i = 0; i < N; i++)
-      if (cc[i] >= h->C) cc[i] = -1;  // FM.java:81: the context feature exists only if its index is < p
-    if ((rc = build_field(h, 0, cu, h->U, 0, 1.0, false))) return bail(rc);
-    if ((rc = build_field(h, 1, cj, h->I, h->U, 1.0, false))) return bail(rc);
-    if ((rc = build_field(h, 2, cc, h->C, h->U + h->I, h->xc, ctx_dense))) return bail(rc);
+    // context coordinate: the context id while its feature index is < p (FM.java:81)
+    FS_TRY(fm_alloc(&d_cc, Na));
+    if (N) {
+      fms_ctx_coord_kernel<<<blocks, 256, 0, h->stream>>>(h->d_c, N, h->C, d_cc);
+      FS_TRY(cudaGetLastError());
+      h->launches++;
+    }
+    rc = build_field(h, 0, h->d_u, false, h->U, 0, 1.0, false, sc);
+    if (!rc) rc = build_field(h, 1, h->d_j, false, h->I, h->U, 1.0, false, sc);
+    if (!rc) rc = build_field(h, 2, d_cc, true, h->C, h->U + h->I, h->xc, ctx_dense, sc);  // takes d_cc over
+    else cudaFree(d_cc);
+    drop();
+    if (rc) return bail(rc);
+#undef FS_TRY
     if (ctx_dense) {
       const int smem = (int)((size_t)h->C * kDenseThreads * sizeof(double2));
       FM_TRY_H(cudaFuncSetAttribute(fm_dense_reduce_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       FM_TRY_H(cudaFuncSetAttribute(fm_dense_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
-  } catch (...) {
-    fm_fail(h, CARS_E_OOM, "host allocation failed");
-    return bail(CARS_E_OOM);
   }
   h->red_blocks = h->sm_count * 4;
   size_t part = (size_t)(2 * (h->max_pieces > h->red_blocks ? h->max_pieces : h->red_blocks));
@@ -481,10 +566,12 @@ extern "C" void cars_fm_destroy(cars_fm_handle* h) {
   cudaFree(h->d_u); cudaFree(h->d_j); cudaFree(h->d_c); cudaFree(h->d_r); cudaFree(h->d_e); cudaFree(h->d_Qc);
   cudaFree(h->d_w0); cudaFree(h->d_w); cudaFree(h->d_V); cudaFree(h->d_part); cudaFree(h->d_scal);
   for (auto& f : h->fld) {
-    cudaFree(f.d_coord_of_row); cudaFree(f.d_perm); cudaFree(f.d_piece_coord); cudaFree(f.d_piece_beg);
+    if (f.owns_coord) cudaFree(f.d_coord_of_row);
+    cudaFree(f.d_perm); cudaFree(f.d_piece_coord); cudaFree(f.d_piece_beg);
     cudaFree(f.d_coord_piece); cudaFree(f.d_coord_rows); cudaFree(f.d_delta);
   }
   if (h->h_scal) cudaFreeHost(h->h_scal);
+  h->copier.destroy();
   if (h->ev_beg) cudaEventDestroy(h->ev_beg);
   if (h->ev_end) cudaEventDestroy(h->ev_end);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

@@ -1,0 +1,96 @@
+// fm_setup.cuh -- set-up of the FM sweep on the device: the engine's internal row order and, per field, the rows
+// sorted by coordinate, cut into pieces (what fm_piece_reduce_kernel / fm_coord_kernel walk).
+// The first version did this with counting sorts on one host thread (1.3 s at 25 M rows, more than six ALS
+// iterations); here it is CUB radix sorts and a few streaming kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+namespace carsfm {
+
+__global__ void __launch_bounds__(256) fms_iota_kernel(uint32_t* v, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = (uint32_t)i;
+}
+
+// first row with an id out of range; *bad starts at ~0  (u < U, j < I, ctx >= 0 -- FM.java:81 tolerates ctx >= C)
+__global__ void __launch_bounds__(256) fms_validate_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ j,
+                                                           const int32_t* __restrict__ c, int64_t n, uint32_t U, uint32_t I,
+                                                           unsigned long long* bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if ((uint32_t)u[i] >= U || (uint32_t)j[i] >= I || c[i] < 0) atomicMin(bad, (unsigned long long)i);
+}
+
+// storage-order key: (item block, context slot); ctx_slots == 1 leaves the context out
+__global__ void __launch_bounds__(256) fms_row_key_kernel(const int32_t* __restrict__ j, const int32_t* __restrict__ c, int64_t n,
+                                                          int32_t items_per_blk, int32_t ctx_slots, int32_t C,
+                                                          uint32_t* __restrict__ key) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int32_t slot = ctx_slots == 1 ? 0 : (c[i] < C ? c[i] : C);
+    key[i] = (uint32_t)(j[i] / items_per_blk) * (uint32_t)ctx_slots + (uint32_t)slot;
+  }
+}
+
+__global__ void __launch_bounds__(256) fms_permute_rows_kernel(const uint32_t* __restrict__ order, int64_t n,
+                                                               const int32_t* __restrict__ u, const int32_t* __restrict__ j,
+                                                               const int32_t* __restrict__ c, const double* __restrict__ r,
+                                                               int32_t* __restrict__ pu, int32_t* __restrict__ pj,
+                                                               int32_t* __restrict__ pc, double* __restrict__ pr) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t k = order[i];
+    pu[i] = u[k]; pj[i] = j[k]; pc[i] = c[k]; pr[i] = r[k];
+  }
+}
+
+// context coordinate of a row: its context id while the feature index stays below p (FM.java:81), else absent
+__global__ void __launch_bounds__(256) fms_ctx_coord_kernel(const int32_t* __restrict__ c, int64_t n, int32_t C,
+                                                            int32_t* __restrict__ coord) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) coord[i] = c[i] < C ? c[i] : -1;
+}
+
+// sort key of a row inside a field (absent rows last) and the per-coordinate row counts
+__global__ void __launch_bounds__(256) fms_field_key_kernel(const int32_t* __restrict__ coord, int64_t n, int32_t ncoord,
+                                                            uint32_t* __restrict__ key, unsigned long long* __restrict__ rows) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int32_t l = coord[i];
+    key[i] = l >= 0 ? (uint32_t)l : (uint32_t)ncoord;
+    if (l >= 0) atomicAdd(rows + l, 1ull);
+  }
+}
+
+// pieces per coordinate (slot ncoord = 0 so that the exclusive scans end with the totals)
+__global__ void __launch_bounds__(256) fms_piece_count_kernel(const unsigned long long* __restrict__ rows, int32_t ncoord,
+                                                              int64_t piece, long long* __restrict__ rows_i64,
+                                                              long long* __restrict__ npieces) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l > ncoord) return;
+  const long long r = l < ncoord ? (long long)rows[l] : 0;
+  rows_i64[l] = r;
+  npieces[l] = (r + piece - 1) / piece;
+}
+
+// piece q belongs to the coordinate l with coord_piece[l] <= q < coord_piece[l + 1]
+__global__ void __launch_bounds__(256) fms_piece_fill_kernel(const long long* __restrict__ coord_piece, const long long* __restrict__ start,
+                                                             int32_t ncoord, int64_t num_pieces, int64_t piece, int64_t total,
+                                                             long long* __restrict__ piece_beg, int32_t* __restrict__ piece_coord) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q == 0) piece_beg[num_pieces] = total;
+  if (q >= num_pieces) return;
+  int lo = 0, hi = ncoord;  // largest l with coord_piece[l] <= q
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (coord_piece[mid] <= q) lo = mid; else hi = mid;
+  }
+  piece_coord[q] = lo;
+  piece_beg[q] = start[lo] + (q - coord_piece[lo]) * piece;
+}
+
+}  // namespace carsfm
