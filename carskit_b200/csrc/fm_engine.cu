@@ -24,6 +24,7 @@ struct FieldStore {
   int64_t *d_piece_beg = nullptr, *d_coord_piece = nullptr, *d_coord_rows = nullptr;
   double* d_delta = nullptr;
   bool wide = false;  // few coordinates with many pieces each: one warp sums a coordinate's pieces
+  bool short_pieces = false;  // on average < 64 rows per piece: 8 lanes per piece instead of a warp
   FmField f{};
 };
 
@@ -87,9 +88,9 @@ static int build_field(cars_fm_handle* h, int which, int32_t* coord, bool owns_c
   const int blocks = h->sm_count * 8;
   fs.d_coord_of_row = coord;
   fs.owns_coord = owns_coord;
-  unsigned long long* d_rows = nullptr;
+  unsigned long long *d_rows = nullptr, *d_rend = nullptr;  // first / one-past-last sorted position of every coordinate
   long long *d_np = nullptr, *d_start = nullptr;
-  auto drop = [&]() { cudaFree(d_rows); cudaFree(d_np); cudaFree(d_start); };
+  auto drop = [&]() { cudaFree(d_rows); cudaFree(d_rend); cudaFree(d_np); cudaFree(d_start); };
 #define BF_TRY(expr)                                                                                    \
   do {                                                                                                  \
     cudaError_t _e = (expr);                                                                            \
@@ -101,6 +102,8 @@ static int build_field(cars_fm_handle* h, int which, int32_t* coord, bool owns_c
   } while (0)
   const size_t nc1 = (size_t)ncoord + 1;
   BF_TRY(fm_alloc(&d_rows, nc1));
+  BF_TRY(fm_alloc(&d_rend, nc1));
+  BF_TRY(cudaMemsetAsync(d_rend, 0, nc1 * 8, h->stream));
   BF_TRY(fm_alloc(&d_np, nc1));
   BF_TRY(fm_alloc(&d_start, nc1));
   BF_TRY(fm_alloc(&fs.d_coord_rows, nc1));
@@ -110,16 +113,18 @@ static int build_field(cars_fm_handle* h, int which, int32_t* coord, bool owns_c
   BF_TRY(cudaMemsetAsync(d_rows, 0, nc1 * 8, h->stream));
   long long tot[2] = {0, 0};  // rows that carry the feature, pieces
   if (N > 0) {
-    fms_field_key_kernel<<<blocks, 256, 0, h->stream>>>(coord, N, ncoord, sc.key, d_rows);
+    fms_field_key_kernel<<<blocks, 256, 0, h->stream>>>(coord, N, ncoord, sc.key);
     BF_TRY(cudaGetLastError());
     int bits = 1;
     while ((1ll << bits) < (long long)ncoord + 1) bits++;
     size_t tb = sc.temp_bytes;
     BF_TRY(cub::DeviceRadixSort::SortPairs(sc.temp, tb, sc.key, sc.key_out, sc.idx, reinterpret_cast<uint32_t*>(fs.d_perm), N, 0,
                                            bits, h->stream));
-    h->launches += 2;
+    fms_run_bounds_kernel<<<blocks, 256, 0, h->stream>>>(sc.key_out, N, ncoord, d_rows, d_rend);
+    BF_TRY(cudaGetLastError());
+    h->launches += 3;
   }
-  fms_piece_count_kernel<<<(unsigned)((nc1 + 255) / 256), 256, 0, h->stream>>>(d_rows, ncoord, kPiece,
+  fms_piece_count_kernel<<<(unsigned)((nc1 + 255) / 256), 256, 0, h->stream>>>(d_rows, d_rend, ncoord, kPiece,
                                                                               reinterpret_cast<long long*>(fs.d_coord_rows), d_np);
   BF_TRY(cudaGetLastError());
   {
@@ -148,6 +153,8 @@ static int build_field(cars_fm_handle* h, int which, int32_t* coord, bool owns_c
   fs.f.num_pieces = num_pieces; fs.f.ncoord = ncoord; fs.f.offset = offset; fs.f.x = x;
   fs.f.dense_blocks = dense ? h->sm_count * 3 : 0;
   fs.wide = dense || (ncoord > 0 && fs.f.num_pieces / ncoord >= 8);
+  fs.short_pieces = num_pieces > 0 && total / num_pieces < 64;
+  if (const char* e = getenv("CARS_FM_LANES_PER_PIECE")) fs.short_pieces = atoi(e) == 8;
   if (fs.f.num_pieces > h->max_pieces) h->max_pieces = fs.f.num_pieces;
   return CARS_OK;
 }
@@ -347,7 +354,33 @@ static int fm_transfer(cars_fm_handle* h, const cars_fm_arrays* a, bool up) {
   };
   FM_TRY(h, cp(h->d_w0, a->w0, 1));
   FM_TRY(h, cp(h->d_w, a->w, (size_t)h->p));
-  FM_TRY(h, cp(h->d_V, a->V, (size_t)h->p * h->k));
+  // the caller's V is [p x k] row-major, the engine's is factor-major: transpose through a staging buffer
+  const size_t vn = (size_t)h->p * h->k;
+  double* d_stage = nullptr;
+  FM_TRY(h, fm_alloc(&d_stage, vn));
+  cudaError_t te = cudaSuccess;
+  if (up) {
+    te = h->copier.h2d(d_stage, a->V, vn * 8);
+    if (te == cudaSuccess) {
+      const dim3 grid((unsigned)((h->p + 31) / 32), (unsigned)((h->k + 31) / 32));
+      fm_transpose_kernel<<<grid, 256, 0, h->stream>>>(d_stage, h->p, h->k, h->d_V);
+      te = cudaGetLastError();
+    }
+    if (te == cudaSuccess) te = cudaStreamSynchronize(h->stream);
+  } else {
+    // d_V as a [k x p] row-major matrix -> [p x k]; the grid's x dimension runs over the long side (p)
+    te = cudaStreamSynchronize(h->stream);
+    if (te == cudaSuccess) {
+      const dim3 grid((unsigned)((h->p + 31) / 32), (unsigned)((h->k + 31) / 32));
+      fm_untranspose_kernel<<<grid, 256, 0, h->stream>>>(h->d_V, h->p, h->k, d_stage);
+      te = cudaGetLastError();
+    }
+    if (te == cudaSuccess) te = cudaStreamSynchronize(h->stream);
+    if (te == cudaSuccess) te = h->copier.d2h(a->V, d_stage, vn * 8);
+  }
+  cudaFree(d_stage);
+  h->launches++;
+  FM_TRY(h, te);
   FM_TRY(h, cudaStreamSynchronize(h->stream));
   (up ? h->h2d : h->d2h) += (int64_t)(1 + h->p + (int64_t)h->p * h->k) * 8;
   return CARS_OK;
@@ -403,8 +436,12 @@ static int field_sweep(cars_fm_handle* h, double* coef, int stride, int col, dou
       FM_TRY(h, cudaGetLastError());
       h->launches++;
     } else if (f.num_pieces > 0) {
-      const unsigned blocks = (unsigned)((f.num_pieces * 32 + 255) / 256);
-      fm_piece_reduce_kernel<MODE><<<blocks, 256, 0, h->stream>>>(f, h->d_e, Qf, coef, stride, col, h->d_part);
+      if (fs.short_pieces)
+        fm_piece_reduce_kernel<MODE, 8><<<(unsigned)((f.num_pieces * 8 + 255) / 256), 256, 0, h->stream>>>(f, h->d_e, Qf, coef, stride,
+                                                                                                         col, h->d_part);
+      else
+        fm_piece_reduce_kernel<MODE, 32><<<(unsigned)((f.num_pieces * 32 + 255) / 256), 256, 0, h->stream>>>(f, h->d_e, Qf, coef,
+                                                                                                           stride, col, h->d_part);
       FM_TRY(h, cudaGetLastError());
       h->launches++;
     }
@@ -457,7 +494,7 @@ extern "C" int cars_fm_iteration(cars_fm_handle* h, double* loss_out) {
   // V_lf, f = 0..k-1 { l = 0..p-1 } (:194-217)
   const double v_reg = (double)h->Nglobal * h->reg_lf;
   for (int f = 0; f < h->k; f++)
-    if ((rc = field_sweep<1>(h, h->d_V, h->k, f, h->d_Qc + (int64_t)f * h->Nq, v_reg, nullptr))) return rc;
+    if ((rc = field_sweep<1>(h, h->d_V + (int64_t)f * h->p, 1, 0, h->d_Qc + (int64_t)f * h->Nq, v_reg, nullptr))) return rc;
   FM_TRY(h, cudaEventRecord(h->ev_end, h->stream));
   FM_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   FM_TRY(h, cudaStreamSynchronize(h->stream));
@@ -502,7 +539,7 @@ extern "C" int cars_fm_iteration_sharded(cars_fm_handle* h, double* dev_buf, car
   if ((rc = field_sweep<0>(h, h->d_w, 1, 0, nullptr, w_reg, &ex))) return rc;
   const double v_reg = (double)h->Nglobal * h->reg_lf;
   for (int f = 0; f < h->k; f++)
-    if ((rc = field_sweep<1>(h, h->d_V, h->k, f, h->d_Qc + (int64_t)f * h->Nq, v_reg, &ex))) return rc;
+    if ((rc = field_sweep<1>(h, h->d_V + (int64_t)f * h->p, 1, 0, h->d_Qc + (int64_t)f * h->Nq, v_reg, &ex))) return rc;
   FM_TRY(h, cudaEventRecord(h->ev_end, h->stream));
   FM_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   FM_TRY(h, cudaStreamSynchronize(h->stream));

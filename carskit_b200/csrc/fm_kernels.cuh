@@ -47,6 +47,49 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// V is kept FACTOR-MAJOR on the device (V[f * p + i]; the caller's array is [p x k] row-major and is transposed on
+// upload / download): every coordinate step works on one factor of all coordinates of a field, a unit-stride
+// slice this way (a 512-byte stride -- one DRAM sector per coordinate, read and written -- the other way).
+// [rows x cols] -> [cols x rows], 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) fm_transpose_kernel(const double* __restrict__ in, int64_t rows, int cols,
+                                                           double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i;
+    const int c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? in[r * cols + c] : 0.0;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i;
+    const int64_t r = r0 + tx;
+    if (r < rows && c < cols) out[(int64_t)c * rows + r] = tile[tx][i];
+  }
+}
+
+// the way back: in = [cols x rows] (factor-major), out = [rows x cols]; same grid as fm_transpose_kernel
+__global__ void __launch_bounds__(256) fm_untranspose_kernel(const double* __restrict__ in, int64_t rows, int cols,
+                                                             double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i;
+    const int64_t r = r0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? in[(int64_t)c * rows + r] : 0.0;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i;
+    const int c = c0 + tx;
+    if (r < rows && c < cols) out[r * cols + c] = tile[tx][i];
+  }
+}
+
 // FM.predict in sparse form, ascending feature index (FM.java:93-113)
 __device__ __forceinline__ double fm_predict_one(const double* __restrict__ w, const double* __restrict__ V, double w0,
                                                  int U, int I, int p, int k, double xc, int u, int j, int c) {
@@ -59,12 +102,12 @@ __device__ __forceinline__ double fm_predict_one(const double* __restrict__ w, c
   double sum = 0.0;
   for (int f = 0; f < k; ++f) {
     double sum1 = 0.0, sum2 = 0.0;
-    double d = V[(int64_t)iu * k + f];
+    double d = V[(int64_t)f * p + iu];
     sum1 = __dadd_rn(sum1, d); sum2 = __dadd_rn(sum2, __dmul_rn(d, d));
-    d = V[(int64_t)ij * k + f];
+    d = V[(int64_t)f * p + ij];
     sum1 = __dadd_rn(sum1, d); sum2 = __dadd_rn(sum2, __dmul_rn(d, d));
     if (has_c) {
-      d = __dmul_rn(V[(int64_t)ic * k + f], xc);
+      d = __dmul_rn(V[(int64_t)f * p + ic], xc);
       sum1 = __dadd_rn(sum1, d); sum2 = __dadd_rn(sum2, __dmul_rn(d, d));
     }
     sum = __dadd_rn(sum, __dsub_rn(__dmul_rn(sum1, sum1), sum2));
@@ -86,9 +129,9 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(const int32_t* __restri
   const int ic = U + I + cc;
   for (int f = 0; f < k; ++f) {
     double v = 0.0;
-    v = __dadd_rn(v, V[(int64_t)uu * k + f]);
-    v = __dadd_rn(v, V[(int64_t)(U + jj) * k + f]);
-    if (ic < p) v = __dadd_rn(v, __dmul_rn(V[(int64_t)ic * k + f], xc));
+    v = __dadd_rn(v, V[(int64_t)f * p + uu]);
+    v = __dadd_rn(v, V[(int64_t)f * p + U + jj]);
+    if (ic < p) v = __dadd_rn(v, __dmul_rn(V[(int64_t)f * p + ic], xc));
     Qc[(int64_t)f * Nq + n] = v;
   }
 }
@@ -151,20 +194,21 @@ __global__ void __launch_bounds__(256) fm_w0_apply_kernel(double* __restrict__ e
   if (i < N) e[i] = __dsub_rn(__dadd_rn(e[i], scal[0]), scal[1]);  // errors + update_w0 - w0 (:165)
 }
 
-// (a) one warp per piece.  MODE 0: w step (:175-179)  num += (e - w_l x) x.
+// (a) one group of LPP lanes per piece (LPP = 32: a warp; LPP = 8 when the pieces are short -- a user with a few
+// dozen rows -- so that a warp works on four pieces).  MODE 0: w step (:175-179)  num += (e - w_l x) x.
 //                         MODE 1: V step (:199-204)  h = x Qc - x^2 V_lf; num += (e - V_lf h) h; den += h^2.
-template <int MODE>
+template <int MODE, int LPP>
 __global__ void __launch_bounds__(256) fm_piece_reduce_kernel(FmField fld, const double* __restrict__ e,
                                                               const double* __restrict__ Qf /*Qc[f]*/,
                                                               const double* __restrict__ coef /*w or V*/, int coef_stride,
                                                               int coef_col, double* __restrict__ part /*[2 x pieces]*/) {
-  const int64_t piece = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (piece >= fld.num_pieces) return;
-  const int lane = threadIdx.x & 31;
-  const int l = fld.piece_coord[piece];
+  const int64_t piece = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPP;
+  const bool valid = piece < fld.num_pieces;  // no early return: the group reductions below shuffle warp-wide
+  const int gl = threadIdx.x % LPP;
+  const int l = valid ? fld.piece_coord[piece] : 0;
   const double x = fld.x;
-  const double cl = coef[(int64_t)(fld.offset + l) * coef_stride + coef_col];
-  const int64_t beg = fld.piece_beg[piece], end = fld.piece_beg[piece + 1];
+  const double cl = valid ? coef[(int64_t)(fld.offset + l) * coef_stride + coef_col] : 0.0;
+  const int64_t beg = valid ? fld.piece_beg[piece] : 0, end = valid ? fld.piece_beg[piece + 1] : 0;
   double num = 0.0, den = 0.0;
   auto add_row = [&](double en, double qn) {  // one row's terms, in the row order of the piece
     if (MODE == 0) {
@@ -175,22 +219,28 @@ __global__ void __launch_bounds__(256) fm_piece_reduce_kernel(FmField fld, const
       den = __dadd_rn(den, __dmul_rn(h, h));
     }
   };
-  int64_t i = beg + lane;
+  int64_t i = beg + gl;
   // four independent gathers in flight per lane (same order of additions as the plain loop)
-  for (; i + 96 < end; i += 128) {
-    const int64_t n0 = fld.perm[i], n1 = fld.perm[i + 32], n2 = fld.perm[i + 64], n3 = fld.perm[i + 96];
+  for (; i + 3 * LPP < end; i += 4 * LPP) {
+    const int64_t n0 = fld.perm[i], n1 = fld.perm[i + LPP], n2 = fld.perm[i + 2 * LPP], n3 = fld.perm[i + 3 * LPP];
     const double e0 = e[n0], e1 = e[n1], e2 = e[n2], e3 = e[n3];
     double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
     if (MODE == 1) { q0 = Qf[n0]; q1 = Qf[n1]; q2 = Qf[n2]; q3 = Qf[n3]; }
     add_row(e0, q0); add_row(e1, q1); add_row(e2, q2); add_row(e3, q3);
   }
-  for (; i < end; i += 32) {
+  for (; i < end; i += LPP) {
     const int64_t n = fld.perm[i];
     add_row(e[n], MODE == 1 ? Qf[n] : 0.0);
   }
-  num = warp_sum(num);
-  if (MODE == 1) den = warp_sum(den);
-  if (lane == 0) {
+#pragma unroll
+  for (int o = LPP / 2; o > 0; o >>= 1) {  // fixed-order tree over the group's lanes
+    num = __dadd_rn(num, __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(num), o, LPP),
+                                          __shfl_down_sync(0xffffffffu, __double2loint(num), o, LPP)));
+    if (MODE == 1)
+      den = __dadd_rn(den, __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(den), o, LPP),
+                                            __shfl_down_sync(0xffffffffu, __double2loint(den), o, LPP)));
+  }
+  if (valid && gl == 0) {
     part[piece] = num;
     part[fld.num_pieces + piece] = den;
   }
