@@ -36,7 +36,7 @@ def _worker(rank, world, port, model_name, F, epochs, out_dir, combine):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("model_name,combine", [("camf_ci", "mean"), ("camf_cu", "mean"), ("biasedmf", "sum")])
+@pytest.mark.parametrize("model_name,combine", [("camf_ci", "mean"), ("camf_cu", "mean"), ("camf_cuci", "mean"), ("biasedmf", "sum")])
 def test_two_gpus_match_block_jacobi_reference(oracle, cars_lib, tmp_path, model_name, combine):
     import torch
     if torch.cuda.device_count() < 2:

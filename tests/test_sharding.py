@@ -141,7 +141,7 @@ def _worker(rank, world, port, model_name, F, epochs, out_dir, combine):
 def _problem(model_name, F):
     from oracle import oracle_py as orc
     model = capi.MODEL_NAMES[model_name]
-    dims = [3, 4] if model in (capi.CAMF_CI, capi.CAMF_CU) else None
+    dims = [3, 4] if model in (capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI) else None
     ts, test = synth.make_training_set(120, 40, dims, 6000, seed=11, order="user_sorted", holdout=0.1)
     g = orc.JavaRandom(5)
     shapes = capi.member_shapes(model, ts.num_users, ts.num_items, ts.num_conditions, F)
@@ -178,7 +178,7 @@ def block_jacobi_reference(oracle, model_name, F, epochs, world, combine="mean")
     return shards, locals_, item, losses
 
 
-@pytest.mark.parametrize("model_name,combine", [("camf_ci", "mean"), ("camf_cu", "mean"), ("biasedmf", "sum")])
+@pytest.mark.parametrize("model_name,combine", [("camf_ci", "mean"), ("camf_cu", "mean"), ("camf_cuci", "mean"), ("biasedmf", "sum")])
 def test_two_rank_gloo_matches_block_jacobi_reference(oracle, tmp_path, model_name, combine):
     import torch.multiprocessing as mp
     F, epochs, world = 8, 3, 2
