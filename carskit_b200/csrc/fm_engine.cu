@@ -45,6 +45,7 @@ struct cars_fm_handle {
   int red_blocks = 0;
   FieldStore fld[3];
   bool uploaded = false, prepared = false;
+  int ppg_short = 2, ppg_long = 1;  // pieces per lane group in fm_piece_reduce_kernel (CARS_FM_PPG_SHORT / _LONG)
   int64_t launches = 0, h2d = 0, d2h = 0;
   cudaEvent_t ev_beg = nullptr, ev_end = nullptr;
   double last_iter_ms = 0;
@@ -209,6 +210,8 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
   FM_TRY_H(fm_alloc(&h->d_Qc, (size_t)h->Nq * h->k));
   FM_TRY_H(fm_alloc(&h->d_w0, 1)); FM_TRY_H(fm_alloc(&h->d_w, (size_t)h->p)); FM_TRY_H(fm_alloc(&h->d_V, (size_t)h->p * h->k));
   FM_TRY_H(h->copier.init(h->device));
+  if (const char* e = getenv("CARS_FM_PPG_SHORT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) h->ppg_short = v; }
+  if (const char* e = getenv("CARS_FM_PPG_LONG")) { const int v = atoi(e); if (v == 1 || v == 2) h->ppg_long = v; }
   {
     // Internal row order.  The rows (errors[n], Q[n][f]) are private to the engine, and every sum of the sweep
     // runs over the rows of ONE coordinate, so the rows may be stored in any order.  They are sorted by item
@@ -436,12 +439,17 @@ static int field_sweep(cars_fm_handle* h, double* coef, int stride, int col, dou
       FM_TRY(h, cudaGetLastError());
       h->launches++;
     } else if (f.num_pieces > 0) {
-      if (fs.short_pieces)
-        fm_piece_reduce_kernel<MODE, 8><<<(unsigned)((f.num_pieces * 8 + 255) / 256), 256, 0, h->stream>>>(f, h->d_e, Qf, coef, stride,
-                                                                                                         col, h->d_part);
-      else
-        fm_piece_reduce_kernel<MODE, 32><<<(unsigned)((f.num_pieces * 32 + 255) / 256), 256, 0, h->stream>>>(f, h->d_e, Qf, coef,
-                                                                                                           stride, col, h->d_part);
+      const int ppg = fs.short_pieces ? h->ppg_short : h->ppg_long;
+      const int lpp = fs.short_pieces ? 8 : 32;
+      const int64_t groups = (f.num_pieces + ppg - 1) / ppg;
+      const unsigned blocks = (unsigned)((groups * lpp + 255) / 256);
+#define PIECE_LAUNCH(L, P) fm_piece_reduce_kernel<MODE, L, P><<<blocks, 256, 0, h->stream>>>(f, h->d_e, Qf, coef, stride, col, h->d_part)
+      if (fs.short_pieces) {
+        if (ppg == 4) PIECE_LAUNCH(8, 4); else if (ppg == 2) PIECE_LAUNCH(8, 2); else PIECE_LAUNCH(8, 1);
+      } else {
+        if (ppg == 2) PIECE_LAUNCH(32, 2); else PIECE_LAUNCH(32, 1);
+      }
+#undef PIECE_LAUNCH
       FM_TRY(h, cudaGetLastError());
       h->launches++;
     }

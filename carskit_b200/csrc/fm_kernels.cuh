@@ -195,54 +195,91 @@ __global__ void __launch_bounds__(256) fm_w0_apply_kernel(double* __restrict__ e
 }
 
 // (a) one group of LPP lanes per piece (LPP = 32: a warp; LPP = 8 when the pieces are short -- a user with a few
-// dozen rows -- so that a warp works on four pieces).  MODE 0: w step (:175-179)  num += (e - w_l x) x.
+// dozen rows -- so that a warp works on four pieces at a time), PPG consecutive pieces per group with the loads of
+// all of them in flight together (a short piece is a chain of four dependent loads: piece -> coordinate ->
+// coefficient, piece -> rows -> e / Qc; two chains per lane hide each other).
+//                         MODE 0: w step (:175-179)  num += (e - w_l x) x.
 //                         MODE 1: V step (:199-204)  h = x Qc - x^2 V_lf; num += (e - V_lf h) h; den += h^2.
-template <int MODE, int LPP>
+template <int MODE, int LPP, int PPG>
 __global__ void __launch_bounds__(256) fm_piece_reduce_kernel(FmField fld, const double* __restrict__ e,
                                                               const double* __restrict__ Qf /*Qc[f]*/,
                                                               const double* __restrict__ coef /*w or V*/, int coef_stride,
                                                               int coef_col, double* __restrict__ part /*[2 x pieces]*/) {
-  const int64_t piece = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPP;
-  const bool valid = piece < fld.num_pieces;  // no early return: the group reductions below shuffle warp-wide
+  const int64_t piece0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPP) * PPG;
   const int gl = threadIdx.x % LPP;
-  const int l = valid ? fld.piece_coord[piece] : 0;
   const double x = fld.x;
-  const double cl = valid ? coef[(int64_t)(fld.offset + l) * coef_stride + coef_col] : 0.0;
-  const int64_t beg = valid ? fld.piece_beg[piece] : 0, end = valid ? fld.piece_beg[piece + 1] : 0;
-  double num = 0.0, den = 0.0;
-  auto add_row = [&](double en, double qn) {  // one row's terms, in the row order of the piece
+  bool valid[PPG];  // no early return: the group reductions below shuffle warp-wide
+  int64_t beg[PPG], end[PPG];
+  double cl[PPG], num[PPG], den[PPG];
+#pragma unroll
+  for (int k = 0; k < PPG; k++) {
+    valid[k] = piece0 + k < fld.num_pieces;
+    beg[k] = valid[k] ? fld.piece_beg[piece0 + k] : 0;
+    end[k] = valid[k] ? fld.piece_beg[piece0 + k + 1] : 0;
+    const int l = valid[k] ? fld.piece_coord[piece0 + k] : 0;
+    cl[k] = valid[k] ? coef[(int64_t)(fld.offset + l) * coef_stride + coef_col] : 0.0;
+    num[k] = 0.0;
+    den[k] = 0.0;
+  }
+  auto add_row = [&](int k, double en, double qn) {  // one row's terms, in the row order of the piece
     if (MODE == 0) {
-      num = __dadd_rn(num, __dmul_rn(__dsub_rn(en, __dmul_rn(cl, x)), x));
+      num[k] = __dadd_rn(num[k], __dmul_rn(__dsub_rn(en, __dmul_rn(cl[k], x)), x));
     } else {
-      const double h = __dsub_rn(__dmul_rn(x, qn), __dmul_rn(__dmul_rn(x, x), cl));
-      num = __dadd_rn(num, __dmul_rn(__dsub_rn(en, __dmul_rn(cl, h)), h));
-      den = __dadd_rn(den, __dmul_rn(h, h));
+      const double h = __dsub_rn(__dmul_rn(x, qn), __dmul_rn(__dmul_rn(x, x), cl[k]));
+      num[k] = __dadd_rn(num[k], __dmul_rn(__dsub_rn(en, __dmul_rn(cl[k], h)), h));
+      den[k] = __dadd_rn(den[k], __dmul_rn(h, h));
     }
   };
-  int64_t i = beg + gl;
-  // four independent gathers in flight per lane (same order of additions as the plain loop)
-  for (; i + 3 * LPP < end; i += 4 * LPP) {
-    const int64_t n0 = fld.perm[i], n1 = fld.perm[i + LPP], n2 = fld.perm[i + 2 * LPP], n3 = fld.perm[i + 3 * LPP];
-    const double e0 = e[n0], e1 = e[n1], e2 = e[n2], e3 = e[n3];
-    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
-    if (MODE == 1) { q0 = Qf[n0]; q1 = Qf[n1]; q2 = Qf[n2]; q3 = Qf[n3]; }
-    add_row(e0, q0); add_row(e1, q1); add_row(e2, q2); add_row(e3, q3);
-  }
-  for (; i < end; i += LPP) {
-    const int64_t n = fld.perm[i];
-    add_row(e[n], MODE == 1 ? Qf[n] : 0.0);
+  // first four rows of every lane in every piece: all gathers in flight together
+  int32_t n0[PPG][4];
+  double e0[PPG][4], q0[PPG][4];
+#pragma unroll
+  for (int k = 0; k < PPG; k++)
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int64_t i = beg[k] + gl + t * LPP;
+      n0[k][t] = i < end[k] ? fld.perm[i] : -1;
+    }
+#pragma unroll
+  for (int k = 0; k < PPG; k++)
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      e0[k][t] = n0[k][t] >= 0 ? e[n0[k][t]] : 0.0;
+      q0[k][t] = (MODE == 1 && n0[k][t] >= 0) ? Qf[n0[k][t]] : 0.0;
+    }
+#pragma unroll
+  for (int k = 0; k < PPG; k++) {
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+      if (n0[k][t] >= 0) add_row(k, e0[k][t], q0[k][t]);
+    // the rest of a long piece, four gathers at a time (same order of additions as a plain loop)
+    int64_t i = beg[k] + gl + 4 * LPP;
+    for (; i + 3 * LPP < end[k]; i += 4 * LPP) {
+      const int64_t a0 = fld.perm[i], a1 = fld.perm[i + LPP], a2 = fld.perm[i + 2 * LPP], a3 = fld.perm[i + 3 * LPP];
+      const double x0 = e[a0], x1 = e[a1], x2 = e[a2], x3 = e[a3];
+      double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+      if (MODE == 1) { y0 = Qf[a0]; y1 = Qf[a1]; y2 = Qf[a2]; y3 = Qf[a3]; }
+      add_row(k, x0, y0); add_row(k, x1, y1); add_row(k, x2, y2); add_row(k, x3, y3);
+    }
+    for (; i < end[k]; i += LPP) {
+      const int64_t n = fld.perm[i];
+      add_row(k, e[n], MODE == 1 ? Qf[n] : 0.0);
+    }
   }
 #pragma unroll
-  for (int o = LPP / 2; o > 0; o >>= 1) {  // fixed-order tree over the group's lanes
-    num = __dadd_rn(num, __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(num), o, LPP),
-                                          __shfl_down_sync(0xffffffffu, __double2loint(num), o, LPP)));
-    if (MODE == 1)
-      den = __dadd_rn(den, __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(den), o, LPP),
-                                            __shfl_down_sync(0xffffffffu, __double2loint(den), o, LPP)));
-  }
-  if (valid && gl == 0) {
-    part[piece] = num;
-    part[fld.num_pieces + piece] = den;
+  for (int k = 0; k < PPG; k++) {
+#pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) {  // fixed-order tree over the group's lanes
+      num[k] = __dadd_rn(num[k], __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(num[k]), o, LPP),
+                                                  __shfl_down_sync(0xffffffffu, __double2loint(num[k]), o, LPP)));
+      if (MODE == 1)
+        den[k] = __dadd_rn(den[k], __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(den[k]), o, LPP),
+                                                    __shfl_down_sync(0xffffffffu, __double2loint(den[k]), o, LPP)));
+    }
+    if (valid[k] && gl == 0) {
+      part[piece0 + k] = num[k];
+      part[fld.num_pieces + piece0 + k] = den[k];
+    }
   }
 }
 

@@ -97,6 +97,12 @@ def test_fm_recommender_mirror_and_errors(oracle, cars_lib):
         assert ex.value.code == -6
     with pytest.raises(capi.CarsError):
         capi.FmEngine(capi.make_desc(ts, capi.FM, 8, num_context_dims=0), keepalive=ts)
+    keep = int(ts.j[11])
+    ts.j[11] = ts.num_items  # range check on the device
+    with pytest.raises(capi.CarsError) as ex:
+        capi.FmEngine(capi.make_desc(ts, capi.FM, 8, num_context_dims=2), keepalive=ts)
+    assert ex.value.code == -1 and "rating 11 " in str(ex.value)
+    ts.j[11] = keep
     with pytest.raises(capi.CarsError):
         capi.Engine(capi.make_desc(ts, capi.FM, 8, num_context_dims=2), keepalive=ts)
 

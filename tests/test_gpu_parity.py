@@ -192,10 +192,12 @@ def test_call_order_errors(oracle, cars_lib):
         with pytest.raises(capi.CarsError):
             eng.predict([999], [0], [0])
     bad = capi.make_desc(ts, capi.CAMF_CI, 8, **REGS)
-    ts.u[0] = 10 ** 6
+    ts.u[7] = 10 ** 6   # ids are range-checked on the device; the message names the FIRST offending rating
+    ts.j[3] = -1
+    ts.ctx[400] = ts.num_contexts
     with pytest.raises(capi.CarsError) as e:
         capi.Engine(bad, keepalive=ts)
-    assert e.value.code == -1
+    assert e.value.code == -1 and "rating 3 " in str(e.value)
 
 
 @pytest.mark.parametrize("model", [capi.PMF, capi.BIASEDMF, capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI])
