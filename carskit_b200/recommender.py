@@ -545,6 +545,50 @@ class FM(IterativeRecommender):
         return {"MAE": sa / len(err), "RMSE": math.sqrt(ss / len(err))}
 
 
+def runCrossValidation(rateMatrix: TrainingSet, name: str, conf: Optional[Dict[str, str]] = None, kFold: int = 5,
+                       rand_seed: int = 1, parallel: bool = True, devices=(0,), inits=None):
+    """CARSKit.runCrossValidation (src/carskit/main/CARSKit.java:387-423) over this path: `DataSplitter ds = new
+    DataSplitter(rateMatrix, kFold)`, one recommender per fold on its own thread (`-p on`, the default of
+    setting.conf:39; `-p off` joins each thread before the next starts), then the average of every measure,
+    accumulated in fold order as `val + measure / kFold` (:415-421).
+
+    Each fold owns a handle (the C ABI is re-entrant per handle) on `devices[fold % len(devices)]`; the ctypes
+    calls release the GIL, so the folds' epochs overlap on the device like the Java threads overlap on the cores.
+    `inits[i]` hands fold i+1 its initial model (the reference's own generator is wall-clock seeded); otherwise
+    fold i+1 draws from seed `rand_seed + i + 1`.  Returns (average measures, the per-fold recommenders)."""
+    import threading
+    from .data import DataSplitter
+    ds = DataSplitter(rateMatrix, kFold, rand_seed)
+    Rec = getRecommender(name)
+    algos, threads, errors = [], [], []
+
+    def run(algo, i):
+        try:
+            algo.execute(init=None if inits is None else inits[i], seed=rand_seed + i + 1)
+        except BaseException as e:  # surfaced after the join, like Recommender.run() logging a failed fold (:1162-1171)
+            errors.append((i + 1, e))
+
+    for i in range(ds.numFold):
+        train, test = ds.getKthFold(i + 1)
+        algo = Rec(train, test, fold=i + 1, conf=conf, device=devices[i % len(devices)])
+        algos.append(algo)
+        t = threading.Thread(target=run, args=(algo, i))
+        threads.append(t)
+        t.start()
+        if not parallel:
+            t.join()
+    if parallel:
+        for t in threads:
+            t.join()
+    if errors:
+        raise RuntimeError(f"fold {errors[0][0]} failed: {errors[0][1]}") from errors[0][1]
+    avg: Dict[str, float] = {}
+    for algo in algos:
+        for m, v in algo.measures.items():
+            avg[m] = avg.get(m, 0.0) + v / ds.numFold
+    return avg, algos
+
+
 def getRecommender(name: str):
     """The `switch` of CARSKit.getRecommender (src/carskit/main/CARSKit.java:429-705) for this path."""
     table = {"pmf": PMF, "biasedmf": BiasedMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM,

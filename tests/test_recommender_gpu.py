@@ -59,6 +59,34 @@ def test_nan_loss_raises_like_the_reference_exits(cars_lib):
     assert rec.engine is None  # the handle is released on the error path
 
 
+def test_cross_validation_folds_in_parallel_match_folds_one_by_one(oracle, cars_lib):
+    # CARSKit.runCrossValidation: K folds from DataSplitter, one recommender (and one engine handle) per thread;
+    # the same folds trained one after the other, and by the oracle, must give the same measures bit for bit
+    from carskit_b200 import data
+    ts, _ = synth.make_training_set(300, 120, [4, 3], 20000, seed=8)
+    conf = {**CONF, "num.factors": "16", "num.max.iter": "4"}
+    K, seed = 3, 5
+    sp = data.DataSplitter(ts, K, seed)
+    inits = [init_arrays(oracle, capi.CAMF_CI, sp.getKthFold(k + 1)[0], 16, seed=40 + k) for k in range(K)]
+    avg_p, algos_p = recommender.runCrossValidation(ts, "camf_ci", conf, kFold=K, rand_seed=seed, parallel=True,
+                                                    inits=[{k: v.copy() for k, v in a.items()} for a in inits])
+    avg_s, algos_s = recommender.runCrossValidation(ts, "camf_ci", conf, kFold=K, rand_seed=seed, parallel=False,
+                                                    inits=[{k: v.copy() for k, v in a.items()} for a in inits])
+    assert avg_p == avg_s and [a.fold for a in algos_p] == [1, 2, 3]
+    want = {}
+    for k in range(K):
+        train, test = sp.getKthFold(k + 1)
+        assert algos_p[k].measures == algos_s[k].measures
+        ref = {n: v.copy() for n, v in inits[k].items()}
+        desc = capi.make_desc(train, capi.CAMF_CI, 16, **REGS)
+        oracle.build_model(desc, ref, oracle.new_state(capi.f32(2e-2), bold_driver=True), 4)
+        sa, ss, cnt = oracle.eval_ratings(desc, ref, test["u"], test["j"], test["ctx"], test["r"], 1.0, 5.0)
+        assert algos_p[k].measures["RMSE"] == math.sqrt(ss / cnt) and algos_p[k].measures["MAE"] == sa / cnt
+        for m, v in algos_p[k].measures.items():
+            want[m] = want.get(m, 0.0) + v / K
+    assert avg_p == want
+
+
 def test_get_recommender_names():
     assert recommender.getRecommender("CAMF_CI") is recommender.CAMF_CI
     with pytest.raises(ValueError):
