@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import re
 from dataclasses import dataclass, field
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -182,4 +182,249 @@ class DataSplitter:
                             global_mean=total / len(r) if len(r) else 0.0)
         test = {"u": ts.u[test_mask].copy(), "j": ts.j[test_mask].copy(),
                 "ctx": ts.ctx[test_mask].copy() if has_ctx else None, "r": ts.r[test_mask].copy()}
+        if getattr(ts, "pair_ids", None) is not None:  # the CRS rows (user-item pair ids) travel with the entries
+            train.pair_ids = ts.pair_ids[keep]
+            test["pair_ids"] = ts.pair_ids[test_mask].copy()
         return train, test
+
+
+# ------------------------------------------------------------------------------------------------------
+# Format conversion: carskit.data.processor.DataTransformer (src/carskit/data/processor/DataTransformer.java)
+# ------------------------------------------------------------------------------------------------------
+def java_string_hash(s: str) -> int:
+    """String.hashCode(): h = 31 * h + c over the UTF-16 code units, in 32-bit two's complement."""
+    h = 0
+    units = s.encode("utf-16-be", "surrogatepass")
+    for i in range(0, len(units), 2):
+        h = (31 * h + ((units[i] << 8) | units[i + 1])) & 0xFFFFFFFF
+    return h
+
+
+def java_hashmap_key_order(keys, jdk: int = 7) -> List[str]:
+    """Iteration order of a java.util.HashMap<String, ?> filled by put() in the given order -- the order in which
+    DataTransformer writes the converted rating lines (`for (String key : newlines.keySet())`,
+    DataTransformer.java:276).  It depends on the JDK the reference runs on:
+
+    jdk = 7 (the files under the reference's sampleData/ were written by one: tests/test_data.py reproduces them
+      byte for byte): hash = h ^ (h >>> 20) ^ (h >>> 12), then ^ (>>> 7) ^ (>>> 4); a new entry goes to the HEAD
+      of its bucket; the table doubles when size >= 0.75 * capacity AND the target bucket is occupied, and the
+      transfer re-inserts every entry at the head of its new bucket (reversing each bucket).
+    jdk = 8: hash = h ^ (h >>> 16); entries are appended, a resize keeps their relative order; doubles while
+      size > 0.75 * capacity.  A bucket that would be treeified (>= 8 entries at capacity >= 64) iterates in an
+      order this function does not reproduce; it raises instead."""
+    uniq, seen = [], set()
+    for k in keys:
+        if k not in seen:
+            seen.add(k)
+            uniq.append(k)
+    if jdk == 7:
+        cap, table = 16, [[] for _ in range(16)]  # a bucket is listed from its head
+        for size, k in enumerate(uniq):
+            h = java_string_hash(k)
+            h ^= (h >> 20) ^ (h >> 12)
+            h = (h ^ (h >> 7) ^ (h >> 4)) & 0xFFFFFFFF
+            if size >= int(cap * 0.75) and table[h & (cap - 1)]:
+                cap *= 2
+                new = [[] for _ in range(cap)]
+                for b in table:
+                    for kk, hh in b:
+                        new[hh & (cap - 1)].insert(0, (kk, hh))
+                table = new
+            table[h & (cap - 1)].insert(0, (k, h))
+        return [kk for b in table for kk, _ in b]
+    if jdk != 8:
+        raise ValueError("jdk must be 7 or 8")
+    cap = 16
+    while len(uniq) > 0.75 * cap:
+        cap *= 2
+    buckets: Dict[int, List[str]] = {}
+    for k in uniq:
+        h = java_string_hash(k)
+        buckets.setdefault((h ^ (h >> 16)) & (cap - 1), []).append(k)
+    if cap >= 64 and any(len(b) >= 8 for b in buckets.values()):
+        raise NotImplementedError("a HashMap bucket reaches the treeify threshold")
+    out: List[str] = []
+    for b in sorted(buckets):
+        out.extend(buckets[b])
+    return out
+
+
+def _detect_format(path: str) -> int:
+    """1 binary / 2 loose / 3 compact, by the header like the reference's users declare it in setting.conf."""
+    with open(path) as f:
+        header = [h.strip().lower() for h in f.readline().rstrip("\r\n").split(",")]
+    if len(header) == 5 and header[3] == "dimension" and header[4] == "condition":
+        return 2
+    if len(header) > 3 and all(":" in h for h in header[3:]):
+        return 1
+    return 3
+
+
+def _read_lines(path: str) -> List[str]:
+    with open(path) as f:
+        return [ln.rstrip("\r\n") for ln in f if ln.rstrip("\r\n") != ""]  # BufferedReader.readLine()
+
+
+class _Conditions:
+    """dim -> conditions: a Guava TreeMultimap (both sorted, DataTransformer.java:60) or LinkedHashMultimap
+    (insertion order, :163/:203/:243)."""
+
+    def __init__(self, sorted_: bool):
+        self.sorted = sorted_
+        self.map: Dict[str, List[str]] = {}
+
+    def put(self, dim: str, cond: str):
+        conds = self.map.setdefault(dim, [])
+        if cond not in conds:
+            conds.append(cond)
+
+    def dims(self) -> List[str]:
+        return sorted(self.map) if self.sorted else list(self.map)
+
+    def conds(self, dim: str) -> List[str]:
+        return sorted(self.map[dim]) if self.sorted else list(self.map[dim])
+
+
+def _scan_conditions(path: str, fmt: int, conditions: _Conditions):
+    lines = _read_lines(path)
+    header = lines[0].split(",")
+    if fmt == 1:      # getConditionsFromBinaryData (:94-103)
+        for h in header[3:]:
+            d, c = h.split(":")[0:2]
+            conditions.put(d.strip().lower(), c.strip().lower())
+    elif fmt == 2:    # getConditionsFromLooseData (:105-117)
+        for ln in lines[1:]:
+            s = ln.split(",")
+            conditions.put(s[3].strip().lower(), s[4].strip().lower() or "na")
+    else:             # getConditionsFromCompactData (:119-138)
+        dims = [h.strip().lower() for h in header[3:]]
+        for ln in lines[1:]:
+            s = ln.split(",")
+            for i, d in enumerate(dims):
+                conditions.put(d, s[3 + i].strip().lower() or "na")
+
+
+def _to_binary(path: str, fmt: int, is_test: bool, conditions: Optional[_Conditions], jdk: int = 7) -> str:
+    """TransformationFrom{Binary,Loose,Compact}ToBinary + PublishNewRatingFiles (:150-297): the text of the new
+    binary-format file."""
+    lines = _read_lines(path)
+    header = lines[0].split(",")
+    if conditions is None:
+        conditions = _Conditions(sorted_=False)
+    newlines: Dict[str, Dict[str, str]] = {}
+    order: List[str] = []
+
+    def put_line(key: str, ctx: Dict[str, str]):
+        if key not in newlines:
+            order.append(key)
+        newlines[key] = ctx
+
+    if fmt == 1:
+        for ln in lines[1:]:
+            s = ln.split(",")
+            ctx: Dict[str, str] = {}
+            for i in range(3, len(header)):
+                if int(s[i].strip()) == 0:
+                    continue
+                d, c = [t.strip().lower() for t in header[i].split(":")[0:2]]
+                ctx[d] = c
+                if not is_test:
+                    conditions.put(d, c)
+            put_line(ln, ctx)
+    elif fmt == 2:
+        for ln in lines[1:]:
+            s = ln.split(",")
+            key = ",".join(t.strip().lower() for t in s[0:3])
+            cond = s[4].strip().lower() or "na"
+            if not is_test:
+                conditions.put(s[3].strip().lower(), cond)
+            if key in newlines:
+                newlines[key][s[3].strip().lower()] = cond
+            else:
+                put_line(key, {s[3].strip().lower(): cond})
+    else:
+        dims = [h.strip().lower() for h in header[3:]]
+        for ln in lines[1:]:
+            s = ln.split(",")
+            ctx = {}
+            for i, d in enumerate(dims):
+                cond = s[3 + i].strip().lower() or "na"
+                ctx[d] = cond
+                if not is_test:
+                    conditions.put(d, cond)
+            put_line(ln, ctx)
+    out = ["User, Item, Rating" + "".join(f", {d}:{c}" for d in conditions.dims() for c in conditions.conds(d))]
+    for key in java_hashmap_key_order(order, jdk):
+        ctx = newlines[key]
+        flags: List[str] = []
+        for d in conditions.dims():
+            mine = ctx.get(d)
+            is_na = mine is None or mine == "na"
+            done = False
+            for c in conditions.conds(d):
+                if fmt == 2:   # isLoose (:262-279)
+                    if is_na:
+                        flags.append("1" if c == "na" else "0")
+                    elif done:
+                        flags.append("0")
+                    else:
+                        done = c == mine
+                        flags.append("1" if done else "0")
+                else:          # :280-285 (a rating line without this dimension is a NullPointerException there)
+                    if mine is None:
+                        raise ValueError(f"rating line '{key}' has no condition for dimension '{d}'")
+                    flags.append("1" if mine == c else "0")
+        s = key.split(",")
+        if len(s) > 3:
+            key = ",".join(t.strip().lower() for t in s[0:3])
+        out.append(key + "," + ",".join(flags))
+    return "\n".join(out) + "\n"
+
+
+def transform_to_binary(train_path: str, test_path: Optional[str] = None, jdk: int = 7):
+    """DataTransformer.run() (:299-395).  One file: converted on its own -- dimensions / conditions in order of
+    first appearance, no `na` columns added.  Train + test: the conditions of BOTH files, sorted, plus an `na`
+    condition per dimension (getConditions, :57-92), shape the header of both outputs.  Returns the text of
+    train.csv (and of test.csv).  The ORDER of the rating lines is the iteration order of a java.util.HashMap and so
+    depends on the JVM (`jdk`, see java_hashmap_key_order); it matters downstream because user / item / pair /
+    context ids are handed out by first appearance (DataDAO.java:238-330)."""
+    f_train = _detect_format(train_path)
+    if test_path is None:
+        if f_train == 1:
+            with open(train_path) as f:
+                return f.read()  # FileIO.copyFile (:304)
+        return _to_binary(train_path, f_train, False, None, jdk)
+    f_test = _detect_format(test_path)
+    conditions = _Conditions(sorted_=True)
+    _scan_conditions(train_path, f_train, conditions)
+    _scan_conditions(test_path, f_test, conditions)
+    for d in conditions.dims():
+        if "na" not in conditions.map[d]:
+            conditions.put(d, "na")
+    return _to_binary(train_path, f_train, False, conditions, jdk), _to_binary(test_path, f_test, True, conditions, jdk)
+
+
+def to_traditional(ts: TrainingSet) -> TrainingSet:
+    """DataDAO.toTraditionalSparseMatrix (DataDAO.java:1241-1257): the 2-D user x item `train` matrix that PMF /
+    BiasedMF iterate (Recommender.java:252): one entry per user-item PAIR that has ratings, its value the mean of
+    the pair's ratings over contexts (SparseVector.mean: sequential sum / count), in CRS order (user ascending,
+    item ascending).  Needs ts.pair_ids (read_binary_csv and DataSplitter provide them).  globalMean stays the one
+    of the {pair x context} matrix (Recommender.java:265 takes it from trainMatrix, not from `train`)."""
+    pair = np.asarray(ts.pair_ids, dtype=np.int64)
+    if pair.shape[0] != ts.nnz:
+        raise ValueError("pair_ids must list the user-item pair id of every entry")
+    sums: Dict[int, List[float]] = {}
+    owner: Dict[int, Tuple[int, int]] = {}
+    for p, u, j, r in zip(pair.tolist(), ts.u.tolist(), ts.j.tolist(), ts.r.tolist()):
+        acc = sums.setdefault(p, [0.0, 0])
+        acc[0] += r
+        acc[1] += 1
+        owner[p] = (u, j)
+    cells: Dict[Tuple[int, int], float] = {}
+    for p in sorted(sums):                      # `for (int uiid : sm.rows())`; Table.put: a later pair of the same
+        cells[owner[p]] = sums[p][0] / sums[p][1]  # (user, item) would overwrite -- pair ids are unique per (u, i)
+    keys = sorted(cells)
+    out = TrainingSet(num_users=ts.num_users, num_items=ts.num_items, u=np.array([k[0] for k in keys], dtype=np.int32),
+                      j=np.array([k[1] for k in keys], dtype=np.int32), r=np.array([cells[k] for k in keys], dtype=np.float64),
+                      ctx=None, global_mean=ts.global_mean)
+    return out
