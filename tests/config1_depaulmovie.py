@@ -2,7 +2,9 @@
 restated here: DataTransformer (compact -> binary) -> DataDAO.readData -> DataSplitter (cv -k 5, --rand-seed 1)
 -> toTraditionalSparseMatrix -> BiasedMF.buildModel (100 iterations, learn.rate 2e-2 -bold-driver) -> evalRatings.
 
-    python scripts/config1.py <path to Movie_DePaulMovie/ratings.txt> [--gpu]
+    python -m tests.config1_depaulmovie <path to Movie_DePaulMovie/ratings.txt> [--gpu]
+
+Lives under tests/ because it checks against the CPU oracle (test infrastructure).
 
 Plumbing check (the config is "CPU, no GPU" in BASELINE.json): the CPU oracle trains every fold; with --gpu the
 engine trains the same folds from the same initial arrays and must return bit-identical MAE / RMSE.  The
@@ -16,8 +18,10 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from carskit_b200 import capi, data  # noqa: E402
-from oracle import oracle_py as orc  # noqa: E402  (scripts/ is harness, not product)
+from oracle import oracle_py as orc  # noqa: E402
 
+if __name__ != "__main__":
+    raise SystemExit("run as: python -m tests.config1_depaulmovie <ratings.txt> [--gpu]")
 path = sys.argv[1]
 use_gpu = "--gpu" in sys.argv
 jdk = 8
