@@ -570,6 +570,10 @@ def runCrossValidation(rateMatrix: TrainingSet, name: str, conf: Optional[Dict[s
 
     for i in range(ds.numFold):
         train, test = ds.getKthFold(i + 1)
+        if Rec.MODEL in (capi.PMF, capi.BIASEDMF) and getattr(train, "pair_ids", None) is not None:
+            # the 2-D models iterate `train = rateDao.toTraditionalSparseMatrix(trainMatrix)` (Recommender.java:252)
+            from .data import to_traditional
+            train = to_traditional(train)
         algo = Rec(train, test, fold=i + 1, conf=conf, device=devices[i % len(devices)])
         algos.append(algo)
         t = threading.Thread(target=run, args=(algo, i))
