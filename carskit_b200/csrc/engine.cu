@@ -220,6 +220,18 @@ static LaunchPlan pick_flagged(int Fp, int variant) {
       }
       return pick_flagged_shape<MODEL, 256, 3>(Fp);
     }
+    case 7: {  // as 3, rows moved with 256-bit loads / stores (rows 32-byte aligned: Fp % 4 == 0)
+      LaunchPlan p;
+      if (Fp > 32 && Fp <= 64 && Fp % 4 == 0) {
+        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 4, 8, 256, 2, true>; p.lpr = 4; p.v = 8;
+        return p;
+      }
+      if (Fp > 64 && Fp <= 128 && Fp % 4 == 0) {
+        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 16, 4, 256, 3, true>; p.lpr = 16; p.v = 4;
+        return p;
+      }
+      return pick_flagged<MODEL>(Fp, 3);
+    }
     case 5: {  // 16 lanes per rating: two ratings per warp, short turns
       LaunchPlan p;
       if (Fp > 32 && Fp <= 64) {
@@ -241,7 +253,7 @@ static LaunchPlan pick_flagged(int Fp, int variant) {
 }
 
 static LaunchPlan pick_flagged_plan(int model, int Fp) {
-  const int v = wavefront_variant(3);
+  const int v = wavefront_variant(7);  // 7: 256-bit row accesses where Fp % 4 == 0, else the shapes of 3 (profiles/)
   switch (model) {
     case CARS_PMF: return pick_flagged<M_PMF>(Fp, v);
     case CARS_BIASEDMF: return pick_flagged<M_BIASEDMF>(Fp, v);

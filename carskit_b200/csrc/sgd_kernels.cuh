@@ -83,6 +83,20 @@ __device__ __forceinline__ double2 ld_cg_f64x2(const double* p) {
 __device__ __forceinline__ void st_cg_f64x2(double* p, double2 v) {
   asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
+// 256-bit L2 accesses (LDG/STG.E.ENL2.256 on sm_100): two adjacent 16-byte chunks in one instruction
+__device__ __forceinline__ void ld_cg_f64x4(const double* p, double2& a, double2& b) {
+  asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+__device__ __forceinline__ void st_cg_f64x4(double* p, double2 a, double2 b) {
+  asm volatile("st.global.cg.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+// Which 16-byte chunk of a row lane `gl` holds in slot v.  Narrow: chunks gl, gl + LPR, ... (a group covers 16 * LPR
+// contiguous bytes per instruction).  WIDE: the lane owns 32-byte pieces gl, gl + LPR, ... -- slots 2w and 2w + 1 are
+// the two halves of piece w -- so that one 256-bit access moves both (rows must be 32-byte aligned: Fp % 4 == 0).
+template <int LPR, bool WIDE>
+__device__ __forceinline__ int chunk_of(int gl, int v) {
+  return WIDE ? 2 * (gl + (v >> 1) * LPR) + (v & 1) : gl + v * LPR;
+}
 __device__ __forceinline__ double ld_cg_f64(const double* p) {
   double v;
   asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
@@ -212,22 +226,36 @@ __device__ __forceinline__ void gather_scalars(const DeviceModel& m, int u, int 
 }
 
 // Factor rows straight from global memory (L2) into registers.
-template <int MODEL, int LPR, int V, bool L1 = false>
+template <int MODEL, int LPR, int V, bool L1 = false, bool WIDE = false>
 __device__ __forceinline__ void gather_rows(const DeviceModel& m, int u, int j, int gl, UserRegs<V>& us,
                                             Operands<V>& o, bool load_user) {
   constexpr bool kUserBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CI);
   const int Fp = m.Fp;
   const double* prow = m.P + (int64_t)u * Fp;
   const double* qrow = m.Q + (int64_t)j * Fp;
+  if (WIDE) {
 #pragma unroll
-  for (int v = 0; v < V; v++) {
-    const int c = gl + v * LPR;  // chunk index
-    if (2 * c < Fp) {
-      o.q[v] = ldm_f64x2<L1>(qrow + 2 * c);
-      if (load_user) us.p[v] = ldm_f64x2<L1>(prow + 2 * c);
-    } else {
-      o.q[v] = make_double2(0.0, 0.0);
-      us.p[v] = make_double2(0.0, 0.0);
+    for (int w = 0; w < V / 2; w++) {
+      const int c = chunk_of<LPR, true>(gl, 2 * w);  // first 16-byte chunk of the lane's 32-byte piece
+      if (2 * c < Fp) {
+        ld_cg_f64x4(qrow + 2 * c, o.q[2 * w], o.q[2 * w + 1]);
+        if (load_user) ld_cg_f64x4(prow + 2 * c, us.p[2 * w], us.p[2 * w + 1]);
+      } else {
+        o.q[2 * w] = o.q[2 * w + 1] = make_double2(0.0, 0.0);
+        us.p[2 * w] = us.p[2 * w + 1] = make_double2(0.0, 0.0);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const int c = gl + v * LPR;  // chunk index
+      if (2 * c < Fp) {
+        o.q[v] = ldm_f64x2<L1>(qrow + 2 * c);
+        if (load_user) us.p[v] = ldm_f64x2<L1>(prow + 2 * c);
+      } else {
+        o.q[v] = make_double2(0.0, 0.0);
+        us.p[v] = make_double2(0.0, 0.0);
+      }
     }
   }
   if (kUserBias && load_user) us.bu = ldm_f64<L1>(m.user_bias + u);
@@ -239,7 +267,7 @@ __device__ __forceinline__ void gather_rows(const DeviceModel& m, int u, int j, 
 // scratch of Fp doubles (for the in-order dot product).  The user's row (and userBias) live in `us`
 // and are written back only when `store_user`.  Returns this lane's contribution to the epoch loss.
 // ------------------------------------------------------------------------------------------------
-template <int MODEL, int LPR, int V, bool L1 = false>
+template <int MODEL, int LPR, int V, bool L1 = false, bool WIDE = false>
 __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, int j, int ctx, double r, double lr,
                                                   double* prod, int gl, unsigned gmask, UserRegs<V>& us,
                                                   const Operands<V>& o, bool store_user) {
@@ -259,7 +287,7 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
   // ---- dot product in f order (DenseMatrix.rowMult) --------------------------------------------
 #pragma unroll
   for (int v = 0; v < V; v++) {
-    const int c = gl + v * LPR;
+    const int c = chunk_of<LPR, WIDE>(gl, v);
     if (2 * c < Fp) {
       double2 t = make_double2(__dmul_rn(us.p[v].x, q[v].x), __dmul_rn(us.p[v].y, q[v].y));
       *reinterpret_cast<double2*>(prod + 2 * c) = t;
@@ -371,9 +399,10 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
   // The regularisation terms of the loss, sum_f regU*p^2 + regI*q^2, are accumulated as regU*sum(p^2) +
   // regI*sum(q^2) with FMAs: `loss` is a report value (1e-11 relative), the model is not.
   double sp = 0.0, sq = 0.0;
+  double2 q_even = make_double2(0.0, 0.0), p_even = make_double2(0.0, 0.0);  // WIDE: first half of a 32-byte piece
 #pragma unroll
   for (int v = 0; v < V; v++) {
-    const int c = gl + v * LPR;
+    const int c = chunk_of<LPR, WIDE>(gl, v);
     if (2 * c < Fp) {
       const double2 po = us.p[v], qo = q[v];
       double2 pn, qn;
@@ -382,8 +411,18 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
       pn.y = __dadd_rn(po.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, qo.y), __dmul_rn(m.reg_u, po.y))));
       qn.y = __dadd_rn(qo.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, po.y), __dmul_rn(m.reg_i, qo.y))));
       us.p[v] = pn;
-      stm_f64x2<L1>(qrow + 2 * c, qn);
-      if (store_user) stm_f64x2<L1>(prow + 2 * c, pn);
+      if (WIDE) {
+        if ((v & 1) == 0) {
+          q_even = qn;
+          p_even = pn;
+        } else {  // c - 1 is the piece's first chunk: one 256-bit store per row
+          st_cg_f64x4(qrow + 2 * (c - 1), q_even, qn);
+          if (store_user) st_cg_f64x4(prow + 2 * (c - 1), p_even, pn);
+        }
+      } else {
+        stm_f64x2<L1>(qrow + 2 * c, qn);
+        if (store_user) stm_f64x2<L1>(prow + 2 * c, pn);
+      }
       sp = fma(po.x, po.x, sp);
       sq = fma(qo.x, qo.x, sq);
       sp = fma(po.y, po.y, sp);
@@ -591,7 +630,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 // ld.global.cg: every data access is served by L2, the point of coherence, so no L1 invalidation
 // (CCTL.IVALL, which ld.acquire.gpu would add on every poll) is needed.
 // ------------------------------------------------------------------------------------------------
-template <int MODEL, int LPR, int V, int THREADS, int MINB>
+template <int MODEL, int LPR, int V, int THREADS, int MINB, bool WIDE = false>
 __global__ void __launch_bounds__(THREADS, MINB)
     sgd_flagged_kernel(DeviceModel m, const RatingRec* __restrict__ recs, int64_t nnz, unsigned* flags,
                        unsigned off_u, unsigned off_j, double lr, double* block_partial
@@ -651,14 +690,14 @@ __global__ void __launch_bounds__(THREADS, MINB)
 #endif
         UserRegs<V> us;
         Operands<V> o;
-        gather_rows<MODEL, LPR, V>(m, rec.u, rec.j, gl, us, o, true);
+        gather_rows<MODEL, LPR, V, false, WIDE>(m, rec.u, rec.j, gl, us, o, true);
         gather_scalars<MODEL, LPR, V>(m, rec.u, rec.j, rec.ctx, gl, o, cond);
 #ifdef CARS_TRACE
         long long tc2;
         asm volatile("mov.u64 %0, %%clock64;" : "=l"(tc2) : "d"(us.p[V - 1].y), "d"(o.q[V - 1].y), "d"(o.cb), "d"(us.p[0].x), "d"(o.q[0].x));
 #endif
-        acc = __dadd_rn(acc, compute_scatter<MODEL, LPR, V>(m, rec.u, rec.j, rec.ctx, rec.r, lr, prod, gl, gmask, us,
-                                                            o, true));
+        acc = __dadd_rn(acc, compute_scatter<MODEL, LPR, V, false, WIDE>(m, rec.u, rec.j, rec.ctx, rec.r, lr, prod, gl,
+                                                                         gmask, us, o, true));
         __syncwarp(gmask);  // the group's stores happen-before lane 0's release
 #ifdef CARS_TRACE
         const long long tc3 = clock64();
