@@ -208,7 +208,7 @@ static LaunchPlan pick_flagged_shape(int Fp) {
 }
 
 template <int MODEL>
-static LaunchPlan pick_flagged(int Fp, int variant) {
+static LaunchPlan pick_flagged(int Fp, int variant, int F = 0) {
   switch (variant) {
     case 1: return pick_flagged_shape<MODEL, 512, 2>(Fp);
     case 2: return pick_flagged_shape<MODEL, 256, 3>(Fp);
@@ -219,6 +219,18 @@ static LaunchPlan pick_flagged(int Fp, int variant) {
         return p;
       }
       return pick_flagged_shape<MODEL, 256, 3>(Fp);
+    }
+    case 8: {  // as 7 with the factor count a compile-time constant (F = 64 / F = 128 exactly)
+      LaunchPlan p;
+      if (F == 64) {
+        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 4, 8, 256, 2, true, 64>; p.lpr = 4; p.v = 8;
+        return p;
+      }
+      if (F == 128) {
+        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 16, 4, 256, 3, true, 128>; p.lpr = 16; p.v = 4;
+        return p;
+      }
+      return pick_flagged<MODEL>(Fp, 7, F);
     }
     case 7: {  // as 3, rows moved with 256-bit loads / stores (rows 32-byte aligned: Fp % 4 == 0)
       LaunchPlan p;
@@ -252,14 +264,14 @@ static LaunchPlan pick_flagged(int Fp, int variant) {
   }
 }
 
-static LaunchPlan pick_flagged_plan(int model, int Fp) {
-  const int v = wavefront_variant(7);  // 7: 256-bit row accesses where Fp % 4 == 0, else the shapes of 3 (profiles/)
+static LaunchPlan pick_flagged_plan(int model, int Fp, int F) {
+  const int v = wavefront_variant(8);  // 8: F = 64 / 128 compiled in + 256-bit row accesses; else 7 (256-bit where Fp % 4 == 0); else 3
   switch (model) {
-    case CARS_PMF: return pick_flagged<M_PMF>(Fp, v);
-    case CARS_BIASEDMF: return pick_flagged<M_BIASEDMF>(Fp, v);
-    case CARS_CAMF_CI: return pick_flagged<M_CAMF_CI>(Fp, v);
-    case CARS_CAMF_CU: return pick_flagged<M_CAMF_CU>(Fp, v);
-    case CARS_CAMF_CUCI: return pick_flagged<M_CAMF_CUCI>(Fp, v);
+    case CARS_PMF: return pick_flagged<M_PMF>(Fp, v, F);
+    case CARS_BIASEDMF: return pick_flagged<M_BIASEDMF>(Fp, v, F);
+    case CARS_CAMF_CI: return pick_flagged<M_CAMF_CI>(Fp, v, F);
+    case CARS_CAMF_CU: return pick_flagged<M_CAMF_CU>(Fp, v, F);
+    case CARS_CAMF_CUCI: return pick_flagged<M_CAMF_CUCI>(Fp, v, F);
   }
   return LaunchPlan{};
 }
@@ -446,7 +458,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     h->smem = (size_t)(Fp + 2) * 8;
   } else {
     LaunchPlan plan = h->dataflow ? pick_dataflow_plan(model, Fp)
-                      : h->flagged ? pick_flagged_plan(model, Fp) : pick_plan(model, desc->mode, Fp);
+                      : h->flagged ? pick_flagged_plan(model, Fp, F) : pick_plan(model, desc->mode, Fp);
     if (!plan.fn) { fail(h, CARS_E_UNSUPPORTED, "no kernel for model %d mode %d F %d", model, desc->mode, F); return bail(CARS_E_UNSUPPORTED); }
     const int G = 32 / plan.lpr;
     groups_per_cta = (plan.threads / 32) * G;
@@ -728,7 +740,7 @@ extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
     h->st.kernel_launches += 1;
     partials = h->loss_blocks;
   } else if (h->flagged) {
-    LaunchPlan plan = pick_flagged_plan(h->d.model, m.Fp);
+    LaunchPlan plan = pick_flagged_plan(h->d.model, m.Fp, m.F);
     CUDA_TRY(h, cudaMemsetAsync(h->d_flags, 0, h->flags_words * sizeof(unsigned), h->stream));
     const RatingRec* recs = h->d_rec;
     int64_t nnz = h->nnz;

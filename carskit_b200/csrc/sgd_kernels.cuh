@@ -226,11 +226,13 @@ __device__ __forceinline__ void gather_scalars(const DeviceModel& m, int u, int 
 }
 
 // Factor rows straight from global memory (L2) into registers.
-template <int MODEL, int LPR, int V, bool L1 = false, bool WIDE = false>
+// FIXF > 0: the number of factors is this compile-time constant (F = Fp = FIXF): the bounds checks fold away and the
+// in-order dot product unrolls into straight-line code.
+template <int MODEL, int LPR, int V, bool L1 = false, bool WIDE = false, int FIXF = 0>
 __device__ __forceinline__ void gather_rows(const DeviceModel& m, int u, int j, int gl, UserRegs<V>& us,
                                             Operands<V>& o, bool load_user) {
   constexpr bool kUserBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CI);
-  const int Fp = m.Fp;
+  const int Fp = FIXF > 0 ? FIXF : m.Fp;
   const double* prow = m.P + (int64_t)u * Fp;
   const double* qrow = m.Q + (int64_t)j * Fp;
   if (WIDE) {
@@ -267,14 +269,14 @@ __device__ __forceinline__ void gather_rows(const DeviceModel& m, int u, int j, 
 // scratch of Fp doubles (for the in-order dot product).  The user's row (and userBias) live in `us`
 // and are written back only when `store_user`.  Returns this lane's contribution to the epoch loss.
 // ------------------------------------------------------------------------------------------------
-template <int MODEL, int LPR, int V, bool L1 = false, bool WIDE = false>
+template <int MODEL, int LPR, int V, bool L1 = false, bool WIDE = false, int FIXF = 0>
 __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, int j, int ctx, double r, double lr,
                                                   double* prod, int gl, unsigned gmask, UserRegs<V>& us,
                                                   const Operands<V>& o, bool store_user) {
   constexpr bool kUserBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CI);
   constexpr bool kItemBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CU);
   constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU || MODEL == M_CAMF_CUCI);
-  const int Fp = m.Fp;
+  const int Fp = FIXF > 0 ? FIXF : m.Fp;
   const int Dmax = m.Dmax;
   double* prow = m.P + (int64_t)u * Fp;
   double* qrow = m.Q + (int64_t)j * Fp;
@@ -296,8 +298,9 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
   __syncwarp(gmask);
   double dot = 0.0;
   {
-    const int F = m.F;
+    const int F = FIXF > 0 ? FIXF : m.F;
     const int F2 = F & ~1;
+#pragma unroll
     for (int f = 0; f < F2; f += 2) {
       double2 t = *reinterpret_cast<const double2*>(prod + f);
       dot = __dadd_rn(dot, t.x);
@@ -630,7 +633,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 // ld.global.cg: every data access is served by L2, the point of coherence, so no L1 invalidation
 // (CCTL.IVALL, which ld.acquire.gpu would add on every poll) is needed.
 // ------------------------------------------------------------------------------------------------
-template <int MODEL, int LPR, int V, int THREADS, int MINB, bool WIDE = false>
+template <int MODEL, int LPR, int V, int THREADS, int MINB, bool WIDE = false, int FIXF = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
     sgd_flagged_kernel(DeviceModel m, const RatingRec* __restrict__ recs, int64_t nnz, unsigned* flags,
                        unsigned off_u, unsigned off_j, double lr, double* block_partial
@@ -646,7 +649,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
   const int gl = lane % LPR;
   const int gw = lane / LPR;
   const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (gw * LPR));
-  const int prod_stride = m.Fp + 2;
+  const int prod_stride = (FIXF > 0 ? FIXF : m.Fp) + 2;
   double* prod = reinterpret_cast<double*>(smem_raw) + (size_t)(warp * G + gw) * prod_stride;
   unsigned* done_u = flags + off_u;
   unsigned* done_j = flags + off_j;
@@ -690,13 +693,13 @@ __global__ void __launch_bounds__(THREADS, MINB)
 #endif
         UserRegs<V> us;
         Operands<V> o;
-        gather_rows<MODEL, LPR, V, false, WIDE>(m, rec.u, rec.j, gl, us, o, true);
+        gather_rows<MODEL, LPR, V, false, WIDE, FIXF>(m, rec.u, rec.j, gl, us, o, true);
         gather_scalars<MODEL, LPR, V>(m, rec.u, rec.j, rec.ctx, gl, o, cond);
 #ifdef CARS_TRACE
         long long tc2;
         asm volatile("mov.u64 %0, %%clock64;" : "=l"(tc2) : "d"(us.p[V - 1].y), "d"(o.q[V - 1].y), "d"(o.cb), "d"(us.p[0].x), "d"(o.q[0].x));
 #endif
-        acc = __dadd_rn(acc, compute_scatter<MODEL, LPR, V, false, WIDE>(m, rec.u, rec.j, rec.ctx, rec.r, lr, prod, gl,
+        acc = __dadd_rn(acc, compute_scatter<MODEL, LPR, V, false, WIDE, FIXF>(m, rec.u, rec.j, rec.ctx, rec.r, lr, prod, gl,
                                                                          gmask, us, o, true));
         __syncwarp(gmask);  // the group's stores happen-before lane 0's release
 #ifdef CARS_TRACE
