@@ -380,7 +380,8 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
                    "items": wl["items"], "conditions": int(sum(wl["dims"])) if wl["dims"] else 0, "context_dims": D,
                    "nnz_per_gpu": nnz_local, "nnz_total": int(nnz_total), "mode": "exact (serial-equivalent; flagged wavefront schedule)",
                    "levels": int(st0.num_levels), "parallelism": f"user-range shards x{world}" if world > 1 else "1 gpu",
-                   "l2": "inputs larger than L2 (ratings 2 GB + P 0.5 GB per epoch vs 126 MB L2); no flush",
+                   "l2": f"inputs larger than L2 (rating records {nnz_local * 32 / 1e9:.1f} GB + P {wl['users'] * F * 8 / 1e9:.2f} GB "
+                         "streamed per epoch vs 126 MB L2); no flush",
                    "e2e_definition": f"recommender.buildModel() with num.max.iter={args.steps} from "
                                      f"{'pinned' if pinned_inputs else 'pageable'} host buffers: cars_create (H2D ratings + "
                                      "device-built schedule) + cars_upload + epochs (loss D2H each) + cars_download"},
