@@ -1129,4 +1129,4 @@ extern "C" int cars_get_stats(const cars_handle* h, cars_stats* out) {
 
 extern "C" void* cars_get_stream(const cars_handle* h) { return h ? (void*)h->stream : nullptr; }
 
-extern "C" const char* cars_version(void) { return "carskit_b200 abi 1, sm_100a, fp64 serial-equivalent SGD"; }
+extern "C" const char* cars_version(void) { return "carskit_b200 abi 2, sm_100a, fp64 serial-equivalent SGD"; }

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CARS_ABI_VERSION 1
+#define CARS_ABI_VERSION 2 /* 2: cars_stats grew (schedule_*_ms), CARS_CAMF_CUCI added */
 
 /* Recommender classes on the hot path. */
 enum cars_model {
