@@ -3,6 +3,7 @@ declares, and fails loudly (no CPU fallback) when there is no CUDA device.  No c
 import ctypes as C
 import os
 import re
+import subprocess
 
 import pytest
 
@@ -106,3 +107,15 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\"[^\"]*oracle", txt, flags=re.M):
                     bad.append(f)
     assert not bad, bad
+
+
+@pytest.mark.skipif(_has_cuda(), reason="on a GPU box the client trains; this check is for boxes without a GPU")
+def test_plain_c_client_links_and_reports_no_device(cars_lib, tmp_path):
+    # the header is consumable from plain C and the library links without Python: examples/c_client.c
+    libdir = os.path.join(ROOT, "carskit_b200")
+    exe = str(tmp_path / "c_client")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_client.c"), "-L", libdir, "-lcarskit_b200",
+                           f"-Wl,-rpath,{libdir}", "-o", exe])
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 3 and "cars_create: -2" in p.stdout and "no CPU path" in p.stdout
