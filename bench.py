@@ -227,7 +227,7 @@ def run_reference(args, wl, wl_name, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl_name, "model": wl["model"], "factors": wl["F"], "users": wl["users"],
+        "config": {"workload": wl_name, "recommender": wl["model"], "factors": wl["F"], "users": wl["users"],
                    "items": wl["items"], "conditions": int(sum(wl["dims"])) if wl["dims"] else 0,
                    "context_dims": D, "nnz": ts.nnz,
                    "note": "reference arm = CPU oracle port of the Java buildModel() loop (no JVM in the image); the loop "
@@ -376,7 +376,7 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl_name, "model": wl["model"], "factors": F, "users_per_gpu": wl["users"],
+        "config": {"workload": wl_name, "recommender": wl["model"], "factors": F, "users_per_gpu": wl["users"],
                    "items": wl["items"], "conditions": int(sum(wl["dims"])) if wl["dims"] else 0, "context_dims": D,
                    "nnz_per_gpu": nnz_local, "nnz_total": int(nnz_total), "mode": "exact (serial-equivalent; flagged wavefront schedule)",
                    "levels": int(st0.num_levels), "parallelism": f"user-range shards x{world}" if world > 1 else "1 gpu",
@@ -490,7 +490,7 @@ def run_fm(args, wl, wl_name, rank, world, local_rank):
         "metric": "fm_als_rating_iterations_per_sec", "value": value, "unit": "rating-iterations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl_name, "model": "fm", "factors": k, "users": wl["users"], "items": wl["items"],
+        "config": {"workload": wl_name, "recommender": "fm", "factors": k, "users": wl["users"], "items": wl["items"],
                    "conditions": int(sum(wl["dims"])), "context_dims": D, "nnz_per_gpu": ts.nnz, "nnz_total": nnz_total,
                    "parallelism": f"row shards x{world}, {3 * (1 + k) + 1} all-reduces of per-coordinate sums per iteration" if world > 1 else "1 gpu",
                    "l2": "inputs larger than L2 (Qc alone is nnz*k*8 bytes); no flush", "wall_ms_per_step": wall * 1e3 / args.steps},
