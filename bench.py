@@ -49,6 +49,15 @@ WORKLOADS = {
                                          nnz=10_000_000, seed=20261017),
     "camf_ci_f64_tiny": dict(model="camf_ci", F=64, users=5_000, items=1_000, dims=[8, 8, 8, 8], nnz=200_000,
                              seed=20261017),
+    # SURVEY.md 8d config 3, "Zipf(1.0)-item variant": item popularity ~ 1/rank.  The dependency DAG of EXACT mode is
+    # as deep as the most popular item's degree (8 % of all ratings), so this is the workload FAST mode exists for.
+    "camf_ci_f64_1Mx100Kx32c_100M_zipf1.0": dict(model="camf_ci", F=64, users=1_000_000, items=100_000, dims=[8, 8, 8, 8],
+                                                 nnz=100_000_000, seed=20261017, item_zipf=1.0),
+    "camf_ci_f64_100Kx10Kx32c_10M_zipf1.0": dict(model="camf_ci", F=64, users=100_000, items=10_000, dims=[8, 8, 8, 8],
+                                                 nnz=10_000_000, seed=20261017, item_zipf=1.0),
+    # BASELINE.json configs[1]: CAMF_C, 10 factors, Frappe-shaped (957 x 4 082, 8 dims with 7/7/2/3/2/9/80/233 conditions)
+    "camf_c_f10_frappe_shaped": dict(model="camf_c", F=10, users=957, items=4082, dims=[7, 7, 2, 3, 2, 9, 80, 233],
+                                     nnz=96_203, seed=1),
     "camf_cu_f128_2Mx200Kx64c_200M": dict(model="camf_cu", F=128, users=2_000_000, items=200_000,
                                           dims=[16, 16, 16, 16], nnz=200_000_000, seed=20261017),
     # FM (reference ALS semantics, FM.java); BASELINE.json configs[3] shape scaled to one GPU's share
@@ -140,7 +149,7 @@ def make_inputs(wl: dict, rank: int):
     from carskit_b200 import capi, synth
     t0 = time.time()
     ts, _ = synth.make_training_set(wl["users"], wl["items"], wl["dims"], wl["nnz"], seed=wl["seed"] + rank,
-                                    order="user_sorted")
+                                    order="user_sorted", item_zipf=wl.get("item_zipf", 0.0))
     model = capi.MODEL_NAMES[wl["model"]]
     F = wl["F"]
     rng = np.random.default_rng(wl["seed"] + 7919)  # same model init on every rank (item side is replicated)
@@ -229,7 +238,7 @@ def run_reference(args, wl, wl_name, rank, world):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl_name, "recommender": wl["model"], "factors": wl["F"], "users": wl["users"],
                    "items": wl["items"], "conditions": int(sum(wl["dims"])) if wl["dims"] else 0,
-                   "context_dims": D, "nnz": ts.nnz,
+                   "context_dims": D, "nnz": ts.nnz, "item_zipf": wl.get("item_zipf", 0.0),
                    "note": "reference arm = CPU oracle port of the Java buildModel() loop (no JVM in the image); the loop "
                            "is sequential, so the host's cores are used the way the reference uses them: one model "
                            "(cross-validation fold) per thread"},
@@ -239,6 +248,109 @@ def run_reference(args, wl, wl_name, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
+
+
+def model_digest(arrs: dict) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for k in sorted(arrs):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(arrs[k]).tobytes())
+    return h.hexdigest()
+
+
+def parity_check(wl, ts, model, arrs, local_rank, mode, epochs=2):
+    """The parity gate at the bench's own size: `epochs` epochs of the SAME arrays on the GPU
+    (through the C ABI) and on the CPU oracle.  EXACT: P, Q and every bias must be bit-identical (SHA-256 of the
+    arrays) and the loss within 1e-11 relative.  FAST is not serial-equivalent: the loss difference is reported."""
+    from carskit_b200 import capi
+    from oracle import oracle_py as orc
+    orc.build()
+    F = wl["F"]
+    regs = dict(reg_u=capi.f32(1e-4), reg_i=capi.f32(1e-4), reg_b=capi.f32(1e-4), reg_c=capi.f32(1e-3))
+    lr = capi.f32(0.02)
+    got = {k: v.copy() for k, v in arrs.items()}
+    desc = capi.make_desc(ts, model, F, device=local_rank, mode=capi.FAST if mode == "fast" else capi.EXACT, **regs)
+    t0 = time.perf_counter()
+    with capi.Engine(desc, keepalive=ts) as eng:
+        eng.upload(got)
+        gl = [eng.epoch(lr) for _ in range(epochs)]
+        eng.download(got)
+    t_gpu = time.perf_counter() - t0
+    ref = {k: v.copy() for k, v in arrs.items()}
+    dref = capi.make_desc(ts, model, F, **regs)
+    t0 = time.perf_counter()
+    rl = [orc.epoch(dref, ref, lr) for _ in range(epochs)]
+    t_cpu = time.perf_counter() - t0
+    out = {"mode": mode, "epochs": epochs, "nnz": ts.nnz,
+           "loss_rel": max(abs(a - b) / abs(b) for a, b in zip(gl, rl)),
+           "oracle_seconds": round(t_cpu, 2), "gpu_seconds_incl_setup": round(t_gpu, 2),
+           "oracle_updates_per_sec_1_thread": ts.nnz * epochs / t_cpu}
+    if mode == "exact":
+        out["digest_equal"] = model_digest(got) == model_digest(ref)
+        out["arrays_bit_identical"] = {k: bool(np.array_equal(got[k], ref[k])) for k in ref}
+        out["bar"] = "P, Q, biases bit-identical (sha256 over the arrays); loss within 1e-11 relative"
+        out["ok"] = bool(out["digest_equal"] and out["loss_rel"] < 1e-11)
+    else:
+        out["max_abs_diff"] = {k: float(np.max(np.abs(got[k] - ref[k]))) if ref[k].size else 0.0 for k in ref}
+        out["bar"] = "not serial-equivalent: loss difference after the same epochs is reported, not gated"
+        out["ok"] = bool(all(math.isfinite(x) for x in gl))
+    return out
+
+
+def rmse_vs_serial(wl, rank, world, local_rank, mode, combine, epochs=5):
+    """N > 1: held-out RMSE of the user-range-sharded run against the serial oracle trained on
+    the UNION of the shards, on a 1 % sample of the workload's shape with ratings that can be learnt (planted
+    low-rank model + noise; the bench workload's own ratings are uniform noise, on which every model has the same
+    held-out RMSE).  Each rank regenerates the same union from the same seed and keeps its user range."""
+    import torch.distributed as dist
+    from carskit_b200 import capi, recommender, sharding, synth
+    users, items, nnz = max(1000, wl["users"] // 100), max(100, wl["items"] // 100), max(10000, wl["nnz"] // 100)
+    ts, test = synth.make_training_set(users * world, items, wl["dims"], nnz * world, seed=wl["seed"] + 31, holdout=0.1,
+                                       planted_rank=8, item_zipf=wl.get("item_zipf", 0.0))
+    F = wl["F"]
+    model = capi.MODEL_NAMES[wl["model"]]
+    rng = np.random.default_rng(wl["seed"] + 17)
+    init = {}
+    for k, shp in capi.member_shapes(model, ts.num_users, ts.num_items, ts.num_conditions, F).items():
+        init[k] = rng.random(shp) if k in ("ic_bias", "uc_bias") else 0.1 * rng.standard_normal(shp)
+    shard, lo = sharding.shard_training_set(ts, rank, world)
+    hi = lo + shard.num_users
+    tshard = sharding.shard_test_set(test, lo, hi)
+    local = {k: (sharding.shard_user_rows(v, lo, hi) if k in ("P", "user_bias", "uc_bias") else v.copy()) for k, v in init.items()}
+    conf = {"num.factors": str(F), "num.max.iter": str(epochs), "learn.rate": "2e-2 -max -1 -bold-driver",
+            "reg.lambda": "0.0001 -c 0.001", "engine.mode": mode, "rating.min": "1", "rating.max": "5"}
+    rec = recommender.getRecommender(wl["model"])(shard, tshard, conf=conf, device=local_rank, world=world, combine=combine)
+    rec.initModel(init=local)
+    rec.keep_engine = True
+    rec.buildModel()
+    sharded = rec.evalRatings()["RMSE"]  # sums |err|^2 and counts over the ranks
+    losses = list(rec.iter_losses)
+    rec.close_engine()
+    out = None
+    if rank == 0:
+        from oracle import oracle_py as orc
+        orc.build()
+        regs = dict(reg_u=capi.f32(1e-4), reg_i=capi.f32(1e-4), reg_b=capi.f32(1e-4), reg_c=capi.f32(1e-3))
+        desc = capi.make_desc(ts, model, F, **regs)
+        ref = {k: v.copy() for k, v in init.items()}
+        lr, last, rl = capi.f32(0.02), 0.0, []
+        for it in range(1, epochs + 1):
+            loss = orc.epoch(desc, ref, lr)
+            rl.append(loss)
+            if it > 1:
+                lr = lr * 1.05 if abs(last) > abs(loss) else lr * 0.5
+            last = loss
+        p = orc.predict(desc, ref, test["u"], test["j"], test["ctx"], bound=True, min_rate=1.0, max_rate=5.0)
+        serial = math.sqrt(float(np.mean((test["r"] - p) ** 2)))
+        out = {"sharded": sharded, "serial": serial, "delta": sharded - serial, "tolerance": 0.02, "epochs": epochs,
+               "ok": bool(abs(sharded - serial) < 0.02),
+               "loss_sharded": losses, "loss_serial": rl,
+               "problem": f"{users * world} users x {items} items, {ts.nnz} train / {len(test['r'])} held-out ratings, planted "
+                          f"rank-8 model + N(0, 0.5) noise, {world} user-range shards, combine={combine}, mode={mode}; serial = "
+                          "CPU oracle on the union of the shards"}
+    dist.barrier()
+    return out
 
 
 def run_b200(args, wl, wl_name, rank, world, local_rank):
@@ -253,12 +365,13 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    mode = args.mode
     ts, model, arrs = make_inputs(wl, rank)
     F = wl["F"]
     D = len(wl["dims"]) if wl["dims"] else 0
     B = algorithmic_bytes(wl["model"], F, D)
     conf = {"num.factors": str(F), "num.max.iter": str(args.steps), "learn.rate": "2e-2 -max -1 -bold-driver",
-            "reg.lambda": "0.0001 -c 0.001"}
+            "reg.lambda": "0.0001 -c 0.001", "engine.mode": mode}
     Rec = recommender.getRecommender(wl["model"])
 
     def barrier():
@@ -267,17 +380,26 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---------------- parity at the bench's own size (rank 0, N = 1) ------------------------------------------
+    parity = None
+    if world == 1 and not args.no_parity:
+        parity = parity_check(wl, ts, model, arrs, local_rank, mode)
+        log(f"[bench] parity: {json.dumps(parity)}")
+        if not parity["ok"]:
+            raise RuntimeError(f"parity check failed: {parity}")
+
     # ---------------- device-resident arm: `value` -----------------------------------------------------
     tstream = torch.cuda.Stream(device=dev)  # the engine's kernels, the collectives and the events share it
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
-    rec = Rec(ts, None, conf=conf, device=local_rank, stream=stream, world=world)
+    rec = Rec(ts, None, conf=conf, device=local_rank, stream=stream, world=world, combine=args.combine)
     rec.initModel(init={k: v.copy() for k, v in arrs.items()})
     t0 = time.time()
     eng = rec.open_engine()
     st0 = eng.stats()
     log(f"[bench] rank {rank}: cars_create+upload {time.time() - t0:.1f}s (schedule {st0.schedule_ms:.0f} ms, "
-        f"levels {st0.num_levels}, max level {st0.max_level_size}, grid {st0.grid_ctas}x{st0.block_threads})")
+        f"levels/chunks {st0.num_levels}, max {st0.max_level_size}, grid {st0.grid_ctas}x{st0.block_threads}, "
+        f"max item degree {st0.max_item_degree}, min item scale {st0.fast_min_item_scale:.3g})")
     losses = []
     for it in range(args.warmup):
         rec.train_epoch(it + 1)
@@ -314,40 +436,54 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
     value = nnz_total * args.steps / (ms * 1e-3)
     rec.close_engine()
     log(f"[bench] rank {rank}: {args.steps} epochs in {ms:.1f} ms; SGD kernel {np.mean(kernel_ms):.2f} ms/epoch; "
-        f"losses {losses[:3]}..")
+        f"losses {losses[:3]}.. {losses[-1]}")
 
     # ---------------- end-to-end arm: recommender.buildModel() from host buffers --------------------------
-    # Inputs live in PINNED host memory (the contract's e2e definition); CARS_BENCH_PAGEABLE=1 times the
-    # pageable path instead (what a JNI caller's GetPrimitiveArrayCritical hands over: staged by host threads).
-    pinned_inputs = os.environ.get("CARS_BENCH_PAGEABLE", "0") != "1"
+    # The contract's e2e: inputs in PINNED host memory.  A JNI caller hands over pageable arrays
+    # (GetPrimitiveArrayCritical), staged by the library's host threads: measured too, as `e2e_pageable`.
     keep_pinned = []
 
-    def pin(a):
-        if a is None or not pinned_inputs:
+    def pin(a, pinned):
+        if a is None or not pinned:
             return a
         t = torch.from_numpy(a).pin_memory()
         keep_pinned.append(t)
         return t.numpy()
 
-    ts_e2e = capi.TrainingSet(num_users=ts.num_users, num_items=ts.num_items, u=pin(ts.u), j=pin(ts.j), r=pin(ts.r),
-                              ctx=pin(ts.ctx), num_conditions=ts.num_conditions, num_contexts=ts.num_contexts,
-                              ctx_ptr=ts.ctx_ptr, ctx_cond=ts.ctx_cond, global_mean=ts.global_mean)
-    rec2 = Rec(ts_e2e, None, conf=conf, device=local_rank, stream=stream, world=world)
-    rec2.initModel(init={k: pin(v) for k, v in arrs.items()})
-    barrier()
-    t0 = time.perf_counter()
-    rec2.buildModel()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    iters = len(rec2.iter_losses)
-    st2 = rec2.stats
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t[0])
-    e2e_value = nnz_total * iters / e2e_s
-    log(f"[bench] rank {rank}: buildModel() e2e {e2e_s:.2f}s for {iters} epochs (schedule {st2.schedule_ms:.0f} ms, "
-        f"h2d {st2.h2d_bytes / 1e9:.2f} GB, d2h {st2.d2h_bytes / 1e9:.2f} GB)")
+    def e2e_run(pinned):
+        ts_e = capi.TrainingSet(num_users=ts.num_users, num_items=ts.num_items, u=pin(ts.u, pinned), j=pin(ts.j, pinned),
+                                r=pin(ts.r, pinned), ctx=pin(ts.ctx, pinned), num_conditions=ts.num_conditions,
+                                num_contexts=ts.num_contexts, ctx_ptr=ts.ctx_ptr, ctx_cond=ts.ctx_cond,
+                                global_mean=ts.global_mean)
+        rec2 = Rec(ts_e, None, conf=conf, device=local_rank, stream=stream, world=world, combine=args.combine)
+        rec2.initModel(init={k: pin(v, pinned) for k, v in arrs.items()})
+        barrier()
+        t0 = time.perf_counter()
+        rec2.buildModel()
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        tt = torch.tensor([secs], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        secs = float(tt[0])
+        iters = len(rec2.iter_losses)
+        st2 = rec2.stats
+        log(f"[bench] rank {rank}: buildModel() e2e ({'pinned' if pinned else 'pageable'}) {secs:.2f}s for {iters} epochs "
+            f"(schedule {st2.schedule_ms:.0f} ms, h2d {st2.h2d_bytes / 1e9:.2f} GB, d2h {st2.d2h_bytes / 1e9:.2f} GB)")
+        return {"value": nnz_total * iters / secs, "unit": UNIT, "h2d_bytes_per_step": int(st2.h2d_bytes / max(1, iters)),
+                "d2h_bytes_per_step": int(st2.d2h_bytes / max(1, iters)), "seconds": secs, "epochs": iters,
+                "host_buffers": "pinned" if pinned else "pageable", "schedule_ms": st2.schedule_ms,
+                "schedule_copy_ms": st2.schedule_copy_ms, "schedule_levels_ms": st2.schedule_levels_ms,
+                "schedule_pack_ms": st2.schedule_pack_ms}
+
+    e2e = e2e_run(True)
+    keep_pinned.clear()
+    e2e_pageable = e2e_run(False)
+
+    # ---------------- N > 1: convergence of the sharded run against the serial loop ---------------------------
+    rvs = None
+    if world > 1 and not args.no_parity:
+        rvs = rmse_vs_serial(wl, rank, world, local_rank, mode, args.combine)
 
     if rank != 0:
         if world > 1:
@@ -371,31 +507,37 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(wl_name, {}).get("dram_bytes_per_launch")
+        traffic = json.load(open(tp)).get(f"{wl_name}:{mode}" if mode != "exact" else wl_name, {}).get("dram_bytes_per_launch")
+    kernel = "sgd_fast_kernel" if mode == "fast" else ("sgd_serial_kernel" if wl["model"] == "camf_c" else "sgd_flagged_kernel")
+    mode_txt = ("fast (hogwild: user-ordered chunks, item side by red.global.add.f64; not serial-equivalent)" if mode == "fast"
+                else "exact (serial-equivalent; flagged wavefront schedule)")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl_name, "recommender": wl["model"], "factors": F, "users_per_gpu": wl["users"],
+        "config": {"workload": wl_name, "recommender": wl["model"], "factors": F, "users": wl["users"],
                    "items": wl["items"], "conditions": int(sum(wl["dims"])) if wl["dims"] else 0, "context_dims": D,
-                   "nnz_per_gpu": nnz_local, "nnz_total": int(nnz_total), "mode": "exact (serial-equivalent; flagged wavefront schedule)",
-                   "levels": int(st0.num_levels), "parallelism": f"user-range shards x{world}" if world > 1 else "1 gpu",
+                   "nnz": nnz_local, "nnz_total": int(nnz_total), "item_zipf": wl.get("item_zipf", 0.0), "mode": mode_txt,
+                   "levels": int(st0.num_levels), "max_item_degree": int(st0.max_item_degree),
+                   "fast_min_item_scale": st0.fast_min_item_scale,
+                   "parallelism": f"user-range shards x{world}: users/nnz above are PER GPU; item block combined "
+                                  f"({args.combine}) by one all-reduce per epoch" if world > 1 else "1 gpu",
                    "l2": f"inputs larger than L2 (rating records {nnz_local * 32 / 1e9:.1f} GB + P {wl['users'] * F * 8 / 1e9:.2f} GB "
                          "streamed per epoch vs 126 MB L2); no flush",
-                   "e2e_definition": f"recommender.buildModel() with num.max.iter={args.steps} from "
-                                     f"{'pinned' if pinned_inputs else 'pageable'} host buffers: cars_create (H2D ratings + "
-                                     "device-built schedule) + cars_upload + epochs (loss D2H each) + cars_download"},
+                   "e2e_definition": f"recommender.buildModel() with num.max.iter={args.steps} from pinned host buffers: "
+                                     "cars_create (H2D ratings + device-built schedule) + cars_upload + epochs (loss D2H each) + "
+                                     "cars_download; e2e_pageable = the same from pageable buffers (what a JNI caller has)"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st2.h2d_bytes / max(1, iters)),
-                "d2h_bytes_per_step": int(st2.d2h_bytes / max(1, iters)), "seconds": e2e_s, "epochs": iters,
-                "host_buffers": "pinned" if pinned_inputs else "pageable",
-                "schedule_ms": st2.schedule_ms, "schedule_copy_ms": st2.schedule_copy_ms,
-                "schedule_levels_ms": st2.schedule_levels_ms, "schedule_pack_ms": st2.schedule_pack_ms},
+        "e2e": e2e,
+        "e2e_pageable": e2e_pageable,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "sgd_flagged_kernel", "kernel_ms_per_launch": kms,
+                     "traffic": traffic, "kernel": kernel, "kernel_ms_per_launch": kms,
                      "algorithmic_bytes_per_update": B, "updates_per_launch": nnz_local, "peak_source": peak_src},
         "cpu_baseline": cpu,
+        "parity": parity,
+        "rmse_vs_serial": rvs,
+        "loss_per_rating_last_epoch": losses[-1] / nnz_local if world == 1 else None,
     }
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -515,6 +657,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("CARS_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison at the bench's size (N = 1) and the "
+                    "rmse_vs_serial mini-run (N > 1)")
+    ap.add_argument("--mode", default=os.environ.get("CARS_BENCH_MODE", "exact"), choices=["exact", "fast"])
+    ap.add_argument("--combine", default="mean", choices=["mean", "sum"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -12,10 +12,11 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 PMF, BIASEDMF, CAMF_C, CAMF_CI, CAMF_CU, FM, CAMF_CUCI = range(7)
 EXACT, FAST = 0, 1
 SCHED_FLAGGED, SCHED_WAVEFRONT, SCHED_DATAFLOW = 0, 1, 2
+COMBINE_MEAN, COMBINE_SUM, COMBINE_TOUCHED = 0, 1, 2
 MODEL_NAMES = {"pmf": PMF, "biasedmf": BIASEDMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM,
                "camf_cuci": CAMF_CUCI}
 
@@ -37,8 +38,9 @@ class CarsDesc(C.Structure):
         ("global_mean", C.c_double),
         ("reg_u", C.c_double), ("reg_i", C.c_double), ("reg_b", C.c_double), ("reg_c", C.c_double),
         ("reg_lw", C.c_double), ("reg_lf", C.c_double),
-        ("num_context_dims", C.c_int32), ("reserved1", C.c_int32), ("global_nnz", C.c_int64),
-        ("stream", C.c_void_p),
+        ("num_context_dims", C.c_int32), ("num_gpus", C.c_int32), ("global_nnz", C.c_int64),
+        ("stream", C.c_void_p), ("gpu_ids", _i32p), ("fast_max_conc", C.c_double), ("tuning", C.c_char_p),
+        ("combine", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -53,6 +55,7 @@ class CarsStats(C.Structure):
         ("schedule_ms", C.c_double), ("last_epoch_ms", C.c_double),
         ("grid_ctas", C.c_int32), ("block_threads", C.c_int32), ("sm_count", C.c_int32), ("reserved", C.c_int32),
         ("schedule_copy_ms", C.c_double), ("schedule_levels_ms", C.c_double), ("schedule_pack_ms", C.c_double),
+        ("fast_min_item_scale", C.c_double), ("fast_min_cond_scale", C.c_double), ("max_item_degree", C.c_int64),
     ]
 
 
@@ -197,6 +200,10 @@ class TrainingSet:
     ctx_ptr: Optional[np.ndarray] = None
     ctx_cond: Optional[np.ndarray] = None
     global_mean: float = 0.0
+    # rateDao.getRatingScale() of the WHOLE data set -> (minRate, maxRate) (Recommender.java:196-200) and
+    # rateDao.numContextDims() (FM.java:86); None / 0 when the arrays did not come through the loader
+    rating_scale: Optional[tuple] = None
+    num_context_dims: int = 0
 
     def __post_init__(self):
         self.u = np.ascontiguousarray(self.u, dtype=np.int32)
@@ -215,9 +222,20 @@ class TrainingSet:
 def make_desc(ts: TrainingSet, model: int, num_factors: int, *, mode: int = EXACT, device: int = 0,
               reg_u: float = 0.0, reg_i: float = 0.0, reg_b: float = 0.0, reg_c: float = 0.0,
               reg_lw: float = 0.0, reg_lf: float = 0.0, num_context_dims: int = 0,
-              stream: int = 0, schedule: int = SCHED_FLAGGED, global_nnz: int = 0) -> CarsDesc:
-    """Fill a cars_desc.  The reg_* values must already be float-widened (use f32())."""
+              stream: int = 0, schedule: int = SCHED_FLAGGED, global_nnz: int = 0, fast_max_conc: float = 0.0,
+              tuning: Optional[str] = None, gpu_ids=None, combine: int = COMBINE_MEAN) -> CarsDesc:
+    """Fill a cars_desc.  The reg_* values must already be float-widened (use f32()).
+    `tuning`: developer knobs "key=value;..." (csrc/tuning.h); `gpu_ids`: N > 1 CUDA ordinals for ONE handle that
+    drives N GPUs from this process (users sharded by range, item block combined with NCCL inside cars_epoch)."""
     d = CarsDesc()
+    d.fast_max_conc = fast_max_conc
+    d.tuning = tuning.encode() if tuning else None
+    d.combine = combine
+    if gpu_ids is not None and len(gpu_ids) > 1:
+        ids = np.ascontiguousarray(gpu_ids, dtype=np.int32)
+        d._gpu_ids_keep = ids  # the descriptor must keep the array alive
+        d.gpu_ids = _ptr_i32(ids)
+        d.num_gpus = len(ids)
     d.abi_version = ABI_VERSION
     d.model, d.mode, d.device = model, mode, device
     d.schedule = schedule

@@ -7,8 +7,11 @@
 #include "schedule.cuh"
 #include "schedule_gpu.cuh"
 #include "sgd_kernels.cuh"
+#include "fast_kernels.cuh"
+#include "fast_schedule.cuh"
 #include "staged_copy.cuh"
 #include "rank_kernels.cuh"
+#include "tuning.h"
 
 #include <cuda_runtime.h>
 
@@ -29,8 +32,15 @@ using namespace cars;
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_create_error = "";
 
+struct LaunchPlan {
+  const void* fn = nullptr;
+  int lpr = 0, v = 0, threads = 0;
+};
+
 struct cars_handle {
   cars_desc d;  // scalars only; pointer members are nulled after create
+  LaunchPlan plan;  // the SGD kernel chosen at create (shape, shared memory and grid belong together)
+  cars::Tuning tune;
   std::string err;
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -53,6 +63,10 @@ struct cars_handle {
   bool serial = false;    // CAMF_C exact: reference order, one warp
   bool dataflow = false;  // default schedule: reference order + per-user / per-item completion counters
   bool flagged = false;   // level order + completion counters (no barriers)
+  bool fast = false;      // FAST mode: user-sorted chunks, item side by reductions (fast_kernels.cuh)
+  double* d_item_scale = nullptr;  // FAST: per-item step damping [num_items]
+  double* d_cond_scale = nullptr;  // FAST, CAMF_C: per-condition step damping [C]
+  bool damp_items = false, damp_conds = false;
   RatingRec* d_rec = nullptr;
   int64_t* d_chunk_start = nullptr;
   double* d_chunk_loss = nullptr;
@@ -104,121 +118,86 @@ static cudaError_t dev_alloc(T** p, size_t n) {
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch: model x (lanes per rating, chunks per lane) chosen from num_factors
 // ------------------------------------------------------------------------------------------------
-// Launch shape of the wavefront kernel: threads per CTA x co-resident CTAs per SM (register cap).
-// Variant 0 is the default; CARS_WF_VARIANT selects another one (tuning knob).
-struct LaunchPlan {
-  const void* fn = nullptr;
-  int lpr = 0, v = 0, threads = 0;
-};
-
-template <int MODEL, int THREADS, int MINB>
-static LaunchPlan pick_wavefront_shape(int Fp) {
-  LaunchPlan p;
-  p.threads = THREADS;
-  if (Fp <= 16) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 1, THREADS, MINB>; p.lpr = 8; p.v = 1;
-  } else if (Fp <= 32) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 2, THREADS, MINB>; p.lpr = 8; p.v = 2;
-  } else if (Fp <= 64) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 8, 4, THREADS, MINB>; p.lpr = 8; p.v = 4;
-  } else if (Fp <= 128) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 16, 4, THREADS, MINB>; p.lpr = 16; p.v = 4;
-  } else if (Fp <= 256) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 32, 4, THREADS, MINB>; p.lpr = 32; p.v = 4;
-  } else if (Fp <= 512) {
-    p.fn = (const void*)sgd_wavefront_kernel<MODEL, 32, 8, THREADS, MINB>; p.lpr = 32; p.v = 8;
-  }
+// One shape for the barrier (K1) and dataflow (K1d) kernels: 256 threads x 3 CTAs per SM, measured best on B200
+// (profiles/r1/bench_wavefront_v2_256x3.json).
+#define CARS_SHAPE_TABLE(KERNEL, MODEL, THREADS, MINB)                                                          \
+  LaunchPlan p;                                                                                                 \
+  p.threads = THREADS;                                                                                          \
+  if (Fp <= 16) { p.fn = (const void*)KERNEL<MODEL, 8, 1, THREADS, MINB>; p.lpr = 8; p.v = 1; }                 \
+  else if (Fp <= 32) { p.fn = (const void*)KERNEL<MODEL, 8, 2, THREADS, MINB>; p.lpr = 8; p.v = 2; }            \
+  else if (Fp <= 64) { p.fn = (const void*)KERNEL<MODEL, 8, 4, THREADS, MINB>; p.lpr = 8; p.v = 4; }            \
+  else if (Fp <= 128) { p.fn = (const void*)KERNEL<MODEL, 16, 4, THREADS, MINB>; p.lpr = 16; p.v = 4; }         \
+  else if (Fp <= 256) { p.fn = (const void*)KERNEL<MODEL, 32, 4, THREADS, MINB>; p.lpr = 32; p.v = 4; }         \
+  else if (Fp <= 512) { p.fn = (const void*)KERNEL<MODEL, 32, 8, THREADS, MINB>; p.lpr = 32; p.v = 8; }         \
   return p;
-}
 
 template <int MODEL>
-static LaunchPlan pick_wavefront(int Fp, int variant) {
-  switch (variant) {
-    case 1: return pick_wavefront_shape<MODEL, 512, 2>(Fp);
-    case 2: return pick_wavefront_shape<MODEL, 256, 3>(Fp);
-    default: return pick_wavefront_shape<MODEL, 512, 1>(Fp);
-  }
-}
+static LaunchPlan pick_wavefront(int Fp) { CARS_SHAPE_TABLE(sgd_wavefront_kernel, MODEL, 256, 3) }
+template <int MODEL>
+static LaunchPlan pick_dataflow(int Fp) { CARS_SHAPE_TABLE(sgd_dataflow_kernel, MODEL, 256, 3) }
 
-static int wavefront_variant(int dflt = 2) {  // 256 threads x 3 CTAs per SM measured best on B200 (profiles/)
-  const char* e = getenv("CARS_WF_VARIANT");
-  return e ? atoi(e) : dflt;
-}
-
-static LaunchPlan pick_plan(int model, int /*mode*/, int Fp) {
-  const int v = wavefront_variant();
+static LaunchPlan pick_plan(int model, int Fp) {
   switch (model) {
-    case CARS_PMF: return pick_wavefront<M_PMF>(Fp, v);
-    case CARS_BIASEDMF: return pick_wavefront<M_BIASEDMF>(Fp, v);
+    case CARS_PMF: return pick_wavefront<M_PMF>(Fp);
+    case CARS_BIASEDMF: return pick_wavefront<M_BIASEDMF>(Fp);
     case CARS_CAMF_C: return LaunchPlan{};  // every rating touches condBias: serial kernel only
-    case CARS_CAMF_CI: return pick_wavefront<M_CAMF_CI>(Fp, v);
-    case CARS_CAMF_CU: return pick_wavefront<M_CAMF_CU>(Fp, v);
-    case CARS_CAMF_CUCI: return pick_wavefront<M_CAMF_CUCI>(Fp, v);
+    case CARS_CAMF_CI: return pick_wavefront<M_CAMF_CI>(Fp);
+    case CARS_CAMF_CU: return pick_wavefront<M_CAMF_CU>(Fp);
+    case CARS_CAMF_CUCI: return pick_wavefront<M_CAMF_CUCI>(Fp);
   }
   return LaunchPlan{};
 }
 
-template <int MODEL, int THREADS, int MINB>
-static LaunchPlan pick_dataflow_shape(int Fp) {
-  LaunchPlan p;
-  p.threads = THREADS;
-  if (Fp <= 16) {
-    p.fn = (const void*)sgd_dataflow_kernel<MODEL, 8, 1, THREADS, MINB>; p.lpr = 8; p.v = 1;
-  } else if (Fp <= 32) {
-    p.fn = (const void*)sgd_dataflow_kernel<MODEL, 8, 2, THREADS, MINB>; p.lpr = 8; p.v = 2;
-  } else if (Fp <= 64) {
-    p.fn = (const void*)sgd_dataflow_kernel<MODEL, 8, 4, THREADS, MINB>; p.lpr = 8; p.v = 4;
-  } else if (Fp <= 128) {
-    p.fn = (const void*)sgd_dataflow_kernel<MODEL, 16, 4, THREADS, MINB>; p.lpr = 16; p.v = 4;
-  } else if (Fp <= 256) {
-    p.fn = (const void*)sgd_dataflow_kernel<MODEL, 32, 4, THREADS, MINB>; p.lpr = 32; p.v = 4;
-  } else if (Fp <= 512) {
-    p.fn = (const void*)sgd_dataflow_kernel<MODEL, 32, 8, THREADS, MINB>; p.lpr = 32; p.v = 8;
+static LaunchPlan pick_dataflow_plan(int model, int Fp) {
+  switch (model) {
+    case CARS_PMF: return pick_dataflow<M_PMF>(Fp);
+    case CARS_BIASEDMF: return pick_dataflow<M_BIASEDMF>(Fp);
+    case CARS_CAMF_CI: return pick_dataflow<M_CAMF_CI>(Fp);
+    case CARS_CAMF_CU: return pick_dataflow<M_CAMF_CU>(Fp);
+    case CARS_CAMF_CUCI: return pick_dataflow<M_CAMF_CUCI>(Fp);
   }
-  return p;
+  return LaunchPlan{};
+}
+
+// FAST (hogwild) kernel.  shape 0 (default): F = 64 -> 4 lanes per rating, 256-bit row accesses, F compiled in;
+// F = 128 -> 16 lanes; otherwise the generic table.  shape 1: 8 lanes per rating at F = 64 (fewer registers).
+template <int MODEL>
+static LaunchPlan pick_fast_generic(int Fp) { CARS_SHAPE_TABLE(sgd_fast_kernel, MODEL, 256, 2) }
+template <int MODEL>
+static LaunchPlan pick_fast(int Fp, int F, int shape) {
+  LaunchPlan p;
+  p.threads = 256;
+  if (F == 64 && shape == 0) { p.fn = (const void*)sgd_fast_kernel<MODEL, 4, 8, 256, 2, true, 64>; p.lpr = 4; p.v = 8; return p; }
+  if (F == 64 && shape == 1) { p.fn = (const void*)sgd_fast_kernel<MODEL, 8, 4, 256, 3, true, 64>; p.lpr = 8; p.v = 4; return p; }
+  if (F == 64 && shape == 2) { p.fn = (const void*)sgd_fast_kernel<MODEL, 8, 4, 256, 2, true, 64>; p.lpr = 8; p.v = 4; return p; }
+  if (F == 128 && shape <= 2) { p.fn = (const void*)sgd_fast_kernel<MODEL, 16, 4, 256, 2, true, 128>; p.lpr = 16; p.v = 4; return p; }
+  return pick_fast_generic<MODEL>(Fp);
+}
+static LaunchPlan pick_fast_plan(int model, int Fp, int F, int shape) {
+  switch (model) {
+    case CARS_PMF: return pick_fast<M_PMF>(Fp, F, shape);
+    case CARS_BIASEDMF: return pick_fast<M_BIASEDMF>(Fp, F, shape);
+    case CARS_CAMF_C: return pick_fast<M_CAMF_C>(Fp, F, shape);
+    case CARS_CAMF_CI: return pick_fast<M_CAMF_CI>(Fp, F, shape);
+    case CARS_CAMF_CU: return pick_fast<M_CAMF_CU>(Fp, F, shape);
+    case CARS_CAMF_CUCI: return pick_fast<M_CAMF_CUCI>(Fp, F, shape);
+  }
+  return LaunchPlan{};
 }
 
 template <int MODEL>
-static LaunchPlan pick_dataflow(int Fp, int variant) {
-  switch (variant) {
-    case 1: return pick_dataflow_shape<MODEL, 512, 2>(Fp);
-    case 2: return pick_dataflow_shape<MODEL, 256, 3>(Fp);
-    default: return pick_dataflow_shape<MODEL, 512, 1>(Fp);
-  }
-}
-
-template <int MODEL, int THREADS, int MINB>
-static LaunchPlan pick_flagged_shape(int Fp) {
-  LaunchPlan p;
-  p.threads = THREADS;
-  if (Fp <= 16) {
-    p.fn = (const void*)sgd_flagged_kernel<MODEL, 8, 1, THREADS, MINB>; p.lpr = 8; p.v = 1;
-  } else if (Fp <= 32) {
-    p.fn = (const void*)sgd_flagged_kernel<MODEL, 8, 2, THREADS, MINB>; p.lpr = 8; p.v = 2;
-  } else if (Fp <= 64) {
-    p.fn = (const void*)sgd_flagged_kernel<MODEL, 8, 4, THREADS, MINB>; p.lpr = 8; p.v = 4;
-  } else if (Fp <= 128) {
-    p.fn = (const void*)sgd_flagged_kernel<MODEL, 16, 4, THREADS, MINB>; p.lpr = 16; p.v = 4;
-  } else if (Fp <= 256) {
-    p.fn = (const void*)sgd_flagged_kernel<MODEL, 32, 4, THREADS, MINB>; p.lpr = 32; p.v = 4;
-  } else if (Fp <= 512) {
-    p.fn = (const void*)sgd_flagged_kernel<MODEL, 32, 8, THREADS, MINB>; p.lpr = 32; p.v = 8;
-  }
-  return p;
-}
+static LaunchPlan pick_flagged_generic(int Fp) { CARS_SHAPE_TABLE(sgd_flagged_kernel, MODEL, 256, 3) }
 
 template <int MODEL>
 static LaunchPlan pick_flagged(int Fp, int variant, int F = 0) {
   switch (variant) {
-    case 1: return pick_flagged_shape<MODEL, 512, 2>(Fp);
-    case 2: return pick_flagged_shape<MODEL, 256, 3>(Fp);
     case 3: {  // 4 lanes per rating (16 factors per lane): more ratings in flight per SM at F <= 64
       LaunchPlan p;
       if (Fp > 32 && Fp <= 64) {
         p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 4, 8, 256, 2>; p.lpr = 4; p.v = 8;
         return p;
       }
-      return pick_flagged_shape<MODEL, 256, 3>(Fp);
+      return pick_flagged_generic<MODEL>(Fp);
     }
     case 8: {  // as 7 with the factor count a compile-time constant (F = 64 / F = 128 exactly)
       LaunchPlan p;
@@ -244,46 +223,18 @@ static LaunchPlan pick_flagged(int Fp, int variant, int F = 0) {
       }
       return pick_flagged<MODEL>(Fp, 3);
     }
-    case 5: {  // 16 lanes per rating: two ratings per warp, short turns
-      LaunchPlan p;
-      if (Fp > 32 && Fp <= 64) {
-        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 16, 2, 256, 4>; p.lpr = 16; p.v = 2;
-        return p;
-      }
-      return pick_flagged_shape<MODEL, 256, 3>(Fp);
-    }
-    case 6: {  // one rating per warp
-      LaunchPlan p;
-      if (Fp > 32 && Fp <= 64) {
-        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 32, 1, 256, 6>; p.lpr = 32; p.v = 1;
-        return p;
-      }
-      return pick_flagged_shape<MODEL, 256, 3>(Fp);
-    }
-    default: return pick_flagged_shape<MODEL, 512, 1>(Fp);
+    default: return pick_flagged_generic<MODEL>(Fp);
   }
 }
 
-static LaunchPlan pick_flagged_plan(int model, int Fp, int F) {
-  const int v = wavefront_variant(8);  // 8: F = 64 / 128 compiled in + 256-bit row accesses; else 7 (256-bit where Fp % 4 == 0); else 3
+// v = 8 (default): F = 64 / 128 compiled in + 256-bit row accesses; else 7 (256-bit where Fp % 4 == 0); else 3
+static LaunchPlan pick_flagged_plan(int model, int Fp, int F, int v) {
   switch (model) {
     case CARS_PMF: return pick_flagged<M_PMF>(Fp, v, F);
     case CARS_BIASEDMF: return pick_flagged<M_BIASEDMF>(Fp, v, F);
     case CARS_CAMF_CI: return pick_flagged<M_CAMF_CI>(Fp, v, F);
     case CARS_CAMF_CU: return pick_flagged<M_CAMF_CU>(Fp, v, F);
     case CARS_CAMF_CUCI: return pick_flagged<M_CAMF_CUCI>(Fp, v, F);
-  }
-  return LaunchPlan{};
-}
-
-static LaunchPlan pick_dataflow_plan(int model, int Fp) {
-  const int v = wavefront_variant();
-  switch (model) {
-    case CARS_PMF: return pick_dataflow<M_PMF>(Fp, v);
-    case CARS_BIASEDMF: return pick_dataflow<M_BIASEDMF>(Fp, v);
-    case CARS_CAMF_CI: return pick_dataflow<M_CAMF_CI>(Fp, v);
-    case CARS_CAMF_CU: return pick_dataflow<M_CAMF_CU>(Fp, v);
-    case CARS_CAMF_CUCI: return pick_dataflow<M_CAMF_CUCI>(Fp, v);
   }
   return LaunchPlan{};
 }
@@ -323,8 +274,9 @@ static int validate(const cars_desc* d) {
   if (d->model == CARS_FM)
     return fail(nullptr, CARS_E_INVALID, "FM is an ALS model with its own entry points: use cars_fm_create");
   if (d->mode != CARS_EXACT && d->mode != CARS_FAST) return fail(nullptr, CARS_E_INVALID, "unknown mode %d", d->mode);
-  if (d->mode == CARS_FAST)
-    return fail(nullptr, CARS_E_UNSUPPORTED, "FAST (non serial-equivalent) mode is not built; use CARS_EXACT");
+  if (d->nnz > 0x7fffffffll)  // rating indices are 32-bit in the record stream, the chains and the frontiers
+    return fail(nullptr, CARS_E_UNSUPPORTED, "nnz %lld exceeds 2^31 - 1 ratings per handle; shard the users over more handles",
+                (long long)d->nnz);
   if (d->num_users <= 0 || d->num_items <= 0) return fail(nullptr, CARS_E_INVALID, "num_users/num_items must be > 0");
   if (d->num_factors <= 0 || d->num_factors > 512)
     return fail(nullptr, CARS_E_UNSUPPORTED, "num_factors %d outside 1..512", d->num_factors);
@@ -376,6 +328,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   } while (0)
 
   h->d = *desc;
+  h->tune = Tuning(desc->tuning);
   h->device = desc->device;
   h->sm_count = prop.multiProcessorCount;
   CUDA_TRY_H(cudaSetDevice(h->device));
@@ -387,7 +340,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   }
   CUDA_TRY_H(cudaEventCreate(&h->ev_beg));
   CUDA_TRY_H(cudaEventCreate(&h->ev_end));
-  CUDA_TRY_H(h->copier.init(h->device));
+  CUDA_TRY_H(h->copier.init(h->device, (int)h->tune.get_ll("copy_threads", 0)));
 
   const int F = desc->num_factors;
   const int Fp = (F + 1) & ~1;
@@ -428,11 +381,10 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
 
   // ---- range checks on the rating arrays -------------------------------------------------------------
   const int64_t nnz = desc->nnz;
-  int sched_req = desc->schedule;
-  if (const char* e = getenv("CARS_SCHEDULE"))
-    sched_req = strcmp(e, "wavefront") == 0 ? CARS_SCHED_WAVEFRONT : strcmp(e, "dataflow") == 0 ? CARS_SCHED_DATAFLOW : CARS_SCHED_FLAGGED;
-  // the flagged schedule validates the ids inside its own pass over the ratings
-  const bool fused_check = (sched_req == CARS_SCHED_FLAGGED && desc->model != CARS_CAMF_C);
+  const int sched_req = desc->schedule;
+  const bool fast = desc->mode == CARS_FAST;
+  // the flagged and the FAST schedule validate the ids inside their own device pass over the ratings
+  const bool fused_check = fast || (sched_req == CARS_SCHED_FLAGGED && desc->model != CARS_CAMF_C);
   for (int64_t n = 0; n < nnz && !fused_check; n++) {
     if ((unsigned)desc->u[n] >= (unsigned)desc->num_users || (unsigned)desc->j[n] >= (unsigned)desc->num_items ||
         (has_ctx && (unsigned)desc->ctx[n] >= (unsigned)desc->num_contexts)) {
@@ -444,26 +396,30 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
 
   // ---- launch geometry (the dataflow schedule sizes its chunks from the number of resident groups) ------
   const int model = desc->model;
-  h->serial = (model == CARS_CAMF_C);
+  h->fast = fast;
+  h->serial = !fast && (model == CARS_CAMF_C);
   const int sched = sched_req;
   if (sched != CARS_SCHED_DATAFLOW && sched != CARS_SCHED_WAVEFRONT && sched != CARS_SCHED_FLAGGED) {
     fail(h, CARS_E_INVALID, "unknown schedule %d", sched);
     return bail(CARS_E_INVALID);
   }
-  h->dataflow = !h->serial && sched == CARS_SCHED_DATAFLOW;
-  h->flagged = !h->serial && sched == CARS_SCHED_FLAGGED;
+  h->dataflow = !fast && !h->serial && sched == CARS_SCHED_DATAFLOW;
+  h->flagged = !fast && !h->serial && sched == CARS_SCHED_FLAGGED;
   int groups_per_cta = 1;
   if (h->serial) {
     h->grid = 1; h->block = 32;
     h->smem = (size_t)(Fp + 2) * 8;
   } else {
-    LaunchPlan plan = h->dataflow ? pick_dataflow_plan(model, Fp)
-                      : h->flagged ? pick_flagged_plan(model, Fp, F) : pick_plan(model, desc->mode, Fp);
+    const int shape = (int)h->tune.get_ll("shape", fast ? 0 : 8);
+    LaunchPlan plan = fast ? pick_fast_plan(model, Fp, F, shape)
+                      : h->dataflow ? pick_dataflow_plan(model, Fp)
+                      : h->flagged ? pick_flagged_plan(model, Fp, F, shape) : pick_plan(model, Fp);
+    h->plan = plan;
     if (!plan.fn) { fail(h, CARS_E_UNSUPPORTED, "no kernel for model %d mode %d F %d", model, desc->mode, F); return bail(CARS_E_UNSUPPORTED); }
     const int G = 32 / plan.lpr;
     groups_per_cta = (plan.threads / 32) * G;
     h->block = plan.threads;
-    h->smem = (size_t)groups_per_cta * (Fp + 2) * 8;
+    h->smem = fast ? 0 : (size_t)groups_per_cta * (Fp + 2) * 8;
     CUDA_TRY_H(cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     int per_sm = 0;
     CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, plan.threads, h->smem));
@@ -475,7 +431,54 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   auto t0 = std::chrono::steady_clock::now();
   h->nnz = nnz;
   const size_t U = desc->num_users, I = desc->num_items, C = desc->num_conditions;
-  if (h->dataflow) {
+  const bool sched_trace = h->tune.get_ll("sched_trace", 0) != 0;
+  if (fast) {
+    // K7h: user-sorted record stream, chunk table and damping factors, all on the device (fast_schedule.cuh)
+    const int64_t total_groups = (int64_t)h->grid * groups_per_cta;
+    int64_t chunk_len = h->tune.get_ll("fast_chunk", 0);
+    if (chunk_len <= 0) {
+      chunk_len = nnz / (8 * total_groups);
+      chunk_len = chunk_len < 32 ? 32 : (chunk_len > 512 ? 512 : chunk_len);
+    }
+    h->num_chunks = nnz ? (nnz + chunk_len - 1) / chunk_len : 0;
+    const double in_flight = (double)(h->num_chunks < total_groups ? h->num_chunks : total_groups);
+    const double max_conc = desc->fast_max_conc == 0.0 ? 8.0 : desc->fast_max_conc;
+    CUDA_TRY_H(dev_alloc(&h->d_rec, (size_t)nnz));
+    CUDA_TRY_H(dev_alloc(&h->d_chunk_start, (size_t)h->num_chunks + 1));
+    CUDA_TRY_H(dev_alloc(&h->d_item_scale, I));
+    if (model == CARS_CAMF_C) CUDA_TRY_H(dev_alloc(&h->d_cond_scale, C));
+    h->flags_words = 64;
+    CUDA_TRY_H(dev_alloc(&h->d_flags, h->flags_words));
+    CUDA_TRY_H(cudaStreamSynchronize(h->stream));  // the context table must have landed
+    FastBuild fb;
+    cudaError_t be = build_fast_on_device(desc->num_users, desc->num_items, desc->num_contexts, nnz, desc->u, desc->j,
+                                          has_ctx ? desc->ctx : nullptr, desc->r, h->stream, h->sm_count, h->copier, chunk_len,
+                                          in_flight, max_conc, h->d_ctx_tab, Dmax, desc->num_conditions, h->d_rec,
+                                          h->d_chunk_start, h->d_item_scale, h->d_cond_scale, &fb);
+    if (fb.bad_index >= 0) {
+      const int64_t n = fb.bad_index;
+      fail(h, CARS_E_INVALID, "rating %lld has an id out of range (u=%d j=%d ctx=%d)", (long long)n, desc->u[n], desc->j[n],
+           has_ctx ? desc->ctx[n] : -1);
+      return bail(CARS_E_INVALID);
+    }
+    if (be != cudaSuccess) {
+      fail(h, be == cudaErrorMemoryAllocation ? CARS_E_OOM : CARS_E_CUDA, "building the FAST schedule failed: %s", cudaGetErrorString(be));
+      return bail(be == cudaErrorMemoryAllocation ? CARS_E_OOM : CARS_E_CUDA);
+    }
+    h->damp_items = fb.min_item_scale < 1.0;
+    h->damp_conds = h->d_cond_scale && fb.min_cond_scale < 1.0;
+    h->num_levels = h->num_chunks;
+    h->max_level_size = fb.max_chunk;
+    h->st.h2d_bytes += fb.h2d_bytes;
+    h->st.kernel_launches += fb.kernel_launches;
+    h->st.schedule_copy_ms = fb.copy_ms;
+    h->st.schedule_levels_ms = fb.sort_ms;
+    h->st.schedule_pack_ms = fb.pack_ms;
+    h->st.fast_min_item_scale = fb.min_item_scale;
+    h->st.fast_min_cond_scale = fb.min_cond_scale;
+    h->st.max_item_degree = fb.max_item_degree;
+    h->st.schedule_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  } else if (h->dataflow) {
     // K7d: reference order is kept; every rating learns its position in its user's and its item's chain,
     // and the stream is cut into chunks (at user changes) that the kernel hands out in order.
     std::vector<RatingRec> recs;
@@ -531,13 +534,13 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     CUDA_TRY_H(dev_alloc(&h->d_rec, (size_t)nnz));
     h->flags_words = 64 + I + U;
     CUDA_TRY_H(dev_alloc(&h->d_flags, h->flags_words));
-    if (getenv("CARS_SCHED_TRACE"))
+    if (sched_trace)
       fprintf(stderr, "[cars schedule] %-28s %8.2f ms\n", "cudaMalloc(records, flags)",
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     FlaggedBuild fb;
     cudaError_t be = build_flagged_on_device(desc->num_users, desc->num_items, desc->num_contexts, nnz, desc->u, desc->j,
                                              has_ctx ? desc->ctx : nullptr, desc->r, h->stream, h->sm_count, h->copier,
-                                             h->d_rec, &fb);
+                                             h->d_rec, &fb, h->tune.is("levels", "host"), sched_trace);
     if (fb.bad_index >= 0) {
       const int64_t n = fb.bad_index;
       fail(h, CARS_E_INVALID, "rating %lld has an id out of range (u=%d j=%d ctx=%d)", (long long)n, desc->u[n], desc->j[n],
@@ -626,6 +629,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   h->st.sm_count = h->sm_count;
   // the handle must not keep caller pointers
   h->d.u = h->d.j = h->d.ctx = nullptr; h->d.r = nullptr; h->d.ctx_ptr = h->d.ctx_cond = nullptr; h->d.stream = nullptr;
+  h->d.gpu_ids = nullptr; h->d.tuning = nullptr;
   *out = h;
   return CARS_OK;
 #undef CUDA_TRY_H
@@ -722,8 +726,17 @@ extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
     void* args[] = {&m, &s, &nnz, &lrate, &h->d_partial};
     CUDA_TRY(h, cudaLaunchKernel(fn, dim3(1), dim3(32), args, h->smem, h->stream));
     h->st.kernel_launches += 1;
+  } else if (h->fast) {
+    FastStream fs;
+    fs.rec = h->d_rec; fs.chunk_start = h->d_chunk_start; fs.counter = h->d_flags; fs.num_chunks = (uint32_t)h->num_chunks;
+    fs.item_scale = h->damp_items ? h->d_item_scale : nullptr;
+    fs.cond_scale = h->damp_conds ? h->d_cond_scale : nullptr;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_flags, 0, h->flags_words * sizeof(unsigned), h->stream));
+    void* args[] = {&m, &fs, &lrate, &h->d_partial};
+    CUDA_TRY(h, cudaLaunchKernel(h->plan.fn, dim3(h->grid), dim3(h->block), args, h->smem, h->stream));
+    h->st.kernel_launches += 1;
   } else if (h->dataflow) {
-    LaunchPlan plan = pick_dataflow_plan(h->d.model, m.Fp);
+    const LaunchPlan& plan = h->plan;
     DataflowStream ds;
     ds.rec = h->d_rec; ds.chunk_start = h->d_chunk_start; ds.chunk_loss = h->d_chunk_loss;
     ds.counter = h->d_flags; ds.done_j = h->d_flags + 64; ds.done_u = h->d_flags + 64 + h->d.num_items;
@@ -740,7 +753,7 @@ extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
     h->st.kernel_launches += 1;
     partials = h->loss_blocks;
   } else if (h->flagged) {
-    LaunchPlan plan = pick_flagged_plan(h->d.model, m.Fp, m.F);
+    const LaunchPlan& plan = h->plan;
     CUDA_TRY(h, cudaMemsetAsync(h->d_flags, 0, h->flags_words * sizeof(unsigned), h->stream));
     const RatingRec* recs = h->d_rec;
     int64_t nnz = h->nnz;
@@ -772,7 +785,7 @@ extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
 #endif
     h->st.kernel_launches += 1;
   } else {
-    LaunchPlan plan = pick_plan(h->d.model, h->d.mode, m.Fp);
+    const LaunchPlan& plan = h->plan;
     CUDA_TRY(h, cudaMemsetAsync(h->d_barrier, 0, sizeof(unsigned), h->stream));
     void* args[] = {&m, &s, &lrate, &h->d_barrier, &h->d_partial};
     CUDA_TRY(h, cudaLaunchCooperativeKernel(plan.fn, dim3(h->grid), dim3(h->block), args, h->smem, h->stream));
@@ -807,19 +820,20 @@ struct ItemPart {
   double* ptr;
   int64_t n;
 };
-static int item_parts(const cars_handle* h, ItemPart out[3]) {
+static int item_parts(const cars_handle* h, ItemPart out[4]) {
   const DeviceModel& m = h->m;
   const int64_t I = h->d.num_items;
   int k = 0;
   out[k++] = {m.Q, I * m.Fp};
   if (m.item_bias) out[k++] = {m.item_bias, I};
   if (m.ic_bias) out[k++] = {m.ic_bias, I * (int64_t)m.C};
+  if (m.cond_bias) out[k++] = {m.cond_bias, (int64_t)m.C};  // CAMF_C (FAST only): shared by every shard
   return k;
 }
 
 extern "C" int cars_item_block_doubles(const cars_handle* h, int64_t* out) {
   if (!h || !out) return CARS_E_INVALID;
-  ItemPart parts[3];
+  ItemPart parts[4];
   const int k = item_parts(h, parts);
   int64_t n = 0;
   for (int i = 0; i < k; i++) n += parts[i].n;
@@ -830,12 +844,12 @@ extern "C" int cars_item_block_doubles(const cars_handle* h, int64_t* out) {
 extern "C" int cars_epoch_sharded_begin(cars_handle* h, double lrate, double* dev_delta) {
   if (!h) return CARS_E_INVALID;
   if (!dev_delta) return fail(h, CARS_E_INVALID, "dev_delta is NULL");
-  if (h->d.model == CARS_CAMF_C)
-    return fail(h, CARS_E_UNSUPPORTED, "CAMF_C shares condBias between all ratings; it is not sharded");
+  if (h->d.model == CARS_CAMF_C && !h->fast)
+    return fail(h, CARS_E_UNSUPPORTED, "CAMF_C in EXACT mode is one chain through condBias; shard it in FAST mode");
   if (h->sharded_pending) return fail(h, CARS_E_STATE, "previous sharded epoch not finished");
   if (!h->uploaded) return fail(h, CARS_E_STATE, "cars_epoch before cars_upload");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  ItemPart parts[3];
+  ItemPart parts[4];
   const int k = item_parts(h, parts);
   int64_t total = 0;
   for (int i = 0; i < k; i++) total += parts[i].n;
@@ -864,7 +878,7 @@ extern "C" int cars_epoch_sharded_finish(cars_handle* h, const double* dev_delta
   if (!h->sharded_pending) return fail(h, CARS_E_STATE, "no sharded epoch pending");
   if (!dev_delta) return fail(h, CARS_E_INVALID, "dev_delta is NULL");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  ItemPart parts[3];
+  ItemPart parts[4];
   const int k = item_parts(h, parts);
   int64_t off = 0;
   const int blocks = h->sm_count * 8;
@@ -1109,7 +1123,7 @@ extern "C" void cars_destroy(cars_handle* h) {
   cudaFree(h->m.P); cudaFree(h->m.Q); cudaFree(h->m.user_bias); cudaFree(h->m.item_bias);
   cudaFree(h->m.cond_bias); cudaFree(h->m.ic_bias); cudaFree(h->m.uc_bias);
   cudaFree(h->d_rec); cudaFree(h->d_chunk_start); cudaFree(h->d_chunk_loss); cudaFree(h->d_flags);
-  cudaFree(h->d_item_old);
+  cudaFree(h->d_item_old); cudaFree(h->d_item_scale); cudaFree(h->d_cond_scale);
   cudaFree(h->d_barrier); cudaFree(h->d_partial); cudaFree(h->d_loss);
   if (h->h_loss) cudaFreeHost(h->h_loss);
   h->copier.destroy();
@@ -1129,4 +1143,4 @@ extern "C" int cars_get_stats(const cars_handle* h, cars_stats* out) {
 
 extern "C" void* cars_get_stream(const cars_handle* h) { return h ? (void*)h->stream : nullptr; }
 
-extern "C" const char* cars_version(void) { return "carskit_b200 abi 2, sm_100a, fp64 serial-equivalent SGD"; }
+extern "C" const char* cars_version(void) { return "carskit_b200 abi 3, sm_100a, fp64 SGD (EXACT serial-equivalent / FAST hogwild), FM ALS, top-N"; }

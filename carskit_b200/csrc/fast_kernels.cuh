@@ -1,0 +1,345 @@
+// fast_kernels.cuh -- K2: the FAST (hogwild) schedule of the CARSKit SGD hot path on sm_100a.
+//
+// Same per-rating arithmetic as sgd_kernels.cuh (CAMF_CI.java:80-121 and siblings), NOT the same order of
+// execution: EXACT mode keeps, for every user and every item, that row's ratings in reference order, so its
+// parallelism is nnz / max item degree -- on skewed data (every real data set under context-aware_data_sets/)
+// the dependency DAG is a few ratings wide and a GPU has nothing to do.  FAST drops the item-side ordering:
+//
+//   * the ratings are stably sorted by user (fast_schedule.cuh) and cut into chunks at user boundaries; a group
+//     of LPR lanes takes chunks from a global counter and walks each one in order, so ONE group runs all the
+//     ratings of a user: P[u], userBias[u] stay in registers across the user's run and ucBias[u][.] is read and
+//     written by one thread per cell -- the user side has no race at all;
+//   * every item-side cell (Q[j], itemBias[j], icBias[j][.], condBias[.]) is read with a plain L2 load -- the
+//     operands of rating n + 1 are requested before the arithmetic of rating n starts (software pipeline in
+//     registers; nothing to poll, so the load is always useful) -- and updated with red.global.add.f64: the
+//     step  lr * (e * p - reg * q)  computed from the possibly stale read is ADDED to whatever the cell holds;
+//   * a cell that many in-flight ratings share would receive the sum of many stale gradients (an effective
+//     learning rate of lr * concurrency: diverges for a Zipf-head item or for CAMF_C's condBias).  Such rows get
+//     their step scaled by  min(1, max_conc / expected concurrency)  (item_scale / cond_scale, computed from the
+//     row's degree at create time; nullptr when no row needs it).
+//
+// With no two in-flight ratings sharing an item the result equals the serial loop up to the order of the dot
+// product (a tree here, sequential in Java) -- tests/test_fast_gpu.py checks exactly that.
+#pragma once
+#include "sgd_kernels.cuh"
+
+namespace cars {
+
+struct FastStream {
+  const RatingRec* rec;        // [nnz] stably sorted by user
+  const int64_t* chunk_start;  // [num_chunks + 1], every boundary is a user boundary
+  unsigned* counter;           // next chunk to hand out (zeroed per epoch)
+  uint32_t num_chunks;
+  const double* item_scale;    // [num_items] step damping of the item-side cells, or nullptr (all 1)
+  const double* cond_scale;    // [C] CAMF_C: step damping of condBias, or nullptr
+};
+
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// Item-side operands of one rating, requested one rating ahead.
+template <int V>
+struct FastOps {
+  double2 q[V];
+  double bj;       // itemBias[j]
+  double cb;       // this lane's item-side condition cell: icBias[j][cond] (CI, CUCI) or condBias[cond] (C)
+  double* cb_ptr;  // nullptr when the lane owns none
+  double scale;    // item_scale[j]
+  double cscale;   // cond_scale[cond] (CAMF_C)
+  int cond;        // this lane's condition id, -1 = none
+};
+
+template <int MODEL, int LPR, int V, bool WIDE, int FIXF>
+__device__ __forceinline__ void fast_load(const DeviceModel& m, const FastStream& s, const RatingRec& rec, int gl,
+                                          FastOps<V>& o) {
+  constexpr bool kItemBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CU);
+  constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU || MODEL == M_CAMF_CUCI);
+  const int Fp = FIXF > 0 ? FIXF : m.Fp;
+  const double* qrow = m.Q + (int64_t)rec.j * Fp;
+  if (WIDE) {
+#pragma unroll
+    for (int w = 0; w < V / 2; w++) {
+      const int c = chunk_of<LPR, true>(gl, 2 * w);
+      if (2 * c < Fp) ld_cg_f64x4(qrow + 2 * c, o.q[2 * w], o.q[2 * w + 1]);
+      else o.q[2 * w] = o.q[2 * w + 1] = make_double2(0.0, 0.0);
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const int c = gl + v * LPR;
+      if (2 * c < Fp) o.q[v] = ld_cg_f64x2(qrow + 2 * c);
+      else o.q[v] = make_double2(0.0, 0.0);
+    }
+  }
+  o.bj = 0.0;
+  if (kItemBias) o.bj = ld_cg_f64(m.item_bias + rec.j);
+  o.scale = 1.0;
+  if (s.item_scale) o.scale = __ldg(s.item_scale + rec.j);
+  o.cb = 0.0;
+  o.cb_ptr = nullptr;
+  o.cscale = 1.0;
+  o.cond = -1;
+  if (kHasCond && gl < m.Dmax) {
+    const int cond = __ldg(m.ctx_tab + (int64_t)rec.ctx * m.Dmax + gl);
+    o.cond = cond;
+    if (cond >= 0) {
+      if (MODEL == M_CAMF_C) {
+        o.cb_ptr = m.cond_bias + cond;
+        if (s.cond_scale) o.cscale = __ldg(s.cond_scale + cond);
+      }
+      if (MODEL == M_CAMF_CI || MODEL == M_CAMF_CUCI) o.cb_ptr = m.ic_bias + (int64_t)rec.j * m.C + cond;
+      if (o.cb_ptr) o.cb = ld_cg_f64(o.cb_ptr);
+    }
+  }
+}
+
+// One rating: arithmetic + user-side stores + item-side reductions.  Returns this lane's loss contribution.
+template <int MODEL, int LPR, int V, bool WIDE, int FIXF>
+__device__ __forceinline__ double fast_update(const DeviceModel& m, const FastStream& s, const RatingRec& rec, double lr,
+                                              int gl, unsigned gmask, UserRegs<V>& us, const FastOps<V>& o) {
+  constexpr bool kUserBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CI);
+  constexpr bool kItemBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CU);
+  constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU || MODEL == M_CAMF_CUCI);
+  constexpr bool kUserCond = (MODEL == M_CAMF_CU || MODEL == M_CAMF_CUCI);  // ucBias[u][cond]: owned by this group
+  const int Fp = FIXF > 0 ? FIXF : m.Fp;
+  const int Dmax = m.Dmax;
+  const int u = rec.u, j = rec.j;
+
+  // the user-side condition cell is read NOW (after the previous rating of this user stored it; same thread)
+  double ucb = 0.0;
+  double* ucb_ptr = nullptr;
+  if (kUserCond && o.cond >= 0) {
+    ucb_ptr = m.uc_bias + (int64_t)u * m.C + o.cond;
+    ucb = ld_cg_f64(ucb_ptr);
+  }
+
+  // ---- dot product: per-lane partial, then a butterfly over the group's lanes ---------------------------------
+  double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+  for (int v = 0; v < V; v++) {
+    d0 = fma(us.p[v].x, o.q[v].x, d0);  // padded slots hold zeros
+    d1 = fma(us.p[v].y, o.q[v].y, d1);
+  }
+  double dot = d0 + d1;
+#pragma unroll
+  for (int w = LPR / 2; w > 0; w >>= 1) {
+    const int lo = __shfl_xor_sync(gmask, __double2loint(dot), w, LPR);
+    const int hi = __shfl_xor_sync(gmask, __double2hiint(dot), w, LPR);
+    dot += __hiloint2double(hi, lo);
+  }
+
+  // ---- predict (the model's own order of additions) ------------------------------------------------------------
+  const double bu = kUserBias ? us.bu : 0.0;
+  const double bj = o.bj;
+  double pred;
+  if (MODEL == M_PMF) pred = dot;
+  if (MODEL == M_BIASEDMF || MODEL == M_CAMF_C) pred = __dadd_rn(__dadd_rn(__dadd_rn(m.global_mean, bu), bj), dot);
+  if (MODEL == M_CAMF_CI) pred = __dadd_rn(__dadd_rn(m.global_mean, bu), dot);
+  if (MODEL == M_CAMF_CU) pred = __dadd_rn(__dadd_rn(m.global_mean, bj), dot);
+  if (MODEL == M_CAMF_CUCI) pred = __dadd_rn(m.global_mean, dot);
+  double lane_loss = 0.0;
+  if (kHasCond) {
+    const int D1 = Dmax < LPR ? Dmax : LPR;
+    const double cbs = MODEL == M_CAMF_CU ? ucb : MODEL == M_CAMF_CUCI ? __dadd_rn(o.cb, ucb) : o.cb;
+    for (int d = 0; d < D1; d++) pred = __dadd_rn(pred, shfl_f64(gmask, cbs, d, LPR));
+    for (int d = LPR; d < Dmax; d++) {  // more context dimensions than lanes in a group: every lane reads them
+      const int cond = __ldg(m.ctx_tab + (int64_t)rec.ctx * Dmax + d);
+      if (cond < 0) continue;
+      double b = 0.0;
+      if (MODEL == M_CAMF_C) b = ld_cg_f64(m.cond_bias + cond);
+      if (MODEL == M_CAMF_CI || MODEL == M_CAMF_CUCI) b = ld_cg_f64(m.ic_bias + (int64_t)j * m.C + cond);
+      if (MODEL == M_CAMF_CU) b = ld_cg_f64(m.uc_bias + (int64_t)u * m.C + cond);
+      if (MODEL == M_CAMF_CUCI) b = __dadd_rn(b, ld_cg_f64(m.uc_bias + (int64_t)u * m.C + cond));
+      pred = __dadd_rn(pred, b);
+    }
+  }
+  const double e = __dsub_rn(rec.r, pred);
+  const double lrj = __dmul_rn(lr, o.scale);  // item-side step (damped for rows many in-flight ratings share)
+
+  // ---- bias steps ----------------------------------------------------------------------------------------------
+  if (kUserBias) us.bu = __dadd_rn(bu, __dmul_rn(lr, __dsub_rn(e, __dmul_rn(m.reg_b, bu))));
+  if (gl == 0) {
+    lane_loss = __dmul_rn(e, e);
+    if (kUserBias) lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_b, bu), bu));
+    if (kItemBias) {
+      red_add_f64(m.item_bias + j, __dmul_rn(lrj, __dsub_rn(e, __dmul_rn(m.reg_b, bj))));
+      lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_b, bj), bj));
+    }
+  }
+  if (kHasCond) {
+    if (o.cb_ptr != nullptr) {  // item-side cell (or condBias): reduction
+      const double lrc = MODEL == M_CAMF_C ? __dmul_rn(lr, o.cscale) : lrj;
+      red_add_f64(o.cb_ptr, __dmul_rn(lrc, __dsub_rn(e, __dmul_rn(m.reg_c, o.cb))));
+      if (MODEL == M_CAMF_C) lane_loss = __dadd_rn(lane_loss, __dmul_rn(m.reg_b, o.cb));  // CAMF_C.java:115
+      else lane_loss = __dadd_rn(lane_loss, __dmul_rn(m.reg_c, __dmul_rn(o.cb, o.cb)));
+    }
+    if (kUserCond && ucb_ptr != nullptr) {  // user-side cell: this thread is its only writer
+      st_cg_f64(ucb_ptr, __dadd_rn(ucb, __dmul_rn(lr, __dsub_rn(e, __dmul_rn(m.reg_c, ucb)))));
+      lane_loss = __dadd_rn(lane_loss, __dmul_rn(m.reg_c, __dmul_rn(ucb, ucb)));
+    }
+    if (gl == 0) {
+      for (int d = LPR; d < Dmax; d++) {
+        const int cond = __ldg(m.ctx_tab + (int64_t)rec.ctx * Dmax + d);
+        if (cond < 0) continue;
+        if (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CUCI) {
+          double* bp = MODEL == M_CAMF_C ? m.cond_bias + cond : m.ic_bias + (int64_t)j * m.C + cond;
+          const double b = ld_cg_f64(bp);
+          const double lrc = (MODEL == M_CAMF_C) ? __dmul_rn(lr, s.cond_scale ? __ldg(s.cond_scale + cond) : 1.0) : lrj;
+          red_add_f64(bp, __dmul_rn(lrc, __dsub_rn(e, __dmul_rn(m.reg_c, b))));
+          lane_loss = __dadd_rn(lane_loss, MODEL == M_CAMF_C ? __dmul_rn(m.reg_b, b) : __dmul_rn(m.reg_c, __dmul_rn(b, b)));
+        }
+        if (kUserCond) {
+          double* bp = m.uc_bias + (int64_t)u * m.C + cond;
+          const double b = ld_cg_f64(bp);
+          st_cg_f64(bp, __dadd_rn(b, __dmul_rn(lr, __dsub_rn(e, __dmul_rn(m.reg_c, b)))));
+          lane_loss = __dadd_rn(lane_loss, __dmul_rn(m.reg_c, __dmul_rn(b, b)));
+        }
+      }
+    }
+    // lane 0 wrote user-side cells that every lane of the group reads for the user's next rating
+    if (kUserCond && Dmax > LPR) __syncwarp(gmask);
+  }
+
+  // ---- factor steps (both from the values read) -----------------------------------------------------------------
+  double* qrow = m.Q + (int64_t)j * Fp;
+  double sp = 0.0, sq = 0.0;
+#pragma unroll
+  for (int v = 0; v < V; v++) {
+    const int c = chunk_of<LPR, WIDE>(gl, v);
+    if (2 * c < Fp) {
+      const double2 po = us.p[v], qo = o.q[v];
+      us.p[v].x = __dadd_rn(po.x, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, qo.x), __dmul_rn(m.reg_u, po.x))));
+      us.p[v].y = __dadd_rn(po.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, qo.y), __dmul_rn(m.reg_u, po.y))));
+      red_add_f64(qrow + 2 * c, __dmul_rn(lrj, __dsub_rn(__dmul_rn(e, po.x), __dmul_rn(m.reg_i, qo.x))));
+      red_add_f64(qrow + 2 * c + 1, __dmul_rn(lrj, __dsub_rn(__dmul_rn(e, po.y), __dmul_rn(m.reg_i, qo.y))));
+      sp = fma(po.x, po.x, sp);
+      sq = fma(qo.x, qo.x, sq);
+      sp = fma(po.y, po.y, sp);
+      sq = fma(qo.y, qo.y, sq);
+    }
+  }
+  return __dadd_rn(lane_loss, fma(m.reg_u, sp, __dmul_rn(m.reg_i, sq)));
+}
+
+// The user's row: read when a user's run starts, written back when it ends (plain L2 accesses: no other group
+// touches P[u] / userBias[u] during the epoch).
+template <int MODEL, int LPR, int V, bool WIDE, int FIXF>
+__device__ __forceinline__ void fast_load_user(const DeviceModel& m, int u, int gl, UserRegs<V>& us) {
+  constexpr bool kUserBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CI);
+  const int Fp = FIXF > 0 ? FIXF : m.Fp;
+  const double* prow = m.P + (int64_t)u * Fp;
+  if (WIDE) {
+#pragma unroll
+    for (int w = 0; w < V / 2; w++) {
+      const int c = chunk_of<LPR, true>(gl, 2 * w);
+      if (2 * c < Fp) ld_cg_f64x4(prow + 2 * c, us.p[2 * w], us.p[2 * w + 1]);
+      else us.p[2 * w] = us.p[2 * w + 1] = make_double2(0.0, 0.0);
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const int c = gl + v * LPR;
+      if (2 * c < Fp) us.p[v] = ld_cg_f64x2(prow + 2 * c);
+      else us.p[v] = make_double2(0.0, 0.0);
+    }
+  }
+  us.bu = 0.0;
+  if (kUserBias) us.bu = ld_cg_f64(m.user_bias + u);
+}
+
+template <int MODEL, int LPR, int V, bool WIDE, int FIXF>
+__device__ __forceinline__ void fast_store_user(const DeviceModel& m, int u, int gl, const UserRegs<V>& us) {
+  constexpr bool kUserBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CI);
+  const int Fp = FIXF > 0 ? FIXF : m.Fp;
+  double* prow = m.P + (int64_t)u * Fp;
+  if (WIDE) {
+#pragma unroll
+    for (int w = 0; w < V / 2; w++) {
+      const int c = chunk_of<LPR, true>(gl, 2 * w);
+      if (2 * c < Fp) st_cg_f64x4(prow + 2 * c, us.p[2 * w], us.p[2 * w + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const int c = gl + v * LPR;
+      if (2 * c < Fp) st_cg_f64x2(prow + 2 * c, us.p[v]);
+    }
+  }
+  if (kUserBias && gl == 0) st_cg_f64(m.user_bias + u, us.bu);
+}
+
+// K2: persistent grid (any size: chunks are only held by running groups, so no co-residency is needed).
+template <int MODEL, int LPR, int V, int THREADS, int MINB, bool WIDE = false, int FIXF = 0>
+__global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, FastStream s, double lr, double* block_partial) {
+  constexpr int WARPS = THREADS / 32;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int gl = lane % LPR;
+  const int gw = lane / LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (gw * LPR));
+
+  int64_t n = 0, end = 0;
+  bool done = false;
+  int prev_u = -1;
+  double acc = 0.0;
+  UserRegs<V> us;
+#pragma unroll
+  for (int v = 0; v < V; v++) us.p[v] = make_double2(0.0, 0.0);
+  us.bu = 0.0;
+  RatingRec rec, recn;
+  rec.u = rec.j = rec.ctx = rec.ku = rec.kj = rec.pad = 0; rec.r = 0.0;
+  recn = rec;
+  FastOps<V> cur, nxt;
+
+  for (;;) {
+    if (!done && n == end) {  // take the next non-empty chunk
+      for (;;) {
+        unsigned c = 0;
+        if (gl == 0) c = atomicAdd(s.counter, 1u);
+        c = __shfl_sync(gmask, c, 0, LPR);
+        if (c >= s.num_chunks) {
+          done = true;
+          break;
+        }
+        n = __ldg(s.chunk_start + c);
+        end = __ldg(s.chunk_start + c + 1);
+        if (n < end) break;
+      }
+      if (!done) {
+        rec = ld_rec(s.rec + n);
+        fast_load<MODEL, LPR, V, WIDE, FIXF>(m, s, rec, gl, cur);
+        prev_u = -1;
+      }
+    }
+    if (__all_sync(0xffffffffu, done)) break;
+    if (!done) {
+      const bool has_next = n + 1 < end;
+      if (has_next) {  // the next rating's item-side operands fly during this rating's arithmetic
+        recn = ld_rec(s.rec + n + 1);
+        fast_load<MODEL, LPR, V, WIDE, FIXF>(m, s, recn, gl, nxt);
+      }
+      if (rec.u != prev_u) fast_load_user<MODEL, LPR, V, WIDE, FIXF>(m, rec.u, gl, us);
+      acc = __dadd_rn(acc, fast_update<MODEL, LPR, V, WIDE, FIXF>(m, s, rec, lr, gl, gmask, us, cur));
+      if (!has_next || recn.u != rec.u) fast_store_user<MODEL, LPR, V, WIDE, FIXF>(m, rec.u, gl, us);
+      prev_u = rec.u;
+      if (has_next) {
+        rec = recn;
+        cur = nxt;
+      }
+      n++;
+    }
+  }
+
+  acc = warp_sum_f64(acc);
+  __shared__ double warp_sum[WARPS];
+  if (lane == 0) warp_sum[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < WARPS; w++) t += warp_sum[w];
+    block_partial[blockIdx.x] = t;
+  }
+}
+
+}  // namespace cars

@@ -4,6 +4,7 @@
 #include "fm_kernels.cuh"
 #include "fm_setup.cuh"
 #include "staged_copy.cuh"
+#include "tuning.h"
 
 #include <cuda_runtime.h>
 
@@ -30,6 +31,7 @@ struct FieldStore {
 
 struct cars_fm_handle {
   std::string err;
+  cars::Tuning tune;  // developer knobs from cars_desc.tuning (no environment variable is read)
   int device = 0, sm_count = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -155,7 +157,7 @@ static int build_field(cars_fm_handle* h, int which, int32_t* coord, bool owns_c
   fs.f.dense_blocks = dense ? h->sm_count * 3 : 0;
   fs.wide = dense || (ncoord > 0 && fs.f.num_pieces / ncoord >= 8);
   fs.short_pieces = num_pieces > 0 && total / num_pieces < 64;
-  if (const char* e = getenv("CARS_FM_LANES_PER_PIECE")) fs.short_pieces = atoi(e) == 8;
+  if (const char* e = h->tune.get("fm_lanes_per_piece")) fs.short_pieces = atoi(e) == 8;
   if (fs.f.num_pieces > h->max_pieces) h->max_pieces = fs.f.num_pieces;
   return CARS_OK;
 }
@@ -182,6 +184,7 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
   cars_fm_handle* h = new (std::nothrow) cars_fm_handle();
   if (!h) return fm_fail(nullptr, CARS_E_OOM, "host allocation failed");
   auto bail = [&](int code) { g_fm_create_error = h->err; cars_fm_destroy(h); return code; };
+  h->tune = cars::Tuning(d->tuning);
   h->device = d->device; h->sm_count = prop.multiProcessorCount;
   h->U = d->num_users; h->I = d->num_items; h->C = d->num_conditions; h->p = h->U + h->I + h->C;
   h->k = d->num_factors; h->D = d->num_context_dims; h->N = d->nnz;
@@ -209,9 +212,9 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
   h->Nq = (N + 1) & ~(int64_t)1;
   FM_TRY_H(fm_alloc(&h->d_Qc, (size_t)h->Nq * h->k));
   FM_TRY_H(fm_alloc(&h->d_w0, 1)); FM_TRY_H(fm_alloc(&h->d_w, (size_t)h->p)); FM_TRY_H(fm_alloc(&h->d_V, (size_t)h->p * h->k));
-  FM_TRY_H(h->copier.init(h->device));
-  if (const char* e = getenv("CARS_FM_PPG_SHORT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) h->ppg_short = v; }
-  if (const char* e = getenv("CARS_FM_PPG_LONG")) { const int v = atoi(e); if (v == 1 || v == 2) h->ppg_long = v; }
+  FM_TRY_H(h->copier.init(h->device, (int)h->tune.get_ll("copy_threads", 0)));
+  if (const char* e = h->tune.get("fm_ppg_short")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) h->ppg_short = v; }
+  if (const char* e = h->tune.get("fm_ppg_long")) { const int v = atoi(e); if (v == 1 || v == 2) h->ppg_long = v; }
   {
     // Internal row order.  The rows (errors[n], Q[n][f]) are private to the engine, and every sum of the sweep
     // runs over the rows of ONE coordinate, so the rows may be stored in any order.  They are sorted by item
@@ -220,11 +223,11 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
     // short contiguous runs in which neighbouring users are neighbours -- instead of 8-byte reads scattered over
     // all N rows, one DRAM sector each (profiles/r1: 0.31 of the HBM roofline before).
     int64_t block_rows = 1536 * 1024;
-    if (const char* e = getenv("CARS_FM_BLOCK_ROWS")) block_rows = atoll(e);
+    block_rows = h->tune.get_ll("fm_block_rows", block_rows);
     // few contexts: that field is reduced by streaming the rows (fm_dense_reduce_kernel), so the context does not
     // enter the row order and a user's rows stay contiguous inside every item block
     int64_t dense_min_rows = 65536;
-    if (const char* e = getenv("CARS_FM_DENSE_MIN_ROWS")) dense_min_rows = atoll(e);
+    dense_min_rows = h->tune.get_ll("fm_dense_min_rows", dense_min_rows);
     const bool ctx_dense = h->C > 0 && h->C <= kDenseMaxCoord && N >= dense_min_rows;
     const int blocks = h->sm_count * 8;
     const size_t Na = (size_t)(N ? N : 1);

@@ -12,8 +12,8 @@
 //      one grid barrier per level, ~4 us each (3 268 levels at config 3)
 //   4. CUB stable radix sort of (level, n), gather_recs_kernel packs the 32-byte RatingRec stream.
 // The stable sort makes the stream independent of the order in which Kahn's frontiers were filled.
-// The previous host pass (one thread, 8 ns per rating: 0.82 s at 100 M ratings) is kept behind
-// CARS_LEVELS=host for A/B measurements (build_flagged_host_levels).
+// The previous host pass (one thread, 8 ns per rating: 0.82 s at 100 M ratings) is kept behind the handle's
+// tuning string ("levels=host") for A/B measurements and as a cross-check in the tests (build_flagged_host_levels).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(256) pack_recs_kernel(RatingSoA s, int64_t n, 
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
     RatingRec x;
-    x.u = s.u[k]; x.j = s.j[k]; x.ctx = s.ctx ? s.ctx[k] : 0; x.ku = s.ku[k];
-    x.kj = s.kj[k]; x.pad = 0; x.r = s.r[k];
+    x.u = s.u[k]; x.j = s.j[k]; x.ctx = s.ctx ? s.ctx[k] : 0; x.ku = s.ku ? s.ku[k] : 0;
+    x.kj = s.kj ? s.kj[k] : 0; x.pad = 0; x.r = s.r[k];
     out[k] = x;
   }
 }
@@ -250,9 +250,9 @@ inline bool build_flagged_host_levels(int32_t num_users, int32_t num_items, int6
 inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items, int32_t num_contexts, int64_t nnz,
                                            const int32_t* u, const int32_t* j, const int32_t* ctx, const double* r,
                                            cudaStream_t stream, int sm_count, StagedCopier& copier, RatingRec* d_rec,
-                                           FlaggedBuild* info) {
+                                           FlaggedBuild* info, bool host_levels = false, bool trace = false) {
   if (nnz == 0) return cudaSuccess;
-  const bool trace = getenv("CARS_SCHED_TRACE") != nullptr;  // host wall time of every phase, to stderr
+  // trace: host wall time of every phase, to stderr (tuning "sched_trace=1")
   auto t_last = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
     if (!trace) return;
@@ -294,10 +294,6 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
     while ((1ll << b) < n_values) b++;
     return b;
   };
-  const bool host_levels = [] {
-    const char* s = getenv("CARS_LEVELS");
-    return s && strcmp(s, "host") == 0;
-  }();
   size_t temp_bytes = 0;  // CUB scratch: the 32-bit-key sort bounds the three sorts below
   SG_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
                                          (uint32_t*)nullptr, nnz, 0, 32, stream));

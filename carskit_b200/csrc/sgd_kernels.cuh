@@ -145,6 +145,24 @@ __device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// Consumer side of the completion counters.  The producer publishes with the release pattern (fence.acq_rel.gpu, then
+// relaxed stores).  The PTX-formal acquire pattern on this side is one ld.acquire.gpu of the counter once the relaxed
+// poll has succeeded; it lowers to LDG.STRONG.GPU + CCTL.IVALL (an L1 invalidation per rating).  The default build
+// omits it: every model access of these kernels is ld/st.global.cg -- served by L2, the point of coherence, never by
+// L1 -- and is issued after the branch on the polled value resolves, i.e. after the counter load has returned from
+// L2, where the producer's row stores were performed before its fence completed.  -DCARS_STRICT_ACQUIRE builds the
+// formal variant (scripts/build_strict.sh; measured cost in DESIGN.md "Memory ordering").
+__device__ __forceinline__ void acquire_after_poll(const unsigned* p, bool mine) {
+#ifdef CARS_STRICT_ACQUIRE
+  if (mine) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  }
+#else
+  (void)p;
+  (void)mine;
+#endif
+}
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -375,6 +393,8 @@ __device__ __forceinline__ double compute_scatter(const DeviceModel& m, int u, i
         lane_loss = __dadd_rn(lane_loss, __dmul_rn(m.reg_c, __dmul_rn(cb2, cb2)));
       }
     }
+    // dims beyond the group's lanes: every lane READ those cells for `pred` above; lane 0 rewrites them below
+    if (Dmax > LPR) __syncwarp(gmask);
     if (gl == 0) {
       for (int d = LPR; d < Dmax; d++) {
         const int cond = __ldg(m.ctx_tab + (int64_t)ctx * Dmax + d);
@@ -600,14 +620,16 @@ __global__ void __launch_bounds__(THREADS, MINB)
       if (gl == 1 && first) ok = (ld_relaxed_u32(s.done_u + rec.u) == (unsigned)rec.ku);
       const unsigned b = __ballot_sync(gmask, ok);
       if ((b & gmask) == gmask) {
-        __syncwarp(gmask);  // the leaders' acquire loads happen-before every lane's loads below
+        acquire_after_poll(gl == 0 ? s.done_j + rec.j : s.done_u + rec.u, gl == 0 || (gl == 1 && first));
+        __syncwarp(gmask);  // the leaders' polls happen-before every lane's loads below
         bool last = (n + 1 == end);
         if (!last) last = (__ldg(&s.rec[n + 1].u) != rec.u);
         acc = __dadd_rn(acc, rating_update<MODEL, LPR, V>(m, rec.u, rec.j, rec.ctx, rec.r, lr, prod, gl, gmask,
                                                           us, first, last));
-        __syncwarp(gmask);  // the group's stores happen-before lane 0's release
-        if (gl == 0) {
-          st_release_u32(s.done_j + rec.j, (unsigned)rec.kj + 1u);
+        __syncwarp(gmask);  // the group's stores happen-before lane 0's fence
+        if (gl == 0) {      // release pattern for BOTH counters: one fence, then two relaxed (strong) stores
+          fence_acq_rel_gpu();
+          st_relaxed_u32(s.done_j + rec.j, (unsigned)rec.kj + 1u);
           if (last) st_relaxed_u32(s.done_u + rec.u, (unsigned)rec.ku + 1u);
         }
         prev_u = rec.u;
@@ -627,11 +649,11 @@ __global__ void __launch_bounds__(THREADS, MINB)
 // (cooperative launch).  A group that is not ready skips its turn (no blocking wait on another group
 // inside a warp).  Levels overlap: the tail of level L runs beside the head of level L+1.
 //
-// Memory ordering: the producer stores its rows (st.global.cg), __syncwarp, then lane 0 publishes the
-// two counters with st.release.gpu (MEMBAR.ALL.GPU, cumulative over the group's stores).  The consumer
-// polls with ld.relaxed.gpu and, after a control dependency and __syncwarp, reads the rows with
-// ld.global.cg: every data access is served by L2, the point of coherence, so no L1 invalidation
-// (CCTL.IVALL, which ld.acquire.gpu would add on every poll) is needed.
+// Memory ordering: the producer stores its rows (st.global.cg), __syncwarp, then lane 0 issues ONE
+// fence.acq_rel.gpu (MEMBAR.ALL.GPU, cumulative over the group's stores) followed by the two relaxed counter
+// stores -- the release pattern for both counters.  The consumer polls with ld.relaxed.gpu and, after the branch
+// on the polled values and __syncwarp, reads the rows with ld.global.cg; see acquire_after_poll() for why the
+// default build does not add the L1-invalidating acquire, and for the strict build that does.
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int LPR, int V, int THREADS, int MINB, bool WIDE = false, int FIXF = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -683,6 +705,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
       if (gl == 1) ok = (ld_relaxed_u32(done_u + rec.u) == (unsigned)rec.ku);
       const unsigned b = __ballot_sync(gmask, ok);
       if ((b & gmask) == gmask) {
+        acquire_after_poll(gl == 0 ? done_j + rec.j : done_u + rec.u, gl < 2);
         __syncwarp(gmask);
         const int64_t nn = n + T;
         if (nn < nnz) next = ld_rec(recs + nn);  // flies during this rating's gather and arithmetic
@@ -705,8 +728,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
 #ifdef CARS_TRACE
         const long long tc3 = clock64();
 #endif
-        if (gl == 0) {
-          st_release_u32(done_j + rec.j, (unsigned)rec.kj + 1u);
+        if (gl == 0) {  // release pattern for BOTH counters: one fence (MEMBAR.ALL.GPU), then two relaxed stores
+          fence_acq_rel_gpu();
+          st_relaxed_u32(done_j + rec.j, (unsigned)rec.kj + 1u);
           st_relaxed_u32(done_u + rec.u, (unsigned)rec.ku + 1u);
         }
 #ifdef CARS_TRACE

@@ -32,14 +32,12 @@ class StagedCopier {
 
   ~StagedCopier() { destroy(); }
 
-  cudaError_t init(int device) {
+  // threads = 0: chosen from the host's core count
+  cudaError_t init(int device, int threads = 0) {
     device_ = device;
     unsigned hc = std::thread::hardware_concurrency();
     workers_ = hc >= 16 ? 6 : hc >= 8 ? 4 : hc >= 4 ? 2 : 1;
-    if (const char* e = getenv("CARS_COPY_THREADS")) {
-      int v = atoi(e);
-      if (v >= 1 && v <= kMaxWorkers) workers_ = v;
-    }
+    if (threads >= 1 && threads <= kMaxWorkers) workers_ = threads;
     return cudaSuccess;
   }
 

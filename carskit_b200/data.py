@@ -101,7 +101,9 @@ def read_binary_csv(path: str) -> Tuple[TrainingSet, RatingDao]:
         total += v
     ts = TrainingSet(num_users=dao.numUsers(), num_items=dao.numItems(), u=uu, j=jj, r=r, ctx=c,
                      num_conditions=dao.numConditions(), num_contexts=dao.numContexts(), ctx_ptr=ctx_ptr,
-                     ctx_cond=np.asarray(flat, dtype=np.int32), global_mean=total / len(r) if len(r) else 0.0)
+                     ctx_cond=np.asarray(flat, dtype=np.int32), global_mean=total / len(r) if len(r) else 0.0,
+                     rating_scale=(dao.ratingScale[0], dao.ratingScale[-1]) if dao.ratingScale else None,
+                     num_context_dims=dao.numContextDims())
     ts.pair_ids = ui  # the CRS row (user-item pair id) of every entry, for callers that need it
     return ts, dao
 
@@ -179,7 +181,8 @@ class DataSplitter:
         train = TrainingSet(num_users=ts.num_users, num_items=ts.num_items, u=ts.u[keep], j=ts.j[keep], r=r,
                             ctx=ts.ctx[keep] if has_ctx else None, num_conditions=ts.num_conditions,
                             num_contexts=ts.num_contexts, ctx_ptr=ts.ctx_ptr, ctx_cond=ts.ctx_cond,
-                            global_mean=total / len(r) if len(r) else 0.0)
+                            global_mean=total / len(r) if len(r) else 0.0, rating_scale=ts.rating_scale,
+                            num_context_dims=ts.num_context_dims)
         test = {"u": ts.u[test_mask].copy(), "j": ts.j[test_mask].copy(),
                 "ctx": ts.ctx[test_mask].copy() if has_ctx else None, "r": ts.r[test_mask].copy()}
         if getattr(ts, "pair_ids", None) is not None:  # the CRS rows (user-item pair ids) travel with the entries
@@ -426,5 +429,6 @@ def to_traditional(ts: TrainingSet) -> TrainingSet:
     keys = sorted(cells)
     out = TrainingSet(num_users=ts.num_users, num_items=ts.num_items, u=np.array([k[0] for k in keys], dtype=np.int32),
                       j=np.array([k[1] for k in keys], dtype=np.int32), r=np.array([cells[k] for k in keys], dtype=np.float64),
-                      ctx=None, global_mean=ts.global_mean)
+                      ctx=None, global_mean=ts.global_mean, rating_scale=ts.rating_scale,
+                      num_context_dims=ts.num_context_dims)
     return out

@@ -117,7 +117,7 @@ class IterativeRecommender:
 
     def __init__(self, trainMatrix: TrainingSet, testMatrix: Optional[dict] = None, fold: int = -1,
                  conf: Optional[Dict[str, str]] = None, device: int = 0, stream: int = 0, world: int = 1,
-                 group=None, combine: str = "mean"):
+                 group=None, combine: str = "mean", mode: str = "exact", tuning: Optional[str] = None):
         """`world` > 1: this process is one rank of a user-range-sharded job (sharding.py); trainMatrix /
         testMatrix are THIS rank's shard and torch.distributed is initialised.  The engine then runs on
         torch's current CUDA stream so the all-reduce is ordered with the kernels."""
@@ -127,6 +127,13 @@ class IterativeRecommender:
         self.trainMatrix, self.testMatrix, self.fold = trainMatrix, testMatrix, fold
         self.device, self.stream = device, stream
         self.world, self.group, self.exchange, self.combine = world, group, None, combine
+        # engine.mode: "exact" (serial-equivalent, the default) or "fast" (hogwild, include/carskit_b200.h cars_mode);
+        # no reference counterpart -- a B200 subclass would read it from the algorithm's option line
+        self.mode = cf.get("engine.mode", mode).lower()
+        if self.mode not in ("exact", "fast"):
+            raise ValueError(f"engine.mode must be exact or fast, not {self.mode}")
+        self.fastMaxConc = float(cf.get("engine.fast.max.conc", 0.0))
+        self.tuning = tuning
         self._torch_stream = None
         self.numUsers, self.numItems = trainMatrix.num_users, trainMatrix.num_items
         self.numConditions = trainMatrix.num_conditions
@@ -147,8 +154,16 @@ class IterativeRecommender:
         self.numIters = int(cf["num.max.iter"])  # :102
         ev = LineConfiger(cf["evaluation.setup"])
         self.earlyStopMeasure = ev.getString("--early-stop")  # Recommender.java:221-229
-        self.minRate = float(cf.get("rating.min", 1.0))  # rateDao.getRatingScale(), Recommender.java:196-198
-        self.maxRate = float(cf.get("rating.max", 5.0))
+        # minRate / maxRate = first / last of rateDao.getRatingScale() (Recommender.java:196-200): they come with the
+        # data (TrainingSet.rating_scale, filled by data.read_binary_csv).  Arrays that did not come through the
+        # loader fall back to the scale of the training ratings themselves; rating.min / rating.max override both.
+        scale = getattr(trainMatrix, "rating_scale", None)
+        if scale is None and trainMatrix.nnz:
+            scale = (float(trainMatrix.r.min()), float(trainMatrix.r.max()))
+        if scale is None:
+            scale = (1.0, 5.0)
+        self.minRate = float(cf.get("rating.min", scale[0]))
+        self.maxRate = float(cf.get("rating.max", scale[1]))
         self.initMean, self.initStd = 0.0, 0.1  # Recommender.java:203-204
 
         self.lRate = float(self.initLRate)  # :106
@@ -223,7 +238,8 @@ class IterativeRecommender:
     def _desc(self):
         return capi.make_desc(self.trainMatrix, self.MODEL, self.numFactors, device=self.device,
                               reg_u=self.regU, reg_i=self.regI, reg_b=self.regB, reg_c=self.regC,
-                              stream=self.stream)
+                              stream=self.stream, mode=capi.FAST if self.mode == "fast" else capi.EXACT,
+                              fast_max_conc=self.fastMaxConc, tuning=self.tuning)
 
     def open_engine(self) -> capi.Engine:
         """cars_create + cars_upload: what buildModel() does before its first iteration."""
@@ -455,7 +471,8 @@ class FM(IterativeRecommender):
         self.regLw, self.regLf = opts.getFloat("-lw", 0.0), opts.getFloat("-lf", 0.0)
         # rateDao.numContextDims(): one condition per dimension in every context (DataDAO.java:281-290)
         ts = trainMatrix
-        self.numContextDims = int(self.cf.get("num.context.dims", 0)) or (
+        # (TrainingSet.num_context_dims when the data came through the loader; the length of the first context otherwise)
+        self.numContextDims = int(self.cf.get("num.context.dims", 0)) or int(getattr(ts, "num_context_dims", 0)) or (
             int(ts.ctx_ptr[1] - ts.ctx_ptr[0]) if ts.ctx_ptr is not None and len(ts.ctx_ptr) > 1 else 1)
         self.p = self.numUsers + self.numItems + self.numConditions
         self.k = self.numFactors

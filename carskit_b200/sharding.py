@@ -42,7 +42,8 @@ def shard_training_set(ts: TrainingSet, rank: int, world: int) -> Tuple[Training
     shard = TrainingSet(num_users=hi - lo, num_items=ts.num_items, u=ts.u[keep] - lo, j=ts.j[keep], r=ts.r[keep],
                         ctx=None if ts.ctx is None else ts.ctx[keep], num_conditions=ts.num_conditions,
                         num_contexts=ts.num_contexts, ctx_ptr=ts.ctx_ptr, ctx_cond=ts.ctx_cond,
-                        global_mean=ts.global_mean)  # globalMean is a property of the WHOLE training matrix
+                        global_mean=ts.global_mean,  # globalMean is a property of the WHOLE training matrix
+                        rating_scale=ts.rating_scale, num_context_dims=ts.num_context_dims)
     return shard, lo
 
 
@@ -68,7 +69,7 @@ def shard_rows(ts: TrainingSet, rank: int, world: int) -> TrainingSet:
     return TrainingSet(num_users=ts.num_users, num_items=ts.num_items, u=ts.u[lo:hi], j=ts.j[lo:hi], r=ts.r[lo:hi],
                        ctx=None if ts.ctx is None else ts.ctx[lo:hi], num_conditions=ts.num_conditions,
                        num_contexts=ts.num_contexts, ctx_ptr=ts.ctx_ptr, ctx_cond=ts.ctx_cond,
-                       global_mean=ts.global_mean)
+                       global_mean=ts.global_mean, rating_scale=ts.rating_scale, num_context_dims=ts.num_context_dims)
 
 
 class CoordinateSumExchange:

@@ -33,9 +33,12 @@ def context_table(dims: Sequence[int]) -> Tuple[np.ndarray, np.ndarray, int, int
 
 def make_training_set(num_users: int, num_items: int, dims: Optional[Sequence[int]], nnz: int, seed: int,
                       order: str = "user_sorted", item_zipf: float = 0.0, rating_levels: int = 5,
-                      holdout: float = 0.0):
+                      holdout: float = 0.0, planted_rank: int = 0, planted_noise: float = 0.5):
     """Unique (u, j, ctx) triples with u uniform, j uniform (or Zipf(item_zipf)), ctx uniform, ratings
-    uniform in {1..rating_levels}.
+    uniform in {1..rating_levels} -- or, with planted_rank > 0, ratings that CAN be learnt:
+    round(clip(mid + b_u + b_j + <p_u, q_j> + b_cond(ctx) + N(0, planted_noise))) from a hidden model of that rank,
+    so that a held-out RMSE says something about the trained model (used by the convergence comparisons of the
+    non serial-equivalent modes: FAST and multi-GPU).
 
     order = "user_sorted": pair ids follow (u, j) order, i.e. a ratings file sorted by user then item.
     order = "shuffled":    pair ids in random first-appearance order (an unsorted ratings file).
@@ -91,7 +94,21 @@ def make_training_set(num_users: int, num_items: int, dims: Optional[Sequence[in
     else:
         key, idx = np.unique(key, return_index=True)  # CRS order; duplicates: keep one
         u, j, c = u[idx].astype(np.int32), j[idx].astype(np.int32), c[idx].astype(np.int32)
-    r = rng.integers(1, rating_levels + 1, size=u.shape[0]).astype(np.float64)
+    if planted_rank > 0:
+        k = int(planted_rank)
+        prng = np.random.default_rng(seed + 104729)
+        hp = prng.standard_normal((num_users, k)) * (0.8 / np.sqrt(k))
+        hq = prng.standard_normal((num_items, k)) * (1.0)
+        hbu, hbj = 0.4 * prng.standard_normal(num_users), 0.4 * prng.standard_normal(num_items)
+        hbc = 0.3 * prng.standard_normal(max(num_cond, 1))
+        val = (rating_levels + 1) / 2.0 + hbu[u] + hbj[j] + np.einsum("nk,nk->n", hp[u], hq[j])
+        if dims is not None:
+            D = int(ctx_ptr[1] - ctx_ptr[0])
+            val += hbc[ctx_cond.reshape(-1, D)[c]].sum(axis=1)
+        val += planted_noise * prng.standard_normal(u.shape[0])
+        r = np.clip(np.rint(val), 1, rating_levels).astype(np.float64)
+    else:
+        r = rng.integers(1, rating_levels + 1, size=u.shape[0]).astype(np.float64)
 
     test = None
     if holdout > 0:

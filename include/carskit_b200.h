@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define CARS_ABI_VERSION 2 /* 2: cars_stats grew (schedule_*_ms), CARS_CAMF_CUCI added */
+#define CARS_ABI_VERSION 3 /* 3: FAST mode built; num_gpus / gpu_ids / combine (single-process multi-GPU);
+                              fast_max_conc; tuning string (replaces every environment knob) */
 
 /* Recommender classes on the hot path. */
 enum cars_model {
@@ -50,9 +51,15 @@ enum cars_model {
  *        sequential fp64 sum in Java) differs, by summation order (~1e-13 relative).
  *        CAMF_C in EXACT mode runs on one warp (every rating touches the shared condBias vector,
  *        CAMF_C.java:107-113), so it is meant for small data.
- * FAST:  reserved for a non serial-equivalent schedule; cars_create() returns CARS_E_UNSUPPORTED
- *        (hogwild updates of the shared condBias vector of CAMF_C were measured to diverge, see
- *        DESIGN.md). */
+ * FAST:  hogwild (kernel K2).  NOT serial-equivalent.  The ratings are re-ordered by
+ *        user; a user's ratings run in order on one group of lanes with P[u] / userBias[u] / ucBias[u][.]
+ *        held privately (no race on the user side), while every item-side cell (Q[j], itemBias[j],
+ *        icBias[j][.], condBias[.]) is read without synchronisation and updated with red.global.add.f64.
+ *        Throughput does not depend on the skew of the data (EXACT's parallelism is nnz / max item degree).
+ *        Rows that many in-flight ratings share (a Zipf-head item, every condBias cell of CAMF_C) would see
+ *        the SUM of many stale gradients, i.e. an effective learning rate multiplied by the concurrency;
+ *        their step is therefore damped to fast_max_conc expected concurrent updates (DESIGN.md "FAST").
+ *        The result differs from the Java loop; tests and bench report the RMSE difference. */
 enum cars_mode { CARS_EXACT = 0, CARS_FAST = 1 };
 
 /* How EXACT mode orders independent ratings (all three are serial-equivalent and bit-identical):
@@ -108,10 +115,27 @@ typedef struct cars_desc {
   double global_mean;      /* Recommender.globalMean (Recommender.java:265) */
   double reg_u, reg_i, reg_b, reg_c, reg_lw, reg_lf;
   int32_t num_context_dims; /* rateDao.numContextDims() (FM.java:86); FM only */
-  int32_t reserved1;
+  int32_t num_gpus;         /* 0 or 1: one GPU (`device`).  N > 1: ONE handle drives N GPUs from this process --
+                               users are sharded by contiguous range over gpu_ids, the item block is combined with
+                               ncclAllReduce inside cars_epoch; `device` and `stream` are ignored */
   int64_t global_nnz;       /* FM row sharding: rows over all ranks; 0 = nnz (single GPU) */
-  void*   stream;          /* cudaStream_t to launch on; NULL = the handle creates its own */
+  void*   stream;           /* cudaStream_t to launch on; NULL = the handle creates its own */
+  const int32_t* gpu_ids;   /* [num_gpus] CUDA ordinals; NULL = 0 .. num_gpus-1 */
+  double  fast_max_conc;    /* FAST: cap on the expected number of concurrent updates of one shared row before
+                               its step is damped; 0 = default (8); < 0 = never damp */
+  const char* tuning;       /* developer knobs "key=value;key=value" (tests / profiling); NULL in normal use.
+                               The library reads NO environment variable. */
+  int32_t combine;          /* num_gpus > 1: enum cars_combine */
+  int32_t reserved1;
 } cars_desc;
+
+/* How the item block is combined between user-range shards once per epoch (DESIGN.md "Multi-GPU"):
+ *   block <- old + scale_j * sum_over_shards(new_shard - old)
+ * MEAN  scale = 1/shards for every row (averages the shards' rows; stable for any shard size)
+ * SUM   scale = 1 (adds the shards' steps; only safe while an epoch moves a row a little)
+ * TOUCHED  scale_j = 1 / (number of shards that have at least one rating of item j): a row only one shard trained
+ *          keeps that shard's full step (sparse item sets), a row every shard trained is averaged */
+enum cars_combine { CARS_COMBINE_MEAN = 0, CARS_COMBINE_SUM = 1, CARS_COMBINE_TOUCHED = 2 };
 
 typedef struct cars_handle cars_handle;
 
@@ -226,6 +250,11 @@ typedef struct cars_stats {
   double  schedule_copy_ms;
   double  schedule_levels_ms;
   double  schedule_pack_ms;
+  /* FAST mode: the smallest step-damping factor of any item row / condBias cell (1 = nothing damped) and the largest
+     item degree (EXACT's parallelism is nnz / max_item_degree) */
+  double  fast_min_item_scale;
+  double  fast_min_cond_scale;
+  int64_t max_item_degree;
 } cars_stats;
 int cars_get_stats(const cars_handle* h, cars_stats* out);
 void* cars_get_stream(const cars_handle* h); /* cudaStream_t the kernels are launched on */

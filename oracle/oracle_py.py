@@ -30,6 +30,7 @@ class EpochState(C.Structure):
 
 def build(force: bool = False) -> str:
     srcs = [os.path.join(_HERE, f) for f in ("cars_oracle.cpp", "fm_oracle.cpp")]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "carskit_b200.h"))  # cars_desc is shared with the product
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return LIB_PATH

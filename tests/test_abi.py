@@ -119,3 +119,15 @@ def test_plain_c_client_links_and_reports_no_device(cars_lib, tmp_path):
                            f"-Wl,-rpath,{libdir}", "-o", exe])
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode == 3 and "cars_create: -2" in p.stdout and "no CPU path" in p.stdout
+
+
+def test_product_sources_read_no_environment_variable():
+    # every developer knob travels in cars_desc.tuning (csrc/tuning.h); only the -DCARS_TRACE developer build may getenv
+    bad = []
+    csrc = os.path.join(ROOT, "carskit_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        txt = open(os.path.join(csrc, f)).read()
+        txt = re.sub(r"#ifdef CARS_TRACE.*?#(else|endif)", "", txt, flags=re.S)
+        if re.search(r"\bgetenv\s*\(", txt):
+            bad.append(f)
+    assert not bad, bad

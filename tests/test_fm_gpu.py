@@ -15,8 +15,9 @@ pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-9, 1e-12
 
 
-def run_gpu(ts, arrs, k, D, iters):
-    desc = capi.make_desc(ts, capi.FM, k, reg_lw=float(np.float32(0.01)), reg_lf=float(np.float32(0.02)), num_context_dims=D)
+def run_gpu(ts, arrs, k, D, iters, tuning=None):
+    desc = capi.make_desc(ts, capi.FM, k, reg_lw=float(np.float32(0.01)), reg_lf=float(np.float32(0.02)), num_context_dims=D,
+                          tuning=tuning)
     got = clone(arrs)
     losses = []
     with capi.FmEngine(desc, keepalive=ts) as eng:
@@ -32,15 +33,14 @@ def run_gpu(ts, arrs, k, D, iters):
 @pytest.mark.parametrize("users,items,dims,nnz,k", [(12, 9, [2, 3], 150, 3), (300, 120, [4, 8], 20000, 16),
                                                     (2000, 50, [32], 60000, 8), (50, 2000, [3, 3, 3], 30000, 64)])
 @pytest.mark.parametrize("block_rows", [None, "700"])
-def test_fm_matches_sparse_oracle(oracle, cars_lib, monkeypatch, users, items, dims, nnz, k, block_rows):
+def test_fm_matches_sparse_oracle(oracle, cars_lib, users, items, dims, nnz, k, block_rows):
     # block_rows: the engine's internal row order (item block, context, caller's order) with tiny blocks, so the
     # permuted layout the big inputs use is exercised at oracle sizes; results do not depend on it beyond rounding
-    if block_rows is not None:
-        monkeypatch.setenv("CARS_FM_BLOCK_ROWS", block_rows)
-        monkeypatch.setenv("CARS_FM_DENSE_MIN_ROWS", "0")  # and the streaming reduce of the context field
+    # (fm_dense_min_rows=0: and the streaming reduce of the context field); knobs travel in cars_desc.tuning
+    tuning = None if block_rows is None else f"fm_block_rows={block_rows};fm_dense_min_rows=0"
     ts, _, prob, arrs = fm_inputs(oracle, users, items, dims, nnz, k, seed=7)
     iters = 3
-    got, losses, st = run_gpu(ts, arrs, k, len(dims), iters)
+    got, losses, st = run_gpu(ts, arrs, k, len(dims), iters, tuning)
     ref = clone(arrs)
     e, Q = oracle.fm_prepare(prob, ref)
     ref_losses = [oracle.fm_iteration(prob, ref, e, Q, closed_den=True) for _ in range(iters)]

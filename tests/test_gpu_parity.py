@@ -129,19 +129,24 @@ def test_camf_c_ragged_contexts(oracle, cars_lib):
     np.testing.assert_allclose(gl, rl, rtol=LOSS_RTOL, atol=0)
 
 
-def test_fast_mode_is_refused_not_faked(oracle, cars_lib):
-    ts, _ = synth.make_training_set(90, 120, [7, 7], 3000, seed=21)
-    with pytest.raises(capi.CarsError) as e:
-        capi.Engine(capi.make_desc(ts, capi.CAMF_C, 10, mode=capi.FAST, **REGS), keepalive=ts)
-    assert e.value.code == -5
-
-
 def test_many_context_dimensions(oracle, cars_lib):
     # more context dimensions (10) than lanes in a group (8): exercises the slow path
     ts, _ = synth.make_training_set(200, 50, [2] * 10, 5000, seed=4)
-    for model in (capi.CAMF_CI, capi.CAMF_CU):
+    for model in (capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI):
         ref, got, rl, gl, _ = run_both(oracle, model, ts, 10, epochs=2, seed=8)
         assert_bit_identical(ref, got)
+
+
+@pytest.mark.parametrize("model", [capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI])
+@pytest.mark.parametrize("F,ndims", [(64, 5), (64, 7), (128, 6), (40, 9)])
+def test_more_context_dimensions_than_lanes_per_rating(oracle, cars_lib, model, F, ndims):
+    # the default flagged plan gives a rating 4 lanes at F in 33..64 (16 at 65..128): any data set with more context
+    # dimensions than that takes the per-dimension slow path of compute_scatter on a MULTI-group kernel
+    ts = synth.make_training_set(300, 80, ([2, 3] * 5)[:ndims], 12000, seed=ndims)[0]
+    for schedule in (capi.SCHED_FLAGGED, capi.SCHED_DATAFLOW):
+        ref, got, rl, gl, _ = run_both(oracle, model, ts, F, epochs=3, seed=8, schedule=schedule)
+        assert_bit_identical(ref, got)
+        np.testing.assert_allclose(gl, rl, rtol=LOSS_RTOL, atol=0)
 
 
 def test_edge_cases(oracle, cars_lib):
@@ -284,14 +289,13 @@ def host_levels(ts):
 
 @pytest.mark.parametrize("order,users,items,nnz,zipf", [("user_sorted", 500, 120, 20000, 0.0), ("shuffled", 3000, 2000, 100000, 1.0),
                                                          ("shuffled", 1, 300, 300, 0.0), ("user_sorted", 4000, 3, 9000, 0.0)])
-def test_device_built_levels_match_the_sequential_pass(oracle, cars_lib, monkeypatch, order, users, items, nnz, zipf):
+def test_device_built_levels_match_the_sequential_pass(oracle, cars_lib, order, users, items, nnz, zipf):
     ts, _ = synth.make_training_set(users, items, [4, 3], nnz, seed=11, order=order, item_zipf=zipf)
     want = host_levels(ts)
-    desc = capi.make_desc(ts, capi.CAMF_CI, 8, **REGS)
     arrs = init_arrays(oracle, capi.CAMF_CI, ts, 8, 1)
     out = {}
     for how in ("device", "host"):
-        monkeypatch.setenv("CARS_LEVELS", how)
+        desc = capi.make_desc(ts, capi.CAMF_CI, 8, tuning=f"levels={how}", **REGS)
         got = {k: v.copy() for k, v in arrs.items()}
         with capi.Engine(desc, keepalive=ts) as eng:
             st = eng.stats()
@@ -347,3 +351,20 @@ def test_large_pageable_and_pinned_transfers(oracle, cars_lib):
             eng.download(got)
         assert_bit_identical(ref, got)
         np.testing.assert_allclose(loss, want_loss, rtol=LOSS_RTOL, atol=0)
+
+
+def test_config2_frappe_shaped_camf_c_bit_identical(oracle, cars_lib):
+    # BASELINE.json configs[1] at full size (scripts/config2.py times the same input): CAMF_C, 10 factors, 957 users x
+    # 4 082 items, 8 context dimensions with 7/7/2/3/2/9/80/233 conditions, 96 203 drawn ratings, 90/10 split.
+    # EXACT mode (one warp, reference order) must reproduce the oracle bit for bit, predictions and RMSE included.
+    ts, test = synth.make_training_set(957, 4082, [7, 7, 2, 3, 2, 9, 80, 233], 96203, seed=1, holdout=0.1)
+    ref, got, rl, gl, st = run_both(oracle, capi.CAMF_C, ts, 10, epochs=5, seed=1)
+    assert_bit_identical(ref, got)
+    np.testing.assert_allclose(gl, rl, rtol=LOSS_RTOL, atol=0)
+    desc = capi.make_desc(ts, capi.CAMF_C, 10, **REGS)
+    with capi.Engine(desc, keepalive=ts) as eng:
+        eng.upload(got)
+        sa, ss = eng.eval_ratings(test["u"], test["j"], test["ctx"], test["r"], 1.0, 5.0)
+    ra, rs, cnt = oracle.eval_ratings(desc, ref, test["u"], test["j"], test["ctx"], test["r"], 1.0, 5.0)
+    assert (sa, ss) == (ra, rs) and cnt == len(test["r"])
+    assert ts.num_conditions == 343 and st.nnz == ts.nnz
