@@ -289,8 +289,10 @@ def parity_check(wl, ts, model, arrs, local_rank, mode, epochs=2):
     if mode == "exact":
         out["digest_equal"] = model_digest(got) == model_digest(ref)
         out["arrays_bit_identical"] = {k: bool(np.array_equal(got[k], ref[k])) for k in ref}
-        out["bar"] = "P, Q, biases bit-identical (sha256 over the arrays); loss within 1e-11 relative"
-        out["ok"] = bool(out["digest_equal"] and out["loss_rel"] < 1e-11)
+        # the loss is a sum of 67 * nnz terms (6.7e9 at config 3): Java adds them one by one, the engine adds per-lane
+        # partials in a fixed tree -- the two roundings differ by ~1e-10 relative at this size (1e-11 at test sizes)
+        out["bar"] = "P, Q, biases bit-identical (sha256 over the arrays); loss within 1e-9 relative"
+        out["ok"] = bool(out["digest_equal"] and out["loss_rel"] < 1e-9)
     else:
         out["max_abs_diff"] = {k: float(np.max(np.abs(got[k] - ref[k]))) if ref[k].size else 0.0 for k in ref}
         out["bar"] = "not serial-equivalent: loss difference after the same epochs is reported, not gated"
@@ -392,7 +394,7 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
     tstream = torch.cuda.Stream(device=dev)  # the engine's kernels, the collectives and the events share it
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
-    rec = Rec(ts, None, conf=conf, device=local_rank, stream=stream, world=world, combine=args.combine)
+    rec = Rec(ts, None, conf=conf, device=local_rank, stream=stream, world=world, combine=args.combine, tuning=args.tuning)
     rec.initModel(init={k: v.copy() for k, v in arrs.items()})
     t0 = time.time()
     eng = rec.open_engine()
@@ -661,6 +663,7 @@ def main():
                     "rmse_vs_serial mini-run (N > 1)")
     ap.add_argument("--mode", default=os.environ.get("CARS_BENCH_MODE", "exact"), choices=["exact", "fast"])
     ap.add_argument("--combine", default="mean", choices=["mean", "sum"])
+    ap.add_argument("--tuning", default=None, help="developer knobs passed in cars_desc.tuning, e.g. shape=1")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

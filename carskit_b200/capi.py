@@ -56,6 +56,7 @@ class CarsStats(C.Structure):
         ("grid_ctas", C.c_int32), ("block_threads", C.c_int32), ("sm_count", C.c_int32), ("reserved", C.c_int32),
         ("schedule_copy_ms", C.c_double), ("schedule_levels_ms", C.c_double), ("schedule_pack_ms", C.c_double),
         ("fast_min_item_scale", C.c_double), ("fast_min_cond_scale", C.c_double), ("max_item_degree", C.c_int64),
+        ("fast_hot_rows", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 

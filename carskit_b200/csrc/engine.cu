@@ -12,6 +12,7 @@
 #include "staged_copy.cuh"
 #include "rank_kernels.cuh"
 #include "tuning.h"
+#include "dev_mem.cuh"
 
 #include <cuda_runtime.h>
 
@@ -47,6 +48,7 @@ struct cars_handle {
   bool own_stream = false;
   cudaEvent_t ev_beg = nullptr, ev_end = nullptr;
   StagedCopier copier;  // host <-> device transfers of the caller's (pageable or pinned) arrays
+  DevMem mem;           // device allocations: the device's stream-ordered pool (dev_mem.cuh)
 
   // model
   DeviceModel m{};
@@ -67,6 +69,9 @@ struct cars_handle {
   double* d_item_scale = nullptr;  // FAST: per-item step damping [num_items]
   double* d_cond_scale = nullptr;  // FAST, CAMF_C: per-condition step damping [C]
   bool damp_items = false, damp_conds = false;
+  signed char* d_hot_slot = nullptr;  // FAST: hot-row slot of every item (-1 = none) [num_items]
+  int32_t* d_hot_items = nullptr;     // FAST: item of every hot slot
+  int num_hot = 0, hot_flush = 16;
   RatingRec* d_rec = nullptr;
   int64_t* d_chunk_start = nullptr;
   double* d_chunk_loss = nullptr;
@@ -111,9 +116,10 @@ static int fail(cars_handle* h, int code, const char* fmt, ...) {
   } while (0)
 
 template <typename T>
-static cudaError_t dev_alloc(T** p, size_t n) {
-  return cudaMalloc(reinterpret_cast<void**>(p), (n ? n : 1) * sizeof(T));
+static cudaError_t dev_alloc_on(const DevMem& mem, T** p, size_t n) {
+  return mem.alloc(reinterpret_cast<void**>(p), (n ? n : 1) * sizeof(T));
 }
+#define dev_alloc(ptr, n) dev_alloc_on(h->mem, ptr, n)  /* every call site has the handle `h` in scope */
 
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch: model x (lanes per rating, chunks per lane) chosen from num_factors
@@ -159,17 +165,18 @@ static LaunchPlan pick_dataflow_plan(int model, int Fp) {
   return LaunchPlan{};
 }
 
-// FAST (hogwild) kernel.  shape 0 (default): F = 64 -> 4 lanes per rating, 256-bit row accesses, F compiled in;
-// F = 128 -> 16 lanes; otherwise the generic table.  shape 1: 8 lanes per rating at F = 64 (fewer registers).
+// FAST (hogwild) kernel.  shape 0 (default): F = 64 -> 8 lanes per rating (8 factors per lane), 256-bit row accesses,
+// F compiled in, 256 threads x 2 CTAs per SM (no spills; 3.35 ms per 10 M ratings against 3.83 ms for 4 lanes and
+// 4.28 ms for 3 CTAs per SM, profiles/r2/fast_shapes.txt); F = 128 -> 16 lanes; otherwise the generic table.
 template <int MODEL>
 static LaunchPlan pick_fast_generic(int Fp) { CARS_SHAPE_TABLE(sgd_fast_kernel, MODEL, 256, 2) }
 template <int MODEL>
 static LaunchPlan pick_fast(int Fp, int F, int shape) {
   LaunchPlan p;
   p.threads = 256;
-  if (F == 64 && shape == 0) { p.fn = (const void*)sgd_fast_kernel<MODEL, 4, 8, 256, 2, true, 64>; p.lpr = 4; p.v = 8; return p; }
+  if (F == 64 && shape == 0) { p.fn = (const void*)sgd_fast_kernel<MODEL, 8, 4, 256, 2, true, 64>; p.lpr = 8; p.v = 4; return p; }
   if (F == 64 && shape == 1) { p.fn = (const void*)sgd_fast_kernel<MODEL, 8, 4, 256, 3, true, 64>; p.lpr = 8; p.v = 4; return p; }
-  if (F == 64 && shape == 2) { p.fn = (const void*)sgd_fast_kernel<MODEL, 8, 4, 256, 2, true, 64>; p.lpr = 8; p.v = 4; return p; }
+  if (F == 64 && shape == 2) { p.fn = (const void*)sgd_fast_kernel<MODEL, 4, 8, 256, 2, true, 64>; p.lpr = 4; p.v = 8; return p; }
   if (F == 128 && shape <= 2) { p.fn = (const void*)sgd_fast_kernel<MODEL, 16, 4, 256, 2, true, 128>; p.lpr = 16; p.v = 4; return p; }
   return pick_fast_generic<MODEL>(Fp);
 }
@@ -340,6 +347,9 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   }
   CUDA_TRY_H(cudaEventCreate(&h->ev_beg));
   CUDA_TRY_H(cudaEventCreate(&h->ev_end));
+  h->mem.stream = h->stream;
+  h->mem.pooled = h->tune.get_ll("pool", 1) != 0;
+  if (h->mem.pooled) CUDA_TRY_H(pool_setup(h->device));
   CUDA_TRY_H(h->copier.init(h->device, (int)h->tune.get_ll("copy_threads", 0)));
 
   const int F = desc->num_factors;
@@ -419,7 +429,9 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     const int G = 32 / plan.lpr;
     groups_per_cta = (plan.threads / 32) * G;
     h->block = plan.threads;
-    h->smem = fast ? 0 : (size_t)groups_per_cta * (Fp + 2) * 8;
+    // FAST: room for the hot rows' accumulators (at most 32 rows / 32 KB) enters the occupancy up front
+    const int hot_max = fast ? (4096 / (Fp + 2) < 32 ? 4096 / (Fp + 2) : 32) : 0;
+    h->smem = fast ? (size_t)hot_max * (Fp + 2) * 8 + (size_t)hot_max * 4 + 16 : (size_t)groups_per_cta * (Fp + 2) * 8;
     CUDA_TRY_H(cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     int per_sm = 0;
     CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, plan.threads, h->smem));
@@ -447,6 +459,11 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     CUDA_TRY_H(dev_alloc(&h->d_chunk_start, (size_t)h->num_chunks + 1));
     CUDA_TRY_H(dev_alloc(&h->d_item_scale, I));
     if (model == CARS_CAMF_C) CUDA_TRY_H(dev_alloc(&h->d_cond_scale, C));
+    const int hot_max = (int)h->tune.get_ll("fast_hot_rows", 4096 / (Fp + 2) < 32 ? 4096 / (Fp + 2) : 32);
+    h->hot_flush = (int)h->tune.get_ll("fast_hot_flush", 16);
+    if (h->hot_flush < 1) h->hot_flush = 1;
+    CUDA_TRY_H(dev_alloc(&h->d_hot_slot, I));
+    CUDA_TRY_H(dev_alloc(&h->d_hot_items, 64));
     h->flags_words = 64;
     CUDA_TRY_H(dev_alloc(&h->d_flags, h->flags_words));
     CUDA_TRY_H(cudaStreamSynchronize(h->stream));  // the context table must have landed
@@ -454,7 +471,8 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     cudaError_t be = build_fast_on_device(desc->num_users, desc->num_items, desc->num_contexts, nnz, desc->u, desc->j,
                                           has_ctx ? desc->ctx : nullptr, desc->r, h->stream, h->sm_count, h->copier, chunk_len,
                                           in_flight, max_conc, h->d_ctx_tab, Dmax, desc->num_conditions, h->d_rec,
-                                          h->d_chunk_start, h->d_item_scale, h->d_cond_scale, &fb);
+                                          h->d_chunk_start, h->d_item_scale, h->d_cond_scale,
+                                          hot_max > 32 ? 32 : hot_max, h->hot_flush, h->grid, h->d_hot_slot, h->d_hot_items, h->mem, &fb);
     if (fb.bad_index >= 0) {
       const int64_t n = fb.bad_index;
       fail(h, CARS_E_INVALID, "rating %lld has an id out of range (u=%d j=%d ctx=%d)", (long long)n, desc->u[n], desc->j[n],
@@ -466,6 +484,8 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
       return bail(be == cudaErrorMemoryAllocation ? CARS_E_OOM : CARS_E_CUDA);
     }
     h->damp_items = fb.min_item_scale < 1.0;
+    h->num_hot = fb.num_hot;
+    h->st.fast_hot_rows = fb.num_hot;
     h->damp_conds = h->d_cond_scale && fb.min_cond_scale < 1.0;
     h->num_levels = h->num_chunks;
     h->max_level_size = fb.max_chunk;
@@ -540,7 +560,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     FlaggedBuild fb;
     cudaError_t be = build_flagged_on_device(desc->num_users, desc->num_items, desc->num_contexts, nnz, desc->u, desc->j,
                                              has_ctx ? desc->ctx : nullptr, desc->r, h->stream, h->sm_count, h->copier,
-                                             h->d_rec, &fb, h->tune.is("levels", "host"), sched_trace);
+                                             h->d_rec, &fb, h->mem, h->tune.is("levels", "host"), sched_trace);
     if (fb.bad_index >= 0) {
       const int64_t n = fb.bad_index;
       fail(h, CARS_E_INVALID, "rating %lld has an id out of range (u=%d j=%d ctx=%d)", (long long)n, desc->u[n], desc->j[n],
@@ -731,6 +751,8 @@ extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
     fs.rec = h->d_rec; fs.chunk_start = h->d_chunk_start; fs.counter = h->d_flags; fs.num_chunks = (uint32_t)h->num_chunks;
     fs.item_scale = h->damp_items ? h->d_item_scale : nullptr;
     fs.cond_scale = h->damp_conds ? h->d_cond_scale : nullptr;
+    fs.hot_slot = h->num_hot > 0 ? h->d_hot_slot : nullptr;
+    fs.hot_items = h->d_hot_items; fs.num_hot = h->num_hot; fs.hot_flush = h->hot_flush;
     CUDA_TRY(h, cudaMemsetAsync(h->d_flags, 0, h->flags_words * sizeof(unsigned), h->stream));
     void* args[] = {&m, &fs, &lrate, &h->d_partial};
     CUDA_TRY(h, cudaLaunchKernel(h->plan.fn, dim3(h->grid), dim3(h->block), args, h->smem, h->stream));
@@ -955,7 +977,7 @@ extern "C" int cars_predict(cars_handle* h, int64_t n, const int32_t* u, const i
   } else {
     cudaStreamSynchronize(h->stream);
   }
-  cudaFree(du); cudaFree(dj); cudaFree(dc); cudaFree(d_out);
+  h->mem.free(du); h->mem.free(dj); h->mem.free(dc); h->mem.free(d_out);
   return rc;
 }
 
@@ -1103,8 +1125,8 @@ extern "C" int cars_rank_topn(cars_handle* h, int64_t num_queries, const int32_t
   if (e == cudaSuccess) e = es;
 #undef RK
   h->st.d2h_bytes += num_queries * ((int64_t)num_recs * 12 + 8);
-  cudaFree(d_qu); cudaFree(d_qc); cudaFree(d_cand); cudaFree(d_cidx); cudaFree(d_rated); cudaFree(d_items);
-  cudaFree(d_count); cudaFree(d_kept); cudaFree(d_rptr); cudaFree(d_scores); cudaFree(d_keys);
+  h->mem.free(d_qu); h->mem.free(d_qc); h->mem.free(d_cand); h->mem.free(d_cidx); h->mem.free(d_rated); h->mem.free(d_items);
+  h->mem.free(d_count); h->mem.free(d_kept); h->mem.free(d_rptr); h->mem.free(d_scores); h->mem.free(d_keys);
   if (rc) return rc;
   if (e != cudaSuccess)
     return fail(h, e == cudaErrorMemoryAllocation ? CARS_E_OOM : CARS_E_CUDA, "cars_rank_topn failed: %s", cudaGetErrorString(e));
@@ -1118,13 +1140,15 @@ extern "C" void cars_destroy(cars_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->d_ctx_tab);
-  cudaFree(h->d_u); cudaFree(h->d_j); cudaFree(h->d_ctx); cudaFree(h->d_r); cudaFree(h->d_level_start);
-  cudaFree(h->m.P); cudaFree(h->m.Q); cudaFree(h->m.user_bias); cudaFree(h->m.item_bias);
-  cudaFree(h->m.cond_bias); cudaFree(h->m.ic_bias); cudaFree(h->m.uc_bias);
-  cudaFree(h->d_rec); cudaFree(h->d_chunk_start); cudaFree(h->d_chunk_loss); cudaFree(h->d_flags);
-  cudaFree(h->d_item_old); cudaFree(h->d_item_scale); cudaFree(h->d_cond_scale);
-  cudaFree(h->d_barrier); cudaFree(h->d_partial); cudaFree(h->d_loss);
+  h->mem.free(h->d_ctx_tab);
+  h->mem.free(h->d_u); h->mem.free(h->d_j); h->mem.free(h->d_ctx); h->mem.free(h->d_r); h->mem.free(h->d_level_start);
+  h->mem.free(h->m.P); h->mem.free(h->m.Q); h->mem.free(h->m.user_bias); h->mem.free(h->m.item_bias);
+  h->mem.free(h->m.cond_bias); h->mem.free(h->m.ic_bias); h->mem.free(h->m.uc_bias);
+  h->mem.free(h->d_rec); h->mem.free(h->d_chunk_start); h->mem.free(h->d_chunk_loss); h->mem.free(h->d_flags);
+  h->mem.free(h->d_item_old); h->mem.free(h->d_item_scale); h->mem.free(h->d_cond_scale);
+  h->mem.free(h->d_hot_slot); h->mem.free(h->d_hot_items);
+  h->mem.free(h->d_barrier); h->mem.free(h->d_partial); h->mem.free(h->d_loss);
+  if (h->stream) cudaStreamSynchronize(h->stream);  // the pool's frees are stream-ordered
   if (h->h_loss) cudaFreeHost(h->h_loss);
   h->copier.destroy();
   if (h->ev_beg) cudaEventDestroy(h->ev_beg);

@@ -32,7 +32,18 @@ struct FastStream {
   uint32_t num_chunks;
   const double* item_scale;    // [num_items] step damping of the item-side cells, or nullptr (all 1)
   const double* cond_scale;    // [C] CAMF_C: step damping of condBias, or nullptr
+  // Hot rows (a Zipf head): same-address reductions serialise in the L2 atomic unit (~35 ns per 64-factor row,
+  // profiles/r2), so an item that owns 8 % of the ratings would bound the epoch on its own.  The steps of the
+  // num_hot most popular items are summed per CTA in shared memory and flushed to Q[j] / itemBias[j] once every
+  // hot_flush updates of the CTA (and at the end of the kernel): hot_flush times fewer global reductions on those rows.
+  const signed char* hot_slot;  // [num_items] slot of a hot item, -1 otherwise; nullptr = no hot rows
+  const int32_t* hot_items;     // [num_hot] item id of every slot
+  int num_hot, hot_flush;
 };
+
+__device__ __forceinline__ double atomic_exch_shared_f64(double* p, double v) {
+  return __longlong_as_double((long long)atomicExch(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__double_as_longlong(v)));
+}
 
 __device__ __forceinline__ void red_add_f64(double* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
@@ -48,6 +59,7 @@ struct FastOps {
   double scale;    // item_scale[j]
   double cscale;   // cond_scale[cond] (CAMF_C)
   int cond;        // this lane's condition id, -1 = none
+  int slot;        // hot-row slot of item j, -1 = none
 };
 
 template <int MODEL, int LPR, int V, bool WIDE, int FIXF>
@@ -76,6 +88,8 @@ __device__ __forceinline__ void fast_load(const DeviceModel& m, const FastStream
   if (kItemBias) o.bj = ld_cg_f64(m.item_bias + rec.j);
   o.scale = 1.0;
   if (s.item_scale) o.scale = __ldg(s.item_scale + rec.j);
+  o.slot = -1;
+  if (s.hot_slot) o.slot = __ldg(s.hot_slot + rec.j);
   o.cb = 0.0;
   o.cb_ptr = nullptr;
   o.cscale = 1.0;
@@ -97,7 +111,7 @@ __device__ __forceinline__ void fast_load(const DeviceModel& m, const FastStream
 // One rating: arithmetic + user-side stores + item-side reductions.  Returns this lane's loss contribution.
 template <int MODEL, int LPR, int V, bool WIDE, int FIXF>
 __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastStream& s, const RatingRec& rec, double lr,
-                                              int gl, unsigned gmask, UserRegs<V>& us, const FastOps<V>& o) {
+                                              int gl, unsigned gmask, UserRegs<V>& us, const FastOps<V>& o, double* sh_hot) {
   constexpr bool kUserBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CI);
   constexpr bool kItemBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CU);
   constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU || MODEL == M_CAMF_CUCI);
@@ -163,7 +177,9 @@ __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastSt
     lane_loss = __dmul_rn(e, e);
     if (kUserBias) lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_b, bu), bu));
     if (kItemBias) {
-      red_add_f64(m.item_bias + j, __dmul_rn(lrj, __dsub_rn(e, __dmul_rn(m.reg_b, bj))));
+      const double step = __dmul_rn(lrj, __dsub_rn(e, __dmul_rn(m.reg_b, bj)));
+      if (o.slot >= 0) atomicAdd(sh_hot + o.slot * (Fp + 2) + Fp, step);
+      else red_add_f64(m.item_bias + j, step);
       lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_b, bj), bj));
     }
   }
@@ -202,7 +218,9 @@ __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastSt
   }
 
   // ---- factor steps (both from the values read) -----------------------------------------------------------------
+  // a hot item's steps go to the CTA's shared-memory accumulator row, everything else straight to L2
   double* qrow = m.Q + (int64_t)j * Fp;
+  double* srow = sh_hot + (o.slot >= 0 ? o.slot : 0) * (Fp + 2);  // (shared address space: ATOMS, not generic ATOM)
   double sp = 0.0, sq = 0.0;
 #pragma unroll
   for (int v = 0; v < V; v++) {
@@ -211,12 +229,40 @@ __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastSt
       const double2 po = us.p[v], qo = o.q[v];
       us.p[v].x = __dadd_rn(po.x, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, qo.x), __dmul_rn(m.reg_u, po.x))));
       us.p[v].y = __dadd_rn(po.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, qo.y), __dmul_rn(m.reg_u, po.y))));
-      red_add_f64(qrow + 2 * c, __dmul_rn(lrj, __dsub_rn(__dmul_rn(e, po.x), __dmul_rn(m.reg_i, qo.x))));
-      red_add_f64(qrow + 2 * c + 1, __dmul_rn(lrj, __dsub_rn(__dmul_rn(e, po.y), __dmul_rn(m.reg_i, qo.y))));
+      const double dx = __dmul_rn(lrj, __dsub_rn(__dmul_rn(e, po.x), __dmul_rn(m.reg_i, qo.x)));
+      const double dy = __dmul_rn(lrj, __dsub_rn(__dmul_rn(e, po.y), __dmul_rn(m.reg_i, qo.y)));
+      if (o.slot >= 0) {
+        atomicAdd(srow + 2 * c, dx);
+        atomicAdd(srow + 2 * c + 1, dy);
+      } else {
+        red_add_f64(qrow + 2 * c, dx);
+        red_add_f64(qrow + 2 * c + 1, dy);
+      }
       sp = fma(po.x, po.x, sp);
       sq = fma(qo.x, qo.x, sq);
       sp = fma(po.y, po.y, sp);
       sq = fma(qo.y, qo.y, sq);
+    }
+  }
+  if (s.hot_slot) {  // every hot_flush-th update of a slot by this CTA moves the accumulated row to L2
+    bool flush = false;
+    if (o.slot >= 0) {
+      __syncwarp(gmask);
+      unsigned* cnt = reinterpret_cast<unsigned*>(sh_hot + s.num_hot * (Fp + 2));
+      unsigned c = 0;
+      if (gl == 0) c = atomicAdd(cnt + o.slot, 1u) + 1u;
+      c = __shfl_sync(gmask, c, 0, LPR);
+      flush = (c % (unsigned)s.hot_flush) == 0u;
+    }
+    if (flush) {
+      for (int f = gl; f < Fp; f += LPR) {
+        const double v = atomic_exch_shared_f64(srow + f, 0.0);
+        if (v != 0.0) red_add_f64(qrow + f, v);
+      }
+      if (kItemBias && gl == 0) {
+        const double v = atomic_exch_shared_f64(srow + Fp, 0.0);
+        if (v != 0.0) red_add_f64(m.item_bias + j, v);
+      }
     }
   }
   return __dadd_rn(lane_loss, fma(m.reg_u, sp, __dmul_rn(m.reg_i, sq)));
@@ -272,7 +318,14 @@ __device__ __forceinline__ void fast_store_user(const DeviceModel& m, int u, int
 // K2: persistent grid (any size: chunks are only held by running groups, so no co-residency is needed).
 template <int MODEL, int LPR, int V, int THREADS, int MINB, bool WIDE = false, int FIXF = 0>
 __global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, FastStream s, double lr, double* block_partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sh_hot = reinterpret_cast<double*>(smem_raw);  // [num_hot x (Fp + 2)] accumulators, then num_hot counters
   constexpr int WARPS = THREADS / 32;
+  const int hot_words = s.hot_slot ? s.num_hot * ((FIXF > 0 ? FIXF : m.Fp) + 2) : 0;
+  if (s.hot_slot) {
+    for (int i = threadIdx.x; i < hot_words + (s.num_hot + 1) / 2; i += THREADS) sh_hot[i] = 0.0;
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int gl = lane % LPR;
@@ -320,7 +373,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, 
         fast_load<MODEL, LPR, V, WIDE, FIXF>(m, s, recn, gl, nxt);
       }
       if (rec.u != prev_u) fast_load_user<MODEL, LPR, V, WIDE, FIXF>(m, rec.u, gl, us);
-      acc = __dadd_rn(acc, fast_update<MODEL, LPR, V, WIDE, FIXF>(m, s, rec, lr, gl, gmask, us, cur));
+      acc = __dadd_rn(acc, fast_update<MODEL, LPR, V, WIDE, FIXF>(m, s, rec, lr, gl, gmask, us, cur, sh_hot));
       if (!has_next || recn.u != rec.u) fast_store_user<MODEL, LPR, V, WIDE, FIXF>(m, rec.u, gl, us);
       prev_u = rec.u;
       if (has_next) {
@@ -339,6 +392,18 @@ __global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, 
     double t = 0.0;
     for (int w = 0; w < WARPS; w++) t += warp_sum[w];
     block_partial[blockIdx.x] = t;
+  }
+  if (s.hot_slot) {  // what the CTA still holds for the hot rows (every warp is past its last update: barrier above)
+    constexpr bool kItemBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CU);
+    const int Fp = FIXF > 0 ? FIXF : m.Fp;
+    for (int i = threadIdx.x; i < hot_words; i += THREADS) {
+      const double v = sh_hot[i];
+      if (v == 0.0) continue;
+      const int slot = i / (Fp + 2), f = i % (Fp + 2);
+      const int j = __ldg(s.hot_items + slot);
+      if (f < Fp) red_add_f64(m.Q + (int64_t)j * Fp + f, v);
+      else if (kItemBias && f == Fp) red_add_f64(m.item_bias + j, v);
+    }
   }
 }
 

@@ -10,6 +10,8 @@
 //      (shared-memory histogram); scale[row] = min(1, max_conc / (degree * groups_in_flight / nnz)) -- the expected
 //      number of in-flight ratings that share the row (fast_kernels.cuh).
 #pragma once
+#include <algorithm>
+
 #include "schedule_gpu.cuh"
 
 namespace cars {
@@ -118,7 +120,28 @@ __global__ void __launch_bounds__(256) fast_scale_kernel(const DegT* __restrict_
   }
 }
 
+// items rated at least min_degree times: (degree << 32 | item) appended to `out` (capacity `cap`)
+__global__ void __launch_bounds__(256) fast_hot_candidates_kernel(const unsigned* __restrict__ deg, int32_t num_items,
+                                                                  int64_t min_degree, unsigned long long* __restrict__ out,
+                                                                  unsigned* __restrict__ count, unsigned cap) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < num_items; j += stride) {
+    const unsigned d = deg[j];
+    if ((int64_t)d >= min_degree && d > 0) {
+      const unsigned k = atomicAdd(count, 1u);
+      if (k < cap) out[k] = ((unsigned long long)d << 32) | (unsigned long long)(uint32_t)j;
+    }
+  }
+}
+
+constexpr int kHotCandCap = 512;
+// A row is accumulated per CTA only if every CTA flushes it at least kHotMinFlushes times per epoch: a row that is
+// merely popular would sit in shared memory until the end of the kernel -- one stale batch step per epoch -- and the
+// staleness bound the damping is computed from (hot_flush updates held back by every CTA) would not describe it.
+constexpr int64_t kHotMinFlushes = 8;
+
 struct FastBuild {
+  int num_hot = 0;
   int64_t num_chunks = 0, max_chunk = 0, bad_index = -1;
   int64_t h2d_bytes = 0, kernel_launches = 0;
   int64_t max_item_degree = 0;
@@ -133,14 +156,15 @@ inline cudaError_t build_fast_on_device(int32_t num_users, int32_t num_items, in
                                         const int32_t* j, const int32_t* ctx, const double* r, cudaStream_t stream, int sm_count,
                                         StagedCopier& copier, int64_t chunk_len, double groups_in_flight, double max_conc,
                                         const int32_t* d_ctx_tab, int Dmax, int C, RatingRec* d_rec, int64_t* d_chunk_start,
-                                        double* d_item_scale, double* d_cond_scale, FastBuild* info) {
+                                        double* d_item_scale, double* d_cond_scale, int hot_max, int hot_flush, int grid_ctas,
+                                        signed char* d_hot_slot, int32_t* d_hot_items, const DevMem& mem, FastBuild* info) {
   if (nnz == 0) return cudaSuccess;
   const size_t N = (size_t)nnz;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   char* arena = nullptr;
   cudaError_t e = cudaSuccess;
   auto cleanup = [&]() {
-    cudaFree(arena);
+    mem.free(arena);
     for (auto& x : ev)
       if (x) cudaEventDestroy(x);
   };
@@ -170,8 +194,10 @@ inline cudaError_t build_fast_on_device(int32_t num_users, int32_t num_items, in
   const size_t o_u = reserve(N * 4), o_j = reserve(N * 4), o_ctx = reserve(ctx ? N * 4 : 0), o_r = reserve(N * 8),
                o_idx = reserve(N * 4), o_ord = reserve(N * 4), o_skey = reserve(N * 4), o_temp = reserve(temp_bytes),
                o_tmp = reserve(N * sizeof(RatingRec)), o_uptr = reserve(((size_t)num_users + 1) * 8),
-               o_ideg = reserve((size_t)num_items * 4), o_cdeg = reserve((size_t)(C > 0 ? C : 1) * 8), o_scal = reserve(64);
-  FB_TRY(cudaMalloc((void**)&arena, total));
+               o_ideg = reserve((size_t)num_items * 4), o_cdeg = reserve((size_t)(C > 0 ? C : 1) * 8), o_scal = reserve(64),
+               o_hot = reserve((size_t)kHotCandCap * 8 + 64);
+  FB_TRY(mem.alloc((void**)&arena, total));
+  FB_TRY(cudaStreamSynchronize(stream));  // the copier fills the arena from its own streams
   RatingSoA d;
   d.u = (int32_t*)(arena + o_u); d.j = (int32_t*)(arena + o_j); d.ctx = ctx ? (int32_t*)(arena + o_ctx) : nullptr;
   d.r = (double*)(arena + o_r);
@@ -183,6 +209,8 @@ inline cudaError_t build_fast_on_device(int32_t num_users, int32_t num_items, in
   int64_t* d_user_ptr = (int64_t*)(arena + o_uptr);
   unsigned* d_ideg = (unsigned*)(arena + o_ideg);
   unsigned long long* d_cdeg = (unsigned long long*)(arena + o_cdeg);
+  unsigned long long* d_hot_cand = (unsigned long long*)(arena + o_hot);
+  unsigned* d_hot_count = (unsigned*)(arena + o_hot + (size_t)kHotCandCap * 8);
   unsigned long long* d_scal = (unsigned long long*)(arena + o_scal);  // [0] bad, [1] max chunk, [2] min item scale bits,
                                                                        // [3] max item degree, [4] min cond scale bits, [5] max cond degree
 
@@ -251,8 +279,52 @@ inline cudaError_t build_fast_on_device(int32_t num_users, int32_t num_items, in
     FB_TRY(cudaGetLastError());
     info->kernel_launches += 2;
   }
+  // ---- hot rows: the most popular items, accumulated per CTA in shared memory (fast_kernels.cuh) -------------------
+  std::vector<unsigned long long> cand;
+  if (hot_max > 0 && max_conc > 0.0 && d_hot_slot) {
+    FB_TRY(cudaMemsetAsync(d_hot_count, 0, 4, stream));
+    fast_hot_candidates_kernel<<<blocks, 256, 0, stream>>>(d_ideg, num_items, kHotMinFlushes * hot_flush * grid_ctas, d_hot_cand,
+                                                           d_hot_count, kHotCandCap);
+    FB_TRY(cudaGetLastError());
+    unsigned ncand = 0;
+    FB_TRY(cudaMemcpyAsync(&ncand, d_hot_count, 4, cudaMemcpyDeviceToHost, stream));
+    FB_TRY(cudaStreamSynchronize(stream));
+    info->kernel_launches += 1;
+    if (ncand > (unsigned)kHotCandCap) ncand = kHotCandCap;
+    if (ncand) {
+      cand.resize(ncand);
+      FB_TRY(cudaMemcpy(cand.data(), d_hot_cand, (size_t)ncand * 8, cudaMemcpyDeviceToHost));
+      std::sort(cand.begin(), cand.end(), [](unsigned long long a, unsigned long long b) {
+        return (a >> 32) != (b >> 32) ? (a >> 32) > (b >> 32) : (uint32_t)a < (uint32_t)b;  // degree desc, item id asc
+      });
+      if ((int)cand.size() > hot_max) cand.resize((size_t)hot_max);
+    }
+  }
   unsigned long long scal[6];
   FB_TRY(cudaMemcpyAsync(scal, d_scal, sizeof scal, cudaMemcpyDeviceToHost, stream));
+  FB_TRY(cudaStreamSynchronize(stream));
+  if (!cand.empty()) {
+    // a hot row's staleness: the in-flight ratings that share it PLUS what the CTAs hold back between flushes
+    std::vector<int32_t> items(cand.size());
+    FB_TRY(cudaMemsetAsync(d_hot_slot, 0xff, (size_t)num_items, stream));
+    double min_scale = 1.0;
+    memcpy(&min_scale, &scal[2], 8);
+    for (size_t k = 0; k < cand.size(); k++) {
+      const int32_t item = (int32_t)(uint32_t)cand[k];
+      const double deg = (double)(cand[k] >> 32);
+      items[k] = item;
+      const double stale = deg * groups_in_flight / (double)nnz + (double)hot_flush * grid_ctas;
+      const double sc = stale > max_conc ? max_conc / stale : 1.0;
+      if (sc < min_scale) min_scale = sc;
+      const signed char slot = (signed char)k;
+      FB_TRY(cudaMemcpyAsync(d_hot_slot + item, &slot, 1, cudaMemcpyHostToDevice, stream));
+      FB_TRY(cudaMemcpyAsync(d_item_scale + item, &sc, 8, cudaMemcpyHostToDevice, stream));
+    }
+    memcpy(&scal[2], &min_scale, 8);
+    FB_TRY(cudaMemcpyAsync(d_hot_items, items.data(), items.size() * 4, cudaMemcpyHostToDevice, stream));
+    FB_TRY(cudaStreamSynchronize(stream));  // `items`, `slot`, `sc` are host temporaries
+    info->num_hot = (int)cand.size();
+  }
   FB_TRY(cudaEventRecord(ev[3], stream));
   FB_TRY(cudaStreamSynchronize(stream));
   info->num_chunks = num_chunks;

@@ -24,6 +24,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <vector>
 
+#include "dev_mem.cuh"
 #include "sgd_kernels.cuh"
 #include "staged_copy.cuh"
 
@@ -250,7 +251,7 @@ inline bool build_flagged_host_levels(int32_t num_users, int32_t num_items, int6
 inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items, int32_t num_contexts, int64_t nnz,
                                            const int32_t* u, const int32_t* j, const int32_t* ctx, const double* r,
                                            cudaStream_t stream, int sm_count, StagedCopier& copier, RatingRec* d_rec,
-                                           FlaggedBuild* info, bool host_levels = false, bool trace = false) {
+                                           FlaggedBuild* info, const DevMem& mem, bool host_levels = false, bool trace = false) {
   if (nnz == 0) return cudaSuccess;
   // trace: host wall time of every phase, to stderr (tuning "sched_trace=1")
   auto t_last = std::chrono::steady_clock::now();
@@ -272,7 +273,7 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
   cudaError_t e = cudaSuccess;
   char* arena = nullptr;  // every temporary below is carved from ONE allocation (cudaMalloc / cudaFree are not free)
   auto cleanup = [&]() {
-    cudaFree(arena);
+    mem.free(arena);
     for (auto& x : ev)
       if (x) cudaEventDestroy(x);
   };
@@ -314,8 +315,9 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
       o_fr0 = reserve((fcap + 1) * 4); o_fr1 = reserve((fcap + 1) * 4); o_ctl = reserve(sizeof(KahnCtl));
     }
     lap("size queries");
-    SG_TRY(cudaMalloc((void**)&arena, total));
-    lap("cudaMalloc(arena)");
+    SG_TRY(mem.alloc((void**)&arena, total));
+    SG_TRY(cudaStreamSynchronize(stream));  // the copier fills the arena from its own streams
+    lap("alloc(arena)");
     d.u = (int32_t*)(arena + o_u); d.j = (int32_t*)(arena + o_j); d.ctx = ctx ? (int32_t*)(arena + o_ctx) : nullptr;
     d.level = (int32_t*)(arena + o_level); d.ku = (int32_t*)(arena + o_ku); d.kj = (int32_t*)(arena + o_kj);
     d.r = (double*)(arena + o_r); d_idx = (uint32_t*)(arena + o_idx); d_ord = (uint32_t*)(arena + o_ord);

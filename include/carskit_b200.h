@@ -255,6 +255,8 @@ typedef struct cars_stats {
   double  fast_min_item_scale;
   double  fast_min_cond_scale;
   int64_t max_item_degree;
+  int32_t fast_hot_rows;    /* FAST: item rows whose steps are summed per CTA in shared memory before they reach L2 */
+  int32_t reserved2;
 } cars_stats;
 int cars_get_stats(const cars_handle* h, cars_stats* out);
 void* cars_get_stream(const cars_handle* h); /* cudaStream_t the kernels are launched on */

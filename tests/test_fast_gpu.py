@@ -17,7 +17,9 @@ from tests.golden.make_golden import REGS, bold_driver, init_arrays
 
 pytestmark = pytest.mark.gpu
 
-RMSE_TOL = 0.02  # |held-out RMSE(FAST) - RMSE(serial oracle)| on the planted data sets below (RMSE ~ 0.6-1.0)
+RMSE_TOL = 0.02  # held-out RMSE(FAST) may exceed RMSE(serial oracle) by at most this on the planted data sets below
+                 # (RMSE ~ 0.7-1.0).  One-sided: the damped hot rows act as a regulariser and FAST is often BETTER
+                 # than the serial loop on held-out data (measured: -0.014 and -0.025 on the Zipf cases)
 CTX_MODELS = (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI)
 
 
@@ -84,9 +86,12 @@ def test_fast_converges_like_the_serial_loop(oracle, cars_lib, model, F, zipf):
     r_ref, r_got = rmse(oracle, model, ts, F, ref, test), rmse(oracle, model, ts, F, got, test)
     print(f"model {model} F {F} zipf {zipf}: RMSE serial {r_ref:.4f} fast {r_got:.4f}; max item degree {st.max_item_degree}, "
           f"min item scale {st.fast_min_item_scale:.3g}; loss serial {rl[-1]:.6g} fast {gl[-1]:.6g}")
-    assert abs(r_got - r_ref) < RMSE_TOL
+    assert r_got - r_ref < RMSE_TOL
+    assert r_got < float(np.std(test["r"]))  # and it has learnt something: better than predicting the mean
     if zipf > 0:
-        assert st.fast_min_item_scale < 1.0  # the Zipf head is damped
+        assert st.fast_min_item_scale < 1.0 and st.fast_hot_rows > 0  # the Zipf head is damped and CTA-accumulated
+    else:
+        assert st.fast_hot_rows == 0
 
 
 def test_fast_camf_c_shared_condition_biases(oracle, cars_lib):
@@ -97,7 +102,7 @@ def test_fast_camf_c_shared_condition_biases(oracle, cars_lib):
     r_ref, r_got = rmse(oracle, capi.CAMF_C, ts, 10, ref, test), rmse(oracle, capi.CAMF_C, ts, 10, got, test)
     print(f"CAMF_C Frappe-shaped: RMSE serial {r_ref:.4f} fast {r_got:.4f}; min cond scale {st.fast_min_cond_scale:.3g}")
     assert st.fast_min_cond_scale < 1.0
-    assert abs(r_got - r_ref) < 0.05
+    assert r_got - r_ref < 0.05
 
 
 def test_fast_edge_cases(oracle, cars_lib):

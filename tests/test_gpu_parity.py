@@ -368,3 +368,53 @@ def test_config2_frappe_shaped_camf_c_bit_identical(oracle, cars_lib):
     ra, rs, cnt = oracle.eval_ratings(desc, ref, test["u"], test["j"], test["ctx"], test["r"], 1.0, 5.0)
     assert (sa, ss) == (ra, rs) and cnt == len(test["r"])
     assert ts.num_conditions == 343 and st.nnz == ts.nnz
+
+
+# ---- against OUTPUTS OF THE REFERENCE ITSELF -------------------------------------------------------------------------
+# tests/golden/jvm_golden.json was produced by executing the reference's own class files (tests/tools/minijvm.py,
+# tests/golden/make_jvm_golden.py) in the container that has /root/reference; the GPU box does not, the vectors travel.
+from tests.golden import make_jvm_golden as JG  # noqa: E402
+
+JVM_GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "jvm_golden.json")))
+
+
+@pytest.mark.parametrize("case", JVM_GOLDEN["cases"], ids=[c["name"] for c in JVM_GOLDEN["cases"]])
+def test_engine_reproduces_the_reference_bytecode_vectors(oracle, cars_lib, case):
+    from carskit_b200 import recommender
+    spec = case["spec"]
+    model, ts, test, arrs = JG.sgd_inputs(oracle, spec)
+    assert JG.sha(ts.u, ts.j, ts.ctx, ts.r, *[arrs[k] for k in sorted(arrs)]) == case["input_sha"], "input generator drift"
+    hy = JG.hyper(spec)
+    lr = f"{hy['lrate']} -max {hy['max_lrate']}" + (" -bold-driver" if hy["bold_driver"] else "") + \
+        (f" -decay {hy['decay']}" if hy["decay"] > 0 else "")
+    conf = {"num.factors": str(spec["F"]), "num.max.iter": str(spec["iters"]), "learn.rate": lr, "reg.lambda": "0.0001 -c 0.001",
+            "rating.min": "1", "rating.max": "5"}
+    rec = recommender.getRecommender(spec["model"])(ts, test, conf=conf)
+    rec.initModel(init=arrs)
+    rec.keep_engine = True
+    rec.buildModel()  # the host mirror of isConverged / updateLRate drives cars_epoch
+    try:
+        assert digest(rec.model) == case["digest"]  # P, Q, biases: bit-identical to what the Java class files computed
+        want = [float.fromhex(x) for x in case["losses_hex"]]
+        np.testing.assert_allclose(rec.iter_losses, want, rtol=LOSS_RTOL, atol=0)
+        pred = rec.predict(test["u"], test["j"], test["ctx"], bound=True)
+        assert [float(x).hex() for x in pred[:40]] == case["pred_hex"]
+    finally:
+        rec.close_engine()
+
+
+def test_fm_engine_within_1e5_of_the_reference_bytecode_vector(oracle, cars_lib):
+    case = JVM_GOLDEN["fm"]
+    spec = case["spec"]
+    ts, test, arrs = JG.fm_inputs(oracle, spec)
+    assert JG.sha(ts.u, ts.j, ts.ctx, ts.r, arrs["w"], arrs["V"]) == case["input_sha"], "input generator drift"
+    desc = capi.make_desc(ts, capi.FM, spec["k"], reg_lw=capi.f32(spec["reg_lw"]), reg_lf=capi.f32(spec["reg_lf"]),
+                          num_context_dims=len(spec["dims"]))
+    with capi.FmEngine(desc, keepalive=ts) as eng:
+        eng.upload(arrs)
+        eng.prepare()
+        for _ in range(spec["iters"]):
+            eng.iteration()
+        pred = eng.predict(test["u"], test["j"], test["ctx"], bound=True, min_rate=1.0, max_rate=5.0)
+    want = np.array([float.fromhex(x) for x in case["pred_hex"]])
+    assert np.max(np.abs(pred - want)) < 1e-5  # the north star's bar for predicted ratings (sums in another order)
