@@ -56,7 +56,7 @@ class CarsStats(C.Structure):
         ("grid_ctas", C.c_int32), ("block_threads", C.c_int32), ("sm_count", C.c_int32), ("reserved", C.c_int32),
         ("schedule_copy_ms", C.c_double), ("schedule_levels_ms", C.c_double), ("schedule_pack_ms", C.c_double),
         ("fast_min_item_scale", C.c_double), ("fast_min_cond_scale", C.c_double), ("max_item_degree", C.c_int64),
-        ("fast_hot_rows", C.c_int32), ("reserved2", C.c_int32),
+        ("fast_hot_rows", C.c_int32), ("num_gpus", C.c_int32), ("exchange_ms", C.c_double),
     ]
 
 
@@ -68,6 +68,7 @@ EXPORTS = [
     "cars_epoch_sharded_finish", "cars_fm_create", "cars_fm_upload", "cars_fm_prepare", "cars_fm_iteration",
     "cars_fm_download", "cars_fm_predict", "cars_fm_get_stats", "cars_fm_last_error", "cars_fm_destroy",
     "cars_fm_exchange_doubles", "cars_fm_iteration_sharded", "cars_fm_get_stream", "cars_rank_topn",
+    "cars_device_count",
 ]
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
@@ -161,6 +162,8 @@ def load_library(path: Optional[str] = None):
     lib.cars_fm_destroy.restype = None
     lib.cars_version.argtypes = []
     lib.cars_version.restype = C.c_char_p
+    lib.cars_device_count.argtypes = []
+    lib.cars_device_count.restype = C.c_int
     if path is None:
         _lib = lib
     return lib

@@ -38,7 +38,10 @@ struct LaunchPlan {
   int lpr = 0, v = 0, threads = 0;
 };
 
+struct MultiGpu;  // multi_gpu.cuh: one handle driving N GPUs (cars_desc.num_gpus > 1)
+
 struct cars_handle {
+  MultiGpu* multi = nullptr;  // non-null: this handle is a front for N per-GPU handles; the members below are unused
   cars_desc d;  // scalars only; pointer members are nulled after create
   LaunchPlan plan;  // the SGD kernel chosen at create (shape, shared memory and grid belong together)
   cars::Tuning tune;
@@ -71,7 +74,7 @@ struct cars_handle {
   bool damp_items = false, damp_conds = false;
   signed char* d_hot_slot = nullptr;  // FAST: hot-row slot of every item (-1 = none) [num_items]
   int32_t* d_hot_items = nullptr;     // FAST: item of every hot slot
-  int num_hot = 0, hot_flush = 16;
+  int num_hot = 0, hot_flush = 16, hot_stride = 0;
   RatingRec* d_rec = nullptr;
   int64_t* d_chunk_start = nullptr;
   double* d_chunk_loss = nullptr;
@@ -120,6 +123,18 @@ static cudaError_t dev_alloc_on(const DevMem& mem, T** p, size_t n) {
   return mem.alloc(reinterpret_cast<void**>(p), (n ? n : 1) * sizeof(T));
 }
 #define dev_alloc(ptr, n) dev_alloc_on(h->mem, ptr, n)  /* every call site has the handle `h` in scope */
+
+static bool model_has_ctx(int model);
+static int multi_create(const cars_desc* desc, cars_handle** out);
+static void multi_destroy(cars_handle* h);
+static int multi_transfer(cars_handle* h, const cars_model_arrays* a, bool to_device);
+static int multi_epoch(cars_handle* h, double lrate, double* loss_out);
+static int multi_predict(cars_handle* h, int64_t n, const int32_t* u, const int32_t* j, const int32_t* ctx, int32_t bound,
+                         double min_rate, double max_rate, double* out);
+static int multi_rank_topn(cars_handle* h, int64_t nq, const int32_t* qu, const int32_t* qc, int32_t num_cand, const int32_t* cand,
+                           const int64_t* rated_ptr, const int32_t* rated_items, double bin_thold, int32_t num_recs,
+                           int32_t* out_items, double* out_scores, int32_t* out_count, int32_t* out_kept);
+static void multi_stats(const cars_handle* h, cars_stats* out);
 
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch: model x (lanes per rating, chunks per lane) chosen from num_factors
@@ -303,6 +318,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   *out = nullptr;
   int rc = validate(desc);
   if (rc) return rc;
+  if (desc->num_gpus > 1) return multi_create(desc, out);
 
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -430,13 +446,20 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     groups_per_cta = (plan.threads / 32) * G;
     h->block = plan.threads;
     // FAST: room for the hot rows' accumulators (at most 32 rows / 32 KB) enters the occupancy up front
-    const int hot_max = fast ? (4096 / (Fp + 2) < 32 ? 4096 / (Fp + 2) : 32) : 0;
-    h->smem = fast ? (size_t)hot_max * (Fp + 2) * 8 + (size_t)hot_max * 4 + 16 : (size_t)groups_per_cta * (Fp + 2) * 8;
+    h->hot_stride = Fp + 2 + ((model == CARS_CAMF_CI || model == CARS_CAMF_CUCI) ? desc->num_conditions : 0);
+    const int hot_max = fast ? (4096 / h->hot_stride < 32 ? 4096 / h->hot_stride : 32) : 0;
+    h->smem = fast ? (size_t)hot_max * h->hot_stride * 8 + (size_t)hot_max * 4 + 16 : (size_t)groups_per_cta * (Fp + 2) * 8;
     CUDA_TRY_H(cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     int per_sm = 0;
     CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, plan.threads, h->smem));
     if (per_sm < 1) { fail(h, CARS_E_CUDA, "SGD kernel does not fit on an SM (smem %zu)", h->smem); return bail(CARS_E_CUDA); }
     h->grid = h->sm_count * per_sm;
+    if (fast) {
+      // A small training set on a full grid would have most of its ratings in flight at once -- every update computed
+      // from values that miss a large share of the epoch's other updates.  Keep at least 256 ratings per group.
+      const int64_t want = (nnz + 256ll * groups_per_cta - 1) / (256ll * groups_per_cta);
+      if (want < h->grid) h->grid = (int)(want < 1 ? 1 : want);
+    }
   }
 
   // ---- schedule ----------------------------------------------------------------------------------------
@@ -459,7 +482,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     CUDA_TRY_H(dev_alloc(&h->d_chunk_start, (size_t)h->num_chunks + 1));
     CUDA_TRY_H(dev_alloc(&h->d_item_scale, I));
     if (model == CARS_CAMF_C) CUDA_TRY_H(dev_alloc(&h->d_cond_scale, C));
-    const int hot_max = (int)h->tune.get_ll("fast_hot_rows", 4096 / (Fp + 2) < 32 ? 4096 / (Fp + 2) : 32);
+    const int hot_max = (int)h->tune.get_ll("fast_hot_rows", 4096 / h->hot_stride < 32 ? 4096 / h->hot_stride : 32);
     h->hot_flush = (int)h->tune.get_ll("fast_hot_flush", 16);
     if (h->hot_flush < 1) h->hot_flush = 1;
     CUDA_TRY_H(dev_alloc(&h->d_hot_slot, I));
@@ -472,7 +495,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
                                           has_ctx ? desc->ctx : nullptr, desc->r, h->stream, h->sm_count, h->copier, chunk_len,
                                           in_flight, max_conc, h->d_ctx_tab, Dmax, desc->num_conditions, h->d_rec,
                                           h->d_chunk_start, h->d_item_scale, h->d_cond_scale,
-                                          hot_max > 32 ? 32 : hot_max, h->hot_flush, h->grid, h->d_hot_slot, h->d_hot_items, h->mem, &fb);
+                                          hot_max > 4096 / h->hot_stride ? 4096 / h->hot_stride : (hot_max > 32 ? 32 : hot_max), h->hot_flush, h->grid, h->d_hot_slot, h->d_hot_items, h->mem, &fb);
     if (fb.bad_index >= 0) {
       const int64_t n = fb.bad_index;
       fail(h, CARS_E_INVALID, "rating %lld has an id out of range (u=%d j=%d ctx=%d)", (long long)n, desc->u[n], desc->j[n],
@@ -686,7 +709,7 @@ static int copy_vec(cars_handle* h, bool to_device, double* dev, double* host, s
   return CARS_OK;
 }
 
-static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device) {
+static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device, bool skip_item_side = false) {
   if (!h) return CARS_E_INVALID;
   if (!a) return fail(h, CARS_E_INVALID, "arrays is NULL");
   if (h->epoch_pending) return fail(h, CARS_E_STATE, "an epoch is pending; call cars_epoch_wait first");
@@ -697,17 +720,20 @@ static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device) 
   const Item need[] = {{m.P, a->P, "P"}, {m.Q, a->Q, "Q"}, {m.user_bias, a->user_bias, "user_bias"},
                        {m.item_bias, a->item_bias, "item_bias"}, {m.cond_bias, a->cond_bias, "cond_bias"},
                        {m.ic_bias, a->ic_bias, "ic_bias"}, {m.uc_bias, a->uc_bias, "uc_bias"}};
-  for (const Item& it : need)
-    if (it.dev && !it.host) return fail(h, CARS_E_INVALID, "model array %s is required for this model but NULL", it.name);
+  for (const Item& it : need) {
+    const bool item_side = it.dev == m.Q || it.dev == m.item_bias || it.dev == m.cond_bias || it.dev == m.ic_bias;
+    if (it.dev && !it.host && !(skip_item_side && item_side))
+      return fail(h, CARS_E_INVALID, "model array %s is required for this model but NULL", it.name);
+  }
   int rc;
   std::vector<CopySeg> segs;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // the staged copies run on the copier's own streams
   if ((rc = copy_rows(h, to_device, m.P, a->P, U, m.F, m.Fp, &segs))) return rc;
-  if ((rc = copy_rows(h, to_device, m.Q, a->Q, I, m.F, m.Fp, &segs))) return rc;
+  if (!skip_item_side && (rc = copy_rows(h, to_device, m.Q, a->Q, I, m.F, m.Fp, &segs))) return rc;
   if (m.user_bias && (rc = copy_vec(h, to_device, m.user_bias, a->user_bias, U, &segs))) return rc;
-  if (m.item_bias && (rc = copy_vec(h, to_device, m.item_bias, a->item_bias, I, &segs))) return rc;
-  if (m.cond_bias && (rc = copy_vec(h, to_device, m.cond_bias, a->cond_bias, C, &segs))) return rc;
-  if (m.ic_bias && (rc = copy_vec(h, to_device, m.ic_bias, a->ic_bias, I * C, &segs))) return rc;
+  if (!skip_item_side && m.item_bias && (rc = copy_vec(h, to_device, m.item_bias, a->item_bias, I, &segs))) return rc;
+  if (!skip_item_side && m.cond_bias && (rc = copy_vec(h, to_device, m.cond_bias, a->cond_bias, C, &segs))) return rc;
+  if (!skip_item_side && m.ic_bias && (rc = copy_vec(h, to_device, m.ic_bias, a->ic_bias, I * C, &segs))) return rc;
   if (m.uc_bias && (rc = copy_vec(h, to_device, m.uc_bias, a->uc_bias, U * C, &segs))) return rc;
   CUDA_TRY(h, h->copier.run(segs.data(), (int)segs.size(), to_device));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // the strided (odd F) row copies
@@ -715,6 +741,7 @@ static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device) 
 }
 
 extern "C" int cars_upload(cars_handle* h, const cars_model_arrays* host) {
+  if (h && h->multi) return multi_transfer(h, host, true);
   int rc = transfer(h, host, true);
   if (rc == CARS_OK) h->uploaded = true;
   return rc;
@@ -722,6 +749,7 @@ extern "C" int cars_upload(cars_handle* h, const cars_model_arrays* host) {
 
 extern "C" int cars_download(cars_handle* h, const cars_model_arrays* host) {
   if (h && !h->uploaded) return fail(h, CARS_E_STATE, "cars_download before cars_upload");
+  if (h && h->multi) return multi_transfer(h, host, false);
   return transfer(h, host, false);
 }
 
@@ -730,6 +758,7 @@ extern "C" int cars_download(cars_handle* h, const cars_model_arrays* host) {
 // ------------------------------------------------------------------------------------------------
 extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
   if (!h) return CARS_E_INVALID;
+  if (h->multi) return fail(h, CARS_E_UNSUPPORTED, "a multi-GPU handle runs whole epochs: use cars_epoch");
   if (!h->uploaded) return fail(h, CARS_E_STATE, "cars_epoch before cars_upload");
   if (h->epoch_pending) return fail(h, CARS_E_STATE, "previous epoch not collected; call cars_epoch_wait");
   CUDA_TRY(h, cudaSetDevice(h->device));
@@ -825,6 +854,7 @@ extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
 
 extern "C" int cars_epoch_wait(cars_handle* h, double* loss_out) {
   if (!h) return CARS_E_INVALID;
+  if (h->multi) return fail(h, CARS_E_UNSUPPORTED, "a multi-GPU handle runs whole epochs: use cars_epoch");
   if (!h->epoch_pending) return fail(h, CARS_E_STATE, "no epoch pending");
   h->epoch_pending = false;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -854,7 +884,7 @@ static int item_parts(const cars_handle* h, ItemPart out[4]) {
 }
 
 extern "C" int cars_item_block_doubles(const cars_handle* h, int64_t* out) {
-  if (!h || !out) return CARS_E_INVALID;
+  if (!h || !out || h->multi) return CARS_E_INVALID;
   ItemPart parts[4];
   const int k = item_parts(h, parts);
   int64_t n = 0;
@@ -865,6 +895,7 @@ extern "C" int cars_item_block_doubles(const cars_handle* h, int64_t* out) {
 
 extern "C" int cars_epoch_sharded_begin(cars_handle* h, double lrate, double* dev_delta) {
   if (!h) return CARS_E_INVALID;
+  if (h->multi) return fail(h, CARS_E_UNSUPPORTED, "a multi-GPU handle exchanges its item block itself: use cars_epoch");
   if (!dev_delta) return fail(h, CARS_E_INVALID, "dev_delta is NULL");
   if (h->d.model == CARS_CAMF_C && !h->fast)
     return fail(h, CARS_E_UNSUPPORTED, "CAMF_C in EXACT mode is one chain through condBias; shard it in FAST mode");
@@ -895,8 +926,13 @@ extern "C" int cars_epoch_sharded_begin(cars_handle* h, double lrate, double* de
   return CARS_OK;
 }
 
-extern "C" int cars_epoch_sharded_finish(cars_handle* h, const double* dev_delta, double scale, double* loss_out) {
+__global__ void item_apply_rows_kernel(double* __restrict__ cur, const double* __restrict__ old, const double* __restrict__ sum,
+                                       const double* __restrict__ row_scale, int64_t row_len, int64_t n);  // multi_gpu.cuh
+
+// row_scale != nullptr: block <- old + row_scale[item] * sum (COMBINE_TOUCHED), else old + scale * sum
+static int sharded_finish_impl(cars_handle* h, const double* dev_delta, double scale, const double* row_scale, double* loss_out) {
   if (!h) return CARS_E_INVALID;
+  if (h->multi) return fail(h, CARS_E_UNSUPPORTED, "a multi-GPU handle exchanges its item block itself: use cars_epoch");
   if (!h->sharded_pending) return fail(h, CARS_E_STATE, "no sharded epoch pending");
   if (!dev_delta) return fail(h, CARS_E_INVALID, "dev_delta is NULL");
   CUDA_TRY(h, cudaSetDevice(h->device));
@@ -904,8 +940,13 @@ extern "C" int cars_epoch_sharded_finish(cars_handle* h, const double* dev_delta
   const int k = item_parts(h, parts);
   int64_t off = 0;
   const int blocks = h->sm_count * 8;
+  const int64_t I = h->d.num_items;
   for (int i = 0; i < k; i++) {
-    item_apply_kernel<<<blocks, 256, 0, h->stream>>>(parts[i].ptr, h->d_item_old + off, dev_delta + off, scale, parts[i].n);
+    const int64_t row_len = parts[i].n / (I > 0 ? I : 1);
+    if (row_scale && parts[i].ptr != h->m.cond_bias && row_len > 0)
+      item_apply_rows_kernel<<<blocks, 256, 0, h->stream>>>(parts[i].ptr, h->d_item_old + off, dev_delta + off, row_scale, row_len, parts[i].n);
+    else
+      item_apply_kernel<<<blocks, 256, 0, h->stream>>>(parts[i].ptr, h->d_item_old + off, dev_delta + off, scale, parts[i].n);
     CUDA_TRY(h, cudaGetLastError());
     h->st.kernel_launches += 1;
     off += parts[i].n;
@@ -914,7 +955,12 @@ extern "C" int cars_epoch_sharded_finish(cars_handle* h, const double* dev_delta
   return cars_epoch_wait(h, loss_out);
 }
 
+extern "C" int cars_epoch_sharded_finish(cars_handle* h, const double* dev_delta, double scale, double* loss_out) {
+  return sharded_finish_impl(h, dev_delta, scale, nullptr, loss_out);
+}
+
 extern "C" int cars_epoch(cars_handle* h, double lrate, double* loss_out) {
+  if (h && h->multi) return multi_epoch(h, lrate, loss_out);
   int rc = cars_epoch_begin(h, lrate);
   if (rc) return rc;
   return cars_epoch_wait(h, loss_out);
@@ -962,6 +1008,7 @@ extern "C" int cars_predict(cars_handle* h, int64_t n, const int32_t* u, const i
   if (h->epoch_pending) return fail(h, CARS_E_STATE, "an epoch is pending; call cars_epoch_wait first");
   if (n < 0 || (n > 0 && (!u || !j || !out))) return fail(h, CARS_E_INVALID, "bad predict arguments");
   if (n == 0) return CARS_OK;
+  if (h->multi) return multi_predict(h, n, u, j, ctx, bound, min_rate, max_rate, out);
   CUDA_TRY(h, cudaSetDevice(h->device));
   int32_t *du = nullptr, *dj = nullptr, *dc = nullptr;
   double* d_out = nullptr;
@@ -1033,6 +1080,9 @@ extern "C" int cars_rank_topn(cars_handle* h, int64_t num_queries, const int32_t
     return fail(h, CARS_E_INVALID, "NULL argument");
   if (num_cand > 0 && !cand) return fail(h, CARS_E_INVALID, "cand is NULL");
   if (num_queries == 0) return CARS_OK;
+  if (h->multi)
+    return multi_rank_topn(h, num_queries, qu, qc, num_cand, cand, rated_ptr, rated_items, bin_thold, num_recs, out_items,
+                           out_scores, out_count, out_kept);
   const int32_t I = h->d.num_items;
   for (int64_t q = 0; q < num_queries; q++)
     if ((unsigned)qu[q] >= (unsigned)h->d.num_users || (has_ctx && (unsigned)qc[q] >= (unsigned)h->d.num_contexts))
@@ -1136,8 +1186,11 @@ extern "C" int cars_rank_topn(cars_handle* h, int64_t num_queries, const int32_t
 // ------------------------------------------------------------------------------------------------
 // misc
 // ------------------------------------------------------------------------------------------------
+#include "multi_gpu.cuh"
+
 extern "C" void cars_destroy(cars_handle* h) {
   if (!h) return;
+  if (h->multi) { multi_destroy(h); return; }
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->mem.free(h->d_ctx_tab);
@@ -1161,10 +1214,26 @@ extern "C" const char* cars_last_error(const cars_handle* h) { return h ? h->err
 
 extern "C" int cars_get_stats(const cars_handle* h, cars_stats* out) {
   if (!h || !out) return CARS_E_INVALID;
+  if (h->multi) { multi_stats(h, out); return CARS_OK; }
   *out = h->st;
+  out->num_gpus = 1;
   return CARS_OK;
 }
 
 extern "C" void* cars_get_stream(const cars_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+extern "C" int cars_device_count(void) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int d = 0; d < ndev; d++) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+  }
+  return ok;
+}
 
 extern "C" const char* cars_version(void) { return "carskit_b200 abi 3, sm_100a, fp64 SGD (EXACT serial-equivalent / FAST hogwild), FM ALS, top-N"; }

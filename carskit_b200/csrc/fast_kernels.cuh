@@ -41,6 +41,12 @@ struct FastStream {
   int num_hot, hot_flush;
 };
 
+// One hot row in shared memory: [Fp factors | itemBias | pad | C icBias cells (CAMF_CI / CAMF_CUCI only)]
+template <int MODEL>
+__host__ __device__ __forceinline__ int hot_row_stride(int Fp, int C) {
+  return Fp + 2 + ((MODEL == M_CAMF_CI || MODEL == M_CAMF_CUCI) ? C : 0);
+}
+
 __device__ __forceinline__ double atomic_exch_shared_f64(double* p, double v) {
   return __longlong_as_double((long long)atomicExch(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__double_as_longlong(v)));
 }
@@ -119,6 +125,8 @@ __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastSt
   const int Fp = FIXF > 0 ? FIXF : m.Fp;
   const int Dmax = m.Dmax;
   const int u = rec.u, j = rec.j;
+  const int hstride = hot_row_stride<MODEL>(Fp, m.C);
+  double* srow = sh_hot + (o.slot >= 0 ? o.slot : 0) * hstride;  // (shared address space: ATOMS, not generic ATOM)
 
   // the user-side condition cell is read NOW (after the previous rating of this user stored it; same thread)
   double ucb = 0.0;
@@ -178,7 +186,7 @@ __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastSt
     if (kUserBias) lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_b, bu), bu));
     if (kItemBias) {
       const double step = __dmul_rn(lrj, __dsub_rn(e, __dmul_rn(m.reg_b, bj)));
-      if (o.slot >= 0) atomicAdd(sh_hot + o.slot * (Fp + 2) + Fp, step);
+      if (o.slot >= 0) atomicAdd(srow + Fp, step);
       else red_add_f64(m.item_bias + j, step);
       lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_b, bj), bj));
     }
@@ -186,7 +194,9 @@ __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastSt
   if (kHasCond) {
     if (o.cb_ptr != nullptr) {  // item-side cell (or condBias): reduction
       const double lrc = MODEL == M_CAMF_C ? __dmul_rn(lr, o.cscale) : lrj;
-      red_add_f64(o.cb_ptr, __dmul_rn(lrc, __dsub_rn(e, __dmul_rn(m.reg_c, o.cb))));
+      const double step = __dmul_rn(lrc, __dsub_rn(e, __dmul_rn(m.reg_c, o.cb)));
+      if (MODEL != M_CAMF_C && o.slot >= 0) atomicAdd(srow + Fp + 2 + o.cond, step);  // a hot item's icBias cell
+      else red_add_f64(o.cb_ptr, step);
       if (MODEL == M_CAMF_C) lane_loss = __dadd_rn(lane_loss, __dmul_rn(m.reg_b, o.cb));  // CAMF_C.java:115
       else lane_loss = __dadd_rn(lane_loss, __dmul_rn(m.reg_c, __dmul_rn(o.cb, o.cb)));
     }
@@ -202,7 +212,9 @@ __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastSt
           double* bp = MODEL == M_CAMF_C ? m.cond_bias + cond : m.ic_bias + (int64_t)j * m.C + cond;
           const double b = ld_cg_f64(bp);
           const double lrc = (MODEL == M_CAMF_C) ? __dmul_rn(lr, s.cond_scale ? __ldg(s.cond_scale + cond) : 1.0) : lrj;
-          red_add_f64(bp, __dmul_rn(lrc, __dsub_rn(e, __dmul_rn(m.reg_c, b))));
+          const double step = __dmul_rn(lrc, __dsub_rn(e, __dmul_rn(m.reg_c, b)));
+          if (MODEL != M_CAMF_C && o.slot >= 0) atomicAdd(srow + Fp + 2 + cond, step);
+          else red_add_f64(bp, step);
           lane_loss = __dadd_rn(lane_loss, MODEL == M_CAMF_C ? __dmul_rn(m.reg_b, b) : __dmul_rn(m.reg_c, __dmul_rn(b, b)));
         }
         if (kUserCond) {
@@ -220,7 +232,6 @@ __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastSt
   // ---- factor steps (both from the values read) -----------------------------------------------------------------
   // a hot item's steps go to the CTA's shared-memory accumulator row, everything else straight to L2
   double* qrow = m.Q + (int64_t)j * Fp;
-  double* srow = sh_hot + (o.slot >= 0 ? o.slot : 0) * (Fp + 2);  // (shared address space: ATOMS, not generic ATOM)
   double sp = 0.0, sq = 0.0;
 #pragma unroll
   for (int v = 0; v < V; v++) {
@@ -248,7 +259,7 @@ __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastSt
     bool flush = false;
     if (o.slot >= 0) {
       __syncwarp(gmask);
-      unsigned* cnt = reinterpret_cast<unsigned*>(sh_hot + s.num_hot * (Fp + 2));
+      unsigned* cnt = reinterpret_cast<unsigned*>(sh_hot + s.num_hot * hstride);
       unsigned c = 0;
       if (gl == 0) c = atomicAdd(cnt + o.slot, 1u) + 1u;
       c = __shfl_sync(gmask, c, 0, LPR);
@@ -262,6 +273,12 @@ __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastSt
       if (kItemBias && gl == 0) {
         const double v = atomic_exch_shared_f64(srow + Fp, 0.0);
         if (v != 0.0) red_add_f64(m.item_bias + j, v);
+      }
+      if (MODEL == M_CAMF_CI || MODEL == M_CAMF_CUCI) {
+        for (int c = gl; c < m.C; c += LPR) {
+          const double v = atomic_exch_shared_f64(srow + Fp + 2 + c, 0.0);
+          if (v != 0.0) red_add_f64(m.ic_bias + (int64_t)j * m.C + c, v);
+        }
       }
     }
   }
@@ -321,7 +338,8 @@ __global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sh_hot = reinterpret_cast<double*>(smem_raw);  // [num_hot x (Fp + 2)] accumulators, then num_hot counters
   constexpr int WARPS = THREADS / 32;
-  const int hot_words = s.hot_slot ? s.num_hot * ((FIXF > 0 ? FIXF : m.Fp) + 2) : 0;
+  const int hstride = hot_row_stride<MODEL>(FIXF > 0 ? FIXF : m.Fp, m.C);
+  const int hot_words = s.hot_slot ? s.num_hot * hstride : 0;
   if (s.hot_slot) {
     for (int i = threadIdx.x; i < hot_words + (s.num_hot + 1) / 2; i += THREADS) sh_hot[i] = 0.0;
     __syncthreads();
@@ -340,9 +358,10 @@ __global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, 
 #pragma unroll
   for (int v = 0; v < V; v++) us.p[v] = make_double2(0.0, 0.0);
   us.bu = 0.0;
-  RatingRec rec, recn;
+  RatingRec rec, recn, recn2;  // current, next (its operands are requested this turn), the one after (record in flight)
   rec.u = rec.j = rec.ctx = rec.ku = rec.kj = rec.pad = 0; rec.r = 0.0;
   recn = rec;
+  recn2 = rec;
   FastOps<V> cur, nxt;
 
   for (;;) {
@@ -361,6 +380,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, 
       }
       if (!done) {
         rec = ld_rec(s.rec + n);
+        if (n + 1 < end) recn = ld_rec(s.rec + n + 1);
         fast_load<MODEL, LPR, V, WIDE, FIXF>(m, s, rec, gl, cur);
         prev_u = -1;
       }
@@ -368,10 +388,10 @@ __global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, 
     if (__all_sync(0xffffffffu, done)) break;
     if (!done) {
       const bool has_next = n + 1 < end;
-      if (has_next) {  // the next rating's item-side operands fly during this rating's arithmetic
-        recn = ld_rec(s.rec + n + 1);
-        fast_load<MODEL, LPR, V, WIDE, FIXF>(m, s, recn, gl, nxt);
-      }
+      // the next rating's item-side operands fly during this rating's arithmetic; ITS record arrived a turn ago
+      // (records are requested two turns ahead, so that the row gather never waits for the record that addresses it)
+      if (has_next) fast_load<MODEL, LPR, V, WIDE, FIXF>(m, s, recn, gl, nxt);
+      if (n + 2 < end) recn2 = ld_rec(s.rec + n + 2);
       if (rec.u != prev_u) fast_load_user<MODEL, LPR, V, WIDE, FIXF>(m, rec.u, gl, us);
       acc = __dadd_rn(acc, fast_update<MODEL, LPR, V, WIDE, FIXF>(m, s, rec, lr, gl, gmask, us, cur, sh_hot));
       if (!has_next || recn.u != rec.u) fast_store_user<MODEL, LPR, V, WIDE, FIXF>(m, rec.u, gl, us);
@@ -379,6 +399,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, 
       if (has_next) {
         rec = recn;
         cur = nxt;
+        recn = recn2;
       }
       n++;
     }
@@ -399,10 +420,11 @@ __global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, 
     for (int i = threadIdx.x; i < hot_words; i += THREADS) {
       const double v = sh_hot[i];
       if (v == 0.0) continue;
-      const int slot = i / (Fp + 2), f = i % (Fp + 2);
+      const int slot = i / hstride, f = i % hstride;
       const int j = __ldg(s.hot_items + slot);
       if (f < Fp) red_add_f64(m.Q + (int64_t)j * Fp + f, v);
       else if (kItemBias && f == Fp) red_add_f64(m.item_bias + j, v);
+      else if ((MODEL == M_CAMF_CI || MODEL == M_CAMF_CUCI) && f >= Fp + 2) red_add_f64(m.ic_bias + (int64_t)j * m.C + (f - Fp - 2), v);
     }
   }
 }

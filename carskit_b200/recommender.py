@@ -117,7 +117,7 @@ class IterativeRecommender:
 
     def __init__(self, trainMatrix: TrainingSet, testMatrix: Optional[dict] = None, fold: int = -1,
                  conf: Optional[Dict[str, str]] = None, device: int = 0, stream: int = 0, world: int = 1,
-                 group=None, combine: str = "mean", mode: str = "exact", tuning: Optional[str] = None):
+                 group=None, combine: str = "mean", mode: str = "exact", tuning: Optional[str] = None, gpu_ids=None):
         """`world` > 1: this process is one rank of a user-range-sharded job (sharding.py); trainMatrix /
         testMatrix are THIS rank's shard and torch.distributed is initialised.  The engine then runs on
         torch's current CUDA stream so the all-reduce is ordered with the kernels."""
@@ -134,6 +134,9 @@ class IterativeRecommender:
             raise ValueError(f"engine.mode must be exact or fast, not {self.mode}")
         self.fastMaxConc = float(cf.get("engine.fast.max.conc", 0.0))
         self.tuning = tuning
+        # gpu_ids with more than one entry: ONE engine handle drives those GPUs from this process (cars_desc.num_gpus);
+        # `world` > 1 is the other route (one process per GPU, torch.distributed owns the collective)
+        self.gpu_ids = list(gpu_ids) if gpu_ids is not None else None
         self._torch_stream = None
         self.numUsers, self.numItems = trainMatrix.num_users, trainMatrix.num_items
         self.numConditions = trainMatrix.num_conditions
@@ -239,7 +242,8 @@ class IterativeRecommender:
         return capi.make_desc(self.trainMatrix, self.MODEL, self.numFactors, device=self.device,
                               reg_u=self.regU, reg_i=self.regI, reg_b=self.regB, reg_c=self.regC,
                               stream=self.stream, mode=capi.FAST if self.mode == "fast" else capi.EXACT,
-                              fast_max_conc=self.fastMaxConc, tuning=self.tuning)
+                              fast_max_conc=self.fastMaxConc, tuning=self.tuning, gpu_ids=self.gpu_ids,
+                              combine={"mean": capi.COMBINE_MEAN, "sum": capi.COMBINE_SUM, "touched": capi.COMBINE_TOUCHED}[self.combine])
 
     def open_engine(self) -> capi.Engine:
         """cars_create + cars_upload: what buildModel() does before its first iteration."""

@@ -6,11 +6,17 @@
  * On a box without an sm_100 GPU cars_create() fails with CARS_E_NO_DEVICE (there is no CPU path) and the client
  * says so and exits 3. */
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "carskit_b200.h"
 
-int main(void) {
+int main(int argc, char** argv) {
+  /* `c_client --gpus N`: ONE handle over N GPUs (cars_desc.num_gpus): users sharded by range inside the library,
+   * item block combined with NCCL inside cars_epoch -- the path a single JVM process uses. */
+  int gpus = 1;
+  for (int a = 1; a + 1 < argc; a++)
+    if (strcmp(argv[a], "--gpus") == 0) gpus = atoi(argv[a + 1]);
   /* ratings in the reference's iteration order: user-item pair id ascending, context id ascending */
   const int32_t u[] = {0, 0, 1, 1, 2, 2}, j[] = {0, 1, 0, 1, 0, 1}, ctx[] = {0, 1, 1, 0, 0, 1};
   const double r[] = {4, 5, 3, 4, 2, 5};
@@ -32,6 +38,10 @@ int main(void) {
   d.global_mean = 23.0 / 6.0;
   d.reg_u = d.reg_i = d.reg_b = (double)1e-4f; /* Java floats widened to double */
   d.reg_c = (double)1e-3f;
+  if (gpus > 1) {
+    d.num_gpus = gpus; /* gpu_ids = NULL: devices 0 .. gpus-1 */
+    d.combine = CARS_COMBINE_MEAN;
+  }
 
   cars_handle* h = NULL;
   int rc = cars_create(&d, &h);
@@ -49,7 +59,9 @@ int main(void) {
     printf("iter %d: loss = %.17g\n", iter, loss);
   }
   if ((rc = cars_download(h, &m)) != CARS_OK) { printf("cars_download: %s\n", cars_last_error(h)); return 1; }
-  printf("P[0][0] = %.17g, %s\n", P[0], cars_version());
+  cars_stats st;
+  cars_get_stats(h, &st);
+  printf("P[0][0] = %.17g, gpus = %d, %s\n", P[0], (int)st.num_gpus, cars_version());
   cars_destroy(h);
   return 0;
 }

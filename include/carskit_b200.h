@@ -206,7 +206,15 @@ int cars_rank_topn(cars_handle* h, int64_t num_queries, const int32_t* qu, const
                    const int32_t* cand, const int64_t* rated_ptr, const int32_t* rated_items, double bin_thold,
                    int32_t num_recs, int32_t* out_items, double* out_scores, int32_t* out_count, int32_t* out_kept);
 
-/* ---- multi-GPU: one process (and one handle) per GPU, users sharded by contiguous range ------------------
+/* ---- multi-GPU -------------------------------------------------------------------------------------------------
+ * Two ways in.  (1) cars_desc.num_gpus > 1: ONE handle drives N GPUs from the calling process -- what a JVM needs
+ * (CARSKit is one process, CARSKit.java:392-412).  cars_create shards the users by contiguous range over gpu_ids,
+ * cars_upload / cars_download address the caller's FULL arrays (user-side rows by offset), cars_epoch runs the shards'
+ * epochs concurrently and combines the item block with ncclAllReduce (NCCL is loaded at run time), cars_predict /
+ * cars_eval_ratings / cars_rank_topn route every query to the GPU that owns its user.  The entry points below this
+ * comment are NOT used then.  (2) One process and one single-GPU handle per GPU (torchrun, MPI): the caller owns the
+ * collective and uses the three entry points below.
+ * ---- (2) one process (and one handle) per GPU, users sharded by contiguous range ------------------
  * The reference is single-process; SURVEY.md 8e defines the sharded semantics: every rank trains the
  * ratings of ITS users against its own copy of the item-side arrays (Q, itemBias, icBias -- "the item
  * block"), then the ranks combine  item_block <- old + sum_over_ranks(new_rank - old)  once per epoch.
@@ -256,7 +264,8 @@ typedef struct cars_stats {
   double  fast_min_cond_scale;
   int64_t max_item_degree;
   int32_t fast_hot_rows;    /* FAST: item rows whose steps are summed per CTA in shared memory before they reach L2 */
-  int32_t reserved2;
+  int32_t num_gpus;         /* devices this handle drives (cars_desc.num_gpus) */
+  double  exchange_ms;      /* num_gpus > 1: device time of the last epoch's ncclAllReduce of the item block (shard 0) */
 } cars_stats;
 int cars_get_stats(const cars_handle* h, cars_stats* out);
 void* cars_get_stream(const cars_handle* h); /* cudaStream_t the kernels are launched on */
@@ -311,6 +320,10 @@ void cars_fm_destroy(cars_fm_handle* h);
 
 /* Library self-description: "carskit_b200 <abi> sm_100a ..." */
 const char* cars_version(void);
+
+/* Number of CUDA devices this library can train on (sm_100 only); 0 when there is none (then cars_create fails with
+ * CARS_E_NO_DEVICE).  Lets a caller spread cross-validation folds over the GPUs (java/carskit/b200/B200.devicesFor). */
+int cars_device_count(void);
 
 #ifdef __cplusplus
 }
