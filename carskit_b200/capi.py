@@ -68,7 +68,8 @@ EXPORTS = [
     "cars_epoch_sharded_finish", "cars_fm_create", "cars_fm_upload", "cars_fm_prepare", "cars_fm_iteration",
     "cars_fm_download", "cars_fm_predict", "cars_fm_get_stats", "cars_fm_last_error", "cars_fm_destroy",
     "cars_fm_exchange_doubles", "cars_fm_iteration_sharded", "cars_fm_get_stream", "cars_rank_topn",
-    "cars_device_count",
+    "cars_device_count", "cars_dataset_read_binary_csv", "cars_dataset_from_arrays", "cars_dataset_save", "cars_dataset_load",
+    "cars_dataset_kfold", "cars_dataset_get_view", "cars_dataset_free", "cars_dataset_last_error",
 ]
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
@@ -81,6 +82,14 @@ class CarsFmArrays(C.Structure):
 class CarsFmStats(C.Structure):
     _fields_ = [("nnz", C.c_int64), ("p", C.c_int64), ("pieces", C.c_int64), ("kernel_launches", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("last_iteration_ms", C.c_double)]
+
+
+class CarsDatasetView(C.Structure):
+    _fields_ = [("num_users", C.c_int32), ("num_items", C.c_int32), ("num_pairs", C.c_int32), ("num_contexts", C.c_int32),
+                ("num_conditions", C.c_int32), ("num_context_dims", C.c_int32), ("nnz", C.c_int64),
+                ("u", _i32p), ("j", _i32p), ("ctx", _i32p), ("pair", _i32p), ("r", _f64p), ("ctx_ptr", _i32p), ("ctx_cond", _i32p),
+                ("global_mean", C.c_double), ("min_rate", C.c_double), ("max_rate", C.c_double),
+                ("num_empty_conditions", C.c_int32), ("empty_conditions", _i32p)]
 
 
 class CarsError(RuntimeError):
@@ -164,6 +173,22 @@ def load_library(path: Optional[str] = None):
     lib.cars_version.restype = C.c_char_p
     lib.cars_device_count.argtypes = []
     lib.cars_device_count.restype = C.c_int
+    lib.cars_dataset_read_binary_csv.argtypes = [C.c_char_p, C.POINTER(H)]
+    lib.cars_dataset_read_binary_csv.restype = C.c_int
+    lib.cars_dataset_from_arrays.argtypes = [C.c_int32] * 5 + [C.c_int64, _i32p, _i32p, _i32p, _f64p, _i32p, _i32p, C.POINTER(H)]
+    lib.cars_dataset_from_arrays.restype = C.c_int
+    lib.cars_dataset_save.argtypes = [H, C.c_char_p]
+    lib.cars_dataset_save.restype = C.c_int
+    lib.cars_dataset_load.argtypes = [C.c_char_p, C.POINTER(H)]
+    lib.cars_dataset_load.restype = C.c_int
+    lib.cars_dataset_kfold.argtypes = [H, C.c_int32, C.c_int64, C.c_int32, C.POINTER(H), C.POINTER(H)]
+    lib.cars_dataset_kfold.restype = C.c_int
+    lib.cars_dataset_get_view.argtypes = [H, C.POINTER(CarsDatasetView)]
+    lib.cars_dataset_get_view.restype = C.c_int
+    lib.cars_dataset_free.argtypes = [H]
+    lib.cars_dataset_free.restype = None
+    lib.cars_dataset_last_error.argtypes = []
+    lib.cars_dataset_last_error.restype = C.c_char_p
     if path is None:
         _lib = lib
     return lib
@@ -492,6 +517,83 @@ class FmEngine:
 
     def __exit__(self, *exc):
         self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Dataset:
+    """cars_dataset: ratings held by the native library (csrc/ingest.cpp) -- DataDAO.readData, DataSplitter and the
+    columnar file without Python loops.  `training_set()` copies the columns into a TrainingSet for cars_desc."""
+
+    def __init__(self, handle):
+        self.lib = load_library()
+        self.h = handle
+
+    @classmethod
+    def _wrap(cls, lib, rc, h):
+        if rc != 0:
+            raise CarsError(rc, lib.cars_dataset_last_error().decode())
+        return cls(h)
+
+    @classmethod
+    def read_binary_csv(cls, path: str) -> "Dataset":
+        lib, h = load_library(), C.c_void_p()
+        return cls._wrap(lib, lib.cars_dataset_read_binary_csv(path.encode(), C.byref(h)), h)
+
+    @classmethod
+    def load(cls, path: str) -> "Dataset":
+        lib, h = load_library(), C.c_void_p()
+        return cls._wrap(lib, lib.cars_dataset_load(path.encode(), C.byref(h)), h)
+
+    @classmethod
+    def from_training_set(cls, ts: TrainingSet, num_context_dims: int = 0) -> "Dataset":
+        lib, h = load_library(), C.c_void_p()
+        rc = lib.cars_dataset_from_arrays(ts.num_users, ts.num_items, ts.num_conditions, ts.num_contexts, num_context_dims, ts.nnz,
+                                          _ptr_i32(ts.u), _ptr_i32(ts.j), _ptr_i32(ts.ctx), _ptr_f64(ts.r), _ptr_i32(ts.ctx_ptr),
+                                          _ptr_i32(ts.ctx_cond), C.byref(h))
+        return cls._wrap(lib, rc, h)
+
+    def save(self, path: str):
+        rc = self.lib.cars_dataset_save(self.h, path.encode())
+        if rc != 0:
+            raise CarsError(rc, self.lib.cars_dataset_last_error().decode())
+
+    def kfold(self, k: int, seed: int, fold: int):
+        tr, te = C.c_void_p(), C.c_void_p()
+        rc = self.lib.cars_dataset_kfold(self.h, k, seed, fold, C.byref(tr), C.byref(te))
+        if rc != 0:
+            raise CarsError(rc, self.lib.cars_dataset_last_error().decode())
+        return Dataset(tr), Dataset(te)
+
+    def view(self) -> CarsDatasetView:
+        v = CarsDatasetView()
+        self.lib.cars_dataset_get_view(self.h, C.byref(v))
+        return v
+
+    def training_set(self) -> TrainingSet:
+        v = self.view()
+        n = v.nnz
+
+        def arr(p, count, dt):
+            return np.ctypeslib.as_array(p, shape=(count,)).astype(dt, copy=True) if count and p else np.empty(0, dt)
+        has_ctx = bool(v.ctx)
+        ts = TrainingSet(num_users=v.num_users, num_items=v.num_items, u=arr(v.u, n, np.int32), j=arr(v.j, n, np.int32),
+                         r=arr(v.r, n, np.float64), ctx=arr(v.ctx, n, np.int32) if has_ctx else None,
+                         num_conditions=v.num_conditions, num_contexts=v.num_contexts,
+                         ctx_ptr=arr(v.ctx_ptr, v.num_contexts + 1, np.int32) if has_ctx else None,
+                         ctx_cond=arr(v.ctx_cond, int(v.ctx_ptr[v.num_contexts]) if v.num_contexts else 0, np.int32) if has_ctx else None,
+                         global_mean=v.global_mean, rating_scale=(v.min_rate, v.max_rate), num_context_dims=v.num_context_dims)
+        ts.pair_ids = arr(v.pair, n, np.int64)
+        return ts
+
+    def close(self):
+        if self.h:
+            self.lib.cars_dataset_free(self.h)
+            self.h = None
 
     def __del__(self):
         try:

@@ -318,6 +318,38 @@ void* cars_fm_get_stream(const cars_fm_handle* h);
 const char* cars_fm_last_error(const cars_fm_handle* h);
 void cars_fm_destroy(cars_fm_handle* h);
 
+/* ---- rating data: native ingest, k-fold split, columnar file (host code; csrc/ingest.cpp) ------------------------
+ * The arrays cars_desc takes, produced without the JVM holding the ratings in boxed Guava tables (DataDAO.java:174, 342):
+ *   cars_dataset_read_binary_csv  DataDAO.readData (DataDAO.java:199-354) over a binary-format ratings file: inner ids by
+ *                                 first appearance (users, items, user-item pairs, contexts), condition id = header column,
+ *                                 duplicates overwrite, zero ratings dropped, CRS order (pair id, context id)
+ *   cars_dataset_from_arrays      wraps arrays that are already in CRS order (e.g. synthetic data)
+ *   cars_dataset_save / _load     columnar file: one contiguous column per array, loads with one read per column
+ *   cars_dataset_kfold            DataSplitter (DataSplitter.java:68-133): fold labels from java.util.Random(seed),
+ *                                 fold k's label = its TEST set, the rest = training set, order kept
+ *   cars_dataset_get_view         the pointers / sizes to copy into a cars_desc (owned by the data set) */
+typedef struct cars_dataset cars_dataset;
+typedef struct cars_dataset_view {
+  int32_t num_users, num_items, num_pairs, num_contexts, num_conditions, num_context_dims;
+  int64_t nnz;
+  const int32_t *u, *j, *ctx, *pair; /* [nnz]; pair = CRS row (user-item pair id); ctx NULL for 2-D data */
+  const double* r;
+  const int32_t *ctx_ptr, *ctx_cond;
+  double global_mean, min_rate, max_rate; /* SparseMatrix.getGlobalAvg; first / last of rateDao.getRatingScale() */
+  int32_t num_empty_conditions;
+  const int32_t* empty_conditions;        /* rateDao.getEmptyContextConditions() (the "dim:na" columns) */
+} cars_dataset_view;
+int cars_dataset_read_binary_csv(const char* path, cars_dataset** out);
+int cars_dataset_from_arrays(int32_t num_users, int32_t num_items, int32_t num_conditions, int32_t num_contexts,
+                             int32_t num_context_dims, int64_t nnz, const int32_t* u, const int32_t* j, const int32_t* ctx,
+                             const double* r, const int32_t* ctx_ptr, const int32_t* ctx_cond, cars_dataset** out);
+int cars_dataset_save(const cars_dataset* d, const char* path);
+int cars_dataset_load(const char* path, cars_dataset** out);
+int cars_dataset_kfold(const cars_dataset* d, int32_t kfold, int64_t seed, int32_t fold, cars_dataset** train, cars_dataset** test);
+int cars_dataset_get_view(const cars_dataset* d, cars_dataset_view* out);
+void cars_dataset_free(cars_dataset* d);
+const char* cars_dataset_last_error(void);
+
 /* Library self-description: "carskit_b200 <abi> sm_100a ..." */
 const char* cars_version(void);
 

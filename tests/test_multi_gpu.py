@@ -170,9 +170,10 @@ def test_single_process_multi_gpu_touched_combine_and_fast_mode(oracle, cars_lib
     ref = {k: v.copy() for k, v in init.items()}
     desc = capi.make_desc(ts, capi.CAMF_CI, 8, **REGS)
     ref_losses = [oracle.epoch(desc, ref, capi.f32(0.02)) for _ in range(2)]
-    for k in ref:  # disjoint item sets: the sharded run IS the serial run
-        assert np.array_equal(got[k], ref[k]), k
-    np.testing.assert_allclose(losses, ref_losses, rtol=1e-11)
+    # disjoint item sets: the sharded run IS the serial run, up to the rounding of  old + (new - old)  in the exchange
+    for k in ref:
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-10, atol=1e-13, err_msg=k)
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-10)
     # FAST mode on two GPUs (CAMF_C too: its shared condBias joins the item block)
     for model in (capi.CAMF_CI, capi.CAMF_C):
         arrs = init_arrays(oracle, model, ts, 8, 4)
