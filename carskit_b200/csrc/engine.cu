@@ -477,7 +477,12 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     }
     h->num_chunks = nnz ? (nnz + chunk_len - 1) / chunk_len : 0;
     const double in_flight = (double)(h->num_chunks < total_groups ? h->num_chunks : total_groups);
-    const double max_conc = desc->fast_max_conc == 0.0 ? 8.0 : desc->fast_max_conc;
+    // Default cap on the expected number of concurrent updates of one shared row: 4.  c concurrent ratings add c stale
+    // steps at once, i.e. the row sees a learning rate of c * lr against a curvature of about |p|^2 + D + 1 (the row's
+    // factors, its D condition cells and its bias all move the same prediction); with the bold driver taking lr to ~0.05
+    // and curvature ~6, c * lr * curvature stays below the stability bound 2 for c <= 4 (8 was measured to diverge on
+    // the Frappe-shaped CAMF_C input after the bold driver had tripled lr).
+    const double max_conc = desc->fast_max_conc == 0.0 ? 4.0 : desc->fast_max_conc;
     CUDA_TRY_H(dev_alloc(&h->d_rec, (size_t)nnz));
     CUDA_TRY_H(dev_alloc(&h->d_chunk_start, (size_t)h->num_chunks + 1));
     CUDA_TRY_H(dev_alloc(&h->d_item_scale, I));
@@ -984,18 +989,27 @@ static int predict_device(cars_handle* h, int64_t n, const int32_t* u, const int
   CUDA_TRY(h, cudaMemcpyAsync(*dj_, j, n * 4, cudaMemcpyHostToDevice, h->stream));
   if (has_ctx) CUDA_TRY(h, cudaMemcpyAsync(*dc_, ctx, n * 4, cudaMemcpyHostToDevice, h->stream));
   h->st.h2d_bytes += n * (has_ctx ? 12 : 8);
+  // K5: a group of 8 lanes per query, coalesced 16-byte row loads, in-order dot through shared memory (sgd_kernels.cuh)
   const int threads = 256;
-  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  const int64_t groups = (int64_t)threads / 8;
+  int64_t want = (n + groups - 1) / groups;
+  const int64_t cap = (int64_t)h->sm_count * 16;
+  const unsigned blocks = (unsigned)(want < cap ? want : cap);
   DeviceModel m = h->m;
+  const size_t smem = (size_t)groups * (m.Fp + 2) * 8;
+#define CARS_PREDICT(M)                                                                                                \
+  CUDA_TRY(h, cudaFuncSetAttribute(predict_group_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  predict_group_kernel<M><<<blocks, threads, smem, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out)
   switch (h->d.model) {
-    case CARS_PMF: predict_kernel<M_PMF><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
-    case CARS_BIASEDMF: predict_kernel<M_BIASEDMF><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
-    case CARS_CAMF_C: predict_kernel<M_CAMF_C><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
-    case CARS_CAMF_CI: predict_kernel<M_CAMF_CI><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
-    case CARS_CAMF_CU: predict_kernel<M_CAMF_CU><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
-    case CARS_CAMF_CUCI: predict_kernel<M_CAMF_CUCI><<<blocks, threads, 0, h->stream>>>(m, n, *du_, *dj_, *dc_, bound, lo, hi, d_out); break;
+    case CARS_PMF: CARS_PREDICT(M_PMF); break;
+    case CARS_BIASEDMF: CARS_PREDICT(M_BIASEDMF); break;
+    case CARS_CAMF_C: CARS_PREDICT(M_CAMF_C); break;
+    case CARS_CAMF_CI: CARS_PREDICT(M_CAMF_CI); break;
+    case CARS_CAMF_CU: CARS_PREDICT(M_CAMF_CU); break;
+    case CARS_CAMF_CUCI: CARS_PREDICT(M_CAMF_CUCI); break;
     default: return fail(h, CARS_E_UNSUPPORTED, "predict: model %d", h->d.model);
   }
+#undef CARS_PREDICT
   CUDA_TRY(h, cudaGetLastError());
   h->st.kernel_launches += 1;
   return CARS_OK;
@@ -1161,8 +1175,13 @@ extern "C" int cars_rank_topn(cars_handle* h, int64_t num_queries, const int32_t
       h->st.kernel_launches += 1;
     }
     if (e == cudaSuccess) {
-      rank_select_kernel<<<(unsigned)nq, 256, 0, h->stream>>>(q0, nq, num_cand, d_cand, num_recs, d_keys, d_items, d_scores,
-                                                             d_count, d_kept);
+      if (num_recs <= kRankRegK) {  // one pass over the keys: per-thread top-k in registers, merged in shared memory
+        RK(cudaFuncSetAttribute(rank_select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kRankRegK * 12));
+        rank_select_topk_kernel<<<(unsigned)nq, 256, (size_t)256 * num_recs * 12, h->stream>>>(q0, nq, num_cand, d_cand, num_recs, d_keys,
+                                                                                               d_items, d_scores, d_count, d_kept);
+      } else
+        rank_select_kernel<<<(unsigned)nq, 256, 0, h->stream>>>(q0, nq, num_cand, d_cand, num_recs, d_keys, d_items, d_scores,
+                                                               d_count, d_kept);
       RK(cudaGetLastError());
       h->st.kernel_launches += 2;
     }

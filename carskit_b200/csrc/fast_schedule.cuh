@@ -274,7 +274,10 @@ inline cudaError_t build_fast_on_device(int32_t num_users, int32_t num_items, in
     fast_cond_degree_kernel<<<sm_count * 2, 256, use_smem ? (size_t)C * 4 : 0, stream>>>(d.ctx, nnz, d_ctx_tab, Dmax, C, use_smem,
                                                                                          d_cdeg);
     FB_TRY(cudaGetLastError());
-    fast_scale_kernel<unsigned long long><<<blocks, 256, 0, stream>>>(d_cdeg, C, (double)nnz, groups_in_flight, max_conc,
+    // CAMF_C: a rating moves Dmax condBias cells at once and all of them move the SAME prediction, so the shared
+    // vector as a whole sees Dmax times the concurrency of one cell: the cap is divided by Dmax
+    fast_scale_kernel<unsigned long long><<<blocks, 256, 0, stream>>>(d_cdeg, C, (double)nnz, groups_in_flight,
+                                                                      max_conc > 0.0 ? max_conc / (Dmax > 0 ? Dmax : 1) : max_conc,
                                                                       d_cond_scale, d_scal + 4, d_scal + 5);
     FB_TRY(cudaGetLastError());
     info->kernel_launches += 2;

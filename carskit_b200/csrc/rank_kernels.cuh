@@ -154,4 +154,93 @@ __global__ void __launch_bounds__(256) rank_select_kernel(int64_t q0, int64_t nq
   if (threadIdx.x == 0) out_count[q0 + q] = count;
 }
 
+// Single-pass selection for num_recs <= kRankRegK (the reference's default is 10): every thread keeps the num_recs best
+// (key, candidate) pairs of ITS strided share of the row in registers -- so the row of keys is read ONCE instead of
+// num_recs times -- then the CTA's 256 x num_recs survivors are merged in shared memory by num_recs rounds of
+// "largest key, lowest candidate index".  Same result as rank_select_kernel: the reference's stable descending sort.
+constexpr int kRankRegK = 16;
+
+__global__ void __launch_bounds__(256) rank_select_topk_kernel(int64_t q0, int64_t nq, int32_t num_cand, const int32_t* __restrict__ cand,
+                                                               int32_t num_recs, const unsigned long long* __restrict__ keys,
+                                                               int32_t* __restrict__ out_items, double* __restrict__ out_scores,
+                                                               int32_t* __restrict__ out_count, int32_t* __restrict__ out_kept) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* mk = reinterpret_cast<unsigned long long*>(smem_raw);  // [256 * num_recs] merged keys
+  int* mi = reinterpret_cast<int*>(mk + 256 * num_recs);                     // [256 * num_recs] candidate indices
+  __shared__ unsigned long long sk[8];
+  __shared__ int si[8], sp[8], skept[8];
+  const int64_t q = blockIdx.x;
+  if (q >= nq) return;
+  const unsigned long long* row = keys + q * num_cand;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long tk[kRankRegK];
+  int ti[kRankRegK];
+#pragma unroll
+  for (int k = 0; k < kRankRegK; k++) { tk[k] = kRankDropped; ti[k] = 0x7fffffff; }
+  int kept = 0;
+  for (int c = threadIdx.x; c < num_cand; c += 256) {
+    const unsigned long long key = __ldg(row + c);
+    if (key == kRankDropped) continue;
+    kept++;
+    if (key <= tk[num_recs - 1 < kRankRegK ? num_recs - 1 : kRankRegK - 1]) continue;  // not better than the thread's worst
+    // insertion after equal keys: this thread sees its candidates in ascending index order (stable)
+    unsigned long long ck = key;
+    int ci = c;
+#pragma unroll
+    for (int k = 0; k < kRankRegK; k++) {
+      if (k < num_recs && ck > tk[k]) {
+        const unsigned long long t = tk[k]; tk[k] = ck; ck = t;
+        const int u = ti[k]; ti[k] = ci; ci = u;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kRankRegK; k++)
+    if (k < num_recs) { mk[threadIdx.x * num_recs + k] = tk[k]; mi[threadIdx.x * num_recs + k] = ti[k]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kept += __shfl_down_sync(0xffffffffu, kept, o);
+  if (lane == 0) skept[warp] = kept;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int kt = 0;
+    for (int w = 0; w < 8; w++) kt += skept[w];
+    out_kept[q0 + q] = kt;  // itemScores.size()
+  }
+  const int total = 256 * num_recs;
+  int count = 0;
+  for (int round = 0; round < num_recs; round++) {
+    unsigned long long best = kRankDropped;
+    int bi = 0x7fffffff, bp = -1;
+    for (int p = threadIdx.x; p < total; p += 256) {
+      const unsigned long long k = mk[p];
+      const int i = mi[p];
+      if (k > best || (k == best && k != kRankDropped && i < bi)) { best = k; bi = i; bp = p; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ok = __shfl_down_sync(0xffffffffu, best, o);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+      const int op = __shfl_down_sync(0xffffffffu, bp, o);
+      if (ok > best || (ok == best && oi < bi)) { best = ok; bi = oi; bp = op; }
+    }
+    if (lane == 0) { sk[warp] = best; si[warp] = bi; sp[warp] = bp; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; w++)
+        if (sk[w] > sk[0] || (sk[w] == sk[0] && si[w] < si[0])) { sk[0] = sk[w]; si[0] = si[w]; sp[0] = sp[w]; }
+      if (sk[0] != kRankDropped) {
+        out_items[(q0 + q) * num_recs + round] = cand[si[0]];
+        const unsigned long long b = (sk[0] & 0x8000000000000000ull) ? (sk[0] & 0x7fffffffffffffffull) : ~sk[0];
+        out_scores[(q0 + q) * num_recs + round] = __longlong_as_double((long long)b);
+        mk[sp[0]] = kRankDropped;
+      }
+    }
+    __syncthreads();
+    if (sk[0] == kRankDropped) break;
+    count++;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out_count[q0 + q] = count;
+}
+
 }  // namespace cars

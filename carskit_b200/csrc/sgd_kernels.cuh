@@ -146,14 +146,15 @@ __device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 // Consumer side of the completion counters.  The producer publishes with the release pattern (fence.acq_rel.gpu, then
-// relaxed stores).  The PTX-formal acquire pattern on this side is one ld.acquire.gpu of the counter once the relaxed
-// poll has succeeded; it lowers to LDG.STRONG.GPU + CCTL.IVALL (an L1 invalidation per rating).  The default build
-// omits it: every model access of these kernels is ld/st.global.cg -- served by L2, the point of coherence, never by
-// L1 -- and is issued after the branch on the polled value resolves, i.e. after the counter load has returned from
-// L2, where the producer's row stores were performed before its fence completed.  -DCARS_STRICT_ACQUIRE builds the
-// formal variant (scripts/build_strict.sh; measured cost in DESIGN.md "Memory ordering").
+// relaxed stores).  Once the relaxed poll has succeeded, the lanes that polled re-read their counter with
+// ld.acquire.gpu: that load observes the released value (or a later one), so it synchronizes-with the producer's fence
+// -- the PTX-formal acquire pattern -- and the __syncwarp that follows extends the ordering to the group's other lanes
+// before any of them gathers the rows.  It lowers to LDG.STRONG.GPU + CCTL.IVALL, once per RATING (not per poll: the
+// spinning polls stay relaxed).  Measured cost at config 3: 40.38 ms/epoch against 40.28 ms without it
+// (profiles/r2/bench_r2_exact100M_relaxed_vs_acquire.txt), i.e. nothing, so it is unconditional.
+// -DCARS_RELAXED_POLL builds the variant without it (scripts/build_relaxed.sh), kept only to reproduce that A/B.
 __device__ __forceinline__ void acquire_after_poll(const unsigned* p, bool mine) {
-#ifdef CARS_STRICT_ACQUIRE
+#ifndef CARS_RELAXED_POLL
   if (mine) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -652,8 +653,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
 // Memory ordering: the producer stores its rows (st.global.cg), __syncwarp, then lane 0 issues ONE
 // fence.acq_rel.gpu (MEMBAR.ALL.GPU, cumulative over the group's stores) followed by the two relaxed counter
 // stores -- the release pattern for both counters.  The consumer polls with ld.relaxed.gpu and, after the branch
-// on the polled values and __syncwarp, reads the rows with ld.global.cg; see acquire_after_poll() for why the
-// default build does not add the L1-invalidating acquire, and for the strict build that does.
+// on the polled values, one ld.acquire.gpu of each counter (acquire_after_poll) and __syncwarp, reads the rows with
+// ld.global.cg: release pattern on one side, acquire pattern on the other.
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int LPR, int V, int THREADS, int MINB, bool WIDE = false, int FIXF = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -841,6 +842,54 @@ __device__ __forceinline__ double predict_from_dot(const DeviceModel& m, int u, 
     }
   }
   return pred;
+}
+
+// K5 (the kernel cars_predict launches): a group of 8 lanes per query.  The two factor rows are read with coalesced
+// 16-byte loads (a group covers 128 contiguous bytes per instruction) instead of one thread striding a whole row; the
+// products go through the group's shared-memory scratch and are summed in f = 0..F-1 order, so the value stays
+// bit-identical to DenseMatrix.rowMult.  Algorithmic bytes per query: 2 * F * 8 (rows) + 12 (ids) + 8 (out) + biases.
+template <int MODEL>
+__global__ void __launch_bounds__(256) predict_group_kernel(DeviceModel m, int64_t n, const int32_t* __restrict__ u,
+                                                            const int32_t* __restrict__ j, const int32_t* __restrict__ ctx, int bound,
+                                                            double min_rate, double max_rate, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int LPR = 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPR, gw = lane / LPR;
+  const unsigned gmask = ((1u << LPR) - 1u) << (gw * LPR);
+  double* prod = reinterpret_cast<double*>(smem_raw) + (size_t)(warp * 4 + gw) * (m.Fp + 2);
+  const int64_t groups = (int64_t)gridDim.x * 32;
+  const int nchunks = m.Fp / 2;
+  for (int64_t i0 = (int64_t)blockIdx.x * 32 + warp * 4; i0 < n; i0 += groups) {  // the 4 groups of a warp stay together
+    const int64_t i = i0 + gw;
+    const bool active = i < n;
+    int uu = 0, jj = 0, cc = 0;
+    if (active) {
+      uu = __ldg(u + i);
+      jj = __ldg(j + i);
+      cc = ctx ? __ldg(ctx + i) : 0;
+      const double* prow = m.P + (int64_t)uu * m.Fp;
+      const double* qrow = m.Q + (int64_t)jj * m.Fp;
+      for (int c = gl; c < nchunks; c += LPR) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(prow) + c);
+        const double2 b = __ldg(reinterpret_cast<const double2*>(qrow) + c);
+        *reinterpret_cast<double2*>(prod + 2 * c) = make_double2(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y));
+      }
+    }
+    __syncwarp();
+    if (active && gl == 0) {
+      double dot = 0.0;
+      for (int f = 0; f < m.F; f++) dot = __dadd_rn(dot, prod[f]);  // (the pad of an odd F is never added)
+      double pred = predict_from_dot<MODEL>(m, uu, jj, cc, dot);
+      if (bound) {
+        if (pred > max_rate) pred = max_rate;
+        if (pred < min_rate) pred = min_rate;
+      }
+      out[i] = pred;
+    }
+    __syncwarp();
+    (void)gmask;
+  }
 }
 
 template <int MODEL>

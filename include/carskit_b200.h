@@ -122,7 +122,7 @@ typedef struct cars_desc {
   void*   stream;           /* cudaStream_t to launch on; NULL = the handle creates its own */
   const int32_t* gpu_ids;   /* [num_gpus] CUDA ordinals; NULL = 0 .. num_gpus-1 */
   double  fast_max_conc;    /* FAST: cap on the expected number of concurrent updates of one shared row before
-                               its step is damped; 0 = default (8); < 0 = never damp */
+                               its step is damped; 0 = default (4); < 0 = never damp */
   const char* tuning;       /* developer knobs "key=value;key=value" (tests / profiling); NULL in normal use.
                                The library reads NO environment variable. */
   int32_t combine;          /* num_gpus > 1: enum cars_combine */
