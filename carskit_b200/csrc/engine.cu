@@ -8,6 +8,7 @@
 #include "schedule_gpu.cuh"
 #include "sgd_kernels.cuh"
 #include "fast_kernels.cuh"
+#include "tagged_kernels.cuh"
 #include "fast_schedule.cuh"
 #include "staged_copy.cuh"
 #include "rank_kernels.cuh"
@@ -69,6 +70,11 @@ struct cars_handle {
   bool dataflow = false;  // default schedule: reference order + per-user / per-item completion counters
   bool flagged = false;   // level order + completion counters (no barriers)
   bool fast = false;      // FAST mode: user-sorted chunks, item side by reductions (fast_kernels.cuh)
+  // K1t: the flagged schedule on tagged rows (tagged_kernels.cuh).  The model then lives in TWO layouts; each knows
+  // whether it is current, and whoever needs the other one converts (a streaming pass over the model: 0.2 ms at config 3)
+  bool tagged = false, std_valid = true, tagged_valid = false;
+  TaggedLayout tl;
+  TaggedModel tm{};
   double* d_item_scale = nullptr;  // FAST: per-item step damping [num_items]
   double* d_cond_scale = nullptr;  // FAST, CAMF_C: per-condition step damping [C]
   bool damp_items = false, damp_conds = false;
@@ -124,6 +130,7 @@ static cudaError_t dev_alloc_on(const DevMem& mem, T** p, size_t n) {
 }
 #define dev_alloc(ptr, n) dev_alloc_on(h->mem, ptr, n)  /* every call site has the handle `h` in scope */
 
+constexpr long long kTaggedDefault = 0;  // K1t is opt-in (tuning "tagged=1") until it has earned the default
 static bool model_has_ctx(int model);
 static int multi_create(const cars_desc* desc, cars_handle** out);
 static void multi_destroy(cars_handle* h);
@@ -165,6 +172,27 @@ static LaunchPlan pick_plan(int model, int Fp) {
     case CARS_CAMF_CI: return pick_wavefront<M_CAMF_CI>(Fp);
     case CARS_CAMF_CU: return pick_wavefront<M_CAMF_CU>(Fp);
     case CARS_CAMF_CUCI: return pick_wavefront<M_CAMF_CUCI>(Fp);
+  }
+  return LaunchPlan{};
+}
+
+// K1t instances: <row lengths in lines> that cover F <= 64 with up to 40 condition cells per row (config 3: 5 + 7 lines)
+// and F <= 128 with a scalar bias; anything longer keeps the counter kernel.
+template <int MODEL>
+static LaunchPlan pick_tagged(int lp, int lq, int ctas) {
+  LaunchPlan p;
+  p.threads = 256; p.lpr = 8; p.v = 0;
+  if (lp <= 5 && lq <= 7) p.fn = ctas == 2 ? (const void*)sgd_tagged_kernel<MODEL, 5, 7, 256, 2> : (const void*)sgd_tagged_kernel<MODEL, 5, 7, 256, 3>;
+  else if (lp <= 9 && lq <= 9) p.fn = (const void*)sgd_tagged_kernel<MODEL, 9, 9, 256, 2>;
+  return p;
+}
+static LaunchPlan pick_tagged_plan(int model, int lp, int lq, int ctas) {
+  switch (model) {
+    case CARS_PMF: return pick_tagged<M_PMF>(lp, lq, ctas);
+    case CARS_BIASEDMF: return pick_tagged<M_BIASEDMF>(lp, lq, ctas);
+    case CARS_CAMF_CI: return pick_tagged<M_CAMF_CI>(lp, lq, ctas);
+    case CARS_CAMF_CU: return pick_tagged<M_CAMF_CU>(lp, lq, ctas);
+    case CARS_CAMF_CUCI: return pick_tagged<M_CAMF_CUCI>(lp, lq, ctas);
   }
   return LaunchPlan{};
 }
@@ -440,6 +468,17 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     LaunchPlan plan = fast ? pick_fast_plan(model, Fp, F, shape)
                       : h->dataflow ? pick_dataflow_plan(model, Fp)
                       : h->flagged ? pick_flagged_plan(model, Fp, F, shape) : pick_plan(model, Fp);
+    if (h->flagged && h->tune.get_ll("tagged", kTaggedDefault) != 0 && !h->tune.is("levels", "host")) {
+      static const int kModelOf[] = {M_PMF, M_BIASEDMF, M_CAMF_C, M_CAMF_CI, M_CAMF_CU, -1, M_CAMF_CUCI};
+      h->tl = tagged_layout(kModelOf[model], F, has_ctx ? desc->num_conditions : 0);
+      LaunchPlan tp = pick_tagged_plan(model, h->tl.p_lines(), h->tl.q_lines(), (int)h->tune.get_ll("tagged_ctas", 3));
+      if (tp.fn) {
+        plan = tp;
+        h->tagged = true;
+        h->tm.lp = h->tl.p_lines();
+        h->tm.lq = h->tl.q_lines();
+      }
+    }
     h->plan = plan;
     if (!plan.fn) { fail(h, CARS_E_UNSUPPORTED, "no kernel for model %d mode %d F %d", model, desc->mode, F); return bail(CARS_E_UNSUPPORTED); }
     const int G = 32 / plan.lpr;
@@ -449,6 +488,10 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     h->hot_stride = Fp + 2 + ((model == CARS_CAMF_CI || model == CARS_CAMF_CUCI) ? desc->num_conditions : 0);
     const int hot_max = fast ? (4096 / h->hot_stride < 32 ? 4096 / h->hot_stride : 32) : 0;
     h->smem = fast ? (size_t)hot_max * h->hot_stride * 8 + (size_t)hot_max * 4 + 16 : (size_t)groups_per_cta * (Fp + 2) * 8;
+    if (h->tagged) {
+      const int extras = (h->tl.p_payload() - F) + (h->tl.q_payload() - F);
+      h->smem = (size_t)groups_per_cta * ((((F + extras + 1) & ~1) + 2) * 8);
+    }
     CUDA_TRY_H(cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     int per_sm = 0;
     CUDA_TRY_H(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, plan.threads, h->smem));
@@ -663,6 +706,10 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   if (model == CARS_CAMF_CI || model == CARS_CAMF_CUCI) CUDA_TRY_H(dev_alloc(&m.ic_bias, I * C));
   if (model == CARS_CAMF_CU || model == CARS_CAMF_CUCI) CUDA_TRY_H(dev_alloc(&m.uc_bias, U * C));
 
+  if (h->tagged) {
+    CUDA_TRY_H(dev_alloc(&h->tm.Pt, U * (size_t)h->tm.lp * 16));
+    CUDA_TRY_H(dev_alloc(&h->tm.Qt, I * (size_t)h->tm.lq * 16));
+  }
   CUDA_TRY_H(dev_alloc(&h->d_barrier, 1));
   CUDA_TRY_H(dev_alloc(&h->d_partial, (size_t)(h->grid > 1024 ? h->grid : 1024)));
   CUDA_TRY_H(dev_alloc(&h->d_loss, 1));
@@ -714,6 +761,28 @@ static int copy_vec(cars_handle* h, bool to_device, double* dev, double* host, s
   return CARS_OK;
 }
 
+// K1t keeps the model in tagged rows; every other consumer reads the standard layout.  Convert on demand.
+static int ensure_std(cars_handle* h) {
+  if (!h->tagged || h->std_valid) return CARS_OK;
+  const int blocks = h->sm_count * 8;
+  tagged_unpack_kernel<<<blocks, 256, 0, h->stream>>>(h->m, h->tl, h->tm, 0, (int64_t)h->d.num_users);
+  tagged_unpack_kernel<<<blocks, 256, 0, h->stream>>>(h->m, h->tl, h->tm, 1, (int64_t)h->d.num_items);
+  CUDA_TRY(h, cudaGetLastError());
+  h->st.kernel_launches += 2;
+  h->std_valid = true;
+  return CARS_OK;
+}
+static int ensure_tagged(cars_handle* h) {
+  if (!h->tagged || h->tagged_valid) return CARS_OK;
+  const int blocks = h->sm_count * 8;
+  tagged_pack_kernel<<<blocks, 256, 0, h->stream>>>(h->m, h->tl, h->tm, 0, (int64_t)h->d.num_users);
+  tagged_pack_kernel<<<blocks, 256, 0, h->stream>>>(h->m, h->tl, h->tm, 1, (int64_t)h->d.num_items);
+  CUDA_TRY(h, cudaGetLastError());
+  h->st.kernel_launches += 2;
+  h->tagged_valid = true;
+  return CARS_OK;
+}
+
 static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device, bool skip_item_side = false) {
   if (!h) return CARS_E_INVALID;
   if (!a) return fail(h, CARS_E_INVALID, "arrays is NULL");
@@ -732,6 +801,7 @@ static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device, 
   }
   int rc;
   std::vector<CopySeg> segs;
+  if (!to_device && (rc = ensure_std(h))) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // the staged copies run on the copier's own streams
   if ((rc = copy_rows(h, to_device, m.P, a->P, U, m.F, m.Fp, &segs))) return rc;
   if (!skip_item_side && (rc = copy_rows(h, to_device, m.Q, a->Q, I, m.F, m.Fp, &segs))) return rc;
@@ -742,6 +812,7 @@ static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device, 
   if (m.uc_bias && (rc = copy_vec(h, to_device, m.uc_bias, a->uc_bias, U * C, &segs))) return rc;
   CUDA_TRY(h, h->copier.run(segs.data(), (int)segs.size(), to_device));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // the strided (odd F) row copies
+  if (to_device) { h->std_valid = true; h->tagged_valid = false; }
   return CARS_OK;
 }
 
@@ -808,6 +879,15 @@ extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
     CUDA_TRY(h, cudaGetLastError());
     h->st.kernel_launches += 1;
     partials = h->loss_blocks;
+  } else if (h->flagged && h->tagged) {
+    int rc = ensure_tagged(h);  // (the conversion is part of the epoch it serves: inside the timed region)
+    if (rc) return rc;
+    const RatingRec* recs = h->d_rec;
+    int64_t nnz = h->nnz;
+    void* args[] = {&m, &h->tl, &h->tm, &recs, &nnz, &lrate, &h->d_partial};
+    CUDA_TRY(h, cudaLaunchCooperativeKernel(h->plan.fn, dim3(h->grid), dim3(h->block), args, h->smem, h->stream));
+    h->st.kernel_launches += 1;
+    h->std_valid = false;
   } else if (h->flagged) {
     const LaunchPlan& plan = h->plan;
     CUDA_TRY(h, cudaMemsetAsync(h->d_flags, 0, h->flags_words * sizeof(unsigned), h->stream));
@@ -907,6 +987,8 @@ extern "C" int cars_epoch_sharded_begin(cars_handle* h, double lrate, double* de
   if (h->sharded_pending) return fail(h, CARS_E_STATE, "previous sharded epoch not finished");
   if (!h->uploaded) return fail(h, CARS_E_STATE, "cars_epoch before cars_upload");
   CUDA_TRY(h, cudaSetDevice(h->device));
+  int rcs = ensure_std(h);
+  if (rcs) return rcs;
   ItemPart parts[4];
   const int k = item_parts(h, parts);
   int64_t total = 0;
@@ -919,6 +1001,7 @@ extern "C" int cars_epoch_sharded_begin(cars_handle* h, double lrate, double* de
   }
   int rc = cars_epoch_begin(h, lrate);
   if (rc) return rc;
+  if ((rc = ensure_std(h))) return rc;  // K1t trained the tagged rows: the delta is taken on the standard layout
   off = 0;
   const int blocks = h->sm_count * 8;
   for (int i = 0; i < k; i++) {
@@ -957,6 +1040,7 @@ static int sharded_finish_impl(cars_handle* h, const double* dev_delta, double s
     off += parts[i].n;
   }
   h->sharded_pending = false;
+  h->tagged_valid = false;  // the item block changed in the standard layout
   return cars_epoch_wait(h, loss_out);
 }
 
@@ -978,6 +1062,8 @@ static int predict_device(cars_handle* h, int64_t n, const int32_t* u, const int
                           int bound, double lo, double hi, double* d_out, int32_t** du_, int32_t** dj_, int32_t** dc_) {
   const bool has_ctx = model_has_ctx(h->d.model);
   if (has_ctx && !ctx) return fail(h, CARS_E_INVALID, "ctx is required for this model");
+  int rce = ensure_std(h);
+  if (rce) return rce;
   for (int64_t i = 0; i < n; i++)
     if ((unsigned)u[i] >= (unsigned)h->d.num_users || (unsigned)j[i] >= (unsigned)h->d.num_items ||
         (has_ctx && (unsigned)ctx[i] >= (unsigned)h->d.num_contexts))
@@ -1117,6 +1203,10 @@ extern "C" int cars_rank_topn(cars_handle* h, int64_t num_queries, const int32_t
   for (int64_t q = 0; q < num_queries; q++) { out_count[q] = 0; out_kept[q] = 0; }
   if (num_cand == 0) return CARS_OK;
   CUDA_TRY(h, cudaSetDevice(h->device));
+  {
+    int rce = ensure_std(h);
+    if (rce) return rce;
+  }
 
   int32_t *d_qu = nullptr, *d_qc = nullptr, *d_cand = nullptr, *d_cidx = nullptr, *d_rated = nullptr, *d_items = nullptr,
           *d_count = nullptr, *d_kept = nullptr;
@@ -1219,6 +1309,7 @@ extern "C" void cars_destroy(cars_handle* h) {
   h->mem.free(h->d_rec); h->mem.free(h->d_chunk_start); h->mem.free(h->d_chunk_loss); h->mem.free(h->d_flags);
   h->mem.free(h->d_item_old); h->mem.free(h->d_item_scale); h->mem.free(h->d_cond_scale);
   h->mem.free(h->d_hot_slot); h->mem.free(h->d_hot_items);
+  h->mem.free(h->tm.Pt); h->mem.free(h->tm.Qt);
   h->mem.free(h->d_barrier); h->mem.free(h->d_partial); h->mem.free(h->d_loss);
   if (h->stream) cudaStreamSynchronize(h->stream);  // the pool's frees are stream-ordered
   if (h->h_loss) cudaFreeHost(h->h_loss);

@@ -43,12 +43,16 @@ __global__ void __launch_bounds__(256) iota_kernel(uint32_t* v, int64_t n) {
 // Records are packed in reference order first (coalesced reads of the six arrays), then moved to level order as
 // whole 32-byte records: one DRAM sector per rating instead of six scattered 4 / 8-byte reads (measured
 // 710 B of DRAM reads per rating before, profiles/r1/launches_r1b_default.txt).
-__global__ void __launch_bounds__(256) pack_recs_kernel(RatingSoA s, int64_t n, RatingRec* __restrict__ out) {
+// succ (may be null): the next rating of the same user / item, or -1 -- packed into `pad` as "last of its user" (bit 0)
+// and "last of its item" (bit 1), which the tagged kernel uses to hand the row back with tag 0 for the next epoch
+__global__ void __launch_bounds__(256) pack_recs_kernel(RatingSoA s, int64_t n, RatingRec* __restrict__ out,
+                                                        const int32_t* __restrict__ succ = nullptr) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
     RatingRec x;
     x.u = s.u[k]; x.j = s.j[k]; x.ctx = s.ctx ? s.ctx[k] : 0; x.ku = s.ku ? s.ku[k] : 0;
-    x.kj = s.kj ? s.kj[k] : 0; x.pad = 0; x.r = s.r[k];
+    x.kj = s.kj ? s.kj[k] : 0; x.r = s.r[k];
+    x.pad = succ ? ((succ[2 * k] < 0 ? 1 : 0) | (succ[2 * k + 1] < 0 ? 2 : 0)) : 0;
     out[k] = x;
   }
 }
@@ -416,7 +420,7 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
     SG_TRY(cub::DeviceRadixSort::SortPairs(d_temp, tb, (const uint32_t*)d.level, d_skey, d_idx, d_ord, nnz, 0,
                                            bits_for(info->num_levels + 1), stream));
   }
-  pack_recs_kernel<<<blocks, 256, 0, stream>>>(d, nnz, d_tmp_rec);
+  pack_recs_kernel<<<blocks, 256, 0, stream>>>(d, nnz, d_tmp_rec, host_levels ? nullptr : d_succ);
   SG_TRY(cudaGetLastError());
   gather_recs_kernel<<<blocks, 256, 0, stream>>>(d_tmp_rec, d_ord, nnz, d_rec);
   SG_TRY(cudaGetLastError());

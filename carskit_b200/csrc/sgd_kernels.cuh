@@ -567,6 +567,17 @@ __device__ __forceinline__ RatingRec ld_rec(const RatingRec* p) {
   return x;
 }
 
+// as ld_rec, keeping the `pad` word (flags of the tagged kernel: last rating of its user / item in the epoch)
+__device__ __forceinline__ RatingRec ld_rec_pad(const RatingRec* p) {
+  const int4 a = __ldg(reinterpret_cast<const int4*>(p));
+  const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+  RatingRec x;
+  x.u = a.x; x.j = a.y; x.ctx = a.z; x.ku = a.w;
+  x.kj = b.x; x.pad = b.y;
+  x.r = __hiloint2double(b.w, b.z);
+  return x;
+}
+
 template <int MODEL, int LPR, int V, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
     sgd_dataflow_kernel(DeviceModel m, DataflowStream s, double lr) {

@@ -22,8 +22,8 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "sgd_golden.json")
 CTX_MODELS = (capi.CAMF_C, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI)
 
 
-def run_both(oracle, model, ts, F, epochs, seed, mode=capi.EXACT, lr0=capi.f32(0.02), schedule=capi.SCHED_FLAGGED):
-    desc = capi.make_desc(ts, model, F, mode=mode, schedule=schedule, **REGS)
+def run_both(oracle, model, ts, F, epochs, seed, mode=capi.EXACT, lr0=capi.f32(0.02), schedule=capi.SCHED_FLAGGED, tuning=None):
+    desc = capi.make_desc(ts, model, F, mode=mode, schedule=schedule, tuning=tuning, **REGS)
     ref = init_arrays(oracle, model, ts, F, seed)
     got = {k: v.copy() for k, v in ref.items()}
     ref_losses, got_losses = [], []
@@ -418,3 +418,37 @@ def test_fm_engine_within_1e5_of_the_reference_bytecode_vector(oracle, cars_lib)
         pred = eng.predict(test["u"], test["j"], test["ctx"], bound=True, min_rate=1.0, max_rate=5.0)
     want = np.array([float.fromhex(x) for x in case["pred_hex"]])
     assert np.max(np.abs(pred - want)) < 1e-5  # the north star's bar for predicted ratings (sums in another order)
+
+
+# ---- K1t: the flagged schedule on tagged rows (csrc/tagged_kernels.cuh, tuning "tagged=1") -------------------------------
+@pytest.mark.parametrize("model", [capi.PMF, capi.BIASEDMF, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI])
+@pytest.mark.parametrize("F", [1, 7, 10, 15, 16, 32, 64, 100, 128])
+@pytest.mark.parametrize("ctas", [2, 3])
+def test_tagged_rows_bit_identical(oracle, cars_lib, model, F, ctas):
+    dims = [4, 3, 2] if model in CTX_MODELS else None
+    ts, test = synth.make_training_set(500, 120, dims, 20000, seed=F, order="user_sorted", holdout=0.1)
+    ref, got, rl, gl, st = run_both(oracle, model, ts, F, epochs=3, seed=F + 1, tuning=f"tagged=1;tagged_ctas={ctas}")
+    assert_bit_identical(ref, got)
+    np.testing.assert_allclose(gl, rl, rtol=LOSS_RTOL, atol=0)
+
+
+@pytest.mark.parametrize("order,users,items,nnz,zipf,dims", [("shuffled", 3000, 2000, 100000, 1.0, [8, 8, 8, 8]), ("user_sorted", 1, 300, 300, 0.0, [3, 3]),
+                                                             ("user_sorted", 4000, 3, 9000, 0.0, [2] * 10), ("shuffled", 20000, 5000, 600000, 0.0, [8, 8, 8, 8])])
+def test_tagged_rows_on_chains_skew_and_many_dimensions(oracle, cars_lib, order, users, items, nnz, zipf, dims):
+    ts, test = synth.make_training_set(users, items, dims, nnz, seed=3, order=order, item_zipf=zipf, holdout=0.05)
+    for model in (capi.CAMF_CI, capi.CAMF_CU):
+        F = 64 if sum(dims) <= 32 else 16
+        desc = capi.make_desc(ts, model, F, tuning="tagged=1", **REGS)
+        ref = init_arrays(oracle, model, ts, F, 9)
+        got = {k: v.copy() for k, v in ref.items()}
+        with capi.Engine(desc, keepalive=ts) as eng:
+            eng.upload(got)
+            for it in range(4):  # several epochs through the same handle: every row's tag must be back at 0 each time
+                lg = eng.epoch(capi.f32(0.02))
+                lo = oracle.epoch(desc, ref, capi.f32(0.02))
+                np.testing.assert_allclose(lg, lo, rtol=LOSS_RTOL)
+                if it == 1:  # predictions in the middle of training come from the standard layout (converted on demand)
+                    p = eng.predict(test["u"], test["j"], test["ctx"], bound=True, min_rate=1.0, max_rate=5.0)
+                    assert np.array_equal(p, oracle.predict(desc, ref, test["u"], test["j"], test["ctx"], bound=True, min_rate=1.0, max_rate=5.0))
+            eng.download(got)
+        assert_bit_identical(ref, got)
