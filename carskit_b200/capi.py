@@ -13,12 +13,12 @@ from typing import Optional
 import numpy as np
 
 ABI_VERSION = 3
-PMF, BIASEDMF, CAMF_C, CAMF_CI, CAMF_CU, FM, CAMF_CUCI = range(7)
+PMF, BIASEDMF, CAMF_C, CAMF_CI, CAMF_CU, FM, CAMF_CUCI, CAMF_ICS = range(8)
 EXACT, FAST = 0, 1
 SCHED_FLAGGED, SCHED_WAVEFRONT, SCHED_DATAFLOW = 0, 1, 2
 COMBINE_MEAN, COMBINE_SUM, COMBINE_TOUCHED = 0, 1, 2
 MODEL_NAMES = {"pmf": PMF, "biasedmf": BIASEDMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM,
-               "camf_cuci": CAMF_CUCI}
+               "camf_cuci": CAMF_CUCI, "camf_ics": CAMF_ICS}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # CARSKIT_B200_LIB selects another build of the same ABI (e.g. the developer build with stage tracing)
@@ -40,12 +40,12 @@ class CarsDesc(C.Structure):
         ("reg_lw", C.c_double), ("reg_lf", C.c_double),
         ("num_context_dims", C.c_int32), ("num_gpus", C.c_int32), ("global_nnz", C.c_int64),
         ("stream", C.c_void_p), ("gpu_ids", _i32p), ("fast_max_conc", C.c_double), ("tuning", C.c_char_p),
-        ("combine", C.c_int32), ("reserved1", C.c_int32),
+        ("combine", C.c_int32), ("num_empty_conditions", C.c_int32), ("empty_conditions", _i32p),
     ]
 
 
 class CarsModelArrays(C.Structure):
-    _fields_ = [(n, _f64p) for n in ("P", "Q", "user_bias", "item_bias", "cond_bias", "ic_bias", "uc_bias")]
+    _fields_ = [(n, _f64p) for n in ("P", "Q", "user_bias", "item_bias", "cond_bias", "ic_bias", "uc_bias", "cc_sim")]
 
 
 class CarsStats(C.Structure):
@@ -233,6 +233,8 @@ class TrainingSet:
     # rateDao.numContextDims() (FM.java:86); None / 0 when the arrays did not come through the loader
     rating_scale: Optional[tuple] = None
     num_context_dims: int = 0
+    # rateDao.getEmptyContextConditions(): the "dim:na" condition id of every context dimension (CAMF_ICS)
+    empty_conditions: Optional[np.ndarray] = None
 
     def __post_init__(self):
         self.u = np.ascontiguousarray(self.u, dtype=np.int32)
@@ -273,7 +275,15 @@ def make_desc(ts: TrainingSet, model: int, num_factors: int, *, mode: int = EXAC
     d.num_factors = num_factors
     d.nnz = ts.nnz
     d.u, d.j, d.r = _ptr_i32(ts.u), _ptr_i32(ts.j), _ptr_f64(ts.r)
-    use_ctx = model in (CAMF_C, CAMF_CI, CAMF_CU, CAMF_CUCI, FM) and ts.ctx is not None
+    use_ctx = model in (CAMF_C, CAMF_CI, CAMF_CU, CAMF_CUCI, FM, CAMF_ICS) and ts.ctx is not None
+    if model == CAMF_ICS:
+        ec = getattr(ts, "empty_conditions", None)
+        if ec is None:
+            raise ValueError("CAMF_ICS needs TrainingSet.empty_conditions (rateDao.getEmptyContextConditions())")
+        ec = np.ascontiguousarray(ec, dtype=np.int32)
+        d._empty_keep = ec
+        d.empty_conditions = _ptr_i32(ec)
+        d.num_empty_conditions = len(ec)
     d.ctx = _ptr_i32(ts.ctx) if use_ctx else None
     d.ctx_ptr = _ptr_i32(ts.ctx_ptr) if use_ctx else None
     d.ctx_cond = _ptr_i32(ts.ctx_cond) if use_ctx else None
@@ -292,6 +302,7 @@ MODEL_MEMBERS = {
     CAMF_CI: ("P", "Q", "user_bias", "ic_bias"),
     CAMF_CU: ("P", "Q", "item_bias", "uc_bias"),
     CAMF_CUCI: ("P", "Q", "ic_bias", "uc_bias"),
+    CAMF_ICS: ("P", "Q", "cc_sim"),
 }
 
 
@@ -299,7 +310,7 @@ def member_shapes(model: int, num_users: int, num_items: int, num_conditions: in
     all_shapes = {
         "P": (num_users, F), "Q": (num_items, F), "user_bias": (num_users,), "item_bias": (num_items,),
         "cond_bias": (num_conditions,), "ic_bias": (num_items, num_conditions),
-        "uc_bias": (num_users, num_conditions),
+        "uc_bias": (num_users, num_conditions), "cc_sim": (num_conditions, num_conditions),
     }
     return {k: all_shapes[k] for k in MODEL_MEMBERS[model]}
 

@@ -18,7 +18,7 @@
 
 namespace cars {
 
-enum : int { M_PMF = 0, M_BIASEDMF = 1, M_CAMF_C = 2, M_CAMF_CI = 3, M_CAMF_CU = 4, M_CAMF_CUCI = 5 };
+enum : int { M_PMF = 0, M_BIASEDMF = 1, M_CAMF_C = 2, M_CAMF_CI = 3, M_CAMF_CU = 4, M_CAMF_CUCI = 5, M_CAMF_ICS = 6 };
 
 // Device-resident state shared by all kernels.  Plain pointers into the handle's allocations.
 struct DeviceModel {
@@ -30,6 +30,8 @@ struct DeviceModel {
   double* ic_bias;    // [num_items x C]
   double* uc_bias;    // [num_users x C]
   const int32_t* ctx_tab;  // [num_contexts x Dmax] condition ids, -1 padded
+  double* cc_sim;             // CAMF_ICS: [C x C], the (max, min) cell of every unordered pair is the live one (SymmMatrix)
+  const int32_t* empty_cond;  // CAMF_ICS: [Dmax] the "na" condition of every dimension (EmptyContextConditions)
   int32_t F, Fp, C, Dmax;
   double global_mean;
   double reg_u, reg_i, reg_b, reg_c;
@@ -545,6 +547,95 @@ __global__ void __launch_bounds__(32, 1)
   if (lane == 0) block_partial[0] = acc;
 }
 
+// K1s-ICS: CAMF_ICS.buildModel (sim/CAMF_ICS.java:62-124), one warp in reference order.  Every rating reads and rewrites
+// cells of the ONE condition-similarity matrix all ratings share (like CAMF_C's condBias), so EXACT mode is a single chain:
+//   dot = P[u].Q[j];  pred = dot;  simc = 1
+//   for i: sim = (cond_i != empty_i) ? cc(cond_i, empty_i) : 1;  [simc *= sim];  loss += regC*sim*sim;  pred = pred*sim
+//   e = r - pred
+//   for the cells read:  cc = sim + lr * (e*dot*simc/sim - regC*sim)
+//   P[u][f] += lr * (e*q*simc - regU*p);  Q[j][f] += lr * (e*p*simc - regI*q)
+template <int V>
+__global__ void __launch_bounds__(32, 1)
+    sgd_serial_ics_kernel(DeviceModel m, RatingStream s, int64_t nnz, double lr, double* block_partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* prod = reinterpret_cast<double*>(smem_raw);
+  const int lane = threadIdx.x;
+  const int Fp = m.Fp, Dmax = m.Dmax;
+  double acc = 0.0;
+  for (int64_t n = 0; n < nnz; n++) {
+    const int u = __ldg(s.u + n), j = __ldg(s.j + n), ctx = __ldg(s.ctx + n);
+    const double r = __ldg(s.r + n);
+    double* prow = m.P + (int64_t)u * Fp;
+    double* qrow = m.Q + (int64_t)j * Fp;
+    double2 p[V], q[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const int c = lane + v * 32;
+      if (2 * c < Fp) {
+        p[v] = *reinterpret_cast<const double2*>(prow + 2 * c);
+        q[v] = *reinterpret_cast<const double2*>(qrow + 2 * c);
+        *reinterpret_cast<double2*>(prod + 2 * c) = make_double2(__dmul_rn(p[v].x, q[v].x), __dmul_rn(p[v].y, q[v].y));
+      }
+    }
+    __syncwarp();
+    double dot = 0.0;
+    for (int f = 0; f < m.F; f++) dot = __dadd_rn(dot, prod[f]);
+    __syncwarp();
+    double pred = dot, simc = 1.0, lane_loss = 0.0;
+    for (int d = 0; d < Dmax; d++) {  // warp-uniform: every lane reads the same cells
+      const int cond = __ldg(m.ctx_tab + (int64_t)ctx * Dmax + d);
+      if (cond < 0) continue;
+      const int e2 = __ldg(m.empty_cond + d);
+      double sim = 1.0;
+      if (cond != e2) {
+        const int hi = cond >= e2 ? cond : e2, lo = cond >= e2 ? e2 : cond;
+        sim = m.cc_sim[(int64_t)hi * m.C + lo];
+        simc = __dmul_rn(simc, sim);
+      }
+      if (lane == 0) lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_c, sim), sim));
+      pred = __dmul_rn(pred, sim);
+    }
+    const double e = __dsub_rn(r, pred);
+    if (lane == 0) lane_loss = __dadd_rn(lane_loss, __dmul_rn(e, e));
+    __syncwarp();  // every lane has read the similarity cells before lane 0 rewrites them
+    if (lane == 0) {
+      for (int d = 0; d < Dmax; d++) {
+        const int cond = __ldg(m.ctx_tab + (int64_t)ctx * Dmax + d);
+        if (cond < 0) continue;
+        const int e2 = __ldg(m.empty_cond + d);
+        if (cond == e2) continue;
+        const int hi = cond >= e2 ? cond : e2, lo = cond >= e2 ? e2 : cond;
+        double* cell = m.cc_sim + (int64_t)hi * m.C + lo;
+        const double sim = *cell;  // (the cells of one rating are distinct: still the value read above)
+        const double t = __dsub_rn(__ddiv_rn(__dmul_rn(__dmul_rn(e, dot), simc), sim), __dmul_rn(m.reg_c, sim));
+        *cell = __dadd_rn(sim, __dmul_rn(lr, t));
+      }
+    }
+    double sp = 0.0, sq = 0.0;
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const int c = lane + v * 32;
+      if (2 * c < Fp) {
+        const double2 po = p[v], qo = q[v];
+        double2 pn, qn;
+        pn.x = __dadd_rn(po.x, __dmul_rn(lr, __dsub_rn(__dmul_rn(__dmul_rn(e, qo.x), simc), __dmul_rn(m.reg_u, po.x))));
+        qn.x = __dadd_rn(qo.x, __dmul_rn(lr, __dsub_rn(__dmul_rn(__dmul_rn(e, po.x), simc), __dmul_rn(m.reg_i, qo.x))));
+        pn.y = __dadd_rn(po.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(__dmul_rn(e, qo.y), simc), __dmul_rn(m.reg_u, po.y))));
+        qn.y = __dadd_rn(qo.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(__dmul_rn(e, po.y), simc), __dmul_rn(m.reg_i, qo.y))));
+        *reinterpret_cast<double2*>(prow + 2 * c) = pn;
+        *reinterpret_cast<double2*>(qrow + 2 * c) = qn;
+        sp = fma(po.x, po.x, sp); sq = fma(qo.x, qo.x, sq);
+        sp = fma(po.y, po.y, sp); sq = fma(qo.y, qo.y, sq);
+      }
+    }
+    acc = __dadd_rn(acc, __dadd_rn(lane_loss, fma(m.reg_u, sp, __dmul_rn(m.reg_i, sq))));
+    __syncwarp();
+    __threadfence_block();
+  }
+  acc = warp_sum_f64(acc);
+  if (lane == 0) block_partial[0] = acc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1d: dataflow SGD (the default schedule).  Ratings stay in the reference's iteration order and are
 // cut into chunks of consecutive ratings; groups take chunks IN ORDER from a global counter and walk
@@ -841,6 +932,16 @@ __device__ __forceinline__ double predict_from_dot(const DeviceModel& m, int u, 
   if (MODEL == M_CAMF_CI) pred = __dadd_rn(__dadd_rn(m.global_mean, m.user_bias[u]), dot);
   if (MODEL == M_CAMF_CU) pred = __dadd_rn(__dadd_rn(m.global_mean, m.item_bias[j]), dot);
   if (MODEL == M_CAMF_CUCI) pred = __dadd_rn(m.global_mean, dot);  // CAMF_CUCI.java:69
+  if (MODEL == M_CAMF_ICS) {  // CAMF_ICS.java:52-58: pred = pred * ccMatrix_ICS.get(conditions.get(i), EmptyContextConditions.get(i))
+    pred = dot;
+    for (int d = 0; d < m.Dmax; d++) {
+      const int cond = m.ctx_tab[(int64_t)ctx * m.Dmax + d];
+      if (cond < 0) continue;
+      const int e2 = m.empty_cond[d];
+      const int hi = cond >= e2 ? cond : e2, lo = cond >= e2 ? e2 : cond;
+      pred = __dmul_rn(pred, m.cc_sim[(int64_t)hi * m.C + lo]);
+    }
+  }
   if (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU || MODEL == M_CAMF_CUCI) {
     for (int d = 0; d < m.Dmax; d++) {
       const int cond = m.ctx_tab[(int64_t)ctx * m.Dmax + d];

@@ -105,6 +105,7 @@ def read_binary_csv(path: str) -> Tuple[TrainingSet, RatingDao]:
                      rating_scale=(dao.ratingScale[0], dao.ratingScale[-1]) if dao.ratingScale else None,
                      num_context_dims=dao.numContextDims())
     ts.pair_ids = ui  # the CRS row (user-item pair id) of every entry, for callers that need it
+    ts.empty_conditions = np.asarray(dao.EmptyContextConditions, dtype=np.int32)
     return ts, dao
 
 

@@ -463,6 +463,21 @@ class CAMF_CUCI(IterativeRecommender):
     GAUSSIAN_CONTEXT_BIAS = True
 
 
+class CAMF_ICS(IterativeRecommender):
+    """carskit.alg.cars.adaptation.dependent.sim.CAMF_ICS (CAMF_ICS.java): independent context similarity -- the rating is
+    P[u].Q[j] times the learnt similarity of every condition to its dimension's "na" condition.  A top-N model (isRankingPred,
+    :29): P, Q ~ U(0, 1), every similarity starts at 1 (:40-48).  EXACT mode, one warp (one chain through ccMatrix_ICS)."""
+    MODEL, algoName = capi.CAMF_ICS, "CAMF_ICS"
+
+    def initModel(self, init=None, seed: int = 0):
+        if init is not None:
+            return super().initModel(init, seed)
+        rng = np.random.default_rng(seed)
+        C = self.numConditions
+        self.model = {"P": rng.random((self.numUsers, self.numFactors)), "Q": rng.random((self.numItems, self.numFactors)),
+                      "cc_sim": np.ones((C, C))}
+
+
 class FM(IterativeRecommender):
     """carskit.alg.cars.adaptation.dependent.FM (FM.java): ALS factorization machine over the one-hot features
     (user, item, context).  `FM=-lw <f> -lf <f>` in the configuration (FM.java:53-54); learn.rate and
@@ -617,7 +632,7 @@ def runCrossValidation(rateMatrix: TrainingSet, name: str, conf: Optional[Dict[s
 def getRecommender(name: str):
     """The `switch` of CARSKit.getRecommender (src/carskit/main/CARSKit.java:429-705) for this path."""
     table = {"pmf": PMF, "biasedmf": BiasedMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM,
-             "camf_cuci": CAMF_CUCI}
+             "camf_cuci": CAMF_CUCI, "camf_ics": CAMF_ICS}
     try:
         return table[name.lower()]
     except KeyError:

@@ -123,4 +123,8 @@ def make_training_set(num_users: int, num_items: int, dims: Optional[Sequence[in
                      ctx=c if dims is not None else None, num_conditions=num_cond,
                      num_contexts=num_ctx if dims is not None else 0, ctx_ptr=ctx_ptr, ctx_cond=ctx_cond,
                      global_mean=gm)
+    if dims is not None:
+        # the first condition of every dimension plays the "dim:na" role (rateDao.getEmptyContextConditions(); CAMF_ICS)
+        ts.empty_conditions = np.concatenate([[0], np.cumsum([int(d) for d in dims])[:-1]]).astype(np.int32)
+        ts.num_context_dims = len(dims)
     return ts, test

@@ -39,9 +39,12 @@ enum cars_model {
   CARS_CAMF_CI  = 3, /* .../cars/adaptation/dependent/dev/CAMF_CI.java:74-131 */
   CARS_CAMF_CU  = 4, /* .../cars/adaptation/dependent/dev/CAMF_CU.java:71-128 */
   CARS_FM       = 5, /* .../cars/adaptation/dependent/FM.java:115-220 (ALS; cars_fm_* entry points below) */
-  CARS_CAMF_CUCI = 6 /* .../cars/adaptation/dependent/dev/CAMF_CUCI.java:78-134: ic_bias AND uc_bias, no user /
+  CARS_CAMF_CUCI = 6, /* .../cars/adaptation/dependent/dev/CAMF_CUCI.java:78-134: ic_bias AND uc_bias, no user /
                         item bias; the reference's Guava tables icBias / ucBias are passed as dense
                         [num_items x C] / [num_users x C] arrays (every cell is initialised, :58-64) */
+  CARS_CAMF_ICS = 7  /* .../cars/adaptation/dependent/sim/CAMF_ICS.java:60-129: similarity-based,
+                        pred = P[u].Q[j] * prod_d sim(cond_d, empty_d) with ONE condition-similarity matrix shared by all
+                        ratings (cc_sim; needs cars_desc.empty_conditions).  Like CAMF_C, EXACT runs on one warp. */
 };
 
 /* Update mode.
@@ -126,7 +129,10 @@ typedef struct cars_desc {
   const char* tuning;       /* developer knobs "key=value;key=value" (tests / profiling); NULL in normal use.
                                The library reads NO environment variable. */
   int32_t combine;          /* num_gpus > 1: enum cars_combine */
-  int32_t reserved1;
+  int32_t num_empty_conditions; /* CAMF_ICS: length of empty_conditions (= number of context dimensions) */
+  const int32_t* empty_conditions; /* CAMF_ICS: rateDao.getEmptyContextConditions() (DataDAO.java:214-215): the "dim:na"
+                               condition of every dimension, in dimension order; the i-th condition of a context is
+                               compared with empty_conditions[i] (CAMF_ICS.java:56, 88) */
 } cars_desc;
 
 /* How the item block is combined between user-range shards once per epoch (DESIGN.md "Multi-GPU"):
@@ -145,6 +151,7 @@ typedef struct cars_handle cars_handle;
  *   cond_bias [num_conditions]                        CAMF.java (condBias), CAMF_C.java:60
  *   ic_bias [num_items x num_conditions]              CAMF_CI.java:58
  *   uc_bias [num_users x num_conditions]              CAMF_CU.java:55
+ *   cc_sim  [num_conditions x num_conditions]         CAMF_ICS.java:45-48
  *   (CAMF_CUCI: both ic_bias and uc_bias, CAMF_CUCI.java:42-43, 58-64) */
 typedef struct cars_model_arrays {
   double* P;
@@ -154,6 +161,9 @@ typedef struct cars_model_arrays {
   double* cond_bias;
   double* ic_bias;
   double* uc_bias;
+  double* cc_sim; /* CAMF_ICS: ccMatrix_ICS as a dense [C x C] array (CAMF.java:44, CAMF_ICS.java:45-48).  librec's
+                     SymmMatrix keeps ONE cell per unordered pair, (max(i,j), min(i,j)): upload reads that cell of the
+                     caller's array, download writes the trained value to BOTH (i,j) and (j,i) */
 } cars_model_arrays;
 
 /* Replaces the set-up a Java buildModel() does implicitly by holding trainMatrix/rateDao: copies the

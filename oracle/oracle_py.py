@@ -119,7 +119,12 @@ class JavaRandom:
 
 def epoch(desc: CarsDesc, arrs: dict, lrate: float) -> float:
     a = make_arrays(arrs)
-    return lib().oracle_epoch(C.byref(desc), C.byref(a), lrate)
+    loss = lib().oracle_epoch(C.byref(desc), C.byref(a), lrate)
+    cc = arrs.get("cc_sim")
+    if cc is not None:  # librec's SymmMatrix holds one cell per unordered pair (max, min): show it on both sides
+        low = np.tril(cc)
+        cc[...] = low + np.tril(cc, -1).T
+    return loss
 
 
 def predict(desc: CarsDesc, arrs: dict, u, j, ctx=None, bound=False, min_rate=0.0, max_rate=0.0) -> np.ndarray:

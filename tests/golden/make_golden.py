@@ -37,8 +37,17 @@ def init_arrays(oracle, model, ts, F, seed):
     g = oracle.JavaRandom(seed)
     shapes = capi.member_shapes(model, ts.num_users, ts.num_items, ts.num_conditions, F)
     # icBias / ucBias ~ U(0,1) (CAMF_CI.java:58-59, CAMF_CU.java:55-56); CAMF_CUCI's tables are Gaussian (:58-64)
-    return {k: (g.uniform(s) if k in ("ic_bias", "uc_bias") and model != capi.CAMF_CUCI else g.gaussian(s))
-            for k, s in shapes.items()}
+    out = {}
+    for k, s in shapes.items():
+        if k == "cc_sim":  # CAMF_ICS.java:45-48: every similarity starts at 1.0
+            out[k] = np.ones(s)
+        elif model == capi.CAMF_ICS:  # CAMF_ICS.java:40-41 (isRankingPred): P.init(), Q.init() -> U(0, 1)
+            out[k] = g.uniform(s)
+        elif k in ("ic_bias", "uc_bias") and model != capi.CAMF_CUCI:
+            out[k] = g.uniform(s)
+        else:
+            out[k] = g.gaussian(s)
+    return out
 
 
 def make_inputs(oracle, spec):

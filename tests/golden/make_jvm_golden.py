@@ -38,6 +38,8 @@ SPECS = [
     dict(name="camf_cu_f16_decay", model="camf_cu", users=40, items=20, dims=[4, 4, 4], nnz=800, F=16, iters=4, seed=16,
          order="user_sorted", bold_driver=False, decay=0.9, max_lrate=0.019),
     dict(name="camf_cuci_f12", model="camf_cuci", users=35, items=30, dims=[5, 4, 3], nnz=800, F=12, iters=4, seed=17, order="shuffled"),
+    dict(name="camf_ics_f9", model="camf_ics", users=35, items=25, dims=[4, 3, 3], nnz=800, F=9, iters=4, seed=19, order="shuffled",
+         lrate=0.005),
 ]
 FM_SPEC = dict(name="fm_k4", users=14, items=10, dims=[2, 3], nnz=160, k=4, iters=3, seed=18, reg_lw=0.01, reg_lf=0.02)
 

@@ -452,3 +452,27 @@ def test_tagged_rows_on_chains_skew_and_many_dimensions(oracle, cars_lib, order,
                     assert np.array_equal(p, oracle.predict(desc, ref, test["u"], test["j"], test["ctx"], bound=True, min_rate=1.0, max_rate=5.0))
             eng.download(got)
         assert_bit_identical(ref, got)
+
+
+# ---- N4: similarity-based CAMF (CAMF_ICS.java) ----------------------------------------------------------------------------
+@pytest.mark.parametrize("F,order", [(10, "user_sorted"), (64, "shuffled"), (100, "user_sorted")])
+def test_camf_ics_bit_identical(oracle, cars_lib, F, order):
+    ts, test = synth.make_training_set(90, 120, [4, 3, 2, 5], 3000, seed=F, order=order, holdout=0.1)
+    desc = capi.make_desc(ts, capi.CAMF_ICS, F, **REGS)
+    ref = init_arrays(oracle, capi.CAMF_ICS, ts, F, 3)
+    for k in ("P", "Q"):
+        ref[k] *= 2.0 / np.sqrt(F)  # keep P[u].Q[j] in the rating range for any F
+    got = {k: v.copy() for k, v in ref.items()}
+    lr = capi.f32(0.005)
+    with capi.Engine(desc, keepalive=ts) as eng:
+        eng.upload(got)
+        for _ in range(3):
+            lg, lo = eng.epoch(lr), oracle.epoch(desc, ref, lr)
+            np.testing.assert_allclose(lg, lo, rtol=LOSS_RTOL)
+        pred = eng.predict(test["u"], test["j"], test["ctx"], bound=False)
+        eng.download(got)
+    assert_bit_identical(ref, got)
+    assert np.any(ref["cc_sim"] != 1.0) and np.array_equal(ref["cc_sim"], ref["cc_sim"].T)
+    assert np.array_equal(pred, oracle.predict(desc, ref, test["u"], test["j"], test["ctx"]))
+    with pytest.raises(capi.CarsError):
+        capi.Engine(capi.make_desc(ts, capi.CAMF_ICS, F, mode=capi.FAST, **REGS), keepalive=ts)

@@ -31,7 +31,7 @@ JARS = [os.path.join(REFERENCE, "jar", "CARSKit-v0.4.0.jar"), os.path.join(REFER
 DEV = "carskit/alg/cars/adaptation/dependent/dev/"
 CLASS_OF = {capi.PMF: "carskit/alg/baseline/cf/PMF", capi.BIASEDMF: "carskit/alg/baseline/cf/BiasedMF",
             capi.CAMF_C: DEV + "CAMF_C", capi.CAMF_CI: DEV + "CAMF_CI", capi.CAMF_CU: DEV + "CAMF_CU",
-            capi.CAMF_CUCI: DEV + "CAMF_CUCI"}
+            capi.CAMF_CUCI: DEV + "CAMF_CUCI", capi.CAMF_ICS: "carskit/alg/cars/adaptation/dependent/sim/CAMF_ICS"}
 REC = "carskit/generic/Recommender"
 ITER = "carskit/generic/IterativeRecommender"
 
@@ -41,17 +41,37 @@ def available() -> bool:
 
 
 class HostTable:
-    """com.google.common.collect.HashBasedTable<Integer, Integer, Double>: only get / put are used (CAMF_CUCI.java:58-64, 96-112)."""
-    jclass = "com/google/common/collect/Table"
+    """com.google.common.collect.HashBasedTable<Integer, Integer, Double>: get / put / contains / size / rowKeySet / row(r).keySet()
+    (CAMF_CUCI.java:58-64, 96-112; CAMF_ICS.java:76-105; librec SymmMatrix).  rowKeySet order = insertion order: the cells a
+    rating updates are distinct, so the order Guava's HashMap would yield does not change any value."""
+    jclass = "com/google/common/collect/HashBasedTable"
 
-    def __init__(self, dense: np.ndarray):
-        self.d = {(r, c): float(dense[r, c]) for r in range(dense.shape[0]) for c in range(dense.shape[1])}
+    def __init__(self, dense: Optional[np.ndarray] = None, lower_triangle: bool = False):
+        self.d = {}
+        if dense is not None:
+            for r in range(dense.shape[0]):
+                for c in range(dense.shape[1]):
+                    if not lower_triangle or r >= c:
+                        self.d[(r, c)] = float(dense[r, c])
+
+    def row_keys(self):
+        return list(dict.fromkeys(r for r, _ in self.d))
+
+    def row(self, r):
+        return HostRow([c for (rr, c) in self.d if rr == r])
 
     def to_dense(self, shape) -> np.ndarray:
         out = np.zeros(shape)
         for (r, c), v in self.d.items():
             out[r, c] = v
         return out
+
+
+class HostRow:
+    jclass = "java/util/Map"
+
+    def __init__(self, keys):
+        self.keys = keys
 
 
 def dense_matrix(a: np.ndarray) -> JObject:
@@ -102,8 +122,17 @@ class ReferenceRun:
         jvm.natives[("carskit/data/processor/DataDAO", "getUserIdFromUI")] = lambda vm, a: self.ui_user[a[1]]
         jvm.natives[("carskit/data/processor/DataDAO", "getItemIdFromUI")] = lambda vm, a: self.ui_item[a[1]]
         jvm.natives[("carskit/generic/ContextRecommender", "getConditions")] = lambda vm, a: self.conds[a[1]]
-        jvm.natives[("com/google/common/collect/Table", "get")] = lambda vm, a: a[0].d.get((a[1], a[2]))
-        jvm.natives[("com/google/common/collect/Table", "put")] = self._table_put
+        for tcls in ("com/google/common/collect/Table", "com/google/common/collect/HashBasedTable"):
+            jvm.natives[(tcls, "get")] = lambda vm, a: a[0].d.get((a[1], a[2]))
+            jvm.natives[(tcls, "put")] = self._table_put
+            jvm.natives[(tcls, "contains")] = lambda vm, a: int((a[1], a[2]) in a[0].d)
+            jvm.natives[(tcls, "size")] = lambda vm, a: len(a[0].d)
+            jvm.natives[(tcls, "rowKeySet")] = lambda vm, a: a[0].row_keys()
+            jvm.natives[(tcls, "row")] = lambda vm, a: a[0].row(a[1])
+            jvm.natives[(tcls, "create")] = lambda vm, a: HostTable()
+        jvm.natives[("java/util/Map", "keySet")] = lambda vm, a: a[0].keys
+        jvm.natives[("java/util/Set", "iterator")] = lambda vm, a: HostIterator(a[0])
+        jvm.natives[("java/util/ArrayList", "get")] = lambda vm, a: a[0][a[1]]
         # ---- statics (IterativeRecommender.java:36-49, Recommender.java:196-204) ---------------------------------
         for name, v in (("regU", reg_u), ("regI", reg_i), ("regB", reg_b), ("regC", reg_c), ("decay", decay),
                         ("maxLRate", max_lrate), ("initLRate", lrate)):
@@ -136,6 +165,11 @@ class ReferenceRun:
             rec.f["itemBias"] = dense_vector(arrays["item_bias"])
         if "cond_bias" in arrays:
             rec.f["condBias"] = dense_vector(arrays["cond_bias"])
+        if model == capi.CAMF_ICS:
+            # ccMatrix_ICS: librec SymmMatrix (interpreted) over a Guava table holding the (max, min) cells (CAMF_ICS.java:45-48)
+            rec.f["ccMatrix_ICS"] = JObject("librec/data/SymmMatrix", dim=int(ts.num_conditions),
+                                            data=HostTable(arrays["cc_sim"], lower_triangle=True))
+            jvm.set_static("carskit/generic/ContextRecommender", "EmptyContextConditions", [int(x) for x in ts.empty_conditions])
         if model == capi.CAMF_CUCI:
             rec.f["icBias"] = HostTable(arrays["ic_bias"])
             rec.f["ucBias"] = HostTable(arrays["uc_bias"])
@@ -186,6 +220,12 @@ class ReferenceRun:
         for key, field in (("user_bias", "userBias"), ("item_bias", "itemBias"), ("cond_bias", "condBias")):
             if key in self.shapes:
                 out[key] = np.array(f[field].f["data"], dtype=np.float64)
+        if "cc_sim" in self.shapes:
+            C = self.shapes["cc_sim"][0]
+            cc = np.zeros((C, C))
+            for (r, c), v in f["ccMatrix_ICS"].f["data"].d.items():
+                cc[r, c] = cc[c, r] = v
+            out["cc_sim"] = cc
         for key, field in (("ic_bias", "icBias"), ("uc_bias", "ucBias")):
             if key in self.shapes:
                 o = f[field]
