@@ -51,7 +51,7 @@ public class BiasedMF_B200 extends BiasedMF {
         // float -> double widening of the static hyper-parameters (IterativeRecommender.java:40): never re-parse "0.001"
         B200.train(Native.BIASEDMF, mode(), numUsers, numItems, 0, numFactors, x, ctx, globalMean,
                 (double) regU, (double) regI, (double) regB, (double) regC, devices(), numIters, control,
-                fP, fQ, fUserBias, fItemBias, null, null, null);
+                fP, fQ, fUserBias, fItemBias, null, null, null, null, null);
         B200.unflatten(fP, P);
         B200.unflatten(fQ, Q);
         B200.unflatten(fUserBias, userBias);

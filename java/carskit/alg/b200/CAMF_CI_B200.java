@@ -58,7 +58,7 @@ public class CAMF_CI_B200 extends CAMF_CI {
         // float -> double widening of the static hyper-parameters (IterativeRecommender.java:40): never re-parse "0.001"
         B200.train(Native.CAMF_CI, mode(), numUsers, numItems, numConditions, numFactors, x, ctx, globalMean,
                 (double) regU, (double) regI, (double) regB, (double) regC, devices(), numIters, control,
-                fP, fQ, fUserBias, null, null, fIcBias, null);
+                fP, fQ, fUserBias, null, null, fIcBias, null, null, null);
         B200.unflatten(fP, P);
         B200.unflatten(fQ, Q);
         B200.unflatten(fUserBias, userBias);

@@ -59,7 +59,7 @@ public class CAMF_CUCI_B200 extends CAMF_CUCI {
         B200.train(Native.CAMF_CUCI, mode, numUsers, numItems, numConditions, numFactors, x, ctx, globalMean,
                 (double) regU, (double) regI, (double) regB, (double) regC,
                 B200.devicesFor(fold, algoOptions == null ? 1 : algoOptions.getInt("-gpus", 1)), numIters, control,
-                fP, fQ, null, null, null, fIc, fUc);
+                fP, fQ, null, null, null, fIc, fUc, null, null);
         B200.unflatten(fP, P);
         B200.unflatten(fQ, Q);
         unflatten(fIc, icBias, numItems, numConditions);

@@ -58,7 +58,7 @@ public class CAMF_CU_B200 extends CAMF_CU {
         // float -> double widening of the static hyper-parameters (IterativeRecommender.java:40): never re-parse "0.001"
         B200.train(Native.CAMF_CU, mode(), numUsers, numItems, numConditions, numFactors, x, ctx, globalMean,
                 (double) regU, (double) regI, (double) regB, (double) regC, devices(), numIters, control,
-                fP, fQ, null, fItemBias, null, null, fUcBias);
+                fP, fQ, null, fItemBias, null, null, fUcBias, null, null);
         B200.unflatten(fP, P);
         B200.unflatten(fQ, Q);
         B200.unflatten(fItemBias, itemBias);

@@ -49,7 +49,7 @@ public class PMF_B200 extends PMF {
         // float -> double widening of the static hyper-parameters (IterativeRecommender.java:40): never re-parse "0.001"
         B200.train(Native.PMF, mode(), numUsers, numItems, 0, numFactors, x, ctx, globalMean,
                 (double) regU, (double) regI, (double) regB, (double) regC, devices(), numIters, control,
-                fP, fQ, null, null, null, null, null);
+                fP, fQ, null, null, null, null, null, null, null);
         B200.unflatten(fP, P);
         B200.unflatten(fQ, Q);
     }

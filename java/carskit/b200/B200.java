@@ -132,19 +132,20 @@ public final class B200 {
     public static void train(int model, int mode, int numUsers, int numItems, int numConditions, int numFactors, Ratings x,
                              int[][] ctxTable, double globalMean, double regU, double regI, double regB, double regC,
                              int[] gpuIds, int numIters, EpochControl ctl, double[] P, double[] Q, double[] userBias,
-                             double[] itemBias, double[] condBias, double[] icBias, double[] ucBias) throws Exception {
+                             double[] itemBias, double[] condBias, double[] icBias, double[] ucBias, double[] ccSim,
+                             int[] emptyConditions) throws Exception {
         int numContexts = ctxTable == null ? 0 : ctxTable[0].length - 1;
         long h = Native.create(model, mode, numUsers, numItems, numConditions, numContexts, numFactors, x.u, x.j, x.ctx, x.r,
                 ctxTable == null ? null : ctxTable[0], ctxTable == null ? null : ctxTable[1], globalMean, regU, regI, regB,
-                regC, gpuIds, Native.COMBINE_MEAN, 0.0);
+                regC, gpuIds, Native.COMBINE_MEAN, 0.0, emptyConditions);
         try {
-            Native.upload(h, P, Q, userBias, itemBias, condBias, icBias, ucBias);
+            Native.upload(h, P, Q, userBias, itemBias, condBias, icBias, ucBias, ccSim);
             for (int iter = 1; iter <= numIters; iter++) {
                 double loss = Native.epoch(h, ctl.lRate()); // == the body of `for (int iter ...)` up to `loss *= 0.5`
                 if (ctl.afterEpoch(iter, loss))
                     break;
             }
-            Native.download(h, P, Q, userBias, itemBias, condBias, icBias, ucBias);
+            Native.download(h, P, Q, userBias, itemBias, condBias, icBias, ucBias, ccSim);
         } finally {
             Native.destroy(h);
         }

@@ -54,7 +54,7 @@ JNIEXPORT jlong JNICALL Java_carskit_b200_Native_create(JNIEnv* env, jclass cls,
                                                         jintArray u, jintArray j, jintArray ctx, jdoubleArray r,
                                                         jintArray ctxPtr, jintArray ctxCond, jdouble globalMean, jdouble regU,
                                                         jdouble regI, jdouble regB, jdouble regC, jintArray gpuIds,
-                                                        jint combine, jdouble fastMaxConc) {
+                                                        jint combine, jdouble fastMaxConc, jintArray emptyConditions) {
   (void)cls;
   cars_desc d;
   memset(&d, 0, sizeof d);
@@ -73,11 +73,14 @@ JNIEXPORT jlong JNICALL Java_carskit_b200_Native_create(JNIEnv* env, jclass cls,
     throw_runtime(env, "carskit_b200: u / j / ctx / r must have the same length");
     return 0;
   }
+  const jsize nempty = len_of(env, emptyConditions);
+  const jsize ngpu = len_of(env, gpuIds);
   pin_t pu = pin(env, u), pj = pin(env, j), pc = pin(env, ctx), pr = pin(env, r), pp = pin(env, ctxPtr), pq = pin(env, ctxCond),
-        pg = pin(env, gpuIds);
+        pg = pin(env, gpuIds), pe = pin(env, emptyConditions);
+  d.empty_conditions = (const int32_t*)pe.p;
+  d.num_empty_conditions = nempty;
   d.u = (const int32_t*)pu.p; d.j = (const int32_t*)pj.p; d.ctx = (const int32_t*)pc.p; d.r = (const double*)pr.p;
   d.ctx_ptr = (const int32_t*)pp.p; d.ctx_cond = (const int32_t*)pq.p;
-  const jsize ngpu = len_of(env, gpuIds);
   if (ngpu > 1) {
     d.num_gpus = ngpu;
     d.gpu_ids = (const int32_t*)pg.p;
@@ -88,7 +91,7 @@ JNIEXPORT jlong JNICALL Java_carskit_b200_Native_create(JNIEnv* env, jclass cls,
   const int rc = cars_create(&d, &h);
   char msg[512];
   if (rc != CARS_OK) { strncpy(msg, cars_last_error(NULL), sizeof msg - 1); msg[sizeof msg - 1] = 0; }
-  unpin(env, pg, JNI_ABORT); unpin(env, pq, JNI_ABORT); unpin(env, pp, JNI_ABORT); unpin(env, pr, JNI_ABORT);
+  unpin(env, pe, JNI_ABORT); unpin(env, pg, JNI_ABORT); unpin(env, pq, JNI_ABORT); unpin(env, pp, JNI_ABORT); unpin(env, pr, JNI_ABORT);
   unpin(env, pc, JNI_ABORT); unpin(env, pj, JNI_ABORT); unpin(env, pu, JNI_ABORT);
   if (rc != CARS_OK) {  /* thrown only after every critical region is closed: no JNI call is allowed inside one */
     throw_runtime(env, msg);
@@ -98,30 +101,30 @@ JNIEXPORT jlong JNICALL Java_carskit_b200_Native_create(JNIEnv* env, jclass cls,
 }
 
 static void transfer(JNIEnv* env, jlong handle, int to_device, jdoubleArray P, jdoubleArray Q, jdoubleArray userBias,
-                     jdoubleArray itemBias, jdoubleArray condBias, jdoubleArray icBias, jdoubleArray ucBias) {
+                     jdoubleArray itemBias, jdoubleArray condBias, jdoubleArray icBias, jdoubleArray ucBias, jdoubleArray ccSim) {
   cars_handle* h = (cars_handle*)(intptr_t)handle;
-  pin_t p[7] = {pin(env, P), pin(env, Q), pin(env, userBias), pin(env, itemBias), pin(env, condBias), pin(env, icBias),
-                pin(env, ucBias)};
+  pin_t p[8] = {pin(env, P), pin(env, Q), pin(env, userBias), pin(env, itemBias), pin(env, condBias), pin(env, icBias),
+                pin(env, ucBias), pin(env, ccSim)};
   cars_model_arrays a;
   a.P = (double*)p[0].p; a.Q = (double*)p[1].p; a.user_bias = (double*)p[2].p; a.item_bias = (double*)p[3].p;
-  a.cond_bias = (double*)p[4].p; a.ic_bias = (double*)p[5].p; a.uc_bias = (double*)p[6].p;
+  a.cond_bias = (double*)p[4].p; a.ic_bias = (double*)p[5].p; a.uc_bias = (double*)p[6].p; a.cc_sim = (double*)p[7].p;
   const int rc = to_device ? cars_upload(h, &a) : cars_download(h, &a);
-  for (int k = 6; k >= 0; k--) unpin(env, p[k], to_device ? JNI_ABORT : 0);  /* download: copy back / commit */
+  for (int k = 7; k >= 0; k--) unpin(env, p[k], to_device ? JNI_ABORT : 0);  /* download: copy back / commit */
   if (rc != CARS_OK) throw_runtime(env, cars_last_error(h));
 }
 
 JNIEXPORT void JNICALL Java_carskit_b200_Native_upload(JNIEnv* env, jclass cls, jlong h, jdoubleArray P, jdoubleArray Q,
                                                        jdoubleArray userBias, jdoubleArray itemBias, jdoubleArray condBias,
-                                                       jdoubleArray icBias, jdoubleArray ucBias) {
+                                                       jdoubleArray icBias, jdoubleArray ucBias, jdoubleArray ccSim) {
   (void)cls;
-  transfer(env, h, 1, P, Q, userBias, itemBias, condBias, icBias, ucBias);
+  transfer(env, h, 1, P, Q, userBias, itemBias, condBias, icBias, ucBias, ccSim);
 }
 
 JNIEXPORT void JNICALL Java_carskit_b200_Native_download(JNIEnv* env, jclass cls, jlong h, jdoubleArray P, jdoubleArray Q,
                                                          jdoubleArray userBias, jdoubleArray itemBias, jdoubleArray condBias,
-                                                         jdoubleArray icBias, jdoubleArray ucBias) {
+                                                         jdoubleArray icBias, jdoubleArray ucBias, jdoubleArray ccSim) {
   (void)cls;
-  transfer(env, h, 0, P, Q, userBias, itemBias, condBias, icBias, ucBias);
+  transfer(env, h, 0, P, Q, userBias, itemBias, condBias, icBias, ucBias, ccSim);
 }
 
 JNIEXPORT jdouble JNICALL Java_carskit_b200_Native_epoch(JNIEnv* env, jclass cls, jlong handle, jdouble lRate) {

@@ -84,11 +84,11 @@ jint Java_carskit_b200_Native_deviceCount(JNIEnv*, jclass);
 jstring Java_carskit_b200_Native_version(JNIEnv*, jclass);
 jlong Java_carskit_b200_Native_create(JNIEnv*, jclass, jint, jint, jint, jint, jint, jint, jint, jintArray, jintArray, jintArray,
                                       jdoubleArray, jintArray, jintArray, jdouble, jdouble, jdouble, jdouble, jdouble, jintArray,
-                                      jint, jdouble);
+                                      jint, jdouble, jintArray);
 void Java_carskit_b200_Native_upload(JNIEnv*, jclass, jlong, jdoubleArray, jdoubleArray, jdoubleArray, jdoubleArray, jdoubleArray,
-                                     jdoubleArray, jdoubleArray);
+                                     jdoubleArray, jdoubleArray, jdoubleArray);
 void Java_carskit_b200_Native_download(JNIEnv*, jclass, jlong, jdoubleArray, jdoubleArray, jdoubleArray, jdoubleArray,
-                                       jdoubleArray, jdoubleArray, jdoubleArray);
+                                       jdoubleArray, jdoubleArray, jdoubleArray, jdoubleArray);
 jdouble Java_carskit_b200_Native_epoch(JNIEnv*, jclass, jlong, jdouble);
 void Java_carskit_b200_Native_predict(JNIEnv*, jclass, jlong, jintArray, jintArray, jintArray, jboolean, jdouble, jdouble,
                                       jdoubleArray);
@@ -111,19 +111,19 @@ int main(void) {
 
   printf("deviceCount = %d\n", (int)Java_carskit_b200_Native_deviceCount(env, NULL));
   jlong h = Java_carskit_b200_Native_create(env, NULL, 3 /* Native.CAMF_CI */, 0, U, I, C, 2, F, &au, &aj, &ac, &ar, &ap, &aq, 23.0 / 6.0,
-                                            (double)1e-4f, (double)1e-4f, (double)1e-4f, (double)1e-3f, NULL, 0, 0.0);
+                                            (double)1e-4f, (double)1e-4f, (double)1e-4f, (double)1e-3f, NULL, 0, 0.0, NULL);
   if (g_pending) {
     printf("RuntimeException: %s\n", g_exception);
     return (g_open_critical == 0 && g_jni_call_inside_critical == 0 && h == 0) ? 3 : 2;
   }
-  Java_carskit_b200_Native_upload(env, NULL, h, &aP, &aQ, &aub, NULL, NULL, &aic, NULL);
+  Java_carskit_b200_Native_upload(env, NULL, h, &aP, &aQ, &aub, NULL, NULL, &aic, NULL, NULL);
   for (int iter = 1; iter <= 3 && !g_pending; iter++)
     printf("iter %d: loss = %.17g\n", iter, Java_carskit_b200_Native_epoch(env, NULL, h, (double)0.02f));
   double out[6];
   struct _jobject ao = arr(out, 6);
   Java_carskit_b200_Native_predict(env, NULL, h, &au, &aj, &ac, JNI_TRUE, 1.0, 5.0, &ao);
   jdoubleArray sums = Java_carskit_b200_Native_evalRatings(env, NULL, h, &au, &aj, &ac, &ar, 1.0, 5.0);
-  Java_carskit_b200_Native_download(env, NULL, h, &aP, &aQ, &aub, NULL, NULL, &aic, NULL);
+  Java_carskit_b200_Native_download(env, NULL, h, &aP, &aQ, &aub, NULL, NULL, &aic, NULL, NULL);
   Java_carskit_b200_Native_destroy(env, NULL, h);
   if (g_pending) { printf("RuntimeException: %s\n", g_exception); return 1; }
   printf("P[0][0] = %.17g, pred[0] = %.17g, sumAbs = %.17g, sumSq = %.17g\n", P[0], out[0], ((double*)sums->data)[0],

@@ -108,6 +108,7 @@ def test_every_reference_member_the_java_sources_use_exists():
                             (dao, "getUserIdFromUI", "(I)I"), (dao, "getItemIdFromUI", "(I)I"), (dao, "numContexts", "()I"),
                             (dao, "numContextDims", "()I"), ("carskit/generic/ContextRecommender", "getConditions", "(I)Ljava/util/List;"),
                             ("carskit/generic/IterativeRecommender", "isConverged", "(I)Z"),
+                            ("librec/data/SymmMatrix", "get", "(II)D"), ("librec/data/SymmMatrix", "set", "(IID)V"),
                             ("happy/coding/io/LineConfiger", "getInt", "(Ljava/lang/String;I)I"),
                             ("happy/coding/io/LineConfiger", "getFloat", "(Ljava/lang/String;)F"),
                             ("happy/coding/io/LineConfiger", "getString", "(Ljava/lang/String;Ljava/lang/String;)Ljava/lang/String;")]:
@@ -119,6 +120,8 @@ def test_every_reference_member_the_java_sources_use_exists():
                             ("carskit/alg/cars/adaptation/dependent/CAMF", "condBias", None),
                             ("carskit/alg/cars/adaptation/dependent/CAMF", "icBias", None),
                             ("carskit/alg/cars/adaptation/dependent/CAMF", "ucBias", None),
+                            ("carskit/alg/cars/adaptation/dependent/CAMF", "ccMatrix_ICS", "Llibrec/data/SymmMatrix;"),
+                            ("carskit/generic/ContextRecommender", "EmptyContextConditions", "Ljava/util/ArrayList;"),
                             ("carskit/generic/Recommender", "train", "Llibrec/data/SparseMatrix;"),
                             ("carskit/generic/Recommender", "trainMatrix", None), ("carskit/generic/Recommender", "rateDao", None),
                             ("carskit/generic/Recommender", "algoOptions", None), ("carskit/generic/Recommender", "globalMean", "D"),
