@@ -354,7 +354,7 @@ def test_large_pageable_and_pinned_transfers(oracle, cars_lib):
 
 
 def test_config2_frappe_shaped_camf_c_bit_identical(oracle, cars_lib):
-    # BASELINE.json configs[1] at full size (scripts/config2.py times the same input): CAMF_C, 10 factors, 957 users x
+    # BASELINE.json configs[1] at full size (bench.py --workload camf_c_f10_frappe_shaped times the same shape): CAMF_C, 10 factors, 957 users x
     # 4 082 items, 8 context dimensions with 7/7/2/3/2/9/80/233 conditions, 96 203 drawn ratings, 90/10 split.
     # EXACT mode (one warp, reference order) must reproduce the oracle bit for bit, predictions and RMSE included.
     ts, test = synth.make_training_set(957, 4082, [7, 7, 2, 3, 2, 9, 80, 233], 96203, seed=1, holdout=0.1)
