@@ -37,6 +37,7 @@ static thread_local std::string g_create_error = "";
 struct LaunchPlan {
   const void* fn = nullptr;
   int lpr = 0, v = 0, threads = 0;
+  bool bulk = false;  // FAST: Q-row steps through TMA add-reduce of a staged row (fast_kernels.cuh, BULK)
 };
 
 struct MultiGpu;  // multi_gpu.cuh: one handle driving N GPUs (cars_desc.num_gpus > 1)
@@ -81,7 +82,7 @@ struct cars_handle {
   bool damp_items = false, damp_conds = false;
   signed char* d_hot_slot = nullptr;  // FAST: hot-row slot of every item (-1 = none) [num_items]
   int32_t* d_hot_items = nullptr;     // FAST: item of every hot slot
-  int num_hot = 0, hot_flush = 16, hot_stride = 0;
+  int num_hot = 0, hot_flush = 16, hot_stride = 0, bulk_offset = 0;
   RatingRec* d_rec = nullptr;
   int64_t* d_chunk_start = nullptr;
   double* d_chunk_loss = nullptr;
@@ -209,20 +210,38 @@ static LaunchPlan pick_dataflow_plan(int model, int Fp) {
   return LaunchPlan{};
 }
 
-// FAST (hogwild) kernel.  shape 0 (default): F = 64 -> 8 lanes per rating (8 factors per lane), 256-bit row accesses,
-// F compiled in, 256 threads x 2 CTAs per SM (no spills; 3.35 ms per 10 M ratings against 3.83 ms for 4 lanes and
-// 4.28 ms for 3 CTAs per SM, profiles/r2/fast_shapes.txt); F = 128 -> 16 lanes; otherwise the generic table.
-template <int MODEL>
-static LaunchPlan pick_fast_generic(int Fp) { CARS_SHAPE_TABLE(sgd_fast_kernel, MODEL, 256, 2) }
+// FAST (hogwild) kernel.  Default (shape 0): the Q-row step of a rating is staged in shared memory and added to Q[j] by
+// ONE TMA add-reduce (BULK, UBLKRED.G.S.ADD.F64) for Fp >= 32 -- 27.5 ms per 100 M ratings against 34.4 ms with 64 scalar
+// REDG per rating on the same box (profiles/r2/fast_bulk_reduce.txt); rows shorter than 32 factors keep the scalar
+// reductions.  F = 64: 8 lanes per rating, 256-bit row accesses, F compiled in, 256 threads x 2 CTAs per SM; F = 128: 16
+// lanes.  shape 5 = the scalar-REDG kernels (A/B), shape 1 / 2 / 4 = other launch shapes measured and rejected.
+template <int MODEL, bool BULK>
+static LaunchPlan pick_fast_generic(int Fp) {
+  LaunchPlan p;
+  p.threads = 256;
+  p.bulk = BULK;
+  if (Fp <= 16) { p.fn = (const void*)sgd_fast_kernel<MODEL, 8, 1, 256, 2, false, 0, BULK>; p.lpr = 8; p.v = 1; }
+  else if (Fp <= 32) { p.fn = (const void*)sgd_fast_kernel<MODEL, 8, 2, 256, 2, false, 0, BULK>; p.lpr = 8; p.v = 2; }
+  else if (Fp <= 64) { p.fn = (const void*)sgd_fast_kernel<MODEL, 8, 4, 256, 2, false, 0, BULK>; p.lpr = 8; p.v = 4; }
+  else if (Fp <= 128) { p.fn = (const void*)sgd_fast_kernel<MODEL, 16, 4, 256, 2, false, 0, BULK>; p.lpr = 16; p.v = 4; }
+  else if (Fp <= 256) { p.fn = (const void*)sgd_fast_kernel<MODEL, 32, 4, 256, 2, false, 0, BULK>; p.lpr = 32; p.v = 4; }
+  else if (Fp <= 512) { p.fn = (const void*)sgd_fast_kernel<MODEL, 32, 8, 256, 2, false, 0, BULK>; p.lpr = 32; p.v = 8; }
+  return p;
+}
 template <int MODEL>
 static LaunchPlan pick_fast(int Fp, int F, int shape) {
   LaunchPlan p;
   p.threads = 256;
-  if (F == 64 && shape == 0) { p.fn = (const void*)sgd_fast_kernel<MODEL, 8, 4, 256, 2, true, 64>; p.lpr = 8; p.v = 4; return p; }
+  const bool bulk = shape != 5 && shape != 1 && shape != 2;
+  if (F == 64 && (shape == 0 || shape == 3)) { p.fn = (const void*)sgd_fast_kernel<MODEL, 8, 4, 256, 2, true, 64, true>; p.lpr = 8; p.v = 4; p.bulk = true; return p; }
+  if (F == 64 && shape == 4) { p.fn = (const void*)sgd_fast_kernel<MODEL, 8, 4, 256, 3, true, 64, true>; p.lpr = 8; p.v = 4; p.bulk = true; return p; }
+  if (F == 64 && shape == 5) { p.fn = (const void*)sgd_fast_kernel<MODEL, 8, 4, 256, 2, true, 64>; p.lpr = 8; p.v = 4; return p; }
   if (F == 64 && shape == 1) { p.fn = (const void*)sgd_fast_kernel<MODEL, 8, 4, 256, 3, true, 64>; p.lpr = 8; p.v = 4; return p; }
   if (F == 64 && shape == 2) { p.fn = (const void*)sgd_fast_kernel<MODEL, 4, 8, 256, 2, true, 64>; p.lpr = 4; p.v = 8; return p; }
-  if (F == 128 && shape <= 2) { p.fn = (const void*)sgd_fast_kernel<MODEL, 16, 4, 256, 2, true, 128>; p.lpr = 16; p.v = 4; return p; }
-  return pick_fast_generic<MODEL>(Fp);
+  if (F == 128 && bulk) { p.fn = (const void*)sgd_fast_kernel<MODEL, 16, 4, 256, 2, true, 128, true>; p.lpr = 16; p.v = 4; p.bulk = true; return p; }
+  if (F == 128) { p.fn = (const void*)sgd_fast_kernel<MODEL, 16, 4, 256, 2, true, 128>; p.lpr = 16; p.v = 4; return p; }
+  if (bulk && Fp >= 32) return pick_fast_generic<MODEL, true>(Fp);
+  return pick_fast_generic<MODEL, false>(Fp);
 }
 static LaunchPlan pick_fast_plan(int model, int Fp, int F, int shape) {
   switch (model) {
@@ -502,6 +521,10 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     h->hot_stride = Fp + 2 + ((model == CARS_CAMF_CI || model == CARS_CAMF_CUCI) ? desc->num_conditions : 0);
     const int hot_max = fast ? (4096 / h->hot_stride < 32 ? 4096 / h->hot_stride : 32) : 0;
     h->smem = fast ? (size_t)hot_max * h->hot_stride * 8 + (size_t)hot_max * 4 + 16 : (size_t)groups_per_cta * (Fp + 2) * 8;
+    if (fast && plan.bulk) {  // two staged delta rows per group behind the hot-row area
+      h->bulk_offset = (int)((h->smem + 127) & ~(size_t)127);
+      h->smem = (size_t)h->bulk_offset + (size_t)groups_per_cta * 2 * Fp * 8;
+    }
     if (h->tagged) {
       const int extras = (h->tl.p_payload() - F) + (h->tl.q_payload() - F);
       h->smem = (size_t)groups_per_cta * ((((F + extras + 1) & ~1) + 2) * 8);
@@ -891,6 +914,7 @@ extern "C" int cars_epoch_begin(cars_handle* h, double lrate) {
     fs.cond_scale = h->damp_conds ? h->d_cond_scale : nullptr;
     fs.hot_slot = h->num_hot > 0 ? h->d_hot_slot : nullptr;
     fs.hot_items = h->d_hot_items; fs.num_hot = h->num_hot; fs.hot_flush = h->hot_flush;
+    fs.bulk_offset = h->bulk_offset;
     CUDA_TRY(h, cudaMemsetAsync(h->d_flags, 0, h->flags_words * sizeof(unsigned), h->stream));
     void* args[] = {&m, &fs, &lrate, &h->d_partial};
     CUDA_TRY(h, cudaLaunchKernel(h->plan.fn, dim3(h->grid), dim3(h->block), args, h->smem, h->stream));

@@ -39,7 +39,18 @@ struct FastStream {
   const signed char* hot_slot;  // [num_items] slot of a hot item, -1 otherwise; nullptr = no hot rows
   const int32_t* hot_items;     // [num_hot] item id of every slot
   int num_hot, hot_flush;
+  int bulk_offset;              // BULK kernels: byte offset of the per-group delta-row slots in dynamic shared memory
 };
+
+// TMA add-reduce of one staged row: global[dst .. dst + bytes) += shared[src ..) as fp64, asynchronously (UBLKRED.G.S.ADD.F64)
+__device__ __forceinline__ void bulk_reduce_add_f64(double* dst, const double* src_shared, int bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(src_shared);
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(sa), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // One hot row in shared memory: [Fp factors | itemBias | pad | C icBias cells (CAMF_CI / CAMF_CUCI only)]
 template <int MODEL>
@@ -115,9 +126,13 @@ __device__ __forceinline__ void fast_load(const DeviceModel& m, const FastStream
 }
 
 // One rating: arithmetic + user-side stores + item-side reductions.  Returns this lane's loss contribution.
-template <int MODEL, int LPR, int V, bool WIDE, int FIXF>
+// BULK: the Q-row step is staged in the group's shared-memory slot `stage` and added to Q[j] by ONE TMA reduce
+// (cp.reduce.async.bulk ... add.f64) instead of F scalar red.global.add.f64 -- the 64 REDG per rating are what bounds the
+// scalar kernel (LSU: 1.3 cycles per lane, profiles/r2/ncu_summary_fast_uniform_100M.txt).
+template <int MODEL, int LPR, int V, bool WIDE, int FIXF, bool BULK = false>
 __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastStream& s, const RatingRec& rec, double lr,
-                                              int gl, unsigned gmask, UserRegs<V>& us, const FastOps<V>& o, double* sh_hot) {
+                                              int gl, unsigned gmask, UserRegs<V>& us, const FastOps<V>& o, double* sh_hot,
+                                              double* stage = nullptr) {
   constexpr bool kUserBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CI);
   constexpr bool kItemBias = (MODEL == M_BIASEDMF || MODEL == M_CAMF_C || MODEL == M_CAMF_CU);
   constexpr bool kHasCond = (MODEL == M_CAMF_C || MODEL == M_CAMF_CI || MODEL == M_CAMF_CU || MODEL == M_CAMF_CUCI);
@@ -233,6 +248,10 @@ __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastSt
   // a hot item's steps go to the CTA's shared-memory accumulator row, everything else straight to L2
   double* qrow = m.Q + (int64_t)j * Fp;
   double sp = 0.0, sq = 0.0;
+  if (BULK && o.slot < 0) {  // the slot was last read by the bulk reduce issued two ratings ago: make sure it is done
+    if (gl == 0) bulk_wait_read_1();
+    __syncwarp(gmask);
+  }
 #pragma unroll
   for (int v = 0; v < V; v++) {
     const int c = chunk_of<LPR, WIDE>(gl, v);
@@ -245,6 +264,8 @@ __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastSt
       if (o.slot >= 0) {
         atomicAdd(srow + 2 * c, dx);
         atomicAdd(srow + 2 * c + 1, dy);
+      } else if (BULK) {
+        *reinterpret_cast<double2*>(stage + 2 * c) = make_double2(dx, dy);
       } else {
         red_add_f64(qrow + 2 * c, dx);
         red_add_f64(qrow + 2 * c + 1, dy);
@@ -254,6 +275,11 @@ __device__ __forceinline__ double fast_update(const DeviceModel& m, const FastSt
       sp = fma(po.y, po.y, sp);
       sq = fma(qo.y, qo.y, sq);
     }
+  }
+  if (BULK && o.slot < 0) {
+    fence_proxy_async_shared();  // this lane's shared-memory writes -> visible to the async proxy
+    __syncwarp(gmask);
+    if (gl == 0) bulk_reduce_add_f64(qrow, stage, Fp * 8);
   }
   if (s.hot_slot) {  // every hot_flush-th update of a slot by this CTA moves the accumulated row to L2
     bool flush = false;
@@ -333,9 +359,9 @@ __device__ __forceinline__ void fast_store_user(const DeviceModel& m, int u, int
 }
 
 // K2: persistent grid (any size: chunks are only held by running groups, so no co-residency is needed).
-template <int MODEL, int LPR, int V, int THREADS, int MINB, bool WIDE = false, int FIXF = 0>
+template <int MODEL, int LPR, int V, int THREADS, int MINB, bool WIDE = false, int FIXF = 0, bool BULK = false>
 __global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, FastStream s, double lr, double* block_partial) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sh_hot = reinterpret_cast<double*>(smem_raw);  // [num_hot x (Fp + 2)] accumulators, then num_hot counters
   constexpr int WARPS = THREADS / 32;
   const int hstride = hot_row_stride<MODEL>(FIXF > 0 ? FIXF : m.Fp, m.C);
@@ -358,6 +384,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, 
 #pragma unroll
   for (int v = 0; v < V; v++) us.p[v] = make_double2(0.0, 0.0);
   us.bu = 0.0;
+  int stage_sel = 0;           // BULK: which of the group's two staging slots the next bulk reduce reads
   RatingRec rec, recn, recn2;  // current, next (its operands are requested this turn), the one after (record in flight)
   rec.u = rec.j = rec.ctx = rec.ku = rec.kj = rec.pad = 0; rec.r = 0.0;
   recn = rec;
@@ -393,7 +420,13 @@ __global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, 
       if (has_next) fast_load<MODEL, LPR, V, WIDE, FIXF>(m, s, recn, gl, nxt);
       if (n + 2 < end) recn2 = ld_rec(s.rec + n + 2);
       if (rec.u != prev_u) fast_load_user<MODEL, LPR, V, WIDE, FIXF>(m, rec.u, gl, us);
-      acc = __dadd_rn(acc, fast_update<MODEL, LPR, V, WIDE, FIXF>(m, s, rec, lr, gl, gmask, us, cur, sh_hot));
+      double* stage = nullptr;
+      if (BULK) {  // two slots per group, used alternately: the TMA may still be reading the previous rating's row
+        const int Fp_ = FIXF > 0 ? FIXF : m.Fp;
+        stage = reinterpret_cast<double*>(smem_raw + s.bulk_offset) + ((size_t)((warp * (32 / LPR) + gw) * 2 + stage_sel)) * Fp_;
+        if (cur.slot < 0) stage_sel ^= 1;  // this rating issues a bulk reduce from `stage`; the next one uses the other slot
+      }
+      acc = __dadd_rn(acc, fast_update<MODEL, LPR, V, WIDE, FIXF, BULK>(m, s, rec, lr, gl, gmask, us, cur, sh_hot, stage));
       if (!has_next || recn.u != rec.u) fast_store_user<MODEL, LPR, V, WIDE, FIXF>(m, rec.u, gl, us);
       prev_u = rec.u;
       if (has_next) {
@@ -405,6 +438,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sgd_fast_kernel(DeviceModel m, 
     }
   }
 
+  if (BULK && gl == 0) bulk_wait_all();  // the staged rows must have been consumed before the CTA's shared memory goes away
   acc = warp_sum_f64(acc);
   __shared__ double warp_sum[WARPS];
   if (lane == 0) warp_sum[warp] = acc;

@@ -8,8 +8,8 @@
 // rounded multiply and add, exactly like predict_kernel -- which is why this is an fp64 SIMT contraction and
 // not a tensor-core GEMM: DMMA accumulates with fused multiply-adds in a different order (and tcgen05 has no
 // fp64 kind), and the north star asks for bit-exact top-N indices.  The P x Q^T structure is still exploited:
-// a CTA stages a tile of 16 query rows and 64 candidate rows in shared memory and every thread keeps four
-// independent accumulation chains in flight.
+// a CTA stages a tile of 64 query rows and 64 candidate rows in shared memory and every thread keeps a 4 x 4
+// block of independent accumulation chains in registers.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,9 +18,9 @@
 
 namespace cars {
 
-constexpr int kRankTQ = 16;  // queries per tile
+constexpr int kRankTQ = 64;  // queries per tile
 constexpr int kRankTJ = 64;  // candidates per tile
-constexpr int kRankFC = 128; // factors staged in shared memory per pass
+constexpr int kRankFC = 64;  // factors staged in shared memory per pass
 
 // Double.compareTo order as an unsigned key (larger key = larger double; -0.0 < +0.0; NaN never gets here)
 __device__ __forceinline__ unsigned long long sortable_key(double v) {
@@ -44,13 +44,15 @@ __global__ void __launch_bounds__(256) rank_score_kernel(DeviceModel m, int64_t 
   double* Qs = Ps + kRankTQ * ld;
   const int64_t qt = (int64_t)blockIdx.y * kRankTQ;
   const int ct = blockIdx.x * kRankTJ;
-  const int tq = threadIdx.x / 16, tj = threadIdx.x % 16;
-  const double* p = Ps + tq * ld;
-  const double* qa = Qs + (tj)*ld;
-  const double* qb = Qs + (tj + 16) * ld;
-  const double* qcc = Qs + (tj + 32) * ld;
-  const double* qd = Qs + (tj + 48) * ld;
-  double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+  // 4 x 4 register tile: thread (ty, tx) scores queries 4 ty .. 4 ty + 3 against candidates tx, tx + 16, tx + 32, tx + 48 --
+  // 8 shared-memory loads feed 16 multiply-add pairs per factor (the 1 x 4 tile of round 1 needed 5 loads for 4 pairs
+  // and sat at 89 % of the L1TEX pipe with the fp64 pipe at 19 %, profiles/r2/ncu_summary_rank_score.txt)
+  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
   for (int f0 = 0; f0 < F; f0 += FC) {
     const int fl = F - f0 < FC ? F - f0 : FC;
     __syncthreads();
@@ -65,24 +67,32 @@ __global__ void __launch_bounds__(256) rank_score_kernel(DeviceModel m, int64_t 
       Qs[r * ld + f] = c < num_cand ? m.Q[(int64_t)cand[c] * m.Fp + f0 + f] : 0.0;
     }
     __syncthreads();
-    for (int f = 0; f < fl; f++) {  // DenseMatrix.rowMult order, four independent chains
-      const double pf = p[f];
-      d0 = __dadd_rn(d0, __dmul_rn(pf, qa[f]));
-      d1 = __dadd_rn(d1, __dmul_rn(pf, qb[f]));
-      d2 = __dadd_rn(d2, __dmul_rn(pf, qcc[f]));
-      d3 = __dadd_rn(d3, __dmul_rn(pf, qd[f]));
+    const double* p0 = Ps + (4 * ty) * ld;
+    const double* qq = Qs + tx * ld;
+    for (int f = 0; f < fl; f++) {  // DenseMatrix.rowMult order: every pair's chain runs f ascending, mul and add rounded separately
+      double pv[4], qv[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) pv[a] = p0[a * ld + f];
+#pragma unroll
+      for (int c = 0; c < 4; c++) qv[c] = qq[(16 * c) * ld + f];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[a][c] = __dadd_rn(acc[a][c], __dmul_rn(pv[a], qv[c]));
     }
   }
-  const int64_t q = qt + tq;
-  if (q >= nq) return;
-  const int u = qu[q0 + q], ctx = qc ? qc[q0 + q] : 0;
-  const double dots[4] = {d0, d1, d2, d3};
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int c = ct + tj + 16 * i;
-    if (c >= num_cand) continue;
-    const double s = predict_from_dot<MODEL>(m, u, cand[c], ctx, dots[i]);
-    keys[q * num_cand + c] = (s == s && s > bin_thold) ? sortable_key(s) : kRankDropped;  // !isNaN && rank > binThold
+  for (int a = 0; a < 4; a++) {
+    const int64_t q = qt + 4 * ty + a;
+    if (q >= nq) continue;
+    const int u = qu[q0 + q], ctx = qc ? qc[q0 + q] : 0;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; c4++) {
+      const int c = ct + tx + 16 * c4;
+      if (c >= num_cand) continue;
+      const double sc = predict_from_dot<MODEL>(m, u, cand[c], ctx, acc[a][c4]);
+      keys[q * num_cand + c] = (sc == sc && sc > bin_thold) ? sortable_key(sc) : kRankDropped;  // !isNaN && rank > binThold
+    }
   }
 }
 

@@ -52,8 +52,10 @@ def rmse(oracle, model, ts, F, arrs, test):
 
 
 @pytest.mark.parametrize("model", [capi.PMF, capi.BIASEDMF, capi.CAMF_CI, capi.CAMF_CU, capi.CAMF_CUCI])
-@pytest.mark.parametrize("F", [10, 64, 100, 128])
-def test_fast_equals_serial_when_no_two_ratings_share_an_item(oracle, cars_lib, model, F):
+@pytest.mark.parametrize("F,shape", [(10, 0), (31, 0), (64, 0), (64, 5), (100, 0), (100, 5), (128, 0), (200, 0)])
+def test_fast_equals_serial_when_no_two_ratings_share_an_item(oracle, cars_lib, model, F, shape):
+    # shape 0: the default -- the Q-row step goes through ONE TMA add-reduce of a staged row for Fp >= 32 (UBLKRED), scalar
+    # red.global.add.f64 below that; shape 5: the scalar kernels at every F
     # every item is rated exactly once: the only chains are the users', and FAST keeps those in order
     users, items = 150, 6000
     rng = np.random.default_rng(F)
@@ -66,7 +68,7 @@ def test_fast_equals_serial_when_no_two_ratings_share_an_item(oracle, cars_lib, 
     ts = capi.TrainingSet(num_users=users, num_items=items, u=u, j=j, r=r, ctx=ctx, num_conditions=base.num_conditions,
                           num_contexts=base.num_contexts, ctx_ptr=base.ctx_ptr, ctx_cond=base.ctx_cond,
                           global_mean=float(r.mean()))
-    ref, got, rl, gl, st = train_both(oracle, model, ts, F, epochs=3, seed=3)
+    ref, got, rl, gl, st = train_both(oracle, model, ts, F, epochs=3, seed=3, tuning=f"shape={shape}")
     for k in ref:
         np.testing.assert_allclose(got[k], ref[k], rtol=1e-11, atol=1e-13, err_msg=k)
     np.testing.assert_allclose(gl, rl, rtol=1e-10)
