@@ -1324,10 +1324,17 @@ extern "C" int cars_rank_topn(cars_handle* h, int64_t num_queries, const int32_t
       h->st.kernel_launches += 1;
     }
     if (e == cudaSuccess) {
-      if (num_recs <= kRankRegK) {  // one pass over the keys: per-thread top-k in registers, merged in shared memory
-        RK(cudaFuncSetAttribute(rank_select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kRankRegK * 12));
-        rank_select_topk_kernel<<<(unsigned)nq, 256, (size_t)256 * num_recs * 12, h->stream>>>(q0, nq, num_cand, d_cand, num_recs, d_keys,
-                                                                                               d_items, d_scores, d_count, d_kept);
+      if (num_recs <= kRankRegK) {  // one pass over the keys: per-thread top-K in registers, merged in shared memory
+        const size_t sm = (size_t)256 * num_recs * 12;
+#define CARS_SELECT(KK)                                                                                                        \
+  RK(cudaFuncSetAttribute(rank_select_topk_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kRankRegK * 12));   \
+  rank_select_topk_kernel<KK><<<(unsigned)nq, 256, sm, h->stream>>>(q0, nq, num_cand, d_cand, num_recs, d_keys, d_items, d_scores, \
+                                                                    d_count, d_kept)
+        if (num_recs <= 4) { CARS_SELECT(4); }
+        else if (num_recs <= 8) { CARS_SELECT(8); }
+        else if (num_recs <= 10) { CARS_SELECT(10); }
+        else { CARS_SELECT(16); }
+#undef CARS_SELECT
       } else
         rank_select_kernel<<<(unsigned)nq, 256, 0, h->stream>>>(q0, nq, num_cand, d_cand, num_recs, d_keys, d_items, d_scores,
                                                                d_count, d_kept);

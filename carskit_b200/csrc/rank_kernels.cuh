@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(256) rank_select_kernel(int64_t q0, int64_t nq
 // "largest key, lowest candidate index".  Same result as rank_select_kernel: the reference's stable descending sort.
 constexpr int kRankRegK = 16;
 
+template <int K>  // K >= num_recs, a compile-time bound so that the thread's list stays in registers (K = 4, 8, 10, 16)
 __global__ void __launch_bounds__(256) rank_select_topk_kernel(int64_t q0, int64_t nq, int32_t num_cand, const int32_t* __restrict__ cand,
                                                                int32_t num_recs, const unsigned long long* __restrict__ keys,
                                                                int32_t* __restrict__ out_items, double* __restrict__ out_scores,
@@ -183,29 +184,29 @@ __global__ void __launch_bounds__(256) rank_select_topk_kernel(int64_t q0, int64
   if (q >= nq) return;
   const unsigned long long* row = keys + q * num_cand;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned long long tk[kRankRegK];
-  int ti[kRankRegK];
+  unsigned long long tk[K];
+  int ti[K];
 #pragma unroll
-  for (int k = 0; k < kRankRegK; k++) { tk[k] = kRankDropped; ti[k] = 0x7fffffff; }
+  for (int k = 0; k < K; k++) { tk[k] = kRankDropped; ti[k] = 0x7fffffff; }
   int kept = 0;
   for (int c = threadIdx.x; c < num_cand; c += 256) {
     const unsigned long long key = __ldg(row + c);
     if (key == kRankDropped) continue;
     kept++;
-    if (key <= tk[num_recs - 1 < kRankRegK ? num_recs - 1 : kRankRegK - 1]) continue;  // not better than the thread's worst
+    if (key <= tk[K - 1]) continue;  // not better than the thread's K-th best (K >= num_recs keeps a superset)
     // insertion after equal keys: this thread sees its candidates in ascending index order (stable)
     unsigned long long ck = key;
     int ci = c;
 #pragma unroll
-    for (int k = 0; k < kRankRegK; k++) {
-      if (k < num_recs && ck > tk[k]) {
+    for (int k = 0; k < K; k++) {
+      if (ck > tk[k]) {
         const unsigned long long t = tk[k]; tk[k] = ck; ck = t;
         const int u = ti[k]; ti[k] = ci; ci = u;
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < kRankRegK; k++)
+  for (int k = 0; k < K; k++)
     if (k < num_recs) { mk[threadIdx.x * num_recs + k] = tk[k]; mi[threadIdx.x * num_recs + k] = ti[k]; }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) kept += __shfl_down_sync(0xffffffffu, kept, o);
