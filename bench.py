@@ -568,7 +568,7 @@ def run_fm(args, wl, wl_name, rank, world, local_rank):
     rng = np.random.default_rng(wl["seed"] + 7919)
     init = {"w0": np.zeros(1), "w": rng.random(p), "V": 0.1 * rng.standard_normal((p, k))}
     conf = {"num.factors": str(k), "num.max.iter": str(args.steps), "FM": "-lw 0.01 -lf 0.02"}
-    rec = recommender.FM(ts, None, conf=conf, device=local_rank, world=world)
+    rec = recommender.FM(ts, None, conf=conf, device=local_rank, world=world, tuning=args.tuning)
     rec.initModel(init={n: v.copy() for n, v in init.items()})
     eng = rec.open_engine()
     for it in range(args.warmup):
@@ -596,7 +596,7 @@ def run_fm(args, wl, wl_name, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         ms, nnz_total = float(tm[0]), int(t[1])
     value = nnz_total * args.steps / (ms * 1e-3)
-    rec2 = recommender.FM(ts, None, conf=conf, device=local_rank, world=world)
+    rec2 = recommender.FM(ts, None, conf=conf, device=local_rank, world=world, tuning=args.tuning)
     rec2.initModel(init=init)
     t0 = time.perf_counter()
     rec2.buildModel()
@@ -646,7 +646,7 @@ def run_fm(args, wl, wl_name, rank, world, local_rank):
                 "seconds": e2e_s},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "fm_piece_reduce_kernel + fm_row_update_kernel (one ALS iteration)",
+                     "traffic": None, "kernel": "fm_run_reduce_kernel + fm_piece_reduce_kernel + fm_dense_reduce_kernel + fm_row_update_kernel (one ALS iteration)",
                      "algorithmic_bytes_per_update": B, "updates_per_launch": ts.nnz},
         "cpu_baseline": cpu,
     }

@@ -24,6 +24,7 @@ struct FieldStore {
   int32_t *d_coord_of_row = nullptr, *d_perm = nullptr, *d_piece_coord = nullptr;
   int64_t *d_piece_beg = nullptr, *d_coord_piece = nullptr, *d_coord_rows = nullptr;
   double* d_delta = nullptr;
+  uint32_t* d_run_off = nullptr;  // run mode (users): fm_run_reduce_kernel's table
   bool wide = false;  // few coordinates with many pieces each: one warp sums a coordinate's pieces
   bool short_pieces = false;  // on average < 64 rows per piece: 8 lanes per piece instead of a warp
   FmField f{};
@@ -44,6 +45,8 @@ struct cars_fm_handle {
   double *d_part = nullptr, *d_scal = nullptr;
   double* h_scal = nullptr;
   int64_t max_pieces = 0;
+  bool run_fuse_update = true;  // fm_run_reduce_kernel<MODE, 2>: the users' row update inside the reduce kernel
+  int32_t row_items_per_blk = 0, row_blocks = 0;  // storage order = (item block, user) when row_blocks > 0
   int red_blocks = 0;
   FieldStore fld[3];
   bool uploaded = false, prepared = false;
@@ -299,18 +302,44 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
           fm_fail(h, CARS_E_UNSUPPORTED, "row-order key does not fit 32 bits");
           return bail(CARS_E_UNSUPPORTED);
         }
-        fms_row_key_kernel<<<blocks, 256, 0, h->stream>>>(r_j, r_c, N, items_per_blk, ctx_slots, h->C, sc.key);
-        FS_TRY(cudaGetLastError());
-        uint32_t* order = nullptr;
+        // contexts streamed (ctx_slots == 1): the rows of a block are put in USER order (stable: the caller's order
+        // inside a user), whatever the caller's order was -- fm_run_reduce_kernel needs the rows of consecutive users
+        // inside a block to be one contiguous run.  Two stable passes: by user, then by item block.
+        const bool by_user = ctx_slots == 1 && h->tune.get_ll("fm_runs", 1) != 0;
+        uint32_t *order = nullptr, *order1 = nullptr;
         FS_TRY(fm_alloc(&order, Na));
+        cudaError_t se = cudaSuccess;
         size_t tb = sc.temp_bytes;
-        cudaError_t se = cub::DeviceRadixSort::SortPairs(sc.temp, tb, sc.key, sc.key_out, sc.idx, order, N, 0, bits, h->stream);
+        if (by_user) {
+          se = fm_alloc(&order1, Na);
+          int ubits = 1;
+          while ((1ll << ubits) < (long long)h->U) ubits++;
+          if (se == cudaSuccess)
+            se = cub::DeviceRadixSort::SortPairs(sc.temp, tb, reinterpret_cast<const uint32_t*>(r_u), sc.key_out, sc.idx, order1, N, 0,
+                                                 ubits, h->stream);
+          if (se == cudaSuccess) {
+            fms_block_key_kernel<<<blocks, 256, 0, h->stream>>>(order1, r_j, N, items_per_blk, sc.key);
+            se = cudaGetLastError();
+          }
+          tb = sc.temp_bytes;
+          if (se == cudaSuccess)
+            se = cub::DeviceRadixSort::SortPairs(sc.temp, tb, sc.key, sc.key_out, order1, order, N, 0, bits, h->stream);
+          h->launches += 2;
+          h->row_items_per_blk = items_per_blk;
+          h->row_blocks = (int32_t)((h->I - 1) / items_per_blk + 1);
+        } else {
+          fms_row_key_kernel<<<blocks, 256, 0, h->stream>>>(r_j, r_c, N, items_per_blk, ctx_slots, h->C, sc.key);
+          se = cudaGetLastError();
+          if (se == cudaSuccess)
+            se = cub::DeviceRadixSort::SortPairs(sc.temp, tb, sc.key, sc.key_out, sc.idx, order, N, 0, bits, h->stream);
+        }
         if (se == cudaSuccess) {
           fms_permute_rows_kernel<<<blocks, 256, 0, h->stream>>>(order, N, r_u, r_j, r_c, r_r, h->d_u, h->d_j, h->d_c, h->d_r);
           se = cudaGetLastError();
         }
         if (se == cudaSuccess) se = cudaStreamSynchronize(h->stream);
         cudaFree(order);
+        cudaFree(order1);
         FS_TRY(se);
         h->launches += 3;
       }
@@ -329,6 +358,33 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
     drop();
     if (rc) return bail(rc);
 #undef FS_TRY
+    // run mode for the user field (fm_run_reduce_kernel): G consecutive users per CTA, G chosen so that a run -- the
+    // group's rows inside one item block -- is ~96 rows
+    if (h->row_blocks >= (int32_t)h->tune.get_ll("fm_run_min_blocks", 8) && N > 0) {
+      FieldStore& fs = h->fld[0];
+      const double rows_per_user_block = (double)N / ((double)h->U * (double)h->row_blocks);
+      int G = 32;
+      while (G < 512 && (double)(2 * G) * rows_per_user_block <= 96.0) G *= 2;
+      const long long tg = h->tune.get_ll("fm_run_users", 0);
+      if (tg == 32 || tg == 64 || tg == 128 || tg == 256 || tg == 512) G = (int)tg;
+      const int32_t ngroups = (h->U + G - 1) / G;
+      const int64_t entries = (int64_t)(ngroups + 1) * h->row_blocks;
+      FM_TRY_H(fm_alloc(&fs.d_run_off, (size_t)entries));
+      fms_run_offsets_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, h->stream>>>(h->d_u, h->d_j, N, h->row_items_per_blk,
+                                                                                       h->row_blocks, G, ngroups, fs.d_run_off);
+      FM_TRY_H(cudaGetLastError());
+      h->launches++;
+      fs.f.run_off = fs.d_run_off; fs.f.run_group = G; fs.f.run_groups = ngroups; fs.f.run_blocks = h->row_blocks;
+      const int smem = (int)fm_run_smem_bytes(G);
+      FM_TRY_H(cudaFuncSetAttribute(fm_run_reduce_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      FM_TRY_H(cudaFuncSetAttribute(fm_run_reduce_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      FM_TRY_H(cudaFuncSetAttribute(fm_run_reduce_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      FM_TRY_H(cudaFuncSetAttribute(fm_run_reduce_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      FM_TRY_H(cudaFuncSetAttribute(fm_run_reduce_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      FM_TRY_H(cudaFuncSetAttribute(fm_run_reduce_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      h->run_fuse_update = h->tune.get_ll("fm_run_fuse_update", 1) != 0;
+      if ((int64_t)h->U > h->max_pieces) h->max_pieces = h->U;  // d_part holds one pair per user
+    }
     if (ctx_dense) {
       const int smem = (int)((size_t)h->C * kDenseThreads * sizeof(double2));
       FM_TRY_H(cudaFuncSetAttribute(fm_dense_reduce_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -435,7 +491,24 @@ static int field_sweep(cars_fm_handle* h, double* coef, int stride, int col, dou
     const FmField& f = fs.f;
     if (f.ncoord == 0) continue;
     // (a)
-    if (f.dense_blocks > 0) {
+    bool coord_done = false, rows_done = false;
+    if (f.run_off) {
+      const size_t smem = fm_run_smem_bytes(f.run_group);
+      if (!ex && h->run_fuse_update) {
+        fm_run_reduce_kernel<MODE, 2><<<f.run_groups, 256, smem, h->stream>>>(f, h->d_e, Qf, coef, stride, col, size_reg, h->d_part,
+                                                                             fs.d_delta, h->d_e, Qf);
+        coord_done = rows_done = true;  // steps (b) and (c) ran inside the kernel
+      } else if (!ex) {
+        fm_run_reduce_kernel<MODE, 1><<<f.run_groups, 256, smem, h->stream>>>(f, h->d_e, Qf, coef, stride, col, size_reg, h->d_part,
+                                                                             fs.d_delta, nullptr, nullptr);
+        coord_done = true;  // step (b) ran in the kernel's epilogue
+      } else {
+        fm_run_reduce_kernel<MODE, 0><<<f.run_groups, 256, smem, h->stream>>>(f, h->d_e, Qf, coef, stride, col, size_reg, h->d_part,
+                                                                             fs.d_delta, nullptr, nullptr);
+      }
+      FM_TRY(h, cudaGetLastError());
+      h->launches++;
+    } else if (f.dense_blocks > 0) {
       const size_t smem = (size_t)f.ncoord * kDenseThreads * sizeof(double2);
       fm_dense_reduce_kernel<MODE><<<f.dense_blocks, kDenseThreads, smem, h->stream>>>(f, h->d_e, Qf, coef, stride, col, h->N,
                                                                                       h->d_part);
@@ -458,7 +531,8 @@ static int field_sweep(cars_fm_handle* h, double* coef, int stride, int col, dou
     }
     // (b)
     const unsigned cb = fs.wide ? (unsigned)(((int64_t)f.ncoord * 32 + 255) / 256) : (unsigned)((f.ncoord + 255) / 256);
-    if (!ex) {
+    if (coord_done) {
+    } else if (!ex) {
       if (fs.wide)
         fm_coord_kernel<MODE, true><<<cb, 256, 0, h->stream>>>(f, h->d_part, size_reg, coef, stride, col, fs.d_delta);
       else
@@ -478,7 +552,7 @@ static int field_sweep(cars_fm_handle* h, double* coef, int stride, int col, dou
       h->launches += 2;
     }
     // (c)
-    if (h->N == 0) continue;
+    if (h->N == 0 || rows_done) continue;
     fm_row_update_kernel<MODE><<<(unsigned)(((h->N + 1) / 2 + 255) / 256), 256, 0, h->stream>>>(f, fs.d_delta, h->N, h->d_e, Qf);
     FM_TRY(h, cudaGetLastError());
     h->launches++;
@@ -615,7 +689,7 @@ extern "C" void cars_fm_destroy(cars_fm_handle* h) {
   cudaFree(h->d_w0); cudaFree(h->d_w); cudaFree(h->d_V); cudaFree(h->d_part); cudaFree(h->d_scal);
   for (auto& f : h->fld) {
     if (f.owns_coord) cudaFree(f.d_coord_of_row);
-    cudaFree(f.d_perm); cudaFree(f.d_piece_coord); cudaFree(f.d_piece_beg);
+    cudaFree(f.d_perm); cudaFree(f.d_piece_coord); cudaFree(f.d_piece_beg); cudaFree(f.d_run_off);
     cudaFree(f.d_coord_piece); cudaFree(f.d_coord_rows); cudaFree(f.d_delta);
   }
   if (h->h_scal) cudaFreeHost(h->h_scal);

@@ -32,6 +32,10 @@ struct FmField {
   int32_t offset;  // index of the field's first coordinate in w / V
   double x;        // feature value of the field
   int32_t dense_blocks;  // > 0: the field is reduced by fm_dense_reduce_kernel on this many CTAs (no pieces)
+  // run mode (fm_run_reduce_kernel): the rows are stored sorted by (row block, coordinate), so the rows of
+  // `run_group` consecutive coordinates inside one row block are ONE contiguous run of the storage order
+  const uint32_t* run_off;  // [(run_groups + 1) x run_blocks] first row of (group, block); nullptr = pieces
+  int32_t run_group, run_groups, run_blocks;
 };
 
 constexpr int kDenseThreads = 128;
@@ -283,9 +287,226 @@ __global__ void __launch_bounds__(256) fm_piece_reduce_kernel(FmField fld, const
   }
 }
 
+// (a'') fields with MANY coordinates of FEW rows each whose rows are stored sorted by (row block, coordinate) -- the
+// users: 25 rows per user and GPU at config 4, spread over 82 item blocks.  Gathering e[perm[i]] reads a 32-byte
+// sector for every 8 bytes it uses (fm_piece_reduce_kernel<1, 8, 2>: 1.35 ms per launch at 125 M rows, L1TEX / L2
+// bound with DRAM at 35 %, profiles/r2/launches_fm_125M.txt).  Here ONE CTA owns `run_group` consecutive coordinates:
+// their rows inside a row block are one contiguous run of the storage order (~80 rows), which the CTA's warps read
+// coalesced, lane = row.  Warp w takes the blocks b = w, w + 8, ..; the terms of consecutive lanes with the same
+// coordinate are joined in row order by shuffles, and the head lane adds the sum to the WARP's accumulator of that
+// coordinate in shared memory (one lane per coordinate and instruction: no conflict, program order = row order).
+// The coordinate's total = its 8 warp accumulators in warp order.  Deterministic.
+// FUSE >= 1: step (b) in the epilogue (new value, delta) -- one launch less per field and factor.
+// FUSE == 2: step (c) too -- the CTA owns ALL rows of its coordinates, so it applies e_n += delta x (Qf likewise) to the
+// runs it has just read (L2 hits: a CTA's rows are ~100 KB) with fm_row_update_kernel's arithmetic; the separate row
+// update's 2.8 GB DRAM read per launch goes away.
+// Latency: the rows of the next kRunSlots - 1 chunks are always in flight -- cp.async into a per-warp ring in shared
+// memory (a lane reads back only what it copied itself: no barrier on the ring) -- and pass 2 of FUSE == 2 loads four
+// chunks before it stores any.
+constexpr int kRunSlots = 4;
+constexpr int kRunSlotBytes = 32 * 4 + 32 * 8 + 32 * 8;  // coordinate, e, Qf of 32 rows
+__host__ __device__ constexpr size_t fm_run_smem_bytes(int G) {
+  return (size_t)G * sizeof(double) + (size_t)8 * G * sizeof(double2) + (size_t)8 * kRunSlots * kRunSlotBytes;
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// iterator over the 32-row chunks of a warp's runs of one batch (lane t holds the bounds of the batch's t-th run)
+struct RunChunks {
+  uint32_t rs, re, pos, end;
+  int t, nruns;
+  bool more;
+  __device__ __forceinline__ void start(uint32_t rs_, uint32_t re_, int nruns_) {
+    rs = rs_; re = re_; nruns = nruns_; t = 0;
+    pos = __shfl_sync(0xffffffffu, rs, 0);
+    end = __shfl_sync(0xffffffffu, re, 0);
+    more = settle();
+  }
+  __device__ __forceinline__ bool settle() {  // skip exhausted / empty runs; false = batch done (warp-uniform)
+    while (pos >= end) {
+      if (++t >= nruns) return false;
+      pos = __shfl_sync(0xffffffffu, rs, t);
+      end = __shfl_sync(0xffffffffu, re, t);
+    }
+    return true;
+  }
+  __device__ __forceinline__ void next() { pos += 32; more = settle(); }
+};
+
+template <int MODE, int FUSE>
+__global__ void __launch_bounds__(256) fm_run_reduce_kernel(FmField fld, const double* __restrict__ e,
+                                                            const double* __restrict__ Qf, double* coef, int coef_stride,
+                                                            int coef_col, double size_reg, double* __restrict__ part,
+                                                            double* __restrict__ delta, double* e_rw, double* Qf_rw) {
+  extern __shared__ __align__(16) unsigned char run_smem[];
+  const int G = fld.run_group;
+  double* coef_s = reinterpret_cast<double*>(run_smem);                              // [G]
+  double2* acc = reinterpret_cast<double2*>(run_smem + (size_t)G * sizeof(double));  // [8][G]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned char* ring = run_smem + (size_t)G * sizeof(double) + (size_t)8 * G * sizeof(double2) +
+                        (size_t)warp * kRunSlots * kRunSlotBytes;  // [kRunSlots][coordinate 32 x 4 | e 32 x 8 | Qf 32 x 8]
+  const int g = blockIdx.x;
+  const int l0 = g * G;
+  const int nl = fld.ncoord - l0 < G ? fld.ncoord - l0 : G;
+  const double x = fld.x;
+  for (int t = tid; t < G; t += 256) coef_s[t] = t < nl ? coef[(int64_t)(fld.offset + l0 + t) * coef_stride + coef_col] : 0.0;
+  for (int t = tid; t < 8 * G; t += 256) acc[t] = make_double2(0.0, 0.0);
+  __syncthreads();
+  double2* wacc = acc + (size_t)warp * G;
+  // FUSE == 2 rewrites the rows it read: no read-only (non-coherent) loads through the __restrict__ pointers then
+  const double* ep = FUSE == 2 ? e_rw : e;
+  const double* qp = FUSE == 2 ? Qf_rw : Qf;
+  const int nb = fld.run_blocks;
+  const uint32_t* off0 = fld.run_off + (int64_t)g * nb;
+  const uint32_t* off1 = off0 + nb;
+
+  // the warp's runs come in batches of 32 (lane t of a batch holds the bounds of block b = base + warp + 8 t)
+  for (int base = 0; base + warp < nb; base += 256) {
+    const int myb = base + warp + 8 * lane;
+    const uint32_t rs = myb < nb ? off0[myb] : 0u, re = myb < nb ? off1[myb] : 0u;
+    int nruns = (nb - base - warp + 7) / 8;
+    if (nruns > 32) nruns = 32;
+    RunChunks it;
+    it.start(rs, re, nruns);
+    int issued = 0;
+    auto issue = [&](int slot) {  // request the iterator's chunk into ring slot `slot` (or nothing), one group either way
+      if (it.more) {
+        unsigned char* sl = ring + slot * kRunSlotBytes;
+        const uint32_t n = it.pos + lane;
+        if (n < it.end) {
+          cp_async_4(sl + lane * 4, fld.coord_of_row + n);
+          cp_async_8(sl + 128 + lane * 8, ep + n);
+          if (MODE == 1) cp_async_8(sl + 384 + lane * 8, qp + n);
+        } else {
+          reinterpret_cast<int*>(sl)[lane] = -1;  // past the run's end
+        }
+        it.next();
+        issued++;
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int k = 0; k < kRunSlots - 1; k++) issue(k);
+    for (int c = 0; c < issued; c++) {
+      issue((c + kRunSlots - 1) % kRunSlots);
+      cp_async_wait<kRunSlots - 1>();  // chunk c has landed (every lane waits for its own copies)
+      const unsigned char* sl = ring + (c % kRunSlots) * kRunSlotBytes;
+      const int cu = reinterpret_cast<const int*>(sl)[lane];
+      const bool ok = cu >= 0;
+      const double ce = ok ? reinterpret_cast<const double*>(sl + 128)[lane] : 0.0;
+      const double cq = (MODE == 1 && ok) ? reinterpret_cast<const double*>(sl + 384)[lane] : 0.0;
+      const int ul = ok ? cu - l0 : 0;
+      const double cl = ok ? coef_s[ul] : 0.0;
+      double num, den = 0.0;
+      if (MODE == 0) {
+        num = __dmul_rn(__dsub_rn(ce, __dmul_rn(cl, x)), x);
+      } else {
+        const double hh = __dsub_rn(__dmul_rn(x, cq), __dmul_rn(__dmul_rn(x, x), cl));
+        num = __dmul_rn(__dsub_rn(ce, __dmul_rn(cl, hh)), hh);
+        den = __dmul_rn(hh, hh);
+      }
+      const int key = ok ? ul : -1 - lane;  // rows past the run's end: singletons nobody adds
+      const int pk = __shfl_up_sync(0xffffffffu, key, 1);
+      const bool head = lane == 0 || pk != key;
+      const unsigned hm = __ballot_sync(0xffffffffu, head);
+      const int hpos = 31 - __clz(hm & (0xffffffffu >> (31 - lane)));
+      const int dist = lane - hpos;
+      for (int d = 1; __ballot_sync(0xffffffffu, dist >= d) != 0u; d++) {  // usually one round: 14 % of a coordinate's runs have a second row
+        const double tn = __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(num), d),
+                                           __shfl_down_sync(0xffffffffu, __double2loint(num), d));
+        const int dd = __shfl_down_sync(0xffffffffu, dist, d);
+        const bool take = lane + d < 32 && dd == d;  // only a head has a lane at distance d from it
+        if (take) num = __dadd_rn(num, tn);
+        if (MODE == 1) {
+          const double td = __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(den), d),
+                                             __shfl_down_sync(0xffffffffu, __double2loint(den), d));
+          if (take) den = __dadd_rn(den, td);
+        }
+      }
+      if (head && ok) {
+        double2 a = wacc[ul];
+        a.x = __dadd_rn(a.x, num);
+        if (MODE == 1) a.y = __dadd_rn(a.y, den);
+        wacc[ul] = a;
+      }
+      __syncwarp();
+    }
+    cp_async_wait<0>();
+  }
+  __syncthreads();
+  for (int t = tid; t < nl; t += 256) {
+    double num = 0.0, den = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      const double2 a = acc[(size_t)w * G + t];
+      num = __dadd_rn(num, a.x);
+      if (MODE == 1) den = __dadd_rn(den, a.y);
+    }
+    const int l = l0 + t;
+    if (FUSE >= 1) {
+      if (MODE == 0) den = __dmul_rn((double)fld.coord_rows[l], __dmul_rn(x, x));
+      den = __dadd_rn(den, size_reg);
+      const double old = coef_s[t];
+      const double nv = __dsub_rn(0.0, num / den);
+      coef[(int64_t)(fld.offset + l) * coef_stride + coef_col] = nv;
+      const double dl = __dsub_rn(nv, old);
+      delta[l] = dl;
+      if (FUSE == 2) coef_s[t] = __dmul_rn(dl, x);  // only thread t reads or writes slot t here
+    } else {
+      part[l] = num;
+      if (MODE == 1) part[(int64_t)fld.ncoord + l] = den;
+    }
+  }
+  if (FUSE == 2) {
+    __syncthreads();
+    for (int base = 0; base + warp < nb; base += 256) {
+      const int myb = base + warp + 8 * lane;
+      const uint32_t rs = myb < nb ? off0[myb] : 0u, re = myb < nb ? off1[myb] : 0u;
+      int nruns = (nb - base - warp + 7) / 8;
+      if (nruns > 32) nruns = 32;
+      RunChunks it;
+      it.start(rs, re, nruns);
+      while (it.more) {  // four chunks' loads (L2 hits mostly) before the first store
+        uint32_t n[4];
+        int uu[4];
+        double ee[4], qq[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          n[k] = 0xffffffffu;
+          if (it.more) {
+            if (it.pos + lane < it.end) n[k] = it.pos + lane;
+            it.next();
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const bool ok = n[k] != 0xffffffffu;
+          uu[k] = ok ? fld.coord_of_row[n[k]] : l0;
+          ee[k] = ok ? e_rw[n[k]] : 0.0;
+          qq[k] = (MODE == 1 && ok) ? Qf_rw[n[k]] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (n[k] == 0xffffffffu) continue;
+          const double d = coef_s[uu[k] - l0];
+          e_rw[n[k]] = __dadd_rn(ee[k], d);
+          if (MODE == 1) Qf_rw[n[k]] = __dadd_rn(qq[k], d);
+        }
+      }
+    }
+  }
+}
+
 // (a') fields with FEW coordinates (contexts: <= kDenseMaxCoord): the rows are streamed in storage order, fully
 // coalesced, and every thread adds a row's terms into ITS OWN accumulator of the row's coordinate in shared
-// memory (bins[coordinate][thread]: no conflicts, fixed order).  A CTA owns a fixed slice of rows; its per-
+// memory (bins[coordinate][thread]: no conflicts, fixed order).  A CTA owns a fixed set of row chunks; its per-
 // coordinate sums (fixed-order tree over the threads) go to part[(block * ncoord + c) * 2 + {0, 1}].  Deterministic.
 template <int MODE>
 __global__ void __launch_bounds__(kDenseThreads) fm_dense_reduce_kernel(FmField fld, const double* __restrict__ e,
@@ -303,8 +524,6 @@ __global__ void __launch_bounds__(kDenseThreads) fm_dense_reduce_kernel(FmField 
   for (int c = tid; c < nc; c += T) cls[c] = coef[(int64_t)(fld.offset + c) * coef_stride + coef_col];
   for (int i = tid; i < nc * T; i += T) bins[i] = make_double2(0.0, 0.0);
   __syncthreads();
-  const int64_t per = (N + gridDim.x - 1) / gridDim.x;
-  const int64_t beg = (int64_t)blockIdx.x * per, end = beg + per < N ? beg + per : N;
   auto add_row = [&](int c, double en, double qn) {
     if (c < 0) return;
     const double cl = cls[c];
@@ -318,20 +537,44 @@ __global__ void __launch_bounds__(kDenseThreads) fm_dense_reduce_kernel(FmField 
     }
     bins[c * T + tid] = b;
   };
-  int64_t n = beg + tid;
-  for (; n + (UNR - 1) * T < end; n += UNR * T) {
-    int c[UNR];
-    double en[UNR], qn[UNR];
+  // The rows are dealt to the CTAs in chunks of UNR * T rows, round-robin (chunk q -> CTA q mod grid): at any time the
+  // grid reads ONE window of grid * 20 KB of every array.  (Giving each CTA one contiguous slice -- 444 streams 2.25 MB
+  // apart per array -- ran at 0.49 of the DRAM peak whatever the number of rows in flight:
+  // profiles/r2/ncu_summary_fm_dense_reduce_125M.txt.)  A thread's rows and their order depend on the grid size only.
+  // Two register buffers: the next chunk is requested before this one's shared-memory updates.
+  constexpr int64_t CH = (int64_t)UNR * T;
+  const int64_t nchunks = N / CH, G = gridDim.x;
+  int ca[UNR], cb[UNR];
+  double ea[UNR], qa[UNR], eb[UNR], qb[UNR];
+  auto fetch = [&](int64_t q, int* c, double* en, double* qn) {
+    const int64_t at = q * CH + tid;
 #pragma unroll
     for (int k = 0; k < UNR; k++) {
-      c[k] = fld.coord_of_row[n + k * T];
-      en[k] = e[n + k * T];
-      qn[k] = MODE == 1 ? Qf[n + k * T] : 0.0;
+      c[k] = fld.coord_of_row[at + k * T];
+      en[k] = e[at + k * T];
+      qn[k] = MODE == 1 ? Qf[at + k * T] : 0.0;
     }
+  };
+  int64_t q = blockIdx.x;
+  if (q < nchunks) {
+    fetch(q, ca, ea, qa);
+    for (;;) {
+      const bool more_b = q + G < nchunks;
+      if (more_b) fetch(q + G, cb, eb, qb);
 #pragma unroll
-    for (int k = 0; k < UNR; k++) add_row(c[k], en[k], qn[k]);
+      for (int k = 0; k < UNR; k++) add_row(ca[k], ea[k], qa[k]);
+      q += G;
+      if (!more_b) break;
+      const bool more_a = q + G < nchunks;
+      if (more_a) fetch(q + G, ca, ea, qa);
+#pragma unroll
+      for (int k = 0; k < UNR; k++) add_row(cb[k], eb[k], qb[k]);
+      q += G;
+      if (!more_a) break;
+    }
   }
-  for (; n < end; n += T) add_row(fld.coord_of_row[n], e[n], MODE == 1 ? Qf[n] : 0.0);
+  if (blockIdx.x == 0)  // the rows after the last full chunk
+    for (int64_t n = nchunks * CH + tid; n < N; n += T) add_row(fld.coord_of_row[n], e[n], MODE == 1 ? Qf[n] : 0.0);
   __syncthreads();
   for (int c = warp; c < nc; c += T / 32) {
     double a = 0.0, b = 0.0;
@@ -366,6 +609,11 @@ __device__ __forceinline__ void coord_piece_sums(const FmField& fld, const doubl
     num = warp_sum(num);
     if (MODE == 1) den = warp_sum(den);
     if (MODE == 0) den = __dmul_rn((double)fld.coord_rows[l], __dmul_rn(fld.x, fld.x));
+    return;
+  }
+  if (fld.run_off) {  // fm_run_reduce_kernel left ONE pair per coordinate
+    num = part[l];
+    den = MODE == 1 ? part[(int64_t)fld.ncoord + l] : __dmul_rn((double)fld.coord_rows[l], __dmul_rn(fld.x, fld.x));
     return;
   }
   const int64_t q0 = fld.coord_piece[l], q1 = fld.coord_piece[l + 1];

@@ -48,6 +48,33 @@ __global__ void __launch_bounds__(256) fms_permute_rows_kernel(const uint32_t* _
   }
 }
 
+// second pass of the (item block, user) row order: the rows are already stably sorted by user (order1); key = item block
+__global__ void __launch_bounds__(256) fms_block_key_kernel(const uint32_t* __restrict__ order1, const int32_t* __restrict__ j,
+                                                            int64_t n, int32_t items_per_blk, uint32_t* __restrict__ key) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    key[i] = (uint32_t)(j[order1[i]] / items_per_blk);
+}
+
+// run table of fm_run_reduce_kernel: off[g * nblk + b] = first row (storage order, sorted by (item block, user)) whose
+// (block, user) is not below (b, g * G); g = 0 .. ngroups inclusive, so that run (g, b) = [off[g][b], off[g + 1][b])
+__global__ void __launch_bounds__(256) fms_run_offsets_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ j,
+                                                              int64_t n, int32_t items_per_blk, int32_t nblk, int32_t G,
+                                                              int32_t ngroups, uint32_t* __restrict__ off) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)(ngroups + 1) * nblk) return;
+  const int32_t g = (int32_t)(t / nblk), b = (int32_t)(t % nblk);
+  const int64_t ub = (int64_t)g * G;
+  int64_t lo = 0, hi = n;  // first row with (block, user) >= (b, ub)
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int32_t mb = j[mid] / items_per_blk;
+    const bool below = mb < b || (mb == b && (int64_t)u[mid] < ub);
+    if (below) lo = mid + 1; else hi = mid;
+  }
+  off[t] = (uint32_t)lo;
+}
+
 // context coordinate of a row: its context id while the feature index stays below p (FM.java:81), else absent
 __global__ void __launch_bounds__(256) fms_ctx_coord_kernel(const int32_t* __restrict__ c, int64_t n, int32_t C,
                                                             int32_t* __restrict__ coord) {

@@ -513,7 +513,7 @@ class FM(IterativeRecommender):
     def _desc(self):
         return capi.make_desc(self.trainMatrix, capi.FM, self.k, device=self.device, reg_lw=self.regLw,
                               reg_lf=self.regLf, num_context_dims=self.numContextDims, stream=self.stream,
-                              global_nnz=self.globalSize)
+                              global_nnz=self.globalSize, tuning=self.tuning)
 
     def _new_engine(self):
         if self.world > 1:  # the coordinate-sum all-reduces must be stream-ordered with the kernels

@@ -50,6 +50,54 @@ def test_fm_matches_sparse_oracle(oracle, cars_lib, users, items, dims, nnz, k, 
     assert st.kernel_launches > 0 and st.nnz == ts.nnz
 
 
+@pytest.mark.parametrize("tuning", ["fm_block_rows=700;fm_dense_min_rows=0;fm_run_users=256",
+                                    "fm_block_rows=300;fm_dense_min_rows=0;fm_run_users=64",
+                                    "fm_block_rows=700;fm_dense_min_rows=0;fm_run_fuse_update=0",
+                                    "fm_block_rows=700;fm_dense_min_rows=0;fm_runs=0"])
+@pytest.mark.parametrize("order", ["user_sorted", "shuffled"])
+def test_fm_user_field_run_reduce(oracle, cars_lib, tuning, order):
+    """fm_run_reduce_kernel (users: contiguous runs of the (item block, user) storage order; step (b) in its epilogue)
+    against the oracle -- for a caller's order that is NOT user-sorted too (the engine sorts the rows of a block by user
+    itself), with groups wider than the field, and with the gathering piece reduce it replaces (fm_runs=0)."""
+    ts, _, prob, arrs = fm_inputs(oracle, 700, 90, [4, 8], 40000, 8, seed=21)
+    if order == "shuffled":
+        perm = np.random.default_rng(5).permutation(ts.nnz)
+        ts.u, ts.j, ts.ctx, ts.r = (np.ascontiguousarray(a[perm]) for a in (ts.u, ts.j, ts.ctx, ts.r))
+        prob = oracle.fm_problem(ts, 8, 2, np.float32(0.01), np.float32(0.02))
+    iters = 3
+    got, losses, _ = run_gpu(ts, arrs, 8, 2, iters, tuning)
+    ref = clone(arrs)
+    e, Q = oracle.fm_prepare(prob, ref)
+    ref_losses = [oracle.fm_iteration(prob, ref, e, Q, closed_den=True) for _ in range(iters)]
+    for name in ("w0", "w", "V"):
+        np.testing.assert_allclose(got[name], ref[name], rtol=RTOL, atol=ATOL, err_msg=name)
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-10)
+
+
+def test_fm_sharded_entry_point_with_one_shard_equals_the_plain_iteration(oracle, cars_lib):
+    """cars_fm_iteration_sharded with a no-op all-reduce (one shard): the split coordinate step (partial sums ->
+    all-reduce -> finish) after fm_run_reduce_kernel gives the fused epilogue's result bit for bit."""
+    import torch
+    ts, _, prob, arrs = fm_inputs(oracle, 500, 80, [4, 8], 30000, 8, seed=23)
+    tuning = "fm_block_rows=700;fm_dense_min_rows=0"
+    a, la, _ = run_gpu(ts, arrs, 8, 2, 2, tuning)
+    desc = capi.make_desc(ts, capi.FM, 8, reg_lw=float(np.float32(0.01)), reg_lf=float(np.float32(0.02)), num_context_dims=2,
+                          tuning=tuning)
+    b = clone(arrs)
+    lb = []
+    with capi.FmEngine(desc, keepalive=ts) as eng:
+        eng.upload(b)
+        eng.prepare()
+        buf = torch.zeros(eng.exchange_doubles(), dtype=torch.float64, device="cuda:0")
+        torch.cuda.synchronize()
+        for _ in range(2):
+            lb.append(eng.iteration_sharded(buf.data_ptr(), lambda ptr, count: None))
+        eng.download(b)
+    assert la == lb
+    for name in ("w0", "w", "V"):
+        assert np.array_equal(a[name], b[name]), name
+
+
 def test_fm_within_1e5_of_the_literal_algorithm(oracle, cars_lib):
     ts, test, prob, arrs = fm_inputs(oracle, 40, 30, [2, 3], 900, 4, seed=9, holdout=0.15)
     dense = clone(arrs)
