@@ -459,26 +459,44 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
                                 r=pin(ts.r, pinned), ctx=pin(ts.ctx, pinned), num_conditions=ts.num_conditions,
                                 num_contexts=ts.num_contexts, ctx_ptr=ts.ctx_ptr, ctx_cond=ts.ctx_cond,
                                 global_mean=ts.global_mean)
-        rec2 = Rec(ts_e, None, conf=conf, device=local_rank, stream=stream, world=world, combine=args.combine)
-        rec2.initModel(init={k: pin(v, pinned) for k, v in arrs.items()})
-        barrier()
-        t0 = time.perf_counter()
-        rec2.buildModel()
-        torch.cuda.synchronize()
-        secs = time.perf_counter() - t0
-        tt = torch.tensor([secs], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        secs = float(tt[0])
+        init_e = {k: pin(v, pinned) for k, v in arrs.items()}
+        # buildModel() is run args.e2e_reps times from the same host buffers and the MEDIAN is reported, every sample
+        # listed: the first call of a process pays one-off costs that are not the path's (device-memory pool growth:
+        # 94-790 ms for the 9 GB schedule arena on the boxes measured, pinned staging buffers) -- a JVM training K folds
+        # pays them once.
+        samples, runs = [], []
+        for _ in range(max(1, args.e2e_reps)):
+            rec2 = Rec(ts_e, None, conf=conf, device=local_rank, stream=stream, world=world, combine=args.combine,
+                       tuning=args.tuning)
+            rec2.initModel(init={k: v.copy() if not pinned else v for k, v in init_e.items()})
+            if pinned:  # restore the initial model in place (the previous repetition trained it)
+                for k, v in arrs.items():
+                    np.copyto(init_e[k], v)
+            barrier()
+            t0 = time.perf_counter()
+            rec2.buildModel()
+            torch.cuda.synchronize()
+            secs = time.perf_counter() - t0
+            tt = torch.tensor([secs], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            samples.append(float(tt[0]))
+            runs.append(rec2)
+        order = sorted(range(len(samples)), key=lambda i: samples[i])
+        mid = order[len(order) // 2]
+        secs, rec2 = samples[mid], runs[mid]
         iters = len(rec2.iter_losses)
         st2 = rec2.stats
-        log(f"[bench] rank {rank}: buildModel() e2e ({'pinned' if pinned else 'pageable'}) {secs:.2f}s for {iters} epochs "
+        log(f"[bench] rank {rank}: buildModel() e2e ({'pinned' if pinned else 'pageable'}) {secs:.2f}s for {iters} epochs, "
+            f"median of {[round(x, 3) for x in samples]} "
             f"(schedule {st2.schedule_ms:.0f} ms, h2d {st2.h2d_bytes / 1e9:.2f} GB, d2h {st2.d2h_bytes / 1e9:.2f} GB)")
         return {"value": nnz_total * iters / secs, "unit": UNIT, "h2d_bytes_per_step": int(st2.h2d_bytes / max(1, iters)),
-                "d2h_bytes_per_step": int(st2.d2h_bytes / max(1, iters)), "seconds": secs, "epochs": iters,
+                "d2h_bytes_per_step": int(st2.d2h_bytes / max(1, iters)), "seconds": secs,
+                "seconds_samples": [round(x, 4) for x in samples], "statistic": "median", "epochs": iters,
                 "host_buffers": "pinned" if pinned else "pageable", "schedule_ms": st2.schedule_ms,
                 "schedule_copy_ms": st2.schedule_copy_ms, "schedule_levels_ms": st2.schedule_levels_ms,
-                "schedule_pack_ms": st2.schedule_pack_ms}
+                "schedule_pack_ms": st2.schedule_pack_ms,
+                "phase_seconds": {k: round(v, 4) for k, v in getattr(rec2, "phase_seconds", {}).items()}}
 
     e2e = e2e_run(True)
     keep_pinned.clear()
@@ -513,7 +531,7 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(f"{wl_name}:{mode}" if mode != "exact" else wl_name, {}).get("dram_bytes_per_launch")
     kernel = "sgd_fast_kernel" if mode == "fast" else ("sgd_serial_kernel" if wl["model"] == "camf_c" else "sgd_flagged_kernel")
-    mode_txt = ("fast (hogwild: user-ordered chunks, item side by red.global.add.f64; not serial-equivalent)" if mode == "fast"
+    mode_txt = ("fast (hogwild: user-ordered chunks, item side by red.global.add.f64 / TMA add-reduce; not serial-equivalent)" if mode == "fast"
                 else "exact (serial-equivalent; flagged wavefront schedule)")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -530,7 +548,8 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
                          "streamed per epoch vs 126 MB L2); no flush",
                    "e2e_definition": f"recommender.buildModel() with num.max.iter={args.steps} from pinned host buffers: "
                                      "cars_create (H2D ratings + device-built schedule) + cars_upload + epochs (loss D2H each) + "
-                                     "cars_download; e2e_pageable = the same from pageable buffers (what a JNI caller has)"},
+                                     "cars_download + cars_destroy; " + f"median of {max(1, args.e2e_reps)} calls, every sample in seconds_samples; " +
+                                     "e2e_pageable = the same from pageable buffers (what a JNI caller has)"},
         "clocks": clocks,
         "e2e": e2e,
         "e2e_pageable": e2e_pageable,
@@ -661,6 +680,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("CARS_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-reps", type=int, default=3, help="buildModel() repetitions of the end-to-end arm (median reported)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison at the bench's size (N = 1) and the "
                     "rmse_vs_serial mini-run (N > 1)")
     ap.add_argument("--mode", default=os.environ.get("CARS_BENCH_MODE", "exact"), choices=["exact", "fast"])

@@ -375,6 +375,7 @@ static int validate(const cars_desc* d) {
 }
 
 extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
+  const auto t_create = std::chrono::steady_clock::now();
   if (!out) return fail(nullptr, CARS_E_INVALID, "out is NULL");
   *out = nullptr;
   int rc = validate(desc);
@@ -777,6 +778,10 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   // the handle must not keep caller pointers
   h->d.u = h->d.j = h->d.ctx = nullptr; h->d.r = nullptr; h->d.ctx_ptr = h->d.ctx_cond = nullptr; h->d.stream = nullptr;
   h->d.gpu_ids = nullptr; h->d.tuning = nullptr; h->d.empty_conditions = nullptr;
+  if (h->tune.get_ll("sched_trace", 0) != 0)
+    fprintf(stderr, "[cars create] total %8.2f ms (before the schedule %8.2f ms, schedule %8.2f ms)\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_create).count(),
+            std::chrono::duration<double, std::milli>(t0 - t_create).count(), h->st.schedule_ms);
   *out = h;
   return CARS_OK;
 #undef CUDA_TRY_H
@@ -874,8 +879,11 @@ static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device, 
 
 extern "C" int cars_upload(cars_handle* h, const cars_model_arrays* host) {
   if (h && h->multi) return multi_transfer(h, host, true);
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = transfer(h, host, true);
   if (rc == CARS_OK) h->uploaded = true;
+  if (h && h->tune.get_ll("sched_trace", 0) != 0)
+    fprintf(stderr, "[cars upload] %8.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   return rc;
 }
 

@@ -359,12 +359,13 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
     if (rc) return bail(rc);
 #undef FS_TRY
     // run mode for the user field (fm_run_reduce_kernel): G consecutive users per CTA, G chosen so that a run -- the
-    // group's rows inside one item block -- is ~96 rows
+    // group's rows inside one item block -- is 24..48 rows (measured at 125 M rows, 25 rows per user: G = 128 / 256 / 512 ->
+    // 291.8 / 299.5 / 296.6 ms per iteration; shorter-lived CTAs leave more of their rows in L2 for the fused row update)
     if (h->row_blocks >= (int32_t)h->tune.get_ll("fm_run_min_blocks", 8) && N > 0) {
       FieldStore& fs = h->fld[0];
       const double rows_per_user_block = (double)N / ((double)h->U * (double)h->row_blocks);
       int G = 32;
-      while (G < 512 && (double)(2 * G) * rows_per_user_block <= 96.0) G *= 2;
+      while (G < 512 && (double)(2 * G) * rows_per_user_block <= 48.0) G *= 2;
       const long long tg = h->tune.get_ll("fm_run_users", 0);
       if (tg == 32 || tg == 64 || tg == 128 || tg == 256 || tg == 512) G = (int)tg;
       const int32_t ngroups = (h->U + G - 1) / G;

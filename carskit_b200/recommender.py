@@ -249,9 +249,13 @@ class IterativeRecommender:
         """cars_create + cars_upload: what buildModel() does before its first iteration."""
         if not self.model:
             raise RuntimeError("buildModel before initModel")
+        import time
+        t0 = time.perf_counter()
         eng = self._new_engine()
+        t1 = time.perf_counter()
         try:
             eng.upload(self.model)
+            self.open_seconds = {"create": t1 - t0, "upload": time.perf_counter() - t1}
             if self.world > 1:
                 from .sharding import ItemBlockExchange
                 self.exchange = ItemBlockExchange(eng, self._exchange_device(), self.group, self.combine,
@@ -295,17 +299,25 @@ class IterativeRecommender:
     def buildModel(self):
         """Replaces the per-rating loop of buildModel() (CAMF_CI.java:74-131 and siblings): flatten once,
         one cars_epoch per iteration, isConverged() on the host, copy the model back."""
+        import time
         self.iter_losses = []
+        t0 = time.perf_counter()
         eng = self.open_engine()
+        t1 = time.perf_counter()
         try:
             for it in range(1, self.numIters + 1):
                 if self.train_epoch(it):
                     break
+            t2 = time.perf_counter()
             eng.download(self.model)
+            t3 = time.perf_counter()
             self.stats = eng.stats()
         finally:
             if not getattr(self, "keep_engine", False):
                 self.close_engine()
+        # where the wall time of one buildModel() went (seconds): create + upload, the epoch loop, download, destroy
+        self.phase_seconds = {"open": t1 - t0, "epochs": t2 - t1, "download": t3 - t2, "close": time.perf_counter() - t3}
+        self.phase_seconds.update(getattr(self, "open_seconds", {}))
 
     # ---- consumers of the trained model ------------------------------------------------------------------
     def _eval_engine(self) -> capi.Engine:
