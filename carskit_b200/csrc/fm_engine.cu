@@ -463,7 +463,27 @@ extern "C" int cars_fm_prepare(cars_fm_handle* h) {
   if (!h) return CARS_E_INVALID;
   if (!h->uploaded) return fm_fail(h, CARS_E_STATE, "cars_fm_prepare before cars_fm_upload");
   FM_TRY(h, cudaSetDevice(h->device));
-  if (h->N) {
+  const bool tiled = h->tune.get_ll("fm_prepare_tiled", h->N >= 65536 ? 1 : 0) != 0;
+  if (h->N && tiled) {
+    // coordinate-major scratch copy of V (a row's coefficient vectors contiguous), then fm_prepare_tiled_kernel
+    double* d_vt = nullptr;
+    FM_TRY(h, fm_alloc(&d_vt, (size_t)h->p * h->k));
+    const dim3 tg((unsigned)((h->p + 31) / 32), (unsigned)((h->k + 31) / 32));
+    fm_untranspose_kernel<<<tg, 256, 0, h->stream>>>(h->d_V, h->p, h->k, d_vt);
+    const int smem = kPrepWarps * 3 * kPrepTile * (int)sizeof(double);
+    cudaError_t pe = cudaFuncSetAttribute(fm_prepare_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (pe == cudaSuccess) {
+      const int64_t want = (h->N + kPrepWarps * 32 - 1) / (kPrepWarps * 32);
+      const int64_t cap = (int64_t)h->sm_count * 4 * 8;
+      fm_prepare_tiled_kernel<<<(unsigned)(want < cap ? want : cap), kPrepWarps * 32, smem, h->stream>>>(
+          h->d_u, h->d_j, h->d_c, h->d_r, h->d_w, d_vt, h->d_w0, h->U, h->I, h->p, h->k, h->xc, h->N, h->Nq, h->d_e, h->d_Qc);
+      pe = cudaGetLastError();
+    }
+    if (pe == cudaSuccess) pe = cudaStreamSynchronize(h->stream);
+    cudaFree(d_vt);
+    FM_TRY(h, pe);
+    h->launches += 2;
+  } else if (h->N) {
     const unsigned blocks = (unsigned)((h->N + 255) / 256);
     fm_prepare_kernel<<<blocks, 256, 0, h->stream>>>(h->d_u, h->d_j, h->d_c, h->d_r, h->d_w, h->d_V, h->d_w0, h->U, h->I,
                                                     h->p, h->k, h->xc, h->N, h->Nq, h->d_e, h->d_Qc);

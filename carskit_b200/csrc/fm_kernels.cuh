@@ -140,6 +140,72 @@ __global__ void __launch_bounds__(256) fm_prepare_kernel(const int32_t* __restri
   }
 }
 
+// The pre-pass for large inputs.  fm_prepare_kernel above walks V factor-major (V[f * p + i]): in the engine's row order a
+// warp's 32 rows belong to 32 different users, so every 8-byte read of a user's coefficient pulls its own 32-byte sector
+// -- 412 GB of DRAM reads for 125 M rows x 64 factors, 87 ms (profiles/r2/ncu_summary_fm_prepare_125M.txt).  Here V comes
+// coordinate-major (Vt[i * k + f], a scratch transpose made by cars_fm_prepare): a row's three coefficient vectors are
+// contiguous, a warp stages 16 factors of its 32 rows at a time in shared memory with coalesced 128-byte reads
+// (16 lanes per row), and every lane then walks ITS row's factors in order -- the same operations in the same order as
+// fm_predict_one / fm_prepare_kernel, so e and Qc are bit-identical to theirs.
+constexpr int kPrepFC = 16;         // factors staged per step
+constexpr int kPrepWarps = 4;       // per CTA
+constexpr int kPrepTile = 32 * (kPrepFC + 1);  // doubles per staged array (row stride 17: conflict-free both ways)
+__global__ void __launch_bounds__(kPrepWarps * 32) fm_prepare_tiled_kernel(
+    const int32_t* __restrict__ u, const int32_t* __restrict__ j, const int32_t* __restrict__ c, const double* __restrict__ r,
+    const double* __restrict__ w, const double* __restrict__ Vt, const double* __restrict__ w0p, int U, int I, int p, int k,
+    double xc, int64_t N, int64_t Nq, double* __restrict__ e, double* __restrict__ Qc) {
+  extern __shared__ __align__(16) unsigned char prep_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* tu = reinterpret_cast<double*>(prep_smem) + (size_t)warp * 3 * kPrepTile;
+  double* tj = tu + kPrepTile;
+  double* tc = tj + kPrepTile;
+  const double w0 = *w0p;
+  const int srow = lane >> 4, sf = lane & 15;  // staging: 16 lanes per row, two rows per load instruction
+  for (int64_t row0 = ((int64_t)blockIdx.x * kPrepWarps + warp) * 32; row0 < N; row0 += (int64_t)gridDim.x * kPrepWarps * 32) {
+    const int64_t n = row0 + lane;
+    const bool ok = n < N;
+    const int iu = ok ? u[n] : 0, ij = U + (ok ? j[n] : 0), ic = U + I + (ok ? c[n] : 0);
+    const bool has_c = ic < p;
+    double pred = w0;
+    pred = __dadd_rn(pred, __dmul_rn(w[iu], 1.0));
+    pred = __dadd_rn(pred, __dmul_rn(w[ij], 1.0));
+    if (has_c) pred = __dadd_rn(pred, __dmul_rn(w[ic], xc));
+    double sum = 0.0;
+    for (int f0 = 0; f0 < k; f0 += kPrepFC) {
+      const int fc = k - f0 < kPrepFC ? k - f0 : kPrepFC;
+#pragma unroll 4
+      for (int rr = 0; rr < 32; rr += 2) {
+        const int row = rr + srow;
+        const int cu = __shfl_sync(0xffffffffu, iu, row), cj = __shfl_sync(0xffffffffu, ij, row);
+        const int cc = __shfl_sync(0xffffffffu, has_c ? ic : -1, row);
+        if (sf < fc) {
+          tu[row * (kPrepFC + 1) + sf] = Vt[(int64_t)cu * k + f0 + sf];
+          tj[row * (kPrepFC + 1) + sf] = Vt[(int64_t)cj * k + f0 + sf];
+          if (cc >= 0) tc[row * (kPrepFC + 1) + sf] = Vt[(int64_t)cc * k + f0 + sf];
+        }
+      }
+      __syncwarp();
+      for (int f = 0; f < fc; f++) {
+        const double vu = tu[lane * (kPrepFC + 1) + f], vj = tj[lane * (kPrepFC + 1) + f];
+        double sum1 = 0.0, sum2 = 0.0, v = 0.0;
+        sum1 = __dadd_rn(sum1, vu); sum2 = __dadd_rn(sum2, __dmul_rn(vu, vu));
+        sum1 = __dadd_rn(sum1, vj); sum2 = __dadd_rn(sum2, __dmul_rn(vj, vj));
+        v = __dadd_rn(v, vu);
+        v = __dadd_rn(v, vj);
+        if (has_c) {
+          const double d = __dmul_rn(tc[lane * (kPrepFC + 1) + f], xc);
+          sum1 = __dadd_rn(sum1, d); sum2 = __dadd_rn(sum2, __dmul_rn(d, d));
+          v = __dadd_rn(v, d);
+        }
+        sum = __dadd_rn(sum, __dsub_rn(__dmul_rn(sum1, sum1), sum2));
+        if (ok) Qc[(int64_t)(f0 + f) * Nq + n] = v;
+      }
+      __syncwarp();
+    }
+    if (ok) e[n] = __dsub_rn(r[n], __dadd_rn(pred, __dmul_rn(0.5, sum)));
+  }
+}
+
 __global__ void __launch_bounds__(256) fm_predict_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ j,
                                                          const int32_t* __restrict__ c, const double* __restrict__ w,
                                                          const double* __restrict__ V, const double* __restrict__ w0p,

@@ -6,7 +6,15 @@
 //            sched_trace=1    host wall time of every schedule-build phase on stderr
 //            copy_threads=<n> host threads of the staged copier (1..8)
 //            fast_chunk=<n>   ratings per chunk of the FAST schedule
-//   FM       fm_block_rows, fm_dense_min_rows, fm_lanes_per_piece, fm_ppg_short, fm_ppg_long
+//            fast_hot_rows=<n> fast_hot_flush=<n>   FAST: hot item rows per CTA (0 = off), updates between flushes
+//            tagged=1 tagged_ctas=<n>   EXACT by tagged rows (K1t) instead of completion counters
+//            pool=0           cudaMalloc / cudaFree instead of the stream-ordered pool
+//   FM       fm_block_rows=<n>      rows per item block of the internal row order (0 = keep the caller's order)
+//            fm_dense_min_rows=<n>  smallest input whose context field is reduced by streaming
+//            fm_runs=0              users by the gathering piece reduce instead of fm_run_reduce_kernel
+//            fm_run_users=<32..512> users per CTA of fm_run_reduce_kernel; fm_run_min_blocks=<n>; fm_run_fuse_update=0
+//            fm_lanes_per_piece, fm_ppg_short, fm_ppg_long   shapes of fm_piece_reduce_kernel
+//            fm_prepare_tiled=0|1   pre-pass over factor-major V (small inputs) / over a coordinate-major scratch copy
 #pragma once
 #include <cstdlib>
 #include <string>

@@ -98,6 +98,19 @@ def test_fm_sharded_entry_point_with_one_shard_equals_the_plain_iteration(oracle
         assert np.array_equal(a[name], b[name]), name
 
 
+def test_fm_tiled_prepass_is_bit_identical_to_the_plain_one(oracle, cars_lib):
+    """fm_prepare_tiled_kernel (coordinate-major scratch copy of V, 16 factors of 32 rows staged per step) performs
+    fm_prepare_kernel's operations in the same order: e and Qc, hence everything trained from them, are bit-identical.
+    k = 21: a ragged last factor step; contexts with index >= p (no feature) are in fm_inputs' data."""
+    for users, items, dims, nnz, k in [(300, 120, [4, 8], 20000, 21), (12, 9, [2, 3], 150, 3), (500, 64, [6], 9000, 64)]:
+        ts, _, prob, arrs = fm_inputs(oracle, users, items, dims, nnz, k, seed=31)
+        a, la, _ = run_gpu(ts, arrs, k, len(dims), 2, "fm_prepare_tiled=0")
+        b, lb, _ = run_gpu(ts, arrs, k, len(dims), 2, "fm_prepare_tiled=1")
+        assert la == lb
+        for name in ("w0", "w", "V"):
+            assert np.array_equal(a[name], b[name]), (name, k)
+
+
 def test_fm_within_1e5_of_the_literal_algorithm(oracle, cars_lib):
     ts, test, prob, arrs = fm_inputs(oracle, 40, 30, [2, 3], 900, 4, seed=9, holdout=0.15)
     dense = clone(arrs)
