@@ -51,6 +51,17 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// cp.async (LDGSTS): global -> shared copies that occupy no register while in flight
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // V is kept FACTOR-MAJOR on the device (V[f * p + i]; the caller's array is [p x k] row-major and is transposed on
 // upload / download): every coordinate step works on one factor of all coordinates of a field, a unit-stride
 // slice this way (a 512-byte stride -- one DRAM sector per coordinate, read and written -- the other way).
@@ -178,12 +189,14 @@ __global__ void __launch_bounds__(kPrepWarps * 32) fm_prepare_tiled_kernel(
         const int row = rr + srow;
         const int cu = __shfl_sync(0xffffffffu, iu, row), cj = __shfl_sync(0xffffffffu, ij, row);
         const int cc = __shfl_sync(0xffffffffu, has_c ? ic : -1, row);
-        if (sf < fc) {
-          tu[row * (kPrepFC + 1) + sf] = Vt[(int64_t)cu * k + f0 + sf];
-          tj[row * (kPrepFC + 1) + sf] = Vt[(int64_t)cj * k + f0 + sf];
-          if (cc >= 0) tc[row * (kPrepFC + 1) + sf] = Vt[(int64_t)cc * k + f0 + sf];
+        if (sf < fc) {  // cp.async: all 48 copies of the step are in flight together, no register holds them
+          cp_async_8(tu + row * (kPrepFC + 1) + sf, Vt + (int64_t)cu * k + f0 + sf);
+          cp_async_8(tj + row * (kPrepFC + 1) + sf, Vt + (int64_t)cj * k + f0 + sf);
+          if (cc >= 0) cp_async_8(tc + row * (kPrepFC + 1) + sf, Vt + (int64_t)cc * k + f0 + sf);
         }
       }
+      cp_async_commit();
+      cp_async_wait<0>();
       __syncwarp();
       for (int f = 0; f < fc; f++) {
         const double vu = tu[lane * (kPrepFC + 1) + f], vj = tj[lane * (kPrepFC + 1) + f];
@@ -374,16 +387,6 @@ constexpr int kRunSlotBytes = 32 * 4 + 32 * 8 + 32 * 8;  // coordinate, e, Qf of
 __host__ __device__ constexpr size_t fm_run_smem_bytes(int G) {
   return (size_t)G * sizeof(double) + (size_t)8 * G * sizeof(double2) + (size_t)8 * kRunSlots * kRunSlotBytes;
 }
-__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // iterator over the 32-row chunks of a warp's runs of one batch (lane t holds the bounds of the batch's t-th run)
 struct RunChunks {
   uint32_t rs, re, pos, end;

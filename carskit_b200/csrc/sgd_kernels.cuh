@@ -146,8 +146,11 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 __device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-// Consumer side of the completion counters.  The producer publishes with the release pattern (fence.acq_rel.gpu, then
+// Producer side: a RELEASE fence is all the release pattern needs.  fence.acq_rel.gpu lowers to MEMBAR.ALL.GPU + ERRBAR +
+// CCTL.IVALL; fence.release.gpu to the same without the CCTL.IVALL (an L1 invalidation per rating that orders nothing the
+// producer needs -- its own later loads of other rows go through the consumer pattern of THEIR ratings).
+__device__ __forceinline__ void fence_release_gpu() { asm volatile("fence.release.gpu;" ::: "memory"); }
+// Consumer side of the completion counters.  The producer publishes with the release pattern (fence.release.gpu, then
 // relaxed stores).  Once the relaxed poll has succeeded, the lanes that polled re-read their counter with
 // ld.acquire.gpu: that load observes the released value (or a later one), so it synchronizes-with the producer's fence
 // -- the PTX-formal acquire pattern -- and the __syncwarp that follows extends the ordering to the group's other lanes
@@ -731,7 +734,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
                                                           us, first, last));
         __syncwarp(gmask);  // the group's stores happen-before lane 0's fence
         if (gl == 0) {      // release pattern for BOTH counters: one fence, then two relaxed (strong) stores
-          fence_acq_rel_gpu();
+          fence_release_gpu();
           st_relaxed_u32(s.done_j + rec.j, (unsigned)rec.kj + 1u);
           if (last) st_relaxed_u32(s.done_u + rec.u, (unsigned)rec.ku + 1u);
         }
@@ -753,7 +756,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 // inside a warp).  Levels overlap: the tail of level L runs beside the head of level L+1.
 //
 // Memory ordering: the producer stores its rows (st.global.cg), __syncwarp, then lane 0 issues ONE
-// fence.acq_rel.gpu (MEMBAR.ALL.GPU, cumulative over the group's stores) followed by the two relaxed counter
+// fence.release.gpu (MEMBAR.ALL.GPU, cumulative over the group's stores) followed by the two relaxed counter
 // stores -- the release pattern for both counters.  The consumer polls with ld.relaxed.gpu and, after the branch
 // on the polled values, one ld.acquire.gpu of each counter (acquire_after_poll) and __syncwarp, reads the rows with
 // ld.global.cg: release pattern on one side, acquire pattern on the other.
@@ -832,7 +835,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
         const long long tc3 = clock64();
 #endif
         if (gl == 0) {  // release pattern for BOTH counters: one fence (MEMBAR.ALL.GPU), then two relaxed stores
-          fence_acq_rel_gpu();
+          fence_release_gpu();
           st_relaxed_u32(done_j + rec.j, (unsigned)rec.kj + 1u);
           st_relaxed_u32(done_u + rec.u, (unsigned)rec.ku + 1u);
         }
