@@ -70,6 +70,12 @@ WORKLOADS = {
     "camf_cu_f128_1250Kx1Mx64c_125M_per_gpu": dict(model="camf_cu", F=128, users=1_250_000, items=1_000_000,
                                                    dims=[16, 16, 16, 16], nnz=125_000_000, seed=20261017),
     "fm_k16_tiny": dict(model="fm", F=16, users=5_000, items=1_000, dims=[32], nnz=200_000, seed=20261017),
+    # the reference's DEFAULT factor count (num.factors=10, setting.conf) and BiasedMF at config 3's size: the run-time-F
+    # path of the kernels (F = 64 / 128 are compiled in)
+    "camf_ci_f10_1Mx100Kx32c_100M": dict(model="camf_ci", F=10, users=1_000_000, items=100_000, dims=[8, 8, 8, 8],
+                                         nnz=100_000_000, seed=20261017),
+    "biasedmf_f10_1Mx100K_100M": dict(model="biasedmf", F=10, users=1_000_000, items=100_000, dims=None,
+                                      nnz=100_000_000, seed=20261017),
 }
 DEFAULT_WORKLOAD = "camf_ci_f64_1Mx100Kx32c_100M"
 
@@ -145,11 +151,19 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # inputs
 # ------------------------------------------------------------------------------------------------------
-def make_inputs(wl: dict, rank: int):
-    from carskit_b200 import capi, synth
+def make_inputs(wl: dict, rank: int, world: int = 1, strong: bool = False):
+    """weak scaling (default, what the driver's SCALE run measures): every rank trains its OWN wl-sized set of users.
+    strong (--scaling strong): the ONE wl-sized training set is cut into `world` user ranges, rank r trains range r."""
+    from carskit_b200 import capi, sharding, synth
     t0 = time.time()
-    ts, _ = synth.make_training_set(wl["users"], wl["items"], wl["dims"], wl["nnz"], seed=wl["seed"] + rank,
+    ts, _ = synth.make_training_set(wl["users"], wl["items"], wl["dims"], wl["nnz"], seed=wl["seed"] + (0 if strong else rank),
                                     order="user_sorted", item_zipf=wl.get("item_zipf", 0.0))
+    if strong and world > 1:
+        ts, _ = sharding.shard_training_set(ts, rank, world)
+        ts = capi.TrainingSet(num_users=ts.num_users, num_items=ts.num_items, u=np.ascontiguousarray(ts.u),
+                              j=np.ascontiguousarray(ts.j), r=np.ascontiguousarray(ts.r),
+                              ctx=None if ts.ctx is None else np.ascontiguousarray(ts.ctx), num_conditions=ts.num_conditions,
+                              num_contexts=ts.num_contexts, ctx_ptr=ts.ctx_ptr, ctx_cond=ts.ctx_cond, global_mean=ts.global_mean)
     model = capi.MODEL_NAMES[wl["model"]]
     F = wl["F"]
     rng = np.random.default_rng(wl["seed"] + 7919)  # same model init on every rank (item side is replicated)
@@ -370,7 +384,8 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
 
     mode = args.mode
-    ts, model, arrs = make_inputs(wl, rank)
+    strong = args.scaling == "strong" and world > 1
+    ts, model, arrs = make_inputs(wl, rank, world, strong)
     F = wl["F"]
     D = len(wl["dims"]) if wl["dims"] else 0
     B = algorithmic_bytes(wl["model"], F, D)
@@ -535,15 +550,17 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
                 else "exact (serial-equivalent; flagged wavefront schedule)")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl_name, "recommender": wl["model"], "factors": F, "users": wl["users"],
                    "items": wl["items"], "conditions": int(sum(wl["dims"])) if wl["dims"] else 0, "context_dims": D,
                    "nnz": nnz_local, "nnz_total": int(nnz_total), "item_zipf": wl.get("item_zipf", 0.0), "mode": mode_txt,
                    "levels": int(st0.num_levels), "max_item_degree": int(st0.max_item_degree),
                    "fast_min_item_scale": st0.fast_min_item_scale,
-                   "parallelism": f"user-range shards x{world}: users/nnz above are PER GPU; item block combined "
-                                  f"({args.combine}) by one all-reduce per epoch" if world > 1 else "1 gpu",
+                   "parallelism": (f"user-range shards x{world}: " +
+                                   ("users above are the WHOLE workload, cut into ranges (strong scaling), nnz is per GPU; "
+                                    if strong else "users/nnz above are PER GPU; ") +
+                                   f"item block combined ({args.combine}) by one all-reduce per epoch") if world > 1 else "1 gpu",
                    "l2": f"inputs larger than L2 (rating records {nnz_local * 32 / 1e9:.1f} GB + P {wl['users'] * F * 8 / 1e9:.2f} GB "
                          "streamed per epoch vs 126 MB L2); no flush",
                    "e2e_definition": f"recommender.buildModel() with num.max.iter={args.steps} from pinned host buffers: "
@@ -680,6 +697,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("CARS_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="N > 1: weak = every rank trains its own workload-sized user range (the driver's SCALE run); "
+                         "strong = the one workload is cut into N user ranges")
     ap.add_argument("--e2e-reps", type=int, default=3, help="buildModel() repetitions of the end-to-end arm (median reported)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison at the bench's size (N = 1) and the "
                     "rmse_vs_serial mini-run (N > 1)")

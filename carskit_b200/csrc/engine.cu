@@ -269,14 +269,23 @@ static LaunchPlan pick_flagged(int Fp, int variant, int F = 0) {
       }
       return pick_flagged_generic<MODEL>(Fp);
     }
+    case 9: {  // A/B of the default at F = 128: 16 lanes per rating x 3 CTAs per SM (48 ratings in flight per SM)
+      LaunchPlan p;
+      if (F == 128) {
+        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 16, 4, 256, 3, true, 128>; p.lpr = 16; p.v = 4;
+        return p;
+      }
+      return pick_flagged<MODEL>(Fp, 8, F);
+    }
     case 8: {  // as 7 with the factor count a compile-time constant (F = 64 / F = 128 exactly)
       LaunchPlan p;
       if (F == 64) {
         p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 4, 8, 256, 2, true, 64>; p.lpr = 4; p.v = 8;
         return p;
       }
-      if (F == 128) {
-        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 16, 4, 256, 3, true, 128>; p.lpr = 16; p.v = 4;
+      if (F == 128) {  // 8 lanes per rating (16 factors per lane), 2 CTAs per SM: 64 ratings in flight per SM -- 118.4 ms
+                       // against 131.1 ms per epoch of config 5's shard for 16 lanes x 3 CTAs (profiles/r2/config5_shapes.txt)
+        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 8, 8, 256, 2, true, 128>; p.lpr = 8; p.v = 8;
         return p;
       }
       return pick_flagged<MODEL>(Fp, 7, F);
