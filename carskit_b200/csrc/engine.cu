@@ -267,8 +267,15 @@ static LaunchPlan pick_flagged(int Fp, int variant, int F = 0) {
         p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 4, 8, 256, 2>; p.lpr = 4; p.v = 8;
         return p;
       }
+      if (Fp <= 16) {  // the reference's default F = 10: 4 lanes per rating, 27.5 against 30.6 ms per 100 M ratings with 8
+                       // (CAMF_CI; BiasedMF 26.7 / 27.4; profiles/r2/config5_shapes.txt)
+        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 4, 2, 256, 3>; p.lpr = 4; p.v = 2;
+        return p;
+      }
       return pick_flagged_generic<MODEL>(Fp);
     }
+    case 11:  // A/B of the default for short rows: the generic table (8 lanes per rating)
+      return pick_flagged_generic<MODEL>(Fp);
     case 9: {  // A/B of the default at F = 128: 16 lanes per rating x 3 CTAs per SM (48 ratings in flight per SM)
       LaunchPlan p;
       if (F == 128) {
@@ -507,7 +514,9 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     h->grid = 1; h->block = 32;
     h->smem = (size_t)(Fp + 2) * 8;
   } else {
-    const int shape = (int)h->tune.get_ll("shape", fast ? 0 : 8);
+    // EXACT default 8; short rows with more than 4 context dimensions keep 8 lanes per rating (shape 11): the lanes of a
+    // group fetch one condition cell each, dimensions beyond the group's lanes take the slow path
+    const int shape = (int)h->tune.get_ll("shape", fast ? 0 : (Fp <= 16 && Dmax > 4 ? 11 : 8));
     LaunchPlan plan = fast ? pick_fast_plan(model, Fp, F, shape)
                       : h->dataflow ? pick_dataflow_plan(model, Fp)
                       : h->flagged ? pick_flagged_plan(model, Fp, F, shape) : pick_plan(model, Fp);
