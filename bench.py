@@ -74,6 +74,8 @@ WORKLOADS = {
     # path of the kernels (F = 64 / 128 are compiled in)
     "camf_ci_f10_1Mx100Kx32c_100M": dict(model="camf_ci", F=10, users=1_000_000, items=100_000, dims=[8, 8, 8, 8],
                                          nnz=100_000_000, seed=20261017),
+    "camf_ci_f32_1Mx100Kx32c_100M": dict(model="camf_ci", F=32, users=1_000_000, items=100_000, dims=[8, 8, 8, 8],
+                                         nnz=100_000_000, seed=20261017),
     "biasedmf_f10_1Mx100K_100M": dict(model="biasedmf", F=10, users=1_000_000, items=100_000, dims=None,
                                       nnz=100_000_000, seed=20261017),
 }

@@ -211,8 +211,8 @@ static LaunchPlan pick_dataflow_plan(int model, int Fp) {
 }
 
 // FAST (hogwild) kernel.  Default (shape 0): the Q-row step of a rating is staged in shared memory and added to Q[j] by
-// ONE TMA add-reduce (BULK, UBLKRED.G.S.ADD.F64) for Fp >= 32 -- 27.5 ms per 100 M ratings against 34.4 ms with 64 scalar
-// REDG per rating on the same box (profiles/r2/fast_bulk_reduce.txt); rows shorter than 32 factors keep the scalar
+// ONE TMA add-reduce (BULK, UBLKRED.G.S.ADD.F64) for Fp >= 64 -- 27.5 ms per 100 M ratings against 34.4 ms with 64 scalar
+// REDG per rating on the same box (profiles/r2/fast_bulk_reduce.txt); rows shorter than 64 factors keep the scalar
 // reductions.  F = 64: 8 lanes per rating, 256-bit row accesses, F compiled in, 256 threads x 2 CTAs per SM; F = 128: 16
 // lanes.  shape 5 = the scalar-REDG kernels (A/B), shape 1 / 2 / 4 = other launch shapes measured and rejected.
 template <int MODEL, bool BULK>
@@ -233,6 +233,9 @@ static LaunchPlan pick_fast(int Fp, int F, int shape) {
   LaunchPlan p;
   p.threads = 256;
   const bool bulk = shape != 5 && shape != 1 && shape != 2;
+  if (Fp > 16 && Fp <= 32 && shape == 7) {  // 4 lanes per rating up to 32 factors: 15.0 against 18.2 ms per 100 M ratings (F = 32)
+    p.fn = (const void*)sgd_fast_kernel<MODEL, 4, 4, 256, 2, false, 0, false>; p.lpr = 4; p.v = 4; return p;
+  }
   if (Fp <= 16 && shape == 6) {  // short rows, 4 lanes per rating (8 ratings per warp instruction instead of 4)
     p.fn = (const void*)sgd_fast_kernel<MODEL, 4, 2, 256, 2, false, 0, false>; p.lpr = 4; p.v = 2; return p;
   }
@@ -243,7 +246,7 @@ static LaunchPlan pick_fast(int Fp, int F, int shape) {
   if (F == 64 && shape == 2) { p.fn = (const void*)sgd_fast_kernel<MODEL, 4, 8, 256, 2, true, 64>; p.lpr = 4; p.v = 8; return p; }
   if (F == 128 && bulk) { p.fn = (const void*)sgd_fast_kernel<MODEL, 16, 4, 256, 2, true, 128, true>; p.lpr = 16; p.v = 4; p.bulk = true; return p; }
   if (F == 128) { p.fn = (const void*)sgd_fast_kernel<MODEL, 16, 4, 256, 2, true, 128>; p.lpr = 16; p.v = 4; return p; }
-  if (bulk && Fp >= 32) return pick_fast_generic<MODEL, true>(Fp);
+  if (bulk && Fp >= 64) return pick_fast_generic<MODEL, true>(Fp);  // F = 32: one 256-byte TMA reduce per rating LOSES to 32 REDG (24.4 vs 18.2 ms)
   return pick_fast_generic<MODEL, false>(Fp);
 }
 static LaunchPlan pick_fast_plan(int model, int Fp, int F, int shape) {
@@ -273,6 +276,10 @@ static LaunchPlan pick_flagged(int Fp, int variant, int F = 0) {
       if (Fp <= 16) {  // the reference's default F = 10: 4 lanes per rating, 27.5 against 30.6 ms per 100 M ratings with 8
                        // (CAMF_CI; BiasedMF 26.7 / 27.4; profiles/r2/config5_shapes.txt)
         p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 4, 2, 256, 3>; p.lpr = 4; p.v = 2;
+        return p;
+      }
+      if (Fp <= 32) {  // F = 32: 31.3 against 34.7 ms per 100 M ratings with 8 lanes
+        p.threads = 256; p.fn = (const void*)sgd_flagged_kernel<MODEL, 4, 4, 256, 3>; p.lpr = 4; p.v = 4;
         return p;
       }
       return pick_flagged_generic<MODEL>(Fp);
@@ -517,11 +524,13 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     h->grid = 1; h->block = 32;
     h->smem = (size_t)(Fp + 2) * 8;
   } else {
-    // EXACT default 8; short rows with more than 4 context dimensions keep 8 lanes per rating (shape 11): the lanes of a
+    // EXACT default 8; rows of at most 32 factors with more than 4 context dimensions keep 8 lanes per rating (shape 11): the lanes of a
     // group fetch one condition cell each, dimensions beyond the group's lanes take the slow path
-    // FAST default 0; short rows with at most 4 context dimensions run 4 lanes per rating (shape 6): 8 ratings per warp
+    // FAST default 0; rows of at most 16 / 32 factors with at most 4 context dimensions run 4 lanes per rating (shape 6 / 7): 8 ratings per warp
     // instruction -- BiasedMF F = 10: 7.8 against 11.4 ms per 100 M ratings, CAMF_CI F = 10: 11.6 against 16.0
-    const int shape = (int)h->tune.get_ll("shape", fast ? (Fp <= 16 && Dmax <= 4 ? 6 : 0) : (Fp <= 16 && Dmax > 4 ? 11 : 8));
+    const bool few_dims = Dmax <= 4;
+    const int shape = (int)h->tune.get_ll("shape", fast ? (few_dims && Fp <= 16 ? 6 : few_dims && Fp <= 32 ? 7 : 0)
+                                                        : (Fp <= 32 && !few_dims ? 11 : 8));
     LaunchPlan plan = fast ? pick_fast_plan(model, Fp, F, shape)
                       : h->dataflow ? pick_dataflow_plan(model, Fp)
                       : h->flagged ? pick_flagged_plan(model, Fp, F, shape) : pick_plan(model, Fp);
