@@ -30,6 +30,10 @@ __device__ __forceinline__ unsigned long long sortable_key(double v) {
 // "not a candidate for this query": below every real key
 constexpr unsigned long long kRankDropped = 0ull;
 
+__device__ __forceinline__ void rank_cp_async_8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
 // scores[q][c] = sortable key of predict(u_q, cand_c, ctx_q) if it is a number > bin_thold, else kRankDropped
 template <int MODEL>
 __global__ void __launch_bounds__(256) rank_score_kernel(DeviceModel m, int64_t q0, int64_t nq, const int32_t* __restrict__ qu,
@@ -56,16 +60,22 @@ __global__ void __launch_bounds__(256) rank_score_kernel(DeviceModel m, int64_t 
   for (int f0 = 0; f0 < F; f0 += FC) {
     const int fl = F - f0 < FC ? F - f0 : FC;
     __syncthreads();
+    // tile fill by cp.async: all of a thread's 32 copies are in flight together and hold no register (with plain loads
+    // the STS behind each LDG carried 54 % of the kernel's stall samples, profiles/r2/ncu_summary_rank_score_4x4_tile.txt)
     for (int i = threadIdx.x; i < kRankTQ * fl; i += 256) {
       const int r = i / fl, f = i % fl;
       const int64_t q = qt + r;
-      Ps[r * ld + f] = q < nq ? m.P[(int64_t)qu[q0 + q] * m.Fp + f0 + f] : 0.0;
+      if (q < nq) rank_cp_async_8(Ps + r * ld + f, m.P + (int64_t)qu[q0 + q] * m.Fp + f0 + f);
+      else Ps[r * ld + f] = 0.0;
     }
     for (int i = threadIdx.x; i < kRankTJ * fl; i += 256) {
       const int r = i / fl, f = i % fl;
       const int c = ct + r;
-      Qs[r * ld + f] = c < num_cand ? m.Q[(int64_t)cand[c] * m.Fp + f0 + f] : 0.0;
+      if (c < num_cand) rank_cp_async_8(Qs + r * ld + f, m.Q + (int64_t)cand[c] * m.Fp + f0 + f);
+      else Qs[r * ld + f] = 0.0;
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     const double* p0 = Ps + (4 * ty) * ld;
     const double* qq = Qs + tx * ld;
