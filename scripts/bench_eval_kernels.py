@@ -30,21 +30,27 @@ with capi.Engine(desc, keepalive=ts) as eng:
     j = rng.integers(0, I, n_pred, dtype=np.int32)
     c = rng.integers(0, ts.num_contexts, n_pred, dtype=np.int32)
     eng.predict(u[:1000], j[:1000], c[:1000], bound=True, min_rate=1.0, max_rate=5.0)
-    t0 = time.perf_counter()
-    out = eng.predict(u, j, c, bound=True, min_rate=1.0, max_rate=5.0)
-    dt = time.perf_counter() - t0
+    samples = []
+    for _ in range(3):  # the first full-size call of a process also grows the device-memory pool: median of three, all listed
+        t0 = time.perf_counter()
+        out = eng.predict(u, j, c, bound=True, min_rate=1.0, max_rate=5.0)
+        samples.append(time.perf_counter() - t0)
+    dt = sorted(samples)[1]
     B = 2 * F * 8 + 12 + 8 + 8 + 4 * 8
-    print(json.dumps({"call": "cars_predict", "queries": n_pred, "seconds_e2e_host_buffers": dt, "queries_per_s_e2e": n_pred / dt,
-                      "algorithmic_bytes_per_query": B, "checksum": float(out[:1000].sum())}))
+    print(json.dumps({"call": "cars_predict", "queries": n_pred, "seconds_e2e_host_buffers": dt, "seconds_samples": samples,
+                      "queries_per_s_e2e": n_pred / dt, "algorithmic_bytes_per_query": B, "checksum": float(out[:1000].sum())}))
     qu = rng.integers(0, U, n_q, dtype=np.int32)
     qc = rng.integers(0, ts.num_contexts, n_q, dtype=np.int32)
     cand = rng.permutation(I).astype(np.int32)
     rptr = np.arange(n_q + 1, dtype=np.int64) * 20
     ritems = rng.integers(0, I, 20 * n_q, dtype=np.int32)
     eng.rank_topn(qu[:64], qc[:64], cand, rptr[:65], ritems[:64 * 20], -1.0, 10)
-    t0 = time.perf_counter()
-    items, scores, count, kept = eng.rank_topn(qu, qc, cand, rptr, ritems, -1.0, 10)
-    dt = time.perf_counter() - t0
+    samples = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        items, scores, count, kept = eng.rank_topn(qu, qc, cand, rptr, ritems, -1.0, 10)
+        samples.append(time.perf_counter() - t0)
+    dt = sorted(samples)[1]
     print(json.dumps({"call": "cars_rank_topn", "queries": n_q, "candidates": I, "num_recs": 10, "seconds_e2e_host_buffers": dt,
-                      "scores_per_s_e2e": n_q * I / dt, "flop_per_score": 2 * F, "key_bytes_per_score": 16,
+                      "seconds_samples": samples, "scores_per_s_e2e": n_q * I / dt, "flop_per_score": 2 * F, "key_bytes_per_score": 16,
                       "checksum": int(items[:100].sum()), "kept_mean": float(kept.mean())}))
