@@ -663,30 +663,40 @@ extern "C" int cars_fm_predict(cars_fm_handle* h, int64_t n, const int32_t* u, c
   if (!h->uploaded) return fm_fail(h, CARS_E_STATE, "cars_fm_predict before cars_fm_upload");
   if (n < 0 || (n > 0 && (!u || !j || !ctx || !out))) return fm_fail(h, CARS_E_INVALID, "bad predict arguments");
   if (n == 0) return CARS_OK;
-  for (int64_t i = 0; i < n; i++)
-    if ((uint32_t)u[i] >= (uint32_t)h->U || (uint32_t)j[i] >= (uint32_t)h->I || ctx[i] < 0)
-      return fm_fail(h, CARS_E_INVALID, "query %lld has an id out of range", (long long)i);
   FM_TRY(h, cudaSetDevice(h->device));
+  // queries through the staged copier (pageable arrays), range check on the device before the kernel indexes with them
   int32_t *du = nullptr, *dj = nullptr, *dc = nullptr;
   double* dout = nullptr;
+  unsigned long long* d_bad = nullptr;
+  unsigned long long bad = ~0ull;
   cudaError_t e = fm_alloc(&du, (size_t)n);
   if (e == cudaSuccess) e = fm_alloc(&dj, (size_t)n);
   if (e == cudaSuccess) e = fm_alloc(&dc, (size_t)n);
   if (e == cudaSuccess) e = fm_alloc(&dout, (size_t)n);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(du, u, n * 4, cudaMemcpyHostToDevice, h->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dj, j, n * 4, cudaMemcpyHostToDevice, h->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dc, ctx, n * 4, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = fm_alloc(&d_bad, 1);
   if (e == cudaSuccess) {
+    cars::CopySeg segs[3] = {{du, (void*)u, (size_t)n * 4}, {dj, (void*)j, (size_t)n * 4}, {dc, (void*)ctx, (size_t)n * 4}};
+    e = h->copier.run(segs, 3, true);
+  }
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0xff, 8, h->stream);
+  if (e == cudaSuccess) {
+    fms_validate_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(du, dj, dc, n, (uint32_t)h->U, (uint32_t)h->I, d_bad);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess && bad == ~0ull) {
     fm_predict_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(du, dj, dc, h->d_w, h->d_V, h->d_w0, h->U, h->I, h->p,
                                                                          h->k, h->xc, n, bound, min_rate, max_rate, dout);
     e = cudaGetLastError();
-    h->launches++;
+    h->launches += 2;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = h->copier.d2h(out, dout, (size_t)n * 8);
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(du); cudaFree(dj); cudaFree(dc); cudaFree(dout);
-  h->h2d += n * 12; h->d2h += n * 8;
+  cudaFree(du); cudaFree(dj); cudaFree(dc); cudaFree(dout); cudaFree(d_bad);
   if (e != cudaSuccess) return fm_fail(h, CARS_E_CUDA, "predict failed: %s", cudaGetErrorString(e));
+  if (bad != ~0ull) return fm_fail(h, CARS_E_INVALID, "query %lld has an id out of range", (long long)bad);
+  h->h2d += n * 12; h->d2h += n * 8;
   return CARS_OK;
 }
 
