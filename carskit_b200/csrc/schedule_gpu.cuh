@@ -334,23 +334,17 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
   }
 
   // ---- the caller's arrays cross PCIe ------------------------------------------------------------------
-  // u and j first: chains and dependency levels need nothing else, so ctx and r (60 % of the bytes) cross while the
-  // device sorts and runs Kahn's algorithm (device-built levels only; the host pass copies everything up front)
   SG_TRY(cudaEventRecord(ev[0], stream));
-  const bool overlap = !host_levels;
-  const auto t_copy0 = std::chrono::steady_clock::now();
   {
     CopySeg segs[4] = {{d.u, (void*)u, N * 4}, {d.j, (void*)j, N * 4}, {d.ctx, (void*)ctx, ctx ? N * 4 : 0}, {d.r, (void*)r, N * 8}};
-    SG_TRY(copier.run(segs, overlap ? 2 : 4, true));
+    SG_TRY(copier.run(segs, 4, true));
   }
-  double copy_host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_copy0).count();
   info->h2d_bytes += nnz * (ctx ? 20 : 16);
-  lap(overlap ? "H2D of u, j" : "H2D of u, j, ctx, r");
+  lap("H2D of u, j, ctx, r");
   SG_TRY(cudaEventRecord(ev[1], stream));
   const int blocks = sm_count * 8;
   SG_TRY(cudaMemsetAsync(d_bad, 0xff, 8, stream));
-  // u and j are range-checked BEFORE the chain kernels index with them (ctx: after its copy, below)
-  validate_ids_kernel<<<blocks, 256, 0, stream>>>(d.u, d.j, overlap ? nullptr : d.ctx, nnz, (uint32_t)num_users, (uint32_t)num_items,
+  validate_ids_kernel<<<blocks, 256, 0, stream>>>(d.u, d.j, d.ctx, nnz, (uint32_t)num_users, (uint32_t)num_items,
                                                   (uint32_t)num_contexts, d_bad);
   SG_TRY(cudaGetLastError());
   unsigned long long bad = 0;
@@ -393,27 +387,8 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
     KahnCtl ctl;
     SG_TRY(cudaMemcpyAsync(&ctl, d_ctl, sizeof ctl, cudaMemcpyDeviceToHost, stream));
     SG_TRY(cudaEventRecord(ev[2], stream));
-    {  // everything above is queued, nothing waited for: ctx and r cross PCIe now, on the copier's streams
-      const auto t1 = std::chrono::steady_clock::now();
-      CopySeg segs[2] = {{d.ctx, (void*)ctx, ctx ? N * 4 : 0}, {d.r, (void*)r, N * 8}};
-      SG_TRY(copier.run(segs, 2, true));
-      copy_host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
-      lap("H2D of ctx, r (beside chains + levels)");
-    }
-    if (ctx) {
-      validate_ids_kernel<<<blocks, 256, 0, stream>>>(d.u, d.j, d.ctx, nnz, (uint32_t)num_users, (uint32_t)num_items,
-                                                      (uint32_t)num_contexts, d_bad);
-      SG_TRY(cudaGetLastError());
-      SG_TRY(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, stream));
-      info->kernel_launches += 1;
-    }
     SG_TRY(cudaStreamSynchronize(stream));
     lap("chains + Kahn levels + sync");
-    if (bad != ~0ull) {
-      info->bad_index = (int64_t)bad;
-      cleanup();
-      return cudaSuccess;
-    }
     if ((int64_t)ctl.processed != nnz) {  // cannot happen for chains built above; refuse rather than train garbage
       cleanup();
       return cudaErrorUnknown;
@@ -454,7 +429,7 @@ inline cudaError_t build_flagged_on_device(int32_t num_users, int32_t num_items,
   SG_TRY(cudaStreamSynchronize(stream));
   float ms = 0.f;
   lap("level sort + pack + sync");
-  info->copy_ms = copy_host_ms;  // host wall time of the staged copies (the second one overlaps the level pass)
+  if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) info->copy_ms = ms;
   if (cudaEventElapsedTime(&ms, ev[1], ev[2]) == cudaSuccess) info->levels_ms = ms;
   if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) info->pack_ms = ms;
   cleanup();
