@@ -275,7 +275,7 @@ def model_digest(arrs: dict) -> str:
     return h.hexdigest()
 
 
-def parity_check(wl, ts, model, arrs, local_rank, mode, epochs=2):
+def parity_check(wl, ts, model, arrs, local_rank, mode, epochs=2, tuning=None):
     """The parity gate at the bench's own size: `epochs` epochs of the SAME arrays on the GPU
     (through the C ABI) and on the CPU oracle.  EXACT: P, Q and every bias must be bit-identical (SHA-256 of the
     arrays) and the loss within 1e-11 relative.  FAST is not serial-equivalent: the loss difference is reported."""
@@ -286,7 +286,7 @@ def parity_check(wl, ts, model, arrs, local_rank, mode, epochs=2):
     regs = dict(reg_u=capi.f32(1e-4), reg_i=capi.f32(1e-4), reg_b=capi.f32(1e-4), reg_c=capi.f32(1e-3))
     lr = capi.f32(0.02)
     got = {k: v.copy() for k, v in arrs.items()}
-    desc = capi.make_desc(ts, model, F, device=local_rank, mode=capi.FAST if mode == "fast" else capi.EXACT, **regs)
+    desc = capi.make_desc(ts, model, F, device=local_rank, mode=capi.FAST if mode == "fast" else capi.EXACT, tuning=tuning, **regs)
     t0 = time.perf_counter()
     with capi.Engine(desc, keepalive=ts) as eng:
         eng.upload(got)
@@ -406,7 +406,7 @@ def run_b200(args, wl, wl_name, rank, world, local_rank):
     # ---------------- parity at the bench's own size (rank 0, N = 1) ------------------------------------------
     parity = None
     if world == 1 and not args.no_parity:
-        parity = parity_check(wl, ts, model, arrs, local_rank, mode)
+        parity = parity_check(wl, ts, model, arrs, local_rank, mode, tuning=args.tuning)
         log(f"[bench] parity: {json.dumps(parity)}")
         if not parity["ok"]:
             raise RuntimeError(f"parity check failed: {parity}")
