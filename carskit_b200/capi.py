@@ -13,12 +13,12 @@ from typing import Optional
 import numpy as np
 
 ABI_VERSION = 3
-PMF, BIASEDMF, CAMF_C, CAMF_CI, CAMF_CU, FM, CAMF_CUCI, CAMF_ICS = range(8)
+PMF, BIASEDMF, CAMF_C, CAMF_CI, CAMF_CU, FM, CAMF_CUCI, CAMF_ICS, CAMF_LCS, CAMF_MCS = range(10)
 EXACT, FAST = 0, 1
 SCHED_FLAGGED, SCHED_WAVEFRONT, SCHED_DATAFLOW = 0, 1, 2
 COMBINE_MEAN, COMBINE_SUM, COMBINE_TOUCHED = 0, 1, 2
 MODEL_NAMES = {"pmf": PMF, "biasedmf": BIASEDMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM,
-               "camf_cuci": CAMF_CUCI, "camf_ics": CAMF_ICS}
+               "camf_cuci": CAMF_CUCI, "camf_ics": CAMF_ICS, "camf_lcs": CAMF_LCS, "camf_mcs": CAMF_MCS}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # CARSKIT_B200_LIB selects another build of the same ABI (e.g. the developer build with stage tracing)
@@ -41,11 +41,13 @@ class CarsDesc(C.Structure):
         ("num_context_dims", C.c_int32), ("num_gpus", C.c_int32), ("global_nnz", C.c_int64),
         ("stream", C.c_void_p), ("gpu_ids", _i32p), ("fast_max_conc", C.c_double), ("tuning", C.c_char_p),
         ("combine", C.c_int32), ("num_empty_conditions", C.c_int32), ("empty_conditions", _i32p),
+        ("num_context_factors", C.c_int32),
     ]
 
 
 class CarsModelArrays(C.Structure):
-    _fields_ = [(n, _f64p) for n in ("P", "Q", "user_bias", "item_bias", "cond_bias", "ic_bias", "uc_bias", "cc_sim")]
+    _fields_ = [(n, _f64p) for n in ("P", "Q", "user_bias", "item_bias", "cond_bias", "ic_bias", "uc_bias", "cc_sim", "cf_lcs",
+                                     "c_mcs")]
 
 
 class CarsStats(C.Structure):
@@ -254,7 +256,7 @@ def make_desc(ts: TrainingSet, model: int, num_factors: int, *, mode: int = EXAC
               reg_u: float = 0.0, reg_i: float = 0.0, reg_b: float = 0.0, reg_c: float = 0.0,
               reg_lw: float = 0.0, reg_lf: float = 0.0, num_context_dims: int = 0,
               stream: int = 0, schedule: int = SCHED_FLAGGED, global_nnz: int = 0, fast_max_conc: float = 0.0,
-              tuning: Optional[str] = None, gpu_ids=None, combine: int = COMBINE_MEAN) -> CarsDesc:
+              tuning: Optional[str] = None, gpu_ids=None, combine: int = COMBINE_MEAN, num_context_factors: int = 10) -> CarsDesc:
     """Fill a cars_desc.  The reg_* values must already be float-widened (use f32()).
     `tuning`: developer knobs "key=value;..." (csrc/tuning.h); `gpu_ids`: N > 1 CUDA ordinals for ONE handle that
     drives N GPUs from this process (users sharded by range, item block combined with NCCL inside cars_epoch)."""
@@ -275,15 +277,18 @@ def make_desc(ts: TrainingSet, model: int, num_factors: int, *, mode: int = EXAC
     d.num_factors = num_factors
     d.nnz = ts.nnz
     d.u, d.j, d.r = _ptr_i32(ts.u), _ptr_i32(ts.j), _ptr_f64(ts.r)
-    use_ctx = model in (CAMF_C, CAMF_CI, CAMF_CU, CAMF_CUCI, FM, CAMF_ICS) and ts.ctx is not None
-    if model == CAMF_ICS:
+    use_ctx = model in (CAMF_C, CAMF_CI, CAMF_CU, CAMF_CUCI, FM, CAMF_ICS, CAMF_LCS, CAMF_MCS) and ts.ctx is not None
+    if model in (CAMF_ICS, CAMF_LCS, CAMF_MCS):
         ec = getattr(ts, "empty_conditions", None)
         if ec is None:
-            raise ValueError("CAMF_ICS needs TrainingSet.empty_conditions (rateDao.getEmptyContextConditions())")
+            raise ValueError("CAMF_ICS / LCS / MCS need TrainingSet.empty_conditions (rateDao.getEmptyContextConditions())")
         ec = np.ascontiguousarray(ec, dtype=np.int32)
         d._empty_keep = ec
         d.empty_conditions = _ptr_i32(ec)
         d.num_empty_conditions = len(ec)
+        d.num_context_factors = num_context_factors  # CAMF_LCS `-f`
+        if not num_context_dims:  # CAMF_MCS: upbound = 1 / sqrt(rateDao.numContextDims())
+            num_context_dims = int(getattr(ts, "num_context_dims", 0)) or len(ec)
     d.ctx = _ptr_i32(ts.ctx) if use_ctx else None
     d.ctx_ptr = _ptr_i32(ts.ctx_ptr) if use_ctx else None
     d.ctx_cond = _ptr_i32(ts.ctx_cond) if use_ctx else None
@@ -303,14 +308,17 @@ MODEL_MEMBERS = {
     CAMF_CU: ("P", "Q", "item_bias", "uc_bias"),
     CAMF_CUCI: ("P", "Q", "ic_bias", "uc_bias"),
     CAMF_ICS: ("P", "Q", "cc_sim"),
+    CAMF_LCS: ("P", "Q", "cf_lcs"),
+    CAMF_MCS: ("P", "Q", "c_mcs"),
 }
 
 
-def member_shapes(model: int, num_users: int, num_items: int, num_conditions: int, F: int):
+def member_shapes(model: int, num_users: int, num_items: int, num_conditions: int, F: int, num_context_factors: int = 10):
     all_shapes = {
         "P": (num_users, F), "Q": (num_items, F), "user_bias": (num_users,), "item_bias": (num_items,),
         "cond_bias": (num_conditions,), "ic_bias": (num_items, num_conditions),
         "uc_bias": (num_users, num_conditions), "cc_sim": (num_conditions, num_conditions),
+        "cf_lcs": (num_conditions, num_context_factors), "c_mcs": (num_conditions,),
     }
     return {k: all_shapes[k] for k in MODEL_MEMBERS[model]}
 

@@ -42,9 +42,14 @@ enum cars_model {
   CARS_CAMF_CUCI = 6, /* .../cars/adaptation/dependent/dev/CAMF_CUCI.java:78-134: ic_bias AND uc_bias, no user /
                         item bias; the reference's Guava tables icBias / ucBias are passed as dense
                         [num_items x C] / [num_users x C] arrays (every cell is initialised, :58-64) */
-  CARS_CAMF_ICS = 7  /* .../cars/adaptation/dependent/sim/CAMF_ICS.java:60-129: similarity-based,
+  CARS_CAMF_ICS = 7, /* .../cars/adaptation/dependent/sim/CAMF_ICS.java:60-129: similarity-based,
                         pred = P[u].Q[j] * prod_d sim(cond_d, empty_d) with ONE condition-similarity matrix shared by all
                         ratings (cc_sim; needs cars_desc.empty_conditions).  Like CAMF_C, EXACT runs on one warp. */
+  CARS_CAMF_LCS = 8, /* .../sim/CAMF_LCS.java:66-146: latent context similarity -- sim(cond, empty) = the dot product of
+                        two rows of cf_lcs [num_conditions x num_context_factors] (`-f`, CAMF_LCS.java:38) */
+  CARS_CAMF_MCS = 9  /* .../sim/CAMF_MCS.java:71-167: multidimensional context similarity -- every condition is a point
+                        c_mcs[cond] on its dimension's axis, sim = 1 - Euclidean distance between the context and the
+                        all-"na" context; positions clamped to (1e-100, 1/sqrt(num_context_dims)); loss *= 0.05 */
 };
 
 /* Update mode.
@@ -132,7 +137,8 @@ typedef struct cars_desc {
   int32_t num_empty_conditions; /* CAMF_ICS: length of empty_conditions (= number of context dimensions) */
   const int32_t* empty_conditions; /* CAMF_ICS: rateDao.getEmptyContextConditions() (DataDAO.java:214-215): the "dim:na"
                                condition of every dimension, in dimension order; the i-th condition of a context is
-                               compared with empty_conditions[i] (CAMF_ICS.java:56, 88) */
+                               compared with empty_conditions[i] (CAMF_ICS.java:56, 88).  CAMF_LCS / CAMF_MCS too */
+  int32_t num_context_factors; /* CAMF_LCS: numF, the `-f` option (CAMF_LCS.java:38; default 10) */
 } cars_desc;
 
 /* How the item block is combined between user-range shards once per epoch (DESIGN.md "Multi-GPU"):
@@ -152,6 +158,7 @@ typedef struct cars_handle cars_handle;
  *   ic_bias [num_items x num_conditions]              CAMF_CI.java:58
  *   uc_bias [num_users x num_conditions]              CAMF_CU.java:55
  *   cc_sim  [num_conditions x num_conditions]         CAMF_ICS.java:45-48
+ *   cf_lcs  [num_conditions x num_context_factors]    CAMF_LCS.java:38-40;   c_mcs [num_conditions]   CAMF_MCS.java:47-48
  *   (CAMF_CUCI: both ic_bias and uc_bias, CAMF_CUCI.java:42-43, 58-64) */
 typedef struct cars_model_arrays {
   double* P;
@@ -164,6 +171,8 @@ typedef struct cars_model_arrays {
   double* cc_sim; /* CAMF_ICS: ccMatrix_ICS as a dense [C x C] array (CAMF.java:44, CAMF_ICS.java:45-48).  librec's
                      SymmMatrix keeps ONE cell per unordered pair, (max(i,j), min(i,j)): upload reads that cell of the
                      caller's array, download writes the trained value to BOTH (i,j) and (j,i) */
+  double* cf_lcs; /* CAMF_LCS: cfMatrix_LCS [num_conditions x num_context_factors] (CAMF.java:46, CAMF_LCS.java:38-40) */
+  double* c_mcs;  /* CAMF_MCS: cVector_MCS [num_conditions] (CAMF.java:47, CAMF_MCS.java:47-48) */
 } cars_model_arrays;
 
 /* Replaces the set-up a Java buildModel() does implicitly by holding trainMatrix/rateDao: copies the

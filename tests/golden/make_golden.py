@@ -41,7 +41,9 @@ def init_arrays(oracle, model, ts, F, seed):
     for k, s in shapes.items():
         if k == "cc_sim":  # CAMF_ICS.java:45-48: every similarity starts at 1.0
             out[k] = np.ones(s)
-        elif model == capi.CAMF_ICS:  # CAMF_ICS.java:40-41 (isRankingPred): P.init(), Q.init() -> U(0, 1)
+        elif k == "c_mcs":  # CAMF_MCS.java:47-48: cVector_MCS.init(upbound) -> U(0, 1 / sqrt(numContextDims))
+            out[k] = g.uniform(s) / np.sqrt(len(ts.empty_conditions))
+        elif model in (capi.CAMF_ICS, capi.CAMF_LCS, capi.CAMF_MCS):  # isRankingPred: P.init(), Q.init(), cfMatrix_LCS.init() -> U(0, 1)
             out[k] = g.uniform(s)
         elif k in ("ic_bias", "uc_bias") and model != capi.CAMF_CUCI:
             out[k] = g.uniform(s)

@@ -45,7 +45,7 @@ def oracle_run(oracle, model, ts, arrs, F, iters, lrate=0.02, bold_driver=True, 
 LIVE = [
     ("pmf", None, "user_sorted", 5), ("biasedmf", None, "user_sorted", 6), ("camf_c", [3, 2, 2], "shuffled", 5),
     ("camf_ci", [3, 2, 2], "user_sorted", 9), ("camf_cu", [4, 3], "shuffled", 4), ("camf_cuci", [2, 2, 3], "user_sorted", 5),
-    ("camf_ics", [3, 3, 2], "shuffled", 6),
+    ("camf_ics", [3, 3, 2], "shuffled", 6), ("camf_lcs", [3, 3, 2], "shuffled", 6), ("camf_mcs", [3, 2, 3], "user_sorted", 5),
 ]
 
 
@@ -55,7 +55,7 @@ def test_oracle_reproduces_the_reference_bytecode_live(oracle, name, dims, order
     model = capi.MODEL_NAMES[name]
     ts, test = synth.make_training_set(25, 14, dims, 350, seed=F, order=order, holdout=0.1)
     arrs = init_arrays(oracle, model, ts, F, seed=F + 7)
-    lrate = 0.005 if name == "camf_ics" else 0.02  # CAMF_ICS starts from U(0, 1) factors: predictions of ~F/4
+    lrate = 0.005 if name in ("camf_ics", "camf_lcs", "camf_mcs") else 0.02  # the similarity models start from U(0, 1) factors: predictions of ~F/4
     ref = carskit_jvm.ReferenceRun(model, ts, arrs, F, lrate=lrate).build_model(3)
     got = {k: v.copy() for k, v in arrs.items()}
     losses, lrates = oracle_run(oracle, model, ts, got, F, 3, lrate=lrate)

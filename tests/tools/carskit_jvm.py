@@ -31,7 +31,9 @@ JARS = [os.path.join(REFERENCE, "jar", "CARSKit-v0.4.0.jar"), os.path.join(REFER
 DEV = "carskit/alg/cars/adaptation/dependent/dev/"
 CLASS_OF = {capi.PMF: "carskit/alg/baseline/cf/PMF", capi.BIASEDMF: "carskit/alg/baseline/cf/BiasedMF",
             capi.CAMF_C: DEV + "CAMF_C", capi.CAMF_CI: DEV + "CAMF_CI", capi.CAMF_CU: DEV + "CAMF_CU",
-            capi.CAMF_CUCI: DEV + "CAMF_CUCI", capi.CAMF_ICS: "carskit/alg/cars/adaptation/dependent/sim/CAMF_ICS"}
+            capi.CAMF_CUCI: DEV + "CAMF_CUCI", capi.CAMF_ICS: "carskit/alg/cars/adaptation/dependent/sim/CAMF_ICS",
+            capi.CAMF_LCS: "carskit/alg/cars/adaptation/dependent/sim/CAMF_LCS",
+            capi.CAMF_MCS: "carskit/alg/cars/adaptation/dependent/sim/CAMF_MCS"}
 REC = "carskit/generic/Recommender"
 ITER = "carskit/generic/IterativeRecommender"
 
@@ -170,6 +172,16 @@ class ReferenceRun:
             rec.f["ccMatrix_ICS"] = JObject("librec/data/SymmMatrix", dim=int(ts.num_conditions),
                                             data=HostTable(arrays["cc_sim"], lower_triangle=True))
             jvm.set_static("carskit/generic/ContextRecommender", "EmptyContextConditions", [int(x) for x in ts.empty_conditions])
+        if model == capi.CAMF_LCS:  # CAMF_LCS.java:36-41: numF = `-f`, cfMatrix_LCS [numConditions x numF]
+            rec.f["cfMatrix_LCS"] = dense_matrix(arrays["cf_lcs"])
+            rec.f["numF"] = int(arrays["cf_lcs"].shape[1])
+            jvm.set_static("carskit/generic/ContextRecommender", "EmptyContextConditions", [int(x) for x in ts.empty_conditions])
+        if model == capi.CAMF_MCS:  # CAMF_MCS.java:39-49: upbound = 1 / sqrt(numContextDims), lowbound = 1 / 10^100
+            import math
+            rec.f["cVector_MCS"] = dense_vector(arrays["c_mcs"])
+            rec.f["upbound"] = 1.0 / math.sqrt(len(ts.empty_conditions))
+            rec.f["lowbound"] = 1.0 / math.pow(10, 100)
+            jvm.set_static("carskit/generic/ContextRecommender", "EmptyContextConditions", [int(x) for x in ts.empty_conditions])
         if model == capi.CAMF_CUCI:
             rec.f["icBias"] = HostTable(arrays["ic_bias"])
             rec.f["ucBias"] = HostTable(arrays["uc_bias"])
@@ -226,6 +238,10 @@ class ReferenceRun:
             for (r, c), v in f["ccMatrix_ICS"].f["data"].d.items():
                 cc[r, c] = cc[c, r] = v
             out["cc_sim"] = cc
+        if "cf_lcs" in self.shapes:
+            out["cf_lcs"] = np.array(f["cfMatrix_LCS"].f["data"], dtype=np.float64).reshape(self.shapes["cf_lcs"])
+        if "c_mcs" in self.shapes:
+            out["c_mcs"] = np.array(f["cVector_MCS"].f["data"], dtype=np.float64)
         for key, field in (("ic_bias", "icBias"), ("uc_bias", "ucBias")):
             if key in self.shapes:
                 o = f[field]
