@@ -344,6 +344,17 @@ static const void* pick_serial_m(int Fp) {
   return nullptr;
 }
 static const void* pick_serial(int model, int Fp) {
+  if (model == CARS_CAMF_LCS || model == CARS_CAMF_MCS) {
+#define CARS_SIM_PICK(K)                                               \
+  if (Fp <= 64) return (const void*)sgd_serial_sim_kernel<1, K>;       \
+  if (Fp <= 128) return (const void*)sgd_serial_sim_kernel<2, K>;      \
+  if (Fp <= 256) return (const void*)sgd_serial_sim_kernel<4, K>;      \
+  if (Fp <= 512) return (const void*)sgd_serial_sim_kernel<8, K>;      \
+  return nullptr;
+    if (model == CARS_CAMF_LCS) { CARS_SIM_PICK(1) }
+    CARS_SIM_PICK(2)
+#undef CARS_SIM_PICK
+  }
   if (model == CARS_CAMF_ICS) {
     if (Fp <= 64) return (const void*)sgd_serial_ics_kernel<1>;
     if (Fp <= 128) return (const void*)sgd_serial_ics_kernel<2>;
@@ -363,7 +374,8 @@ static const void* pick_serial(int model, int Fp) {
 }
 
 static bool model_has_ctx(int model) {
-  return model == CARS_CAMF_C || model == CARS_CAMF_CI || model == CARS_CAMF_CU || model == CARS_CAMF_CUCI || model == CARS_CAMF_ICS;
+  return model == CARS_CAMF_C || model == CARS_CAMF_CI || model == CARS_CAMF_CU || model == CARS_CAMF_CUCI || model == CARS_CAMF_ICS ||
+         model == CARS_CAMF_LCS || model == CARS_CAMF_MCS;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -373,12 +385,16 @@ static int validate(const cars_desc* d) {
   if (!d) return fail(nullptr, CARS_E_INVALID, "desc is NULL");
   if (d->abi_version != CARS_ABI_VERSION)
     return fail(nullptr, CARS_E_INVALID, "abi_version %d != %d", d->abi_version, CARS_ABI_VERSION);
-  if (d->model < CARS_PMF || d->model > CARS_CAMF_ICS) return fail(nullptr, CARS_E_INVALID, "unknown model %d", d->model);
-  if (d->model == CARS_CAMF_ICS) {
+  if (d->model < CARS_PMF || d->model > CARS_CAMF_MCS) return fail(nullptr, CARS_E_INVALID, "unknown model %d", d->model);
+  if (d->model == CARS_CAMF_LCS && (d->num_context_factors <= 0 || d->num_context_factors > 4096))
+    return fail(nullptr, CARS_E_INVALID, "CAMF_LCS needs num_context_factors in 1..4096 (the `-f` option, CAMF_LCS.java:38)");
+  if (d->model == CARS_CAMF_MCS && d->num_context_dims <= 0)
+    return fail(nullptr, CARS_E_INVALID, "CAMF_MCS needs num_context_dims > 0 (rateDao.numContextDims(), CAMF_MCS.java:44)");
+  if (d->model == CARS_CAMF_ICS || d->model == CARS_CAMF_LCS || d->model == CARS_CAMF_MCS) {
     if (d->mode == CARS_FAST || d->num_gpus > 1)
-      return fail(nullptr, CARS_E_UNSUPPORTED, "CAMF_ICS is built for EXACT mode on one GPU (one chain through the similarity matrix)");
+      return fail(nullptr, CARS_E_UNSUPPORTED, "CAMF_ICS / LCS / MCS are built for EXACT mode on one GPU (one chain through the shared similarity cells)");
     if (!d->empty_conditions || d->num_empty_conditions <= 0)
-      return fail(nullptr, CARS_E_INVALID, "CAMF_ICS needs empty_conditions (rateDao.getEmptyContextConditions())");
+      return fail(nullptr, CARS_E_INVALID, "CAMF_ICS / LCS / MCS need empty_conditions (rateDao.getEmptyContextConditions())");
   }
   if (d->model == CARS_FM)
     return fail(nullptr, CARS_E_INVALID, "FM is an ALS model with its own entry points: use cars_fm_create");
@@ -498,7 +514,8 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   const int sched_req = desc->schedule;
   const bool fast = desc->mode == CARS_FAST;
   // the flagged and the FAST schedule validate the ids inside their own device pass over the ratings
-  const bool fused_check = fast || (sched_req == CARS_SCHED_FLAGGED && desc->model != CARS_CAMF_C && desc->model != CARS_CAMF_ICS);
+  const bool fused_check = fast || (sched_req == CARS_SCHED_FLAGGED && desc->model != CARS_CAMF_C && desc->model != CARS_CAMF_ICS &&
+                                   desc->model != CARS_CAMF_LCS && desc->model != CARS_CAMF_MCS);
   for (int64_t n = 0; n < nnz && !fused_check; n++) {
     if ((unsigned)desc->u[n] >= (unsigned)desc->num_users || (unsigned)desc->j[n] >= (unsigned)desc->num_items ||
         (has_ctx && (unsigned)desc->ctx[n] >= (unsigned)desc->num_contexts)) {
@@ -511,7 +528,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   // ---- launch geometry (the dataflow schedule sizes its chunks from the number of resident groups) ------
   const int model = desc->model;
   h->fast = fast;
-  h->serial = !fast && (model == CARS_CAMF_C || model == CARS_CAMF_ICS);
+  h->serial = !fast && (model == CARS_CAMF_C || model == CARS_CAMF_ICS || model == CARS_CAMF_LCS || model == CARS_CAMF_MCS);
   const int sched = sched_req;
   if (sched != CARS_SCHED_DATAFLOW && sched != CARS_SCHED_WAVEFRONT && sched != CARS_SCHED_FLAGGED) {
     fail(h, CARS_E_INVALID, "unknown schedule %d", sched);
@@ -535,7 +552,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
                       : h->dataflow ? pick_dataflow_plan(model, Fp)
                       : h->flagged ? pick_flagged_plan(model, Fp, F, shape) : pick_plan(model, Fp);
     if (h->flagged && h->tune.get_ll("tagged", kTaggedDefault) != 0 && !h->tune.is("levels", "host")) {
-      static const int kModelOf[] = {M_PMF, M_BIASEDMF, M_CAMF_C, M_CAMF_CI, M_CAMF_CU, -1, M_CAMF_CUCI, M_CAMF_ICS};
+      static const int kModelOf[] = {M_PMF, M_BIASEDMF, M_CAMF_C, M_CAMF_CI, M_CAMF_CU, -1, M_CAMF_CUCI, M_CAMF_ICS, M_CAMF_LCS, M_CAMF_MCS};
       h->tl = tagged_layout(kModelOf[model], F, has_ctx ? desc->num_conditions : 0);
       LaunchPlan tp = pick_tagged_plan(model, h->tl.p_lines(), h->tl.q_lines(), (int)h->tune.get_ll("tagged_ctas", 3));
       if (tp.fn) {
@@ -776,7 +793,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   if (model == CARS_CAMF_C) CUDA_TRY_H(dev_alloc(&m.cond_bias, C));
   if (model == CARS_CAMF_CI || model == CARS_CAMF_CUCI) CUDA_TRY_H(dev_alloc(&m.ic_bias, I * C));
   if (model == CARS_CAMF_CU || model == CARS_CAMF_CUCI) CUDA_TRY_H(dev_alloc(&m.uc_bias, U * C));
-  if (model == CARS_CAMF_ICS) {
+  if (model == CARS_CAMF_ICS || model == CARS_CAMF_LCS || model == CARS_CAMF_MCS) {
     if (desc->num_empty_conditions < Dmax) {
       fail(h, CARS_E_INVALID, "a context has %d conditions but only %d empty conditions were given", Dmax, desc->num_empty_conditions);
       return bail(CARS_E_INVALID);
@@ -786,7 +803,16 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
         fail(h, CARS_E_INVALID, "empty_conditions[%d] = %d is not a condition id", d, desc->empty_conditions[d]);
         return bail(CARS_E_INVALID);
       }
-    CUDA_TRY_H(dev_alloc(&m.cc_sim, C * C));
+    if (model == CARS_CAMF_ICS) CUDA_TRY_H(dev_alloc(&m.cc_sim, C * C));
+    if (model == CARS_CAMF_LCS) {
+      m.numF = desc->num_context_factors;
+      CUDA_TRY_H(dev_alloc(&m.cf_lcs, C * (size_t)m.numF));
+    }
+    if (model == CARS_CAMF_MCS) {
+      m.mcs_upbound = 1.0 / std::sqrt((double)desc->num_context_dims);  // CAMF_MCS.java:44-45
+      m.mcs_lowbound = 1.0 / 1e100;
+      CUDA_TRY_H(dev_alloc(&m.c_mcs, C));
+    }
     CUDA_TRY_H(dev_alloc(&h->d_empty_cond, (size_t)desc->num_empty_conditions));
     CUDA_TRY_H(cudaMemcpyAsync(h->d_empty_cond, desc->empty_conditions, (size_t)desc->num_empty_conditions * 4, cudaMemcpyHostToDevice, h->stream));
     m.empty_cond = h->d_empty_cond;
@@ -883,7 +909,8 @@ static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device, 
   struct Item { double* dev; double* host; const char* name; };
   const Item need[] = {{m.P, a->P, "P"}, {m.Q, a->Q, "Q"}, {m.user_bias, a->user_bias, "user_bias"},
                        {m.item_bias, a->item_bias, "item_bias"}, {m.cond_bias, a->cond_bias, "cond_bias"},
-                       {m.ic_bias, a->ic_bias, "ic_bias"}, {m.uc_bias, a->uc_bias, "uc_bias"}, {m.cc_sim, a->cc_sim, "cc_sim"}};
+                       {m.ic_bias, a->ic_bias, "ic_bias"}, {m.uc_bias, a->uc_bias, "uc_bias"}, {m.cc_sim, a->cc_sim, "cc_sim"},
+                       {m.cf_lcs, a->cf_lcs, "cf_lcs"}, {m.c_mcs, a->c_mcs, "c_mcs"}};
   for (const Item& it : need) {
     const bool item_side = it.dev == m.Q || it.dev == m.item_bias || it.dev == m.cond_bias || it.dev == m.ic_bias;
     if (it.dev && !it.host && !(skip_item_side && item_side))
@@ -901,6 +928,8 @@ static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device, 
   if (!skip_item_side && m.ic_bias && (rc = copy_vec(h, to_device, m.ic_bias, a->ic_bias, I * C, &segs))) return rc;
   if (m.uc_bias && (rc = copy_vec(h, to_device, m.uc_bias, a->uc_bias, U * C, &segs))) return rc;
   if (m.cc_sim && (rc = copy_vec(h, to_device, m.cc_sim, a->cc_sim, C * C, &segs))) return rc;
+  if (m.cf_lcs && (rc = copy_vec(h, to_device, m.cf_lcs, a->cf_lcs, C * (size_t)m.numF, &segs))) return rc;
+  if (m.c_mcs && (rc = copy_vec(h, to_device, m.c_mcs, a->c_mcs, C, &segs))) return rc;
   CUDA_TRY(h, h->copier.run(segs.data(), (int)segs.size(), to_device));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // the strided (odd F) row copies
   if (to_device) { h->std_valid = true; h->tagged_valid = false; }
@@ -1208,6 +1237,8 @@ static int predict_device(cars_handle* h, int64_t n, const int32_t* u, const int
     case CARS_CAMF_CU: CARS_PREDICT(M_CAMF_CU); break;
     case CARS_CAMF_CUCI: CARS_PREDICT(M_CAMF_CUCI); break;
     case CARS_CAMF_ICS: CARS_PREDICT(M_CAMF_ICS); break;
+    case CARS_CAMF_LCS: CARS_PREDICT(M_CAMF_LCS); break;
+    case CARS_CAMF_MCS: CARS_PREDICT(M_CAMF_MCS); break;
     default: return fail(h, CARS_E_UNSUPPORTED, "predict: model %d", h->d.model);
   }
 #undef CARS_PREDICT
@@ -1372,6 +1403,8 @@ extern "C" int cars_rank_topn(cars_handle* h, int64_t num_queries, const int32_t
       case CARS_CAMF_CU: RK(launch_rank_score<M_CAMF_CU>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
       case CARS_CAMF_CUCI: RK(launch_rank_score<M_CAMF_CUCI>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
       case CARS_CAMF_ICS: RK(launch_rank_score<M_CAMF_ICS>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
+      case CARS_CAMF_LCS: RK(launch_rank_score<M_CAMF_LCS>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
+      case CARS_CAMF_MCS: RK(launch_rank_score<M_CAMF_MCS>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
       default: rc = fail(h, CARS_E_UNSUPPORTED, "rank: model %d", h->d.model); break;
     }
     if (rc) break;
@@ -1433,7 +1466,7 @@ extern "C" void cars_destroy(cars_handle* h) {
   h->mem.free(h->d_item_old); h->mem.free(h->d_item_scale); h->mem.free(h->d_cond_scale);
   h->mem.free(h->d_hot_slot); h->mem.free(h->d_hot_items);
   h->mem.free(h->tm.Pt); h->mem.free(h->tm.Qt);
-  h->mem.free(h->m.cc_sim); h->mem.free(h->d_empty_cond);
+  h->mem.free(h->m.cc_sim); h->mem.free(h->m.cf_lcs); h->mem.free(h->m.c_mcs); h->mem.free(h->d_empty_cond);
   h->mem.free(h->d_barrier); h->mem.free(h->d_partial); h->mem.free(h->d_loss);
   if (h->stream) cudaStreamSynchronize(h->stream);  // the pool's frees are stream-ordered
   if (h->h_loss) cudaFreeHost(h->h_loss);

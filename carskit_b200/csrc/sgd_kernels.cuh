@@ -18,7 +18,7 @@
 
 namespace cars {
 
-enum : int { M_PMF = 0, M_BIASEDMF = 1, M_CAMF_C = 2, M_CAMF_CI = 3, M_CAMF_CU = 4, M_CAMF_CUCI = 5, M_CAMF_ICS = 6 };
+enum : int { M_PMF = 0, M_BIASEDMF = 1, M_CAMF_C = 2, M_CAMF_CI = 3, M_CAMF_CU = 4, M_CAMF_CUCI = 5, M_CAMF_ICS = 6, M_CAMF_LCS = 7, M_CAMF_MCS = 8 };
 
 // Device-resident state shared by all kernels.  Plain pointers into the handle's allocations.
 struct DeviceModel {
@@ -31,7 +31,11 @@ struct DeviceModel {
   double* uc_bias;    // [num_users x C]
   const int32_t* ctx_tab;  // [num_contexts x Dmax] condition ids, -1 padded
   double* cc_sim;             // CAMF_ICS: [C x C], the (max, min) cell of every unordered pair is the live one (SymmMatrix)
-  const int32_t* empty_cond;  // CAMF_ICS: [Dmax] the "na" condition of every dimension (EmptyContextConditions)
+  const int32_t* empty_cond;  // CAMF_ICS / LCS / MCS: [Dmax] the "na" condition of every dimension (EmptyContextConditions)
+  double* cf_lcs;             // CAMF_LCS: [C x numF] latent condition vectors (cfMatrix_LCS)
+  double* c_mcs;              // CAMF_MCS: [C] condition positions (cVector_MCS)
+  double mcs_upbound, mcs_lowbound;  // CAMF_MCS.java:44-45: 1 / sqrt(numContextDims), 1 / 10^100
+  int32_t numF;               // CAMF_LCS: `-f`
   int32_t F, Fp, C, Dmax;
   double global_mean;
   double reg_u, reg_i, reg_b, reg_c;
@@ -639,6 +643,136 @@ __global__ void __launch_bounds__(32, 1)
   if (lane == 0) block_partial[0] = acc;
 }
 
+// K1s-LCS / K1s-MCS: CAMF_LCS.buildModel (sim/CAMF_LCS.java:66-146) and CAMF_MCS.buildModel (sim/CAMF_MCS.java:71-167), one
+// warp in reference order -- like CAMF_ICS every rating reads and rewrites cells all ratings share (the condition vectors /
+// positions of the dimensions' "na" conditions), so EXACT mode is a single chain.  The similarity part is warp-uniform
+// (every lane computes the same values from the same cells); lane 0 owns the loss terms and the rewrites.
+//   LCS: sim_d = cf[cond_d] . cf[na_d] (f ascending);  pred = dot * prod sim_d;  cf rows += lr * (e*dot*simc*other/sim - regC*own)
+//   MCS: dist = sqrt(sum diff_d^2), diff_d = pos[cond_d] - pos[na_d];  pred = dot * (1 - dist);  positions moved along diff,
+//        clamped to (lowbound, upbound); a zero dist becomes lowbound in the update loop AND stays so for the factor steps
+template <int V, int KIND /*1 = LCS, 2 = MCS*/>
+__global__ void __launch_bounds__(32, 1)
+    sgd_serial_sim_kernel(DeviceModel m, RatingStream s, int64_t nnz, double lr, double* block_partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* prod = reinterpret_cast<double*>(smem_raw);
+  const int lane = threadIdx.x;
+  const int Fp = m.Fp, Dmax = m.Dmax, numF = m.numF;
+  double acc = 0.0;
+  for (int64_t n = 0; n < nnz; n++) {
+    const int u = __ldg(s.u + n), j = __ldg(s.j + n), ctx = __ldg(s.ctx + n);
+    const double r = __ldg(s.r + n);
+    double* prow = m.P + (int64_t)u * Fp;
+    double* qrow = m.Q + (int64_t)j * Fp;
+    double2 p[V], q[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const int c = lane + v * 32;
+      if (2 * c < Fp) {
+        p[v] = *reinterpret_cast<const double2*>(prow + 2 * c);
+        q[v] = *reinterpret_cast<const double2*>(qrow + 2 * c);
+        *reinterpret_cast<double2*>(prod + 2 * c) = make_double2(__dmul_rn(p[v].x, q[v].x), __dmul_rn(p[v].y, q[v].y));
+      }
+    }
+    __syncwarp();
+    double dot = 0.0;
+    for (int f = 0; f < m.F; f++) dot = __dadd_rn(dot, prod[f]);
+    __syncwarp();
+    double pred = dot, simc = 1.0, dist = 0.0, lane_loss = 0.0;
+    for (int d = 0; d < Dmax; d++) {  // warp-uniform
+      const int cond = __ldg(m.ctx_tab + (int64_t)ctx * Dmax + d);
+      if (cond < 0) continue;
+      const int e2 = __ldg(m.empty_cond + d);
+      if (KIND == 1) {
+        double sim = 1.0;
+        if (cond != e2) {
+          const double* c1 = m.cf_lcs + (int64_t)cond * numF;
+          const double* c2 = m.cf_lcs + (int64_t)e2 * numF;
+          sim = 0.0;
+          for (int f = 0; f < numF; f++) sim = __dadd_rn(sim, __dmul_rn(c1[f], c2[f]));
+          simc = __dmul_rn(simc, sim);
+        }
+        pred = __dmul_rn(pred, sim);
+      } else {
+        const double pos1 = m.c_mcs[cond], pos2 = m.c_mcs[e2];
+        const double diff = __dsub_rn(pos1, pos2);
+        dist = __dadd_rn(dist, __dmul_rn(diff, diff));
+        if (lane == 0)
+          lane_loss = __dadd_rn(lane_loss, __dadd_rn(__dmul_rn(__dmul_rn(m.reg_c, pos1), pos1), __dmul_rn(__dmul_rn(m.reg_c, pos2), pos2)));
+      }
+    }
+    if (KIND == 2) {
+      dist = __dsqrt_rn(dist);
+      pred = __dmul_rn(pred, __dsub_rn(1.0, dist));
+    }
+    const double e = __dsub_rn(r, pred);
+    if (lane == 0) lane_loss = __dadd_rn(lane_loss, __dmul_rn(e, e));
+    __syncwarp();  // every lane has read the shared cells before lane 0 rewrites them
+    if (lane == 0) {
+      for (int d = 0; d < Dmax; d++) {
+        const int cond = __ldg(m.ctx_tab + (int64_t)ctx * Dmax + d);
+        if (cond < 0) continue;
+        const int e2 = __ldg(m.empty_cond + d);
+        if (cond == e2) continue;
+        if (KIND == 1) {
+          double* c1 = m.cf_lcs + (int64_t)cond * numF;
+          double* c2 = m.cf_lcs + (int64_t)e2 * numF;
+          double sim = 0.0;  // the rows of one rating are distinct: still the value the prediction used
+          for (int f = 0; f < numF; f++) sim = __dadd_rn(sim, __dmul_rn(c1[f], c2[f]));
+          const double g = __dmul_rn(__dmul_rn(e, dot), simc);
+          for (int f = 0; f < numF; f++) {
+            const double c1f = c1[f], c2f = c2[f];
+            const double d1 = __dsub_rn(__ddiv_rn(__dmul_rn(g, c2f), sim), __dmul_rn(m.reg_c, c1f));
+            const double d2 = __dsub_rn(__ddiv_rn(__dmul_rn(g, c1f), sim), __dmul_rn(m.reg_c, c2f));
+            c1[f] = __dadd_rn(c1f, __dmul_rn(lr, d1));
+            c2[f] = __dadd_rn(c2f, __dmul_rn(lr, d2));
+            lane_loss = __dadd_rn(lane_loss, __dadd_rn(__dmul_rn(__dmul_rn(m.reg_c, c1f), c1f), __dmul_rn(__dmul_rn(m.reg_c, c2f), c2f)));
+          }
+        } else {
+          const double pos1 = m.c_mcs[cond], pos2 = m.c_mcs[e2];
+          const double diff = __dsub_rn(pos1, pos2);  // the cells of one rating are distinct: the first loop's value
+          if (dist == 0.0) dist = m.mcs_lowbound;
+          const double t = __ddiv_rn(__dmul_rn(__dmul_rn(e, dot), diff), dist);
+          double n1 = __dadd_rn(pos1, __dmul_rn(lr, __dsub_rn(t, __dmul_rn(m.reg_c, pos1))));
+          double n2 = __dsub_rn(pos2, __dmul_rn(lr, __dadd_rn(t, __dmul_rn(m.reg_c, pos2))));
+          n1 = n1 < 0.0 ? m.mcs_lowbound : n1;
+          n1 = n1 > m.mcs_upbound ? __dsub_rn(m.mcs_upbound, m.mcs_lowbound) : n1;
+          n2 = n2 < 0.0 ? m.mcs_lowbound : n2;
+          n2 = n2 > m.mcs_upbound ? __dsub_rn(m.mcs_upbound, m.mcs_lowbound) : n2;
+          m.c_mcs[cond] = n1;
+          m.c_mcs[e2] = n2;
+        }
+      }
+    }
+    if (KIND == 2) {  // lane 0 may have replaced a zero distance
+      dist = __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(dist), 0), __shfl_sync(0xffffffffu, __double2loint(dist), 0));
+      simc = __dsub_rn(1.0, dist);
+    }
+    double sp = 0.0, sq = 0.0;
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const int c = lane + v * 32;
+      if (2 * c < Fp) {
+        const double2 po = p[v], qo = q[v];
+        double2 pn, qn;
+        pn.x = __dadd_rn(po.x, __dmul_rn(lr, __dsub_rn(__dmul_rn(__dmul_rn(e, qo.x), simc), __dmul_rn(m.reg_u, po.x))));
+        qn.x = __dadd_rn(qo.x, __dmul_rn(lr, __dsub_rn(__dmul_rn(__dmul_rn(e, po.x), simc), __dmul_rn(m.reg_i, qo.x))));
+        pn.y = __dadd_rn(po.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(__dmul_rn(e, qo.y), simc), __dmul_rn(m.reg_u, po.y))));
+        qn.y = __dadd_rn(qo.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(__dmul_rn(e, po.y), simc), __dmul_rn(m.reg_i, qo.y))));
+        *reinterpret_cast<double2*>(prow + 2 * c) = pn;
+        *reinterpret_cast<double2*>(qrow + 2 * c) = qn;
+        sp = fma(po.x, po.x, sp); sq = fma(qo.x, qo.x, sq);
+        sp = fma(po.y, po.y, sp); sq = fma(qo.y, qo.y, sq);
+      }
+    }
+    acc = __dadd_rn(acc, __dadd_rn(lane_loss, fma(m.reg_u, sp, __dmul_rn(m.reg_i, sq))));
+    __syncwarp();
+    __threadfence_block();
+  }
+  acc = warp_sum_f64(acc);
+  // CAMF_MCS.java:158: loss *= 0.05 (the host-side finalisation halves): a report value, 1e-11 relative
+  if (lane == 0) block_partial[0] = KIND == 2 ? acc * 0.1 : acc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1d: dataflow SGD (the default schedule).  Ratings stay in the reference's iteration order and are
 // cut into chunks of consecutive ratings; groups take chunks IN ORDER from a global counter and walk
@@ -935,6 +1069,28 @@ __device__ __forceinline__ double predict_from_dot(const DeviceModel& m, int u, 
   if (MODEL == M_CAMF_CI) pred = __dadd_rn(__dadd_rn(m.global_mean, m.user_bias[u]), dot);
   if (MODEL == M_CAMF_CU) pred = __dadd_rn(__dadd_rn(m.global_mean, m.item_bias[j]), dot);
   if (MODEL == M_CAMF_CUCI) pred = __dadd_rn(m.global_mean, dot);  // CAMF_CUCI.java:69
+  if (MODEL == M_CAMF_LCS) {  // CAMF_LCS.java:44-62: pred = pred * rowMult(cfMatrix_LCS, cond, cfMatrix_LCS, empty)
+    pred = dot;
+    for (int d = 0; d < m.Dmax; d++) {
+      const int cond = m.ctx_tab[(int64_t)ctx * m.Dmax + d];
+      if (cond < 0) continue;
+      const double* c1 = m.cf_lcs + (int64_t)cond * m.numF;
+      const double* c2 = m.cf_lcs + (int64_t)m.empty_cond[d] * m.numF;
+      double sim = 0.0;
+      for (int f = 0; f < m.numF; f++) sim = __dadd_rn(sim, __dmul_rn(c1[f], c2[f]));
+      pred = __dmul_rn(pred, sim);
+    }
+  }
+  if (MODEL == M_CAMF_MCS) {  // CAMF_MCS.java:52-69: pred = pred * (1 - sqrt(sum_d (pos(cond_d) - pos(empty_d))^2))
+    double dist = 0.0;
+    for (int d = 0; d < m.Dmax; d++) {
+      const int cond = m.ctx_tab[(int64_t)ctx * m.Dmax + d];
+      if (cond < 0) continue;
+      const double diff = __dsub_rn(m.c_mcs[cond], m.c_mcs[m.empty_cond[d]]);
+      dist = __dadd_rn(dist, __dmul_rn(diff, diff));
+    }
+    pred = __dmul_rn(dot, __dsub_rn(1.0, __dsqrt_rn(dist)));
+  }
   if (MODEL == M_CAMF_ICS) {  // CAMF_ICS.java:52-58: pred = pred * ccMatrix_ICS.get(conditions.get(i), EmptyContextConditions.get(i))
     pred = dot;
     for (int d = 0; d < m.Dmax; d++) {

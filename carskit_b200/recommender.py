@@ -186,7 +186,8 @@ class IterativeRecommender:
         produced elsewhere (what a JNI subclass receives from Java).  Otherwise P, Q and the bias
         vectors are drawn N(initMean, initStd) and icBias/ucBias U(0,1) (CAMF_CI.java:55-60); the
         reference's own generator is wall-clock seeded, so any generator is faithful."""
-        shapes = capi.member_shapes(self.MODEL, self.numUsers, self.numItems, self.numConditions, self.numFactors)
+        shapes = capi.member_shapes(self.MODEL, self.numUsers, self.numItems, self.numConditions, self.numFactors,
+                                    getattr(self, "numContextFactors", 10))
         if init is not None:
             for k, s in shapes.items():
                 a = np.ascontiguousarray(init[k], dtype=np.float64)
@@ -243,6 +244,7 @@ class IterativeRecommender:
                               reg_u=self.regU, reg_i=self.regI, reg_b=self.regB, reg_c=self.regC,
                               stream=self.stream, mode=capi.FAST if self.mode == "fast" else capi.EXACT,
                               fast_max_conc=self.fastMaxConc, tuning=self.tuning, gpu_ids=self.gpu_ids,
+                              num_context_factors=getattr(self, "numContextFactors", 10),
                               combine={"mean": capi.COMBINE_MEAN, "sum": capi.COMBINE_SUM, "touched": capi.COMBINE_TOUCHED}[self.combine])
 
     def open_engine(self) -> capi.Engine:
@@ -490,6 +492,38 @@ class CAMF_ICS(IterativeRecommender):
                       "cc_sim": np.ones((C, C))}
 
 
+class CAMF_LCS(IterativeRecommender):
+    """carskit.alg.cars.adaptation.dependent.sim.CAMF_LCS (CAMF_LCS.java): latent context similarity -- every condition has a
+    vector of `-f` factors (default 10, :38), sim(condition, "na") = their dot product.  P, Q and the vectors ~ U(0, 1)."""
+    MODEL, algoName = capi.CAMF_LCS, "CAMF_LCS"
+
+    def __init__(self, trainMatrix, testMatrix=None, fold=-1, conf=None, device=0, stream=0, **kw):
+        super().__init__(trainMatrix, testMatrix, fold, conf, device, stream, **kw)
+        self.numContextFactors = int(LineConfiger(self.cf.get("CAMF_LCS", "-f 10")).getFloat("-f", 10))  # algoOptions.getInt("-f", 10)
+
+    def initModel(self, init=None, seed: int = 0):
+        if init is not None:
+            return super().initModel(init, seed)
+        rng = np.random.default_rng(seed)
+        self.model = {"P": rng.random((self.numUsers, self.numFactors)), "Q": rng.random((self.numItems, self.numFactors)),
+                      "cf_lcs": rng.random((self.numConditions, self.numContextFactors))}
+
+
+class CAMF_MCS(IterativeRecommender):
+    """carskit.alg.cars.adaptation.dependent.sim.CAMF_MCS (CAMF_MCS.java): multidimensional context similarity -- every
+    condition is a position on its dimension's axis, sim = 1 - distance(context, all-"na" context); positions start in
+    U(0, 1 / sqrt(numContextDims)) (:44-48) and are clamped there; the reference scales this model's loss by 0.05 (:158)."""
+    MODEL, algoName = capi.CAMF_MCS, "CAMF_MCS"
+
+    def initModel(self, init=None, seed: int = 0):
+        if init is not None:
+            return super().initModel(init, seed)
+        rng = np.random.default_rng(seed)
+        dims = max(1, len(self.trainMatrix.empty_conditions))
+        self.model = {"P": rng.random((self.numUsers, self.numFactors)), "Q": rng.random((self.numItems, self.numFactors)),
+                      "c_mcs": rng.random(self.numConditions) / np.sqrt(dims)}
+
+
 class FM(IterativeRecommender):
     """carskit.alg.cars.adaptation.dependent.FM (FM.java): ALS factorization machine over the one-hot features
     (user, item, context).  `FM=-lw <f> -lf <f>` in the configuration (FM.java:53-54); learn.rate and
@@ -644,7 +678,7 @@ def runCrossValidation(rateMatrix: TrainingSet, name: str, conf: Optional[Dict[s
 def getRecommender(name: str):
     """The `switch` of CARSKit.getRecommender (src/carskit/main/CARSKit.java:429-705) for this path."""
     table = {"pmf": PMF, "biasedmf": BiasedMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM,
-             "camf_cuci": CAMF_CUCI, "camf_ics": CAMF_ICS}
+             "camf_cuci": CAMF_CUCI, "camf_ics": CAMF_ICS, "camf_lcs": CAMF_LCS, "camf_mcs": CAMF_MCS}
     try:
         return table[name.lower()]
     except KeyError:

@@ -134,10 +134,20 @@ public final class B200 {
                              int[] gpuIds, int numIters, EpochControl ctl, double[] P, double[] Q, double[] userBias,
                              double[] itemBias, double[] condBias, double[] icBias, double[] ucBias, double[] ccSim,
                              int[] emptyConditions) throws Exception {
+        train(model, mode, numUsers, numItems, numConditions, numFactors, x, ctxTable, globalMean, regU, regI, regB, regC, gpuIds,
+                numIters, ctl, P, Q, userBias, itemBias, condBias, icBias, ucBias, ccSim, emptyConditions, 0);
+    }
+
+    /** As above; `ccSim` is the similarity model's own array, numContextFactors CAMF_LCS's `-f`. */
+    public static void train(int model, int mode, int numUsers, int numItems, int numConditions, int numFactors, Ratings x,
+                             int[][] ctxTable, double globalMean, double regU, double regI, double regB, double regC,
+                             int[] gpuIds, int numIters, EpochControl ctl, double[] P, double[] Q, double[] userBias,
+                             double[] itemBias, double[] condBias, double[] icBias, double[] ucBias, double[] ccSim,
+                             int[] emptyConditions, int numContextFactors) throws Exception {
         int numContexts = ctxTable == null ? 0 : ctxTable[0].length - 1;
         long h = Native.create(model, mode, numUsers, numItems, numConditions, numContexts, numFactors, x.u, x.j, x.ctx, x.r,
                 ctxTable == null ? null : ctxTable[0], ctxTable == null ? null : ctxTable[1], globalMean, regU, regI, regB,
-                regC, gpuIds, Native.COMBINE_MEAN, 0.0, emptyConditions);
+                regC, gpuIds, Native.COMBINE_MEAN, 0.0, emptyConditions, numContextFactors);
         try {
             Native.upload(h, P, Q, userBias, itemBias, condBias, icBias, ucBias, ccSim);
             for (int iter = 1; iter <= numIters; iter++) {

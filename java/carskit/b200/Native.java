@@ -15,7 +15,7 @@ public final class Native {
     }
 
     // enum cars_model
-    public static final int PMF = 0, BIASEDMF = 1, CAMF_C = 2, CAMF_CI = 3, CAMF_CU = 4, FM = 5, CAMF_CUCI = 6, CAMF_ICS = 7;
+    public static final int PMF = 0, BIASEDMF = 1, CAMF_C = 2, CAMF_CI = 3, CAMF_CU = 4, FM = 5, CAMF_CUCI = 6, CAMF_ICS = 7, CAMF_LCS = 8, CAMF_MCS = 9;
     // enum cars_mode: EXACT is serial-equivalent (P, Q, biases bit-identical to the Java loop); FAST is hogwild
     public static final int EXACT = 0, FAST = 1;
     // enum cars_combine (multi-GPU item-block combine)
@@ -33,15 +33,20 @@ public final class Native {
      * getConditions(ctx) yields (ContextRecommender.java:53-61). The reg* values are the static FLOAT fields widened
      * with a (double) cast by the caller (IterativeRecommender.java:40). gpuIds: null or one id = single GPU; more
      * than one = ONE handle drives all of them (users sharded by range, item block all-reduced inside epoch()).
-     * emptyConditions: rateDao.getEmptyContextConditions() for CAMF_ICS, null otherwise.
+     * emptyConditions: rateDao.getEmptyContextConditions() for CAMF_ICS / LCS / MCS, null otherwise (its length is also
+     * CAMF_MCS's numContextDims). numContextFactors: CAMF_LCS's `-f` (CAMF_LCS.java:38), 0 otherwise.
      * The arrays are copied to the device during the call; nothing stays pinned. Returns the handle.
      */
     public static native long create(int model, int mode, int numUsers, int numItems, int numConditions, int numContexts,
                                      int numFactors, int[] u, int[] j, int[] ctx, double[] r, int[] ctxPtr, int[] ctxCond,
                                      double globalMean, double regU, double regI, double regB, double regC,
-                                     int[] gpuIds, int combine, double fastMaxConc, int[] emptyConditions);
+                                     int[] gpuIds, int combine, double fastMaxConc, int[] emptyConditions,
+                                     int numContextFactors);
 
-    /** cars_upload: flat row-major arrays as initModel() made them; null where the model has no such member. */
+    /**
+     * cars_upload: flat row-major arrays as initModel() made them; null where the model has no such member. `ccSim` is the
+     * similarity model's own array: ccMatrix_ICS [C x C], cfMatrix_LCS [C x numF] or cVector_MCS [C].
+     */
     public static native void upload(long h, double[] P, double[] Q, double[] userBias, double[] itemBias,
                                      double[] condBias, double[] icBias, double[] ucBias, double[] ccSim);
 

@@ -54,7 +54,8 @@ JNIEXPORT jlong JNICALL Java_carskit_b200_Native_create(JNIEnv* env, jclass cls,
                                                         jintArray u, jintArray j, jintArray ctx, jdoubleArray r,
                                                         jintArray ctxPtr, jintArray ctxCond, jdouble globalMean, jdouble regU,
                                                         jdouble regI, jdouble regB, jdouble regC, jintArray gpuIds,
-                                                        jint combine, jdouble fastMaxConc, jintArray emptyConditions) {
+                                                        jint combine, jdouble fastMaxConc, jintArray emptyConditions,
+                                                        jint numContextFactors) {
   (void)cls;
   cars_desc d;
   memset(&d, 0, sizeof d);
@@ -79,6 +80,8 @@ JNIEXPORT jlong JNICALL Java_carskit_b200_Native_create(JNIEnv* env, jclass cls,
         pg = pin(env, gpuIds), pe = pin(env, emptyConditions);
   d.empty_conditions = (const int32_t*)pe.p;
   d.num_empty_conditions = nempty;
+  d.num_context_factors = numContextFactors; /* CAMF_LCS */
+  d.num_context_dims = nempty;               /* CAMF_MCS: one "na" condition per context dimension */
   d.u = (const int32_t*)pu.p; d.j = (const int32_t*)pj.p; d.ctx = (const int32_t*)pc.p; d.r = (const double*)pr.p;
   d.ctx_ptr = (const int32_t*)pp.p; d.ctx_cond = (const int32_t*)pq.p;
   if (ngpu > 1) {
@@ -107,7 +110,9 @@ static void transfer(JNIEnv* env, jlong handle, int to_device, jdoubleArray P, j
                 pin(env, ucBias), pin(env, ccSim)};
   cars_model_arrays a;
   a.P = (double*)p[0].p; a.Q = (double*)p[1].p; a.user_bias = (double*)p[2].p; a.item_bias = (double*)p[3].p;
-  a.cond_bias = (double*)p[4].p; a.ic_bias = (double*)p[5].p; a.uc_bias = (double*)p[6].p; a.cc_sim = (double*)p[7].p;
+  a.cond_bias = (double*)p[4].p; a.ic_bias = (double*)p[5].p; a.uc_bias = (double*)p[6].p;
+  /* the similarity model's own array: the engine reads the member its model has (ccMatrix_ICS / cfMatrix_LCS / cVector_MCS) */
+  a.cc_sim = a.cf_lcs = a.c_mcs = (double*)p[7].p;
   const int rc = to_device ? cars_upload(h, &a) : cars_download(h, &a);
   for (int k = 7; k >= 0; k--) unpin(env, p[k], to_device ? JNI_ABORT : 0);  /* download: copy back / commit */
   if (rc != CARS_OK) throw_runtime(env, cars_last_error(h));

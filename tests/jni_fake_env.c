@@ -84,7 +84,7 @@ jint Java_carskit_b200_Native_deviceCount(JNIEnv*, jclass);
 jstring Java_carskit_b200_Native_version(JNIEnv*, jclass);
 jlong Java_carskit_b200_Native_create(JNIEnv*, jclass, jint, jint, jint, jint, jint, jint, jint, jintArray, jintArray, jintArray,
                                       jdoubleArray, jintArray, jintArray, jdouble, jdouble, jdouble, jdouble, jdouble, jintArray,
-                                      jint, jdouble, jintArray);
+                                      jint, jdouble, jintArray, jint);
 void Java_carskit_b200_Native_upload(JNIEnv*, jclass, jlong, jdoubleArray, jdoubleArray, jdoubleArray, jdoubleArray, jdoubleArray,
                                      jdoubleArray, jdoubleArray, jdoubleArray);
 void Java_carskit_b200_Native_download(JNIEnv*, jclass, jlong, jdoubleArray, jdoubleArray, jdoubleArray, jdoubleArray,
@@ -111,7 +111,7 @@ int main(void) {
 
   printf("deviceCount = %d\n", (int)Java_carskit_b200_Native_deviceCount(env, NULL));
   jlong h = Java_carskit_b200_Native_create(env, NULL, 3 /* Native.CAMF_CI */, 0, U, I, C, 2, F, &au, &aj, &ac, &ar, &ap, &aq, 23.0 / 6.0,
-                                            (double)1e-4f, (double)1e-4f, (double)1e-4f, (double)1e-3f, NULL, 0, 0.0, NULL);
+                                            (double)1e-4f, (double)1e-4f, (double)1e-4f, (double)1e-3f, NULL, 0, 0.0, NULL, 0);
   if (g_pending) {
     printf("RuntimeException: %s\n", g_exception);
     return (g_open_critical == 0 && g_jni_call_inside_critical == 0 && h == 0) ? 3 : 2;

@@ -476,3 +476,38 @@ def test_camf_ics_bit_identical(oracle, cars_lib, F, order):
     assert np.array_equal(pred, oracle.predict(desc, ref, test["u"], test["j"], test["ctx"]))
     with pytest.raises(capi.CarsError):
         capi.Engine(capi.make_desc(ts, capi.CAMF_ICS, F, mode=capi.FAST, **REGS), keepalive=ts)
+
+
+@pytest.mark.parametrize("name,F,order,numF", [("camf_lcs", 10, "user_sorted", 10), ("camf_lcs", 64, "shuffled", 7), ("camf_lcs", 100, "user_sorted", 3),
+                                               ("camf_mcs", 10, "shuffled", 0), ("camf_mcs", 64, "user_sorted", 0), ("camf_mcs", 130, "shuffled", 0)])
+def test_camf_lcs_mcs_bit_identical(oracle, cars_lib, name, F, order, numF):
+    """CAMF_LCS / CAMF_MCS (sim/CAMF_LCS.java, sim/CAMF_MCS.java) on the one-warp serial kernel: P, Q and the condition vectors /
+    positions bit-identical to the oracle (itself bit-identical to the executed bytecode), bounded and unbounded predictions too."""
+    model = capi.MODEL_NAMES[name]
+    ts, test = synth.make_training_set(90, 120, [4, 3, 2, 5], 3000, seed=F, order=order, holdout=0.1)
+    kw = dict(num_context_factors=numF) if numF else {}
+    desc = capi.make_desc(ts, model, F, **REGS, **kw)
+    shapes = capi.member_shapes(model, ts.num_users, ts.num_items, ts.num_conditions, F, numF or 10)
+    g = oracle.JavaRandom(F + 3)
+    ref = {k: g.uniform(shp) for k, shp in shapes.items()}
+    for k in ("P", "Q"):
+        ref[k] *= 2.0 / np.sqrt(F)  # keep P[u].Q[j] in the rating range for any F
+    if "cf_lcs" in ref:
+        ref["cf_lcs"] *= 2.0 / np.sqrt(numF)  # similarities of ~1
+    if "c_mcs" in ref:
+        ref["c_mcs"] /= np.sqrt(4)  # CAMF_MCS.java:44-48: U(0, upbound)
+    got = {k: v.copy() for k, v in ref.items()}
+    lr = capi.f32(0.002)
+    with capi.Engine(desc, keepalive=ts) as eng:
+        eng.upload(got)
+        for _ in range(3):
+            lg, lo = eng.epoch(lr), oracle.epoch(desc, ref, lr)
+            np.testing.assert_allclose(lg, lo, rtol=LOSS_RTOL)
+        pred = eng.predict(test["u"], test["j"], test["ctx"], bound=False)
+        predb = eng.predict(test["u"], test["j"], test["ctx"], bound=True, min_rate=1.0, max_rate=5.0)
+        eng.download(got)
+    assert_bit_identical(ref, got)
+    assert np.array_equal(pred, oracle.predict(desc, ref, test["u"], test["j"], test["ctx"]))
+    assert np.array_equal(predb, oracle.predict(desc, ref, test["u"], test["j"], test["ctx"], bound=True, min_rate=1.0, max_rate=5.0))
+    with pytest.raises(capi.CarsError):
+        capi.Engine(capi.make_desc(ts, model, F, mode=capi.FAST, **REGS, **kw), keepalive=ts)
