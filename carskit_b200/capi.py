@@ -13,12 +13,12 @@ from typing import Optional
 import numpy as np
 
 ABI_VERSION = 3
-PMF, BIASEDMF, CAMF_C, CAMF_CI, CAMF_CU, FM, CAMF_CUCI, CAMF_ICS, CAMF_LCS, CAMF_MCS = range(10)
+PMF, BIASEDMF, CAMF_C, CAMF_CI, CAMF_CU, FM, CAMF_CUCI, CAMF_ICS, CAMF_LCS, CAMF_MCS, SVDPP = range(11)
 EXACT, FAST = 0, 1
 SCHED_FLAGGED, SCHED_WAVEFRONT, SCHED_DATAFLOW = 0, 1, 2
 COMBINE_MEAN, COMBINE_SUM, COMBINE_TOUCHED = 0, 1, 2
 MODEL_NAMES = {"pmf": PMF, "biasedmf": BIASEDMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM,
-               "camf_cuci": CAMF_CUCI, "camf_ics": CAMF_ICS, "camf_lcs": CAMF_LCS, "camf_mcs": CAMF_MCS}
+               "camf_cuci": CAMF_CUCI, "camf_ics": CAMF_ICS, "camf_lcs": CAMF_LCS, "camf_mcs": CAMF_MCS, "svdpp": SVDPP}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # CARSKIT_B200_LIB selects another build of the same ABI (e.g. the developer build with stage tracing)
@@ -47,7 +47,7 @@ class CarsDesc(C.Structure):
 
 class CarsModelArrays(C.Structure):
     _fields_ = [(n, _f64p) for n in ("P", "Q", "user_bias", "item_bias", "cond_bias", "ic_bias", "uc_bias", "cc_sim", "cf_lcs",
-                                     "c_mcs")]
+                                     "c_mcs", "Y")]
 
 
 class CarsStats(C.Structure):
@@ -310,6 +310,7 @@ MODEL_MEMBERS = {
     CAMF_ICS: ("P", "Q", "cc_sim"),
     CAMF_LCS: ("P", "Q", "cf_lcs"),
     CAMF_MCS: ("P", "Q", "c_mcs"),
+    SVDPP: ("P", "Q", "user_bias", "item_bias", "Y"),
 }
 
 
@@ -318,7 +319,7 @@ def member_shapes(model: int, num_users: int, num_items: int, num_conditions: in
         "P": (num_users, F), "Q": (num_items, F), "user_bias": (num_users,), "item_bias": (num_items,),
         "cond_bias": (num_conditions,), "ic_bias": (num_items, num_conditions),
         "uc_bias": (num_users, num_conditions), "cc_sim": (num_conditions, num_conditions),
-        "cf_lcs": (num_conditions, num_context_factors), "c_mcs": (num_conditions,),
+        "cf_lcs": (num_conditions, num_context_factors), "c_mcs": (num_conditions,), "Y": (num_items, F),
     }
     return {k: all_shapes[k] for k in MODEL_MEMBERS[model]}
 

@@ -47,9 +47,14 @@ enum cars_model {
                         ratings (cc_sim; needs cars_desc.empty_conditions).  Like CAMF_C, EXACT runs on one warp. */
   CARS_CAMF_LCS = 8, /* .../sim/CAMF_LCS.java:66-146: latent context similarity -- sim(cond, empty) = the dot product of
                         two rows of cf_lcs [num_conditions x num_context_factors] (`-f`, CAMF_LCS.java:38) */
-  CARS_CAMF_MCS = 9  /* .../sim/CAMF_MCS.java:71-167: multidimensional context similarity -- every condition is a point
+  CARS_CAMF_MCS = 9, /* .../sim/CAMF_MCS.java:71-167: multidimensional context similarity -- every condition is a point
                         c_mcs[cond] on its dimension's axis, sim = 1 - Euclidean distance between the context and the
                         all-"na" context; positions clamped to (1e-100, 1/sqrt(num_context_dims)); loss *= 0.05 */
+  CARS_SVDPP = 10    /* src/carskit/alg/baseline/cf/SVDPlusPlus.java:55-147: BiasedMF plus the implicit-
+                        feedback factors Y [num_items x F] of every item the user rated (2-D `train`, ctx = NULL).  Every
+                        rating of user u rewrites Y[k] for ALL items k the user rated: measured DAG width 1.08-1.10
+                        (profiles/r2/svdpp_dag_width.txt), so EXACT runs on one warp; userItemsCache = the user's items in
+                        ascending order (train.getColumns(u)), derived from u / j by cars_create */
 };
 
 /* Update mode.
@@ -173,6 +178,7 @@ typedef struct cars_model_arrays {
                      caller's array, download writes the trained value to BOTH (i,j) and (j,i) */
   double* cf_lcs; /* CAMF_LCS: cfMatrix_LCS [num_conditions x num_context_factors] (CAMF.java:46, CAMF_LCS.java:38-40) */
   double* c_mcs;  /* CAMF_MCS: cVector_MCS [num_conditions] (CAMF.java:47, CAMF_MCS.java:47-48) */
+  double* Y;      /* SVD++: implicit-feedback item factors [num_items x F] (SVDPlusPlus.java:37, 48-49) */
 } cars_model_arrays;
 
 /* Replaces the set-up a Java buildModel() does implicitly by holding trainMatrix/rateDao: copies the

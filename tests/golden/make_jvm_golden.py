@@ -40,6 +40,7 @@ SPECS = [
     dict(name="camf_cuci_f12", model="camf_cuci", users=35, items=30, dims=[5, 4, 3], nnz=800, F=12, iters=4, seed=17, order="shuffled"),
     dict(name="camf_ics_f9", model="camf_ics", users=35, items=25, dims=[4, 3, 3], nnz=800, F=9, iters=4, seed=19, order="shuffled",
          lrate=0.005),
+    dict(name="svdpp_f10", model="svdpp", users=40, items=25, dims=None, nnz=600, F=10, iters=4, seed=23, order="user_sorted"),
     dict(name="camf_lcs_f8", model="camf_lcs", users=35, items=25, dims=[4, 3, 3], nnz=800, F=8, iters=4, seed=21, order="shuffled",
          lrate=0.0002),  # U(0, 1) condition vectors of 10 factors: similarities of ~2.5 per dimension, predictions of ~30
     dict(name="camf_mcs_f8", model="camf_mcs", users=35, items=25, dims=[3, 4, 2], nnz=800, F=8, iters=4, seed=22, order="user_sorted",

@@ -43,7 +43,8 @@ def oracle_run(oracle, model, ts, arrs, F, iters, lrate=0.02, bold_driver=True, 
 
 # ---- 1. live ---------------------------------------------------------------------------------------------------------
 LIVE = [
-    ("pmf", None, "user_sorted", 5), ("biasedmf", None, "user_sorted", 6), ("camf_c", [3, 2, 2], "shuffled", 5),
+    ("pmf", None, "user_sorted", 5), ("biasedmf", None, "user_sorted", 6), ("svdpp", None, "user_sorted", 5),
+    ("camf_c", [3, 2, 2], "shuffled", 5),
     ("camf_ci", [3, 2, 2], "user_sorted", 9), ("camf_cu", [4, 3], "shuffled", 4), ("camf_cuci", [2, 2, 3], "user_sorted", 5),
     ("camf_ics", [3, 3, 2], "shuffled", 6), ("camf_lcs", [3, 3, 2], "shuffled", 6), ("camf_mcs", [3, 2, 3], "user_sorted", 5),
 ]

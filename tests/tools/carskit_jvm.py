@@ -30,6 +30,7 @@ REFERENCE = "/root/reference"
 JARS = [os.path.join(REFERENCE, "jar", "CARSKit-v0.4.0.jar"), os.path.join(REFERENCE, "lib", "librec-v1.4-alpha.jar")]
 DEV = "carskit/alg/cars/adaptation/dependent/dev/"
 CLASS_OF = {capi.PMF: "carskit/alg/baseline/cf/PMF", capi.BIASEDMF: "carskit/alg/baseline/cf/BiasedMF",
+            capi.SVDPP: "carskit/alg/baseline/cf/SVDPlusPlus",
             capi.CAMF_C: DEV + "CAMF_C", capi.CAMF_CI: DEV + "CAMF_CI", capi.CAMF_CU: DEV + "CAMF_CU",
             capi.CAMF_CUCI: DEV + "CAMF_CUCI", capi.CAMF_ICS: "carskit/alg/cars/adaptation/dependent/sim/CAMF_ICS",
             capi.CAMF_LCS: "carskit/alg/cars/adaptation/dependent/sim/CAMF_LCS",
@@ -102,7 +103,7 @@ class ReferenceRun:
         self.jar = Jar(*JARS)
         self.jvm = jvm = MiniJVM(self.jar)
         self.cls = CLASS_OF[model]
-        has_ctx = model not in (capi.PMF, capi.BIASEDMF)
+        has_ctx = model not in (capi.PMF, capi.BIASEDMF, capi.SVDPP)
         # ---- trainMatrix / train ------------------------------------------------------------------------------
         if has_ctx:
             # rows = user-item pair ids in first-appearance order of the CRS stream (entries of one pair are adjacent)
@@ -172,6 +173,11 @@ class ReferenceRun:
             rec.f["ccMatrix_ICS"] = JObject("librec/data/SymmMatrix", dim=int(ts.num_conditions),
                                             data=HostTable(arrays["cc_sim"], lower_triangle=True))
             jvm.set_static("carskit/generic/ContextRecommender", "EmptyContextConditions", [int(x) for x in ts.empty_conditions])
+        if model == capi.SVDPP:  # SVDPlusPlus.java:45-52: Y, and userItemsCache = train.rowColumnsCache(): getColumns(u), ascending
+            rec.f["Y"] = dense_matrix(arrays["Y"])
+            items = [sorted(int(x) for x in ts.j[ts.u == uu]) for uu in range(ts.num_users)]
+            rec.f["userItemsCache"] = JObject("com/google/common/cache/LoadingCache", items=items)
+            jvm.natives[("com/google/common/cache/LoadingCache", "get")] = lambda vm, a: a[0].f["items"][a[1]]
         if model == capi.CAMF_LCS:  # CAMF_LCS.java:36-41: numF = `-f`, cfMatrix_LCS [numConditions x numF]
             rec.f["cfMatrix_LCS"] = dense_matrix(arrays["cf_lcs"])
             rec.f["numF"] = int(arrays["cf_lcs"].shape[1])
@@ -238,6 +244,8 @@ class ReferenceRun:
             for (r, c), v in f["ccMatrix_ICS"].f["data"].d.items():
                 cc[r, c] = cc[c, r] = v
             out["cc_sim"] = cc
+        if "Y" in self.shapes:
+            out["Y"] = np.array(f["Y"].f["data"], dtype=np.float64).reshape(self.shapes["Y"])
         if "cf_lcs" in self.shapes:
             out["cf_lcs"] = np.array(f["cfMatrix_LCS"].f["data"], dtype=np.float64).reshape(self.shapes["cf_lcs"])
         if "c_mcs" in self.shapes:
