@@ -60,6 +60,7 @@ struct cars_handle {
   int Dmax = 0;
   int32_t* d_ctx_tab = nullptr;
   int32_t* d_empty_cond = nullptr;  // CAMF_ICS
+  int32_t *d_ui_ptr = nullptr, *d_ui_items = nullptr;  // SVD++: userItemsCache in CSR form
   bool uploaded = false;
 
   // ratings in schedule order
@@ -344,6 +345,13 @@ static const void* pick_serial_m(int Fp) {
   return nullptr;
 }
 static const void* pick_serial(int model, int Fp) {
+  if (model == CARS_SVDPP) {
+    if (Fp <= 64) return (const void*)sgd_serial_svdpp_kernel<1>;
+    if (Fp <= 128) return (const void*)sgd_serial_svdpp_kernel<2>;
+    if (Fp <= 256) return (const void*)sgd_serial_svdpp_kernel<4>;
+    if (Fp <= 512) return (const void*)sgd_serial_svdpp_kernel<8>;
+    return nullptr;
+  }
   if (model == CARS_CAMF_LCS || model == CARS_CAMF_MCS) {
 #define CARS_SIM_PICK(K)                                               \
   if (Fp <= 64) return (const void*)sgd_serial_sim_kernel<1, K>;       \
@@ -385,7 +393,9 @@ static int validate(const cars_desc* d) {
   if (!d) return fail(nullptr, CARS_E_INVALID, "desc is NULL");
   if (d->abi_version != CARS_ABI_VERSION)
     return fail(nullptr, CARS_E_INVALID, "abi_version %d != %d", d->abi_version, CARS_ABI_VERSION);
-  if (d->model < CARS_PMF || d->model > CARS_CAMF_MCS) return fail(nullptr, CARS_E_INVALID, "unknown model %d", d->model);
+  if (d->model < CARS_PMF || d->model > CARS_SVDPP) return fail(nullptr, CARS_E_INVALID, "unknown model %d", d->model);
+  if (d->model == CARS_SVDPP && (d->mode == CARS_FAST || d->num_gpus > 1))
+    return fail(nullptr, CARS_E_UNSUPPORTED, "SVD++ is built for EXACT mode on one GPU (every rating rewrites Y of all the user's items: one chain)");
   if (d->model == CARS_CAMF_LCS && (d->num_context_factors <= 0 || d->num_context_factors > 4096))
     return fail(nullptr, CARS_E_INVALID, "CAMF_LCS needs num_context_factors in 1..4096 (the `-f` option, CAMF_LCS.java:38)");
   if (d->model == CARS_CAMF_MCS && d->num_context_dims <= 0)
@@ -515,7 +525,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   const bool fast = desc->mode == CARS_FAST;
   // the flagged and the FAST schedule validate the ids inside their own device pass over the ratings
   const bool fused_check = fast || (sched_req == CARS_SCHED_FLAGGED && desc->model != CARS_CAMF_C && desc->model != CARS_CAMF_ICS &&
-                                   desc->model != CARS_CAMF_LCS && desc->model != CARS_CAMF_MCS);
+                                   desc->model != CARS_CAMF_LCS && desc->model != CARS_CAMF_MCS && desc->model != CARS_SVDPP);
   for (int64_t n = 0; n < nnz && !fused_check; n++) {
     if ((unsigned)desc->u[n] >= (unsigned)desc->num_users || (unsigned)desc->j[n] >= (unsigned)desc->num_items ||
         (has_ctx && (unsigned)desc->ctx[n] >= (unsigned)desc->num_contexts)) {
@@ -528,7 +538,8 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   // ---- launch geometry (the dataflow schedule sizes its chunks from the number of resident groups) ------
   const int model = desc->model;
   h->fast = fast;
-  h->serial = !fast && (model == CARS_CAMF_C || model == CARS_CAMF_ICS || model == CARS_CAMF_LCS || model == CARS_CAMF_MCS);
+  h->serial = !fast && (model == CARS_CAMF_C || model == CARS_CAMF_ICS || model == CARS_CAMF_LCS || model == CARS_CAMF_MCS ||
+                        model == CARS_SVDPP);
   const int sched = sched_req;
   if (sched != CARS_SCHED_DATAFLOW && sched != CARS_SCHED_WAVEFRONT && sched != CARS_SCHED_FLAGGED) {
     fail(h, CARS_E_INVALID, "unknown schedule %d", sched);
@@ -539,7 +550,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   int groups_per_cta = 1;
   if (h->serial) {
     h->grid = 1; h->block = 32;
-    h->smem = (size_t)(Fp + 2) * 8;
+    h->smem = (size_t)((model == CARS_SVDPP ? 2 : 1) * Fp + 2) * 8;  // SVD++: + Q[j] for the lanes' Y[k].Q[j] chains
   } else {
     // EXACT default 8; rows of at most 32 factors with more than 4 context dimensions keep 8 lanes per rating (shape 11): the lanes of a
     // group fetch one condition cell each, dimensions beyond the group's lanes take the slow path
@@ -552,7 +563,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
                       : h->dataflow ? pick_dataflow_plan(model, Fp)
                       : h->flagged ? pick_flagged_plan(model, Fp, F, shape) : pick_plan(model, Fp);
     if (h->flagged && h->tune.get_ll("tagged", kTaggedDefault) != 0 && !h->tune.is("levels", "host")) {
-      static const int kModelOf[] = {M_PMF, M_BIASEDMF, M_CAMF_C, M_CAMF_CI, M_CAMF_CU, -1, M_CAMF_CUCI, M_CAMF_ICS, M_CAMF_LCS, M_CAMF_MCS};
+      static const int kModelOf[] = {M_PMF, M_BIASEDMF, M_CAMF_C, M_CAMF_CI, M_CAMF_CU, -1, M_CAMF_CUCI, M_CAMF_ICS, M_CAMF_LCS, M_CAMF_MCS, M_SVDPP};
       h->tl = tagged_layout(kModelOf[model], F, has_ctx ? desc->num_conditions : 0);
       LaunchPlan tp = pick_tagged_plan(model, h->tl.p_lines(), h->tl.q_lines(), (int)h->tune.get_ll("tagged_ctas", 3));
       if (tp.fn) {
@@ -788,8 +799,34 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   m.ctx_tab = h->d_ctx_tab;
   CUDA_TRY_H(dev_alloc(&m.P, U * Fp));
   CUDA_TRY_H(dev_alloc(&m.Q, I * Fp));
-  if (model == CARS_BIASEDMF || model == CARS_CAMF_C || model == CARS_CAMF_CI) CUDA_TRY_H(dev_alloc(&m.user_bias, U));
-  if (model == CARS_BIASEDMF || model == CARS_CAMF_C || model == CARS_CAMF_CU) CUDA_TRY_H(dev_alloc(&m.item_bias, I));
+  if (model == CARS_BIASEDMF || model == CARS_CAMF_C || model == CARS_CAMF_CI || model == CARS_SVDPP) CUDA_TRY_H(dev_alloc(&m.user_bias, U));
+  if (model == CARS_BIASEDMF || model == CARS_CAMF_C || model == CARS_CAMF_CU || model == CARS_SVDPP) CUDA_TRY_H(dev_alloc(&m.item_bias, I));
+  if (model == CARS_SVDPP) {
+    // userItemsCache = train.rowColumnsCache() (SVDPlusPlus.java:51): every user's items ascending, whatever the order of the
+    // rating stream -- built here on the host (the one-warp chain is for small data) and kept on the device in CSR form
+    CUDA_TRY_H(dev_alloc(&m.Y, I * Fp));
+    CUDA_TRY_H(cudaMemsetAsync(m.Y, 0, I * Fp * sizeof(double), h->stream));
+    std::vector<int32_t> uptr(U + 1, 0), uitems((size_t)nnz);
+    for (int64_t n = 0; n < nnz; n++) {
+      if ((uint32_t)desc->u[n] >= (uint32_t)U || (uint32_t)desc->j[n] >= (uint32_t)I) {
+        fail(h, CARS_E_INVALID, "rating %lld has an id out of range (u=%d j=%d ctx=-1)", (long long)n, desc->u[n], desc->j[n]);
+        return bail(CARS_E_INVALID);
+      }
+      uptr[desc->u[n] + 1]++;
+    }
+    for (size_t k = 0; k < U; k++) uptr[k + 1] += uptr[k];
+    {
+      std::vector<int32_t> fill(uptr.begin(), uptr.end() - 1);
+      for (int64_t n = 0; n < nnz; n++) uitems[fill[desc->u[n]]++] = desc->j[n];
+      for (size_t k = 0; k < U; k++) std::sort(uitems.begin() + uptr[k], uitems.begin() + uptr[k + 1]);
+    }
+    CUDA_TRY_H(dev_alloc(&h->d_ui_ptr, U + 1));
+    CUDA_TRY_H(dev_alloc(&h->d_ui_items, (size_t)nnz));
+    CUDA_TRY_H(cudaMemcpyAsync(h->d_ui_ptr, uptr.data(), (U + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    if (nnz) CUDA_TRY_H(cudaMemcpyAsync(h->d_ui_items, uitems.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY_H(cudaStreamSynchronize(h->stream));  // the host vectors die here
+    m.ui_ptr = h->d_ui_ptr; m.ui_items = h->d_ui_items;
+  }
   if (model == CARS_CAMF_C) CUDA_TRY_H(dev_alloc(&m.cond_bias, C));
   if (model == CARS_CAMF_CI || model == CARS_CAMF_CUCI) CUDA_TRY_H(dev_alloc(&m.ic_bias, I * C));
   if (model == CARS_CAMF_CU || model == CARS_CAMF_CUCI) CUDA_TRY_H(dev_alloc(&m.uc_bias, U * C));
@@ -910,7 +947,7 @@ static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device, 
   const Item need[] = {{m.P, a->P, "P"}, {m.Q, a->Q, "Q"}, {m.user_bias, a->user_bias, "user_bias"},
                        {m.item_bias, a->item_bias, "item_bias"}, {m.cond_bias, a->cond_bias, "cond_bias"},
                        {m.ic_bias, a->ic_bias, "ic_bias"}, {m.uc_bias, a->uc_bias, "uc_bias"}, {m.cc_sim, a->cc_sim, "cc_sim"},
-                       {m.cf_lcs, a->cf_lcs, "cf_lcs"}, {m.c_mcs, a->c_mcs, "c_mcs"}};
+                       {m.cf_lcs, a->cf_lcs, "cf_lcs"}, {m.c_mcs, a->c_mcs, "c_mcs"}, {m.Y, a->Y, "Y"}};
   for (const Item& it : need) {
     const bool item_side = it.dev == m.Q || it.dev == m.item_bias || it.dev == m.cond_bias || it.dev == m.ic_bias;
     if (it.dev && !it.host && !(skip_item_side && item_side))
@@ -922,6 +959,7 @@ static int transfer(cars_handle* h, const cars_model_arrays* a, bool to_device, 
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // the staged copies run on the copier's own streams
   if ((rc = copy_rows(h, to_device, m.P, a->P, U, m.F, m.Fp, &segs))) return rc;
   if (!skip_item_side && (rc = copy_rows(h, to_device, m.Q, a->Q, I, m.F, m.Fp, &segs))) return rc;
+  if (m.Y && (rc = copy_rows(h, to_device, m.Y, a->Y, I, m.F, m.Fp, &segs))) return rc;
   if (m.user_bias && (rc = copy_vec(h, to_device, m.user_bias, a->user_bias, U, &segs))) return rc;
   if (!skip_item_side && m.item_bias && (rc = copy_vec(h, to_device, m.item_bias, a->item_bias, I, &segs))) return rc;
   if (!skip_item_side && m.cond_bias && (rc = copy_vec(h, to_device, m.cond_bias, a->cond_bias, C, &segs))) return rc;
@@ -1238,6 +1276,7 @@ static int predict_device(cars_handle* h, int64_t n, const int32_t* u, const int
     case CARS_CAMF_CUCI: CARS_PREDICT(M_CAMF_CUCI); break;
     case CARS_CAMF_ICS: CARS_PREDICT(M_CAMF_ICS); break;
     case CARS_CAMF_LCS: CARS_PREDICT(M_CAMF_LCS); break;
+    case CARS_SVDPP: CARS_PREDICT(M_SVDPP); break;
     case CARS_CAMF_MCS: CARS_PREDICT(M_CAMF_MCS); break;
     default: return fail(h, CARS_E_UNSUPPORTED, "predict: model %d", h->d.model);
   }
@@ -1404,6 +1443,7 @@ extern "C" int cars_rank_topn(cars_handle* h, int64_t num_queries, const int32_t
       case CARS_CAMF_CUCI: RK(launch_rank_score<M_CAMF_CUCI>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
       case CARS_CAMF_ICS: RK(launch_rank_score<M_CAMF_ICS>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
       case CARS_CAMF_LCS: RK(launch_rank_score<M_CAMF_LCS>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
+      case CARS_SVDPP: RK(launch_rank_score<M_SVDPP>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
       case CARS_CAMF_MCS: RK(launch_rank_score<M_CAMF_MCS>(h, q0, nq, d_qu, d_qc, num_cand, d_cand, bin_thold, d_keys)); break;
       default: rc = fail(h, CARS_E_UNSUPPORTED, "rank: model %d", h->d.model); break;
     }
@@ -1466,7 +1506,7 @@ extern "C" void cars_destroy(cars_handle* h) {
   h->mem.free(h->d_item_old); h->mem.free(h->d_item_scale); h->mem.free(h->d_cond_scale);
   h->mem.free(h->d_hot_slot); h->mem.free(h->d_hot_items);
   h->mem.free(h->tm.Pt); h->mem.free(h->tm.Qt);
-  h->mem.free(h->m.cc_sim); h->mem.free(h->m.cf_lcs); h->mem.free(h->m.c_mcs); h->mem.free(h->d_empty_cond);
+  h->mem.free(h->m.cc_sim); h->mem.free(h->m.cf_lcs); h->mem.free(h->m.c_mcs); h->mem.free(h->m.Y); h->mem.free(h->d_ui_ptr); h->mem.free(h->d_ui_items); h->mem.free(h->d_empty_cond);
   h->mem.free(h->d_barrier); h->mem.free(h->d_partial); h->mem.free(h->d_loss);
   if (h->stream) cudaStreamSynchronize(h->stream);  // the pool's frees are stream-ordered
   if (h->h_loss) cudaFreeHost(h->h_loss);

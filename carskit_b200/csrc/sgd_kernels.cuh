@@ -18,7 +18,7 @@
 
 namespace cars {
 
-enum : int { M_PMF = 0, M_BIASEDMF = 1, M_CAMF_C = 2, M_CAMF_CI = 3, M_CAMF_CU = 4, M_CAMF_CUCI = 5, M_CAMF_ICS = 6, M_CAMF_LCS = 7, M_CAMF_MCS = 8 };
+enum : int { M_PMF = 0, M_BIASEDMF = 1, M_CAMF_C = 2, M_CAMF_CI = 3, M_CAMF_CU = 4, M_CAMF_CUCI = 5, M_CAMF_ICS = 6, M_CAMF_LCS = 7, M_CAMF_MCS = 8, M_SVDPP = 9 };
 
 // Device-resident state shared by all kernels.  Plain pointers into the handle's allocations.
 struct DeviceModel {
@@ -36,6 +36,9 @@ struct DeviceModel {
   double* c_mcs;              // CAMF_MCS: [C] condition positions (cVector_MCS)
   double mcs_upbound, mcs_lowbound;  // CAMF_MCS.java:44-45: 1 / sqrt(numContextDims), 1 / 10^100
   int32_t numF;               // CAMF_LCS: `-f`
+  double* Y;                  // SVD++: [num_items x Fp] implicit-feedback item factors
+  const int32_t* ui_ptr;      // SVD++: [num_users + 1] userItemsCache in CSR form: the items user u rated, ascending
+  const int32_t* ui_items;    //        [nnz]
   int32_t F, Fp, C, Dmax;
   double global_mean;
   double reg_u, reg_i, reg_b, reg_c;
@@ -643,6 +646,108 @@ __global__ void __launch_bounds__(32, 1)
   if (lane == 0) block_partial[0] = acc;
 }
 
+// K1s-SVD++: SVDPlusPlus.buildModel (baseline/cf/SVDPlusPlus.java:55-124), one warp in reference order.  Every rating of
+// user u reads and rewrites Y[k] for ALL items k the user rated, so two ratings conflict whenever their users share any
+// item: the dependency DAG is ~1 rating wide (profiles/r2/svdpp_dag_width.txt) and EXACT mode is a single chain.  Inside a
+// rating the work is parallel: lanes own factors (16-byte chunks) for the row updates and the sum over Y, and own ITEMS for
+// the |items(u)| dot products Y[k].Q[j] of the prediction, which are then added in item order.
+template <int V>
+__global__ void __launch_bounds__(32, 1)
+    sgd_serial_svdpp_kernel(DeviceModel m, RatingStream s, int64_t nnz, double lr, double* block_partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* prod = reinterpret_cast<double*>(smem_raw);  // [Fp + 2] products for the in-order dot
+  double* qs = prod + m.Fp + 2;                        // [Fp] Q[j] for the lanes' Y[k].Q[j] chains
+  const int lane = threadIdx.x;
+  const int Fp = m.Fp, F = m.F;
+  double acc = 0.0;
+  for (int64_t n = 0; n < nnz; n++) {
+    const int u = __ldg(s.u + n), j = __ldg(s.j + n);
+    const double r = __ldg(s.r + n);
+    const int ia = __ldg(m.ui_ptr + u), ib = __ldg(m.ui_ptr + u + 1);
+    const double w = __dsqrt_rn((double)(ib - ia));
+    double* prow = m.P + (int64_t)u * Fp;
+    double* qrow = m.Q + (int64_t)j * Fp;
+    double2 p[V], q[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const int c = lane + v * 32;
+      if (2 * c < Fp) {
+        p[v] = *reinterpret_cast<const double2*>(prow + 2 * c);
+        q[v] = *reinterpret_cast<const double2*>(qrow + 2 * c);
+        *reinterpret_cast<double2*>(prod + 2 * c) = make_double2(__dmul_rn(p[v].x, q[v].x), __dmul_rn(p[v].y, q[v].y));
+        *reinterpret_cast<double2*>(qs + 2 * c) = q[v];
+      }
+    }
+    __syncwarp();
+    double dot = 0.0;
+    for (int f = 0; f < F; f++) dot = __dadd_rn(dot, prod[f]);
+    const double bu = m.user_bias[u], bj = m.item_bias[j];
+    double pred = __dadd_rn(__dadd_rn(__dadd_rn(m.global_mean, bu), bj), dot);
+    for (int base = ia; base < ib; base += 32) {  // 32 items at a time: lane = item, then added in item order
+      double t = 0.0;
+      if (base + lane < ib) {
+        const double* yrow = m.Y + (int64_t)__ldg(m.ui_items + base + lane) * Fp;
+        double yq = 0.0;
+        for (int f = 0; f < F; f++) yq = __dadd_rn(yq, __dmul_rn(yrow[f], qs[f]));
+        t = __ddiv_rn(yq, w);
+      }
+      const int cnt = ib - base < 32 ? ib - base : 32;
+      for (int i = 0; i < cnt; i++)
+        pred = __dadd_rn(pred, __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(t), i), __shfl_sync(0xffffffffu, __double2loint(t), i)));
+    }
+    const double e = __dsub_rn(r, pred);
+    double lane_loss = 0.0;
+    if (lane == 0) {
+      lane_loss = __dmul_rn(e, e);
+      m.user_bias[u] = __dadd_rn(bu, __dmul_rn(lr, __dsub_rn(e, __dmul_rn(m.reg_b, bu))));
+      lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_b, bu), bu));
+      m.item_bias[j] = __dadd_rn(bj, __dmul_rn(lr, __dsub_rn(e, __dmul_rn(m.reg_b, bj))));
+      lane_loss = __dadd_rn(lane_loss, __dmul_rn(__dmul_rn(m.reg_b, bj), bj));
+    }
+    __syncwarp();  // every lane has read Y for the prediction before anyone rewrites it
+    double sp = 0.0, sq = 0.0, sy = 0.0;
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const int c = lane + v * 32;
+      if (2 * c < Fp) {
+        double2 sum = make_double2(0.0, 0.0);  // sum_ys[f], items in order (SVDPlusPlus.java:85-92)
+        for (int i = ia; i < ib; i++) {
+          const double2 y = *reinterpret_cast<const double2*>(m.Y + (int64_t)__ldg(m.ui_items + i) * Fp + 2 * c);
+          sum.x = __dadd_rn(sum.x, y.x);
+          sum.y = __dadd_rn(sum.y, y.y);
+        }
+        if (w > 0.0) { sum.x = __ddiv_rn(sum.x, w); sum.y = __ddiv_rn(sum.y, w); }
+        const double2 po = p[v], qo = q[v];
+        double2 pn, qn;
+        pn.x = __dadd_rn(po.x, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, qo.x), __dmul_rn(m.reg_u, po.x))));
+        pn.y = __dadd_rn(po.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, qo.y), __dmul_rn(m.reg_u, po.y))));
+        qn.x = __dadd_rn(qo.x, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, __dadd_rn(po.x, sum.x)), __dmul_rn(m.reg_i, qo.x))));
+        qn.y = __dadd_rn(qo.y, __dmul_rn(lr, __dsub_rn(__dmul_rn(e, __dadd_rn(po.y, sum.y)), __dmul_rn(m.reg_i, qo.y))));
+        *reinterpret_cast<double2*>(prow + 2 * c) = pn;
+        *reinterpret_cast<double2*>(qrow + 2 * c) = qn;
+        sp = fma(po.x, po.x, sp); sq = fma(qo.x, qo.x, sq);
+        sp = fma(po.y, po.y, sp); sq = fma(qo.y, qo.y, sq);
+        const double gx = __ddiv_rn(__dmul_rn(e, qo.x), w), gy = __ddiv_rn(__dmul_rn(e, qo.y), w);  // euj * qjf / w, the OLD qjf
+        for (int i = ia; i < ib; i++) {
+          double2* yp = reinterpret_cast<double2*>(m.Y + (int64_t)__ldg(m.ui_items + i) * Fp + 2 * c);
+          const double2 y = *yp;
+          double2 yn;
+          yn.x = __dadd_rn(y.x, __dmul_rn(lr, __dsub_rn(gx, __dmul_rn(m.reg_u, y.x))));
+          yn.y = __dadd_rn(y.y, __dmul_rn(lr, __dsub_rn(gy, __dmul_rn(m.reg_u, y.y))));
+          *yp = yn;
+          sy = fma(y.x, y.x, sy);
+          sy = fma(y.y, y.y, sy);
+        }
+      }
+    }
+    acc = __dadd_rn(acc, __dadd_rn(lane_loss, fma(m.reg_u, __dadd_rn(sp, sy), __dmul_rn(m.reg_i, sq))));
+    __syncwarp();
+    __threadfence_block();
+  }
+  acc = warp_sum_f64(acc);
+  if (lane == 0) block_partial[0] = acc;
+}
+
 // K1s-LCS / K1s-MCS: CAMF_LCS.buildModel (sim/CAMF_LCS.java:66-146) and CAMF_MCS.buildModel (sim/CAMF_MCS.java:71-167), one
 // warp in reference order -- like CAMF_ICS every rating reads and rewrites cells all ratings share (the condition vectors /
 // positions of the dimensions' "na" conditions), so EXACT mode is a single chain.  The similarity part is warp-uniform
@@ -1069,6 +1174,18 @@ __device__ __forceinline__ double predict_from_dot(const DeviceModel& m, int u, 
   if (MODEL == M_CAMF_CI) pred = __dadd_rn(__dadd_rn(m.global_mean, m.user_bias[u]), dot);
   if (MODEL == M_CAMF_CU) pred = __dadd_rn(__dadd_rn(m.global_mean, m.item_bias[j]), dot);
   if (MODEL == M_CAMF_CUCI) pred = __dadd_rn(m.global_mean, dot);  // CAMF_CUCI.java:69
+  if (MODEL == M_SVDPP) {  // SVDPlusPlus.java:139-147: BiasedMF's prediction + sum_k rowMult(Y, k, Q, j) / sqrt(|items(u)|)
+    pred = __dadd_rn(__dadd_rn(__dadd_rn(m.global_mean, m.user_bias[u]), m.item_bias[j]), dot);
+    const int a = m.ui_ptr[u], b = m.ui_ptr[u + 1];
+    const double w = __dsqrt_rn((double)(b - a));
+    const double* qrow = m.Q + (int64_t)j * m.Fp;
+    for (int i = a; i < b; i++) {
+      const double* yrow = m.Y + (int64_t)m.ui_items[i] * m.Fp;
+      double yq = 0.0;
+      for (int f = 0; f < m.F; f++) yq = __dadd_rn(yq, __dmul_rn(yrow[f], qrow[f]));
+      pred = __dadd_rn(pred, __ddiv_rn(yq, w));
+    }
+  }
   if (MODEL == M_CAMF_LCS) {  // CAMF_LCS.java:44-62: pred = pred * rowMult(cfMatrix_LCS, cond, cfMatrix_LCS, empty)
     pred = dot;
     for (int d = 0; d < m.Dmax; d++) {

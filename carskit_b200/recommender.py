@@ -458,6 +458,13 @@ class BiasedMF(IterativeRecommender):
     MODEL, algoName = capi.BIASEDMF, "BiasedMF"
 
 
+class SVDPlusPlus(IterativeRecommender):
+    """carskit.alg.baseline.cf.SVDPlusPlus (SVDPlusPlus.java): BiasedMF plus the implicit-feedback factors Y of every item the
+    user rated.  Every rating rewrites Y[k] for all of the user's items, so the engine runs it as ONE chain (one warp):
+    bit-identical to the reference, meant for the small data sets the dependency structure allows."""
+    MODEL, algoName = capi.SVDPP, "SVD++"
+
+
 class CAMF_C(IterativeRecommender):
     MODEL, algoName = capi.CAMF_C, "CAMF_C"
 
@@ -678,7 +685,7 @@ def runCrossValidation(rateMatrix: TrainingSet, name: str, conf: Optional[Dict[s
 def getRecommender(name: str):
     """The `switch` of CARSKit.getRecommender (src/carskit/main/CARSKit.java:429-705) for this path."""
     table = {"pmf": PMF, "biasedmf": BiasedMF, "camf_c": CAMF_C, "camf_ci": CAMF_CI, "camf_cu": CAMF_CU, "fm": FM,
-             "camf_cuci": CAMF_CUCI, "camf_ics": CAMF_ICS, "camf_lcs": CAMF_LCS, "camf_mcs": CAMF_MCS}
+             "camf_cuci": CAMF_CUCI, "camf_ics": CAMF_ICS, "camf_lcs": CAMF_LCS, "camf_mcs": CAMF_MCS, "svdpp": SVDPlusPlus, "svd++": SVDPlusPlus}
     try:
         return table[name.lower()]
     except KeyError:

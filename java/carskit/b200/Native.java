@@ -15,7 +15,7 @@ public final class Native {
     }
 
     // enum cars_model
-    public static final int PMF = 0, BIASEDMF = 1, CAMF_C = 2, CAMF_CI = 3, CAMF_CU = 4, FM = 5, CAMF_CUCI = 6, CAMF_ICS = 7, CAMF_LCS = 8, CAMF_MCS = 9;
+    public static final int PMF = 0, BIASEDMF = 1, CAMF_C = 2, CAMF_CI = 3, CAMF_CU = 4, FM = 5, CAMF_CUCI = 6, CAMF_ICS = 7, CAMF_LCS = 8, CAMF_MCS = 9, SVDPP = 10;
     // enum cars_mode: EXACT is serial-equivalent (P, Q, biases bit-identical to the Java loop); FAST is hogwild
     public static final int EXACT = 0, FAST = 1;
     // enum cars_combine (multi-GPU item-block combine)
@@ -45,7 +45,7 @@ public final class Native {
 
     /**
      * cars_upload: flat row-major arrays as initModel() made them; null where the model has no such member. `ccSim` is the
-     * similarity model's own array: ccMatrix_ICS [C x C], cfMatrix_LCS [C x numF] or cVector_MCS [C].
+     * model's own extra array: ccMatrix_ICS [C x C], cfMatrix_LCS [C x numF], cVector_MCS [C] or SVD++'s Y [numItems x F].
      */
     public static native void upload(long h, double[] P, double[] Q, double[] userBias, double[] itemBias,
                                      double[] condBias, double[] icBias, double[] ucBias, double[] ccSim);

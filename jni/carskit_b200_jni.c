@@ -111,8 +111,8 @@ static void transfer(JNIEnv* env, jlong handle, int to_device, jdoubleArray P, j
   cars_model_arrays a;
   a.P = (double*)p[0].p; a.Q = (double*)p[1].p; a.user_bias = (double*)p[2].p; a.item_bias = (double*)p[3].p;
   a.cond_bias = (double*)p[4].p; a.ic_bias = (double*)p[5].p; a.uc_bias = (double*)p[6].p;
-  /* the similarity model's own array: the engine reads the member its model has (ccMatrix_ICS / cfMatrix_LCS / cVector_MCS) */
-  a.cc_sim = a.cf_lcs = a.c_mcs = (double*)p[7].p;
+  /* the similarity model's own array: the engine reads the member its model has (ccMatrix_ICS / cfMatrix_LCS / cVector_MCS / SVD++'s Y) */
+  a.cc_sim = a.cf_lcs = a.c_mcs = a.Y = (double*)p[7].p;
   const int rc = to_device ? cars_upload(h, &a) : cars_download(h, &a);
   for (int k = 7; k >= 0; k--) unpin(env, p[k], to_device ? JNI_ABORT : 0);  /* download: copy back / commit */
   if (rc != CARS_OK) throw_runtime(env, cars_last_error(h));

@@ -511,3 +511,28 @@ def test_camf_lcs_mcs_bit_identical(oracle, cars_lib, name, F, order, numF):
     assert np.array_equal(predb, oracle.predict(desc, ref, test["u"], test["j"], test["ctx"], bound=True, min_rate=1.0, max_rate=5.0))
     with pytest.raises(capi.CarsError):
         capi.Engine(capi.make_desc(ts, model, F, mode=capi.FAST, **REGS, **kw), keepalive=ts)
+
+
+@pytest.mark.parametrize("F,order", [(10, "user_sorted"), (7, "shuffled"), (64, "user_sorted"), (130, "shuffled")])
+def test_svdpp_bit_identical(oracle, cars_lib, F, order):
+    """SVD++ (baseline/cf/SVDPlusPlus.java) on the one-warp serial kernel: P, Q, both biases and Y bit-identical to the oracle
+    (itself bit-identical to the executed bytecode) -- a user's items are taken ascending (train.getColumns(u)) whatever the
+    order of the rating stream; users with 1 .. 60 items, so the 32-items-at-a-time prediction loop takes both paths."""
+    ts, test = synth.make_training_set(60, 90, None, 2400, seed=F, order=order, holdout=0.1)
+    test["ctx"] = None
+    desc = capi.make_desc(ts, capi.SVDPP, F, **REGS)
+    ref = init_arrays(oracle, capi.SVDPP, ts, F, 3)
+    got = {k: v.copy() for k, v in ref.items()}
+    lr = capi.f32(0.01)
+    with capi.Engine(desc, keepalive=ts) as eng:
+        eng.upload(got)
+        for _ in range(3):
+            lg, lo = eng.epoch(lr), oracle.epoch(desc, ref, lr)
+            np.testing.assert_allclose(lg, lo, rtol=LOSS_RTOL)
+        pred = eng.predict(test["u"], test["j"], None, bound=True, min_rate=1.0, max_rate=5.0)
+        eng.download(got)
+    assert_bit_identical(ref, got)
+    assert np.bincount(ts.u, minlength=60).max() > 32
+    assert np.array_equal(pred, oracle.predict(desc, ref, test["u"], test["j"], None, bound=True, min_rate=1.0, max_rate=5.0))
+    with pytest.raises(capi.CarsError):
+        capi.Engine(capi.make_desc(ts, capi.SVDPP, F, mode=capi.FAST, **REGS), keepalive=ts)

@@ -123,6 +123,7 @@ def test_every_reference_member_the_java_sources_use_exists():
                             ("carskit/alg/cars/adaptation/dependent/CAMF", "ccMatrix_ICS", "Llibrec/data/SymmMatrix;"),
                             ("carskit/alg/cars/adaptation/dependent/CAMF", "cfMatrix_LCS", "Llibrec/data/DenseMatrix;"),
                             ("carskit/alg/cars/adaptation/dependent/CAMF", "cVector_MCS", "Llibrec/data/DenseVector;"),
+                            ("carskit/alg/baseline/cf/SVDPlusPlus", "Y", "Llibrec/data/DenseMatrix;"),
                             ("carskit/generic/ContextRecommender", "EmptyContextConditions", "Ljava/util/ArrayList;"),
                             ("carskit/generic/Recommender", "train", "Llibrec/data/SparseMatrix;"),
                             ("carskit/generic/Recommender", "trainMatrix", None), ("carskit/generic/Recommender", "rateDao", None),
