@@ -34,4 +34,16 @@ struct DevMem {
   }
 };
 
+// Compute capability and SM count by cudaDeviceGetAttribute (microseconds).  cudaGetDeviceProperties fills ~80 fields through
+// the driver and was measured at 3-88 ms per call on the B200 boxes (sched_trace) -- the largest jitter of cars_create.
+struct DeviceFacts {
+  int major = 0, minor = 0, sm_count = 0;
+};
+inline cudaError_t device_facts(int device, DeviceFacts* out) {
+  cudaError_t e = cudaDeviceGetAttribute(&out->major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&out->minor, cudaDevAttrComputeCapabilityMinor, device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&out->sm_count, cudaDevAttrMultiProcessorCount, device);
+  return e;
+}
+
 }  // namespace cars

@@ -434,6 +434,12 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   if (rc) return rc;
   if (desc->num_gpus > 1) return multi_create(desc, out);
 
+  const bool create_trace = desc->tuning && strstr(desc->tuning, "sched_trace=1") != nullptr;
+  auto clap = [&](const char* what) {
+    if (create_trace)
+      fprintf(stderr, "[cars create] +%8.2f ms  %s\n",
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_create).count(), what);
+  };
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)
@@ -441,8 +447,9 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
                 ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
   if (desc->device < 0 || desc->device >= ndev)
     return fail(nullptr, CARS_E_INVALID, "device %d out of range (have %d)", desc->device, ndev);
-  cudaDeviceProp prop;
-  CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, desc->device));
+  DeviceFacts prop;
+  CUDA_TRY(nullptr, device_facts(desc->device, &prop));
+  clap("cudaGetDeviceCount + device attributes");
   if (prop.major != 10)
     return fail(nullptr, CARS_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
                 desc->device, prop.major, prop.minor);
@@ -467,7 +474,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   h->d = *desc;
   h->tune = Tuning(desc->tuning);
   h->device = desc->device;
-  h->sm_count = prop.multiProcessorCount;
+  h->sm_count = prop.sm_count;
   CUDA_TRY_H(cudaSetDevice(h->device));
   if (desc->stream) {
     h->stream = (cudaStream_t)desc->stream;
@@ -479,8 +486,10 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
   CUDA_TRY_H(cudaEventCreate(&h->ev_end));
   h->mem.stream = h->stream;
   h->mem.pooled = h->tune.get_ll("pool", 1) != 0;
+  clap("stream + events");
   if (h->mem.pooled) CUDA_TRY_H(pool_setup(h->device));
   CUDA_TRY_H(h->copier.init(h->device, (int)h->tune.get_ll("copy_threads", 0)));
+  clap("pool_setup + copier.init");
 
   const int F = desc->num_factors;
   const int Fp = (F + 1) & ~1;
@@ -518,6 +527,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     h->st.h2d_bytes += (int64_t)ctx_tab.size() * 4;
   }
   h->Dmax = Dmax;
+  clap("context table");
 
   // ---- range checks on the rating arrays -------------------------------------------------------------
   const int64_t nnz = desc->nnz;
@@ -603,6 +613,7 @@ extern "C" int cars_create(const cars_desc* desc, cars_handle** out) {
     }
   }
 
+  clap("launch plan (cudaFuncSetAttribute + occupancy)");
   // ---- schedule ----------------------------------------------------------------------------------------
   auto t0 = std::chrono::steady_clock::now();
   h->nnz = nnz;

@@ -3,6 +3,7 @@
 #include "../../include/carskit_b200.h"
 #include "fm_kernels.cuh"
 #include "fm_setup.cuh"
+#include "dev_mem.cuh"
 #include "staged_copy.cuh"
 #include "tuning.h"
 
@@ -180,15 +181,15 @@ extern "C" int cars_fm_create(const cars_desc* d, cars_fm_handle** out) {
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0) return fm_fail(nullptr, CARS_E_NO_DEVICE, "no CUDA device; this engine has no CPU path");
   if (d->device < 0 || d->device >= ndev) return fm_fail(nullptr, CARS_E_INVALID, "device %d out of range", d->device);
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess || prop.major != 10)
+  cars::DeviceFacts prop;
+  if (cars::device_facts(d->device, &prop) != cudaSuccess || prop.major != 10)
     return fm_fail(nullptr, CARS_E_NO_DEVICE, "device %d is not sm_100", d->device);
 
   cars_fm_handle* h = new (std::nothrow) cars_fm_handle();
   if (!h) return fm_fail(nullptr, CARS_E_OOM, "host allocation failed");
   auto bail = [&](int code) { g_fm_create_error = h->err; cars_fm_destroy(h); return code; };
   h->tune = cars::Tuning(d->tuning);
-  h->device = d->device; h->sm_count = prop.multiProcessorCount;
+  h->device = d->device; h->sm_count = prop.sm_count;
   h->U = d->num_users; h->I = d->num_items; h->C = d->num_conditions; h->p = h->U + h->I + h->C;
   h->k = d->num_factors; h->D = d->num_context_dims; h->N = d->nnz;
   h->Nglobal = d->global_nnz > 0 ? d->global_nnz : d->nnz;
