@@ -3,6 +3,7 @@ the CPU: hyper-parameters are Java floats widened to double (IterativeRecommende
 updateLRate (:145-229) take the same decisions as the oracle's restatement when fed the same loss sequence.  No
 engine is opened here (the constructor does not touch the GPU)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -76,3 +77,25 @@ def test_java_hashset_order_known_answer():
     big = list(range(70000, 70013))  # 13 > 12 entries: capacity 32; 70000 = 0x11170 -> (h ^ h >> 16) & 31
     out = recommender.java_hashset_order(big).tolist()
     assert sorted(out) == big and out == sorted(big, key=lambda v: ((v ^ (v >> 16)) & 31, big.index(v)))
+
+
+def test_recommender_registry_and_model_members():
+    """Every recommender name CARSKit.getRecommender would dispatch for this path maps to a class whose MODEL, member list and
+    member shapes agree with the C ABI's enum (include/carskit_b200.h) -- incl. the one-chain models (ICS / LCS / MCS / SVD++)."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "carskit_b200.h")).read()
+    enum = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(CARS_[A-Z_]+?)\s*=\s*(\d+)\s*[,/ ]", hdr.split("enum cars_model")[1].split("};")[0])}
+    want = {"pmf": "CARS_PMF", "biasedmf": "CARS_BIASEDMF", "svd++": "CARS_SVDPP", "camf_c": "CARS_CAMF_C", "camf_ci": "CARS_CAMF_CI",
+            "camf_cu": "CARS_CAMF_CU", "camf_cuci": "CARS_CAMF_CUCI", "camf_ics": "CARS_CAMF_ICS", "camf_lcs": "CARS_CAMF_LCS",
+            "camf_mcs": "CARS_CAMF_MCS", "fm": "CARS_FM"}
+    for name, sym in want.items():
+        cls = recommender.getRecommender(name)
+        assert cls.MODEL == enum[sym], (name, cls.MODEL, enum[sym])
+    shapes = capi.member_shapes(capi.CAMF_LCS, 7, 5, 9, 4, num_context_factors=3)
+    assert shapes == {"P": (7, 4), "Q": (5, 4), "cf_lcs": (9, 3)}
+    assert capi.member_shapes(capi.CAMF_MCS, 7, 5, 9, 4) == {"P": (7, 4), "Q": (5, 4), "c_mcs": (9,)}
+    assert capi.member_shapes(capi.SVDPP, 7, 5, 0, 4) == {"P": (7, 4), "Q": (5, 4), "user_bias": (7,), "item_bias": (5,), "Y": (5, 4)}
+    # the ctypes mirrors have one field per header member, in the header's order
+    fields = [n for n, _ in capi.CarsModelArrays._fields_]
+    hdr_fields = re.findall(r"double\*\s+(\w+);", hdr.split("typedef struct cars_model_arrays {")[1].split("} cars_model_arrays;")[0])
+    assert fields == hdr_fields
