@@ -755,6 +755,20 @@ __global__ void __launch_bounds__(32, 1)
 //   LCS: sim_d = cf[cond_d] . cf[na_d] (f ascending);  pred = dot * prod sim_d;  cf rows += lr * (e*dot*simc*other/sim - regC*own)
 //   MCS: dist = sqrt(sum diff_d^2), diff_d = pos[cond_d] - pos[na_d];  pred = dot * (1 - dist);  positions moved along diff,
 //        clamped to (lowbound, upbound); a zero dist becomes lowbound in the update loop AND stays so for the factor steps
+// DenseMatrix.rowMult(cfMatrix_LCS, a, cfMatrix_LCS, b) by one warp: the products are formed lane-parallel (lane = factor), the
+// sum runs f ascending through shuffles -- the same additions in the same order, without a chain of dependent loads
+__device__ __forceinline__ double lcs_row_mult(const double* c1, const double* c2, int numF, int lane) {
+  double sim = 0.0;
+  for (int f0 = 0; f0 < numF; f0 += 32) {
+    const int f = f0 + lane;
+    const double pr = f < numF ? __dmul_rn(c1[f], c2[f]) : 0.0;
+    const int cnt = numF - f0 < 32 ? numF - f0 : 32;
+    for (int i = 0; i < cnt; i++)
+      sim = __dadd_rn(sim, __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(pr), i), __shfl_sync(0xffffffffu, __double2loint(pr), i)));
+  }
+  return sim;
+}
+
 template <int V, int KIND /*1 = LCS, 2 = MCS*/>
 __global__ void __launch_bounds__(32, 1)
     sgd_serial_sim_kernel(DeviceModel m, RatingStream s, int64_t nnz, double lr, double* block_partial) {
@@ -790,10 +804,7 @@ __global__ void __launch_bounds__(32, 1)
       if (KIND == 1) {
         double sim = 1.0;
         if (cond != e2) {
-          const double* c1 = m.cf_lcs + (int64_t)cond * numF;
-          const double* c2 = m.cf_lcs + (int64_t)e2 * numF;
-          sim = 0.0;
-          for (int f = 0; f < numF; f++) sim = __dadd_rn(sim, __dmul_rn(c1[f], c2[f]));
+          sim = lcs_row_mult(m.cf_lcs + (int64_t)cond * numF, m.cf_lcs + (int64_t)e2 * numF, numF, lane);
           simc = __dmul_rn(simc, sim);
         }
         pred = __dmul_rn(pred, sim);
@@ -811,28 +822,36 @@ __global__ void __launch_bounds__(32, 1)
     }
     const double e = __dsub_rn(r, pred);
     if (lane == 0) lane_loss = __dadd_rn(lane_loss, __dmul_rn(e, e));
-    __syncwarp();  // every lane has read the shared cells before lane 0 rewrites them
-    if (lane == 0) {
+    __syncwarp();  // every lane has read the shared cells before they are rewritten
+    if (KIND == 1) {  // LCS: lane = factor of the two condition vectors (the factors' updates are independent of each other)
       for (int d = 0; d < Dmax; d++) {
         const int cond = __ldg(m.ctx_tab + (int64_t)ctx * Dmax + d);
         if (cond < 0) continue;
         const int e2 = __ldg(m.empty_cond + d);
         if (cond == e2) continue;
-        if (KIND == 1) {
-          double* c1 = m.cf_lcs + (int64_t)cond * numF;
-          double* c2 = m.cf_lcs + (int64_t)e2 * numF;
-          double sim = 0.0;  // the rows of one rating are distinct: still the value the prediction used
-          for (int f = 0; f < numF; f++) sim = __dadd_rn(sim, __dmul_rn(c1[f], c2[f]));
-          const double g = __dmul_rn(__dmul_rn(e, dot), simc);
-          for (int f = 0; f < numF; f++) {
-            const double c1f = c1[f], c2f = c2[f];
-            const double d1 = __dsub_rn(__ddiv_rn(__dmul_rn(g, c2f), sim), __dmul_rn(m.reg_c, c1f));
-            const double d2 = __dsub_rn(__ddiv_rn(__dmul_rn(g, c1f), sim), __dmul_rn(m.reg_c, c2f));
-            c1[f] = __dadd_rn(c1f, __dmul_rn(lr, d1));
-            c2[f] = __dadd_rn(c2f, __dmul_rn(lr, d2));
-            lane_loss = __dadd_rn(lane_loss, __dadd_rn(__dmul_rn(__dmul_rn(m.reg_c, c1f), c1f), __dmul_rn(__dmul_rn(m.reg_c, c2f), c2f)));
-          }
-        } else {
+        double* c1 = m.cf_lcs + (int64_t)cond * numF;
+        double* c2 = m.cf_lcs + (int64_t)e2 * numF;
+        // the rows of one rating are distinct: still the value the prediction used
+        const double sim = lcs_row_mult(c1, c2, numF, lane);
+        const double g = __dmul_rn(__dmul_rn(e, dot), simc);
+        for (int f = lane; f < numF; f += 32) {
+          const double c1f = c1[f], c2f = c2[f];
+          const double d1 = __dsub_rn(__ddiv_rn(__dmul_rn(g, c2f), sim), __dmul_rn(m.reg_c, c1f));
+          const double d2 = __dsub_rn(__ddiv_rn(__dmul_rn(g, c1f), sim), __dmul_rn(m.reg_c, c2f));
+          c1[f] = __dadd_rn(c1f, __dmul_rn(lr, d1));
+          c2[f] = __dadd_rn(c2f, __dmul_rn(lr, d2));
+          lane_loss = __dadd_rn(lane_loss, __dadd_rn(__dmul_rn(__dmul_rn(m.reg_c, c1f), c1f), __dmul_rn(__dmul_rn(m.reg_c, c2f), c2f)));
+        }
+        __syncwarp();
+      }
+    }
+    if (KIND == 2 && lane == 0) {
+      for (int d = 0; d < Dmax; d++) {
+        const int cond = __ldg(m.ctx_tab + (int64_t)ctx * Dmax + d);
+        if (cond < 0) continue;
+        const int e2 = __ldg(m.empty_cond + d);
+        if (cond == e2) continue;
+        {
           const double pos1 = m.c_mcs[cond], pos2 = m.c_mcs[e2];
           const double diff = __dsub_rn(pos1, pos2);  // the cells of one rating are distinct: the first loop's value
           if (dist == 0.0) dist = m.mcs_lowbound;
